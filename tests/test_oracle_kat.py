@@ -1,0 +1,151 @@
+"""Pins for the CPU oracle that do not need a GPU: glibc rand()/shuffle against the real
+libc of this image, canonical exp against libm, the SOGP recursion against the independent
+numpy restatement of matlab/sogp.m, and the known-answer vectors of SURVEY.md section 4."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+
+from sogp_numpy import SogpNumpy
+
+
+def test_rand_stream_matches_real_glibc(oracle_mod):
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(1)  # unseeded rand() == srand(1)
+    real = np.array([libc.rand() for _ in range(20000)], dtype=np.uint32)
+    assert np.array_equal(oracle_mod.rand_stream(0, 20000), real)
+    assert np.array_equal(oracle_mod.rand_stream(777, 100), real[777:877])
+    assert real[:4].tolist() == [1804289383, 846930886, 1681692777, 1714636915]
+
+
+def test_shuffle_kat_and_real_glibc(oracle_mod):
+    got = oracle_mod.shuffles(0, [1, 2, 5, 8])
+    assert got.tolist() == [0, 1, 0, 4, 3, 1, 0, 2, 7, 5, 0, 6, 1, 2, 4, 3]
+    # sparse_gp.hpp:42-56 run over the real libc rand()
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(1)
+    sizes = [3, 1, 40, 17, 2, 256]
+    want = []
+    for n in sizes:
+        ind = list(range(n))
+        for i in range(n - 1, 0, -1):
+            r = libc.rand() % i
+            ind[i], ind[r] = ind[r], ind[i]
+        want += ind
+    assert oracle_mod.shuffles(0, sizes).tolist() == want
+
+
+def test_exp_within_one_ulp_of_libm(oracle_mod):
+    rng = np.random.default_rng(0)
+    x = np.concatenate([-rng.uniform(0, 60, 200000), -rng.uniform(0, 1e-2, 200000), -rng.uniform(0, 1e-6, 50000),
+                        rng.uniform(0, 5, 50000), np.array([0.0, -0.0, -1e-300, -700.0, -744.0])])
+    got = oracle_mod.exp_array(x)
+    ref = np.array([math.exp(v) for v in x])  # libm (np.exp is numpy's own SIMD kernel)
+    ulp = np.abs(got.view(np.int64) - ref.view(np.int64))
+    assert ulp.max() <= 1
+    assert (ulp > 0).mean() < 0.06
+    assert oracle_mod.exp_array(np.array([0.0]))[0] == 1.0
+    assert oracle_mod.exp_array(np.array([-800.0]))[0] == 0.0
+    assert math.isnan(oracle_mod.exp_array(np.array([np.nan]))[0])
+
+
+def test_float_literal_constants():
+    assert float(np.float32(1e-6)) == 9.9999999747524271e-07
+    assert float(np.float32(1e-12)) == 9.999999960041972e-13
+    assert float(np.float32(1e-9)) == 9.9999997171806854e-10
+    assert float(np.float32(1e-1)) == 0.10000000149011612
+    assert float(np.float32(np.sqrt(np.float32(3.0))) / np.float32(2.0)) * float(np.float32(0.15)) == 0.12990381339803569
+
+
+def test_sogp_survey_smoke_vector(oracle_mod):
+    o = oracle_mod.Oracle(capacity=2, shuffle=0)
+    r = o.fit_patches([0, 4], [0, .05, 0, .05], [0, 0, .05, .05], [.01, .02, -.01, 0])
+    assert r["nbv"].tolist() == [2]
+    assert r["bv_idx"].tolist() == [2, 1]
+    np.testing.assert_allclose(r["alpha"], [-0.04287038525668329, 0.04292043524805538], rtol=1e-9)
+    np.testing.assert_allclose(o.predict(0, [[0.025, 0.025]])[0], 0.0050018719900836684, rtol=1e-8)
+    st = o.stats()
+    assert (st["n_full"], st["n_del_cap"], st["n_sparse"], st["n_first"]) == (3, 2, 0, 1)
+
+
+def _patch(rng, n, res=0.1):
+    x1 = rng.uniform(-res / 2, res / 2, n)
+    x2 = rng.uniform(-res / 2, res / 2, n)
+    y = 0.02 * np.sin(40 * x1) * np.cos(30 * x2) + rng.normal(0, 0.003, n)
+    return x1, x2, y
+
+
+@pytest.mark.parametrize("cap,hyper", [(100, dict(sigmaf_sq=100.0, l_sq=1.0, s0=float(np.float32(0.1)))),
+                                      (12, dict(sigmaf_sq=1.0, l_sq=(0.1 / 12) ** 2, s0=1e-4)),
+                                      (30, dict(sigmaf_sq=1.0, l_sq=(0.1 / 12) ** 2, s0=1e-4))])
+def test_sogp_matches_numpy_witness(oracle_mod, cap, hyper):
+    """Oracle (canonical arithmetic) vs numpy restatement of matlab/sogp.m: same BV sets and
+    event sequences, alpha to rounding level scaled by the conditioning of the hyper-set."""
+    rng = np.random.default_rng(cap)
+    n = 300
+    x1, x2, y = _patch(rng, n)
+    o = oracle_mod.Oracle(capacity=cap, shuffle=0, **hyper)
+    r = o.fit_patches([0, n], x1, x2, y, dump=True)
+    w = SogpNumpy(capacity=cap, s20=hyper["s0"], sigmaf_sq=hyper["sigmaf_sq"], l_sq=hyper["l_sq"])
+    for i in range(n):
+        w.add([x1[i], x2[i]], y[i], i)
+    st = o.stats()
+    well_conditioned = hyper["l_sq"] < 1.0
+    if well_conditioned:
+        assert sorted(r["bv_idx"].tolist()) == sorted(w.idx)
+        assert r["bv_idx"].tolist() == w.idx  # same slot order too
+        assert st["n_full"] == w.events.count("full") and st["n_sparse"] == w.events.count("sparse")
+        assert st["n_del_cap"] == w.events.count("delcap") and st["n_del_geo"] == w.events.count("delgeo")
+        np.testing.assert_allclose(r["alpha"], w.alpha, rtol=1e-7, atol=1e-9)
+        N = int(r["nbv"][0])
+        np.testing.assert_allclose(r["C"].reshape(N, N), w.C, rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(r["Q"].reshape(N, N), w.Q, rtol=1e-6, atol=1e-6)
+    # predictions agree in both regimes (the ill-conditioned REF set hides BV-set noise)
+    X = np.stack(_patch(rng, 50)[:2], axis=1)
+    f = o.predict(0, X)
+    fw = np.array([w.predict(x) for x in X])
+    np.testing.assert_allclose(f, fw, atol=2e-4 if not well_conditioned else 1e-8)
+
+
+def test_sogp_invariants(oracle_mod):
+    """Q K_BV ~ I, symmetry of C and Q, size <= capacity."""
+    rng = np.random.default_rng(5)
+    n, cap, res = 400, 20, 0.1
+    x1, x2, y = _patch(rng, n)
+    hyper = dict(sigmaf_sq=1.0, l_sq=(res / 12) ** 2, s0=1e-4)
+    o = oracle_mod.Oracle(capacity=cap, shuffle=1, **hyper)
+    r = o.fit_patches([0, n], x1, x2, y, dump=True)
+    N = int(r["nbv"][0])
+    assert 1 <= N <= cap
+    Cm, Qm = r["C"].reshape(N, N), r["Q"].reshape(N, N)
+    assert np.array_equal(Cm, Cm.T) and np.array_equal(Qm, Qm.T)  # canonical updates are bitwise symmetric
+    b = np.stack([r["bv1"], r["bv2"]])
+    d = b[:, :, None] - b[:, None, :]
+    K = np.exp(-0.5 / hyper["l_sq"] * (d * d).sum(axis=0))
+    np.testing.assert_allclose(Qm @ K, np.eye(N), atol=1e-6)
+    # BVs are points of the patch, addressed through the shuffle permutation
+    assert np.array_equal(r["bv1"], x1[r["bv_idx"]]) and np.array_equal(r["bv2"], x2[r["bv_idx"]])
+    perm = r["perm"]
+    assert sorted(perm.tolist()) == list(range(n))
+    assert perm.tolist() == oracle_mod.shuffles(0, [n]).tolist()
+
+
+def test_rand_stream_accounting_across_patches(oracle_mod):
+    """Patch p's height shuffle starts after 2*(n_q - 1) draws per earlier non-empty patch
+    (gp_compressor.cpp:162-163: height GP then RGB field GP both shuffle)."""
+    rng = np.random.default_rng(9)
+    sizes = [5, 0, 9, 1, 7]
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    x1, x2, y = _patch(rng, off[-1])
+    o = oracle_mod.Oracle(capacity=4)
+    r = o.fit_patches(off, x1, x2, y)
+    pos = 0
+    for p, n in enumerate(sizes):
+        if n == 0:
+            continue
+        want = oracle_mod.shuffles(pos, [n])
+        assert r["perm"][off[p]:off[p + 1]].tolist() == want.tolist()
+        pos += 2 * (n - 1)
+    assert o.rand_offset() == pos
+    assert r["nbv"][1] == 0
