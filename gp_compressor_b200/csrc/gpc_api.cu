@@ -1,0 +1,682 @@
+// gpc_api.cu — the extern "C" layer of libgpc_b200.so (see include/gpc.h).
+// Host-side orchestration only: buffer management, stage sequencing, sharding, timing.
+// All arithmetic of the path runs in the kernels of k_*.cu; there is no CPU fallback.
+#include <cstdio>
+#include <cstring>
+
+#include "gpc_internal.h"
+
+namespace gpc {
+thread_local uint64_t g_launches = 0;
+}
+
+using namespace gpc;
+
+struct gpc_handle {
+    gpc_config cfg;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    uint64_t rand_offset = 0;
+    gpc_stats stats;
+    // sizes
+    int64_t n_in = 0, n_patches = 0, n_claimed = 0, patch_lo = 0, patch_hi = 0, n_decoded = 0, n_bv_total = -1;
+    uint32_t depth = 0;
+    double lattice_min[3] = {0, 0, 0};
+    bool have_fit = false, have_frames = false, have_binning = false, have_cloud = false;
+    int64_t s_begin = 0, s_count = 0;  // stream range of this shard
+    // device buffers
+    DevBuf cloud;                               // input cloud (n_in * 32)
+    DevBuf off, x1, x2, y, perm, patch_of;      // claimed stream, patch-major
+    DevBuf fx1, fx2, fy;                        // fit stream (add order)
+    DevBuf draws, roff, rnd, scan_tmp, small;   // rand bookkeeping, scan scratch, small readbacks
+    DevBuf nbv, flags, alpha, b1, b2, bidx, dumpC, dumpQ, queue0, queue1, qcount, kstats;
+    DevBuf nonempty, slot, out32, heights;
+    DevBuf quat, mean, rgbmean, Rm, center, code, ncand, owner, st_idx;
+    DevBuf tmpA, tmpB, tmpC;
+    std::vector<cudaEvent_t> ev;
+    BinningWork* bw = nullptr;
+};
+
+namespace {
+
+int fail(gpc_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(h, GPC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));           \
+    } while (0)
+
+struct StageTimer {
+    gpc_handle* h;
+    size_t used = 0;
+    std::vector<std::pair<float*, std::pair<size_t, size_t>>> spans;
+    explicit StageTimer(gpc_handle* hh) : h(hh) {}
+    size_t mark() {
+        if (used == h->ev.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            h->ev.push_back(e);
+        }
+        cudaEventRecord(h->ev[used], h->stream);
+        return used++;
+    }
+    void span(float* dst, size_t a, size_t b) { spans.push_back({dst, {a, b}}); }
+    void resolve() {
+        for (auto& s : spans) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, h->ev[s.second.first], h->ev[s.second.second]);
+            *s.first += ms;
+        }
+    }
+};
+
+double kernel_cl(const gpc_config& c) { return (double)(-0.5f) / c.l_sq; }  // -0.5f / p(1), rbf_kernel.cpp:17
+
+// Patches [lo, hi) of shard r out of c: contiguous ranges of the visiting order with about
+// equal numbers of claimed points.  off is the host copy of the patch offsets.
+void shard_range(const std::vector<int64_t>& off, int r, int c, int64_t* lo, int64_t* hi) {
+    const int64_t P = (int64_t)off.size() - 1;
+    const int64_t total = off[P];
+    auto bound = [&](int k) -> int64_t {
+        if (k <= 0) return 0;
+        if (k >= c) return P;
+        int64_t target = (int64_t)((__int128)total * k / c);
+        int64_t a = 0, b = P;  // first p with off[p] >= target
+        while (a < b) {
+            int64_t m = (a + b) / 2;
+            if (off[m] >= target) b = m; else a = m + 1;
+        }
+        return a;
+    };
+    *lo = bound(r);
+    *hi = bound(r + 1);
+}
+
+// Shuffle + SOGP fit of patches [patch_lo, patch_hi) over the stream held in h->off/x1/x2/y.
+int run_fit(gpc_handle* h, StageTimer& tm) {
+    const gpc_config& c = h->cfg;
+    cudaStream_t st = h->stream;
+    const int64_t P = h->n_patches;
+    if (c.capacity < 1) return fail(h, GPC_ERR_INVALID, "capacity must be >= 1 (the reference's -1 / 0 modes are not built)");
+    const int need_ld = c.capacity + 1;
+    if (need_ld > sogp_bucket_ld(3))
+        return fail(h, GPC_ERR_INVALID, "capacity > 117 needs the packed / cluster SOGP kernel (not built yet)");
+    // shard bounds from the host copy of the offsets
+    std::vector<int64_t> hoff(P + 1);
+    CK(cudaMemcpyAsync(hoff.data(), h->off.p, (P + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    h->n_claimed = hoff[P];
+    shard_range(hoff, c.shard_rank, c.shard_count, &h->patch_lo, &h->patch_hi);
+    const int64_t lo = h->patch_lo, hi = h->patch_hi, PL = hi - lo;
+    h->s_begin = hoff[lo];
+    h->s_count = hoff[hi] - hoff[lo];
+    const int64_t S = h->n_claimed;
+    size_t t0 = tm.mark();
+    // rand stream bookkeeping (all patches: the stream is global across patches)
+    const int mult = c.shuffle ? (c.rgb_rand ? 2 : 1) : 0;
+    uint64_t draws_lo = 0, draws_hi = 0, draws_all = 0;
+    for (int64_t p = 0; p < P; p++) {
+        int64_t n = hoff[p + 1] - hoff[p];
+        uint64_t d = n > 0 ? (uint64_t)(n - 1) * mult : 0;
+        if (p == lo) draws_lo = draws_all;
+        draws_all += d;
+        if (p + 1 == hi) draws_hi = draws_all;
+    }
+    if (PL == 0) draws_hi = draws_lo;
+    CK(h->perm.reserve(std::max<int64_t>(S, 1) * sizeof(int32_t)));
+    CK(h->patch_of.reserve(std::max<int64_t>(S, 1) * sizeof(int32_t)));
+    CK(h->fx1.reserve(std::max<int64_t>(S, 1) * sizeof(double)));
+    CK(h->fx2.reserve(std::max<int64_t>(S, 1) * sizeof(double)));
+    CK(h->fy.reserve(std::max<int64_t>(S, 1) * sizeof(double)));
+    if (PL > 0 && h->s_count > 0) {
+        CK(h->draws.reserve((P + 1) * sizeof(int64_t)));
+        CK(h->roff.reserve((P + 2) * sizeof(int64_t)));
+        CK(h->scan_tmp.reserve(scan_tmp_bytes(P + 1)));
+        launch_patch_draws(h->off.as<int64_t>(), P, mult, h->draws.as<int64_t>(), st);
+        launch_exclusive_scan_i64(h->draws.as<int64_t>(), h->roff.as<int64_t>(), P, h->scan_tmp.p, st);
+        const int64_t nd = (int64_t)(draws_hi - draws_lo);
+        if (c.shuffle && nd > 0) {
+            CK(h->rnd.reserve(nd * sizeof(uint32_t)));
+            launch_rand_stream(h->rand_offset + draws_lo, nd, h->rnd.as<uint32_t>(), st);
+        }
+        launch_shuffle(h->off.as<int64_t>() + lo, PL, h->roff.as<int64_t>() + lo, h->rnd.as<uint32_t>(), c.shuffle,
+                       h->perm.as<int32_t>(), h->patch_of.as<int32_t>(), h->s_begin, h->s_count, st);
+        launch_gather_stream(h->off.as<int64_t>() + lo, h->patch_of.as<int32_t>(), h->perm.as<int32_t>(),
+                             h->x1.as<double>(), h->x2.as<double>(), h->y.as<double>(), h->s_begin, h->s_count,
+                             h->fx1.as<double>(), h->fx2.as<double>(), h->fy.as<double>(), st);
+    }
+    h->rand_offset += draws_all;
+    size_t t1 = tm.mark();
+    tm.span(&h->stats.ms_shuffle, t0, t1);
+    // outputs
+    const int cap = c.capacity;
+    const int64_t PLa = std::max<int64_t>(PL, 1);
+    CK(h->nbv.reserve(PLa * sizeof(int32_t)));
+    CK(h->flags.reserve(PLa * sizeof(int32_t)));
+    CK(h->alpha.reserve(PLa * cap * sizeof(double)));
+    CK(h->b1.reserve(PLa * cap * sizeof(double)));
+    CK(h->b2.reserve(PLa * cap * sizeof(double)));
+    CK(h->bidx.reserve(PLa * cap * sizeof(int32_t)));
+    if (c.keep_state) {
+        CK(h->dumpC.reserve(PLa * (size_t)cap * cap * sizeof(double)));
+        CK(h->dumpQ.reserve(PLa * (size_t)cap * cap * sizeof(double)));
+    }
+    CK(h->queue0.reserve(PLa * sizeof(int32_t)));
+    CK(h->queue1.reserve(PLa * sizeof(int32_t)));
+    CK(h->qcount.reserve(4 * sizeof(int32_t)));
+    CK(h->kstats.reserve(16 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(h->kstats.p, 0, 16 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(h->qcount.p, 0, 4 * sizeof(int32_t), st));
+    SogpArgs a;
+    a.off = h->off.as<int64_t>();
+    a.fx1 = h->fx1.as<double>(); a.fx2 = h->fx2.as<double>(); a.fy = h->fy.as<double>();
+    a.forig = h->perm.as<int32_t>();
+    a.capacity = cap;
+    a.s20 = c.s0; a.eps_tol = c.eps_tol; a.p0 = c.sigmaf_sq; a.cl = kernel_cl(c);
+    a.out_first = lo;
+    a.nbv = h->nbv.as<int32_t>(); a.flags = h->flags.as<int32_t>();
+    a.o_alpha = h->alpha.as<double>(); a.o_b1 = h->b1.as<double>(); a.o_b2 = h->b2.as<double>();
+    a.o_idx = h->bidx.as<int32_t>();
+    a.dumpC = c.keep_state ? h->dumpC.as<double>() : nullptr;
+    a.dumpQ = c.keep_state ? h->dumpQ.as<double>() : nullptr;
+    a.stats = h->kstats.as<unsigned long long>();
+    int64_t work = PL;
+    const int32_t* ids = nullptr;
+    for (int b = 0; b < 4 && work > 0; b++) {
+        const int bl = sogp_bucket_ld(b);
+        const bool final_bucket = need_ld <= bl;
+        a.ld = final_bucket ? need_ld : bl;
+        a.patch_ids = ids;
+        a.first_patch = lo;
+        a.n_work = (int)work;
+        DevBuf& q = (b & 1) ? h->queue1 : h->queue0;
+        a.queue = final_bucket ? nullptr : q.as<int32_t>();
+        a.queue_count = h->qcount.as<int32_t>() + b;
+        CK(launch_sogp_fit(b, a, st));
+        g_launches++;
+        if (final_bucket) break;
+        int32_t qn = 0;
+        CK(cudaMemcpyAsync(&qn, h->qcount.as<int32_t>() + b, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        h->stats.escalated[b] = (uint64_t)qn;
+        work = qn;
+        ids = q.as<int32_t>();
+    }
+    size_t t2 = tm.mark();
+    tm.span(&h->stats.ms_fit, t1, t2);
+    h->have_fit = true;
+    h->n_bv_total = -1;
+    return GPC_OK;
+}
+
+int read_fit_stats(gpc_handle* h) {
+    unsigned long long k[16];
+    CK(cudaMemcpyAsync(k, h->kstats.p, sizeof(k), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    gpc_stats& s = h->stats;
+    s.n_add = k[0]; s.n_first = k[1]; s.n_sparse = k[2]; s.n_full = k[3]; s.n_del_cap = k[4]; s.n_del_geo = k[5];
+    s.sum_n = k[6]; s.sum_n2_common = k[7]; s.sum_n2_sparse = k[8]; s.sum_n2_full = k[9]; s.sum_n2_del = k[10];
+    return GPC_OK;
+}
+
+void reset_stats(gpc_handle* h) {
+    std::memset(&h->stats, 0, sizeof(h->stats));
+    g_launches = 0;
+}
+
+int run_decode(gpc_handle* h, bool want_cloud, bool want_heights, StageTimer& tm) {
+    const gpc_config& c = h->cfg;
+    cudaStream_t st = h->stream;
+    if (!h->have_fit) return fail(h, GPC_ERR_STATE, "decompress before compress / fit / set_params");
+    const int64_t PL = h->patch_hi - h->patch_lo;
+    const int64_t g2 = (int64_t)c.sz * c.sz;
+    size_t t0 = tm.mark();
+    CK(h->nonempty.reserve((PL + 1) * sizeof(int64_t)));
+    CK(h->slot.reserve((PL + 2) * sizeof(int64_t)));
+    CK(h->scan_tmp.reserve(scan_tmp_bytes(PL + 1)));
+    launch_flag_nonempty(h->nbv.as<int32_t>(), PL, h->nonempty.as<int64_t>(), st);
+    launch_exclusive_scan_i64(h->nonempty.as<int64_t>(), h->slot.as<int64_t>(), PL, h->scan_tmp.p, st);
+    g_launches += 4;
+    int64_t n_nonempty = 0;
+    CK(cudaMemcpyAsync(&n_nonempty, h->slot.as<int64_t>() + PL, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    h->n_decoded = n_nonempty * g2;
+    if (want_cloud) CK(h->out32.reserve(std::max<int64_t>(h->n_decoded, 1) * GPC_POINT_BYTES));
+    if (want_heights) CK(h->heights.reserve(std::max<int64_t>(h->n_decoded, 1) * sizeof(double)));
+    PredictArgs a;
+    a.n_patches = PL;
+    a.nbv = h->nbv.as<int32_t>();
+    a.slot = h->slot.as<int64_t>();
+    a.stride = c.capacity;
+    a.alpha = h->alpha.as<double>(); a.b1 = h->b1.as<double>(); a.b2 = h->b2.as<double>();
+    if (h->have_frames) {
+        a.quat = h->quat.as<double>() + 4 * h->patch_lo;
+        a.mean = h->mean.as<double>() + 3 * h->patch_lo;
+        a.rgbmean = h->rgbmean.as<double>() + 3 * h->patch_lo;
+    } else {
+        a.quat = a.mean = a.rgbmean = nullptr;
+    }
+    a.res = c.res; a.sz = c.sz; a.p0 = c.sigmaf_sq; a.cl = kernel_cl(c);
+    a.out32 = want_cloud ? h->out32.as<uint8_t>() : nullptr;
+    a.heights = want_heights ? h->heights.as<double>() : nullptr;
+    launch_predict_grid(a, st);
+    g_launches++;
+    CK(cudaGetLastError());
+    size_t t1 = tm.mark();
+    tm.span(&h->stats.ms_predict, t0, t1);
+    return GPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gpc_version(void) { return "gpc_b200 0.1 (sm_100a)"; }
+
+int gpc_config_default(gpc_config* c) {
+    if (!c) return GPC_ERR_INVALID;
+    c->res = (double)0.1f;         // gp_compressor.h:65
+    c->sz = 10;                    // gp_compressor.h:65
+    c->capacity = 100;             // sparse_gp.h:48
+    c->s0 = (double)1e-1f;         // sparse_gp.h:48
+    c->eps_tol = (double)1e-6f;    // sparse_gp.hpp:31
+    c->sigmaf_sq = (double)100e-0f;  // rbf_kernel.h:24
+    c->l_sq = 1.0;                 // rbf_kernel.h:24
+    c->leaf_order = 0;
+    c->shuffle = 1;
+    c->rgb_rand = 1;
+    c->device = 0;
+    c->shard_rank = 0;
+    c->shard_count = 1;
+    c->keep_state = 0;
+    return GPC_OK;
+}
+
+int gpc_create(const gpc_config* cfg, gpc_handle** out) {
+    if (!cfg || !out) return GPC_ERR_INVALID;
+    *out = nullptr;
+    if (!(cfg->res > 0) || cfg->sz < 1 || cfg->shard_count < 1 || cfg->shard_rank < 0 || cfg->shard_rank >= cfg->shard_count ||
+        !(cfg->l_sq > 0))
+        return GPC_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) return GPC_ERR_CUDA;
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return GPC_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return GPC_ERR_CUDA;
+    if (prop.major != 10) return GPC_ERR_CUDA;  // sm_100a SASS only
+    gpc_handle* h = new gpc_handle();
+    h->cfg = *cfg;
+    std::memset(&h->stats, 0, sizeof(h->stats));
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return GPC_ERR_CUDA; }
+    static RandTables tables;
+    static bool tables_ready = false;
+    if (!tables_ready) { rand_tables_init(&tables); tables_ready = true; }
+    if (rand_upload_tables(&tables) != cudaSuccess) { cudaStreamDestroy(h->stream); delete h; return GPC_ERR_CUDA; }
+    *out = h;
+    return GPC_OK;
+}
+
+void gpc_destroy(gpc_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf* bufs[] = {&h->cloud, &h->off, &h->x1, &h->x2, &h->y, &h->perm, &h->patch_of, &h->fx1, &h->fx2, &h->fy, &h->draws,
+                      &h->roff, &h->rnd, &h->scan_tmp, &h->small, &h->nbv, &h->flags, &h->alpha, &h->b1, &h->b2, &h->bidx,
+                      &h->dumpC, &h->dumpQ, &h->queue0, &h->queue1, &h->qcount, &h->kstats, &h->nonempty, &h->slot, &h->out32,
+                      &h->heights, &h->quat, &h->mean, &h->rgbmean, &h->Rm, &h->center, &h->code, &h->ncand, &h->owner,
+                      &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC};
+    for (DevBuf* b : bufs) b->release();
+    binning_free(h->bw);
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char* gpc_last_error(const gpc_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int gpc_set_rand_offset(gpc_handle* h, uint64_t offset) {
+    if (!h) return GPC_ERR_INVALID;
+    h->rand_offset = offset;
+    return GPC_OK;
+}
+
+int gpc_fit_patches(gpc_handle* h, int64_t P, const int64_t* off, const double* x1, const double* x2, const double* y) {
+    if (!h || P < 0 || !off) return GPC_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    if (off[0] != 0) return fail(h, GPC_ERR_INVALID, "off[0] must be 0");
+    for (int64_t p = 0; p < P; p++)
+        if (off[p + 1] < off[p] || off[p + 1] - off[p] > 0x7fffffff) return fail(h, GPC_ERR_INVALID, "offsets must be non-decreasing");
+    const int64_t S = off[P];
+    if (S > 0 && (!x1 || !x2 || !y)) return GPC_ERR_INVALID;
+    reset_stats(h);
+    StageTimer tm(h);
+    cudaStream_t st = h->stream;
+    size_t tA = tm.mark();
+    CK(h->off.reserve((P + 1) * sizeof(int64_t)));
+    CK(h->x1.reserve(std::max<int64_t>(S, 1) * sizeof(double)));
+    CK(h->x2.reserve(std::max<int64_t>(S, 1) * sizeof(double)));
+    CK(h->y.reserve(std::max<int64_t>(S, 1) * sizeof(double)));
+    CK(cudaMemcpyAsync(h->off.p, off, (P + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    if (S > 0) {
+        CK(cudaMemcpyAsync(h->x1.p, x1, S * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->x2.p, x2, S * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->y.p, y, S * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    size_t tB = tm.mark();
+    tm.span(&h->stats.ms_h2d, tA, tB);
+    h->n_patches = P;
+    h->n_in = S;
+    h->have_frames = false;
+    h->have_binning = false;
+    int rc = run_fit(h, tm);
+    if (rc) return rc;
+    size_t tC = tm.mark();
+    tm.span(&h->stats.ms_total, tA, tC);
+    rc = read_fit_stats(h);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    tm.resolve();
+    h->stats.kernel_launches = g_launches;
+    return GPC_OK;
+}
+
+int gpc_upload_cloud(gpc_handle* h, const void* cloud, int64_t n) {
+    if (!h || n < 0 || (n > 0 && !cloud)) return GPC_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(h->cloud.reserve(std::max<int64_t>(n, 1) * GPC_POINT_BYTES));
+    if (n > 0) CK(cudaMemcpyAsync(h->cloud.p, cloud, n * GPC_POINT_BYTES, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->n_in = n;
+    h->have_cloud = true;
+    return GPC_OK;
+}
+
+int gpc_compress_resident(gpc_handle* h) {
+    if (!h) return GPC_ERR_INVALID;
+    if (!h->have_cloud) return fail(h, GPC_ERR_STATE, "gpc_compress_resident before gpc_upload_cloud");
+    return fail(h, GPC_ERR_STATE, "binning stages not built yet");
+}
+
+int gpc_compress(gpc_handle* h, const void* cloud, int64_t n) {
+    int rc = gpc_upload_cloud(h, cloud, n);
+    if (rc) return rc;
+    return gpc_compress_resident(h);
+}
+
+int gpc_decompress_resident(gpc_handle* h, int64_t* n_out) {
+    if (!h) return GPC_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    reset_stats(h);
+    StageTimer tm(h);
+    size_t tA = tm.mark();
+    int rc = run_decode(h, true, true, tm);
+    if (rc) return rc;
+    size_t tB = tm.mark();
+    tm.span(&h->stats.ms_total, tA, tB);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    tm.resolve();
+    h->stats.kernel_launches = g_launches;
+    if (n_out) *n_out = h->n_decoded;
+    return GPC_OK;
+}
+
+int gpc_decompress(gpc_handle* h, void* out, int64_t capacity_points, int64_t* n_out) {
+    if (!h) return GPC_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    reset_stats(h);
+    StageTimer tm(h);
+    size_t tA = tm.mark();
+    int rc = run_decode(h, true, false, tm);
+    if (rc) return rc;
+    size_t tB = tm.mark();
+    if (out) {
+        if (capacity_points < h->n_decoded) return fail(h, GPC_ERR_INVALID, "output buffer too small");
+        if (h->n_decoded > 0)
+            CK(cudaMemcpyAsync(out, h->out32.p, h->n_decoded * GPC_POINT_BYTES, cudaMemcpyDeviceToHost, h->stream));
+    }
+    size_t tC = tm.mark();
+    tm.span(&h->stats.ms_d2h, tB, tC);
+    tm.span(&h->stats.ms_total, tA, tC);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    tm.resolve();
+    h->stats.kernel_launches = g_launches;
+    if (n_out) *n_out = h->n_decoded;
+    return GPC_OK;
+}
+
+int gpc_get_heights(gpc_handle* h, double* out, int64_t capacity) {
+    if (!h || !out) return GPC_ERR_INVALID;
+    if (capacity < h->n_decoded) return fail(h, GPC_ERR_INVALID, "heights buffer too small");
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->n_decoded > 0) CK(cudaMemcpy(out, h->heights.p, h->n_decoded * sizeof(double), cudaMemcpyDeviceToHost));
+    return GPC_OK;
+}
+
+int gpc_predict(gpc_handle* h, int64_t patch, const double* X, int64_t m, double* f, double* sigma) {
+    if (!h || m < 0 || (m > 0 && (!X || !f))) return GPC_ERR_INVALID;
+    if (!h->have_fit) return fail(h, GPC_ERR_STATE, "predict before fit");
+    if (patch < h->patch_lo || patch >= h->patch_hi) return fail(h, GPC_ERR_INVALID, "patch outside this shard");
+    if (sigma && !h->cfg.keep_state) return fail(h, GPC_ERR_INVALID, "sigma needs gpc_config.keep_state");
+    CK(cudaSetDevice(h->cfg.device));
+    if (m == 0) return GPC_OK;
+    const gpc_config& c = h->cfg;
+    const int64_t op = patch - h->patch_lo;
+    int32_t N = 0;
+    CK(cudaMemcpy(&N, h->nbv.as<int32_t>() + op, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CK(h->tmpA.reserve(2 * m * sizeof(double)));
+    CK(h->tmpB.reserve(m * sizeof(double)));
+    CK(h->tmpC.reserve(m * sizeof(double)));
+    CK(cudaMemcpyAsync(h->tmpA.p, X, 2 * m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    launch_predict_points(h->alpha.as<double>() + op * c.capacity, h->b1.as<double>() + op * c.capacity,
+                          h->b2.as<double>() + op * c.capacity, N,
+                          sigma ? h->dumpC.as<double>() + op * (int64_t)c.capacity * c.capacity : nullptr, c.sigmaf_sq,
+                          kernel_cl(c), c.s0, h->tmpA.as<double>(), m, h->tmpB.as<double>(),
+                          sigma ? h->tmpC.as<double>() : nullptr, h->stream);
+    CK(cudaMemcpyAsync(f, h->tmpB.p, m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (sigma) CK(cudaMemcpyAsync(sigma, h->tmpC.p, m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    return GPC_OK;
+}
+
+int gpc_get_sizes(gpc_handle* h, gpc_sizes* s) {
+    if (!h || !s) return GPC_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->have_fit && h->n_bv_total < 0) {
+        const int64_t PL = h->patch_hi - h->patch_lo;
+        std::vector<int32_t> nb(PL);
+        if (PL > 0) CK(cudaMemcpy(nb.data(), h->nbv.p, PL * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        int64_t t = 0;
+        for (int32_t v : nb) t += v;
+        h->n_bv_total = t;
+    }
+    s->n_in = h->n_in; s->n_patches = h->n_patches; s->n_claimed = h->n_claimed;
+    s->n_bv_total = h->have_fit ? h->n_bv_total : 0;
+    s->patch_lo = h->patch_lo; s->patch_hi = h->patch_hi; s->n_decoded = h->n_decoded;
+    s->rand_offset = h->rand_offset;
+    for (int a = 0; a < 3; a++) s->lattice_min[a] = h->lattice_min[a];
+    s->depth = h->depth; s->pad = 0;
+    return GPC_OK;
+}
+
+int gpc_get_stats(gpc_handle* h, gpc_stats* s) {
+    if (!h || !s) return GPC_ERR_INVALID;
+    *s = h->stats;
+    return GPC_OK;
+}
+
+int gpc_get_params(gpc_handle* h, int32_t* nbv, int64_t* bv_off, int32_t* bv_index, double* bv1, double* bv2, double* alpha,
+                   int32_t* flags) {
+    if (!h) return GPC_ERR_INVALID;
+    if (!h->have_fit) return fail(h, GPC_ERR_STATE, "no fit held by the handle");
+    CK(cudaSetDevice(h->cfg.device));
+    const int64_t PL = h->patch_hi - h->patch_lo;
+    const int cap = h->cfg.capacity;
+    std::vector<int32_t> nb(PL);
+    if (PL > 0) CK(cudaMemcpy(nb.data(), h->nbv.p, PL * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (nbv) std::memcpy(nbv, nb.data(), PL * sizeof(int32_t));
+    if (flags && PL > 0) CK(cudaMemcpy(flags, h->flags.p, PL * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    std::vector<int64_t> bo(PL + 1, 0);
+    for (int64_t p = 0; p < PL; p++) bo[p + 1] = bo[p] + nb[p];
+    if (bv_off) std::memcpy(bv_off, bo.data(), (PL + 1) * sizeof(int64_t));
+    // strided device arrays -> compact host arrays (results leave through the host here)
+    auto compact = [&](const DevBuf& src, void* dst, size_t esz) -> int {
+        if (!dst || PL == 0) return GPC_OK;
+        std::vector<uint8_t> tmp((size_t)PL * cap * esz);
+        CK(cudaMemcpy(tmp.data(), src.p, tmp.size(), cudaMemcpyDeviceToHost));
+        for (int64_t p = 0; p < PL; p++)
+            std::memcpy((uint8_t*)dst + bo[p] * esz, tmp.data() + (size_t)p * cap * esz, (size_t)nb[p] * esz);
+        return GPC_OK;
+    };
+    int rc;
+    if ((rc = compact(h->bidx, bv_index, sizeof(int32_t)))) return rc;
+    if ((rc = compact(h->b1, bv1, sizeof(double)))) return rc;
+    if ((rc = compact(h->b2, bv2, sizeof(double)))) return rc;
+    if ((rc = compact(h->alpha, alpha, sizeof(double)))) return rc;
+    return GPC_OK;
+}
+
+int gpc_get_state(gpc_handle* h, int64_t patch, double* C, double* Q) {
+    if (!h) return GPC_ERR_INVALID;
+    if (!h->have_fit || !h->cfg.keep_state) return fail(h, GPC_ERR_STATE, "gpc_get_state needs a fit made with keep_state");
+    if (patch < h->patch_lo || patch >= h->patch_hi) return fail(h, GPC_ERR_INVALID, "patch outside this shard");
+    CK(cudaSetDevice(h->cfg.device));
+    const int64_t op = patch - h->patch_lo;
+    const int cap = h->cfg.capacity;
+    int32_t N = 0;
+    CK(cudaMemcpy(&N, h->nbv.as<int32_t>() + op, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (C && N > 0) CK(cudaMemcpy(C, h->dumpC.as<double>() + op * (int64_t)cap * cap, (size_t)N * N * sizeof(double), cudaMemcpyDeviceToHost));
+    if (Q && N > 0) CK(cudaMemcpy(Q, h->dumpQ.as<double>() + op * (int64_t)cap * cap, (size_t)N * N * sizeof(double), cudaMemcpyDeviceToHost));
+    return GPC_OK;
+}
+
+int gpc_set_params(gpc_handle* h, int64_t P, const int32_t* nbv, const double* bv1, const double* bv2, const double* alpha,
+                   const double* quat4, const double* mean3, const double* rgbmean3) {
+    if (!h || P < 0 || !nbv || !bv1 || !bv2 || !alpha) return GPC_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    const int cap = h->cfg.capacity;
+    std::vector<int64_t> off(P + 1, 0);
+    for (int64_t p = 0; p < P; p++) {
+        if (nbv[p] < 0 || nbv[p] > cap) return fail(h, GPC_ERR_INVALID, "nbv exceeds capacity");
+        off[p + 1] = off[p] + 1;  // shard by patch count
+    }
+    int64_t lo, hi;
+    shard_range(off, h->cfg.shard_rank, h->cfg.shard_count, &lo, &hi);
+    const int64_t PL = hi - lo, PLa = std::max<int64_t>(PL, 1);
+    std::vector<int64_t> bo(P + 1, 0);
+    for (int64_t p = 0; p < P; p++) bo[p + 1] = bo[p] + nbv[p];
+    CK(h->nbv.reserve(PLa * sizeof(int32_t)));
+    CK(h->flags.reserve(PLa * sizeof(int32_t)));
+    CK(h->alpha.reserve(PLa * cap * sizeof(double)));
+    CK(h->b1.reserve(PLa * cap * sizeof(double)));
+    CK(h->b2.reserve(PLa * cap * sizeof(double)));
+    auto expand = [&](const double* src, DevBuf& dst) -> int {
+        std::vector<double> tmp((size_t)PLa * cap, 0.0);
+        for (int64_t p = lo; p < hi; p++) std::memcpy(&tmp[(size_t)(p - lo) * cap], src + bo[p], (size_t)nbv[p] * sizeof(double));
+        CK(cudaMemcpy(dst.p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
+        return GPC_OK;
+    };
+    int rc;
+    if ((rc = expand(alpha, h->alpha))) return rc;
+    if ((rc = expand(bv1, h->b1))) return rc;
+    if ((rc = expand(bv2, h->b2))) return rc;
+    if (PL > 0) CK(cudaMemcpy(h->nbv.p, nbv + lo, PL * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemset(h->flags.p, 0, PLa * sizeof(int32_t)));
+    h->have_frames = false;
+    if (quat4 && mean3 && rgbmean3 && P > 0) {
+        CK(h->quat.reserve(P * 4 * sizeof(double)));
+        CK(h->mean.reserve(P * 3 * sizeof(double)));
+        CK(h->rgbmean.reserve(P * 3 * sizeof(double)));
+        CK(cudaMemcpy(h->quat.p, quat4, P * 4 * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->mean.p, mean3, P * 3 * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->rgbmean.p, rgbmean3, P * 3 * sizeof(double), cudaMemcpyHostToDevice));
+        h->have_frames = true;
+    }
+    h->n_patches = P;
+    h->patch_lo = lo;
+    h->patch_hi = hi;
+    h->have_fit = true;
+    h->have_binning = false;
+    h->n_bv_total = -1;
+    return GPC_OK;
+}
+
+int gpc_get_patches(gpc_handle* h, uint64_t* code, float* center3, int32_t* n_candidates, double* R9, double* quat4,
+                    double* mean3, double* rgbmean3, int64_t* patch_off) {
+    if (!h) return GPC_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    const int64_t P = h->n_patches;
+    if (patch_off) {
+        if (!h->have_fit && !h->have_binning) return fail(h, GPC_ERR_STATE, "no patches held by the handle");
+        CK(cudaMemcpy(patch_off, h->off.p, (P + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    }
+    if (code || center3 || n_candidates || R9) {
+        if (!h->have_binning) return fail(h, GPC_ERR_STATE, "patch frames need a compress on this handle");
+        if (code && P) CK(cudaMemcpy(code, h->code.p, P * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        if (center3 && P) CK(cudaMemcpy(center3, h->center.p, P * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+        if (n_candidates && P) CK(cudaMemcpy(n_candidates, h->ncand.p, P * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (R9 && P) CK(cudaMemcpy(R9, h->Rm.p, P * 9 * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    if (quat4 || mean3 || rgbmean3) {
+        if (!h->have_frames) return fail(h, GPC_ERR_STATE, "no patch frames held by the handle");
+        if (quat4 && P) CK(cudaMemcpy(quat4, h->quat.p, P * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+        if (mean3 && P) CK(cudaMemcpy(mean3, h->mean.p, P * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+        if (rgbmean3 && P) CK(cudaMemcpy(rgbmean3, h->rgbmean.p, P * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return GPC_OK;
+}
+
+int gpc_get_assignment(gpc_handle* h, int32_t* owner, int32_t* stream_index, double* x1, double* x2, double* y, int32_t* perm) {
+    if (!h) return GPC_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    const int64_t S = h->n_claimed;
+    if (owner || stream_index) {
+        if (!h->have_binning) return fail(h, GPC_ERR_STATE, "assignment needs a compress on this handle");
+        if (owner && h->n_in) CK(cudaMemcpy(owner, h->owner.p, h->n_in * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (stream_index && S) CK(cudaMemcpy(stream_index, h->st_idx.p, S * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    }
+    if (!h->have_fit && (x1 || x2 || y || perm)) return fail(h, GPC_ERR_STATE, "no stream held by the handle");
+    if (x1 && S) CK(cudaMemcpy(x1, h->x1.p, S * sizeof(double), cudaMemcpyDeviceToHost));
+    if (x2 && S) CK(cudaMemcpy(x2, h->x2.p, S * sizeof(double), cudaMemcpyDeviceToHost));
+    if (y && S) CK(cudaMemcpy(y, h->y.p, S * sizeof(double), cudaMemcpyDeviceToHost));
+    if (perm && h->s_count) {
+        // only this shard's range of the permutation is defined
+        std::memset(perm, 0xff, S * sizeof(int32_t));
+        CK(cudaMemcpy(perm + h->s_begin, h->perm.as<int32_t>() + h->s_begin, h->s_count * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    }
+    return GPC_OK;
+}
+
+int gpc_debug_exp(gpc_handle* h, const double* x, double* out, int64_t n) {
+    if (!h || n < 0 || (n > 0 && (!x || !out))) return GPC_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    if (n == 0) return GPC_OK;
+    CK(h->tmpA.reserve(n * sizeof(double)));
+    CK(h->tmpB.reserve(n * sizeof(double)));
+    CK(cudaMemcpyAsync(h->tmpA.p, x, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    launch_debug_exp(h->tmpA.as<double>(), h->tmpB.as<double>(), n, h->stream);
+    CK(cudaMemcpyAsync(out, h->tmpB.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    return GPC_OK;
+}
+
+int gpc_debug_rand(gpc_handle* h, uint64_t offset, int64_t n, uint32_t* out) {
+    if (!h || n < 0 || (n > 0 && !out)) return GPC_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    if (n == 0) return GPC_OK;
+    CK(h->tmpA.reserve(n * sizeof(uint32_t)));
+    launch_rand_stream(offset, n, h->tmpA.as<uint32_t>(), h->stream);
+    CK(cudaMemcpyAsync(out, h->tmpA.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    return GPC_OK;
+}
+
+}  // extern "C"

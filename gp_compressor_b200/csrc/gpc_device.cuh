@@ -1,0 +1,95 @@
+// gpc_device.cuh — device-side canonical arithmetic shared by every kernel.
+//
+// All translation units are compiled with -fmad=false: the compiler never contracts a*b+c,
+// every fused multiply-add is an explicit fma().  FP64 add/mul/fma/div/sqrt are IEEE
+// round-to-nearest on sm_100a, so a scalar CPU program performing the same operation
+// sequence produces the same bits (that program is the test oracle, which keeps its own
+// independent copy of these definitions).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gpc {
+
+// float literals of the reference widened to double (sparse_gp.hpp:124,146,229,236)
+__device__ __forceinline__ double tiny12() { return (double)1e-12f; }
+__device__ __forceinline__ double geo9() { return (double)1e-9f; }
+
+// Canonical exp: replaces glibc exp at rbf_kernel.cpp:17.  n = rint(x/ln2) by the
+// 1.5*2^52 trick, Cody-Waite reduction with two fma, degree-13 Taylor Horner with fma,
+// exponent insertion.  <= 1 ulp from libm.
+__device__ __forceinline__ double gpc_exp(double x) {
+    if (x != x) return x;
+    if (x > 709.0) return __longlong_as_double(0x7ff0000000000000LL);
+    if (x < -745.0) return 0.0;
+    const double INV_LN2 = 1.4426950408889634;
+    const double MAGIC = 6755399441055744.0;
+    const double LN2_HI = 0x1.62e42fefa39efp-1;
+    const double LN2_LO = 0x1.abc9e3b39803fp-56;
+    double t = __dmul_rn(x, INV_LN2);
+    double kd = __dadd_rn(t, MAGIC);
+    int n = (int)(unsigned int)(unsigned long long)__double_as_longlong(kd);
+    kd = __dadd_rn(kd, -MAGIC);
+    double r = fma(kd, -LN2_HI, x);
+    r = fma(kd, -LN2_LO, r);
+    double p = 1.0 / 6227020800.0;
+    p = fma(p, r, 1.0 / 479001600.0);
+    p = fma(p, r, 1.0 / 39916800.0);
+    p = fma(p, r, 1.0 / 3628800.0);
+    p = fma(p, r, 1.0 / 362880.0);
+    p = fma(p, r, 1.0 / 40320.0);
+    p = fma(p, r, 1.0 / 5040.0);
+    p = fma(p, r, 1.0 / 720.0);
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    int adj = 0;
+    if (n < -1020) { adj = 1; n += 1020; }
+    long long pb = __double_as_longlong(p) + ((long long)n << 52);
+    p = __longlong_as_double(pb);
+    if (adj) p = __dmul_rn(p, 0x1p-1020);
+    return p;
+}
+
+// rbf_kernel::kernel_function, rbf_kernel.cpp:15-18 : p0 * exp((-0.5f/p1) * ||xi-xj||^2)
+__device__ __forceinline__ double rbf(double x1, double x2, double b1, double b2, double p0, double cl) {
+    double d1 = __dadd_rn(x1, -b1), d2 = __dadd_rn(x2, -b2);
+    double sq = __dadd_rn(__dmul_rn(d1, d1), __dmul_rn(d2, d2));
+    return __dmul_rn(p0, gpc_exp(__dmul_rn(cl, sq)));
+}
+
+__device__ __forceinline__ double shfl_xor_d(double v, int off) {
+    return __shfl_xor_sync(0xffffffffu, v, off);
+}
+// 5-step xor butterfly; every lane ends with the same bits (a+b == b+a)
+__device__ __forceinline__ double butterfly32(double p) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) p = __dadd_rn(p, shfl_xor_d(p, off));
+    return p;
+}
+// canonical dot: 32 lane-strided fma partials + butterfly.  a, b in shared or global memory.
+__device__ __forceinline__ double warp_dot32(const double* a, const double* b, int n, int lane) {
+    double p = 0.0;
+    for (int j = lane; j < n; j += 32) p = fma(a[j], b[j], p);
+    return butterfly32(p);
+}
+// canonical row product: 4 strided fma partials, (a0+a1)+(a2+a3).  m[j*stride] is element j.
+__device__ __forceinline__ double row4(const double* m, int stride, const double* k, int n) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int j = 0;
+    for (; j + 3 < n; j += 4) {
+        a0 = fma(m[(size_t)j * stride], k[j], a0);
+        a1 = fma(m[(size_t)(j + 1) * stride], k[j + 1], a1);
+        a2 = fma(m[(size_t)(j + 2) * stride], k[j + 2], a2);
+        a3 = fma(m[(size_t)(j + 3) * stride], k[j + 3], a3);
+    }
+    if (j < n) a0 = fma(m[(size_t)j * stride], k[j], a0);
+    if (j + 1 < n) a1 = fma(m[(size_t)(j + 1) * stride], k[j + 1], a1);
+    if (j + 2 < n) a2 = fma(m[(size_t)(j + 2) * stride], k[j + 2], a2);
+    return __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
+}
+
+}  // namespace gpc

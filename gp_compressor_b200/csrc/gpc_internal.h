@@ -1,0 +1,115 @@
+// gpc_internal.h — handle layout and kernel launch prototypes (host side of libgpc_b200.so)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gpc.h"
+
+namespace gpc {
+
+extern thread_local uint64_t g_launches;  // kernels launched by the current API call
+
+struct BinningWork;                       // scratch of the binning stages (k_binning.cu)
+void binning_free(BinningWork* w);
+
+// Grow-only device buffer owned by the handle.
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// ---- K6: glibc rand stream + shuffle -------------------------------------------------
+struct RandTables {       // x^(2^k) mod (x^31 - x^28 - 1) over Z/2^32, k = 0..47, and r_0..r_60
+    uint32_t pow2[48][31];
+    uint32_t base[61];
+};
+void rand_tables_init(RandTables* t);                       // host, once per process
+cudaError_t rand_upload_tables(const RandTables* t);        // to __constant__
+// out[i] = rand() value number (offset + i), i < n
+void launch_rand_stream(uint64_t offset, int64_t n, uint32_t* out, cudaStream_t s);
+
+// ---- scans and small utilities ---------------------------------------------------------
+// exclusive scan of n int64 values; out has n+1 entries (out[n] = total). tmp >= scan_tmp_bytes(n)
+size_t scan_tmp_bytes(int64_t n);
+void launch_exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, void* tmp, cudaStream_t s);
+
+// ---- K6b/c: per-patch shuffle and gather into the fit stream -------------------------------
+// draws[p] = (n_p > 0 ? (n_p - 1) * mult : 0)
+void launch_patch_draws(const int64_t* off, int64_t n_patches, int mult, int64_t* draws, cudaStream_t s);
+// perm (patch-local) for every patch; rnd holds the stream starting at the handle's offset
+void launch_shuffle(const int64_t* off, int64_t n_patches, const int64_t* roff, const uint32_t* rnd,
+                    int do_shuffle, int32_t* perm, int32_t* patch_of, int64_t s_begin, int64_t s_count,
+                    cudaStream_t s);
+void launch_gather_stream(const int64_t* off, const int32_t* patch_of, const int32_t* perm, const double* x1,
+                          const double* x2, const double* y, int64_t s_begin, int64_t s_count, double* fx1,
+                          double* fx2, double* fy, cudaStream_t s);
+
+// ---- K7: SOGP fit ---------------------------------------------------------------------
+struct SogpArgs {
+    const int64_t* off;      // n_patches + 1 stream offsets (global patch numbering)
+    const double *fx1, *fx2, *fy;  // fit stream in add order (already shuffled)
+    const int32_t* forig;    // patch-local original position of each stream element
+    const int32_t* patch_ids;  // patches to process (nullptr: first_patch + blockIdx.x)
+    int64_t first_patch;
+    int n_work;              // number of CTAs
+    int ld;                  // storage leading dimension (N + 1 <= ld at all times)
+    int capacity;
+    double s20, eps_tol, p0, cl;
+    // outputs, indexed by (patch - out_first) * capacity
+    int64_t out_first;
+    int32_t* nbv;
+    int32_t* flags;
+    double *o_alpha, *o_b1, *o_b2;
+    int32_t* o_idx;
+    double *dumpC, *dumpQ;   // optional, (patch - out_first) * capacity^2
+    int32_t* queue;          // overflow queue for the next bucket (nullptr: overflow impossible)
+    int32_t* queue_count;
+    unsigned long long* stats;  // 11 counters, see gpc_stats
+};
+// bucket b supports ld <= {16, 32, 64, 118}
+int sogp_bucket_ld(int bucket);
+size_t sogp_smem_bytes(int ld);
+cudaError_t launch_sogp_fit(int bucket, const SogpArgs& a, cudaStream_t s);
+
+// ---- K8: grid prediction ----------------------------------------------------------------
+struct PredictArgs {
+    int64_t n_patches;           // patches of this shard
+    const int32_t* nbv;          // per patch
+    const int64_t* slot;         // exclusive scan of (nbv > 0), n_patches + 1
+    int stride;                  // parameter stride per patch (capacity)
+    const double *alpha, *b1, *b2;
+    const double *quat, *mean, *rgbmean;  // may be nullptr (identity frame)
+    double res;
+    int sz;
+    double p0, cl;
+    uint8_t* out32;              // may be nullptr
+    double* heights;             // may be nullptr
+};
+void launch_flag_nonempty(const int32_t* nbv, int64_t n, int64_t* flags, cudaStream_t s);
+void launch_predict_grid(const PredictArgs& a, cudaStream_t s);
+void launch_predict_points(const double* alpha, const double* b1, const double* b2, int N, const double* C,
+                           double p0, double cl, double s20, const double* X, int64_t m, double* f,
+                           double* sigma, cudaStream_t s);
+void launch_debug_exp(const double* x, double* out, int64_t n, cudaStream_t s);
+
+}  // namespace gpc

@@ -1,0 +1,198 @@
+// k_util.cu — scans, the per-patch shuffle (K6b) and the gather into the fit stream (K6c).
+#include "gpc_device.cuh"
+#include "gpc_internal.h"
+
+namespace gpc {
+
+// ------------------------------------------------------------------------------------
+// Exclusive scan of int64 (three launches: tile sums, scan of sums, apply).
+// ------------------------------------------------------------------------------------
+constexpr int SCAN_T = 256;
+constexpr int SCAN_E = 8;
+constexpr int SCAN_TILE = SCAN_T * SCAN_E;
+
+__device__ inline int64_t block_exclusive_scan(int64_t v, int64_t* total) {
+    __shared__ int64_t warp_sums[SCAN_T / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int64_t x = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        int64_t y = __shfl_up_sync(0xffffffffu, x, off);
+        if (lane >= off) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        int64_t s = (lane < SCAN_T / 32) ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            int64_t y = __shfl_up_sync(0xffffffffu, s, off);
+            if (lane >= off) s += y;
+        }
+        if (lane < SCAN_T / 32) warp_sums[lane] = s;
+    }
+    __syncthreads();
+    int64_t base = (wid > 0) ? warp_sums[wid - 1] : 0;
+    *total = warp_sums[SCAN_T / 32 - 1];
+    __syncthreads();
+    return base + x - v;
+}
+
+__global__ void __launch_bounds__(SCAN_T) scan_tile_sums(const int64_t* __restrict__ in, int64_t n, int64_t* __restrict__ sums) {
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_E;
+    int64_t s = 0;
+#pragma unroll
+    for (int e = 0; e < SCAN_E; e++)
+        if (base + e < n) s += in[base + e];
+    int64_t total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_T) scan_sums_inplace(int64_t* sums, int64_t n_tiles, int64_t* grand_total) {
+    int64_t carry = 0;
+    for (int64_t b = 0; b < n_tiles; b += SCAN_T) {
+        int64_t i = b + threadIdx.x;
+        int64_t v = (i < n_tiles) ? sums[i] : 0;
+        int64_t total;
+        int64_t ex = block_exclusive_scan(v, &total);
+        if (i < n_tiles) sums[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *grand_total = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_T) scan_apply(const int64_t* __restrict__ in, int64_t n, const int64_t* __restrict__ sums,
+                                                     int64_t* __restrict__ out) {
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_E;
+    int64_t v[SCAN_E];
+    int64_t s = 0;
+#pragma unroll
+    for (int e = 0; e < SCAN_E; e++) {
+        v[e] = (base + e < n) ? in[base + e] : 0;
+        s += v[e];
+    }
+    int64_t total;
+    int64_t ex = block_exclusive_scan(s, &total) + sums[blockIdx.x];
+#pragma unroll
+    for (int e = 0; e < SCAN_E; e++) {
+        if (base + e < n) out[base + e] = ex;
+        ex += v[e];
+    }
+}
+
+size_t scan_tmp_bytes(int64_t n) {
+    int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    return (size_t)(tiles + 1) * sizeof(int64_t);
+}
+
+void launch_exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, void* tmp, cudaStream_t s) {
+    if (n <= 0) {
+        cudaMemsetAsync(out, 0, sizeof(int64_t), s);
+        return;
+    }
+    int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    int64_t* sums = reinterpret_cast<int64_t*>(tmp);
+    scan_tile_sums<<<(unsigned)tiles, SCAN_T, 0, s>>>(in, n, sums);
+    scan_sums_inplace<<<1, SCAN_T, 0, s>>>(sums, tiles, out + n);
+    scan_apply<<<(unsigned)tiles, SCAN_T, 0, s>>>(in, n, sums, out);
+}
+
+// ------------------------------------------------------------------------------------
+// rand() draws per patch: the height GP shuffles n_p points with n_p - 1 draws, then the
+// RGB field GP does the same (gp_compressor.cpp:162-163), so mult = 2 in the full path.
+// ------------------------------------------------------------------------------------
+__global__ void patch_draws_kernel(const int64_t* __restrict__ off, int64_t n_patches, int mult, int64_t* __restrict__ draws) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_patches) return;
+    int64_t n = off[p + 1] - off[p];
+    draws[p] = (n > 0) ? (n - 1) * mult : 0;
+}
+void launch_patch_draws(const int64_t* off, int64_t n_patches, int mult, int64_t* draws, cudaStream_t s) {
+    if (n_patches <= 0) return;
+    patch_draws_kernel<<<(unsigned)((n_patches + 255) / 256), 256, 0, s>>>(off, n_patches, mult, draws);
+}
+
+// patch_of[s] = the patch whose range holds stream element s; perm[s] = identity (patch-local)
+// (off points at the first patch of the shard; stream indices stay absolute)
+__global__ void patch_of_kernel(const int64_t* __restrict__ off, int64_t n_patches, int64_t s_begin, int64_t s_count,
+                                int32_t* __restrict__ patch_of, int32_t* __restrict__ perm) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= s_count) return;
+    s += s_begin;
+    // last p with off[p] <= s
+    int64_t lo = 0, hi = n_patches;  // invariant: off[lo] <= s < off[hi]
+    while (hi - lo > 1) {
+        int64_t mid = (lo + hi) >> 1;
+        if (off[mid] <= s) lo = mid; else hi = mid;
+    }
+    patch_of[s] = (int32_t)lo;
+    perm[s] = (int32_t)(s - off[lo]);
+}
+
+// sparse_gp::shuffle, sparse_gp.hpp:42-56: for i = n-1..1: r = rand() % i; swap(ind[i], ind[r]).
+// One thread per patch (the swap chain is sequential); rnd[roff[p] - roff0 + t] is draw t.
+__global__ void shuffle_kernel(const int64_t* __restrict__ off, int64_t n_patches, const int64_t* __restrict__ roff,
+                               const uint32_t* __restrict__ rnd, int32_t* __restrict__ perm) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_patches) return;
+    const int64_t o = off[p];
+    const int n = (int)(off[p + 1] - o);
+    if (n < 2) return;
+    const uint32_t* r = rnd + (roff[p] - roff[0]);
+    int32_t* ind = perm + o;
+    for (int i = n - 1; i > 0; --i) {
+        uint32_t rr = r[n - 1 - i] % (uint32_t)i;
+        int32_t a = ind[i], b = ind[rr];
+        ind[i] = b;
+        ind[rr] = a;
+    }
+}
+
+void launch_shuffle(const int64_t* off, int64_t n_patches, const int64_t* roff, const uint32_t* rnd, int do_shuffle,
+                    int32_t* perm, int32_t* patch_of, int64_t s_begin, int64_t s_count, cudaStream_t s) {
+    if (s_count <= 0 || n_patches <= 0) return;
+    patch_of_kernel<<<(unsigned)((s_count + 255) / 256), 256, 0, s>>>(off, n_patches, s_begin, s_count, patch_of, perm);
+    if (do_shuffle) shuffle_kernel<<<(unsigned)((n_patches + 127) / 128), 128, 0, s>>>(off, n_patches, roff, rnd, perm);
+}
+
+// fit stream in add order: element t of patch p is point perm[off[p] + t]
+__global__ void gather_stream_kernel(const int64_t* __restrict__ off, const int32_t* __restrict__ patch_of,
+                                     const int32_t* __restrict__ perm, const double* __restrict__ x1,
+                                     const double* __restrict__ x2, const double* __restrict__ y, int64_t s_begin,
+                                     int64_t s_count, double* __restrict__ fx1, double* __restrict__ fx2,
+                                     double* __restrict__ fy) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= s_count) return;
+    s += s_begin;
+    int64_t src = off[patch_of[s]] + perm[s];
+    fx1[s] = x1[src];
+    fx2[s] = x2[src];
+    fy[s] = y[src];
+}
+void launch_gather_stream(const int64_t* off, const int32_t* patch_of, const int32_t* perm, const double* x1,
+                          const double* x2, const double* y, int64_t s_begin, int64_t s_count, double* fx1, double* fx2,
+                          double* fy, cudaStream_t s) {
+    if (s_count <= 0) return;
+    gather_stream_kernel<<<(unsigned)((s_count + 255) / 256), 256, 0, s>>>(off, patch_of, perm, x1, x2, y, s_begin, s_count, fx1, fx2, fy);
+}
+
+__global__ void flag_nonempty_kernel(const int32_t* __restrict__ nbv, int64_t n, int64_t* __restrict__ flags) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = nbv[i] > 0 ? 1 : 0;
+}
+void launch_flag_nonempty(const int32_t* nbv, int64_t n, int64_t* flags, cudaStream_t s) {
+    if (n <= 0) return;
+    flag_nonempty_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(nbv, n, flags);
+}
+
+__global__ void debug_exp_kernel(const double* __restrict__ x, double* __restrict__ out, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = gpc_exp(x[i]);
+}
+void launch_debug_exp(const double* x, double* out, int64_t n, cudaStream_t s) {
+    if (n <= 0) return;
+    debug_exp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, out, n);
+}
+
+}  // namespace gpc

@@ -1,0 +1,146 @@
+/* gpc.h — C ABI of libgpc_b200.so, the B200 (sm_100a) implementation of the
+ * gp_compressor compress / decompress hot path.
+ *
+ * The reference (nilsbore/gp_compressor, /root/reference) has no FFI or plugin layer: the
+ * boundary of this path is the public surface of three C++ classes.  Each entry point
+ * below names the reference member it replaces (file:line under /root/reference/src).
+ * Plain pointers and sizes only; the caller owns every host buffer, the handle owns all
+ * device memory and streams; no allocation crosses the ABI.  There is no CPU fallback:
+ * every compute entry point fails with GPC_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Point clouds are arrays of PCL PointXYZRGB records, 32 bytes each:
+ *   float x, y, z, 1.0f | uint8 b, g, r, a | 12 bytes padding.
+ *
+ * Threading: one handle = one host thread = one CUDA device (gpc_config.device).
+ * Multi-GPU runs use one process (or thread) and one handle per GPU; patches shard with
+ * gpc_config.shard_rank / shard_count and no collective.
+ */
+#ifndef GPC_H
+#define GPC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPC_OK 0
+#define GPC_ERR_INVALID 1   /* bad argument / unsupported configuration */
+#define GPC_ERR_CUDA 2      /* CUDA runtime failure or no usable device  */
+#define GPC_ERR_STATE 3     /* call sequence error (e.g. decompress before compress) */
+#define GPC_ERR_OVERFLOW 4  /* octree deeper than 21 levels (63-bit Morton code)     */
+
+#define GPC_POINT_BYTES 32
+
+typedef struct gpc_handle gpc_handle;
+
+/* Constructor arguments of the reference classes on this path, plus the knobs the
+ * reference hard-codes.  gpc_config_default() fills the reference's values. */
+typedef struct gpc_config {
+    double res;         /* gp_compressor(cloud, res, sz): voxel size, gp_compressor.h:65 (default 0.1f) */
+    int32_t sz;         /* gp_compressor(cloud, res, sz): grid side at decode, gp_compressor.h:65 (10)  */
+    int32_t capacity;   /* sparse_gp(capacity, s0): max basis vectors, sparse_gp.h:48 (100)             */
+    double s0;          /* sparse_gp(capacity, s0): noise variance s20, sparse_gp.h:48 (1e-1f)          */
+    double eps_tol;     /* sparse_gp ctor literal, sparse_gp.hpp:31 (1e-6f)                             */
+    double sigmaf_sq;   /* rbf_kernel(sigmaf_sq, l_sq), rbf_kernel.h:24 (100)                           */
+    double l_sq;        /* rbf_kernel(sigmaf_sq, l_sq), rbf_kernel.h:24 (1)                             */
+    int32_t leaf_order; /* 0: reverse Morton (PCL 1.7/1.8 leaf iterator), 1: Morton (PCL >= 1.9)        */
+    int32_t shuffle;    /* 1: sparse_gp::shuffle before adding (sparse_gp.hpp:62-63); 0: input order    */
+    int32_t rgb_rand;   /* 1: skip the rand() draws the RGB field GP consumes (gp_compressor.cpp:163)   */
+    int32_t device;     /* CUDA device ordinal                                                          */
+    int32_t shard_rank; /* this handle fits / decodes patches of shard shard_rank ...                   */
+    int32_t shard_count;/* ... out of shard_count contiguous ranges of the patch visiting order (1)     */
+    int32_t keep_state; /* 1: keep dense C and Q per patch (gpc_get_state, predictive variance)         */
+} gpc_config;
+
+typedef struct gpc_sizes {
+    int64_t n_in;        /* points given to the last compress                                  */
+    int64_t n_patches;   /* octree leaves = patches (gp_compressor.cpp:182), all shards        */
+    int64_t n_claimed;   /* points claimed by some patch (gp_compressor.cpp:88-97)             */
+    int64_t n_bv_total;  /* sum of basis-vector counts over this shard's patches               */
+    int64_t patch_lo;    /* first patch (gp_index) of this shard                               */
+    int64_t patch_hi;    /* one past the last patch of this shard                              */
+    int64_t n_decoded;   /* points produced by the last decompress                             */
+    uint64_t rand_offset;/* rand() draws consumed so far by this handle                        */
+    double lattice_min[3]; /* octree bounding-box minimum (PCL min_x_/min_y_/min_z_)           */
+    uint32_t depth;      /* octree depth                                                       */
+    uint32_t pad;
+} gpc_sizes;
+
+/* Event counters of the SOGP fit (the flop / byte accounting of DESIGN.md uses them) and
+ * per-stage device times of the last call, in milliseconds (CUDA events). */
+typedef struct gpc_stats {
+    uint64_t n_add, n_first, n_sparse, n_full, n_del_cap, n_del_geo;
+    uint64_t sum_n, sum_n2_common, sum_n2_sparse, sum_n2_full, sum_n2_del;
+    uint64_t escalated[4];      /* patches that left SOGP bucket b for a larger one */
+    uint64_t kernel_launches;   /* kernels launched by the last compress / decompress */
+    float ms_h2d, ms_lattice, ms_keys, ms_sort, ms_leaves, ms_rotation, ms_claim, ms_group,
+          ms_shuffle, ms_fit, ms_d2h, ms_predict, ms_total;
+} gpc_stats;
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+int gpc_config_default(gpc_config* cfg);
+int gpc_create(const gpc_config* cfg, gpc_handle** out);     /* gp_compressor ctor, gp_compressor.cpp:12-19 */
+void gpc_destroy(gpc_handle* h);
+const char* gpc_last_error(const gpc_handle* h);             /* replaces print + exit(0), gp_compressor.cpp:136-139 */
+const char* gpc_version(void);
+
+/* ---- compress: gp_compressor::save_compressed, gp_compressor.cpp:21-27 ---------------
+ * = project_cloud (:177-249) + train_processes (:121-175).  Host buffer in; the timed
+ * end-to-end call.  gpc_upload_cloud + gpc_compress_resident split the same work so that
+ * the device part can be timed with the cloud already in HBM. */
+int gpc_compress(gpc_handle* h, const void* cloud32_host, int64_t n_points);
+int gpc_upload_cloud(gpc_handle* h, const void* cloud32_host, int64_t n_points);
+int gpc_compress_resident(gpc_handle* h);
+
+/* ---- sparse_gp<rbf_kernel,gaussian_noise>::add_measurements, sparse_gp.hpp:59-86 ------
+ * on n_patches independent processes at once: patch p owns rows off[p]..off[p+1] of
+ * X = (x1, x2) and y.  Includes the shuffle (rand stream continues from the handle's
+ * offset).  Replaces any previous fit held by the handle. */
+int gpc_fit_patches(gpc_handle* h, int64_t n_patches, const int64_t* off,
+                    const double* x1, const double* x2, const double* y);
+
+/* ---- decompress: gp_compressor::load_compressed, gp_compressor.cpp:267-386 ------------
+ * Writes sz*sz points per non-empty patch, patches in gp_index order.  out may be NULL
+ * (device-only run, result stays in HBM).  capacity_points guards the host buffer. */
+int gpc_decompress(gpc_handle* h, void* out_cloud32_host, int64_t capacity_points, int64_t* n_out);
+int gpc_decompress_resident(gpc_handle* h, int64_t* n_out);
+/* f* of sparse_gp::predict_measurements for every grid point of the last decompress */
+int gpc_get_heights(gpc_handle* h, double* heights_host, int64_t capacity);
+
+/* ---- sparse_gp::predict_measurements, sparse_gp.hpp:299-351 ---------------------------
+ * on one patch (gp_index) at m arbitrary local coordinates X (m x 2, row-major).
+ * sigma may be NULL; when given it needs keep_state (conf = false branch, :346). */
+int gpc_predict(gpc_handle* h, int64_t patch, const double* X, int64_t m, double* f, double* sigma);
+
+/* ---- results ---------------------------------------------------------------------------
+ * Any output pointer may be NULL.  Per-patch arrays are indexed by gp_index over ALL
+ * patches (frames are computed on every shard); fitted parameters cover this shard only
+ * and are addressed relative to patch_lo. */
+int gpc_get_sizes(gpc_handle* h, gpc_sizes* s);
+int gpc_get_stats(gpc_handle* h, gpc_stats* s);
+/* rotations / means / RGB_means (gp_compressor.h:36-40), leaf keys and centres */
+int gpc_get_patches(gpc_handle* h, uint64_t* code, float* center3, int32_t* n_candidates,
+                    double* R9, double* quat4, double* mean3, double* rgbmean3, int64_t* patch_off);
+/* owner[i] = gp_index of the patch that claimed input point i, or -1;  stream arrays in
+ * patch-major claim order: original index and local (x1, x2, y) of gp_compressor.cpp:146-155 */
+int gpc_get_assignment(gpc_handle* h, int32_t* owner, int32_t* stream_index,
+                       double* x1, double* x2, double* y, int32_t* perm);
+/* alpha, BV (sparse_gp.h:22,26) per patch: bv_off has (patch_hi - patch_lo + 1) entries */
+int gpc_get_params(gpc_handle* h, int32_t* nbv, int64_t* bv_off, int32_t* bv_index,
+                   double* bv1, double* bv2, double* alpha, int32_t* flags);
+int gpc_get_state(gpc_handle* h, int64_t patch, double* C, double* Q);  /* N x N, row-major */
+/* decode-only use: install fitted parameters (and optionally frames) from the host */
+int gpc_set_params(gpc_handle* h, int64_t n_patches, const int32_t* nbv, const double* bv1,
+                   const double* bv2, const double* alpha, const double* quat4,
+                   const double* mean3, const double* rgbmean3);
+int gpc_set_rand_offset(gpc_handle* h, uint64_t offset);
+
+/* ---- test hooks: the device versions of the canonical primitives ----------------------- */
+int gpc_debug_exp(gpc_handle* h, const double* x, double* out, int64_t n);
+int gpc_debug_rand(gpc_handle* h, uint64_t offset, int64_t n, uint32_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPC_H */
