@@ -1,8 +1,11 @@
 // gpc_api.cu — the extern "C" layer of libgpc_b200.so (see include/gpc.h).
 // Host-side orchestration only: buffer management, stage sequencing, sharding, timing.
 // All arithmetic of the path runs in the kernels of k_*.cu; there is no CPU fallback.
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 
 #include "gpc_internal.h"
 
@@ -33,8 +36,10 @@ struct gpc_handle {
     DevBuf nonempty, slot, out32, heights;
     DevBuf quat, mean, rgbmean, Rm, center, code, ncand, owner, st_idx;
     DevBuf tmpA, tmpB, tmpC;
+    // binning scratch
+    DevBuf keys, keys2, vals, vals2, ovals, ovals2, sort_tmp, flags64, ex, leaf_of, leaf_start, leaf_code_a, spt, nbr, nnbr,
+        center_a, Rm_a, ncand_a, pt0, pt1, pt2, hbuf, rgb;
     std::vector<cudaEvent_t> ev;
-    BinningWork* bw = nullptr;
 };
 
 namespace {
@@ -271,6 +276,224 @@ int run_decode(gpc_handle* h, bool want_cloud, bool want_heights, StageTimer& tm
     return GPC_OK;
 }
 
+// ---- PCL OctreePointCloud::adoptBoundingBoxToPoint / getKeyBitSize for one point [RECALLED PCL 1.7] ----
+// Scalar control logic on the host (a handful of doubles per growth event); the search for the
+// point that triggers each event runs on the device (first_violation_kernel).
+struct HostLattice {
+    double mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
+    double res = 0;
+    unsigned depth = 0;
+    bool defined = false;
+};
+
+void lattice_adopt(HostLattice& L, const float* p) {
+    const float minValue = std::numeric_limits<float>::epsilon();
+    for (;;) {
+        bool lo[3], up[3];
+        for (int a = 0; a < 3; a++) { lo[a] = (double)p[a] < L.mn[a]; up[a] = (double)p[a] >= L.mx[a]; }
+        if (L.defined && !(lo[0] || lo[1] || lo[2] || up[0] || up[1] || up[2])) break;
+        if (L.defined) {
+            double side = (double)(1u << L.depth) * L.res;
+            for (int a = 0; a < 3; a++)
+                if (!up[a]) L.mn[a] -= side;
+            L.depth++;
+            side = (double)(1u << L.depth) * L.res - minValue;
+            for (int a = 0; a < 3; a++) L.mx[a] = L.mn[a] + side;
+            if (L.depth > 30) break;
+        } else {
+            for (int a = 0; a < 3; a++) { L.mn[a] = (double)p[a] - L.res / 2; L.mx[a] = (double)p[a] + L.res / 2; }
+            unsigned mk[3];
+            for (int a = 0; a < 3; a++) mk[a] = (unsigned)((L.mx[a] - L.mn[a]) / L.res);
+            unsigned maxv = std::max(std::max(std::max(mk[0], mk[1]), mk[2]), 2u);
+            L.depth = (unsigned)std::ceil(std::log((double)maxv) / std::log(2.0) - minValue);
+            double side = (double)(1u << L.depth) * L.res - minValue;
+            for (int a = 0; a < 3; a++) {
+                double over = (side - (L.mx[a] - L.mn[a])) / 2.0;
+                L.mn[a] -= over;
+                L.mx[a] += over;
+            }
+            L.defined = true;
+        }
+    }
+}
+
+LatticeDev to_dev(const HostLattice& L) {
+    LatticeDev d;
+    for (int a = 0; a < 3; a++) { d.mn[a] = L.mn[a]; d.mx[a] = L.mx[a]; }
+    d.res = L.res;
+    d.depth = L.depth;
+    return d;
+}
+
+int bits_for(uint64_t v) {  // bits needed to represent values 0..v
+    int b = 1;
+    while (b < 64 && (v >> b)) b++;
+    return b;
+}
+
+// project_cloud (gp_compressor.cpp:177-249) on the resident cloud: fills off/x1/x2/y and frames.
+int run_binning(gpc_handle* h, StageTimer& tm) {
+    const gpc_config& c = h->cfg;
+    cudaStream_t st = h->stream;
+    const int64_t n = h->n_in;
+    const uint8_t* cloud = h->cloud.as<uint8_t>();
+    if (n > 0x7fffffff) return fail(h, GPC_ERR_INVALID, "more than 2^31-1 points");
+    h->have_binning = h->have_frames = h->have_fit = false;
+    CK(h->small.reserve(64));
+    unsigned long long* d_best = h->small.as<unsigned long long>();
+    unsigned long long* d_nvalid = d_best + 1;
+    // ---- lattice replay ----
+    size_t t0 = tm.mark();
+    HostLattice L;
+    L.res = c.res;
+    int64_t start = 0;
+    for (;;) {
+        launch_first_violation(cloud, n, start, to_dev(L), L.defined ? 1 : 0, d_best, st);
+        unsigned long long best = 0;
+        CK(cudaMemcpyAsync(&best, d_best, sizeof(best), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (best == ~0ull) break;
+        float p[4];
+        CK(cudaMemcpyAsync(p, cloud + (int64_t)best * GPC_POINT_BYTES, sizeof(p), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        lattice_adopt(L, p);
+        if (L.depth > 21) return fail(h, GPC_ERR_OVERFLOW, "octree deeper than 21 levels: res too small for the cloud extent");
+        start = (int64_t)best + 1;
+    }
+    h->depth = L.depth;
+    for (int a = 0; a < 3; a++) h->lattice_min[a] = L.mn[a];
+    size_t t1 = tm.mark();
+    tm.span(&h->stats.ms_lattice, t0, t1);
+    h->n_patches = 0;
+    h->n_claimed = 0;
+    CK(h->off.reserve(2 * sizeof(int64_t)));
+    CK(h->owner.reserve(std::max<int64_t>(n, 1) * sizeof(int32_t)));
+    if (n > 0) CK(cudaMemsetAsync(h->owner.p, 0xff, n * sizeof(int32_t), st));
+    if (!L.defined) {  // no finite point: no leaves
+        CK(cudaMemsetAsync(h->off.p, 0, sizeof(int64_t), st));
+        h->have_binning = h->have_frames = true;
+        return GPC_OK;
+    }
+    const LatticeDev lat = to_dev(L);
+    // ---- keys + Morton sort ----
+    CK(h->keys.reserve(n * sizeof(uint64_t)));
+    CK(h->keys2.reserve(n * sizeof(uint64_t)));
+    CK(h->vals.reserve(n * sizeof(uint32_t)));
+    CK(h->vals2.reserve(n * sizeof(uint32_t)));
+    CK(h->sort_tmp.reserve(radix_sort_tmp_bytes(n)));
+    launch_point_keys(cloud, n, lat, h->keys.as<uint64_t>(), h->vals.as<uint32_t>(), d_nvalid, st);
+    size_t t2 = tm.mark();
+    tm.span(&h->stats.ms_keys, t1, t2);
+    int which = launch_radix_sort(h->keys.as<uint64_t>(), h->vals.as<uint32_t>(), h->keys2.as<uint64_t>(), h->vals2.as<uint32_t>(), n,
+                                  3 * (int)L.depth + 1, h->sort_tmp.p, st);
+    uint64_t* skeys = which ? h->keys2.as<uint64_t>() : h->keys.as<uint64_t>();
+    uint32_t* svals = which ? h->vals2.as<uint32_t>() : h->vals.as<uint32_t>();
+    uint64_t* fkeys = which ? h->keys.as<uint64_t>() : h->keys2.as<uint64_t>();  // free buffer for the owner keys
+    size_t t3 = tm.mark();
+    tm.span(&h->stats.ms_sort, t2, t3);
+    unsigned long long nv = 0;
+    CK(cudaMemcpyAsync(&nv, d_nvalid, sizeof(nv), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int64_t n_valid = (int64_t)nv;
+    // ---- leaves ----
+    CK(h->flags64.reserve(n_valid * sizeof(int64_t)));
+    CK(h->ex.reserve((n_valid + 1) * sizeof(int64_t)));
+    CK(h->scan_tmp.reserve(scan_tmp_bytes(n_valid)));
+    launch_mark_heads(skeys, n_valid, h->flags64.as<int64_t>(), st);
+    launch_exclusive_scan_i64(h->flags64.as<int64_t>(), h->ex.as<int64_t>(), n_valid, h->scan_tmp.p, st);
+    g_launches += 3;
+    int64_t P = 0;
+    CK(cudaMemcpyAsync(&P, h->ex.as<int64_t>() + n_valid, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    h->n_patches = P;
+    CK(h->leaf_of.reserve(n_valid * sizeof(int32_t)));
+    CK(h->leaf_start.reserve((P + 1) * sizeof(int64_t)));
+    CK(h->leaf_code_a.reserve(P * sizeof(uint64_t)));
+    CK(h->spt.reserve(n_valid * 16));
+    launch_fill_leaves(skeys, svals, h->ex.as<int64_t>(), n_valid, cloud, h->leaf_of.as<int32_t>(), h->leaf_start.as<int64_t>(),
+                       h->leaf_code_a.as<uint64_t>(), h->spt.p, st);
+    size_t t4 = tm.mark();
+    tm.span(&h->stats.ms_leaves, t3, t4);
+    // ---- neighbours + rotation ----
+    CK(h->nbr.reserve(P * 27 * sizeof(int32_t)));
+    CK(h->nnbr.reserve(P * sizeof(int32_t)));
+    CK(h->center_a.reserve(P * 3 * sizeof(float)));
+    CK(h->Rm_a.reserve(P * 9 * sizeof(double)));
+    CK(h->ncand_a.reserve(P * sizeof(int32_t)));
+    const double radius = (double)(std::sqrt(3.0f) / 2.0f) * c.res;  // gp_compressor.cpp:194
+    const double r2 = radius * radius;
+    const double half = c.res / 2.0f;                                // gp_compressor.cpp:85
+    launch_leaf_neighbours(h->leaf_code_a.as<uint64_t>(), P, lat, h->nbr.as<int32_t>(), h->nnbr.as<int32_t>(), h->center_a.as<float>(), st);
+    launch_leaf_rotation(h->spt.p, h->leaf_start.as<int64_t>(), h->nbr.as<int32_t>(), h->nnbr.as<int32_t>(), h->center_a.as<float>(), P,
+                         r2, h->Rm_a.as<double>(), h->ncand_a.as<int32_t>(), st);
+    size_t t5 = tm.mark();
+    tm.span(&h->stats.ms_rotation, t4, t5);
+    // ---- claim ----
+    CK(h->ovals.reserve(n_valid * sizeof(uint32_t)));
+    CK(h->ovals2.reserve(n_valid * sizeof(uint32_t)));
+    CK(h->pt0.reserve(n_valid * sizeof(double)));
+    CK(h->pt1.reserve(n_valid * sizeof(double)));
+    CK(h->pt2.reserve(n_valid * sizeof(double)));
+    launch_claim(h->spt.p, h->leaf_of.as<int32_t>(), h->nbr.as<int32_t>(), h->nnbr.as<int32_t>(), h->center_a.as<float>(),
+                 h->Rm_a.as<double>(), h->ncand_a.as<int32_t>(), n_valid, P, r2, half, c.leaf_order, fkeys, h->ovals.as<uint32_t>(),
+                 h->pt0.as<double>(), h->pt1.as<double>(), h->pt2.as<double>(), st);
+    size_t t6 = tm.mark();
+    tm.span(&h->stats.ms_claim, t5, t6);
+    // ---- group by owner (stable) ----
+    // the Morton-sorted keys are dead now (leaf codes extracted): reuse their buffer as the sort's second key buffer
+    int which2 = launch_radix_sort(fkeys, h->ovals.as<uint32_t>(), skeys, h->ovals2.as<uint32_t>(), n_valid, bits_for((uint64_t)P),
+                                   h->sort_tmp.p, st);
+    const uint64_t* gkeys = which2 ? skeys : fkeys;
+    const uint32_t* gvals = which2 ? h->ovals2.as<uint32_t>() : h->ovals.as<uint32_t>();
+    size_t t7 = tm.mark();
+    tm.span(&h->stats.ms_sort, t6, t7);
+    CK(h->off.reserve((P + 1) * sizeof(int64_t)));
+    launch_patch_bounds(gkeys, n_valid, P, h->off.as<int64_t>(), st);
+    int64_t S = 0;
+    CK(cudaMemcpyAsync(&S, h->off.as<int64_t>() + P, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    h->n_claimed = S;
+    const int64_t Sa = std::max<int64_t>(S, 1);
+    CK(h->st_idx.reserve(Sa * sizeof(int32_t)));
+    CK(h->hbuf.reserve(Sa * sizeof(double)));
+    CK(h->x1.reserve(Sa * sizeof(double)));
+    CK(h->x2.reserve(Sa * sizeof(double)));
+    CK(h->y.reserve(Sa * sizeof(double)));
+    CK(h->rgb.reserve(Sa * sizeof(uint32_t)));
+    launch_group_gather(gkeys, gvals, svals, h->spt.p, h->pt0.as<double>(), h->pt1.as<double>(), h->pt2.as<double>(), S,
+                        h->st_idx.as<int32_t>(), h->hbuf.as<double>(), h->x1.as<double>(), h->x2.as<double>(), h->rgb.as<uint32_t>(),
+                        h->owner.as<int32_t>(), st);
+    CK(h->code.reserve(P * sizeof(uint64_t)));
+    CK(h->center.reserve(P * 3 * sizeof(float)));
+    CK(h->ncand.reserve(P * sizeof(int32_t)));
+    CK(h->Rm.reserve(P * 9 * sizeof(double)));
+    CK(h->quat.reserve(P * 4 * sizeof(double)));
+    CK(h->mean.reserve(P * 3 * sizeof(double)));
+    CK(h->rgbmean.reserve(P * 3 * sizeof(double)));
+    launch_patch_frames(h->off.as<int64_t>(), P, c.leaf_order, h->hbuf.as<double>(), h->rgb.as<uint32_t>(), h->leaf_code_a.as<uint64_t>(),
+                        h->center_a.as<float>(), h->Rm_a.as<double>(), h->ncand_a.as<int32_t>(), h->y.as<double>(),
+                        h->code.as<uint64_t>(), h->center.as<float>(), h->ncand.as<int32_t>(), h->Rm.as<double>(),
+                        h->quat.as<double>(), h->mean.as<double>(), h->rgbmean.as<double>(), st);
+    size_t t8 = tm.mark();
+    tm.span(&h->stats.ms_group, t7, t8);
+    CK(cudaGetLastError());
+    h->have_binning = h->have_frames = true;
+    return GPC_OK;
+}
+
+int compress_resident_impl(gpc_handle* h, StageTimer& tm) {
+    int rc = run_binning(h, tm);
+    if (rc) return rc;
+    if (h->n_patches == 0) {
+        h->patch_lo = h->patch_hi = 0;
+        h->s_begin = h->s_count = 0;
+        h->have_fit = true;
+        h->n_bv_total = 0;
+        return GPC_OK;
+    }
+    return run_fit(h, tm);
+}
+
 }  // namespace
 
 extern "C" {
@@ -328,9 +551,10 @@ void gpc_destroy(gpc_handle* h) {
                       &h->roff, &h->rnd, &h->scan_tmp, &h->small, &h->nbv, &h->flags, &h->alpha, &h->b1, &h->b2, &h->bidx,
                       &h->dumpC, &h->dumpQ, &h->queue0, &h->queue1, &h->qcount, &h->kstats, &h->nonempty, &h->slot, &h->out32,
                       &h->heights, &h->quat, &h->mean, &h->rgbmean, &h->Rm, &h->center, &h->code, &h->ncand, &h->owner,
-                      &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC};
+                      &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
+                      &h->ovals2, &h->sort_tmp, &h->flags64, &h->ex, &h->leaf_of, &h->leaf_start, &h->leaf_code_a, &h->spt,
+                      &h->nbr, &h->nnbr, &h->center_a, &h->Rm_a, &h->ncand_a, &h->pt0, &h->pt1, &h->pt2, &h->hbuf, &h->rgb};
     for (DevBuf* b : bufs) b->release();
-    binning_free(h->bw);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -398,13 +622,44 @@ int gpc_upload_cloud(gpc_handle* h, const void* cloud, int64_t n) {
 int gpc_compress_resident(gpc_handle* h) {
     if (!h) return GPC_ERR_INVALID;
     if (!h->have_cloud) return fail(h, GPC_ERR_STATE, "gpc_compress_resident before gpc_upload_cloud");
-    return fail(h, GPC_ERR_STATE, "binning stages not built yet");
+    CK(cudaSetDevice(h->cfg.device));
+    reset_stats(h);
+    StageTimer tm(h);
+    size_t tA = tm.mark();
+    int rc = compress_resident_impl(h, tm);
+    if (rc) return rc;
+    size_t tB = tm.mark();
+    tm.span(&h->stats.ms_total, tA, tB);
+    if (h->n_patches > 0 && (rc = read_fit_stats(h))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    tm.resolve();
+    h->stats.kernel_launches = g_launches;
+    return GPC_OK;
 }
 
 int gpc_compress(gpc_handle* h, const void* cloud, int64_t n) {
-    int rc = gpc_upload_cloud(h, cloud, n);
+    if (!h || n < 0 || (n > 0 && !cloud)) return GPC_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    reset_stats(h);
+    StageTimer tm(h);
+    size_t tA = tm.mark();
+    CK(h->cloud.reserve(std::max<int64_t>(n, 1) * GPC_POINT_BYTES));
+    if (n > 0) CK(cudaMemcpyAsync(h->cloud.p, cloud, n * GPC_POINT_BYTES, cudaMemcpyHostToDevice, h->stream));
+    h->n_in = n;
+    h->have_cloud = true;
+    size_t tB = tm.mark();
+    tm.span(&h->stats.ms_h2d, tA, tB);
+    int rc = compress_resident_impl(h, tm);
     if (rc) return rc;
-    return gpc_compress_resident(h);
+    size_t tC = tm.mark();
+    tm.span(&h->stats.ms_total, tA, tC);
+    if (h->n_patches > 0 && (rc = read_fit_stats(h))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    tm.resolve();
+    h->stats.kernel_launches = g_launches;
+    return GPC_OK;
 }
 
 int gpc_decompress_resident(gpc_handle* h, int64_t* n_out) {

@@ -12,8 +12,6 @@ namespace gpc {
 
 extern thread_local uint64_t g_launches;  // kernels launched by the current API call
 
-struct BinningWork;                       // scratch of the binning stages (k_binning.cu)
-void binning_free(BinningWork* w);
 
 // Grow-only device buffer owned by the handle.
 struct DevBuf {
@@ -37,6 +35,39 @@ struct DevBuf {
     template <class T>
     T* as() const { return reinterpret_cast<T*>(p); }
 };
+
+// ---- K1..K5: binning ----------------------------------------------------------------------
+struct LatticeDev {          // PCL octree bounding box (doubles), voxel size and depth
+    double mn[3], mx[3];
+    double res;
+    uint32_t depth;
+};
+void launch_first_violation(const uint8_t* cloud, int64_t n, int64_t start, const LatticeDev& lat, int defined,
+                            unsigned long long* best, cudaStream_t s);
+void launch_point_keys(const uint8_t* cloud, int64_t n, const LatticeDev& lat, uint64_t* keys, uint32_t* vals,
+                       unsigned long long* n_valid, cudaStream_t s);
+size_t radix_sort_tmp_bytes(int64_t n);
+int launch_radix_sort(uint64_t* keys, uint32_t* vals, uint64_t* keys2, uint32_t* vals2, int64_t n, int nbits, void* tmp,
+                      cudaStream_t s);
+void launch_iota_u32(uint32_t* v, int64_t n, cudaStream_t s);
+void launch_mark_heads(const uint64_t* keys, int64_t n, int64_t* flags, cudaStream_t s);
+void launch_fill_leaves(const uint64_t* keys, const uint32_t* vals, const int64_t* ex, int64_t n, const uint8_t* cloud,
+                        int32_t* leaf_of, int64_t* leaf_start, uint64_t* leaf_code, void* spt, cudaStream_t s);
+void launch_leaf_neighbours(const uint64_t* leaf_code, int64_t P, const LatticeDev& lat, int32_t* nbr, int32_t* nnbr,
+                            float* center, cudaStream_t s);
+void launch_leaf_rotation(const void* spt, const int64_t* leaf_start, const int32_t* nbr, const int32_t* nnbr,
+                          const float* center, int64_t P, double r2, double* Rm, int32_t* ncand, cudaStream_t s);
+void launch_claim(const void* spt, const int32_t* leaf_of, const int32_t* nbr, const int32_t* nnbr, const float* center,
+                  const double* Rm, const int32_t* ncand, int64_t n_valid, int64_t P, double r2, double half, int leaf_order,
+                  uint64_t* okey, uint32_t* oval, double* pt0, double* pt1, double* pt2, cudaStream_t s);
+void launch_patch_bounds(const uint64_t* okey, int64_t n_valid, int64_t P, int64_t* patch_off, cudaStream_t s);
+void launch_group_gather(const uint64_t* okey, const uint32_t* oval, const uint32_t* sorted_idx, const void* spt,
+                         const double* pt0, const double* pt1, const double* pt2, int64_t n_claimed, int32_t* st_idx, double* h,
+                         double* x1, double* x2, uint32_t* rgb, int32_t* owner, cudaStream_t s);
+void launch_patch_frames(const int64_t* patch_off, int64_t P, int leaf_order, const double* h, const uint32_t* rgb,
+                         const uint64_t* leaf_code_a, const float* center_a, const double* Rm_a, const int32_t* ncand_a, double* y,
+                         uint64_t* code, float* center, int32_t* ncand, double* Rm, double* quat, double* mean, double* rgbmean,
+                         cudaStream_t s);
 
 // ---- K6: glibc rand stream + shuffle -------------------------------------------------
 struct RandTables {       // x^(2^k) mod (x^31 - x^28 - 1) over Z/2^32, k = 0..47, and r_0..r_60

@@ -1,13 +1,567 @@
-// k_binning.cu — K1..K5: lattice, voxel keys, leaves, plane-fit rotation, claim + projection.
+// k_binning.cu — K1, K3, K4, K5: lattice replay, voxel keys, leaves, plane-fit rotation,
+// point claiming and local-frame projection.
+//
+// Replaces gp_compressor::project_cloud / compute_rotation / project_points
+// (/root/reference/src/gp_compressor.cpp:29-118,177-249) together with the PCL octree
+// calls it makes (setInputCloud / addPointsFromInputCloud / leaf iterator /
+// generate_voxel_center / radiusSearch; gp_octree.cpp:3-11).  The octree is never built:
+// its observable behaviour is restated as data-parallel stages
+//   lattice   : PCL's bounding-box growth replayed by "first violating point" searches
+//   keys      : integer voxel key -> Morton code (child index x<<2|y<<1|z, gp_octree.cpp:138-140)
+//   leaves    : run heads of the sorted codes; visiting order = reverse Morton (PCL 1.7/1.8)
+//   rotation  : per leaf, canonical sums over the points of its <= 27 neighbour leaves that
+//               lie within the search radius, then a 4x4 factorisation for the plane normal
+//   claim     : owner(p) = first leaf in visiting order that has p in its candidate list
+//               and accepts it in the box test (the occupied_indices greedy loop, :80-89)
+//   group     : stable sort by owner; per-patch mean height / colour and frame outputs
 #include "gpc_device.cuh"
 #include "gpc_internal.h"
 
 namespace gpc {
 
-struct BinningWork {
-    int unused = 0;
-};
+namespace {
 
-void binning_free(BinningWork* w) { delete w; }
+__device__ __forceinline__ bool finite3(float x, float y, float z) {
+    return isfinite(x) && isfinite(y) && isfinite(z);
+}
+
+__device__ __forceinline__ uint64_t spread3(uint32_t v) {  // bit b -> bit 3b, 21 bits
+    uint64_t x = v & 0x1fffffu;
+    x = (x | (x << 32)) & 0x1f00000000ffffULL;
+    x = (x | (x << 16)) & 0x1f0000ff0000ffULL;
+    x = (x | (x << 8)) & 0x100f00f00f00f00fULL;
+    x = (x | (x << 4)) & 0x10c30c30c30c30c3ULL;
+    x = (x | (x << 2)) & 0x1249249249249249ULL;
+    return x;
+}
+__device__ __forceinline__ uint32_t compact3(uint64_t x) {
+    x &= 0x1249249249249249ULL;
+    x = (x | (x >> 2)) & 0x10c30c30c30c30c3ULL;
+    x = (x | (x >> 4)) & 0x100f00f00f00f00fULL;
+    x = (x | (x >> 8)) & 0x1f0000ff0000ffULL;
+    x = (x | (x >> 16)) & 0x1f00000000ffffULL;
+    x = (x | (x >> 32)) & 0x1fffffULL;
+    return (uint32_t)x;
+}
+__device__ __forceinline__ uint64_t morton(uint32_t kx, uint32_t ky, uint32_t kz) {
+    return (spread3(kx) << 2) | (spread3(ky) << 1) | spread3(kz);
+}
+
+// ---- lattice replay: first point (index >= start) that is finite and, when the box is
+// defined, violates [mn, mx)  (PCL adoptBoundingBoxToPoint) ---------------------------------
+__global__ void __launch_bounds__(256) first_violation_kernel(const uint8_t* __restrict__ cloud, int64_t n, int64_t start,
+                                                              LatticeDev lat, int defined,
+                                                              unsigned long long* __restrict__ best) {
+    __shared__ unsigned long long sbest;
+    __shared__ int skip;
+    const int64_t tile = (int64_t)blockIdx.x * 4096;
+    if (threadIdx.x == 0) {
+        sbest = ~0ull;
+        skip = (unsigned long long)(start + tile) >= *(volatile unsigned long long*)best;  // an earlier hit exists
+    }
+    __syncthreads();
+    if (skip) return;
+    unsigned long long mine = ~0ull;
+    for (int r = 0; r < 16; r++) {
+        int64_t i = start + tile + r * 256 + threadIdx.x;
+        if (i >= n) break;
+        const float4 p = *reinterpret_cast<const float4*>(cloud + i * GPC_POINT_BYTES);
+        if (!finite3(p.x, p.y, p.z)) continue;
+        bool hit = !defined;
+        if (defined) {
+            const double x = p.x, y = p.y, z = p.z;
+            hit = x < lat.mn[0] || y < lat.mn[1] || z < lat.mn[2] || x >= lat.mx[0] || y >= lat.mx[1] || z >= lat.mx[2];
+        }
+        if (hit) { mine = (unsigned long long)i; break; }
+    }
+    if (mine != ~0ull) atomicMin(&sbest, mine);
+    __syncthreads();
+    if (threadIdx.x == 0 && sbest != ~0ull) atomicMin(best, sbest);
+}
+
+// ---- K1: voxel key -> Morton code (PCL genOctreeKeyforPoint) --------------------------------
+__global__ void __launch_bounds__(256) point_keys_kernel(const uint8_t* __restrict__ cloud, int64_t n, LatticeDev lat,
+                                                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                         unsigned long long* __restrict__ n_valid) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = false;
+    if (i < n) {
+        const float4 p = *reinterpret_cast<const float4*>(cloud + i * GPC_POINT_BYTES);
+        uint64_t code = 1ull << (3 * lat.depth);  // non-finite points sort behind every voxel
+        if (finite3(p.x, p.y, p.z)) {
+            ok = true;
+            uint32_t kx = __double2uint_rz(__ddiv_rn(__dadd_rn((double)p.x, -lat.mn[0]), lat.res));
+            uint32_t ky = __double2uint_rz(__ddiv_rn(__dadd_rn((double)p.y, -lat.mn[1]), lat.res));
+            uint32_t kz = __double2uint_rz(__ddiv_rn(__dadd_rn((double)p.z, -lat.mn[2]), lat.res));
+            code = morton(kx, ky, kz);
+        }
+        keys[i] = code;
+        vals[i] = (uint32_t)i;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_valid, (unsigned long long)__popc(m));
+}
+
+// ---- K3: leaves = runs of equal codes --------------------------------------------------------
+__global__ void mark_heads_kernel(const uint64_t* __restrict__ keys, int64_t n, int64_t* __restrict__ flags) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) flags[s] = (s == 0 || keys[s] != keys[s - 1]) ? 1 : 0;
+}
+// ex = exclusive scan of flags (ex[n] = number of leaves)
+__global__ void fill_leaves_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                   const int64_t* __restrict__ ex, int64_t n, const uint8_t* __restrict__ cloud,
+                                   int32_t* __restrict__ leaf_of, int64_t* __restrict__ leaf_start,
+                                   uint64_t* __restrict__ leaf_code, float4* __restrict__ spt) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n) return;
+    if (s == n) { leaf_start[ex[n]] = n; return; }
+    const bool head = ex[s + 1] != ex[s];
+    const int64_t a = ex[s + 1] - 1;
+    leaf_of[s] = (int32_t)a;
+    if (head) { leaf_start[a] = s; leaf_code[a] = keys[s]; }
+    const uint8_t* src = cloud + (int64_t)vals[s] * GPC_POINT_BYTES;
+    float4 p = *reinterpret_cast<const float4*>(src);
+    p.w = __uint_as_float(*reinterpret_cast<const uint32_t*>(src + 16));  // b,g,r,a bytes
+    spt[s] = p;
+}
+
+// ---- neighbour table + voxel centres, one warp per leaf ------------------------------------
+__global__ void __launch_bounds__(256) leaf_neighbours_kernel(const uint64_t* __restrict__ leaf_code, int64_t P, LatticeDev lat,
+                                                              int32_t* __restrict__ nbr, int32_t* __restrict__ nnbr,
+                                                              float* __restrict__ center) {
+    const int64_t a = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (a >= P) return;
+    const uint64_t code = leaf_code[a];
+    const uint32_t kx = compact3(code >> 2), ky = compact3(code >> 1), kz = compact3(code);
+    const int64_t kmax = ((int64_t)1 << lat.depth) - 1;
+    int32_t id = -1;
+    if (lane < 27) {
+        const int64_t x = (int64_t)kx + (lane / 9) - 1, y = (int64_t)ky + ((lane / 3) % 3) - 1, z = (int64_t)kz + (lane % 3) - 1;
+        if (x >= 0 && y >= 0 && z >= 0 && x <= kmax && y <= kmax && z <= kmax) {
+            const uint64_t nc = morton((uint32_t)x, (uint32_t)y, (uint32_t)z);
+            int64_t lo = 0, hi = P;  // first index with leaf_code >= nc
+            while (lo < hi) {
+                int64_t mid = (lo + hi) >> 1;
+                if (leaf_code[mid] < nc) lo = mid + 1; else hi = mid;
+            }
+            if (lo < P && leaf_code[lo] == nc) id = (int32_t)lo;
+        }
+    }
+    // ascending leaf index = ascending Morton = PCL radiusSearch child order 0..7
+    int rank = 0;
+    for (int l = 0; l < 27; l++) {
+        int32_t o = __shfl_sync(0xffffffffu, id, l);
+        if (o >= 0 && o < id) rank++;
+    }
+    const int cnt = __popc(__ballot_sync(0xffffffffu, id >= 0));
+    if (id >= 0) nbr[a * 27 + rank] = id;
+    if (lane >= cnt && lane < 27) nbr[a * 27 + lane] = -1;
+    if (lane == 0) nnbr[a] = cnt;
+    if (lane < 3) {
+        const uint32_t k = lane == 0 ? kx : (lane == 1 ? ky : kz);
+        // genLeafNodeCenterFromOctreeKey: float((double(k) + 0.5f) * res + min)
+        center[a * 3 + lane] = (float)__dadd_rn(__dmul_rn(__dadd_rn((double)k, 0.5), lat.res), lat.mn[lane]);
+    }
+}
+
+// ---- plane fit: smallest right singular vector of A = [x y z 1] from centred sums ----------
+// G_c = A_c' A_c (A_c = [p - c, 1]); G_c = L D L'; M = sqrt(D) L' S with S = [[I,0],[c',1]];
+// one-sided Jacobi on the 4x4 M.  Same operation sequence as the test oracle.
+__device__ void smallest_right_singular_vector(const double* g, const double* c, double* v) {
+    double G[4][4];
+    G[0][0] = g[0]; G[0][1] = g[1]; G[0][2] = g[2]; G[0][3] = g[6];
+    G[1][1] = g[3]; G[1][2] = g[4]; G[1][3] = g[7];
+    G[2][2] = g[5]; G[2][3] = g[8];
+    G[3][3] = g[9];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (j < i) G[i][j] = G[j][i];
+    double Lm[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+    double D[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        double d = G[j][j];
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+            if (t < j) d = d - (Lm[j][t] * Lm[j][t]) * D[t];
+        if (!(d > 0.0)) d = 0.0;
+        D[j] = d;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (i > j) {
+                double a = G[i][j];
+#pragma unroll
+                for (int t = 0; t < 4; t++)
+                    if (t < j) a = a - (Lm[i][t] * Lm[j][t]) * D[t];
+                Lm[i][j] = (d > 0.0) ? a / d : 0.0;
+            }
+    }
+    double M[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        double sd = sqrt(D[i]);
+        double u[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) u[j] = (j >= i) ? sd * Lm[j][i] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) M[i][j] = fma(u[3], c[j], u[j]);
+        M[i][3] = u[3];
+    }
+    double V[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+    for (int sweep = 0; sweep < 30; sweep++) {
+        bool rotated = false;
+#pragma unroll
+        for (int p = 0; p < 3; p++)
+#pragma unroll
+            for (int q = 1; q < 4; q++) {
+                if (q <= p) continue;
+                double a = 0, b = 0, gpq = 0;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    a = fma(M[t][p], M[t][p], a);
+                    b = fma(M[t][q], M[t][q], b);
+                    gpq = fma(M[t][p], M[t][q], gpq);
+                }
+                if (gpq == 0.0) continue;
+                if (gpq * gpq <= 0x1p-106 * (a * b)) continue;
+                rotated = true;
+                double zeta = (b - a) / (2.0 * gpq);
+                double t = 1.0 / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
+                if (zeta < 0.0) t = -t;
+                double cs = 1.0 / sqrt(fma(t, t, 1.0));
+                double sn = cs * t;
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    double mp = M[r][p], mq = M[r][q];
+                    M[r][p] = cs * mp - sn * mq;
+                    M[r][q] = sn * mp + cs * mq;
+                    double vp = V[r][p], vq = V[r][q];
+                    V[r][p] = cs * vp - sn * vq;
+                    V[r][q] = sn * vp + cs * vq;
+                }
+            }
+        if (!rotated) break;
+    }
+    int best = 0;
+    double bestn = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        double nn = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) nn = fma(M[t][j], M[t][j], nn);
+        if (j == 0 || nn < bestn) { bestn = nn; best = j; }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) v[r] = (best == 0) ? V[r][0] : (best == 1) ? V[r][1] : (best == 2) ? V[r][2] : V[r][3];
+}
+
+__device__ __forceinline__ void cross3(const double* a, const double* b, double* o) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ void normalize3(double* v) {
+    double n2 = v[0] * v[0] + (v[1] * v[1] + v[2] * v[2]);
+    double n = sqrt(n2);
+    v[0] = v[0] / n; v[1] = v[1] / n; v[2] = v[2] / n;
+}
+// gp_compressor.cpp:38-63
+__device__ void rotation_from_normal(double* nrm, double* R) {
+    normalize3(nrm);
+    double ex[3] = {1, 0, 0}, ey[3] = {0, 1, 0}, ez[3] = {0, 0, 1};
+    double c1[3];
+    const double ax = fabs(nrm[0]), ay = fabs(nrm[1]), az = fabs(nrm[2]);
+    if (ax > ay && ax > az) {
+        if (nrm[0] < 0) { nrm[0] *= -1; nrm[1] *= -1; nrm[2] *= -1; }
+        cross3(ez, nrm, c1);
+    } else if (ay > ax && ay > az) {
+        if (nrm[1] < 0) { nrm[0] *= -1; nrm[1] *= -1; nrm[2] *= -1; }
+        cross3(ex, nrm, c1);
+    } else {
+        if (nrm[2] < 0) { nrm[0] *= -1; nrm[1] *= -1; nrm[2] *= -1; }
+        cross3(ey, nrm, c1);
+    }
+    normalize3(c1);
+    double c2[3];
+    cross3(nrm, c1, c2);
+#pragma unroll
+    for (int r = 0; r < 3; r++) { R[r * 3 + 0] = nrm[r]; R[r * 3 + 1] = c1[r]; R[r * 3 + 2] = c2[r]; }
+}
+
+// Eigen Quaterniond <- Matrix3d (gp_compressor.cpp:240), q = (x, y, z, w)
+__device__ void rot_to_quat(const double* R, double* q) {
+#define MR(r, c) R[(r) * 3 + (c)]
+    double t = (MR(0, 0) + MR(1, 1)) + MR(2, 2);
+    if (t > 0.0) {
+        t = sqrt(t + 1.0);
+        q[3] = 0.5 * t;
+        t = 0.5 / t;
+        q[0] = (MR(2, 1) - MR(1, 2)) * t;
+        q[1] = (MR(0, 2) - MR(2, 0)) * t;
+        q[2] = (MR(1, 0) - MR(0, 1)) * t;
+    } else {
+        int i = 0;
+        if (MR(1, 1) > MR(0, 0)) i = 1;
+        if (MR(2, 2) > MR(i, i)) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = sqrt(((MR(i, i) - MR(j, j)) - MR(k, k)) + 1.0);
+        q[i] = 0.5 * t;
+        t = 0.5 / t;
+        q[3] = (MR(k, j) - MR(j, k)) * t;
+        q[j] = (MR(j, i) + MR(i, j)) * t;
+        q[k] = (MR(k, i) + MR(i, k)) * t;
+    }
+#undef MR
+}
+
+// ---- K4: rotation per leaf, one warp per leaf ------------------------------------------------
+__global__ void __launch_bounds__(128) leaf_rotation_kernel(const float4* __restrict__ spt, const int64_t* __restrict__ leaf_start,
+                                                            const int32_t* __restrict__ nbr, const int32_t* __restrict__ nnbr,
+                                                            const float* __restrict__ center, int64_t P, double r2,
+                                                            double* __restrict__ Rm, int32_t* __restrict__ ncand) {
+    const int64_t a = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (a >= P) return;
+    const float cx = center[a * 3], cy = center[a * 3 + 1], cz = center[a * 3 + 2];
+    double s[10];
+#pragma unroll
+    for (int q = 0; q < 10; q++) s[q] = 0.0;
+    const int cnt = nnbr[a];
+    for (int t = 0; t < cnt; t++) {
+        const int32_t v = nbr[a * 27 + t];
+        const int64_t lo = leaf_start[v], hi = leaf_start[v + 1];
+        for (int64_t i = lo + lane; i < hi; i += 32) {
+            const float4 p = spt[i];
+            // PCL pointSquaredDist: float (p - c).squaredNorm(); accept iff <= radius^2 (double)
+            const float fx = __fsub_rn(p.x, cx), fy = __fsub_rn(p.y, cy), fz = __fsub_rn(p.z, cz);
+            const float d2 = __fadd_rn(__fmul_rn(fx, fx), __fadd_rn(__fmul_rn(fy, fy), __fmul_rn(fz, fz)));
+            if ((double)d2 > r2) continue;
+            const double ux = __dadd_rn((double)p.x, -(double)cx), uy = __dadd_rn((double)p.y, -(double)cy),
+                         uz = __dadd_rn((double)p.z, -(double)cz);
+            s[0] = fma(ux, ux, s[0]); s[1] = fma(ux, uy, s[1]); s[2] = fma(ux, uz, s[2]);
+            s[3] = fma(uy, uy, s[3]); s[4] = fma(uy, uz, s[4]); s[5] = fma(uz, uz, s[5]);
+            s[6] = __dadd_rn(s[6], ux); s[7] = __dadd_rn(s[7], uy); s[8] = __dadd_rn(s[8], uz);
+            s[9] = __dadd_rn(s[9], 1.0);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 10; q++) s[q] = butterfly32(s[q]);
+    const int m = (int)s[9];
+    double R[9];
+    if (m < 4) {  // gp_compressor.cpp:31-34
+#pragma unroll
+        for (int q = 0; q < 9; q++) R[q] = (q % 4 == 0) ? 1.0 : 0.0;
+    } else {
+        const double cd[3] = {(double)cx, (double)cy, (double)cz};
+        double v[4];
+        smallest_right_singular_vector(s, cd, v);
+        double nrm[3] = {v[0], v[1], v[2]};
+        rotation_from_normal(nrm, R);
+    }
+    if (lane < 9) {
+        double val = R[0];
+#pragma unroll
+        for (int q = 1; q < 9; q++)
+            if (lane == q) val = R[q];
+        Rm[a * 9 + lane] = val;
+    }
+    if (lane == 0) ncand[a] = m;
+}
+
+// ---- K5: owner and local coordinates, one thread per (Morton-sorted) point --------------------
+__global__ void __launch_bounds__(256) claim_kernel(const float4* __restrict__ spt, const int32_t* __restrict__ leaf_of,
+                                                    const int32_t* __restrict__ nbr, const int32_t* __restrict__ nnbr,
+                                                    const float* __restrict__ center, const double* __restrict__ Rm,
+                                                    const int32_t* __restrict__ ncand, int64_t n_valid, int64_t P, double r2,
+                                                    double half, int leaf_order, uint64_t* __restrict__ okey,
+                                                    uint32_t* __restrict__ oval, double* __restrict__ pt0,
+                                                    double* __restrict__ pt1, double* __restrict__ pt2) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_valid) return;
+    const float4 p = spt[s];
+    const int32_t a = leaf_of[s];
+    const int cnt = nnbr[a];
+    uint64_t key = (uint64_t)P;  // unclaimed points sort behind every patch
+    double q0 = 0, q1 = 0, q2 = 0;
+    for (int t = 0; t < cnt; t++) {
+        const int32_t v = (leaf_order == 0) ? nbr[(int64_t)a * 27 + (cnt - 1 - t)] : nbr[(int64_t)a * 27 + t];
+        const float cx = center[(int64_t)v * 3], cy = center[(int64_t)v * 3 + 1], cz = center[(int64_t)v * 3 + 2];
+        const float fx = __fsub_rn(p.x, cx), fy = __fsub_rn(p.y, cy), fz = __fsub_rn(p.z, cz);
+        const float d2 = __fadd_rn(__fmul_rn(fx, fx), __fadd_rn(__fmul_rn(fy, fy), __fmul_rn(fz, fz)));
+        if ((double)d2 > r2) continue;
+        if (ncand[v] == 0) continue;
+        const double* R = Rm + (int64_t)v * 9;
+        const double d0 = __dadd_rn((double)p.x, -(double)cx), d1 = __dadd_rn((double)p.y, -(double)cy),
+                     d2d = __dadd_rn((double)p.z, -(double)cz);
+        // pt = R' (p - centre), gp_compressor.cpp:84
+        const double a0 = __dadd_rn(__dadd_rn(__dmul_rn(R[0], d0), __dmul_rn(R[3], d1)), __dmul_rn(R[6], d2d));
+        const double a1 = __dadd_rn(__dadd_rn(__dmul_rn(R[1], d0), __dmul_rn(R[4], d1)), __dmul_rn(R[7], d2d));
+        const double a2 = __dadd_rn(__dadd_rn(__dmul_rn(R[2], d0), __dmul_rn(R[5], d1)), __dmul_rn(R[8], d2d));
+        if (a1 > half || a1 < -half || a2 > half || a2 < -half) continue;  // :85
+        key = (uint64_t)((leaf_order == 0) ? (P - 1 - v) : v);
+        q0 = a0; q1 = a1; q2 = a2;
+        break;
+    }
+    okey[s] = key;
+    oval[s] = (uint32_t)s;
+    pt0[s] = q0; pt1[s] = q1; pt2[s] = q2;
+}
+
+// patch_off[i] = first sorted position whose owner key >= i (i = 0..P)
+__global__ void patch_bounds_kernel(const uint64_t* __restrict__ okey, int64_t n_valid, int64_t P, int64_t* __restrict__ patch_off) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > P) return;
+    int64_t lo = 0, hi = n_valid;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (okey[mid] < (uint64_t)i) lo = mid + 1; else hi = mid;
+    }
+    patch_off[i] = lo;
+}
+
+__global__ void group_gather_kernel(const uint64_t* __restrict__ okey, const uint32_t* __restrict__ oval,
+                                    const uint32_t* __restrict__ sorted_idx, const float4* __restrict__ spt,
+                                    const double* __restrict__ pt0, const double* __restrict__ pt1,
+                                    const double* __restrict__ pt2, int64_t n_claimed, int32_t* __restrict__ st_idx,
+                                    double* __restrict__ h, double* __restrict__ x1, double* __restrict__ x2,
+                                    uint32_t* __restrict__ rgb, int32_t* __restrict__ owner) {
+    int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_claimed) return;
+    const uint32_t s = oval[d];
+    const uint32_t orig = sorted_idx[s];
+    st_idx[d] = (int32_t)orig;
+    h[d] = pt0[s];
+    x1[d] = pt1[s];
+    x2[d] = pt2[s];
+    rgb[d] = __float_as_uint(spt[s].w);
+    owner[orig] = (int32_t)okey[d];
+}
+
+// per patch (gp_index i): mean height, colour mean, y = height - mean, frame outputs; warp per patch
+__global__ void __launch_bounds__(128) patch_frames_kernel(const int64_t* __restrict__ patch_off, int64_t P, int leaf_order,
+                                                           const double* __restrict__ h, const uint32_t* __restrict__ rgb,
+                                                           const uint64_t* __restrict__ leaf_code_a, const float* __restrict__ center_a,
+                                                           const double* __restrict__ Rm_a, const int32_t* __restrict__ ncand_a,
+                                                           double* __restrict__ y, uint64_t* __restrict__ code,
+                                                           float* __restrict__ center, int32_t* __restrict__ ncand,
+                                                           double* __restrict__ Rm, double* __restrict__ quat,
+                                                           double* __restrict__ mean, double* __restrict__ rgbmean) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= P) return;
+    const int64_t a = (leaf_order == 0) ? (P - 1 - i) : i;
+    const int64_t lo = patch_off[i], hi = patch_off[i + 1];
+    double sh = 0.0, sr = 0.0, sg = 0.0, sb = 0.0;
+    for (int64_t d = lo + lane; d < hi; d += 32) {
+        sh = __dadd_rn(sh, h[d]);
+        const uint32_t c = rgb[d];
+        sr = __dadd_rn(sr, (double)((c >> 16) & 255u));
+        sg = __dadd_rn(sg, (double)((c >> 8) & 255u));
+        sb = __dadd_rn(sb, (double)(c & 255u));
+    }
+    sh = butterfly32(sh); sr = butterfly32(sr); sg = butterfly32(sg); sb = butterfly32(sb);
+    const double cnt = (double)(hi - lo);
+    const double mn = sh / cnt;  // NaN for an empty patch, as in the reference (:101)
+    for (int64_t d = lo + lane; d < hi; d += 32) y[d] = __dadd_rn(h[d], -mn);
+    if (lane == 0) {
+        code[i] = leaf_code_a[a];
+        ncand[i] = ncand_a[a];
+        double R[9];
+        for (int q = 0; q < 9; q++) { R[q] = Rm_a[a * 9 + q]; Rm[i * 9 + q] = R[q]; }
+        double qq[4];
+        rot_to_quat(R, qq);
+        for (int q = 0; q < 4; q++) quat[i * 4 + q] = qq[q];
+        for (int dd = 0; dd < 3; dd++) {
+            const float c = center_a[a * 3 + dd];
+            center[i * 3 + dd] = c;
+            mean[i * 3 + dd] = __dadd_rn((double)c, __dmul_rn(mn, R[dd * 3]));  // centre += mn*R.col(0), :116
+        }
+        rgbmean[i * 3 + 0] = sr / cnt; rgbmean[i * 3 + 1] = sg / cnt; rgbmean[i * 3 + 2] = sb / cnt;
+    }
+}
+
+}  // namespace
+
+void launch_first_violation(const uint8_t* cloud, int64_t n, int64_t start, const LatticeDev& lat, int defined,
+                            unsigned long long* best, cudaStream_t s) {
+    cudaMemsetAsync(best, 0xff, sizeof(unsigned long long), s);
+    if (start >= n) return;
+    int64_t tiles = (n - start + 4095) / 4096;
+    first_violation_kernel<<<(unsigned)tiles, 256, 0, s>>>(cloud, n, start, lat, defined, best);
+    g_launches++;
+}
+
+void launch_point_keys(const uint8_t* cloud, int64_t n, const LatticeDev& lat, uint64_t* keys, uint32_t* vals,
+                       unsigned long long* n_valid, cudaStream_t s) {
+    cudaMemsetAsync(n_valid, 0, sizeof(unsigned long long), s);
+    if (n <= 0) return;
+    point_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cloud, n, lat, keys, vals, n_valid);
+    g_launches++;
+}
+
+void launch_mark_heads(const uint64_t* keys, int64_t n, int64_t* flags, cudaStream_t s) {
+    if (n <= 0) return;
+    mark_heads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(keys, n, flags);
+    g_launches++;
+}
+
+void launch_fill_leaves(const uint64_t* keys, const uint32_t* vals, const int64_t* ex, int64_t n, const uint8_t* cloud,
+                        int32_t* leaf_of, int64_t* leaf_start, uint64_t* leaf_code, void* spt, cudaStream_t s) {
+    fill_leaves_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, s>>>(keys, vals, ex, n, cloud, leaf_of, leaf_start, leaf_code,
+                                                                     reinterpret_cast<float4*>(spt));
+    g_launches++;
+}
+
+void launch_leaf_neighbours(const uint64_t* leaf_code, int64_t P, const LatticeDev& lat, int32_t* nbr, int32_t* nnbr,
+                            float* center, cudaStream_t s) {
+    if (P <= 0) return;
+    leaf_neighbours_kernel<<<(unsigned)((P * 32 + 255) / 256), 256, 0, s>>>(leaf_code, P, lat, nbr, nnbr, center);
+    g_launches++;
+}
+
+void launch_leaf_rotation(const void* spt, const int64_t* leaf_start, const int32_t* nbr, const int32_t* nnbr,
+                          const float* center, int64_t P, double r2, double* Rm, int32_t* ncand, cudaStream_t s) {
+    if (P <= 0) return;
+    leaf_rotation_kernel<<<(unsigned)((P * 32 + 127) / 128), 128, 0, s>>>(reinterpret_cast<const float4*>(spt), leaf_start, nbr,
+                                                                        nnbr, center, P, r2, Rm, ncand);
+    g_launches++;
+}
+
+void launch_claim(const void* spt, const int32_t* leaf_of, const int32_t* nbr, const int32_t* nnbr, const float* center,
+                  const double* Rm, const int32_t* ncand, int64_t n_valid, int64_t P, double r2, double half, int leaf_order,
+                  uint64_t* okey, uint32_t* oval, double* pt0, double* pt1, double* pt2, cudaStream_t s) {
+    if (n_valid <= 0) return;
+    claim_kernel<<<(unsigned)((n_valid + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4*>(spt), leaf_of, nbr, nnbr, center,
+                                                                  Rm, ncand, n_valid, P, r2, half, leaf_order, okey, oval, pt0, pt1,
+                                                                  pt2);
+    g_launches++;
+}
+
+void launch_patch_bounds(const uint64_t* okey, int64_t n_valid, int64_t P, int64_t* patch_off, cudaStream_t s) {
+    patch_bounds_kernel<<<(unsigned)((P + 1 + 255) / 256), 256, 0, s>>>(okey, n_valid, P, patch_off);
+    g_launches++;
+}
+
+void launch_group_gather(const uint64_t* okey, const uint32_t* oval, const uint32_t* sorted_idx, const void* spt,
+                         const double* pt0, const double* pt1, const double* pt2, int64_t n_claimed, int32_t* st_idx, double* h,
+                         double* x1, double* x2, uint32_t* rgb, int32_t* owner, cudaStream_t s) {
+    if (n_claimed <= 0) return;
+    group_gather_kernel<<<(unsigned)((n_claimed + 255) / 256), 256, 0, s>>>(okey, oval, sorted_idx, reinterpret_cast<const float4*>(spt),
+                                                                          pt0, pt1, pt2, n_claimed, st_idx, h, x1, x2, rgb, owner);
+    g_launches++;
+}
+
+void launch_patch_frames(const int64_t* patch_off, int64_t P, int leaf_order, const double* h, const uint32_t* rgb,
+                         const uint64_t* leaf_code_a, const float* center_a, const double* Rm_a, const int32_t* ncand_a, double* y,
+                         uint64_t* code, float* center, int32_t* ncand, double* Rm, double* quat, double* mean, double* rgbmean,
+                         cudaStream_t s) {
+    if (P <= 0) return;
+    patch_frames_kernel<<<(unsigned)((P * 32 + 127) / 128), 128, 0, s>>>(patch_off, P, leaf_order, h, rgb, leaf_code_a, center_a, Rm_a,
+                                                                       ncand_a, y, code, center, ncand, Rm, quat, mean, rgbmean);
+    g_launches++;
+}
 
 }  // namespace gpc

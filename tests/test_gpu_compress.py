@@ -1,0 +1,191 @@
+"""GPU parity tests of the whole path through the C ABI (gpc_compress / gpc_decompress)
+against the CPU oracle: identical lattice, leaves, visiting order, candidate counts,
+rotations, patch assignment and per-patch point order (bit-exact, integer / index work),
+identical BV index sets, alpha and reconstructed cloud (tolerance 1e-9 relative required by
+the north star; bit-equality asserted because both sides use the same canonical arithmetic)."""
+import numpy as np
+import pytest
+
+from gp_compressor_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+F32 = lambda v: float(np.float32(v))
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gp_compressor_b200 as G
+    G.load()
+    return G
+
+
+def eq(a, b):
+    return np.array_equal(a, b, equal_nan=True)
+
+
+def compare_all(G, O, cloud, decode=True, **cfg):
+    h = G.Handle(**cfg)
+    h.compress(cloud)
+    o = O.Oracle(**cfg)
+    want = o.compress(cloud)
+    bo = o.binning()
+    bg = h.patches()
+    ag = h.assignment()
+    assert bg["depth"] == bo["depth"]
+    assert eq(bg["lattice_min"], bo["lattice_min"])
+    assert bg["n_leaves"] == bo["n_leaves"] and bg["n_claimed"] == bo["n_claimed"]
+    for k in ("leaf_code", "leaf_center", "leaf_ncand", "patch_off"):
+        assert eq(bg[k], bo[k]), k
+    assert eq(ag["owner"], bo["owner"]), "patch assignment differs"
+    assert eq(ag["st_idx"], bo["st_idx"]), "per-patch point order differs"
+    for k in ("leaf_R", "leaf_quat", "leaf_mean", "leaf_rgbmean"):
+        assert eq(bg[k], bo[k]), k
+    for k in ("st_x1", "st_x2", "st_y"):
+        assert eq(ag[k], bo[k]), k
+    assert eq(ag["perm"], want["perm"])
+    got = h.params()
+    assert eq(got["nbv"], want["nbv"]) and eq(got["bv_idx"], want["bv_idx"])
+    np.testing.assert_allclose(got["alpha"], want["alpha"], rtol=1e-9, atol=0)
+    assert eq(got["alpha"], want["alpha"])
+    gs, os_ = h.stats(), o.stats()
+    for k in ("n_add", "n_first", "n_sparse", "n_full", "n_del_cap", "n_del_geo"):
+        assert gs[k] == os_[k], k
+    assert h.sizes().rand_offset == o.rand_offset()
+    if decode:
+        cloud_o, heights_o = o.decode()
+        assert h.decompress_resident() == heights_o.size
+        hg = h.heights()
+        np.testing.assert_allclose(hg, heights_o, rtol=1e-9, atol=0)
+        cloud_g = h.decompress()
+        assert eq(cloud_g, cloud_o)
+    return h, o
+
+
+def test_c1_planar_bumps_reference_config(G, oracle_mod):
+    """BASELINE configs[0] at reduced size: gp_compressor(cloud, 0.15f, 20), capacity 100, reference hyper-parameters."""
+    cloud = synth.c1_planar_bumps(30000, seed=1)
+    h, o = compare_all(G, oracle_mod, cloud, res=F32(0.15), sz=20, capacity=100)
+    assert h.sizes().n_patches > 1000
+
+
+def test_c2_indoor_capacity30_both_hypersets(G, oracle_mod):
+    cloud = synth.c2_indoor(60000, seed=2)
+    compare_all(G, oracle_mod, cloud, res=F32(0.1), sz=10, capacity=30)
+    compare_all(G, oracle_mod, cloud, res=F32(0.1), sz=10, capacity=30, **synth.hyper_bind(F32(0.1)))
+
+
+def test_c5_outdoor_small(G, oracle_mod):
+    cloud = synth.c5_outdoor(80000, seed=5)
+    compare_all(G, oracle_mod, cloud, res=F32(0.2), sz=10, capacity=100)
+
+
+def test_dense_patches_capacity_binds(G, oracle_mod):
+    cloud = synth.c3_dense_floor(40000, seed=3, side=1.0)  # ~400 points per patch
+    compare_all(G, oracle_mod, cloud, res=F32(0.1), sz=10, capacity=20, **synth.hyper_bind(F32(0.1)))
+
+
+def test_morton_leaf_order(G, oracle_mod):
+    cloud = synth.c1_planar_bumps(8000, seed=3)
+    compare_all(G, oracle_mod, cloud, res=F32(0.15), sz=5, capacity=30, leaf_order=1)
+
+
+def test_edge_clouds(G, oracle_mod):
+    rng = np.random.default_rng(0)
+    # empty, single point, non-finite points, all points in one voxel, exact duplicates, < 4 candidates
+    empty = np.zeros((0, 32), dtype=np.uint8)
+    h = G.Handle()
+    h.compress(empty)
+    assert h.sizes().n_patches == 0 and h.decompress_resident() == 0
+    one = synth.pack_cloud(np.array([[1.0, 2.0, 3.0]]), np.array([[10, 20, 30]], dtype=np.uint8))
+    compare_all(G, oracle_mod, one, capacity=5)
+    xyz = rng.uniform(-1, 1, (3000, 3))
+    xyz[::7, 0] = np.nan
+    xyz[5::11, 2] = np.inf
+    rgb = rng.integers(0, 256, (3000, 3)).astype(np.uint8)
+    compare_all(G, oracle_mod, synth.pack_cloud(xyz, rgb), res=F32(0.25), capacity=10)
+    allnan = synth.pack_cloud(np.full((10, 3), np.nan))
+    h = G.Handle()
+    h.compress(allnan)
+    assert h.sizes().n_patches == 0
+    tiny = synth.pack_cloud(rng.uniform(0, 0.01, (500, 3)), rgb[:500])
+    compare_all(G, oracle_mod, tiny, capacity=8, **synth.hyper_bind(F32(0.1)))
+    dup = np.repeat(rng.uniform(0, 1, (300, 3)), 4, axis=0)
+    compare_all(G, oracle_mod, synth.pack_cloud(dup, np.repeat(rgb[:300], 4, axis=0)), res=F32(0.2), capacity=10)
+    sparse = synth.pack_cloud(rng.uniform(0, 50, (200, 3)), rgb[:200])  # isolated points: m < 4 -> identity rotation
+    compare_all(G, oracle_mod, sparse, res=F32(0.1), capacity=5)
+
+
+def test_lattice_growth_directions_and_exact_planes(G, oracle_mod):
+    rng = np.random.default_rng(1)
+    # first point in the middle, later points far away in every direction: growth on all sides
+    xyz = np.concatenate([[[0.0, 0.0, 0.0]], rng.uniform(-40, 40, (5000, 3)) * [1, 1, 0.02]])
+    compare_all(G, oracle_mod, synth.pack_cloud(xyz), res=F32(0.5), capacity=10)
+    # noise-free axis-aligned planes (singular Gram matrix, exact ties in the dominant-axis test)
+    u = rng.uniform(0, 2, (4000, 2))
+    planes = np.concatenate([np.c_[u[:1500], np.zeros(1500)], np.c_[np.zeros(1500), u[1500:3000]],
+                             np.c_[u[3000:, 0], np.full(1000, 1.0), u[3000:, 1]]])
+    compare_all(G, oracle_mod, synth.pack_cloud(planes), res=F32(0.1), capacity=10)
+
+
+def test_second_compress_continues_rand_stream(G, oracle_mod):
+    cloud = synth.c1_planar_bumps(5000, seed=9)
+    cfg = dict(res=F32(0.15), sz=4, capacity=20)
+    h = G.Handle(**cfg)
+    o = oracle_mod.Oracle(**cfg)
+    for _ in range(2):
+        h.compress(cloud)
+        want = o.compress(cloud)
+        assert eq(h.assignment()["perm"], want["perm"])
+        assert eq(h.params()["alpha"], want["alpha"])
+    assert h.sizes().rand_offset == o.rand_offset() > 0
+
+
+def test_upload_then_resident_equals_host_call(G):
+    cloud = synth.c2_indoor(20000, seed=12)
+    a = G.Handle(capacity=30)
+    a.compress(cloud)
+    b = G.Handle(capacity=30)
+    b.upload_cloud(cloud)
+    b.compress_resident()
+    assert eq(a.params()["alpha"], b.params()["alpha"])
+    assert eq(a.decompress(), b.decompress())
+
+
+def test_sharded_compress_is_world_size_invariant(G, oracle_mod):
+    cloud = synth.c2_indoor(30000, seed=7)
+    cfg = dict(res=F32(0.1), sz=6, capacity=30)
+    o = oracle_mod.Oracle(**cfg)
+    want = o.compress(cloud)
+    cloud_o, _ = o.decode()
+    for world in (2, 4, 8):
+        nbv, alpha, clouds = [], [], []
+        for r in range(world):
+            h = G.Handle(shard_rank=r, shard_count=world, **cfg)
+            h.compress(cloud)
+            p = h.params()
+            nbv.append(p["nbv"]); alpha.append(p["alpha"])
+            clouds.append(h.decompress())
+        assert eq(np.concatenate(nbv), want["nbv"])
+        assert eq(np.concatenate(alpha), want["alpha"])
+        assert eq(np.concatenate(clouds), cloud_o)
+
+
+def test_reconstruction_rmse_is_small(G):
+    """Round-trip property at a larger size: the decoded surface stays close to the data."""
+    cloud = synth.c1_planar_bumps(60000, seed=4)
+    h = G.Handle(res=F32(0.15), sz=20, capacity=100)
+    h.compress(cloud)
+    a = h.assignment()
+    off = h.patches(binning=False, frames=False)["patch_off"]
+    se, cnt = 0.0, 0
+    for p in range(0, len(off) - 1, 37):
+        lo, hi = off[p], off[p + 1]
+        if hi == lo:
+            continue
+        X = np.stack([a["st_x1"][lo:hi], a["st_x2"][lo:hi]], axis=1)
+        f = h.predict(p, X)
+        se += float(((f - a["st_y"][lo:hi]) ** 2).sum())
+        cnt += hi - lo
+    rmse = np.sqrt(se / cnt)
+    assert rmse < 0.01

@@ -160,8 +160,9 @@ def test_decode_only_with_frames(G, oracle_mod):
     o = oracle_mod.Oracle(**cfg)
     o.set_params(**prm)
     cloud_o, heights_o = o.decode()
-    cloud_g = h.decompress()
+    assert h.decompress_resident() == heights_o.size
     assert np.array_equal(h.heights(), heights_o)
+    cloud_g = h.decompress()
     assert np.array_equal(cloud_g, cloud_o)
 
 
