@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the gp_compressor hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c2bind|c1|c5] [--points M]
+
+Metric (BASELINE.json): compress pts/s (+ decompress pts/s), quoted on configs[1]:
+synthetic 5M-point indoor-scan cloud, 0.1 m patches, SOGP capacity 30, 1 x B200.
+A step = one compress (K1..K7) + one decompress (K8) of one batch (one cloud per GPU).
+
+  value         compress pts/s with the cloud already resident in HBM (device timeline, CUDA
+                events on the handle's stream, max over ranks)
+  e2e           the same metric through the host-buffer C-ABI calls gpc_compress +
+                gpc_get_params (+ gpc_decompress): H2D of the cloud from pinned memory and D2H
+                of the results inside the timed region
+  roofline      for the stage that dominates the step (see DESIGN.md for the byte / flop models)
+  cpu_baseline  the CPU oracle (a port of the reference path; the reference itself cannot be
+                built here) timed on this box's host cores on rank 0
+
+--impl reference times the CPU oracle with all host threads on the same workload.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F32 = lambda v: float(np.float32(v))
+
+
+def workload(name, points, seed_shift=0):
+    from gp_compressor_b200 import synth
+    if name in ("c2", "c2bind"):
+        n = points or 5_000_000
+        cfg = dict(res=F32(0.1), sz=10, capacity=30)
+        if name == "c2bind":
+            cfg.update(synth.hyper_bind(F32(0.1)))
+        desc = "C2 synthetic indoor scan, %d pts, res 0.1f, sz 10, capacity 30, hyper=%s" % (n, "BIND" if name == "c2bind" else "REF (reference defaults)")
+        return synth.c2_indoor(n, seed=2 + seed_shift), cfg, desc
+    if name == "c1":
+        n = points or 100_000
+        return synth.c1_planar_bumps(n, seed=1 + seed_shift), dict(res=F32(0.15), sz=20, capacity=100), "C1 planar+bumps, %d pts, res 0.15f, sz 20, capacity 100, hyper=REF" % n
+    if name == "c5":
+        n = points or 50_000_000
+        return synth.c5_outdoor(n, seed=5 + seed_shift), dict(res=F32(0.2), sz=10, capacity=100), "C5 outdoor LiDAR-like, %d pts, res 0.2f, sz 10, capacity 100, hyper=REF" % n
+    raise SystemExit("unknown workload " + name)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---- algorithmic byte / flop models ------------------------------------
+def stage_models(n_pts, n_valid, n_claimed, depth, n_patches, st, cap):
+    sort_passes = -(-(3 * depth + 1) // 8) + -(-max(1, int(n_patches).bit_length()) // 8)
+    return {
+        "ms_sort": ("radix sort (hist + scatter, both sorts)", "hbm", sort_passes * n_valid * (8.0 + 12.0 + 12.0)),
+        "ms_keys": ("point_keys", "hbm", n_pts * (32.0 + 12.0)),
+        "ms_leaves": ("mark_heads + scan + fill_leaves", "hbm", n_valid * (8 + 8 + 8 + 8 + 8 + 12 + 4 + 32 + 16.0)),
+        "ms_claim": ("claim", "hbm", n_valid * (16 + 4 + 12 + 24.0)),
+        "ms_group": ("group_gather + patch_frames", "hbm", n_claimed * (12 + 4 + 16 + 24 + 4 + 8 + 8 + 8 + 4 + 8 + 8.0)),
+        "ms_shuffle": ("rand + shuffle + gather", "hbm", n_claimed * (8 + 4 + 4 + 4 + 24 + 24.0)),
+    }
+
+
+def sogp_flops(st):
+    E = 28.0  # flops per exp by convention
+    return (4 * st["sum_n2_common"] + (13 + E) * st["sum_n"] + 20 * (st["n_add"] - st["n_first"])
+            + 2 * st["sum_n2_sparse"] + 4 * st["n_sparse"] * 0 + 4 * st["sum_n2_full"] + 6 * st["sum_n2_del"])
+
+
+def sogp_smem_bytes(st):
+    # matvecs read C and Q once (16 N^2); sparse rank-1 reads+writes C (16 N^2); full update reads+writes
+    # C and Q (32 (N+1)^2); a deletion reads+writes C and Q (32 (M-1)^2)
+    return 16.0 * st["sum_n2_common"] + 16.0 * st["sum_n2_sparse"] + 32.0 * st["sum_n2_full"] + 32.0 * st["sum_n2_del"]
+
+
+def run_reference(args, rank, world):
+    """The reference arm: the reference's CPU implementation of the path (here: its port, the oracle,
+    because the reference needs PCL + Eigen which are absent) on all host threads."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    cloud, cfg, desc = workload(args.workload, args.points)
+    cores = os.cpu_count() or 1
+    o = O.Oracle(threads=cores, **cfg)
+    n = cloud.shape[0]
+    tc, td, nd = [], [], 0
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        o.compress(cloud)
+        t1 = time.perf_counter()
+        cl, _ = o.decode(want_heights=False)
+        t2 = time.perf_counter()
+        nd = cl.shape[0]
+        if it >= args.warmup:
+            tc.append(t1 - t0); td.append(t2 - t1)
+    sec = float(np.sum(tc))
+    v = n * len(tc) / sec
+    line = {"impl": "reference", "metric": "compress pts/s", "value": v, "unit": "pts/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * (sec + float(np.sum(td))) / len(tc), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "sample": "whole cloud per step", "l2": "n/a (CPU)"},
+            "decompress": {"value": nd * len(td) / float(np.sum(td)), "unit": "grid pts/s"},
+            "cpu_baseline": {"value": v, "unit": "pts/s", "cores": cores, "kind": "port", "sample": "%d pts (whole workload) per step" % n},
+            "e2e": {"value": v, "unit": "pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--points", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import gp_compressor_b200 as G
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cloud_np, cfg, desc = workload(args.workload, args.points, seed_shift=rank)  # weak scaling: one cloud per GPU
+    n = cloud_np.shape[0]
+    # pinned host buffers for the end-to-end arm
+    pin_in = torch.empty((n, 32), dtype=torch.uint8, pin_memory=True)
+    pin_in.numpy()[:] = cloud_np
+    h = G.Handle(device=local, **cfg)
+    ext = torch.cuda.ExternalStream(h.stream(), device=torch.device("cuda", local))
+
+    # ---- device-resident arm -----------------------------------------------------------
+    h.upload_cloud_ptr(pin_in.data_ptr(), n)
+    evs, stage_acc = [], {}
+    n_dec = 0
+    launches = 0
+    sampler = None
+    e_all0 = torch.cuda.Event(enable_timing=True)
+    for it in range(args.warmup + args.steps):
+        if it == args.warmup:
+            barrier()
+            sampler = ClockSampler(local) if rank == 0 else None
+            e_all0.record(ext)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e2 = torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        h.compress_resident()
+        st_c = h.stats()
+        e1.record(ext)
+        n_dec = h.decompress_resident()
+        st_d = h.stats()
+        e2.record(ext)
+        if it >= args.warmup:
+            evs.append((e0, e1, e2))
+            launches += st_c["kernel_launches"] + st_d["kernel_launches"]
+            for k, v in st_c.items():
+                if k.startswith("ms_"):
+                    stage_acc[k] = stage_acc.get(k, 0.0) + v
+            stage_acc["ms_predict"] = stage_acc.get("ms_predict", 0.0) + st_d["ms_predict"]
+    e_all1 = torch.cuda.Event(enable_timing=True); e_all1.record(ext)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    total_ms = e_all0.elapsed_time(e_all1)
+    comp_ms = [a.elapsed_time(b) for a, b, _ in evs]
+    dec_ms = [b.elapsed_time(c) for _, b, c in evs]
+    sizes = h.sizes()
+    fit_stats = st_c
+    K = args.steps
+    t = torch.tensor([float(np.sum(comp_ms)), float(np.sum(dec_ms)), total_ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(n), float(n_dec)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    comp_s, dec_s, tot_s = (t / 1e3).tolist()
+    n_all, ndec_all = cnt.tolist()
+    value = n_all * K / comp_s
+    dec_value = ndec_all * K / dec_s
+
+    # ---- end-to-end arm: host buffers through the C ABI --------------------------------------
+    out_cap = int(sizes.patch_hi - sizes.patch_lo) * cfg["sz"] * cfg["sz"]
+    pin_out = torch.empty((max(out_cap, 1), 32), dtype=torch.uint8, pin_memory=True)
+    e2e_c, e2e_d = [], []
+    d2h = 0
+    for it in range(args.warmup + args.steps):
+        if it == args.warmup:
+            barrier()
+        t0 = time.perf_counter()
+        h.compress_ptr(pin_in.data_ptr(), n)
+        prm = h.params()                      # compressed parameters back on the host
+        t1 = time.perf_counter()
+        nd = h.decompress_ptr(pin_out.data_ptr(), pin_out.shape[0])
+        t2 = time.perf_counter()
+        if it >= args.warmup:
+            e2e_c.append(t1 - t0); e2e_d.append(t2 - t1)
+            d2h = sum(v.nbytes for v in prm.values() if hasattr(v, "nbytes")) + nd * 32
+    barrier()
+    te = torch.tensor([float(np.sum(e2e_c)), float(np.sum(e2e_d))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_cs, e2e_ds = te.tolist()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant stage --------------------------------------------------------
+    peak, peak_src = measured_peaks()
+    stage_ms = {k: v / K for k, v in stage_acc.items() if k not in ("ms_total", "ms_h2d", "ms_d2h")}
+    dom = max(stage_ms, key=stage_ms.get)
+    n_valid = n  # all points finite in the synthetic clouds
+    models = stage_models(n, n_valid, sizes.n_claimed, sizes.depth, sizes.n_patches, fit_stats, cfg["capacity"])
+    roof = None
+    if dom in models:
+        name, bound, nbytes = models[dom]
+        ach = nbytes / (stage_ms[dom] * 1e-3) / 1e9
+        roof = {"kernel": name, "bound": bound, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "stage_ms": stage_ms[dom]}
+    elif dom == "ms_fit":
+        fl = sogp_flops(fit_stats)
+        sm = sogp_smem_bytes(fit_stats)
+        sec = stage_ms[dom] * 1e-3
+        # FP64 / shared-memory peaks: theoretical B200 figures until the micro-benchmarks of profiles/ replace them
+        fp64_peak, smem_peak = 37.2e12, 37.2e12
+        f1, f2 = fl / sec / fp64_peak, sm / sec / smem_peak
+        roof = {"kernel": "sogp_fit_kernel (K7)", "bound": "smem" if f2 >= f1 else "fp64", "achieved": (sm if f2 >= f1 else fl) / sec / 1e9,
+                "peak": (smem_peak if f2 >= f1 else fp64_peak) / 1e9, "unit": "GB/s" if f2 >= f1 else "GFLOP/s", "frac": max(f1, f2),
+                "traffic": None, "peak_source": "theoretical 148 SM x 128 B/clk (64 DFMA/clk) x 1.965 GHz", "stage_ms": stage_ms[dom],
+                "fp64_frac": f1, "smem_frac": f2, "mean_n": fit_stats["sum_n"] / max(1, fit_stats["n_add"] - fit_stats["n_first"])}
+    elif dom == "ms_predict":
+        fl = n_dec * (37.0 * (sizes.n_bv_total / max(1, n_dec / (cfg["sz"] ** 2))) + 18)
+        sec = stage_ms[dom] * 1e-3
+        roof = {"kernel": "predict_grid_kernel (K8)", "bound": "fp64", "achieved": fl / sec / 1e9, "peak": 37200.0, "unit": "GFLOP/s",
+                "frac": fl / sec / 37.2e12, "traffic": None, "peak_source": "theoretical", "stage_ms": stage_ms[dom]}
+    else:
+        roof = {"kernel": dom, "bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None}
+
+    # ---- CPU baseline (oracle, 1 thread = faithful to the single-threaded reference) -------------
+    cpu = None
+    if not args.no_cpu_baseline and world >= 1:
+        from oracle import oracle as O
+        sample = min(n, 2_000_000)
+        sub = np.ascontiguousarray(cloud_np[:sample])
+        o = O.Oracle(threads=1, **cfg)
+        t0 = time.perf_counter()
+        o.compress(sub)
+        t1 = time.perf_counter()
+        cpu = {"value": sample / (t1 - t0), "unit": "pts/s", "cores": 1, "kind": "port",
+               "sample": "first %d points of the same cloud, 1 thread (the reference is single-threaded)" % sample}
+
+    line = {
+        "metric": "compress pts/s", "value": value, "unit": "pts/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": desc, "per_gpu_points": n, "l2": "inputs larger than L2 (%.0f MB cloud + sort buffers per step)" % (n * 32 / 1e6),
+                   "parallelism": "one cloud per GPU, patches independent, no collective"},
+        "decompress": {"value": dec_value, "unit": "grid pts/s", "points_per_step": ndec_all},
+        "compress_ms": 1e3 * comp_s / K, "decompress_ms": 1e3 * dec_s / K,
+        "stages_ms": {k: round(v, 4) for k, v in sorted(stage_ms.items())},
+        "patches": int(sizes.n_patches), "claimed": int(sizes.n_claimed), "mean_bv": sizes.n_bv_total / max(1, sizes.n_patches),
+        "escalated": fit_stats["escalated"],
+        "roofline": roof, "cpu_baseline": cpu,
+        "e2e": {"value": n_all * K / e2e_cs, "unit": "pts/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": int(d2h),
+                "decompress_value": ndec_all * K / e2e_ds, "compress_ms": 1e3 * e2e_cs / K, "decompress_ms": 1e3 * e2e_ds / K},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

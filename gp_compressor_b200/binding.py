@@ -20,7 +20,7 @@ SYMBOLS = [
     "gpc_config_default", "gpc_create", "gpc_destroy", "gpc_last_error", "gpc_version", "gpc_compress",
     "gpc_upload_cloud", "gpc_compress_resident", "gpc_fit_patches", "gpc_decompress", "gpc_decompress_resident",
     "gpc_get_heights", "gpc_predict", "gpc_get_sizes", "gpc_get_stats", "gpc_get_patches", "gpc_get_assignment",
-    "gpc_get_params", "gpc_get_state", "gpc_set_params", "gpc_set_rand_offset", "gpc_debug_exp", "gpc_debug_rand",
+    "gpc_get_params", "gpc_get_state", "gpc_set_params", "gpc_set_rand_offset", "gpc_get_stream", "gpc_debug_exp", "gpc_debug_rand",
 ]
 
 
@@ -81,6 +81,7 @@ def load():
     L.gpc_get_state.argtypes = [vp, i64, vp, vp]
     L.gpc_set_params.argtypes = [vp, i64] + [vp] * 7
     L.gpc_set_rand_offset.argtypes = [vp, u64]
+    L.gpc_get_stream.argtypes = [vp, C.POINTER(vp)]
     L.gpc_debug_exp.argtypes = [vp, vp, vp, i64]
     L.gpc_debug_rand.argtypes = [vp, u64, i64, vp]
     _LIB = L
@@ -250,6 +251,11 @@ class Handle:
         if quat is not None:
             quat, mean, rgbmean = (np.ascontiguousarray(a, dtype=np.float64) for a in (quat, mean, rgbmean))
         self._ck(load().gpc_set_params(self.h, nbv.size, _p(nbv), _p(bv1), _p(bv2), _p(alpha), _p(quat), _p(mean), _p(rgbmean)))
+
+    def stream(self):
+        s = C.c_void_p()
+        self._ck(load().gpc_get_stream(self.h, C.byref(s)))
+        return s.value or 0
 
     def set_rand_offset(self, off):
         self._ck(load().gpc_set_rand_offset(self.h, off))

@@ -245,7 +245,6 @@ int run_decode(gpc_handle* h, bool want_cloud, bool want_heights, StageTimer& tm
     CK(h->scan_tmp.reserve(scan_tmp_bytes(PL + 1)));
     launch_flag_nonempty(h->nbv.as<int32_t>(), PL, h->nonempty.as<int64_t>(), st);
     launch_exclusive_scan_i64(h->nonempty.as<int64_t>(), h->slot.as<int64_t>(), PL, h->scan_tmp.p, st);
-    g_launches += 4;
     int64_t n_nonempty = 0;
     CK(cudaMemcpyAsync(&n_nonempty, h->slot.as<int64_t>() + PL, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -269,7 +268,6 @@ int run_decode(gpc_handle* h, bool want_cloud, bool want_heights, StageTimer& tm
     a.out32 = want_cloud ? h->out32.as<uint8_t>() : nullptr;
     a.heights = want_heights ? h->heights.as<double>() : nullptr;
     launch_predict_grid(a, st);
-    g_launches++;
     CK(cudaGetLastError());
     size_t t1 = tm.mark();
     tm.span(&h->stats.ms_predict, t0, t1);
@@ -401,7 +399,6 @@ int run_binning(gpc_handle* h, StageTimer& tm) {
     CK(h->scan_tmp.reserve(scan_tmp_bytes(n_valid)));
     launch_mark_heads(skeys, n_valid, h->flags64.as<int64_t>(), st);
     launch_exclusive_scan_i64(h->flags64.as<int64_t>(), h->ex.as<int64_t>(), n_valid, h->scan_tmp.p, st);
-    g_launches += 3;
     int64_t P = 0;
     CK(cudaMemcpyAsync(&P, h->ex.as<int64_t>() + n_valid, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -561,6 +558,12 @@ void gpc_destroy(gpc_handle* h) {
 }
 
 const char* gpc_last_error(const gpc_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int gpc_get_stream(gpc_handle* h, void** stream) {
+    if (!h || !stream) return GPC_ERR_INVALID;
+    *stream = (void*)h->stream;
+    return GPC_OK;
+}
 
 int gpc_set_rand_offset(gpc_handle* h, uint64_t offset) {
     if (!h) return GPC_ERR_INVALID;

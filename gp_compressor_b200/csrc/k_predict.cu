@@ -144,6 +144,7 @@ void launch_predict_grid(const PredictArgs& a, cudaStream_t s) {
     if (a.n_patches <= 0) return;
     size_t smem = (size_t)3 * a.stride * sizeof(double);
     predict_grid_kernel<<<(unsigned)a.n_patches, PRED_T, smem, s>>>(a);
+    g_launches++;
 }
 
 void launch_predict_points(const double* alpha, const double* b1, const double* b2, int N, const double* C, double p0,

@@ -96,6 +96,7 @@ void launch_rand_stream(uint64_t offset, int64_t n, uint32_t* out, cudaStream_t 
     int64_t threads = (n + RAND_PER_THREAD - 1) / RAND_PER_THREAD;
     int blocks = (int)((threads + 127) / 128);
     rand_stream_kernel<<<blocks, 128, 0, s>>>(offset, n, out);
+    g_launches++;
 }
 
 }  // namespace gpc

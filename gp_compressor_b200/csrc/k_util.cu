@@ -96,6 +96,7 @@ void launch_exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, void*
     scan_tile_sums<<<(unsigned)tiles, SCAN_T, 0, s>>>(in, n, sums);
     scan_sums_inplace<<<1, SCAN_T, 0, s>>>(sums, tiles, out + n);
     scan_apply<<<(unsigned)tiles, SCAN_T, 0, s>>>(in, n, sums, out);
+    g_launches += 3;
 }
 
 // ------------------------------------------------------------------------------------
@@ -111,6 +112,7 @@ __global__ void patch_draws_kernel(const int64_t* __restrict__ off, int64_t n_pa
 void launch_patch_draws(const int64_t* off, int64_t n_patches, int mult, int64_t* draws, cudaStream_t s) {
     if (n_patches <= 0) return;
     patch_draws_kernel<<<(unsigned)((n_patches + 255) / 256), 256, 0, s>>>(off, n_patches, mult, draws);
+    g_launches++;
 }
 
 // patch_of[s] = the patch whose range holds stream element s; perm[s] = identity (patch-local)
@@ -153,7 +155,11 @@ void launch_shuffle(const int64_t* off, int64_t n_patches, const int64_t* roff, 
                     int32_t* perm, int32_t* patch_of, int64_t s_begin, int64_t s_count, cudaStream_t s) {
     if (s_count <= 0 || n_patches <= 0) return;
     patch_of_kernel<<<(unsigned)((s_count + 255) / 256), 256, 0, s>>>(off, n_patches, s_begin, s_count, patch_of, perm);
-    if (do_shuffle) shuffle_kernel<<<(unsigned)((n_patches + 127) / 128), 128, 0, s>>>(off, n_patches, roff, rnd, perm);
+    g_launches++;
+    if (do_shuffle) {
+        shuffle_kernel<<<(unsigned)((n_patches + 127) / 128), 128, 0, s>>>(off, n_patches, roff, rnd, perm);
+        g_launches++;
+    }
 }
 
 // fit stream in add order: element t of patch p is point perm[off[p] + t]
@@ -175,6 +181,7 @@ void launch_gather_stream(const int64_t* off, const int32_t* patch_of, const int
                           double* fy, cudaStream_t s) {
     if (s_count <= 0) return;
     gather_stream_kernel<<<(unsigned)((s_count + 255) / 256), 256, 0, s>>>(off, patch_of, perm, x1, x2, y, s_begin, s_count, fx1, fx2, fy);
+    g_launches++;
 }
 
 __global__ void flag_nonempty_kernel(const int32_t* __restrict__ nbv, int64_t n, int64_t* __restrict__ flags) {
@@ -184,6 +191,7 @@ __global__ void flag_nonempty_kernel(const int32_t* __restrict__ nbv, int64_t n,
 void launch_flag_nonempty(const int32_t* nbv, int64_t n, int64_t* flags, cudaStream_t s) {
     if (n <= 0) return;
     flag_nonempty_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(nbv, n, flags);
+    g_launches++;
 }
 
 __global__ void debug_exp_kernel(const double* __restrict__ x, double* __restrict__ out, int64_t n) {

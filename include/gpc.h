@@ -135,6 +135,8 @@ int gpc_set_params(gpc_handle* h, int64_t n_patches, const int32_t* nbv, const d
                    const double* bv2, const double* alpha, const double* quat4,
                    const double* mean3, const double* rgbmean3);
 int gpc_set_rand_offset(gpc_handle* h, uint64_t offset);
+/* the cudaStream_t every kernel and copy of this handle is issued on (for CUDA-event timing by the caller) */
+int gpc_get_stream(gpc_handle* h, void** stream);
 
 /* ---- test hooks: the device versions of the canonical primitives ----------------------- */
 int gpc_debug_exp(gpc_handle* h, const double* x, double* out, int64_t n);
