@@ -32,7 +32,7 @@ struct gpc_handle {
     DevBuf off, x1, x2, y, perm, patch_of;      // claimed stream, patch-major
     DevBuf fx1, fx2, fy;                        // fit stream (add order)
     DevBuf draws, roff, rnd, scan_tmp, small;   // rand bookkeeping, scan scratch, small readbacks
-    DevBuf nbv, flags, alpha, b1, b2, bidx, dumpC, dumpQ, queue0, queue1, qcount, kstats;
+    DevBuf nbv, flags, alpha, b1, b2, bidx, dumpC, dumpQ, queue0, queue1, qcount, kstats, hand0, hand1;
     DevBuf nonempty, slot, out32, heights;
     DevBuf quat, mean, rgbmean, Rm, center, code, ncand, owner, st_idx;
     DevBuf tmpA, tmpB, tmpC;
@@ -199,10 +199,17 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
         a.first_patch = lo;
         a.n_work = (int)work;
         DevBuf& q = (b & 1) ? h->queue1 : h->queue0;
+        DevBuf& ho = (b & 1) ? h->hand1 : h->hand0;
+        DevBuf& hi_ = (b & 1) ? h->hand0 : h->hand1;
         a.queue = final_bucket ? nullptr : q.as<int32_t>();
         a.queue_count = h->qcount.as<int32_t>() + b;
+        a.handoff_in = (b > 0) ? hi_.as<double>() : nullptr;
+        a.handoff_out = nullptr;
+        if (!final_bucket) {
+            CK(ho.reserve((size_t)work * sogp_handoff_slot_bytes(b)));
+            a.handoff_out = ho.as<double>();
+        }
         CK(launch_sogp_fit(b, a, st));
-        g_launches++;
         if (final_bucket) break;
         int32_t qn = 0;
         CK(cudaMemcpyAsync(&qn, h->qcount.as<int32_t>() + b, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -546,7 +553,7 @@ void gpc_destroy(gpc_handle* h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->cloud, &h->off, &h->x1, &h->x2, &h->y, &h->perm, &h->patch_of, &h->fx1, &h->fx2, &h->fy, &h->draws,
                       &h->roff, &h->rnd, &h->scan_tmp, &h->small, &h->nbv, &h->flags, &h->alpha, &h->b1, &h->b2, &h->bidx,
-                      &h->dumpC, &h->dumpQ, &h->queue0, &h->queue1, &h->qcount, &h->kstats, &h->nonempty, &h->slot, &h->out32,
+                      &h->dumpC, &h->dumpQ, &h->queue0, &h->queue1, &h->hand0, &h->hand1, &h->qcount, &h->kstats, &h->nonempty, &h->slot, &h->out32,
                       &h->heights, &h->quat, &h->mean, &h->rgbmean, &h->Rm, &h->center, &h->code, &h->ncand, &h->owner,
                       &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
                       &h->ovals2, &h->sort_tmp, &h->flags64, &h->ex, &h->leaf_of, &h->leaf_start, &h->leaf_code_a, &h->spt,

@@ -115,11 +115,13 @@ struct SogpArgs {
     double *dumpC, *dumpQ;   // optional, (patch - out_first) * capacity^2
     int32_t* queue;          // overflow queue for the next bucket (nullptr: overflow impossible)
     int32_t* queue_count;
+    const double* handoff_in;  // state slots written by the previous bucket (slot = blockIdx.x), or nullptr
+    double* handoff_out;       // state slots for patches that outgrow this bucket (slot = queue position)
     unsigned long long* stats;  // 11 counters, see gpc_stats
 };
 // bucket b supports ld <= {16, 32, 64, 118}
 int sogp_bucket_ld(int bucket);
-size_t sogp_smem_bytes(int ld);
+size_t sogp_handoff_slot_bytes(int bucket);
 cudaError_t launch_sogp_fit(int bucket, const SogpArgs& a, cudaStream_t s);
 
 // ---- K8: grid prediction ----------------------------------------------------------------

@@ -6,14 +6,21 @@
 // sequential (each add depends on the previous state); the parallelism is over patches
 // (grid) and over the N x N state (threads of the CTA).
 //
-// Shared-memory state per CTA: C and Q (ld x ld doubles each, bitwise symmetric, so
-// "row i" is read as the contiguous column i), alpha, BV, and the work vectors.
-// Thread mapping with NT = 2*RB threads: for the two matvecs thread t computes row
-// (t % RB) of matrix (t / RB) with the canonical 4-partial order; for rank-1/rank-2
-// updates thread t owns row (t % RB) and the columns j = (t / RB), (t / RB) + 2, ...
-// The three dot products use the canonical 32-lane order and are computed redundantly by
-// every warp (no broadcast barrier).  Buckets: RB = 16/32/64/128; a patch whose BV count
-// outgrows its bucket is pushed to the next bucket's queue and refitted there.
+// State per CTA in shared memory: C and Q (LD x LD doubles each, bitwise symmetric, so
+// "row i" is read as the contiguous column i: conflict-free), plus work vectors.
+//
+// Bucket 0 (N + 1 <= 16): ONE WARP per patch.  Lane l < 16 owns index l of alpha / BV / k in
+// registers; lanes 0-15 compute rows of C k, lanes 16-31 rows of Q k; the three dot products
+// are one product per lane and one shared butterfly; rank-1 updates split columns between
+// the two half-warps.  No block barrier, only __syncwarp.
+// Buckets 1-3 (LD 32 / 64 / 118): NT = 2*RB threads.  Thread t computes matvec row t % RB of
+// matrix t / RB; for rank-1 / rank-2 updates it owns row t % RB and every second column; the
+// dot products are computed redundantly by every warp (no broadcast barrier).
+//
+// Every patch starts in bucket 0.  When a full update would not fit the bucket, the CTA
+// writes its complete state (N, next point, counters, alpha, BV, C, Q) to a hand-off slot and
+// queues the patch; the next bucket's kernel resumes from that state — no work is redone
+// and the arithmetic is the same in every bucket.
 #include "gpc_device.cuh"
 #include "gpc_internal.h"
 
@@ -21,48 +28,324 @@ namespace gpc {
 
 namespace {
 
-template <int NT>
-__device__ __forceinline__ void cta_sync() {
-    if (NT == 32) __syncwarp(); else __syncthreads();
-}
+constexpr int NCNT = 10;  // first sparse full dcap dgeo sumn n2c n2s n2f n2d
 
-struct Smem {
-    double *C, *Q, *alpha, *b1, *b2, *kv, *ck, *ev, *sv, *qsv, *qcv;
-    int* bidx;
+__host__ __device__ constexpr int slot_doubles(int ld) { return 2 + NCNT + 3 * ld + 2 * ld * ld + (ld + 1) / 2; }
+
+struct Counters {
+    unsigned long long c[NCNT];
+    unsigned int run;  // sparse points seen at the current N, not yet folded into c[]
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int i = 0; i < NCNT; i++) c[i] = 0;
+        run = 0;
+    }
+    __device__ __forceinline__ void flush(int N) {
+        const unsigned long long n2 = (unsigned long long)N * N;
+        c[1] += run; c[5] += (unsigned long long)run * N; c[6] += run * n2; c[7] += run * n2;
+        run = 0;
+    }
+    __device__ __forceinline__ void full(int N) {
+        c[2]++; c[5] += N; c[6] += (unsigned long long)N * N; c[8] += (unsigned long long)(N + 1) * (N + 1);
+    }
 };
 
-__device__ __forceinline__ Smem carve(double* base, int ld) {
-    Smem s;
-    s.C = base;
-    s.Q = s.C + ld * ld;
-    s.alpha = s.Q + ld * ld;
-    s.b1 = s.alpha + ld;
-    s.b2 = s.b1 + ld;
-    s.kv = s.b2 + ld;
-    s.ck = s.kv + ld;
-    s.ev = s.ck + ld;
-    s.sv = s.ev + ld;
-    s.qsv = s.sv + ld;
-    s.qcv = s.qsv + ld;
-    s.bidx = reinterpret_cast<int*>(s.qcv + ld);
-    return s;
+__device__ __forceinline__ void publish(const SogpArgs& a, const Counters& k, int n) {
+    unsigned long long* st = a.stats;
+    atomicAdd(st + 0, (unsigned long long)n);
+#pragma unroll
+    for (int i = 0; i < NCNT; i++)
+        if (k.c[i]) atomicAdd(st + 1 + i, k.c[i]);
 }
 
-// argmin with the reference's "first strict minimum" scan (sparse_gp.hpp:210-217,230-236).
-// MODE 0: score_i = alpha_i^2 / (Q_ii + C_ii);  MODE 1: score_i = 1 / Q_ii.
-// Every lane returns the same (loc, score).  A NaN score never wins unless it is score_0,
-// in which case nothing is ever "< minscore" and loc stays 0 with a NaN minimum.
-template <int MODE>
-__device__ __forceinline__ int warp_argmin(const Smem& s, int ld, int N, int lane, double* minscore) {
+// "first strict minimum" combine of (score, index) pairs (sparse_gp.hpp:210-217, 230-236)
+__device__ __forceinline__ void argmin_combine(double& best, int& bi) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        double ob = shfl_xor_d(best, off);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (oi != 0x7fffffff && (bi == 0x7fffffff || ob < best || (ob == best && oi < bi))) { best = ob; bi = oi; }
+    }
+}
+
+// =====================================================================================
+// Bucket 0: one warp per patch, LD = 16
+// =====================================================================================
+constexpr int W_LD = 16;
+
+__global__ void __launch_bounds__(32, 20) sogp_fit_warp_kernel(SogpArgs a) {
+    __shared__ double C[W_LD * W_LD], Q[W_LD * W_LD], kv[W_LD], sv[W_LD], ev[W_LD];
+    const int lane = threadIdx.x;
+    const int r = lane & 15, mat = lane >> 4;
+    const int64_t patch = a.patch_ids ? (int64_t)a.patch_ids[blockIdx.x] : a.first_patch + blockIdx.x;
+    const int64_t o = a.off[patch];
+    const int n = (int)(a.off[patch + 1] - o);
+    const int64_t op = patch - a.out_first;
+    if (n == 0) {
+        if (lane == 0) { a.nbv[op] = 0; a.flags[op] = 0; }
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < W_LD * W_LD / 32; i++) { C[lane + 32 * i] = 0.0; Q[lane + 32 * i] = 0.0; }
+    __syncwarp();
+    const double kstar = a.p0, s20 = a.s20, p0 = a.p0, cl = a.cl, eps_tol = a.eps_tol;
+    const int cap = a.capacity, ldmax = a.ld;
+    double alpha = 0.0, b1 = 0.0, b2 = 0.0;  // lane l < 16 owns entry l
+    int bidx = -1;
+    int N = 0;
+    Counters cnt;
+    cnt.init();
+    double* const Mrow = (mat ? Q : C) + r;
+
+    double nx1 = a.fx1[o], nx2 = a.fx2[o], ny = a.fy[o];
+    int norig = a.forig[o];
+    for (int tt = 0; tt < n; ++tt) {
+        const double x1 = nx1, x2 = nx2, y = ny;
+        const int orig = norig;
+        if (tt + 1 < n) {
+            nx1 = a.fx1[o + tt + 1]; nx2 = a.fx2[o + tt + 1]; ny = a.fy[o + tt + 1];
+            norig = a.forig[o + tt + 1];
+        }
+        if (N == 0) {  // sparse_gp.hpp:100-110
+            if (lane == 0) {
+                const double d = __dadd_rn(kstar, s20);
+                alpha = __ddiv_rn(y, d);
+                C[0] = __ddiv_rn(-1.0, d);
+                Q[0] = __ddiv_rn(1.0, kstar);
+                b1 = x1; b2 = x2; bidx = orig;
+            }
+            N = 1;
+            cnt.c[0]++;
+            __syncwarp();
+            continue;
+        }
+        // k = K(x, BV) (:119); lanes >= N hold zeros
+        double kl = 0.0;
+        if (lane < N) { kl = rbf(x1, x2, b1, b2, p0, cl); kv[lane] = kl; }
+        __syncwarp();
+        // lanes 0-15: (C k)_r ; lanes 16-31: (Q k)_r = e_hat_r   (:122, :140)
+        double rv = 0.0;
+        if (r < N) rv = row4(Mrow, W_LD, kv, N);
+        const double el = __shfl_down_sync(0xffffffffu, rv, 16);
+        // m = alpha'k, k'Ck, k'e_hat: one product per lane, shared butterfly
+        double pm = 0.0, pc = 0.0, pe = 0.0;
+        if (lane < N) { pm = fma(alpha, kl, 0.0); pc = fma(kl, rv, 0.0); pe = fma(kl, el, 0.0); }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            pm = __dadd_rn(pm, shfl_xor_d(pm, off));
+            pc = __dadd_rn(pc, shfl_xor_d(pc, off));
+            pe = __dadd_rn(pe, shfl_xor_d(pe, off));
+        }
+        const double s2 = __dadd_rn(kstar, pc);
+        const double den = __dadd_rn(s20, s2);
+        const double rr = __ddiv_rn(-1.0, den);               // gaussian_noise.cpp:15-18
+        const double q = __ddiv_rn(__dadd_rn(y, -pm), den);   // gaussian_noise.cpp:9-12
+        double gamma = __dadd_rn(kstar, -pe);                 // :144
+        if (gamma < tiny12()) gamma = 0.0;
+        if (gamma < eps_tol) {
+            // sparse update (:155-163)
+            cnt.run++;
+            const double eta = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn(gamma, rr)));
+            if (lane < N) {
+                const double sh = __dadd_rn(rv, el);
+                sv[lane] = sh;
+                alpha = __dadd_rn(alpha, __dmul_rn(sh, __dmul_rn(q, eta)));
+            }
+            __syncwarp();
+            const double re = __dmul_rn(rr, eta);
+            if (r < N) {
+                const double si = sv[r];
+                for (int j = mat; j < N; j += 2) {
+                    const int idx = j * W_LD + r;
+                    C[idx] = fma(re, __dmul_rn(si, sv[j]), C[idx]);
+                }
+            }
+            continue;  // Q and N unchanged: neither deletion loop can fire
+        }
+        // full update (:164-203)
+        cnt.flush(N);
+        if (N + 1 > ldmax) {  // does not fit this bucket: hand the state to the next one
+            int pos = 0;
+            if (lane == 0) pos = atomicAdd(a.queue_count, 1);
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            double* slot = a.handoff_out + (size_t)pos * slot_doubles(W_LD);
+            if (lane == 0) {
+                a.queue[pos] = (int32_t)patch;
+                reinterpret_cast<int*>(slot)[0] = N;
+                reinterpret_cast<int*>(slot)[1] = tt;
+                for (int i = 0; i < NCNT; i++) reinterpret_cast<unsigned long long*>(slot + 2)[i] = cnt.c[i];
+            }
+            double* v = slot + 2 + NCNT;
+            if (lane < W_LD) {
+                v[lane] = alpha; v[W_LD + lane] = b1; v[2 * W_LD + lane] = b2;
+                reinterpret_cast<int*>(v + 3 * W_LD + 2 * W_LD * W_LD)[lane] = bidx;
+            }
+            for (int i = lane; i < W_LD * W_LD; i += 32) { v[3 * W_LD + i] = C[i]; v[3 * W_LD + W_LD * W_LD + i] = Q[i]; }
+            return;
+        }
+        cnt.full(N);
+        if (lane < N) {
+            sv[lane] = rv;
+            ev[lane] = el;
+            alpha = __dadd_rn(alpha, __dmul_rn(q, rv));
+        }
+        if (lane == N) {
+            sv[N] = 1.0;
+            ev[N] = -1.0;
+            alpha = __dadd_rn(0.0, __dmul_rn(q, 1.0));
+            b1 = x1; b2 = x2; bidx = orig;
+        }
+        __syncwarp();
+        {
+            const double ig = __ddiv_rn(1.0, gamma);
+            const int N1 = N + 1;
+            if (r < N1) {
+                const double si = sv[r], ei = ev[r];
+                for (int j = mat; j < N1; j += 2) {
+                    const int idx = j * W_LD + r;
+                    C[idx] = fma(rr, __dmul_rn(si, sv[j]), C[idx]);
+                    Q[idx] = fma(ig, __dmul_rn(ei, ev[j]), Q[idx]);
+                }
+            }
+            N = N1;
+        }
+        __syncwarp();
+        // capacity deletions (:206-223) then geometric deletions (:226-242)
+        double minscore = 0.0;
+        for (int phase = 0; phase < 2; phase++) {
+            for (;;) {
+                if (phase == 0 ? !(N > cap) : !(minscore < geo9() && N > 1)) break;
+                double best = 0.0;
+                int bi = 0x7fffffff, nan0 = 0;
+                if (lane < N) {
+                    const double qii = Q[lane * W_LD + lane];
+                    const double sc = (phase == 0) ? __ddiv_rn(__dmul_rn(alpha, alpha), __dadd_rn(qii, C[lane * W_LD + lane]))
+                                                   : __ddiv_rn(1.0, qii);
+                    if (sc != sc) nan0 = (lane == 0);
+                    else { best = sc; bi = lane; }
+                }
+                argmin_combine(best, bi);
+                nan0 = __shfl_sync(0xffffffffu, nan0, 0);
+                int loc = bi;
+                if (nan0) { loc = 0; best = __longlong_as_double(0x7ff8000000000000LL); }
+                if (phase == 1) {
+                    minscore = best;
+                    if (!(minscore < geo9())) break;
+                }
+                // ---- delete_bv(loc), :252-295 ----
+                const int L = N - 1, M = N - 1;
+                cnt.c[9] += (unsigned long long)M * M;
+                cnt.c[phase == 0 ? 3 : 4]++;
+                double csi = 0, qsi = 0, repc = 0, repq = 0;
+                const int src = (lane == loc) ? L : lane;
+                if (lane < N) {
+                    csi = C[loc * W_LD + src]; qsi = Q[loc * W_LD + src];
+                    repc = C[L * W_LD + src]; repq = Q[L * W_LD + src];
+                }
+                const double cstar = C[loc * W_LD + loc], qstar = Q[loc * W_LD + loc];
+                const double astar = __shfl_sync(0xffffffffu, alpha, loc);
+                const double aL = __shfl_sync(0xffffffffu, alpha, L);
+                const double b1L = __shfl_sync(0xffffffffu, b1, L), b2L = __shfl_sync(0xffffffffu, b2, L);
+                const int idL = __shfl_sync(0xffffffffu, bidx, L);
+                __syncwarp();
+                const double qcs = __dadd_rn(qstar, cstar);
+                const double coef = __ddiv_rn(astar, qcs);
+                const double iq = __ddiv_rn(1.0, qstar), iqc = __ddiv_rn(1.0, qcs);
+                if (lane < N) {
+                    if (lane < M) {
+                        if (loc != L) {
+                            C[loc * W_LD + lane] = repc; C[lane * W_LD + loc] = repc;
+                            Q[loc * W_LD + lane] = repq; Q[lane * W_LD + loc] = repq;
+                            if (lane == loc) { b1 = b1L; b2 = b2L; bidx = idL; }
+                        }
+                        const double qci = __dadd_rn(qsi, csi);
+                        const double ai = (lane == loc) ? aL : alpha;
+                        alpha = __dadd_rn(ai, -__dmul_rn(coef, qci));
+                        sv[lane] = qsi;   // Qstar
+                        ev[lane] = qci;   // Qstar + Cstar
+                    }
+                    C[L * W_LD + lane] = 0.0; C[lane * W_LD + L] = 0.0;
+                    Q[L * W_LD + lane] = 0.0; Q[lane * W_LD + L] = 0.0;
+                    if (lane == L) { alpha = 0.0; b1 = 0.0; b2 = 0.0; bidx = -1; }
+                }
+                __syncwarp();
+                if (r < M) {
+                    const double qi = sv[r], ci = ev[r];
+                    for (int j = mat; j < M; j += 2) {
+                        const int idx = j * W_LD + r;
+                        const double u = __dmul_rn(qi, sv[j]);
+                        const double v = __dmul_rn(ci, ev[j]);
+                        const double w = fma(u, iq, -__dmul_rn(v, iqc));
+                        C[idx] = __dadd_rn(C[idx], w);
+                        Q[idx] = fma(-u, iq, Q[idx]);
+                    }
+                }
+                N = M;
+                __syncwarp();
+            }
+        }
+    }
+    cnt.flush(N);
+    __syncwarp();
+    if (lane == 0) {
+        a.nbv[op] = N;
+        const double c00 = C[0];
+        a.flags[op] = (c00 != c00) ? 1 : 0;
+        publish(a, cnt, n);
+    }
+    const int64_t ob = op * cap;
+    if (lane < N) {
+        a.o_alpha[ob + lane] = alpha;
+        a.o_b1[ob + lane] = b1;
+        a.o_b2[ob + lane] = b2;
+        a.o_idx[ob + lane] = bidx;
+    }
+    if (a.dumpC) {
+        const int64_t od = op * (int64_t)cap * cap;
+        for (int e = lane; e < N * N; e += 32) {
+            const int i = e / N, j = e - i * N;
+            a.dumpC[od + e] = C[j * W_LD + i];
+            a.dumpQ[od + e] = Q[j * W_LD + i];
+        }
+    }
+}
+
+// =====================================================================================
+// Buckets 1-3: NT = 2*RB threads per patch, LD constexpr
+// =====================================================================================
+template <int NT>
+__device__ __forceinline__ void cta_sync() {
+    __syncthreads();
+}
+
+template <int LD>
+struct Smem {
+    double* base;
+    __device__ __forceinline__ double* C() const { return base; }
+    __device__ __forceinline__ double* Q() const { return base + LD * LD; }
+    __device__ __forceinline__ double* alpha() const { return base + 2 * LD * LD; }
+    __device__ __forceinline__ double* b1() const { return base + 2 * LD * LD + LD; }
+    __device__ __forceinline__ double* b2() const { return base + 2 * LD * LD + 2 * LD; }
+    __device__ __forceinline__ double* kv() const { return base + 2 * LD * LD + 3 * LD; }
+    __device__ __forceinline__ double* ck() const { return base + 2 * LD * LD + 4 * LD; }
+    __device__ __forceinline__ double* ev() const { return base + 2 * LD * LD + 5 * LD; }
+    __device__ __forceinline__ double* sv() const { return base + 2 * LD * LD + 6 * LD; }
+    __device__ __forceinline__ double* qsv() const { return base + 2 * LD * LD + 7 * LD; }
+    __device__ __forceinline__ double* qcv() const { return base + 2 * LD * LD + 8 * LD; }
+    __device__ __forceinline__ int* bidx() const { return reinterpret_cast<int*>(base + 2 * LD * LD + 9 * LD); }
+};
+
+template <int LD, int MODE>
+__device__ __forceinline__ int warp_argmin(const Smem<LD>& s, int N, int lane, double* minscore) {
     double best = 0.0;
     int bi = 0x7fffffff;
     int nan0 = 0;
     for (int i = lane; i < N; i += 32) {
-        double qii = s.Q[i * ld + i];
+        const double qii = s.Q()[i * LD + i];
         double sc;
         if (MODE == 0) {
-            double a = s.alpha[i];
-            sc = __ddiv_rn(__dmul_rn(a, a), __dadd_rn(qii, s.C[i * ld + i]));
+            const double al = s.alpha()[i];
+            sc = __ddiv_rn(__dmul_rn(al, al), __dadd_rn(qii, s.C()[i * LD + i]));
         } else {
             sc = __ddiv_rn(1.0, qii);
         }
@@ -72,12 +355,7 @@ __device__ __forceinline__ int warp_argmin(const Smem& s, int ld, int N, int lan
         }
         if (bi == 0x7fffffff || sc < best) { best = sc; bi = i; }
     }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        double ob = shfl_xor_d(best, off);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-        if (oi != 0x7fffffff && (bi == 0x7fffffff || ob < best || (ob == best && oi < bi))) { best = ob; bi = oi; }
-    }
+    argmin_combine(best, bi);
     nan0 = __shfl_sync(0xffffffffu, nan0, 0);
     if (nan0) {
         *minscore = __longlong_as_double(0x7ff8000000000000LL);
@@ -88,66 +366,66 @@ __device__ __forceinline__ int warp_argmin(const Smem& s, int ld, int N, int lan
 }
 
 // sparse_gp::delete_bv, sparse_gp.hpp:252-295.  Uniform across the CTA; ends with a barrier.
-template <int RB, int NT>
-__device__ __forceinline__ void delete_bv(const Smem& s, int ld, int& N, int loc, int t) {
+template <int LD, int RB, int NT>
+__device__ __forceinline__ void delete_bv(const Smem<LD>& s, int& N, int loc, int t) {
     const int L = N - 1, M = N - 1;
     const int irow = t & (RB - 1), jg = t / RB;
+    double* const C = s.C();
+    double* const Q = s.Q();
     double csi = 0, qsi = 0, repc = 0, repq = 0, ai = 0, nb1 = 0, nb2 = 0;
     int nidx = -1;
     if (t < N) {
-        const int i = t;
-        const int src = (i == loc) ? L : i;  // Cs(loc) = Cs(L), Crep(loc) = Crep(L), alpha(loc) = alpha(L)
-        csi = s.C[loc * ld + src];
-        qsi = s.Q[loc * ld + src];
-        repc = s.C[L * ld + src];
-        repq = s.Q[L * ld + src];
-        ai = s.alpha[src];
-        if (i == loc) { nb1 = s.b1[L]; nb2 = s.b2[L]; nidx = s.bidx[L]; }
+        const int src = (t == loc) ? L : t;  // Cs(loc) = Cs(L), Crep(loc) = Crep(L), alpha(loc) = alpha(L)
+        csi = C[loc * LD + src];
+        qsi = Q[loc * LD + src];
+        repc = C[L * LD + src];
+        repq = Q[L * LD + src];
+        ai = s.alpha()[src];
+        if (t == loc) { nb1 = s.b1()[L]; nb2 = s.b2()[L]; nidx = s.bidx()[L]; }
     }
-    const double cstar = s.C[loc * ld + loc], qstar = s.Q[loc * ld + loc], astar = s.alpha[loc];
+    const double cstar = C[loc * LD + loc], qstar = Q[loc * LD + loc], astar = s.alpha()[loc];
     cta_sync<NT>();
     const double qcs = __dadd_rn(qstar, cstar);
     const double coef = __ddiv_rn(astar, qcs);
     const double iq = __ddiv_rn(1.0, qstar), iqc = __ddiv_rn(1.0, qcs);
     if (t < N) {
-        const int i = t;
-        if (i < M) {
+        if (t < M) {
             if (loc != L) {
-                s.C[loc * ld + i] = repc; s.C[i * ld + loc] = repc;
-                s.Q[loc * ld + i] = repq; s.Q[i * ld + loc] = repq;
-                if (i == loc) { s.b1[loc] = nb1; s.b2[loc] = nb2; s.bidx[loc] = nidx; }
+                C[loc * LD + t] = repc; C[t * LD + loc] = repc;
+                Q[loc * LD + t] = repq; Q[t * LD + loc] = repq;
+                if (t == loc) { s.b1()[loc] = nb1; s.b2()[loc] = nb2; s.bidx()[loc] = nidx; }
             }
-            double qci = __dadd_rn(qsi, csi);
-            s.alpha[i] = __dadd_rn(ai, -__dmul_rn(coef, qci));
-            s.qsv[i] = qsi;
-            s.qcv[i] = qci;
+            const double qci = __dadd_rn(qsi, csi);
+            s.alpha()[t] = __dadd_rn(ai, -__dmul_rn(coef, qci));
+            s.qsv()[t] = qsi;
+            s.qcv()[t] = qci;
         }
-        s.C[L * ld + i] = 0.0; s.C[i * ld + L] = 0.0;
-        s.Q[L * ld + i] = 0.0; s.Q[i * ld + L] = 0.0;
-        if (i == L) { s.alpha[L] = 0.0; s.b1[L] = 0.0; s.b2[L] = 0.0; s.bidx[L] = -1; }
+        C[L * LD + t] = 0.0; C[t * LD + L] = 0.0;
+        Q[L * LD + t] = 0.0; Q[t * LD + L] = 0.0;
+        if (t == L) { s.alpha()[L] = 0.0; s.b1()[L] = 0.0; s.b2()[L] = 0.0; s.bidx()[L] = -1; }
     }
     cta_sync<NT>();
     if (irow < M) {
-        const double qi = s.qsv[irow], ci = s.qcv[irow];
+        const double qi = s.qsv()[irow], ci = s.qcv()[irow];
         for (int j = jg; j < M; j += 2) {
-            const int idx = j * ld + irow;
-            double u = __dmul_rn(qi, s.qsv[j]);
-            double v = __dmul_rn(ci, s.qcv[j]);
-            double tt = __dmul_rn(v, iqc);
-            double w = fma(u, iq, -tt);
-            s.C[idx] = __dadd_rn(s.C[idx], w);
-            s.Q[idx] = fma(-u, iq, s.Q[idx]);
+            const int idx = j * LD + irow;
+            const double u = __dmul_rn(qi, s.qsv()[j]);
+            const double v = __dmul_rn(ci, s.qcv()[j]);
+            const double w = fma(u, iq, -__dmul_rn(v, iqc));
+            C[idx] = __dadd_rn(C[idx], w);
+            Q[idx] = fma(-u, iq, Q[idx]);
         }
     }
     N = M;
     cta_sync<NT>();
 }
 
-template <int RB, int NT>
+template <int LD, int RB, int NT, int LD_IN>
 __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
     extern __shared__ double smem_d[];
-    const int ld = a.ld;
-    const Smem s = carve(smem_d, ld);
+    const Smem<LD> s{smem_d};
+    double* const C = s.C();
+    double* const Q = s.Q();
     const int t = threadIdx.x, lane = t & 31;
     const int irow = t & (RB - 1), jg = t / RB;
     const int64_t patch = a.patch_ids ? (int64_t)a.patch_ids[blockIdx.x] : a.first_patch + blockIdx.x;
@@ -158,19 +436,37 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
         if (t == 0) { a.nbv[op] = 0; a.flags[op] = 0; }
         return;
     }
-    for (int i = t; i < 2 * ld * ld + 9 * ld; i += NT) smem_d[i] = 0.0;
-    for (int i = t; i < ld; i += NT) s.bidx[i] = -1;
+    for (int i = t; i < 2 * LD * LD + 9 * LD; i += NT) smem_d[i] = 0.0;
+    for (int i = t; i < LD; i += NT) s.bidx()[i] = -1;
     cta_sync<NT>();
 
     const double kstar = a.p0, s20 = a.s20, p0 = a.p0, cl = a.cl, eps_tol = a.eps_tol;
-    const int cap = a.capacity;
-    int N = 0;
-    unsigned long long c_first = 0, c_sparse = 0, c_full = 0, c_dcap = 0, c_dgeo = 0;
-    unsigned long long c_sumn = 0, c_n2c = 0, c_n2s = 0, c_n2f = 0, c_n2d = 0;
+    const int cap = a.capacity, ldmax = a.ld;
+    int N = 0, tt0 = 0;
+    Counters cnt;
+    cnt.init();
+    if (a.handoff_in) {  // resume a patch that outgrew the previous bucket
+        const double* slot = a.handoff_in + (size_t)blockIdx.x * slot_doubles(LD_IN);
+        N = reinterpret_cast<const int*>(slot)[0];
+        tt0 = reinterpret_cast<const int*>(slot)[1];
+#pragma unroll
+        for (int i = 0; i < NCNT; i++) cnt.c[i] = reinterpret_cast<const unsigned long long*>(slot + 2)[i];
+        const double* v = slot + 2 + NCNT;
+        for (int i = t; i < LD_IN; i += NT) {
+            s.alpha()[i] = v[i]; s.b1()[i] = v[LD_IN + i]; s.b2()[i] = v[2 * LD_IN + i];
+            s.bidx()[i] = reinterpret_cast<const int*>(v + 3 * LD_IN + 2 * LD_IN * LD_IN)[i];
+        }
+        for (int e = t; e < LD_IN * LD_IN; e += NT) {
+            const int j = e / LD_IN, i = e - j * LD_IN;
+            C[j * LD + i] = v[3 * LD_IN + e];
+            Q[j * LD + i] = v[3 * LD_IN + LD_IN * LD_IN + e];
+        }
+        cta_sync<NT>();
+    }
 
-    double nx1 = a.fx1[o], nx2 = a.fx2[o], ny = a.fy[o];
-    int norig = a.forig[o];
-    for (int tt = 0; tt < n; ++tt) {
+    double nx1 = a.fx1[o + tt0], nx2 = a.fx2[o + tt0], ny = a.fy[o + tt0];
+    int norig = a.forig[o + tt0];
+    for (int tt = tt0; tt < n; ++tt) {
         const double x1 = nx1, x2 = nx2, y = ny;
         const int orig = norig;
         if (tt + 1 < n) {  // prefetch the next point of the stream
@@ -179,35 +475,32 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
         }
         if (N == 0) {  // sparse_gp.hpp:100-110
             if (t == 0) {
-                double d = __dadd_rn(kstar, s20);
-                s.alpha[0] = __ddiv_rn(y, d);
-                s.C[0] = __ddiv_rn(-1.0, d);
-                s.Q[0] = __ddiv_rn(1.0, kstar);
-                s.b1[0] = x1; s.b2[0] = x2; s.bidx[0] = orig;
+                const double d = __dadd_rn(kstar, s20);
+                s.alpha()[0] = __ddiv_rn(y, d);
+                C[0] = __ddiv_rn(-1.0, d);
+                Q[0] = __ddiv_rn(1.0, kstar);
+                s.b1()[0] = x1; s.b2()[0] = x2; s.bidx()[0] = orig;
             }
             N = 1;
-            c_first++;
+            cnt.c[0]++;
             cta_sync<NT>();
             continue;
         }
-        c_sumn += N;
-        c_n2c += (unsigned long long)N * N;
         // k = K(x, BV)  (sparse_gp.hpp:119)
-        if (t < N) s.kv[t] = rbf(x1, x2, s.b1[t], s.b2[t], p0, cl);
+        if (t < N) s.kv()[t] = rbf(x1, x2, s.b1()[t], s.b2()[t], p0, cl);
         cta_sync<NT>();
         // C k and e_hat = Q k (:122,:140), m = alpha' k (:121)
         if (irow < N) {
-            const double* Mx = jg ? s.Q : s.C;
-            double r = row4(Mx + irow, ld, s.kv, N);
-            (jg ? s.ev : s.ck)[irow] = r;
+            const double rv = row4((jg ? Q : C) + irow, LD, s.kv(), N);
+            (jg ? s.ev() : s.ck())[irow] = rv;
         }
-        const double m = warp_dot32(s.alpha, s.kv, N, lane);
+        const double m = warp_dot32(s.alpha(), s.kv(), N, lane);
         cta_sync<NT>();
         double kck = 0.0, ke = 0.0;
         for (int j = lane; j < N; j += 32) {
-            double kj = s.kv[j];
-            kck = fma(kj, s.ck[j], kck);
-            ke = fma(kj, s.ev[j], ke);
+            const double kj = s.kv()[j];
+            kck = fma(kj, s.ck()[j], kck);
+            ke = fma(kj, s.ev()[j], ke);
         }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
@@ -216,62 +509,74 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
         }
         const double s2 = __dadd_rn(kstar, kck);
         const double den = __dadd_rn(s20, s2);
-        const double r = __ddiv_rn(-1.0, den);                // gaussian_noise.cpp:15-18
+        const double rr = __ddiv_rn(-1.0, den);               // gaussian_noise.cpp:15-18
         const double q = __ddiv_rn(__dadd_rn(y, -m), den);    // gaussian_noise.cpp:9-12
         double gamma = __dadd_rn(kstar, -ke);                 // sparse_gp.hpp:144
         if (gamma < tiny12()) gamma = 0.0;
         if (gamma < eps_tol) {
             // sparse update (sparse_gp.hpp:155-163)
-            c_sparse++;
-            c_n2s += (unsigned long long)N * N;
-            const double eta = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn(gamma, r)));
+            cnt.run++;
+            const double eta = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn(gamma, rr)));
             if (t < N) {
-                double sh = __dadd_rn(s.ck[t], s.ev[t]);
-                s.sv[t] = sh;
-                s.alpha[t] = __dadd_rn(s.alpha[t], __dmul_rn(sh, __dmul_rn(q, eta)));
+                const double sh = __dadd_rn(s.ck()[t], s.ev()[t]);
+                s.sv()[t] = sh;
+                s.alpha()[t] = __dadd_rn(s.alpha()[t], __dmul_rn(sh, __dmul_rn(q, eta)));
             }
             cta_sync<NT>();
-            const double re = __dmul_rn(r, eta);
+            const double re = __dmul_rn(rr, eta);
             if (irow < N) {
-                const double si = s.sv[irow];
+                const double si = s.sv()[irow];
                 for (int j = jg; j < N; j += 2) {
-                    const int idx = j * ld + irow;
-                    s.C[idx] = fma(re, __dmul_rn(si, s.sv[j]), s.C[idx]);
+                    const int idx = j * LD + irow;
+                    C[idx] = fma(re, __dmul_rn(si, s.sv()[j]), C[idx]);
                 }
             }
             continue;  // Q and N unchanged: neither deletion loop can fire
         }
         // full update (sparse_gp.hpp:164-203)
-        if (N + 1 > ld) {  // does not fit this bucket: hand the patch to the next one
+        cnt.flush(N);
+        if (N + 1 > ldmax) {  // does not fit this bucket: hand the state to the next one
+            __shared__ int spos;
+            if (t == 0) spos = atomicAdd(a.queue_count, 1);
+            cta_sync<NT>();
+            const int pos = spos;
+            double* slot = a.handoff_out + (size_t)pos * slot_doubles(LD);
             if (t == 0) {
-                int pos = atomicAdd(a.queue_count, 1);
                 a.queue[pos] = (int32_t)patch;
+                reinterpret_cast<int*>(slot)[0] = N;
+                reinterpret_cast<int*>(slot)[1] = tt;
+                for (int i = 0; i < NCNT; i++) reinterpret_cast<unsigned long long*>(slot + 2)[i] = cnt.c[i];
             }
+            double* v = slot + 2 + NCNT;
+            for (int i = t; i < LD; i += NT) {
+                v[i] = s.alpha()[i]; v[LD + i] = s.b1()[i]; v[2 * LD + i] = s.b2()[i];
+                reinterpret_cast<int*>(v + 3 * LD + 2 * LD * LD)[i] = s.bidx()[i];
+            }
+            for (int i = t; i < LD * LD; i += NT) { v[3 * LD + i] = C[i]; v[3 * LD + LD * LD + i] = Q[i]; }
             return;
         }
-        c_full++;
-        c_n2f += (unsigned long long)(N + 1) * (N + 1);
+        cnt.full(N);
         if (t < N) {
-            double sc = s.ck[t];
-            s.sv[t] = sc;
-            s.alpha[t] = __dadd_rn(s.alpha[t], __dmul_rn(q, sc));
+            const double sc = s.ck()[t];
+            s.sv()[t] = sc;
+            s.alpha()[t] = __dadd_rn(s.alpha()[t], __dmul_rn(q, sc));
         }
         if (t == N) {
-            s.sv[N] = 1.0;
-            s.alpha[N] = __dadd_rn(0.0, __dmul_rn(q, 1.0));
-            s.ev[N] = -1.0;
-            s.b1[N] = x1; s.b2[N] = x2; s.bidx[N] = orig;
+            s.sv()[N] = 1.0;
+            s.alpha()[N] = __dadd_rn(0.0, __dmul_rn(q, 1.0));
+            s.ev()[N] = -1.0;
+            s.b1()[N] = x1; s.b2()[N] = x2; s.bidx()[N] = orig;
         }
         cta_sync<NT>();
         {
             const double ig = __ddiv_rn(1.0, gamma);
             const int N1 = N + 1;
             if (irow < N1) {
-                const double si = s.sv[irow], ei = s.ev[irow];
+                const double si = s.sv()[irow], ei = s.ev()[irow];
                 for (int j = jg; j < N1; j += 2) {
-                    const int idx = j * ld + irow;
-                    s.C[idx] = fma(r, __dmul_rn(si, s.sv[j]), s.C[idx]);
-                    s.Q[idx] = fma(ig, __dmul_rn(ei, s.ev[j]), s.Q[idx]);
+                    const int idx = j * LD + irow;
+                    C[idx] = fma(rr, __dmul_rn(si, s.sv()[j]), C[idx]);
+                    Q[idx] = fma(ig, __dmul_rn(ei, s.ev()[j]), Q[idx]);
                 }
             }
             N = N1;
@@ -280,51 +585,64 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
         // capacity deletions (sparse_gp.hpp:206-223)
         while (N > cap) {
             double ms;
-            int loc = warp_argmin<0>(s, ld, N, lane, &ms);
-            c_n2d += (unsigned long long)(N - 1) * (N - 1);
-            delete_bv<RB, NT>(s, ld, N, loc, t);
-            c_dcap++;
+            const int loc = warp_argmin<LD, 0>(s, N, lane, &ms);
+            cnt.c[9] += (unsigned long long)(N - 1) * (N - 1);
+            delete_bv<LD, RB, NT>(s, N, loc, t);
+            cnt.c[3]++;
         }
         // geometric deletions (sparse_gp.hpp:226-242)
         {
             double minscore = 0.0;
             while (minscore < geo9() && N > 1) {
-                int loc = warp_argmin<1>(s, ld, N, lane, &minscore);
+                const int loc = warp_argmin<LD, 1>(s, N, lane, &minscore);
                 if (minscore < geo9()) {
-                    c_n2d += (unsigned long long)(N - 1) * (N - 1);
-                    delete_bv<RB, NT>(s, ld, N, loc, t);
-                    c_dgeo++;
+                    cnt.c[9] += (unsigned long long)(N - 1) * (N - 1);
+                    delete_bv<LD, RB, NT>(s, N, loc, t);
+                    cnt.c[4]++;
                 }
             }
         }
     }
+    cnt.flush(N);
     cta_sync<NT>();
     // results
     if (t == 0) {
         a.nbv[op] = N;
-        double c00 = s.C[0];
+        const double c00 = C[0];
         a.flags[op] = (c00 != c00) ? 1 : 0;
-        unsigned long long* st = a.stats;
-        atomicAdd(st + 0, (unsigned long long)n);
-        atomicAdd(st + 1, c_first); atomicAdd(st + 2, c_sparse); atomicAdd(st + 3, c_full);
-        atomicAdd(st + 4, c_dcap); atomicAdd(st + 5, c_dgeo); atomicAdd(st + 6, c_sumn);
-        atomicAdd(st + 7, c_n2c); atomicAdd(st + 8, c_n2s); atomicAdd(st + 9, c_n2f); atomicAdd(st + 10, c_n2d);
+        publish(a, cnt, n - 0);
     }
     const int64_t ob = op * cap;
     for (int i = t; i < N; i += NT) {
-        a.o_alpha[ob + i] = s.alpha[i];
-        a.o_b1[ob + i] = s.b1[i];
-        a.o_b2[ob + i] = s.b2[i];
-        a.o_idx[ob + i] = s.bidx[i];
+        a.o_alpha[ob + i] = s.alpha()[i];
+        a.o_b1[ob + i] = s.b1()[i];
+        a.o_b2[ob + i] = s.b2()[i];
+        a.o_idx[ob + i] = s.bidx()[i];
     }
     if (a.dumpC) {
         const int64_t od = op * (int64_t)cap * cap;
         for (int e = t; e < N * N; e += NT) {
-            int i = e / N, j = e - i * N;
-            a.dumpC[od + e] = s.C[j * ld + i];
-            a.dumpQ[od + e] = s.Q[j * ld + i];
+            const int i = e / N, j = e - i * N;
+            a.dumpC[od + e] = C[j * LD + i];
+            a.dumpQ[od + e] = Q[j * LD + i];
         }
     }
+}
+
+template <int LD>
+constexpr size_t cta_smem_bytes() { return (size_t)(2 * LD * LD + 9 * LD) * sizeof(double) + (size_t)LD * sizeof(int); }
+
+template <int LD, int RB, int NT, int LD_IN>
+cudaError_t launch_cta_bucket(const SogpArgs& a, cudaStream_t st) {
+    constexpr size_t smem = cta_smem_bytes<LD>();
+    static bool configured = false;
+    if (smem > 48 * 1024 && !configured) {
+        cudaError_t e = cudaFuncSetAttribute(sogp_fit_kernel<LD, RB, NT, LD_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    sogp_fit_kernel<LD, RB, NT, LD_IN><<<a.n_work, NT, smem, st>>>(a);
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -334,28 +652,18 @@ int sogp_bucket_ld(int bucket) {
     return lds[bucket];
 }
 
-size_t sogp_smem_bytes(int ld) { return (size_t)(2 * ld * ld + 9 * ld) * sizeof(double) + (size_t)ld * sizeof(int); }
-
-template <int RB, int NT>
-static cudaError_t launch_bucket(const SogpArgs& a, cudaStream_t st) {
-    size_t smem = sogp_smem_bytes(a.ld);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(sogp_fit_kernel<RB, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
-    sogp_fit_kernel<RB, NT><<<a.n_work, NT, smem, st>>>(a);
-    return cudaGetLastError();
-}
+size_t sogp_handoff_slot_bytes(int bucket) { return (size_t)slot_doubles(sogp_bucket_ld(bucket)) * sizeof(double); }
 
 cudaError_t launch_sogp_fit(int bucket, const SogpArgs& a, cudaStream_t st) {
     if (a.n_work <= 0) return cudaSuccess;
+    g_launches++;
     switch (bucket) {
-        case 0: return launch_bucket<16, 32>(a, st);
-        case 1: return launch_bucket<32, 64>(a, st);
-        case 2: return launch_bucket<64, 128>(a, st);
-        default: return launch_bucket<128, 256>(a, st);
+        case 0:
+            sogp_fit_warp_kernel<<<a.n_work, 32, 0, st>>>(a);
+            return cudaGetLastError();
+        case 1: return launch_cta_bucket<32, 32, 64, 16>(a, st);
+        case 2: return launch_cta_bucket<64, 64, 128, 32>(a, st);
+        default: return launch_cta_bucket<118, 128, 256, 64>(a, st);
     }
 }
 
