@@ -25,7 +25,7 @@ struct gpc_handle {
     int64_t n_in = 0, n_patches = 0, n_claimed = 0, patch_lo = 0, patch_hi = 0, n_decoded = 0, n_bv_total = -1;
     uint32_t depth = 0;
     double lattice_min[3] = {0, 0, 0};
-    bool have_fit = false, have_frames = false, have_binning = false, have_cloud = false;
+    bool have_fit = false, have_frames = false, have_binning = false, have_cloud = false, params_packed = false;
     int64_t s_begin = 0, s_count = 0;  // stream range of this shard
     // device buffers
     DevBuf cloud;                               // input cloud (n_in * 32)
@@ -34,6 +34,7 @@ struct gpc_handle {
     DevBuf draws, roff, rnd, scan_tmp, small;   // rand bookkeeping, scan scratch, small readbacks
     DevBuf nbv, flags, alpha, b1, b2, bidx, dumpC, dumpQ, queue0, queue1, qcount, kstats, hand0, hand1;
     DevBuf nonempty, slot, out32, heights;
+    DevBuf bv_off, palpha, pb1, pb2, pidx;      // packed copies of the fitted parameters (what leaves for the host)
     DevBuf quat, mean, rgbmean, Rm, center, code, ncand, owner, st_idx;
     DevBuf tmpA, tmpB, tmpC;
     // binning scratch
@@ -220,8 +221,25 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
     }
     size_t t2 = tm.mark();
     tm.span(&h->stats.ms_fit, t1, t2);
+    // pack the parameters on the device: what the host fetches is sum(nbv) entries, not capacity per patch
+    CK(h->bv_off.reserve((PLa + 1) * sizeof(int64_t)));
+    CK(h->nonempty.reserve((PLa + 1) * sizeof(int64_t)));
+    CK(h->scan_tmp.reserve(scan_tmp_bytes(PLa + 1)));
+    CK(h->palpha.reserve(PLa * cap * sizeof(double)));
+    CK(h->pb1.reserve(PLa * cap * sizeof(double)));
+    CK(h->pb2.reserve(PLa * cap * sizeof(double)));
+    CK(h->pidx.reserve(PLa * cap * sizeof(int32_t)));
+    launch_compact_params(h->nbv.as<int32_t>(), PL, cap, h->alpha.as<double>(), h->b1.as<double>(), h->b2.as<double>(),
+                          h->bidx.as<int32_t>(), h->nonempty.as<int64_t>(), h->bv_off.as<int64_t>(), h->scan_tmp.p,
+                          h->palpha.as<double>(), h->pb1.as<double>(), h->pb2.as<double>(), h->pidx.as<int32_t>(), st);
+    int64_t tot = 0;
+    CK(cudaMemcpyAsync(&tot, h->bv_off.as<int64_t>() + PL, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    h->n_bv_total = tot;
+    size_t t3 = tm.mark();
+    tm.span(&h->stats.ms_group, t2, t3);
     h->have_fit = true;
-    h->n_bv_total = -1;
+    h->params_packed = true;
     return GPC_OK;
 }
 
@@ -493,6 +511,8 @@ int compress_resident_impl(gpc_handle* h, StageTimer& tm) {
         h->s_begin = h->s_count = 0;
         h->have_fit = true;
         h->n_bv_total = 0;
+        h->params_packed = false;
+        CK(h->nbv.reserve(sizeof(int32_t)));
         return GPC_OK;
     }
     return run_fit(h, tm);
@@ -553,7 +573,7 @@ void gpc_destroy(gpc_handle* h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->cloud, &h->off, &h->x1, &h->x2, &h->y, &h->perm, &h->patch_of, &h->fx1, &h->fx2, &h->fy, &h->draws,
                       &h->roff, &h->rnd, &h->scan_tmp, &h->small, &h->nbv, &h->flags, &h->alpha, &h->b1, &h->b2, &h->bidx,
-                      &h->dumpC, &h->dumpQ, &h->queue0, &h->queue1, &h->hand0, &h->hand1, &h->qcount, &h->kstats, &h->nonempty, &h->slot, &h->out32,
+                      &h->dumpC, &h->dumpQ, &h->queue0, &h->queue1, &h->hand0, &h->hand1, &h->qcount, &h->kstats, &h->bv_off, &h->palpha, &h->pb1, &h->pb2, &h->pidx, &h->nonempty, &h->slot, &h->out32,
                       &h->heights, &h->quat, &h->mean, &h->rgbmean, &h->Rm, &h->center, &h->code, &h->ncand, &h->owner,
                       &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
                       &h->ovals2, &h->sort_tmp, &h->flags64, &h->ex, &h->leaf_of, &h->leaf_start, &h->leaf_code_a, &h->spt,
@@ -753,13 +773,9 @@ int gpc_predict(gpc_handle* h, int64_t patch, const double* X, int64_t m, double
 int gpc_get_sizes(gpc_handle* h, gpc_sizes* s) {
     if (!h || !s) return GPC_ERR_INVALID;
     CK(cudaSetDevice(h->cfg.device));
-    if (h->have_fit && h->n_bv_total < 0) {
-        const int64_t PL = h->patch_hi - h->patch_lo;
-        std::vector<int32_t> nb(PL);
-        if (PL > 0) CK(cudaMemcpy(nb.data(), h->nbv.p, PL * sizeof(int32_t), cudaMemcpyDeviceToHost));
-        int64_t t = 0;
-        for (int32_t v : nb) t += v;
-        h->n_bv_total = t;
+    if (h->have_fit && !h->params_packed) {
+        int rc = gpc_get_params(h, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        if (rc) return rc;
     }
     s->n_in = h->n_in; s->n_patches = h->n_patches; s->n_claimed = h->n_claimed;
     s->n_bv_total = h->have_fit ? h->n_bv_total : 0;
@@ -781,29 +797,37 @@ int gpc_get_params(gpc_handle* h, int32_t* nbv, int64_t* bv_off, int32_t* bv_ind
     if (!h) return GPC_ERR_INVALID;
     if (!h->have_fit) return fail(h, GPC_ERR_STATE, "no fit held by the handle");
     CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->stream;
     const int64_t PL = h->patch_hi - h->patch_lo;
     const int cap = h->cfg.capacity;
-    std::vector<int32_t> nb(PL);
-    if (PL > 0) CK(cudaMemcpy(nb.data(), h->nbv.p, PL * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    if (nbv) std::memcpy(nbv, nb.data(), PL * sizeof(int32_t));
-    if (flags && PL > 0) CK(cudaMemcpy(flags, h->flags.p, PL * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    std::vector<int64_t> bo(PL + 1, 0);
-    for (int64_t p = 0; p < PL; p++) bo[p + 1] = bo[p] + nb[p];
-    if (bv_off) std::memcpy(bv_off, bo.data(), (PL + 1) * sizeof(int64_t));
-    // strided device arrays -> compact host arrays (results leave through the host here)
-    auto compact = [&](const DevBuf& src, void* dst, size_t esz) -> int {
-        if (!dst || PL == 0) return GPC_OK;
-        std::vector<uint8_t> tmp((size_t)PL * cap * esz);
-        CK(cudaMemcpy(tmp.data(), src.p, tmp.size(), cudaMemcpyDeviceToHost));
-        for (int64_t p = 0; p < PL; p++)
-            std::memcpy((uint8_t*)dst + bo[p] * esz, tmp.data() + (size_t)p * cap * esz, (size_t)nb[p] * esz);
-        return GPC_OK;
-    };
-    int rc;
-    if ((rc = compact(h->bidx, bv_index, sizeof(int32_t)))) return rc;
-    if ((rc = compact(h->b1, bv1, sizeof(double)))) return rc;
-    if ((rc = compact(h->b2, bv2, sizeof(double)))) return rc;
-    if ((rc = compact(h->alpha, alpha, sizeof(double)))) return rc;
+    if (!h->params_packed) {  // parameters installed by gpc_set_params: pack them now
+        const int64_t PLa = std::max<int64_t>(PL, 1);
+        CK(h->bv_off.reserve((PLa + 1) * sizeof(int64_t)));
+        CK(h->nonempty.reserve((PLa + 1) * sizeof(int64_t)));
+        CK(h->scan_tmp.reserve(scan_tmp_bytes(PLa + 1)));
+        CK(h->palpha.reserve(PLa * cap * sizeof(double)));
+        CK(h->pb1.reserve(PLa * cap * sizeof(double)));
+        CK(h->pb2.reserve(PLa * cap * sizeof(double)));
+        CK(h->pidx.reserve(PLa * cap * sizeof(int32_t)));
+        CK(h->bidx.reserve(PLa * cap * sizeof(int32_t)));
+        launch_compact_params(h->nbv.as<int32_t>(), PL, cap, h->alpha.as<double>(), h->b1.as<double>(), h->b2.as<double>(),
+                              h->bidx.as<int32_t>(), h->nonempty.as<int64_t>(), h->bv_off.as<int64_t>(), h->scan_tmp.p,
+                              h->palpha.as<double>(), h->pb1.as<double>(), h->pb2.as<double>(), h->pidx.as<int32_t>(), st);
+        int64_t tot = 0;
+        CK(cudaMemcpyAsync(&tot, h->bv_off.as<int64_t>() + PL, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        h->n_bv_total = tot;
+        h->params_packed = true;
+    }
+    const int64_t T = h->n_bv_total;
+    if (nbv && PL > 0) CK(cudaMemcpyAsync(nbv, h->nbv.p, PL * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (flags && PL > 0) CK(cudaMemcpyAsync(flags, h->flags.p, PL * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (bv_off) CK(cudaMemcpyAsync(bv_off, h->bv_off.p, (PL + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (bv_index && T > 0) CK(cudaMemcpyAsync(bv_index, h->pidx.p, T * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (bv1 && T > 0) CK(cudaMemcpyAsync(bv1, h->pb1.p, T * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (bv2 && T > 0) CK(cudaMemcpyAsync(bv2, h->pb2.p, T * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (alpha && T > 0) CK(cudaMemcpyAsync(alpha, h->palpha.p, T * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return GPC_OK;
 }
 
@@ -869,6 +893,7 @@ int gpc_set_params(gpc_handle* h, int64_t P, const int32_t* nbv, const double* b
     h->have_fit = true;
     h->have_binning = false;
     h->n_bv_total = -1;
+    h->params_packed = false;
     return GPC_OK;
 }
 

@@ -19,18 +19,17 @@ __device__ __forceinline__ double geo9() { return (double)1e-9f; }
 // 1.5*2^52 trick, Cody-Waite reduction with two fma, degree-13 Taylor Horner with fma,
 // exponent insertion.  <= 1 ulp from libm.
 __device__ __forceinline__ double gpc_exp(double x) {
-    if (x != x) return x;
-    if (x > 709.0) return __longlong_as_double(0x7ff0000000000000LL);
-    if (x < -745.0) return 0.0;
     const double INV_LN2 = 1.4426950408889634;
     const double MAGIC = 6755399441055744.0;
     const double LN2_HI = 0x1.62e42fefa39efp-1;
     const double LN2_LO = 0x1.abc9e3b39803fp-56;
-    double t = __dmul_rn(x, INV_LN2);
+    // the special cases (NaN, overflow, underflow) are selected at the end: no branches on the hot path
+    const double xc = fmin(fmax(x, -746.0), 710.0);  // NaN -> -746 (fmax/fmin return the number)
+    double t = __dmul_rn(xc, INV_LN2);
     double kd = __dadd_rn(t, MAGIC);
     int n = (int)(unsigned int)(unsigned long long)__double_as_longlong(kd);
     kd = __dadd_rn(kd, -MAGIC);
-    double r = fma(kd, -LN2_HI, x);
+    double r = fma(kd, -LN2_HI, xc);
     r = fma(kd, -LN2_LO, r);
     double p = 1.0 / 6227020800.0;
     p = fma(p, r, 1.0 / 479001600.0);
@@ -46,11 +45,14 @@ __device__ __forceinline__ double gpc_exp(double x) {
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    int adj = 0;
-    if (n < -1020) { adj = 1; n += 1020; }
+    const bool sub = n < -1020;           // subnormal result: scale in two exact steps
+    n += sub ? 1020 : 0;
     long long pb = __double_as_longlong(p) + ((long long)n << 52);
     p = __longlong_as_double(pb);
-    if (adj) p = __dmul_rn(p, 0x1p-1020);
+    p = __dmul_rn(p, sub ? 0x1p-1020 : 1.0);
+    if (x > 709.0) p = __longlong_as_double(0x7ff0000000000000LL);
+    if (x < -745.0) p = 0.0;
+    if (x != x) p = x;
     return p;
 }
 

@@ -138,6 +138,9 @@ struct PredictArgs {
     uint8_t* out32;              // may be nullptr
     double* heights;             // may be nullptr
 };
+void launch_compact_params(const int32_t* nbv, int64_t n_patches, int stride, const double* alpha, const double* b1,
+                           const double* b2, const int32_t* idx, int64_t* widened, int64_t* bv_off, void* scan_tmp,
+                           double* palpha, double* pb1, double* pb2, int32_t* pidx, cudaStream_t s);
 void launch_flag_nonempty(const int32_t* nbv, int64_t n, int64_t* flags, cudaStream_t s);
 void launch_predict_grid(const PredictArgs& a, cudaStream_t s);
 void launch_predict_points(const double* alpha, const double* b1, const double* b2, int N, const double* C,

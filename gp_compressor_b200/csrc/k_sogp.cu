@@ -69,12 +69,44 @@ __device__ __forceinline__ void argmin_combine(double& best, int& bi) {
 }
 
 // =====================================================================================
-// Bucket 0: one warp per patch, LD = 16
+// Bucket 0: one warp per patch.  Rows are contiguous (row r at r * W_LD, W_LD = 18: the
+// two pad columns keep 16-byte alignment and make the 128-bit row loads of a quarter-warp
+// hit distinct banks).  C and Q are bitwise symmetric, so row r == column r.
 // =====================================================================================
-constexpr int W_LD = 16;
+constexpr int W_N = 16;    // N + 1 <= 16
+constexpr int W_LD = 18;
 
-__global__ void __launch_bounds__(32, 20) sogp_fit_warp_kernel(SogpArgs a) {
-    __shared__ double C[W_LD * W_LD], Q[W_LD * W_LD], kv[W_LD], sv[W_LD], ev[W_LD];
+struct WarpSmem {
+    double C[W_N * W_LD], Q[W_N * W_LD];
+    double kv[W_N], sv[W_N], ev[W_N];
+    unsigned long long cnt[NCNT];
+};
+
+// canonical row4 over a contiguous row with 128-bit loads: identical operation order
+__device__ __forceinline__ double row4_contig(const double* row, const double* k, int n) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int j = 0;
+    for (; j + 3 < n; j += 4) {
+        const double2 m01 = *reinterpret_cast<const double2*>(row + j), m23 = *reinterpret_cast<const double2*>(row + j + 2);
+        const double2 k01 = *reinterpret_cast<const double2*>(k + j), k23 = *reinterpret_cast<const double2*>(k + j + 2);
+        a0 = fma(m01.x, k01.x, a0);
+        a1 = fma(m01.y, k01.y, a1);
+        a2 = fma(m23.x, k23.x, a2);
+        a3 = fma(m23.y, k23.y, a3);
+    }
+    if (j < n) {
+        const double2 m01 = *reinterpret_cast<const double2*>(row + j), k01 = *reinterpret_cast<const double2*>(k + j);
+        a0 = fma(m01.x, k01.x, a0);
+        if (j + 1 < n) a1 = fma(m01.y, k01.y, a1);
+        if (j + 2 < n) a2 = fma(row[j + 2], k[j + 2], a2);
+    }
+    return __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
+}
+
+__global__ void __launch_bounds__(32, 28) sogp_fit_warp_kernel(SogpArgs a) {
+    __shared__ __align__(16) WarpSmem sm;
+    double* const C = sm.C;
+    double* const Q = sm.Q;
     const int lane = threadIdx.x;
     const int r = lane & 15, mat = lane >> 4;
     const int64_t patch = a.patch_ids ? (int64_t)a.patch_ids[blockIdx.x] : a.first_patch + blockIdx.x;
@@ -86,16 +118,18 @@ __global__ void __launch_bounds__(32, 20) sogp_fit_warp_kernel(SogpArgs a) {
         return;
     }
 #pragma unroll
-    for (int i = 0; i < W_LD * W_LD / 32; i++) { C[lane + 32 * i] = 0.0; Q[lane + 32 * i] = 0.0; }
+    for (int i = 0; i < W_N * W_LD / 32; i++) { C[lane + 32 * i] = 0.0; Q[lane + 32 * i] = 0.0; }
+    if (lane < NCNT) sm.cnt[lane] = 0;
     __syncwarp();
     const double kstar = a.p0, s20 = a.s20, p0 = a.p0, cl = a.cl, eps_tol = a.eps_tol;
     const int cap = a.capacity, ldmax = a.ld;
     double alpha = 0.0, b1 = 0.0, b2 = 0.0;  // lane l < 16 owns entry l
     int bidx = -1;
     int N = 0;
-    Counters cnt;
-    cnt.init();
-    double* const Mrow = (mat ? Q : C) + r;
+    unsigned int run = 0;  // sparse points at the current N, folded into sm.cnt when N changes
+    double* const Mrow = (mat ? Q : C) + r * W_LD;
+    double* const Crow = C + r * W_LD;
+    double* const Qrow = Q + r * W_LD;
 
     double nx1 = a.fx1[o], nx2 = a.fx2[o], ny = a.fy[o];
     int norig = a.forig[o];
@@ -113,23 +147,26 @@ __global__ void __launch_bounds__(32, 20) sogp_fit_warp_kernel(SogpArgs a) {
                 C[0] = __ddiv_rn(-1.0, d);
                 Q[0] = __ddiv_rn(1.0, kstar);
                 b1 = x1; b2 = x2; bidx = orig;
+                sm.cnt[0]++;
             }
             N = 1;
-            cnt.c[0]++;
             __syncwarp();
             continue;
         }
         // k = K(x, BV) (:119); lanes >= N hold zeros
-        double kl = 0.0;
-        if (lane < N) { kl = rbf(x1, x2, b1, b2, p0, cl); kv[lane] = kl; }
+        const bool act = lane < N;
+        double kl = rbf(x1, x2, b1, b2, p0, cl);
+        kl = act ? kl : 0.0;
+        if (act) sm.kv[lane] = kl;
         __syncwarp();
         // lanes 0-15: (C k)_r ; lanes 16-31: (Q k)_r = e_hat_r   (:122, :140)
         double rv = 0.0;
-        if (r < N) rv = row4(Mrow, W_LD, kv, N);
+        if (r < N) rv = row4_contig(Mrow, sm.kv, N);
         const double el = __shfl_down_sync(0xffffffffu, rv, 16);
         // m = alpha'k, k'Ck, k'e_hat: one product per lane, shared butterfly
-        double pm = 0.0, pc = 0.0, pe = 0.0;
-        if (lane < N) { pm = fma(alpha, kl, 0.0); pc = fma(kl, rv, 0.0); pe = fma(kl, el, 0.0); }
+        double pm = act ? fma(alpha, kl, 0.0) : 0.0;
+        double pc = act ? fma(kl, rv, 0.0) : 0.0;
+        double pe = act ? fma(kl, el, 0.0) : 0.0;
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
             pm = __dadd_rn(pm, shfl_xor_d(pm, off));
@@ -144,54 +181,69 @@ __global__ void __launch_bounds__(32, 20) sogp_fit_warp_kernel(SogpArgs a) {
         if (gamma < tiny12()) gamma = 0.0;
         if (gamma < eps_tol) {
             // sparse update (:155-163)
-            cnt.run++;
+            run++;
             const double eta = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn(gamma, rr)));
-            if (lane < N) {
-                const double sh = __dadd_rn(rv, el);
-                sv[lane] = sh;
+            const double sh = __dadd_rn(rv, el);
+            if (act) {
+                sm.sv[lane] = sh;
                 alpha = __dadd_rn(alpha, __dmul_rn(sh, __dmul_rn(q, eta)));
             }
             __syncwarp();
             const double re = __dmul_rn(rr, eta);
             if (r < N) {
-                const double si = sv[r];
-                for (int j = mat; j < N; j += 2) {
-                    const int idx = j * W_LD + r;
-                    C[idx] = fma(re, __dmul_rn(si, sv[j]), C[idx]);
+                const double si = sm.sv[r];
+                // column pairs (j, j+1): half-warp 0 takes j = 0,4,8,12; half-warp 1 takes j = 2,6,10,14
+                for (int j = 2 * mat; j < N; j += 4) {
+                    double2 c = *reinterpret_cast<double2*>(Crow + j);
+                    const double2 s2v = *reinterpret_cast<const double2*>(sm.sv + j);
+                    c.x = fma(re, __dmul_rn(si, s2v.x), c.x);
+                    if (j + 1 < N) c.y = fma(re, __dmul_rn(si, s2v.y), c.y);
+                    *reinterpret_cast<double2*>(Crow + j) = c;
                 }
             }
             continue;  // Q and N unchanged: neither deletion loop can fire
         }
         // full update (:164-203)
-        cnt.flush(N);
+        if (lane == 0) {
+            const unsigned long long n2 = (unsigned long long)N * N;
+            sm.cnt[1] += run; sm.cnt[5] += (unsigned long long)run * N; sm.cnt[6] += run * n2; sm.cnt[7] += run * n2;
+        }
+        run = 0;
         if (N + 1 > ldmax) {  // does not fit this bucket: hand the state to the next one
             int pos = 0;
             if (lane == 0) pos = atomicAdd(a.queue_count, 1);
             pos = __shfl_sync(0xffffffffu, pos, 0);
-            double* slot = a.handoff_out + (size_t)pos * slot_doubles(W_LD);
+            double* slot = a.handoff_out + (size_t)pos * slot_doubles(W_N);
+            __syncwarp();
             if (lane == 0) {
                 a.queue[pos] = (int32_t)patch;
                 reinterpret_cast<int*>(slot)[0] = N;
                 reinterpret_cast<int*>(slot)[1] = tt;
-                for (int i = 0; i < NCNT; i++) reinterpret_cast<unsigned long long*>(slot + 2)[i] = cnt.c[i];
+                for (int i = 0; i < NCNT; i++) reinterpret_cast<unsigned long long*>(slot + 2)[i] = sm.cnt[i];
             }
             double* v = slot + 2 + NCNT;
-            if (lane < W_LD) {
-                v[lane] = alpha; v[W_LD + lane] = b1; v[2 * W_LD + lane] = b2;
-                reinterpret_cast<int*>(v + 3 * W_LD + 2 * W_LD * W_LD)[lane] = bidx;
+            if (lane < W_N) {
+                v[lane] = alpha; v[W_N + lane] = b1; v[2 * W_N + lane] = b2;
+                reinterpret_cast<int*>(v + 3 * W_N + 2 * W_N * W_N)[lane] = bidx;
             }
-            for (int i = lane; i < W_LD * W_LD; i += 32) { v[3 * W_LD + i] = C[i]; v[3 * W_LD + W_LD * W_LD + i] = Q[i]; }
+            for (int e = lane; e < W_N * W_N; e += 32) {
+                const int j = e / W_N, i = e - j * W_N;
+                v[3 * W_N + e] = C[i * W_LD + j];
+                v[3 * W_N + W_N * W_N + e] = Q[i * W_LD + j];
+            }
             return;
         }
-        cnt.full(N);
-        if (lane < N) {
-            sv[lane] = rv;
-            ev[lane] = el;
+        if (lane == 0) {
+            sm.cnt[2]++; sm.cnt[5] += N; sm.cnt[6] += (unsigned long long)N * N; sm.cnt[8] += (unsigned long long)(N + 1) * (N + 1);
+        }
+        if (act) {
+            sm.sv[lane] = rv;
+            sm.ev[lane] = el;
             alpha = __dadd_rn(alpha, __dmul_rn(q, rv));
         }
         if (lane == N) {
-            sv[N] = 1.0;
-            ev[N] = -1.0;
+            sm.sv[N] = 1.0;
+            sm.ev[N] = -1.0;
             alpha = __dadd_rn(0.0, __dmul_rn(q, 1.0));
             b1 = x1; b2 = x2; bidx = orig;
         }
@@ -200,11 +252,10 @@ __global__ void __launch_bounds__(32, 20) sogp_fit_warp_kernel(SogpArgs a) {
             const double ig = __ddiv_rn(1.0, gamma);
             const int N1 = N + 1;
             if (r < N1) {
-                const double si = sv[r], ei = ev[r];
+                const double si = sm.sv[r], ei = sm.ev[r];
                 for (int j = mat; j < N1; j += 2) {
-                    const int idx = j * W_LD + r;
-                    C[idx] = fma(rr, __dmul_rn(si, sv[j]), C[idx]);
-                    Q[idx] = fma(ig, __dmul_rn(ei, ev[j]), Q[idx]);
+                    Crow[j] = fma(rr, __dmul_rn(si, sm.sv[j]), Crow[j]);
+                    Qrow[j] = fma(ig, __dmul_rn(ei, sm.ev[j]), Qrow[j]);
                 }
             }
             N = N1;
@@ -234,8 +285,7 @@ __global__ void __launch_bounds__(32, 20) sogp_fit_warp_kernel(SogpArgs a) {
                 }
                 // ---- delete_bv(loc), :252-295 ----
                 const int L = N - 1, M = N - 1;
-                cnt.c[9] += (unsigned long long)M * M;
-                cnt.c[phase == 0 ? 3 : 4]++;
+                if (lane == 0) { sm.cnt[9] += (unsigned long long)M * M; sm.cnt[phase == 0 ? 3 : 4]++; }
                 double csi = 0, qsi = 0, repc = 0, repq = 0;
                 const int src = (lane == loc) ? L : lane;
                 if (lane < N) {
@@ -261,8 +311,8 @@ __global__ void __launch_bounds__(32, 20) sogp_fit_warp_kernel(SogpArgs a) {
                         const double qci = __dadd_rn(qsi, csi);
                         const double ai = (lane == loc) ? aL : alpha;
                         alpha = __dadd_rn(ai, -__dmul_rn(coef, qci));
-                        sv[lane] = qsi;   // Qstar
-                        ev[lane] = qci;   // Qstar + Cstar
+                        sm.sv[lane] = qsi;   // Qstar
+                        sm.ev[lane] = qci;   // Qstar + Cstar
                     }
                     C[L * W_LD + lane] = 0.0; C[lane * W_LD + L] = 0.0;
                     Q[L * W_LD + lane] = 0.0; Q[lane * W_LD + L] = 0.0;
@@ -270,14 +320,13 @@ __global__ void __launch_bounds__(32, 20) sogp_fit_warp_kernel(SogpArgs a) {
                 }
                 __syncwarp();
                 if (r < M) {
-                    const double qi = sv[r], ci = ev[r];
+                    const double qi = sm.sv[r], ci = sm.ev[r];
                     for (int j = mat; j < M; j += 2) {
-                        const int idx = j * W_LD + r;
-                        const double u = __dmul_rn(qi, sv[j]);
-                        const double v = __dmul_rn(ci, ev[j]);
+                        const double u = __dmul_rn(qi, sm.sv[j]);
+                        const double v = __dmul_rn(ci, sm.ev[j]);
                         const double w = fma(u, iq, -__dmul_rn(v, iqc));
-                        C[idx] = __dadd_rn(C[idx], w);
-                        Q[idx] = fma(-u, iq, Q[idx]);
+                        Crow[j] = __dadd_rn(Crow[j], w);
+                        Qrow[j] = fma(-u, iq, Qrow[j]);
                     }
                 }
                 N = M;
@@ -285,13 +334,17 @@ __global__ void __launch_bounds__(32, 20) sogp_fit_warp_kernel(SogpArgs a) {
             }
         }
     }
-    cnt.flush(N);
     __syncwarp();
     if (lane == 0) {
+        const unsigned long long n2 = (unsigned long long)N * N;
+        sm.cnt[1] += run; sm.cnt[5] += (unsigned long long)run * N; sm.cnt[6] += run * n2; sm.cnt[7] += run * n2;
         a.nbv[op] = N;
         const double c00 = C[0];
         a.flags[op] = (c00 != c00) ? 1 : 0;
-        publish(a, cnt, n);
+        unsigned long long* st = a.stats;
+        atomicAdd(st + 0, (unsigned long long)n);
+        for (int i = 0; i < NCNT; i++)
+            if (sm.cnt[i]) atomicAdd(st + 1 + i, sm.cnt[i]);
     }
     const int64_t ob = op * cap;
     if (lane < N) {
@@ -304,8 +357,8 @@ __global__ void __launch_bounds__(32, 20) sogp_fit_warp_kernel(SogpArgs a) {
         const int64_t od = op * (int64_t)cap * cap;
         for (int e = lane; e < N * N; e += 32) {
             const int i = e / N, j = e - i * N;
-            a.dumpC[od + e] = C[j * W_LD + i];
-            a.dumpQ[od + e] = Q[j * W_LD + i];
+            a.dumpC[od + e] = C[i * W_LD + j];
+            a.dumpQ[od + e] = Q[i * W_LD + j];
         }
     }
 }
@@ -661,7 +714,7 @@ cudaError_t launch_sogp_fit(int bucket, const SogpArgs& a, cudaStream_t st) {
         case 0:
             sogp_fit_warp_kernel<<<a.n_work, 32, 0, st>>>(a);
             return cudaGetLastError();
-        case 1: return launch_cta_bucket<32, 32, 64, 16>(a, st);
+        case 1: return launch_cta_bucket<32, 32, 64, W_N>(a, st);
         case 2: return launch_cta_bucket<64, 64, 128, 32>(a, st);
         default: return launch_cta_bucket<118, 128, 256, 64>(a, st);
     }

@@ -194,6 +194,44 @@ void launch_flag_nonempty(const int32_t* nbv, int64_t n, int64_t* flags, cudaStr
     g_launches++;
 }
 
+// nbv (int32) -> int64 for the scan
+__global__ void widen_i32_kernel(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+// strided per-patch parameters (stride = capacity) -> packed arrays at bv_off[p]; one warp per patch
+__global__ void __launch_bounds__(256) compact_params_kernel(const int32_t* __restrict__ nbv, const int64_t* __restrict__ bv_off,
+                                                             int64_t n_patches, int stride, const double* __restrict__ alpha,
+                                                             const double* __restrict__ b1, const double* __restrict__ b2,
+                                                             const int32_t* __restrict__ idx, double* __restrict__ palpha,
+                                                             double* __restrict__ pb1, double* __restrict__ pb2,
+                                                             int32_t* __restrict__ pidx) {
+    const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p >= n_patches) return;
+    const int n = nbv[p];
+    const int64_t src = p * stride, dst = bv_off[p];
+    for (int i = lane; i < n; i += 32) {
+        palpha[dst + i] = alpha[src + i];
+        pb1[dst + i] = b1[src + i];
+        pb2[dst + i] = b2[src + i];
+        pidx[dst + i] = idx[src + i];
+    }
+}
+void launch_compact_params(const int32_t* nbv, int64_t n_patches, int stride, const double* alpha, const double* b1,
+                           const double* b2, const int32_t* idx, int64_t* widened, int64_t* bv_off, void* scan_tmp,
+                           double* palpha, double* pb1, double* pb2, int32_t* pidx, cudaStream_t s) {
+    if (n_patches <= 0) {
+        cudaMemsetAsync(bv_off, 0, sizeof(int64_t), s);
+        return;
+    }
+    widen_i32_kernel<<<(unsigned)((n_patches + 255) / 256), 256, 0, s>>>(nbv, n_patches, widened);
+    launch_exclusive_scan_i64(widened, bv_off, n_patches, scan_tmp, s);
+    compact_params_kernel<<<(unsigned)((n_patches * 32 + 255) / 256), 256, 0, s>>>(nbv, bv_off, n_patches, stride, alpha, b1, b2, idx,
+                                                                                 palpha, pb1, pb2, pidx);
+    g_launches += 2;
+}
+
 __global__ void debug_exp_kernel(const double* __restrict__ x, double* __restrict__ out, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = gpc_exp(x[i]);
