@@ -56,11 +56,47 @@ __device__ __forceinline__ double gpc_exp(double x) {
     return p;
 }
 
+// gpc_exp for arguments that are <= 0 or NaN (the RBF exponent): same arithmetic, fewer selects
+__device__ __forceinline__ double gpc_exp_nonpos(double x) {
+    const double INV_LN2 = 1.4426950408889634;
+    const double MAGIC = 6755399441055744.0;
+    const double LN2_HI = 0x1.62e42fefa39efp-1;
+    const double LN2_LO = 0x1.abc9e3b39803fp-56;
+    const bool special = !(x >= -745.0);          // underflow to 0, or NaN
+    const double xc = special ? -745.0 : x;
+    double t = __dmul_rn(xc, INV_LN2);
+    double kd = __dadd_rn(t, MAGIC);
+    int n = (int)(unsigned int)(unsigned long long)__double_as_longlong(kd);
+    kd = __dadd_rn(kd, -MAGIC);
+    double r = fma(kd, -LN2_HI, xc);
+    r = fma(kd, -LN2_LO, r);
+    double p = 1.0 / 6227020800.0;
+    p = fma(p, r, 1.0 / 479001600.0);
+    p = fma(p, r, 1.0 / 39916800.0);
+    p = fma(p, r, 1.0 / 3628800.0);
+    p = fma(p, r, 1.0 / 362880.0);
+    p = fma(p, r, 1.0 / 40320.0);
+    p = fma(p, r, 1.0 / 5040.0);
+    p = fma(p, r, 1.0 / 720.0);
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const bool sub = n < -1020;
+    n += sub ? 1020 : 0;
+    p = __longlong_as_double(__double_as_longlong(p) + ((long long)n << 52));
+    p = __dmul_rn(p, sub ? 0x1p-1020 : 1.0);
+    if (special) p = (x != x) ? x : 0.0;
+    return p;
+}
+
 // rbf_kernel::kernel_function, rbf_kernel.cpp:15-18 : p0 * exp((-0.5f/p1) * ||xi-xj||^2)
 __device__ __forceinline__ double rbf(double x1, double x2, double b1, double b2, double p0, double cl) {
     double d1 = __dadd_rn(x1, -b1), d2 = __dadd_rn(x2, -b2);
     double sq = __dadd_rn(__dmul_rn(d1, d1), __dmul_rn(d2, d2));
-    return __dmul_rn(p0, gpc_exp(__dmul_rn(cl, sq)));
+    return __dmul_rn(p0, gpc_exp_nonpos(__dmul_rn(cl, sq)));  // cl < 0 (l_sq > 0 is checked at gpc_create), sq >= 0
 }
 
 __device__ __forceinline__ double shfl_xor_d(double v, int off) {

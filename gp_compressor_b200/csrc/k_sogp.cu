@@ -76,11 +76,32 @@ __device__ __forceinline__ void argmin_combine(double& best, int& bi) {
 constexpr int W_N = 16;    // N + 1 <= 16
 constexpr int W_LD = 18;
 
+struct __align__(16) StagedPoint { double x1, x2, y; int orig, pad; };
 struct WarpSmem {
     double C[W_N * W_LD], Q[W_N * W_LD];
     double kv[W_N], sv[W_N], ev[W_N];
+    StagedPoint pts[32];          // the next 32 points of the patch's stream, loaded coalesced
     unsigned long long cnt[NCNT];
 };
+
+// (M k)_r for a contiguous, zero-padded row: groups of 4 columns up to ceil(n/4)*4.  Pad columns hold
+// exact zeros and k is finite, so the extra terms leave the accumulators (never -0) bit-unchanged:
+// the result equals the canonical row4 over n columns.
+__device__ __forceinline__ double row4_padded16(const double* row, const double* k, int n) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        if (4 * g < n) {
+            const double2 m01 = *reinterpret_cast<const double2*>(row + 4 * g), m23 = *reinterpret_cast<const double2*>(row + 4 * g + 2);
+            const double2 k01 = *reinterpret_cast<const double2*>(k + 4 * g), k23 = *reinterpret_cast<const double2*>(k + 4 * g + 2);
+            a0 = fma(m01.x, k01.x, a0);
+            a1 = fma(m01.y, k01.y, a1);
+            a2 = fma(m23.x, k23.x, a2);
+            a3 = fma(m23.y, k23.y, a3);
+        }
+    }
+    return __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
+}
 
 // canonical row4 over a contiguous row with 128-bit loads: identical operation order
 __device__ __forceinline__ double row4_contig(const double* row, const double* k, int n) {
@@ -120,6 +141,7 @@ __global__ void __launch_bounds__(32, 28) sogp_fit_warp_kernel(SogpArgs a) {
 #pragma unroll
     for (int i = 0; i < W_N * W_LD / 32; i++) { C[lane + 32 * i] = 0.0; Q[lane + 32 * i] = 0.0; }
     if (lane < NCNT) sm.cnt[lane] = 0;
+    if (lane < W_N) { sm.kv[lane] = 0.0; sm.sv[lane] = 0.0; sm.ev[lane] = 0.0; }  // pad terms must be finite
     __syncwarp();
     const double kstar = a.p0, s20 = a.s20, p0 = a.p0, cl = a.cl, eps_tol = a.eps_tol;
     const int cap = a.capacity, ldmax = a.ld;
@@ -131,15 +153,24 @@ __global__ void __launch_bounds__(32, 28) sogp_fit_warp_kernel(SogpArgs a) {
     double* const Crow = C + r * W_LD;
     double* const Qrow = Q + r * W_LD;
 
-    double nx1 = a.fx1[o], nx2 = a.fx2[o], ny = a.fy[o];
-    int norig = a.forig[o];
+    const double* const gx1 = a.fx1 + o;
+    const double* const gx2 = a.fx2 + o;
+    const double* const gy = a.fy + o;
+    const int32_t* const go = a.forig + o;
     for (int tt = 0; tt < n; ++tt) {
-        const double x1 = nx1, x2 = nx2, y = ny;
-        const int orig = norig;
-        if (tt + 1 < n) {
-            nx1 = a.fx1[o + tt + 1]; nx2 = a.fx2[o + tt + 1]; ny = a.fy[o + tt + 1];
-            norig = a.forig[o + tt + 1];
+        if ((tt & 31) == 0) {  // stage the next 32 points: one coalesced load per lane
+            __syncwarp();
+            const int i = tt + lane;
+            if (i < n) {
+                StagedPoint sp;
+                sp.x1 = gx1[i]; sp.x2 = gx2[i]; sp.y = gy[i]; sp.orig = go[i]; sp.pad = 0;
+                sm.pts[lane] = sp;
+            }
+            __syncwarp();
         }
+        const StagedPoint pt = sm.pts[tt & 31];
+        const double x1 = pt.x1, x2 = pt.x2, y = pt.y;
+        const int orig = pt.orig;
         if (N == 0) {  // sparse_gp.hpp:100-110
             if (lane == 0) {
                 const double d = __dadd_rn(kstar, s20);
@@ -161,7 +192,7 @@ __global__ void __launch_bounds__(32, 28) sogp_fit_warp_kernel(SogpArgs a) {
         __syncwarp();
         // lanes 0-15: (C k)_r ; lanes 16-31: (Q k)_r = e_hat_r   (:122, :140)
         double rv = 0.0;
-        if (r < N) rv = row4_contig(Mrow, sm.kv, N);
+        if (r < N) rv = row4_padded16(Mrow, sm.kv, N);
         const double el = __shfl_down_sync(0xffffffffu, rv, 16);
         // m = alpha'k, k'Ck, k'e_hat: one product per lane, shared butterfly
         double pm = act ? fma(alpha, kl, 0.0) : 0.0;
@@ -183,22 +214,24 @@ __global__ void __launch_bounds__(32, 28) sogp_fit_warp_kernel(SogpArgs a) {
             // sparse update (:155-163)
             run++;
             const double eta = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn(gamma, rr)));
-            const double sh = __dadd_rn(rv, el);
-            if (act) {
-                sm.sv[lane] = sh;
-                alpha = __dadd_rn(alpha, __dmul_rn(sh, __dmul_rn(q, eta)));
-            }
+            const double sh = act ? __dadd_rn(rv, el) : 0.0;
+            if (lane < W_N) sm.sv[lane] = sh;  // zero beyond N: pad columns stay exact zeros below
+            if (act) alpha = __dadd_rn(alpha, __dmul_rn(sh, __dmul_rn(q, eta)));
             __syncwarp();
             const double re = __dmul_rn(rr, eta);
             if (r < N) {
                 const double si = sm.sv[r];
                 // column pairs (j, j+1): half-warp 0 takes j = 0,4,8,12; half-warp 1 takes j = 2,6,10,14
-                for (int j = 2 * mat; j < N; j += 4) {
-                    double2 c = *reinterpret_cast<double2*>(Crow + j);
-                    const double2 s2v = *reinterpret_cast<const double2*>(sm.sv + j);
-                    c.x = fma(re, __dmul_rn(si, s2v.x), c.x);
-                    if (j + 1 < N) c.y = fma(re, __dmul_rn(si, s2v.y), c.y);
-                    *reinterpret_cast<double2*>(Crow + j) = c;
+#pragma unroll
+                for (int p4 = 0; p4 < 4; p4++) {
+                    const int j = 2 * mat + 4 * p4;
+                    if (j < N) {
+                        double2 c = *reinterpret_cast<double2*>(Crow + j);
+                        const double2 s2v = *reinterpret_cast<const double2*>(sm.sv + j);
+                        c.x = fma(re, __dmul_rn(si, s2v.x), c.x);
+                        if (j + 1 < N) c.y = fma(re, __dmul_rn(si, s2v.y), c.y);
+                        *reinterpret_cast<double2*>(Crow + j) = c;
+                    }
                 }
             }
             continue;  // Q and N unchanged: neither deletion loop can fire
