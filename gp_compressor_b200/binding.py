@@ -20,7 +20,7 @@ SYMBOLS = [
     "gpc_config_default", "gpc_create", "gpc_destroy", "gpc_last_error", "gpc_version", "gpc_compress",
     "gpc_upload_cloud", "gpc_compress_resident", "gpc_fit_patches", "gpc_decompress", "gpc_decompress_resident",
     "gpc_get_heights", "gpc_predict", "gpc_get_sizes", "gpc_get_stats", "gpc_get_patches", "gpc_get_assignment",
-    "gpc_get_params", "gpc_get_state", "gpc_set_params", "gpc_set_rand_offset", "gpc_get_stream", "gpc_debug_exp", "gpc_debug_rand",
+    "gpc_get_params", "gpc_get_state", "gpc_set_params", "gpc_set_rand_offset", "gpc_get_stream", "gpc_debug_exp", "gpc_debug_rand", "gpc_debug_peak", "gpc_shard_range",
 ]
 
 
@@ -84,6 +84,8 @@ def load():
     L.gpc_get_stream.argtypes = [vp, C.POINTER(vp)]
     L.gpc_debug_exp.argtypes = [vp, vp, vp, i64]
     L.gpc_debug_rand.argtypes = [vp, u64, i64, vp]
+    L.gpc_debug_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    L.gpc_shard_range.argtypes = [vp, i64, C.c_int32, C.c_int32, C.POINTER(i64), C.POINTER(i64)]
     _LIB = L
     return L
 
@@ -96,6 +98,16 @@ def default_config():
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def shard_range(off, rank, count):
+    """Patches [lo, hi) owned by shard `rank` of `count` (host arithmetic only, no GPU needed)."""
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    lo, hi = C.c_int64(0), C.c_int64(0)
+    rc = load().gpc_shard_range(_p(off), off.size - 1, rank, count, C.byref(lo), C.byref(hi))
+    if rc != GPC_OK:
+        raise GpcError(f"gpc_shard_range failed with code {rc}")
+    return lo.value, hi.value
 
 
 class GpcError(RuntimeError):
@@ -266,6 +278,11 @@ class Handle:
         out = np.zeros_like(x)
         self._ck(load().gpc_debug_exp(self.h, _p(x), _p(out), x.size))
         return out
+
+    def debug_peak(self, kind):
+        v = C.c_double(0)
+        self._ck(load().gpc_debug_peak(self.h, kind, C.byref(v)))
+        return v.value
 
     def debug_rand(self, offset, n):
         out = np.zeros(n, dtype=np.uint32)

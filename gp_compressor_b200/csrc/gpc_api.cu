@@ -957,6 +957,22 @@ int gpc_debug_exp(gpc_handle* h, const double* x, double* out, int64_t n) {
     return GPC_OK;
 }
 
+int gpc_debug_peak(gpc_handle* h, int kind, double* value) {
+    if (!h || !value || kind < 0 || kind > 1) return GPC_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+    CK(measure_peak(kind, sms, h->stream, value));
+    return GPC_OK;
+}
+
+int gpc_shard_range(const int64_t* off, int64_t n_patches, int32_t shard_rank, int32_t shard_count, int64_t* lo, int64_t* hi) {
+    if (!off || n_patches < 0 || shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count || !lo || !hi) return GPC_ERR_INVALID;
+    std::vector<int64_t> o(off, off + n_patches + 1);
+    shard_range(o, shard_rank, shard_count, lo, hi);
+    return GPC_OK;
+}
+
 int gpc_debug_rand(gpc_handle* h, uint64_t offset, int64_t n, uint32_t* out) {
     if (!h || n < 0 || (n > 0 && !out)) return GPC_ERR_INVALID;
     CK(cudaSetDevice(h->cfg.device));

@@ -146,6 +146,7 @@ void launch_predict_grid(const PredictArgs& a, cudaStream_t s);
 void launch_predict_points(const double* alpha, const double* b1, const double* b2, int N, const double* C,
                            double p0, double cl, double s20, const double* X, int64_t m, double* f,
                            double* sigma, cudaStream_t s);
+cudaError_t measure_peak(int kind, int sm_count, cudaStream_t s, double* value);
 void launch_debug_exp(const double* x, double* out, int64_t n, cudaStream_t s);
 
 }  // namespace gpc

@@ -141,6 +141,14 @@ int gpc_get_stream(gpc_handle* h, void** stream);
 /* ---- test hooks: the device versions of the canonical primitives ----------------------- */
 int gpc_debug_exp(gpc_handle* h, const double* x, double* out, int64_t n);
 int gpc_debug_rand(gpc_handle* h, uint64_t offset, int64_t n, uint32_t* out);
+/* roofline denominators measured on the device: kind 0 = FP64 FLOP/s (DFMA), kind 1 = shared-memory bytes/s */
+int gpc_debug_peak(gpc_handle* h, int kind, double* value);
+
+/* ---- sharding rule (pure host arithmetic, no device needed) -------------------------------
+ * Patches [lo, hi) that shard_rank of shard_count owns, given the patch offsets off[0..n_patches]:
+ * contiguous ranges of the visiting order holding about equal numbers of claimed points.  This
+ * is the rule gpc_compress / gpc_fit_patches / gpc_set_params apply internally. */
+int gpc_shard_range(const int64_t* off, int64_t n_patches, int32_t shard_rank, int32_t shard_count, int64_t* lo, int64_t* hi);
 
 #ifdef __cplusplus
 }
