@@ -1,0 +1,80 @@
+// oracle/ref_sogp.cpp — TEST INFRASTRUCTURE.  Harness around THE REFERENCE'S OWN sparse_gp.hpp,
+// rbf_kernel.cpp and gaussian_noise.cpp, compiled from where they lie under /root/reference/src (never
+// copied) against oracle/eigen_shim.  It exposes the reference's SOGP (add_measurements incl. its rand()
+// shuffle, predict_measurements) and the private state (alpha, BV, C, Q) to the tests and to
+// tests/golden/make_golden.py.  Private members are reached with the usual test-harness trick.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <iostream>
+#include <sstream>
+#include <vector>
+
+#include <Eigen/Dense>
+
+#include "octave_convenience.h"  // std headers first: the access trick below must not reach them
+#define private public
+#define protected public
+#include "sparse_gp.h"
+#undef private
+#undef protected
+#include "gaussian_noise.h"
+#include "rbf_kernel.h"
+
+typedef sparse_gp<rbf_kernel, gaussian_noise> ref_gp;
+
+extern "C" {
+
+// Fits one process.  rand_offset: number of rand() draws consumed before this call (srand(1) = the unseeded
+// stream).  Returns current_size; fills alpha/bv (2 x N, column j = BV j)/C/Q (N x N row-major) up to max_n.
+int ref_sogp_fit(int n, const double* x1, const double* x2, const double* y, int capacity, double s0, double sigmaf_sq,
+                 double l_sq, double eps_tol, unsigned long long rand_offset, int max_n, double* alpha, double* bv1, double* bv2,
+                 double* C, double* Q, int n_pred, const double* px1, const double* px2, double* f_star, double* sigma) {
+    srand(1);
+    for (unsigned long long i = 0; i < rand_offset; i++) rand();
+    ref_gp gp(capacity, s0);
+    gp.kernel.param()(0) = sigmaf_sq;
+    gp.kernel.param()(1) = l_sq;
+    gp.eps_tol = eps_tol;
+    Eigen::MatrixXd X(n, 2);
+    Eigen::VectorXd Y(n);
+    for (int i = 0; i < n; i++) { X(i, 0) = x1[i]; X(i, 1) = x2[i]; Y(i) = y[i]; }
+    gp.add_measurements(X, Y);
+    const int N = gp.size();
+    if (N > max_n) return -N;
+    for (int i = 0; i < N; i++) {
+        alpha[i] = gp.alpha(i);
+        bv1[i] = gp.BV(0, i);
+        bv2[i] = gp.BV(1, i);
+        for (int j = 0; j < N; j++) { C[i * N + j] = gp.C(i, j); Q[i * N + j] = gp.Q(i, j); }
+    }
+    if (n_pred > 0) {
+        Eigen::MatrixXd Xs(n_pred, 2);
+        for (int i = 0; i < n_pred; i++) { Xs(i, 0) = px1[i]; Xs(i, 1) = px2[i]; }
+        Eigen::VectorXd f, sg;
+        gp.predict_measurements(f, Xs, sg);
+        for (int i = 0; i < n_pred; i++) { f_star[i] = f(i); sigma[i] = sg(i); }
+    }
+    return N;
+}
+
+// sparse_gp::shuffle alone (sparse_gp.hpp:42-56) over the real rand()
+void ref_shuffle(int n, unsigned long long rand_offset, int* out) {
+    srand(1);
+    for (unsigned long long i = 0; i < rand_offset; i++) rand();
+    ref_gp gp(10, 0.1);
+    std::vector<int> ind;
+    gp.shuffle(ind, n);
+    for (int i = 0; i < n; i++) out[i] = ind[i];
+}
+
+double ref_kernel(double sigmaf_sq, double l_sq, double a1, double a2, double b1, double b2) {
+    rbf_kernel k(sigmaf_sq, l_sq);
+    Eigen::Vector2d a, b;
+    a(0) = a1; a(1) = a2; b(0) = b1; b(1) = b2;
+    return k.kernel_function(a, b);
+}
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+"""ctypes wrapper of oracle/_ref/libref_sogp.so (the reference's own sparse_gp.hpp / rbf_kernel.cpp /
+gaussian_noise.cpp compiled over oracle/eigen_shim).  Test infrastructure."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(_HERE, "_ref", "libref_sogp.so")
+_LIB = None
+
+
+def available():
+    if os.path.isdir("/root/reference/src"):
+        from . import ref_build
+        ref_build.build()
+    return os.path.exists(SO)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(SO)
+        L.ref_sogp_fit.restype = C.c_int
+        L.ref_sogp_fit.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                   C.c_ulonglong, C.c_int] + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 4
+        L.ref_shuffle.argtypes = [C.c_int, C.c_ulonglong, C.c_void_p]
+        L.ref_kernel.restype = C.c_double
+        L.ref_kernel.argtypes = [C.c_double] * 6
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def fit(x1, x2, y, capacity=100, s0=float(np.float32(1e-1)), sigmaf_sq=100.0, l_sq=1.0, eps_tol=float(np.float32(1e-6)),
+        rand_offset=0, pred=None):
+    """sparse_gp<rbf_kernel, gaussian_noise>(capacity, s0).add_measurements(X, y) of the reference itself."""
+    x1, x2, y = (np.ascontiguousarray(a, dtype=np.float64) for a in (x1, x2, y))
+    n = x1.size
+    mx = (capacity if capacity > 0 else n) + 2
+    alpha, b1, b2 = np.zeros(mx), np.zeros(mx), np.zeros(mx)
+    Cm, Qm = np.zeros(mx * mx), np.zeros(mx * mx)
+    if pred is None:
+        pred = np.zeros((0, 2))
+    pred = np.ascontiguousarray(pred, dtype=np.float64).reshape(-1, 2)
+    p1, p2 = np.ascontiguousarray(pred[:, 0]), np.ascontiguousarray(pred[:, 1])
+    f, sg = np.zeros(pred.shape[0]), np.zeros(pred.shape[0])
+    N = lib().ref_sogp_fit(n, _p(x1), _p(x2), _p(y), capacity, s0, sigmaf_sq, l_sq, eps_tol, rand_offset, mx, _p(alpha), _p(b1), _p(b2),
+                           _p(Cm), _p(Qm), pred.shape[0], _p(p1), _p(p2), _p(f), _p(sg))
+    assert N >= 0
+    return dict(N=N, alpha=alpha[:N].copy(), bv1=b1[:N].copy(), bv2=b2[:N].copy(), C=Cm[:N * N].reshape(N, N).copy(),
+                Q=Qm[:N * N].reshape(N, N).copy(), f=f, sigma=sg)
+
+
+def shuffle(n, rand_offset=0):
+    out = np.zeros(n, dtype=np.int32)
+    lib().ref_shuffle(n, rand_offset, _p(out))
+    return out
+
+
+def kernel(sigmaf_sq, l_sq, a, b):
+    return lib().ref_kernel(sigmaf_sq, l_sq, a[0], a[1], b[0], b[1])

@@ -1,0 +1,43 @@
+"""Generates tests/golden/ref_sogp.npz from THE REFERENCE'S OWN SOURCE (oracle/_ref, see oracle/ref_build.py):
+inputs and outputs of sparse_gp<rbf_kernel,gaussian_noise>::add_measurements / predict_measurements for a
+few seeded patches.  Run in the container that has /root/reference:  python tests/golden/make_golden.py"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_source as R  # noqa: E402
+
+CASES = [  # name, n, capacity, hyper-parameters
+    ("ref_defaults_cap100", 300, 100, dict(sigmaf_sq=100.0, l_sq=1.0, s0=float(np.float32(1e-1)))),
+    ("ref_defaults_cap30", 500, 30, dict(sigmaf_sq=100.0, l_sq=1.0, s0=float(np.float32(1e-1)))),
+    ("bind_cap12", 400, 12, dict(sigmaf_sq=1.0, l_sq=(0.1 / 12) ** 2, s0=1e-4)),
+    ("bind_cap30", 600, 30, dict(sigmaf_sq=1.0, l_sq=(0.1 / 12) ** 2, s0=1e-4)),
+    ("bind_cap60", 900, 60, dict(sigmaf_sq=1.0, l_sq=(0.1 / 12) ** 2, s0=1e-4)),
+    ("tiny_n3", 3, 100, dict(sigmaf_sq=1.0, l_sq=(0.1 / 12) ** 2, s0=1e-4)),
+]
+
+
+def main():
+    assert R.available(), "needs /root/reference (or a prebuilt oracle/_ref)"
+    out = {}
+    for k, (name, n, cap, hyp) in enumerate(CASES):
+        rng = np.random.default_rng(100 + k)
+        x1 = rng.uniform(-0.05, 0.05, n)
+        x2 = rng.uniform(-0.05, 0.05, n)
+        y = 0.02 * np.sin(40 * x1) * np.cos(30 * x2) + 0.5 * x1 + rng.normal(0, 0.003, n)
+        pred = rng.uniform(-0.05, 0.05, (25, 2))
+        r = R.fit(x1, x2, y, capacity=cap, rand_offset=7 * k, pred=pred, **hyp)
+        for key, v in dict(x1=x1, x2=x2, y=y, pred=pred, alpha=r["alpha"], bv1=r["bv1"], bv2=r["bv2"], C=r["C"], Q=r["Q"], f=r["f"],
+                           sigma=r["sigma"], meta=np.array([n, cap, 7 * k, r["N"]], dtype=np.int64),
+                           hyper=np.array([hyp["sigmaf_sq"], hyp["l_sq"], hyp["s0"]])).items():
+            out[f"{name}/{key}"] = v
+    out["shuffle_n57_off3"] = R.shuffle(57, 3)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_sogp.npz"), **out)
+    print("wrote", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()
