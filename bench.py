@@ -61,7 +61,7 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -166,7 +166,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
@@ -208,12 +208,11 @@ def main():
     evs, stage_acc = [], {}
     n_dec = 0
     launches = 0
-    sampler = None
+    sampler = ClockSampler(local) if rank == 0 else None   # runs over warm-up, the timed loops and the e2e loops
     e_all0 = torch.cuda.Event(enable_timing=True)
     for it in range(args.warmup + args.steps):
         if it == args.warmup:
             barrier()
-            sampler = ClockSampler(local) if rank == 0 else None
             e_all0.record(ext)
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e2 = torch.cuda.Event(enable_timing=True)
         e0.record(ext)
@@ -232,7 +231,6 @@ def main():
             stage_acc["ms_predict"] = stage_acc.get("ms_predict", 0.0) + st_d["ms_predict"]
     e_all1 = torch.cuda.Event(enable_timing=True); e_all1.record(ext)
     barrier()
-    clocks = sampler.stop() if sampler else None
     total_ms = e_all0.elapsed_time(e_all1)
     comp_ms = [a.elapsed_time(b) for a, b, _ in evs]
     dec_ms = [b.elapsed_time(c) for _, b, c in evs]
@@ -267,6 +265,9 @@ def main():
             e2e_c.append(t1 - t0); e2e_d.append(t2 - t1)
             d2h = sum(v.nbytes for v in prm.values() if hasattr(v, "nbytes")) + nd * 32
     barrier()
+    clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + device-resident timed loop + end-to-end loop (nvidia-smi -lms 20)"
     te = torch.tensor([float(np.sum(e2e_c)), float(np.sum(e2e_d))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -293,18 +294,19 @@ def main():
         fl = sogp_flops(fit_stats)
         sm = sogp_smem_bytes(fit_stats)
         sec = stage_ms[dom] * 1e-3
-        # FP64 / shared-memory peaks: theoretical B200 figures until the micro-benchmarks of profiles/ replace them
-        fp64_peak, smem_peak = 37.2e12, 37.2e12
+        # FP64 / shared-memory peaks measured on this device by the library's micro-benchmarks (csrc/k_peaks.cu)
+        fp64_peak, smem_peak = h.debug_peak(0), h.debug_peak(1)
         f1, f2 = fl / sec / fp64_peak, sm / sec / smem_peak
         roof = {"kernel": "sogp_fit_kernel (K7)", "bound": "smem" if f2 >= f1 else "fp64", "achieved": (sm if f2 >= f1 else fl) / sec / 1e9,
                 "peak": (smem_peak if f2 >= f1 else fp64_peak) / 1e9, "unit": "GB/s" if f2 >= f1 else "GFLOP/s", "frac": max(f1, f2),
-                "traffic": None, "peak_source": "theoretical 148 SM x 128 B/clk (64 DFMA/clk) x 1.965 GHz", "stage_ms": stage_ms[dom],
+                "traffic": None, "peak_source": "measured here: independent DFMA chains %.1f TFLOP/s, conflict-free LDS.128 %.1f TB/s (gpc_debug_peak)" % (fp64_peak / 1e12, smem_peak / 1e12), "stage_ms": stage_ms[dom],
                 "fp64_frac": f1, "smem_frac": f2, "mean_n": fit_stats["sum_n"] / max(1, fit_stats["n_add"] - fit_stats["n_first"])}
     elif dom == "ms_predict":
         fl = n_dec * (37.0 * (sizes.n_bv_total / max(1, n_dec / (cfg["sz"] ** 2))) + 18)
         sec = stage_ms[dom] * 1e-3
-        roof = {"kernel": "predict_grid_kernel (K8)", "bound": "fp64", "achieved": fl / sec / 1e9, "peak": 37200.0, "unit": "GFLOP/s",
-                "frac": fl / sec / 37.2e12, "traffic": None, "peak_source": "theoretical", "stage_ms": stage_ms[dom]}
+        fp64_peak = h.debug_peak(0)
+        roof = {"kernel": "predict_grid_kernel (K8)", "bound": "fp64", "achieved": fl / sec / 1e9, "peak": fp64_peak / 1e9, "unit": "GFLOP/s",
+                "frac": fl / sec / fp64_peak, "traffic": None, "peak_source": "measured here (gpc_debug_peak)", "stage_ms": stage_ms[dom]}
     else:
         roof = {"kernel": dom, "bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None}
 

@@ -958,7 +958,7 @@ int gpc_debug_exp(gpc_handle* h, const double* x, double* out, int64_t n) {
 }
 
 int gpc_debug_peak(gpc_handle* h, int kind, double* value) {
-    if (!h || !value || kind < 0 || kind > 1) return GPC_ERR_INVALID;
+    if (!h || !value || kind < 0 || kind > 2) return GPC_ERR_INVALID;
     CK(cudaSetDevice(h->cfg.device));
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));

@@ -141,7 +141,7 @@ int gpc_get_stream(gpc_handle* h, void** stream);
 /* ---- test hooks: the device versions of the canonical primitives ----------------------- */
 int gpc_debug_exp(gpc_handle* h, const double* x, double* out, int64_t n);
 int gpc_debug_rand(gpc_handle* h, uint64_t offset, int64_t n, uint32_t* out);
-/* roofline denominators measured on the device: kind 0 = FP64 FLOP/s (DFMA), kind 1 = shared-memory bytes/s */
+/* roofline denominators measured on the device: kind 0 = FP64 FLOP/s (DFMA), kind 1 = shared-memory bytes/s with 128-bit loads, kind 2 = with 64-bit loads */
 int gpc_debug_peak(gpc_handle* h, int kind, double* value);
 
 /* ---- sharding rule (pure host arithmetic, no device needed) -------------------------------
