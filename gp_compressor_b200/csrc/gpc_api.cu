@@ -39,7 +39,7 @@ struct gpc_handle {
     DevBuf tmpA, tmpB, tmpC;
     // binning scratch
     DevBuf keys, keys2, vals, vals2, ovals, ovals2, sort_tmp, flags64, ex, leaf_of, leaf_start, leaf_code_a, spt, nbr, nnbr,
-        center_a, Rm_a, ncand_a, pt0, pt1, pt2, hbuf, rgb;
+        center_a, Rm_a, ncand_a, pt0, pt1, pt2, hbuf, rgb, leaf_sums;
     std::vector<cudaEvent_t> ev;
 };
 
@@ -442,12 +442,13 @@ int run_binning(gpc_handle* h, StageTimer& tm) {
     CK(h->center_a.reserve(P * 3 * sizeof(float)));
     CK(h->Rm_a.reserve(P * 9 * sizeof(double)));
     CK(h->ncand_a.reserve(P * sizeof(int32_t)));
+    CK(h->leaf_sums.reserve(P * 10 * sizeof(double)));
     const double radius = (double)(std::sqrt(3.0f) / 2.0f) * c.res;  // gp_compressor.cpp:194
     const double r2 = radius * radius;
     const double half = c.res / 2.0f;                                // gp_compressor.cpp:85
     launch_leaf_neighbours(h->leaf_code_a.as<uint64_t>(), P, lat, h->nbr.as<int32_t>(), h->nnbr.as<int32_t>(), h->center_a.as<float>(), st);
     launch_leaf_rotation(h->spt.p, h->leaf_start.as<int64_t>(), h->nbr.as<int32_t>(), h->nnbr.as<int32_t>(), h->center_a.as<float>(), P,
-                         r2, h->Rm_a.as<double>(), h->ncand_a.as<int32_t>(), st);
+                         r2, h->leaf_sums.as<double>(), h->Rm_a.as<double>(), h->ncand_a.as<int32_t>(), st);
     size_t t5 = tm.mark();
     tm.span(&h->stats.ms_rotation, t4, t5);
     // ---- claim ----
@@ -577,7 +578,7 @@ void gpc_destroy(gpc_handle* h) {
                       &h->heights, &h->quat, &h->mean, &h->rgbmean, &h->Rm, &h->center, &h->code, &h->ncand, &h->owner,
                       &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
                       &h->ovals2, &h->sort_tmp, &h->flags64, &h->ex, &h->leaf_of, &h->leaf_start, &h->leaf_code_a, &h->spt,
-                      &h->nbr, &h->nnbr, &h->center_a, &h->Rm_a, &h->ncand_a, &h->pt0, &h->pt1, &h->pt2, &h->hbuf, &h->rgb};
+                      &h->nbr, &h->nnbr, &h->center_a, &h->Rm_a, &h->ncand_a, &h->pt0, &h->pt1, &h->pt2, &h->hbuf, &h->rgb, &h->leaf_sums};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     cudaStreamDestroy(h->stream);

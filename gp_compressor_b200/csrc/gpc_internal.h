@@ -56,7 +56,7 @@ void launch_fill_leaves(const uint64_t* keys, const uint32_t* vals, const int64_
 void launch_leaf_neighbours(const uint64_t* leaf_code, int64_t P, const LatticeDev& lat, int32_t* nbr, int32_t* nnbr,
                             float* center, cudaStream_t s);
 void launch_leaf_rotation(const void* spt, const int64_t* leaf_start, const int32_t* nbr, const int32_t* nnbr,
-                          const float* center, int64_t P, double r2, double* Rm, int32_t* ncand, cudaStream_t s);
+                          const float* center, int64_t P, double r2, double* sums, double* Rm, int32_t* ncand, cudaStream_t s);
 void launch_claim(const void* spt, const int32_t* leaf_of, const int32_t* nbr, const int32_t* nnbr, const float* center,
                   const double* Rm, const int32_t* ncand, int64_t n_valid, int64_t P, double r2, double half, int leaf_order,
                   uint64_t* okey, uint32_t* oval, double* pt0, double* pt1, double* pt2, cudaStream_t s);

@@ -317,11 +317,12 @@ __device__ void rot_to_quat(const double* R, double* q) {
 #undef MR
 }
 
-// ---- K4: rotation per leaf, one warp per leaf ------------------------------------------------
-__global__ void __launch_bounds__(128) leaf_rotation_kernel(const float4* __restrict__ spt, const int64_t* __restrict__ leaf_start,
-                                                            const int32_t* __restrict__ nbr, const int32_t* __restrict__ nnbr,
-                                                            const float* __restrict__ center, int64_t P, double r2,
-                                                            double* __restrict__ Rm, int32_t* __restrict__ ncand) {
+// ---- K4: rotation per leaf.  (a) one warp per leaf: canonical sums over the candidate points;
+// (b) one thread per leaf: 4x4 factorisation and frame (the serial part runs once, not 32 times) ----------
+__global__ void __launch_bounds__(256) leaf_sums_kernel(const float4* __restrict__ spt, const int64_t* __restrict__ leaf_start,
+                                                        const int32_t* __restrict__ nbr, const int32_t* __restrict__ nnbr,
+                                                        const float* __restrict__ center, int64_t P, double r2,
+                                                        double* __restrict__ sums) {
     const int64_t a = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (a >= P) return;
@@ -349,26 +350,37 @@ __global__ void __launch_bounds__(128) leaf_rotation_kernel(const float4* __rest
     }
 #pragma unroll
     for (int q = 0; q < 10; q++) s[q] = butterfly32(s[q]);
+    if (lane < 10) {
+        double val = s[0];
+#pragma unroll
+        for (int q = 1; q < 10; q++)
+            if (lane == q) val = s[q];
+        sums[(int64_t)lane * P + a] = val;  // SoA: the solve kernel reads coalesced
+    }
+}
+
+__global__ void __launch_bounds__(128) leaf_solve_kernel(const double* __restrict__ sums, const float* __restrict__ center, int64_t P,
+                                                         double* __restrict__ Rm, int32_t* __restrict__ ncand) {
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= P) return;
+    double s[10];
+#pragma unroll
+    for (int q = 0; q < 10; q++) s[q] = sums[(int64_t)q * P + a];
     const int m = (int)s[9];
     double R[9];
     if (m < 4) {  // gp_compressor.cpp:31-34
 #pragma unroll
         for (int q = 0; q < 9; q++) R[q] = (q % 4 == 0) ? 1.0 : 0.0;
     } else {
-        const double cd[3] = {(double)cx, (double)cy, (double)cz};
+        const double cd[3] = {(double)center[a * 3], (double)center[a * 3 + 1], (double)center[a * 3 + 2]};
         double v[4];
         smallest_right_singular_vector(s, cd, v);
         double nrm[3] = {v[0], v[1], v[2]};
         rotation_from_normal(nrm, R);
     }
-    if (lane < 9) {
-        double val = R[0];
 #pragma unroll
-        for (int q = 1; q < 9; q++)
-            if (lane == q) val = R[q];
-        Rm[a * 9 + lane] = val;
-    }
-    if (lane == 0) ncand[a] = m;
+    for (int q = 0; q < 9; q++) Rm[a * 9 + q] = R[q];
+    ncand[a] = m;
 }
 
 // ---- K5: owner and local coordinates, one thread per (Morton-sorted) point --------------------
@@ -523,11 +535,12 @@ void launch_leaf_neighbours(const uint64_t* leaf_code, int64_t P, const LatticeD
 }
 
 void launch_leaf_rotation(const void* spt, const int64_t* leaf_start, const int32_t* nbr, const int32_t* nnbr,
-                          const float* center, int64_t P, double r2, double* Rm, int32_t* ncand, cudaStream_t s) {
+                          const float* center, int64_t P, double r2, double* sums, double* Rm, int32_t* ncand, cudaStream_t s) {
     if (P <= 0) return;
-    leaf_rotation_kernel<<<(unsigned)((P * 32 + 127) / 128), 128, 0, s>>>(reinterpret_cast<const float4*>(spt), leaf_start, nbr,
-                                                                        nnbr, center, P, r2, Rm, ncand);
-    g_launches++;
+    leaf_sums_kernel<<<(unsigned)((P * 32 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4*>(spt), leaf_start, nbr, nnbr, center,
+                                                                    P, r2, sums);
+    leaf_solve_kernel<<<(unsigned)((P + 127) / 128), 128, 0, s>>>(sums, center, P, Rm, ncand);
+    g_launches += 2;
 }
 
 void launch_claim(const void* spt, const int32_t* leaf_of, const int32_t* nbr, const int32_t* nnbr, const float* center,
