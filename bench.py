@@ -334,6 +334,8 @@ def main():
         "stages_ms": {k: round(v, 4) for k, v in sorted(stage_ms.items())},
         "patches": int(sizes.n_patches), "claimed": int(sizes.n_claimed), "mean_bv": sizes.n_bv_total / max(1, sizes.n_patches),
         "escalated": fit_stats["escalated"],
+        "fit_events": {k: int(fit_stats[k]) for k in ("n_add", "n_first", "n_sparse", "n_full", "n_del_cap", "n_del_geo", "sum_n", "sum_n2_common",
+                                                      "sum_n2_sparse", "sum_n2_full", "sum_n2_del")},
         "roofline": roof, "cpu_baseline": cpu,
         "e2e": {"value": n_all * K / e2e_cs, "unit": "pts/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": int(d2h),
                 "decompress_value": ndec_all * K / e2e_ds, "compress_ms": 1e3 * e2e_cs / K, "decompress_ms": 1e3 * e2e_ds / K},

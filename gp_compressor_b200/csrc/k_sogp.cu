@@ -397,6 +397,340 @@ __global__ void __launch_bounds__(32, 28) sogp_fit_warp_kernel(SogpArgs a) {
 }
 
 // =====================================================================================
+// Bucket 1 (N + 1 <= 32): TWO WARPS per patch.  Warp 0 owns C, warp 1 owns Q (rows contiguous,
+// P_LD = 34).  Both warps keep alpha / BV / k for index `lane` in registers and compute every scalar
+// redundantly, so a sparse point needs ONE block barrier (the exchange of C k and Q k); the rank-1
+// update of C is done by warp 0 alone while warp 1 already runs ahead to the next point's Q k.
+// A full update costs two barriers, each deletion two more.  Same arithmetic as every other bucket.
+// =====================================================================================
+constexpr int P_N = 32;
+constexpr int P_LD = 34;
+
+struct PairSmem {
+    double C[P_N * P_LD], Q[P_N * P_LD];
+    double kv[2][P_N];          // per-warp copy of k
+    double xv[2][2][P_N];       // [parity of the point][matrix][row]: C k and Q k exchange
+    double sv[2][P_N], ev[2][P_N];
+    StagedPoint pts[2][32];
+    unsigned long long cnt[NCNT];
+    int spos;
+};
+
+template <int NG>
+__device__ __forceinline__ double row4_padded(const double* row, const double* k, int n) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+        if (4 * g < n) {
+            const double2 m01 = *reinterpret_cast<const double2*>(row + 4 * g), m23 = *reinterpret_cast<const double2*>(row + 4 * g + 2);
+            const double2 k01 = *reinterpret_cast<const double2*>(k + 4 * g), k23 = *reinterpret_cast<const double2*>(k + 4 * g + 2);
+            a0 = fma(m01.x, k01.x, a0);
+            a1 = fma(m01.y, k01.y, a1);
+            a2 = fma(m23.x, k23.x, a2);
+            a3 = fma(m23.y, k23.y, a3);
+        }
+    }
+    return __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
+}
+
+__global__ void __launch_bounds__(64, 10) sogp_fit_pair_kernel(SogpArgs a) {
+    __shared__ __align__(16) PairSmem sm;
+    const int t = threadIdx.x, lane = t & 31, mat = t >> 5;
+    double* const Mown = mat ? sm.Q : sm.C;
+    double* const Mrow = Mown + lane * P_LD;
+    const int64_t patch = a.patch_ids ? (int64_t)a.patch_ids[blockIdx.x] : a.first_patch + blockIdx.x;
+    const int64_t o = a.off[patch];
+    const int n = (int)(a.off[patch + 1] - o);
+    const int64_t op = patch - a.out_first;
+    if (n == 0) {
+        if (t == 0) { a.nbv[op] = 0; a.flags[op] = 0; }
+        return;
+    }
+    for (int i = t; i < P_N * P_LD; i += 64) { sm.C[i] = 0.0; sm.Q[i] = 0.0; }
+    sm.kv[mat][lane] = 0.0; sm.sv[mat][lane] = 0.0; sm.ev[mat][lane] = 0.0;
+    if (t < NCNT) sm.cnt[t] = 0;
+    __syncthreads();
+    const double kstar = a.p0, s20 = a.s20, p0 = a.p0, cl = a.cl, eps_tol = a.eps_tol;
+    const int cap = a.capacity, ldmax = a.ld;
+    double alpha = 0.0, b1 = 0.0, b2 = 0.0;
+    int bidx = -1;
+    int N = 0, tt0 = 0;
+    unsigned int run = 0;
+    if (a.handoff_in) {  // resume a patch that outgrew bucket 0 (slots hold W_N x W_N column-major matrices)
+        const double* slot = a.handoff_in + (size_t)blockIdx.x * slot_doubles(W_N);
+        N = reinterpret_cast<const int*>(slot)[0];
+        tt0 = reinterpret_cast<const int*>(slot)[1];
+        if (t < NCNT) sm.cnt[t] = reinterpret_cast<const unsigned long long*>(slot + 2)[t];
+        const double* v = slot + 2 + NCNT;
+        if (lane < W_N) {
+            alpha = v[lane]; b1 = v[W_N + lane]; b2 = v[2 * W_N + lane];
+            bidx = reinterpret_cast<const int*>(v + 3 * W_N + 2 * W_N * W_N)[lane];
+        }
+        for (int e = t; e < W_N * W_N; e += 64) {
+            const int j = e / W_N, i = e - j * W_N;
+            sm.C[i * P_LD + j] = v[3 * W_N + e];
+            sm.Q[i * P_LD + j] = v[3 * W_N + W_N * W_N + e];
+        }
+        __syncthreads();
+    }
+    const double* const gx1 = a.fx1 + o;
+    const double* const gx2 = a.fx2 + o;
+    const double* const gy = a.fy + o;
+    const int32_t* const go = a.forig + o;
+    const bool w0l0 = (t == 0);
+
+    for (int tt = tt0; tt < n; ++tt) {
+        if ((tt & 31) == 0 || tt == tt0) {  // each warp stages its own copy of the next 32 points
+            __syncwarp();
+            const int i = (tt & ~31) + lane;
+            if (i < n) {
+                StagedPoint sp;
+                sp.x1 = gx1[i]; sp.x2 = gx2[i]; sp.y = gy[i]; sp.orig = go[i]; sp.pad = 0;
+                sm.pts[mat][lane] = sp;
+            }
+            __syncwarp();
+        }
+        const StagedPoint pt = sm.pts[mat][tt & 31];
+        const double x1 = pt.x1, x2 = pt.x2, y = pt.y;
+        const int orig = pt.orig;
+        if (N == 0) {  // sparse_gp.hpp:100-110
+            const double d = __dadd_rn(kstar, s20);
+            if (lane == 0) { alpha = __ddiv_rn(y, d); b1 = x1; b2 = x2; bidx = orig; }
+            if (t == 0) { sm.C[0] = __ddiv_rn(-1.0, d); sm.cnt[0]++; }
+            if (t == 32) sm.Q[0] = __ddiv_rn(1.0, kstar);
+            N = 1;
+            __syncthreads();
+            continue;
+        }
+        const bool act = lane < N;
+        double kl = rbf(x1, x2, b1, b2, p0, cl);
+        kl = act ? kl : 0.0;
+        sm.kv[mat][lane] = kl;
+        __syncwarp();
+        double rv = 0.0;
+        if (act) rv = row4_padded<8>(Mrow, sm.kv[mat], N);
+        const int par = tt & 1;
+        sm.xv[par][mat][lane] = rv;
+        __syncthreads();  // the one barrier of a sparse point
+        const double other = sm.xv[par][1 - mat][lane];
+        const double ck = mat ? other : rv, el = mat ? rv : other;
+        double pm = act ? fma(alpha, kl, 0.0) : 0.0;
+        double pc = act ? fma(kl, ck, 0.0) : 0.0;
+        double pe = act ? fma(kl, el, 0.0) : 0.0;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            pm = __dadd_rn(pm, shfl_xor_d(pm, off));
+            pc = __dadd_rn(pc, shfl_xor_d(pc, off));
+            pe = __dadd_rn(pe, shfl_xor_d(pe, off));
+        }
+        const double s2 = __dadd_rn(kstar, pc);
+        const double den = __dadd_rn(s20, s2);
+        const double rr = __ddiv_rn(-1.0, den);
+        const double q = __ddiv_rn(__dadd_rn(y, -pm), den);
+        double gamma = __dadd_rn(kstar, -pe);
+        if (gamma < tiny12()) gamma = 0.0;
+        if (gamma < eps_tol) {
+            // sparse update (:155-163): Q untouched, warp 1 goes straight on to the next point
+            run++;
+            const double eta = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn(gamma, rr)));
+            const double sh = act ? __dadd_rn(ck, el) : 0.0;
+            if (act) alpha = __dadd_rn(alpha, __dmul_rn(sh, __dmul_rn(q, eta)));
+            if (mat == 0) {
+                sm.sv[0][lane] = sh;
+                __syncwarp();
+                const double re = __dmul_rn(rr, eta);
+                if (act) {
+#pragma unroll
+                    for (int p2 = 0; p2 < P_N / 2; p2++) {
+                        const int j = 2 * p2;
+                        if (j < N) {
+                            double2 c = *reinterpret_cast<double2*>(Mrow + j);
+                            const double2 s2v = *reinterpret_cast<const double2*>(sm.sv[0] + j);
+                            c.x = fma(re, __dmul_rn(sh, s2v.x), c.x);
+                            if (j + 1 < N) c.y = fma(re, __dmul_rn(sh, s2v.y), c.y);
+                            *reinterpret_cast<double2*>(Mrow + j) = c;
+                        }
+                    }
+                }
+            }
+            continue;
+        }
+        // full update (:164-203)
+        if (w0l0) {
+            const unsigned long long n2 = (unsigned long long)N * N;
+            sm.cnt[1] += run; sm.cnt[5] += (unsigned long long)run * N; sm.cnt[6] += run * n2; sm.cnt[7] += run * n2;
+        }
+        run = 0;
+        if (N + 1 > ldmax) {  // hand the state to bucket 2 (slots hold P_N x P_N column-major matrices)
+            if (t == 0) sm.spos = atomicAdd(a.queue_count, 1);
+            __syncthreads();
+            const int pos = sm.spos;
+            double* slot = a.handoff_out + (size_t)pos * slot_doubles(P_N);
+            if (t == 0) {
+                a.queue[pos] = (int32_t)patch;
+                reinterpret_cast<int*>(slot)[0] = N;
+                reinterpret_cast<int*>(slot)[1] = tt;
+                for (int i = 0; i < NCNT; i++) reinterpret_cast<unsigned long long*>(slot + 2)[i] = sm.cnt[i];
+            }
+            double* v = slot + 2 + NCNT;
+            if (mat == 0) {
+                v[lane] = alpha; v[P_N + lane] = b1; v[2 * P_N + lane] = b2;
+                reinterpret_cast<int*>(v + 3 * P_N + 2 * P_N * P_N)[lane] = bidx;
+            }
+            for (int e = t; e < P_N * P_N; e += 64) {
+                const int j = e / P_N, i = e - j * P_N;
+                v[3 * P_N + e] = sm.C[i * P_LD + j];
+                v[3 * P_N + P_N * P_N + e] = sm.Q[i * P_LD + j];
+            }
+            return;
+        }
+        if (w0l0) {
+            sm.cnt[2]++; sm.cnt[5] += N; sm.cnt[6] += (unsigned long long)N * N; sm.cnt[8] += (unsigned long long)(N + 1) * (N + 1);
+        }
+        {
+            double svl = act ? ck : 0.0, evl = act ? el : 0.0;
+            if (act) alpha = __dadd_rn(alpha, __dmul_rn(q, ck));
+            if (lane == N) {
+                svl = 1.0; evl = -1.0;
+                alpha = __dadd_rn(0.0, __dmul_rn(q, 1.0));
+                b1 = x1; b2 = x2; bidx = orig;
+            }
+            sm.sv[mat][lane] = svl;
+            sm.ev[mat][lane] = evl;
+            __syncwarp();
+            const int N1 = N + 1;
+            const double coef = mat ? __ddiv_rn(1.0, gamma) : rr;       // Q += (1/gamma) e' e'^T ; C += r s s^T
+            const double* const vec = mat ? sm.ev[1] : sm.sv[0];
+            const double vi = mat ? evl : svl;
+            if (lane < N1) {
+#pragma unroll 4
+                for (int j = 0; j < N1; j += 2) {
+                    double2 c = *reinterpret_cast<double2*>(Mrow + j);
+                    const double2 w2 = *reinterpret_cast<const double2*>(vec + j);
+                    c.x = fma(coef, __dmul_rn(vi, w2.x), c.x);
+                    if (j + 1 < N1) c.y = fma(coef, __dmul_rn(vi, w2.y), c.y);
+                    *reinterpret_cast<double2*>(Mrow + j) = c;
+                }
+            }
+            N = N1;
+        }
+        // capacity deletions (:206-223) then geometric deletions (:226-242)
+        double minscore = 0.0;
+        for (int phase = 0; phase < 2; phase++) {
+            for (;;) {
+                if (phase == 0 ? !(N > cap) : !(minscore < geo9() && N > 1)) break;
+                __syncthreads();  // both matrices up to date before their diagonals / columns are read
+                double best = 0.0;
+                int bi = 0x7fffffff, nan0 = 0;
+                if (lane < N) {
+                    const double qii = sm.Q[lane * P_LD + lane];
+                    const double sc = (phase == 0) ? __ddiv_rn(__dmul_rn(alpha, alpha), __dadd_rn(qii, sm.C[lane * P_LD + lane]))
+                                                   : __ddiv_rn(1.0, qii);
+                    if (sc != sc) nan0 = (lane == 0);
+                    else { best = sc; bi = lane; }
+                }
+                argmin_combine(best, bi);
+                nan0 = __shfl_sync(0xffffffffu, nan0, 0);
+                int loc = bi;
+                if (nan0) { loc = 0; best = __longlong_as_double(0x7ff8000000000000LL); }
+                if (phase == 1) {
+                    minscore = best;
+                    if (!(minscore < geo9())) break;
+                }
+                // ---- delete_bv(loc), :252-295 ----
+                const int L = N - 1, M = N - 1;
+                if (w0l0) { sm.cnt[9] += (unsigned long long)M * M; sm.cnt[phase == 0 ? 3 : 4]++; }
+                double csi = 0, qsi = 0, rep = 0;
+                const int src = (lane == loc) ? L : lane;
+                if (lane < N) {
+                    csi = sm.C[loc * P_LD + src]; qsi = sm.Q[loc * P_LD + src];
+                    rep = Mown[L * P_LD + src];
+                }
+                const double cstar = sm.C[loc * P_LD + loc], qstar = sm.Q[loc * P_LD + loc];
+                const double astar = __shfl_sync(0xffffffffu, alpha, loc);
+                const double aL = __shfl_sync(0xffffffffu, alpha, L);
+                const double b1L = __shfl_sync(0xffffffffu, b1, L), b2L = __shfl_sync(0xffffffffu, b2, L);
+                const int idL = __shfl_sync(0xffffffffu, bidx, L);
+                __syncthreads();  // every read of the old matrices is done
+                const double qcs = __dadd_rn(qstar, cstar);
+                const double coef = __ddiv_rn(astar, qcs);
+                const double iq = __ddiv_rn(1.0, qstar), iqc = __ddiv_rn(1.0, qcs);
+                double qci = 0.0;
+                if (lane < N) {
+                    if (lane < M) {
+                        if (loc != L) {
+                            Mown[loc * P_LD + lane] = rep; Mown[lane * P_LD + loc] = rep;
+                            if (lane == loc) { b1 = b1L; b2 = b2L; bidx = idL; }
+                        }
+                        qci = __dadd_rn(qsi, csi);
+                        const double ai = (lane == loc) ? aL : alpha;
+                        alpha = __dadd_rn(ai, -__dmul_rn(coef, qci));
+                    } else {
+                        qsi = 0.0;
+                    }
+                    Mown[L * P_LD + lane] = 0.0; Mown[lane * P_LD + L] = 0.0;
+                    if (lane == L) { alpha = 0.0; b1 = 0.0; b2 = 0.0; bidx = -1; }
+                } else {
+                    qsi = 0.0;
+                }
+                sm.sv[mat][lane] = qsi;   // Qstar (zero beyond M)
+                sm.ev[mat][lane] = qci;   // Qstar + Cstar
+                __syncwarp();
+                if (lane < M) {
+                    const double* const qv = sm.sv[mat];
+                    const double* const cv = sm.ev[mat];
+#pragma unroll 4
+                    for (int j = 0; j < M; j += 2) {
+                        double2 c = *reinterpret_cast<double2*>(Mrow + j);
+                        const double2 q2 = *reinterpret_cast<const double2*>(qv + j);
+                        const double2 c2 = *reinterpret_cast<const double2*>(cv + j);
+                        const double u0 = __dmul_rn(qsi, q2.x), u1 = __dmul_rn(qsi, q2.y);
+                        if (mat == 0) {
+                            const double w0 = fma(u0, iq, -__dmul_rn(__dmul_rn(qci, c2.x), iqc));
+                            const double w1 = fma(u1, iq, -__dmul_rn(__dmul_rn(qci, c2.y), iqc));
+                            c.x = __dadd_rn(c.x, w0);
+                            if (j + 1 < M) c.y = __dadd_rn(c.y, w1);
+                        } else {
+                            c.x = fma(-u0, iq, c.x);
+                            if (j + 1 < M) c.y = fma(-u1, iq, c.y);
+                        }
+                        *reinterpret_cast<double2*>(Mrow + j) = c;
+                    }
+                }
+                N = M;
+            }
+        }
+    }
+    __syncthreads();
+    if (t == 0) {
+        const unsigned long long n2 = (unsigned long long)N * N;
+        sm.cnt[1] += run; sm.cnt[5] += (unsigned long long)run * N; sm.cnt[6] += run * n2; sm.cnt[7] += run * n2;
+        a.nbv[op] = N;
+        const double c00 = sm.C[0];
+        a.flags[op] = (c00 != c00) ? 1 : 0;
+        unsigned long long* st = a.stats;
+        atomicAdd(st + 0, (unsigned long long)n);
+        for (int i = 0; i < NCNT; i++)
+            if (sm.cnt[i]) atomicAdd(st + 1 + i, sm.cnt[i]);
+    }
+    const int64_t ob = op * cap;
+    if (mat == 0 && lane < N) {
+        a.o_alpha[ob + lane] = alpha;
+        a.o_b1[ob + lane] = b1;
+        a.o_b2[ob + lane] = b2;
+        a.o_idx[ob + lane] = bidx;
+    }
+    if (a.dumpC) {
+        const int64_t od = op * (int64_t)cap * cap;
+        for (int e = t; e < N * N; e += 64) {
+            const int i = e / N, j = e - i * N;
+            a.dumpC[od + e] = sm.C[i * P_LD + j];
+            a.dumpQ[od + e] = sm.Q[i * P_LD + j];
+        }
+    }
+}
+
+// =====================================================================================
 // Buckets 1-3: NT = 2*RB threads per patch, LD constexpr
 // =====================================================================================
 template <int NT>
@@ -747,7 +1081,9 @@ cudaError_t launch_sogp_fit(int bucket, const SogpArgs& a, cudaStream_t st) {
         case 0:
             sogp_fit_warp_kernel<<<a.n_work, 32, 0, st>>>(a);
             return cudaGetLastError();
-        case 1: return launch_cta_bucket<32, 32, 64, W_N>(a, st);
+        case 1:
+            sogp_fit_pair_kernel<<<a.n_work, 64, 0, st>>>(a);
+            return cudaGetLastError();
         case 2: return launch_cta_bucket<64, 64, 128, 32>(a, st);
         default: return launch_cta_bucket<118, 128, 256, 64>(a, st);
     }
