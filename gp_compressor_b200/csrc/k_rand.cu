@@ -56,9 +56,9 @@ cudaError_t rand_upload_tables(const RandTables* T) {
     return cudaMemcpyToSymbol(c_base, T->base, sizeof(T->base));
 }
 
-constexpr int RAND_PER_THREAD = 512;
+constexpr int RAND_PER_THREAD = 2048;
 
-__global__ void __launch_bounds__(128) rand_stream_kernel(uint64_t offset, int64_t n, uint32_t* __restrict__ out) {
+__global__ void __launch_bounds__(32) rand_stream_kernel(uint64_t offset, int64_t n, uint32_t* __restrict__ out) {
     int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t first = b * RAND_PER_THREAD;
     if (first >= n) return;
@@ -94,8 +94,8 @@ __global__ void __launch_bounds__(128) rand_stream_kernel(uint64_t offset, int64
 void launch_rand_stream(uint64_t offset, int64_t n, uint32_t* out, cudaStream_t s) {
     if (n <= 0) return;
     int64_t threads = (n + RAND_PER_THREAD - 1) / RAND_PER_THREAD;
-    int blocks = (int)((threads + 127) / 128);
-    rand_stream_kernel<<<blocks, 128, 0, s>>>(offset, n, out);
+    int blocks = (int)((threads + 31) / 32);  // small blocks: the few thousand threads spread over all SMs
+    rand_stream_kernel<<<blocks, 32, 0, s>>>(offset, n, out);
     g_launches++;
 }
 

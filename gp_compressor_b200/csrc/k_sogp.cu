@@ -58,14 +58,28 @@ __device__ __forceinline__ void publish(const SogpArgs& a, const Counters& k, in
         if (k.c[i]) atomicAdd(st + 1 + i, k.c[i]);
 }
 
-// "first strict minimum" combine of (score, index) pairs (sparse_gp.hpp:210-217, 230-236)
-__device__ __forceinline__ void argmin_combine(double& best, int& bi) {
+// argmin with the reference's "first strict minimum" scan (sparse_gp.hpp:210-217, 230-236) over one
+// score per lane (idx = the element the lane holds, 0x7fffffff if none).  A NaN score never wins unless
+// it is element 0, in which case nothing is ever "< minscore": loc stays 0 and the minimum is NaN.
+// Min by butterfly on the value alone, then the lowest index among the lanes that hold that value.
+__device__ __forceinline__ int warp_first_min(double sc, int idx, double* minscore) {
+    const bool valid = idx != 0x7fffffff;
+    const bool isn = sc != sc;
+    const int nan0 = __any_sync(0xffffffffu, valid && isn && idx == 0);
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    const double v = (valid && !isn) ? sc : inf;
+    double m = v;
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        double ob = shfl_xor_d(best, off);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-        if (oi != 0x7fffffff && (bi == 0x7fffffff || ob < best || (ob == best && oi < bi))) { best = ob; bi = oi; }
+    for (int off = 16; off >= 1; off >>= 1) m = fmin(m, shfl_xor_d(m, off));
+    int cand = (valid && !isn && v == m) ? idx : 0x7fffffff;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, off));
+    if (nan0) {
+        *minscore = __longlong_as_double(0x7ff8000000000000LL);
+        return 0;
     }
+    *minscore = m;
+    return cand;
 }
 
 // =====================================================================================
@@ -299,23 +313,20 @@ __global__ void __launch_bounds__(32, 28) sogp_fit_warp_kernel(SogpArgs a) {
         for (int phase = 0; phase < 2; phase++) {
             for (;;) {
                 if (phase == 0 ? !(N > cap) : !(minscore < geo9() && N > 1)) break;
-                double best = 0.0;
-                int bi = 0x7fffffff, nan0 = 0;
+                double sc = 0.0;
                 if (lane < N) {
                     const double qii = Q[lane * W_LD + lane];
-                    const double sc = (phase == 0) ? __ddiv_rn(__dmul_rn(alpha, alpha), __dadd_rn(qii, C[lane * W_LD + lane]))
-                                                   : __ddiv_rn(1.0, qii);
-                    if (sc != sc) nan0 = (lane == 0);
-                    else { best = sc; bi = lane; }
+                    sc = (phase == 0) ? __ddiv_rn(__dmul_rn(alpha, alpha), __dadd_rn(qii, C[lane * W_LD + lane])) : __ddiv_rn(1.0, qii);
                 }
-                argmin_combine(best, bi);
-                nan0 = __shfl_sync(0xffffffffu, nan0, 0);
-                int loc = bi;
-                if (nan0) { loc = 0; best = __longlong_as_double(0x7ff8000000000000LL); }
                 if (phase == 1) {
-                    minscore = best;
-                    if (!(minscore < geo9())) break;
+                    // exact shortcut: the scan deletes iff score_0 is not NaN and some score is < 1e-9f
+                    const bool hit = __any_sync(0xffffffffu, lane < N && sc < geo9());
+                    const bool nan0 = __any_sync(0xffffffffu, lane == 0 && sc != sc);
+                    if (!hit || nan0) { minscore = geo9(); break; }
                 }
+                double best;
+                const int loc = warp_first_min(sc, lane < N ? lane : 0x7fffffff, &best);
+                if (phase == 1) minscore = best;
                 // ---- delete_bv(loc), :252-295 ----
                 const int L = N - 1, M = N - 1;
                 if (lane == 0) { sm.cnt[9] += (unsigned long long)M * M; sm.cnt[phase == 0 ? 3 : 4]++; }
@@ -620,23 +631,20 @@ __global__ void __launch_bounds__(64, 10) sogp_fit_pair_kernel(SogpArgs a) {
             for (;;) {
                 if (phase == 0 ? !(N > cap) : !(minscore < geo9() && N > 1)) break;
                 __syncthreads();  // both matrices up to date before their diagonals / columns are read
-                double best = 0.0;
-                int bi = 0x7fffffff, nan0 = 0;
+                double sc = 0.0;
                 if (lane < N) {
                     const double qii = sm.Q[lane * P_LD + lane];
-                    const double sc = (phase == 0) ? __ddiv_rn(__dmul_rn(alpha, alpha), __dadd_rn(qii, sm.C[lane * P_LD + lane]))
-                                                   : __ddiv_rn(1.0, qii);
-                    if (sc != sc) nan0 = (lane == 0);
-                    else { best = sc; bi = lane; }
+                    sc = (phase == 0) ? __ddiv_rn(__dmul_rn(alpha, alpha), __dadd_rn(qii, sm.C[lane * P_LD + lane])) : __ddiv_rn(1.0, qii);
                 }
-                argmin_combine(best, bi);
-                nan0 = __shfl_sync(0xffffffffu, nan0, 0);
-                int loc = bi;
-                if (nan0) { loc = 0; best = __longlong_as_double(0x7ff8000000000000LL); }
                 if (phase == 1) {
-                    minscore = best;
-                    if (!(minscore < geo9())) break;
+                    // exact shortcut: the scan deletes iff score_0 is not NaN and some score is < 1e-9f
+                    const bool hit = __any_sync(0xffffffffu, lane < N && sc < geo9());
+                    const bool nan0 = __any_sync(0xffffffffu, lane == 0 && sc != sc);
+                    if (!hit || nan0) { minscore = geo9(); break; }
                 }
+                double best;
+                const int loc = warp_first_min(sc, lane < N ? lane : 0x7fffffff, &best);
+                if (phase == 1) minscore = best;
                 // ---- delete_bv(loc), :252-295 ----
                 const int L = N - 1, M = N - 1;
                 if (w0l0) { sm.cnt[9] += (unsigned long long)M * M; sm.cnt[phase == 0 ? 3 : 4]++; }
@@ -759,7 +767,7 @@ template <int LD, int MODE>
 __device__ __forceinline__ int warp_argmin(const Smem<LD>& s, int N, int lane, double* minscore) {
     double best = 0.0;
     int bi = 0x7fffffff;
-    int nan0 = 0;
+    bool hit = false, nan0 = false;
     for (int i = lane; i < N; i += 32) {
         const double qii = s.Q()[i * LD + i];
         double sc;
@@ -768,21 +776,25 @@ __device__ __forceinline__ int warp_argmin(const Smem<LD>& s, int N, int lane, d
             sc = __ddiv_rn(__dmul_rn(al, al), __dadd_rn(qii, s.C()[i * LD + i]));
         } else {
             sc = __ddiv_rn(1.0, qii);
+            hit = hit || (sc < geo9());
         }
         if (sc != sc) {
-            if (i == 0) nan0 = 1;
+            if (i == 0) nan0 = true;
             continue;
         }
         if (bi == 0x7fffffff || sc < best) { best = sc; bi = i; }
     }
-    argmin_combine(best, bi);
-    nan0 = __shfl_sync(0xffffffffu, nan0, 0);
-    if (nan0) {
-        *minscore = __longlong_as_double(0x7ff8000000000000LL);
-        return 0;
+    if (MODE == 1) {  // exact shortcut of the geometric scan: nothing to delete unless some score < 1e-9f
+        if (!__any_sync(0xffffffffu, hit) || __any_sync(0xffffffffu, nan0)) {
+            *minscore = geo9();
+            return 0;
+        }
     }
-    *minscore = best;
-    return bi;
+    // lanes hold their own first strict minimum; NaN element 0 is re-detected by the helper through idx 0
+    double sc0 = best;
+    int idx0 = bi;
+    if (nan0) { sc0 = __longlong_as_double(0x7ff8000000000000LL); idx0 = 0; }
+    return warp_first_min(sc0, idx0, minscore);
 }
 
 // sparse_gp::delete_bv, sparse_gp.hpp:252-295.  Uniform across the CTA; ends with a barrier.
