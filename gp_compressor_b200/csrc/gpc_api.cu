@@ -32,7 +32,7 @@ struct gpc_handle {
     DevBuf off, x1, x2, y, perm, patch_of;      // claimed stream, patch-major
     DevBuf fx1, fx2, fy;                        // fit stream (add order)
     DevBuf draws, roff, rnd, scan_tmp, small;   // rand bookkeeping, scan scratch, small readbacks
-    DevBuf nbv, flags, alpha, b1, b2, bidx, dumpC, dumpQ, queue0, queue1, qcount, kstats, hand0, hand1;
+    DevBuf nbv, flags, alpha, b1, b2, bidx, dumpC, dumpQ, queue0, queue1, qcount, kstats, hand0, hand1, spill;
     DevBuf nonempty, slot, out32, heights;
     DevBuf bv_off, palpha, pb1, pb2, pidx;      // packed copies of the fitted parameters (what leaves for the host)
     DevBuf quat, mean, rgbmean, Rm, center, code, ncand, owner, st_idx;
@@ -109,8 +109,7 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
     const int64_t P = h->n_patches;
     if (c.capacity < 1) return fail(h, GPC_ERR_INVALID, "capacity must be >= 1 (the reference's -1 / 0 modes are not built)");
     const int need_ld = c.capacity + 1;
-    if (need_ld > sogp_bucket_ld(3))
-        return fail(h, GPC_ERR_INVALID, "capacity > 117 needs the packed / cluster SOGP kernel (not built yet)");
+    if (need_ld > sogp_bucket_ld(4)) return fail(h, GPC_ERR_INVALID, "capacity > 201 is not supported");
     // shard bounds from the host copy of the offsets
     std::vector<int64_t> hoff(P + 1);
     CK(cudaMemcpyAsync(hoff.data(), h->off.p, (P + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -173,10 +172,10 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
     }
     CK(h->queue0.reserve(PLa * sizeof(int32_t)));
     CK(h->queue1.reserve(PLa * sizeof(int32_t)));
-    CK(h->qcount.reserve(4 * sizeof(int32_t)));
+    CK(h->qcount.reserve(8 * sizeof(int32_t)));
     CK(h->kstats.reserve(16 * sizeof(unsigned long long)));
     CK(cudaMemsetAsync(h->kstats.p, 0, 16 * sizeof(unsigned long long), st));
-    CK(cudaMemsetAsync(h->qcount.p, 0, 4 * sizeof(int32_t), st));
+    CK(cudaMemsetAsync(h->qcount.p, 0, 8 * sizeof(int32_t), st));
     SogpArgs a;
     a.off = h->off.as<int64_t>();
     a.fx1 = h->fx1.as<double>(); a.fx2 = h->fx2.as<double>(); a.fy = h->fy.as<double>();
@@ -192,7 +191,8 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
     a.stats = h->kstats.as<unsigned long long>();
     int64_t work = PL;
     const int32_t* ids = nullptr;
-    for (int b = 0; b < 4 && work > 0; b++) {
+    a.spill = nullptr;
+    for (int b = 0; b < 5 && work > 0; b++) {
         const int bl = sogp_bucket_ld(b);
         const bool final_bucket = need_ld <= bl;
         a.ld = final_bucket ? need_ld : bl;
@@ -210,12 +210,16 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
             CK(ho.reserve((size_t)work * sogp_handoff_slot_bytes(b)));
             a.handoff_out = ho.as<double>();
         }
+        if (b == 4) {
+            CK(h->spill.reserve((size_t)work * sogp_spill_bytes_per_patch()));
+            a.spill = h->spill.as<double>();
+        }
         CK(launch_sogp_fit(b, a, st));
         if (final_bucket) break;
         int32_t qn = 0;
         CK(cudaMemcpyAsync(&qn, h->qcount.as<int32_t>() + b, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        h->stats.escalated[b] = (uint64_t)qn;
+        if (b < 4) h->stats.escalated[b] = (uint64_t)qn;
         work = qn;
         ids = q.as<int32_t>();
     }
@@ -574,7 +578,7 @@ void gpc_destroy(gpc_handle* h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->cloud, &h->off, &h->x1, &h->x2, &h->y, &h->perm, &h->patch_of, &h->fx1, &h->fx2, &h->fy, &h->draws,
                       &h->roff, &h->rnd, &h->scan_tmp, &h->small, &h->nbv, &h->flags, &h->alpha, &h->b1, &h->b2, &h->bidx,
-                      &h->dumpC, &h->dumpQ, &h->queue0, &h->queue1, &h->hand0, &h->hand1, &h->qcount, &h->kstats, &h->bv_off, &h->palpha, &h->pb1, &h->pb2, &h->pidx, &h->nonempty, &h->slot, &h->out32,
+                      &h->dumpC, &h->dumpQ, &h->queue0, &h->queue1, &h->hand0, &h->hand1, &h->spill, &h->qcount, &h->kstats, &h->bv_off, &h->palpha, &h->pb1, &h->pb2, &h->pidx, &h->nonempty, &h->slot, &h->out32,
                       &h->heights, &h->quat, &h->mean, &h->rgbmean, &h->Rm, &h->center, &h->code, &h->ncand, &h->owner,
                       &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
                       &h->ovals2, &h->sort_tmp, &h->flags64, &h->ex, &h->leaf_of, &h->leaf_start, &h->leaf_code_a, &h->spt,

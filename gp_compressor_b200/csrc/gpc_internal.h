@@ -117,11 +117,13 @@ struct SogpArgs {
     int32_t* queue_count;
     const double* handoff_in;  // state slots written by the previous bucket (slot = blockIdx.x), or nullptr
     double* handoff_out;       // state slots for patches that outgrow this bucket (slot = queue position)
+    double* spill;             // bucket 4 only: per-CTA state slices in global memory
     unsigned long long* stats;  // 11 counters, see gpc_stats
 };
-// bucket b supports ld <= {16, 32, 64, 118}
+// bucket b supports ld <= {16, 32, 64, 118, 202}; bucket 4 keeps its state in global memory
 int sogp_bucket_ld(int bucket);
 size_t sogp_handoff_slot_bytes(int bucket);
+size_t sogp_spill_bytes_per_patch();
 cudaError_t launch_sogp_fit(int bucket, const SogpArgs& a, cudaStream_t s);
 
 // ---- K8: grid prediction ----------------------------------------------------------------

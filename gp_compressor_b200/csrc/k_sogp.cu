@@ -852,9 +852,12 @@ __device__ __forceinline__ void delete_bv(const Smem<LD>& s, int& N, int loc, in
     cta_sync<NT>();
 }
 
-template <int LD, int RB, int NT, int LD_IN>
+template <int LD, int RB, int NT, int LD_IN, bool SPILL>
 __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
-    extern __shared__ double smem_d[];
+    extern __shared__ double smem_dyn[];
+    // SPILL: the state lives in a per-CTA slice of global memory (L2-resident) instead of shared memory;
+    // block barriers order the accesses exactly as they do for shared memory.
+    double* const smem_d = SPILL ? a.spill + (size_t)blockIdx.x * (2 * LD * LD + 10 * LD) : smem_dyn;
     const Smem<LD> s{smem_d};
     double* const C = s.C();
     double* const Q = s.Q();
@@ -1064,25 +1067,27 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
 template <int LD>
 constexpr size_t cta_smem_bytes() { return (size_t)(2 * LD * LD + 9 * LD) * sizeof(double) + (size_t)LD * sizeof(int); }
 
-template <int LD, int RB, int NT, int LD_IN>
+template <int LD, int RB, int NT, int LD_IN, bool SPILL>
 cudaError_t launch_cta_bucket(const SogpArgs& a, cudaStream_t st) {
-    constexpr size_t smem = cta_smem_bytes<LD>();
+    constexpr size_t smem = SPILL ? 0 : cta_smem_bytes<LD>();
     static bool configured = false;
     if (smem > 48 * 1024 && !configured) {
-        cudaError_t e = cudaFuncSetAttribute(sogp_fit_kernel<LD, RB, NT, LD_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(sogp_fit_kernel<LD, RB, NT, LD_IN, SPILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    sogp_fit_kernel<LD, RB, NT, LD_IN><<<a.n_work, NT, smem, st>>>(a);
+    sogp_fit_kernel<LD, RB, NT, LD_IN, SPILL><<<a.n_work, NT, smem, st>>>(a);
     return cudaGetLastError();
 }
 
 }  // namespace
 
 int sogp_bucket_ld(int bucket) {
-    static const int lds[4] = {16, 32, 64, 118};
+    static const int lds[5] = {16, 32, 64, 118, 202};
     return lds[bucket];
 }
+
+size_t sogp_spill_bytes_per_patch() { return (size_t)(2 * 202 * 202 + 10 * 202) * sizeof(double); }
 
 size_t sogp_handoff_slot_bytes(int bucket) { return (size_t)slot_doubles(sogp_bucket_ld(bucket)) * sizeof(double); }
 
@@ -1096,8 +1101,9 @@ cudaError_t launch_sogp_fit(int bucket, const SogpArgs& a, cudaStream_t st) {
         case 1:
             sogp_fit_pair_kernel<<<a.n_work, 64, 0, st>>>(a);
             return cudaGetLastError();
-        case 2: return launch_cta_bucket<64, 64, 128, 32>(a, st);
-        default: return launch_cta_bucket<118, 128, 256, 64>(a, st);
+        case 2: return launch_cta_bucket<64, 64, 128, 32, false>(a, st);
+        case 3: return launch_cta_bucket<118, 128, 256, 64, false>(a, st);
+        default: return launch_cta_bucket<202, 256, 512, 118, true>(a, st);
     }
 }
 

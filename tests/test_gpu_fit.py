@@ -79,10 +79,10 @@ def test_device_rand_stream(G, oracle_mod):
     assert np.array_equal(a[700:], b)
 
 
-@pytest.mark.parametrize("cap", [1, 2, 5, 15, 16, 20, 31, 40, 64, 100, 117])
+@pytest.mark.parametrize("cap", [1, 2, 5, 15, 16, 20, 31, 32, 40, 63, 64, 100, 117, 118, 150, 200])
 def test_fit_bind_hyperset_all_buckets(G, oracle_mod, cap):
     """Capacity binds: exercises full updates, capacity deletions and every SOGP bucket."""
-    sizes = [0, 1, 2, 3, 17, 64, 150, 0, 333, 40]
+    sizes = [0, 1, 2, 3, 17, 64, 150, 0, 333, 40] + ([700] if cap > 100 else [])
     off, x1, x2, y = make_patches(100 + cap, sizes)
     check_fit(G, oracle_mod, off, x1, x2, y, capacity=cap, **bind())
 
@@ -207,6 +207,6 @@ def test_errors(G):
     with pytest.raises(G.GpcError):
         G.Handle(capacity=0).fit_patches([0, 1], [0.0], [0.0], [0.0])
     with pytest.raises(G.GpcError):
-        G.Handle(capacity=200).fit_patches([0, 1], [0.0], [0.0], [0.0])
+        G.Handle(capacity=202).fit_patches([0, 1], [0.0], [0.0], [0.0])
     with pytest.raises(G.GpcError):
         G.Handle().decompress_resident()

@@ -2,6 +2,7 @@
 import collections, csv, io, re, subprocess, sys
 
 def launches(path, top=14):
+    top = int(top)
     rows=[r for r in csv.reader(open(path)) if len(r)>10]
     hdr=rows[0]; ki=hdr.index('Kernel Name'); vi=hdr.index('Metric Value')
     agg=collections.OrderedDict()
