@@ -1,0 +1,59 @@
+"""BASELINE configs[2] and [3] at single-GPU scale: SOGP capacity sweep (shared-memory-resident vs spill regime) on a
+dense cloud, and decode-only grid evaluation.  Prints markdown tables (stored in profiles/)."""
+import sys, time
+sys.path.insert(0, '.')
+import numpy as np
+import gp_compressor_b200 as G
+from gp_compressor_b200 import synth
+F32 = lambda v: float(np.float32(v))
+
+def fp64_flops(st):
+    return (4 * st["sum_n2_common"] + 41 * st["sum_n"] + 20 * (st["n_add"] - st["n_first"]) + 2 * st["sum_n2_sparse"]
+            + 4 * st["sum_n2_full"] + 6 * st["sum_n2_del"])
+def smem_bytes(st):
+    return 16.0 * st["sum_n2_common"] + 16.0 * st["sum_n2_sparse"] + 32.0 * st["sum_n2_full"] + 32.0 * st["sum_n2_del"]
+
+def c3(points, side):
+    cloud = synth.c3_dense_floor(points, seed=3, side=side)
+    print(f"\n### C3 capacity sweep: {points} pts on {side}x{side} m (~{points / (side / 0.1) ** 2:.0f} pts/patch), res 0.1f, hyper BIND, 1 x B200\n")
+    print("| capacity | bucket regime | fit ms | compress pts/s | mean BV | full / sparse / cap-del | GFLOP/s (alg.) | SMEM GB/s (alg.) | frac of LDS.128 peak |")
+    print("|---|---|---|---|---|---|---|---|---|")
+    h0 = G.Handle()
+    smem_peak = h0.debug_peak(1)
+    for cap in (10, 20, 30, 50, 75, 100, 117, 150, 200):
+        h = G.Handle(res=F32(0.1), sz=10, capacity=cap, **synth.hyper_bind(F32(0.1)))
+        h.upload_cloud(cloud)
+        best = None
+        for it in range(2):
+            h.compress_resident()
+            st = h.stats()
+            if best is None or st["ms_total"] < best["ms_total"]:
+                best = st
+        s = h.sizes()
+        regime = "warp (<=15)" if cap <= 15 else "pair (<=31)" if cap <= 31 else "CTA smem (<=63)" if cap <= 63 else "CTA smem (<=117)" if cap <= 117 else "spill (global/L2)"
+        sec = best["ms_fit"] * 1e-3
+        print(f"| {cap} | {regime} | {best['ms_fit']:.2f} | {points / (best['ms_total'] * 1e-3):.3e} | {s.n_bv_total / max(1, s.n_patches):.1f} | "
+              f"{best['n_full']} / {best['n_sparse']} / {best['n_del_cap']} | {fp64_flops(best) / sec / 1e9:.0f} | {smem_bytes(best) / sec / 1e9:.0f} | {smem_bytes(best) / sec / smem_peak:.3f} |")
+        h.close()
+
+def c4(n_patches, nbv, sz=64):
+    prm = synth.c4_patch_params(n_patches=n_patches, nbv=nbv, seed=4)
+    h = G.Handle(res=F32(0.1), sz=sz, capacity=nbv)
+    h.set_params(**prm)
+    fp64_peak = h.debug_peak(0)
+    best = 1e9
+    for it in range(3):
+        n = h.decompress_resident()
+        best = min(best, h.stats()["ms_predict"])
+    flops = n * (37.0 * nbv + 18)
+    print(f"| {n_patches} | {nbv} | {sz}x{sz} | {n} | {best:.2f} | {n / (best * 1e-3):.3e} | {flops / (best * 1e-3) / 1e12:.2f} | {flops / (best * 1e-3) / fp64_peak:.3f} | {n * 32 / (best * 1e-3) / 1e9:.0f} |")
+    h.close()
+
+if __name__ == "__main__":
+    c3(1_000_000, 3.2)
+    print("\n### C4 decode only (per-GPU share of the 1M-patch configuration), REF kernel, 1 x B200\n")
+    print("| patches | BVs/patch | grid | output pts | predict ms | grid pts/s | TFLOP/s (37N+18 per pt) | frac of FP64 peak | output GB/s |")
+    print("|---|---|---|---|---|---|---|---|---|")
+    c4(125_000, 30)
+    c4(125_000, 100)
+    c4(250_000, 30)
