@@ -367,8 +367,8 @@ int run_binning(gpc_handle* h, StageTimer& tm) {
     if (n > 0x7fffffff) return fail(h, GPC_ERR_INVALID, "more than 2^31-1 points");
     h->have_binning = h->have_frames = h->have_fit = false;
     CK(h->small.reserve(64));
-    unsigned long long* d_best = h->small.as<unsigned long long>();
-    unsigned long long* d_nvalid = d_best + 1;
+    unsigned long long* d_best = h->small.as<unsigned long long>();  // [0] index, [1..2] the point (4 floats)
+    unsigned long long* d_nvalid = d_best + 4;
     // ---- lattice replay ----
     size_t t0 = tm.mark();
     HostLattice L;
@@ -376,13 +376,13 @@ int run_binning(gpc_handle* h, StageTimer& tm) {
     int64_t start = 0;
     for (;;) {
         launch_first_violation(cloud, n, start, to_dev(L), L.defined ? 1 : 0, d_best, st);
-        unsigned long long best = 0;
-        CK(cudaMemcpyAsync(&best, d_best, sizeof(best), cudaMemcpyDeviceToHost, st));
+        unsigned long long rb[3] = {0, 0, 0};
+        CK(cudaMemcpyAsync(rb, d_best, sizeof(rb), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        const unsigned long long best = rb[0];
         if (best == ~0ull) break;
         float p[4];
-        CK(cudaMemcpyAsync(p, cloud + (int64_t)best * GPC_POINT_BYTES, sizeof(p), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        std::memcpy(p, &rb[1], sizeof(p));
         lattice_adopt(L, p);
         if (L.depth > 21) return fail(h, GPC_ERR_OVERFLOW, "octree deeper than 21 levels: res too small for the cloud extent");
         start = (int64_t)best + 1;
@@ -408,7 +408,7 @@ int run_binning(gpc_handle* h, StageTimer& tm) {
     CK(h->vals.reserve(n * sizeof(uint32_t)));
     CK(h->vals2.reserve(n * sizeof(uint32_t)));
     CK(h->sort_tmp.reserve(radix_sort_tmp_bytes(n)));
-    launch_point_keys(cloud, n, lat, h->keys.as<uint64_t>(), h->vals.as<uint32_t>(), d_nvalid, st);
+    launch_point_keys(cloud, n, lat, h->keys.as<uint64_t>(), h->vals.as<uint32_t>(), st);
     size_t t2 = tm.mark();
     tm.span(&h->stats.ms_keys, t1, t2);
     int which = launch_radix_sort(h->keys.as<uint64_t>(), h->vals.as<uint32_t>(), h->keys2.as<uint64_t>(), h->vals2.as<uint32_t>(), n,
@@ -416,6 +416,7 @@ int run_binning(gpc_handle* h, StageTimer& tm) {
     uint64_t* skeys = which ? h->keys2.as<uint64_t>() : h->keys.as<uint64_t>();
     uint32_t* svals = which ? h->vals2.as<uint32_t>() : h->vals.as<uint32_t>();
     uint64_t* fkeys = which ? h->keys.as<uint64_t>() : h->keys2.as<uint64_t>();  // free buffer for the owner keys
+    launch_count_valid(skeys, n, L.depth, d_nvalid, st);
     size_t t3 = tm.mark();
     tm.span(&h->stats.ms_sort, t2, t3);
     unsigned long long nv = 0;

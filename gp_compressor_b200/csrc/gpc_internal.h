@@ -44,8 +44,8 @@ struct LatticeDev {          // PCL octree bounding box (doubles), voxel size an
 };
 void launch_first_violation(const uint8_t* cloud, int64_t n, int64_t start, const LatticeDev& lat, int defined,
                             unsigned long long* best, cudaStream_t s);
-void launch_point_keys(const uint8_t* cloud, int64_t n, const LatticeDev& lat, uint64_t* keys, uint32_t* vals,
-                       unsigned long long* n_valid, cudaStream_t s);
+void launch_point_keys(const uint8_t* cloud, int64_t n, const LatticeDev& lat, uint64_t* keys, uint32_t* vals, cudaStream_t s);
+void launch_count_valid(const uint64_t* sorted_keys, int64_t n, uint32_t depth, unsigned long long* n_valid, cudaStream_t s);
 size_t radix_sort_tmp_bytes(int64_t n);
 int launch_radix_sort(uint64_t* keys, uint32_t* vals, uint64_t* keys2, uint32_t* vals2, int64_t n, int nbits, void* tmp,
                       cudaStream_t s);

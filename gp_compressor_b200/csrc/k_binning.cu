@@ -79,17 +79,23 @@ __global__ void __launch_bounds__(256) first_violation_kernel(const uint8_t* __r
     if (threadIdx.x == 0 && sbest != ~0ull) atomicMin(best, sbest);
 }
 
+// copies the winning point next to the index so that the host needs one read-back per growth event
+__global__ void fetch_violator_kernel(const uint8_t* __restrict__ cloud, unsigned long long* __restrict__ best) {
+    const unsigned long long b = best[0];
+    if (b == ~0ull) return;
+    const float4 p = *reinterpret_cast<const float4*>(cloud + (int64_t)b * GPC_POINT_BYTES);
+    float* o = reinterpret_cast<float*>(best + 1);
+    o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = 0.0f;
+}
+
 // ---- K1: voxel key -> Morton code (PCL genOctreeKeyforPoint) --------------------------------
 __global__ void __launch_bounds__(256) point_keys_kernel(const uint8_t* __restrict__ cloud, int64_t n, LatticeDev lat,
-                                                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                                         unsigned long long* __restrict__ n_valid) {
+                                                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool ok = false;
     if (i < n) {
         const float4 p = *reinterpret_cast<const float4*>(cloud + i * GPC_POINT_BYTES);
         uint64_t code = 1ull << (3 * lat.depth);  // non-finite points sort behind every voxel
         if (finite3(p.x, p.y, p.z)) {
-            ok = true;
             uint32_t kx = __double2uint_rz(__ddiv_rn(__dadd_rn((double)p.x, -lat.mn[0]), lat.res));
             uint32_t ky = __double2uint_rz(__ddiv_rn(__dadd_rn((double)p.y, -lat.mn[1]), lat.res));
             uint32_t kz = __double2uint_rz(__ddiv_rn(__dadd_rn((double)p.z, -lat.mn[2]), lat.res));
@@ -98,8 +104,16 @@ __global__ void __launch_bounds__(256) point_keys_kernel(const uint8_t* __restri
         keys[i] = code;
         vals[i] = (uint32_t)i;
     }
-    unsigned m = __ballot_sync(0xffffffffu, ok);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_valid, (unsigned long long)__popc(m));
+}
+
+// number of finite points = first sorted position whose key carries the "non-finite" bit
+__global__ void count_valid_kernel(const uint64_t* __restrict__ skeys, int64_t n, uint64_t invalid, unsigned long long* __restrict__ n_valid) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (skeys[mid] < invalid) lo = mid + 1; else hi = mid;
+    }
+    *n_valid = (unsigned long long)lo;
 }
 
 // ---- K3: leaves = runs of equal codes --------------------------------------------------------
@@ -503,14 +517,18 @@ void launch_first_violation(const uint8_t* cloud, int64_t n, int64_t start, cons
     if (start >= n) return;
     int64_t tiles = (n - start + 4095) / 4096;
     first_violation_kernel<<<(unsigned)tiles, 256, 0, s>>>(cloud, n, start, lat, defined, best);
+    fetch_violator_kernel<<<1, 1, 0, s>>>(cloud, best);
+    g_launches += 2;
+}
+
+void launch_point_keys(const uint8_t* cloud, int64_t n, const LatticeDev& lat, uint64_t* keys, uint32_t* vals, cudaStream_t s) {
+    if (n <= 0) return;
+    point_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cloud, n, lat, keys, vals);
     g_launches++;
 }
 
-void launch_point_keys(const uint8_t* cloud, int64_t n, const LatticeDev& lat, uint64_t* keys, uint32_t* vals,
-                       unsigned long long* n_valid, cudaStream_t s) {
-    cudaMemsetAsync(n_valid, 0, sizeof(unsigned long long), s);
-    if (n <= 0) return;
-    point_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cloud, n, lat, keys, vals, n_valid);
+void launch_count_valid(const uint64_t* sorted_keys, int64_t n, uint32_t depth, unsigned long long* n_valid, cudaStream_t s) {
+    count_valid_kernel<<<1, 1, 0, s>>>(sorted_keys, n, 1ull << (3 * depth), n_valid);
     g_launches++;
 }
 
