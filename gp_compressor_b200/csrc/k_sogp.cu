@@ -13,9 +13,10 @@
 // registers; lanes 0-15 compute rows of C k, lanes 16-31 rows of Q k; the three dot products
 // are one product per lane and one shared butterfly; rank-1 updates split columns between
 // the two half-warps.  No block barrier, only __syncwarp.
-// Buckets 1-3 (LD 32 / 64 / 118): NT = 2*RB threads.  Thread t computes matvec row t % RB of
-// matrix t / RB; for rank-1 / rank-2 updates it owns row t % RB and every second column; the
-// dot products are computed redundantly by every warp (no broadcast barrier).
+// Buckets 2-4 (LD 64 / 118 / 202): NT = 4*RB threads.  A warp covers 16 rows of one matrix for the matvec
+// (its two half-warps split the canonical partial sums and combine them with one shuffle); for rank-1 /
+// rank-2 updates a thread owns one row and every fourth column; the dot products are computed redundantly
+// by every warp (no broadcast barrier).
 //
 // Every patch starts in bucket 0.  When a full update would not fit the bucket, the CTA
 // writes its complete state (N, next point, counters, alpha, BV, C, Q) to a hand-off slot and
@@ -801,7 +802,9 @@ __device__ __forceinline__ int warp_argmin(const Smem<LD>& s, int N, int lane, d
 template <int LD, int RB, int NT>
 __device__ __forceinline__ void delete_bv(const Smem<LD>& s, int& N, int loc, int t) {
     const int L = N - 1, M = N - 1;
-    const int irow = t & (RB - 1), jg = t / RB;
+    const int lane_ = t & 31, w_ = t >> 5;
+    const int irow = 16 * (w_ % (RB / 16)) + (lane_ & 15);
+    const int jq = 2 * (w_ / (RB / 16)) + (lane_ >> 4);
     double* const C = s.C();
     double* const Q = s.Q();
     double csi = 0, qsi = 0, repc = 0, repq = 0, ai = 0, nb1 = 0, nb2 = 0;
@@ -839,7 +842,7 @@ __device__ __forceinline__ void delete_bv(const Smem<LD>& s, int& N, int loc, in
     cta_sync<NT>();
     if (irow < M) {
         const double qi = s.qsv()[irow], ci = s.qcv()[irow];
-        for (int j = jg; j < M; j += 2) {
+        for (int j = jq; j < M; j += 4) {
             const int idx = j * LD + irow;
             const double u = __dmul_rn(qi, s.qsv()[j]);
             const double v = __dmul_rn(ci, s.qcv()[j]);
@@ -861,8 +864,14 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
     const Smem<LD> s{smem_d};
     double* const C = s.C();
     double* const Q = s.Q();
-    const int t = threadIdx.x, lane = t & 31;
-    const int irow = t & (RB - 1), jg = t / RB;
+    // NT = 4*RB threads.  A warp covers 16 rows: lanes 0-15 and 16-31 hold the same rows and split the columns.
+    // Matvec: warps [0, RB/16) take C, the rest Q; a half-warp accumulates the canonical partials a_{2h}, a_{2h+1}.
+    // Updates: row irow, columns j = jq (mod 4) with jq = 2*mat + half.
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int half = lane >> 4;
+    const int irow = 16 * (w % (RB / 16)) + (lane & 15);
+    const int mat = w / (RB / 16);
+    const int jq = 2 * mat + half;
     const int64_t patch = a.patch_ids ? (int64_t)a.patch_ids[blockIdx.x] : a.first_patch + blockIdx.x;
     const int64_t o = a.off[patch];
     const int n = (int)(a.off[patch + 1] - o);
@@ -925,9 +934,18 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
         if (t < N) s.kv()[t] = rbf(x1, x2, s.b1()[t], s.b2()[t], p0, cl);
         cta_sync<NT>();
         // C k and e_hat = Q k (:122,:140), m = alpha' k (:121)
-        if (irow < N) {
-            const double rv = row4((jg ? Q : C) + irow, LD, s.kv(), N);
-            (jg ? s.ev() : s.ck())[irow] = rv;
+        {
+            const double* const Mx = (mat ? Q : C) + irow;
+            double a0 = 0.0, a1 = 0.0;
+            if (irow < N) {
+                for (int j = 2 * half; j < N; j += 4) {
+                    a0 = fma(Mx[j * LD], s.kv()[j], a0);
+                    if (j + 1 < N) a1 = fma(Mx[(j + 1) * LD], s.kv()[j + 1], a1);
+                }
+            }
+            const double pr = __dadd_rn(a0, a1);                       // (a0+a1) in half 0, (a2+a3) in half 1
+            const double rv = __dadd_rn(pr, shfl_xor_d(pr, 16));       // canonical (a0+a1)+(a2+a3)
+            if (irow < N && half == 0) (mat ? s.ev() : s.ck())[irow] = rv;
         }
         const double m = warp_dot32(s.alpha(), s.kv(), N, lane);
         cta_sync<NT>();
@@ -961,7 +979,7 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
             const double re = __dmul_rn(rr, eta);
             if (irow < N) {
                 const double si = s.sv()[irow];
-                for (int j = jg; j < N; j += 2) {
+                for (int j = jq; j < N; j += 4) {
                     const int idx = j * LD + irow;
                     C[idx] = fma(re, __dmul_rn(si, s.sv()[j]), C[idx]);
                 }
@@ -1008,7 +1026,7 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
             const int N1 = N + 1;
             if (irow < N1) {
                 const double si = s.sv()[irow], ei = s.ev()[irow];
-                for (int j = jg; j < N1; j += 2) {
+                for (int j = jq; j < N1; j += 4) {
                     const int idx = j * LD + irow;
                     C[idx] = fma(rr, __dmul_rn(si, s.sv()[j]), C[idx]);
                     Q[idx] = fma(ig, __dmul_rn(ei, s.ev()[j]), Q[idx]);
@@ -1101,9 +1119,9 @@ cudaError_t launch_sogp_fit(int bucket, const SogpArgs& a, cudaStream_t st) {
         case 1:
             sogp_fit_pair_kernel<<<a.n_work, 64, 0, st>>>(a);
             return cudaGetLastError();
-        case 2: return launch_cta_bucket<64, 64, 128, 32, false>(a, st);
-        case 3: return launch_cta_bucket<118, 128, 256, 64, false>(a, st);
-        default: return launch_cta_bucket<202, 256, 512, 118, true>(a, st);
+        case 2: return launch_cta_bucket<64, 64, 256, 32, false>(a, st);
+        case 3: return launch_cta_bucket<118, 128, 512, 64, false>(a, st);
+        default: return launch_cta_bucket<202, 256, 1024, 118, true>(a, st);
     }
 }
 

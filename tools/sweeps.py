@@ -13,14 +13,14 @@ def fp64_flops(st):
 def smem_bytes(st):
     return 16.0 * st["sum_n2_common"] + 16.0 * st["sum_n2_sparse"] + 32.0 * st["sum_n2_full"] + 32.0 * st["sum_n2_del"]
 
-def c3(points, side):
+def c3(points, side, caps=(10, 20, 30, 50, 75, 100, 117, 150, 200)):
     cloud = synth.c3_dense_floor(points, seed=3, side=side)
     print(f"\n### C3 capacity sweep: {points} pts on {side}x{side} m (~{points / (side / 0.1) ** 2:.0f} pts/patch), res 0.1f, hyper BIND, 1 x B200\n")
     print("| capacity | bucket regime | fit ms | compress pts/s | mean BV | full / sparse / cap-del | GFLOP/s (alg.) | SMEM GB/s (alg.) | frac of LDS.128 peak |")
     print("|---|---|---|---|---|---|---|---|---|")
     h0 = G.Handle()
     smem_peak = h0.debug_peak(1)
-    for cap in (10, 20, 30, 50, 75, 100, 117, 150, 200):
+    for cap in caps:
         h = G.Handle(res=F32(0.1), sz=10, capacity=cap, **synth.hyper_bind(F32(0.1)))
         h.upload_cloud(cloud)
         best = None
@@ -50,6 +50,9 @@ def c4(n_patches, nbv, sz=64):
     h.close()
 
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "c3":
+        c3(1_000_000, 3.2, caps=tuple(int(v) for v in sys.argv[2:]))
+        sys.exit(0)
     c3(1_000_000, 3.2)
     print("\n### C4 decode only (per-GPU share of the 1M-patch configuration), REF kernel, 1 x B200\n")
     print("| patches | BVs/patch | grid | output pts | predict ms | grid pts/s | TFLOP/s (37N+18 per pt) | frac of FP64 peak | output GB/s |")
