@@ -742,14 +742,10 @@ __global__ void __launch_bounds__(64, 10) sogp_fit_pair_kernel(SogpArgs a) {
 // =====================================================================================
 // Buckets 1-3: NT = 2*RB threads per patch, LD constexpr
 // =====================================================================================
-template <int NT>
-__device__ __forceinline__ void cta_sync() {
-    __syncthreads();
-}
-
 template <int LD>
 struct Smem {
     double* base;
+    static constexpr int kDoubles = 2 * LD * LD + 9 * LD + 8;
     __device__ __forceinline__ double* C() const { return base; }
     __device__ __forceinline__ double* Q() const { return base + LD * LD; }
     __device__ __forceinline__ double* alpha() const { return base + 2 * LD * LD; }
@@ -761,44 +757,52 @@ struct Smem {
     __device__ __forceinline__ double* sv() const { return base + 2 * LD * LD + 6 * LD; }
     __device__ __forceinline__ double* qsv() const { return base + 2 * LD * LD + 7 * LD; }
     __device__ __forceinline__ double* qcv() const { return base + 2 * LD * LD + 8 * LD; }
-    __device__ __forceinline__ int* bidx() const { return reinterpret_cast<int*>(base + 2 * LD * LD + 9 * LD); }
+    __device__ __forceinline__ double* scv() const { return kv(); }                          // deletion scores (k is dead by then)
+    __device__ __forceinline__ double* scal() const { return base + 2 * LD * LD + 9 * LD; }  // CTA-wide scalars
+    __device__ __forceinline__ int* bidx() const { return reinterpret_cast<int*>(base + kDoubles); }
 };
 
+// One score per BV, computed ONCE by thread i (a division each), then every warp reduces the scores from
+// shared memory with the "first strict minimum" rule.  MODE 0: alpha_i^2 / (Q_ii + C_ii) (sparse_gp.hpp:213);
+// MODE 1: 1 / Q_ii with the exact shortcut "delete iff score_0 is not NaN and some score < 1e-9f" (:229-236).
+// Contains block barriers: must be reached by all threads.  Returns loc, or -1 when MODE 1 finds nothing to delete.
 template <int LD, int MODE>
-__device__ __forceinline__ int warp_argmin(const Smem<LD>& s, int N, int lane, double* minscore) {
-    double best = 0.0;
-    int bi = 0x7fffffff;
-    bool hit = false, nan0 = false;
-    for (int i = lane; i < N; i += 32) {
-        const double qii = s.Q()[i * LD + i];
-        double sc;
+__device__ __forceinline__ int block_argmin(const Smem<LD>& s, int N, int t, int lane) {
+    double sc = 0.0;
+    if (t < N) {
+        const double qii = s.Q()[t * LD + t];
         if (MODE == 0) {
-            const double al = s.alpha()[i];
-            sc = __ddiv_rn(__dmul_rn(al, al), __dadd_rn(qii, s.C()[i * LD + i]));
+            const double al = s.alpha()[t];
+            sc = __ddiv_rn(__dmul_rn(al, al), __dadd_rn(qii, s.C()[t * LD + t]));
         } else {
             sc = __ddiv_rn(1.0, qii);
-            hit = hit || (sc < geo9());
         }
-        if (sc != sc) {
+        s.scv()[t] = sc;
+    }
+    if (MODE == 1) {
+        if (!__syncthreads_or(t < N && sc < geo9())) return -1;
+        if (s.scv()[0] != s.scv()[0]) return -1;  // score_0 is NaN: nothing is ever "< minscore"
+    } else {
+        __syncthreads();
+    }
+    double best = 0.0;
+    int bi = 0x7fffffff;
+    bool nan0 = false;
+    for (int i = lane; i < N; i += 32) {
+        const double v = s.scv()[i];
+        if (v != v) {
             if (i == 0) nan0 = true;
             continue;
         }
-        if (bi == 0x7fffffff || sc < best) { best = sc; bi = i; }
+        if (bi == 0x7fffffff || v < best) { best = v; bi = i; }
     }
-    if (MODE == 1) {  // exact shortcut of the geometric scan: nothing to delete unless some score < 1e-9f
-        if (!__any_sync(0xffffffffu, hit) || __any_sync(0xffffffffu, nan0)) {
-            *minscore = geo9();
-            return 0;
-        }
-    }
-    // lanes hold their own first strict minimum; NaN element 0 is re-detected by the helper through idx 0
-    double sc0 = best;
-    int idx0 = bi;
-    if (nan0) { sc0 = __longlong_as_double(0x7ff8000000000000LL); idx0 = 0; }
-    return warp_first_min(sc0, idx0, minscore);
+    if (nan0) { best = __longlong_as_double(0x7ff8000000000000LL); bi = 0; }
+    double ms;
+    return warp_first_min(best, bi, &ms);
 }
 
 // sparse_gp::delete_bv, sparse_gp.hpp:252-295.  Uniform across the CTA; ends with a barrier.
+// The three divisions are done by warp 0 only and published through scal[4..6].
 template <int LD, int RB, int NT>
 __device__ __forceinline__ void delete_bv(const Smem<LD>& s, int& N, int loc, int t) {
     const int L = N - 1, M = N - 1;
@@ -818,11 +822,17 @@ __device__ __forceinline__ void delete_bv(const Smem<LD>& s, int& N, int loc, in
         ai = s.alpha()[src];
         if (t == loc) { nb1 = s.b1()[L]; nb2 = s.b2()[L]; nidx = s.bidx()[L]; }
     }
-    const double cstar = C[loc * LD + loc], qstar = Q[loc * LD + loc], astar = s.alpha()[loc];
-    cta_sync<NT>();
-    const double qcs = __dadd_rn(qstar, cstar);
-    const double coef = __ddiv_rn(astar, qcs);
-    const double iq = __ddiv_rn(1.0, qstar), iqc = __ddiv_rn(1.0, qcs);
+    double coef0 = 0.0, iq0 = 0.0, iqc0 = 0.0;
+    if (w_ == 0) {
+        const double cstar = C[loc * LD + loc], qstar = Q[loc * LD + loc], astar = s.alpha()[loc];
+        const double qcs = __dadd_rn(qstar, cstar);
+        coef0 = __ddiv_rn(astar, qcs);
+        iq0 = __ddiv_rn(1.0, qstar);
+        iqc0 = __ddiv_rn(1.0, qcs);
+    }
+    __syncthreads();  // every read of the old state is done
+    if (t == 0) { s.scal()[4] = coef0; s.scal()[5] = iq0; s.scal()[6] = iqc0; }
+    double qci = 0.0;
     if (t < N) {
         if (t < M) {
             if (loc != L) {
@@ -830,8 +840,7 @@ __device__ __forceinline__ void delete_bv(const Smem<LD>& s, int& N, int loc, in
                 Q[loc * LD + t] = repq; Q[t * LD + loc] = repq;
                 if (t == loc) { s.b1()[loc] = nb1; s.b2()[loc] = nb2; s.bidx()[loc] = nidx; }
             }
-            const double qci = __dadd_rn(qsi, csi);
-            s.alpha()[t] = __dadd_rn(ai, -__dmul_rn(coef, qci));
+            qci = __dadd_rn(qsi, csi);
             s.qsv()[t] = qsi;
             s.qcv()[t] = qci;
         }
@@ -839,7 +848,9 @@ __device__ __forceinline__ void delete_bv(const Smem<LD>& s, int& N, int loc, in
         Q[L * LD + t] = 0.0; Q[t * LD + L] = 0.0;
         if (t == L) { s.alpha()[L] = 0.0; s.b1()[L] = 0.0; s.b2()[L] = 0.0; s.bidx()[L] = -1; }
     }
-    cta_sync<NT>();
+    __syncthreads();
+    const double coef = s.scal()[4], iq = s.scal()[5], iqc = s.scal()[6];
+    if (t < M) s.alpha()[t] = __dadd_rn(ai, -__dmul_rn(coef, qci));
     if (irow < M) {
         const double qi = s.qsv()[irow], ci = s.qcv()[irow];
         for (int j = jq; j < M; j += 4) {
@@ -852,7 +863,7 @@ __device__ __forceinline__ void delete_bv(const Smem<LD>& s, int& N, int loc, in
         }
     }
     N = M;
-    cta_sync<NT>();
+    __syncthreads();
 }
 
 template <int LD, int RB, int NT, int LD_IN, bool SPILL>
@@ -860,7 +871,7 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
     extern __shared__ double smem_dyn[];
     // SPILL: the state lives in a per-CTA slice of global memory (L2-resident) instead of shared memory;
     // block barriers order the accesses exactly as they do for shared memory.
-    double* const smem_d = SPILL ? a.spill + (size_t)blockIdx.x * (2 * LD * LD + 10 * LD) : smem_dyn;
+    double* const smem_d = SPILL ? a.spill + (size_t)blockIdx.x * (Smem<LD>::kDoubles + LD) : smem_dyn;
     const Smem<LD> s{smem_d};
     double* const C = s.C();
     double* const Q = s.Q();
@@ -880,9 +891,9 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
         if (t == 0) { a.nbv[op] = 0; a.flags[op] = 0; }
         return;
     }
-    for (int i = t; i < 2 * LD * LD + 9 * LD; i += NT) smem_d[i] = 0.0;
+    for (int i = t; i < Smem<LD>::kDoubles; i += NT) smem_d[i] = 0.0;
     for (int i = t; i < LD; i += NT) s.bidx()[i] = -1;
-    cta_sync<NT>();
+    __syncthreads();
 
     const double kstar = a.p0, s20 = a.s20, p0 = a.p0, cl = a.cl, eps_tol = a.eps_tol;
     const int cap = a.capacity, ldmax = a.ld;
@@ -905,7 +916,7 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
             C[j * LD + i] = v[3 * LD_IN + e];
             Q[j * LD + i] = v[3 * LD_IN + LD_IN * LD_IN + e];
         }
-        cta_sync<NT>();
+        __syncthreads();
     }
 
     double nx1 = a.fx1[o + tt0], nx2 = a.fx2[o + tt0], ny = a.fy[o + tt0];
@@ -927,13 +938,13 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
             }
             N = 1;
             cnt.c[0]++;
-            cta_sync<NT>();
+            __syncthreads();
             continue;
         }
         // k = K(x, BV)  (sparse_gp.hpp:119)
         if (t < N) s.kv()[t] = rbf(x1, x2, s.b1()[t], s.b2()[t], p0, cl);
-        cta_sync<NT>();
-        // C k and e_hat = Q k (:122,:140), m = alpha' k (:121)
+        __syncthreads();
+        // C k and e_hat = Q k (:122,:140); warp 0 also computes m = alpha' k (:121)
         {
             const double* const Mx = (mat ? Q : C) + irow;
             double a0 = 0.0, a1 = 0.0;
@@ -947,8 +958,10 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
             const double rv = __dadd_rn(pr, shfl_xor_d(pr, 16));       // canonical (a0+a1)+(a2+a3)
             if (irow < N && half == 0) (mat ? s.ev() : s.ck())[irow] = rv;
         }
-        const double m = warp_dot32(s.alpha(), s.kv(), N, lane);
-        cta_sync<NT>();
+        double m = 0.0;
+        if (w == 0) m = warp_dot32(s.alpha(), s.kv(), N, lane);
+        __syncthreads();
+        // every warp: k'Ck and k'e_hat (cheap, no division) -> gamma and the sparse / full decision
         double kck = 0.0, ke = 0.0;
         for (int j = lane; j < N; j += 32) {
             const double kj = s.kv()[j];
@@ -960,23 +973,37 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
             kck = __dadd_rn(kck, shfl_xor_d(kck, off));
             ke = __dadd_rn(ke, shfl_xor_d(ke, off));
         }
-        const double s2 = __dadd_rn(kstar, kck);
-        const double den = __dadd_rn(s20, s2);
-        const double rr = __ddiv_rn(-1.0, den);               // gaussian_noise.cpp:15-18
-        const double q = __ddiv_rn(__dadd_rn(y, -m), den);    // gaussian_noise.cpp:9-12
         double gamma = __dadd_rn(kstar, -ke);                 // sparse_gp.hpp:144
         if (gamma < tiny12()) gamma = 0.0;
-        if (gamma < eps_tol) {
+        const bool sparse = gamma < eps_tol;
+        // warp 0 alone does the divisions and publishes them: scal[0] = r, [1] = q, [2] = q*eta | -, [3] = r*eta | 1/gamma
+        if (w == 0) {
+            const double s2 = __dadd_rn(kstar, kck);
+            const double den = __dadd_rn(s20, s2);
+            const double rr = __ddiv_rn(-1.0, den);               // gaussian_noise.cpp:15-18
+            const double q = __ddiv_rn(__dadd_rn(y, -m), den);    // gaussian_noise.cpp:9-12
+            double c2, c3;
+            if (sparse) {
+                const double eta = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn(gamma, rr)));
+                c2 = __dmul_rn(q, eta);
+                c3 = __dmul_rn(rr, eta);
+            } else {
+                c2 = 0.0;
+                c3 = __ddiv_rn(1.0, gamma);
+            }
+            if (lane == 0) { s.scal()[0] = rr; s.scal()[1] = q; s.scal()[2] = c2; s.scal()[3] = c3; }
+        }
+        if (sparse) {
             // sparse update (sparse_gp.hpp:155-163)
             cnt.run++;
-            const double eta = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn(gamma, rr)));
+            double sh = 0.0;
             if (t < N) {
-                const double sh = __dadd_rn(s.ck()[t], s.ev()[t]);
+                sh = __dadd_rn(s.ck()[t], s.ev()[t]);
                 s.sv()[t] = sh;
-                s.alpha()[t] = __dadd_rn(s.alpha()[t], __dmul_rn(sh, __dmul_rn(q, eta)));
             }
-            cta_sync<NT>();
-            const double re = __dmul_rn(rr, eta);
+            __syncthreads();
+            const double qe = s.scal()[2], re = s.scal()[3];
+            if (t < N) s.alpha()[t] = __dadd_rn(s.alpha()[t], __dmul_rn(sh, qe));
             if (irow < N) {
                 const double si = s.sv()[irow];
                 for (int j = jq; j < N; j += 4) {
@@ -991,7 +1018,7 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
         if (N + 1 > ldmax) {  // does not fit this bucket: hand the state to the next one
             __shared__ int spos;
             if (t == 0) spos = atomicAdd(a.queue_count, 1);
-            cta_sync<NT>();
+            __syncthreads();
             const int pos = spos;
             double* slot = a.handoff_out + (size_t)pos * slot_doubles(LD);
             if (t == 0) {
@@ -1009,20 +1036,21 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
             return;
         }
         cnt.full(N);
+        double sct = 0.0;
         if (t < N) {
-            const double sc = s.ck()[t];
-            s.sv()[t] = sc;
-            s.alpha()[t] = __dadd_rn(s.alpha()[t], __dmul_rn(q, sc));
+            sct = s.ck()[t];
+            s.sv()[t] = sct;
         }
         if (t == N) {
             s.sv()[N] = 1.0;
-            s.alpha()[N] = __dadd_rn(0.0, __dmul_rn(q, 1.0));
             s.ev()[N] = -1.0;
             s.b1()[N] = x1; s.b2()[N] = x2; s.bidx()[N] = orig;
         }
-        cta_sync<NT>();
+        __syncthreads();
         {
-            const double ig = __ddiv_rn(1.0, gamma);
+            const double rr = s.scal()[0], q = s.scal()[1], ig = s.scal()[3];
+            if (t < N) s.alpha()[t] = __dadd_rn(s.alpha()[t], __dmul_rn(q, sct));
+            if (t == N) s.alpha()[N] = __dadd_rn(0.0, __dmul_rn(q, 1.0));
             const int N1 = N + 1;
             if (irow < N1) {
                 const double si = s.sv()[irow], ei = s.ev()[irow];
@@ -1034,36 +1062,31 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
             }
             N = N1;
         }
-        cta_sync<NT>();
+        __syncthreads();
         // capacity deletions (sparse_gp.hpp:206-223)
         while (N > cap) {
-            double ms;
-            const int loc = warp_argmin<LD, 0>(s, N, lane, &ms);
+            const int loc = block_argmin<LD, 0>(s, N, t, lane);
             cnt.c[9] += (unsigned long long)(N - 1) * (N - 1);
             delete_bv<LD, RB, NT>(s, N, loc, t);
             cnt.c[3]++;
         }
         // geometric deletions (sparse_gp.hpp:226-242)
-        {
-            double minscore = 0.0;
-            while (minscore < geo9() && N > 1) {
-                const int loc = warp_argmin<LD, 1>(s, N, lane, &minscore);
-                if (minscore < geo9()) {
-                    cnt.c[9] += (unsigned long long)(N - 1) * (N - 1);
-                    delete_bv<LD, RB, NT>(s, N, loc, t);
-                    cnt.c[4]++;
-                }
-            }
+        while (N > 1) {
+            const int loc = block_argmin<LD, 1>(s, N, t, lane);
+            if (loc < 0) break;
+            cnt.c[9] += (unsigned long long)(N - 1) * (N - 1);
+            delete_bv<LD, RB, NT>(s, N, loc, t);
+            cnt.c[4]++;
         }
     }
     cnt.flush(N);
-    cta_sync<NT>();
+    __syncthreads();
     // results
     if (t == 0) {
         a.nbv[op] = N;
         const double c00 = C[0];
         a.flags[op] = (c00 != c00) ? 1 : 0;
-        publish(a, cnt, n - 0);
+        publish(a, cnt, n);
     }
     const int64_t ob = op * cap;
     for (int i = t; i < N; i += NT) {
@@ -1083,7 +1106,7 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
 }
 
 template <int LD>
-constexpr size_t cta_smem_bytes() { return (size_t)(2 * LD * LD + 9 * LD) * sizeof(double) + (size_t)LD * sizeof(int); }
+constexpr size_t cta_smem_bytes() { return (size_t)Smem<LD>::kDoubles * sizeof(double) + (size_t)LD * sizeof(int); }
 
 template <int LD, int RB, int NT, int LD_IN, bool SPILL>
 cudaError_t launch_cta_bucket(const SogpArgs& a, cudaStream_t st) {
@@ -1105,7 +1128,7 @@ int sogp_bucket_ld(int bucket) {
     return lds[bucket];
 }
 
-size_t sogp_spill_bytes_per_patch() { return (size_t)(2 * 202 * 202 + 10 * 202) * sizeof(double); }
+size_t sogp_spill_bytes_per_patch() { return (size_t)(2 * 202 * 202 + 11 * 202 + 8) * sizeof(double); }
 
 size_t sogp_handoff_slot_bytes(int bucket) { return (size_t)slot_doubles(sogp_bucket_ld(bucket)) * sizeof(double); }
 

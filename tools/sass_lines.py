@@ -3,6 +3,7 @@ instructions per CUDA source line.  usage: sass_lines.py <report.ncu-rep> <kerne
 import collections, csv, io, re, subprocess, sys
 rep, kname, sass = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+ncu_name = sys.argv[5] if len(sys.argv) > 5 else kname
 # line info per instruction index within the function
 lines = open(sass).read().split("\n")
 start = None
@@ -17,7 +18,7 @@ for l in lines[start + 1:]:
         f = m.group(1).split("/")[-1]; cur = (f, int(m.group(2)), (m.group(3) or "").split("/")[-1], int(m.group(4) or 0)); continue
     if re.match(r"\s+/\*[0-9a-f]{4}\*/", l): per_instr.append((cur, l.strip()))
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-blk = [b for b in txt.split('"Kernel Name",')[1:] if kname in b.split("\n")[0]][0]
+blk = [b for b in txt.split('"Kernel Name",')[1:] if ncu_name in b.split("\n")[0]][0]
 rows = list(csv.reader(io.StringIO('"Kernel Name",' + blk))); h = rows[1]
 ie = h.index("Instructions Executed"); isamp = h.index("# Samples")
 cnt = [(int(r[ie]), int(r[isamp])) for r in rows[2:] if len(r) > ie and r[ie].isdigit()]
