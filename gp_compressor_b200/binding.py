@@ -223,6 +223,11 @@ class Handle:
         r["patch_lo"], r["patch_hi"] = s.patch_lo, s.patch_hi
         return r
 
+    def params_into(self, nbv_ptr, bv_off_ptr, idx_ptr, bv1_ptr, bv2_ptr, alpha_ptr, flags_ptr):
+        """gpc_get_params into caller-owned (e.g. pinned) buffers given as raw addresses."""
+        vp = lambda p: C.c_void_p(p) if p else None
+        self._ck(load().gpc_get_params(self.h, vp(nbv_ptr), vp(bv_off_ptr), vp(idx_ptr), vp(bv1_ptr), vp(bv2_ptr), vp(alpha_ptr), vp(flags_ptr)))
+
     def state(self, patch, n):
         Cm = np.zeros((n, n))
         Qm = np.zeros((n, n))

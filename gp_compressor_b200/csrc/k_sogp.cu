@@ -139,7 +139,7 @@ __device__ __forceinline__ double row4_contig(const double* row, const double* k
     return __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
 }
 
-__global__ void __launch_bounds__(32, 28) sogp_fit_warp_kernel(SogpArgs a) {
+__global__ void __launch_bounds__(32, 32) sogp_fit_warp_kernel(SogpArgs a) {
     __shared__ __align__(16) WarpSmem sm;
     double* const C = sm.C;
     double* const Q = sm.Q;
