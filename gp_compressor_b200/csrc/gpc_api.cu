@@ -124,8 +124,10 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
     // rand stream bookkeeping (all patches: the stream is global across patches)
     const int mult = c.shuffle ? (c.rgb_rand ? 2 : 1) : 0;
     uint64_t draws_lo = 0, draws_hi = 0, draws_all = 0;
+    int64_t max_np = 0;
     for (int64_t p = 0; p < P; p++) {
         int64_t n = hoff[p + 1] - hoff[p];
+        if (n > max_np) max_np = n;
         uint64_t d = n > 0 ? (uint64_t)(n - 1) * mult : 0;
         if (p == lo) draws_lo = draws_all;
         draws_all += d;
@@ -149,7 +151,7 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
             launch_rand_stream(h->rand_offset + draws_lo, nd, h->rnd.as<uint32_t>(), st);
         }
         launch_shuffle(h->off.as<int64_t>() + lo, PL, h->roff.as<int64_t>() + lo, h->rnd.as<uint32_t>(), c.shuffle,
-                       h->perm.as<int32_t>(), h->patch_of.as<int32_t>(), h->s_begin, h->s_count, st);
+                       h->perm.as<int32_t>(), h->patch_of.as<int32_t>(), h->s_begin, h->s_count, max_np, st);
         launch_gather_stream(h->off.as<int64_t>() + lo, h->patch_of.as<int32_t>(), h->perm.as<int32_t>(),
                              h->x1.as<double>(), h->x2.as<double>(), h->y.as<double>(), h->s_begin, h->s_count,
                              h->fx1.as<double>(), h->fx2.as<double>(), h->fy.as<double>(), st);

@@ -70,9 +70,11 @@ void launch_patch_frames(const int64_t* patch_off, int64_t P, int leaf_order, co
                          cudaStream_t s);
 
 // ---- K6: glibc rand stream + shuffle -------------------------------------------------
-struct RandTables {       // x^(2^k) mod (x^31 - x^28 - 1) over Z/2^32, k = 0..47, and r_0..r_60
-    uint32_t pow2[48][31];
-    uint32_t base[61];
+struct RandTables {       // polynomials are mod (x^31 - x^28 - 1) over Z/2^32
+    uint32_t pow2[48][31];    // x^(2^k)
+    uint32_t base[91];        // s[0..90]
+    uint32_t red[30][31];     // x^(31+k)
+    uint32_t lanepow[32][31]; // x^(512 l)
 };
 void rand_tables_init(RandTables* t);                       // host, once per process
 cudaError_t rand_upload_tables(const RandTables* t);        // to __constant__
@@ -90,7 +92,7 @@ void launch_patch_draws(const int64_t* off, int64_t n_patches, int mult, int64_t
 // perm (patch-local) for every patch; rnd holds the stream starting at the handle's offset
 void launch_shuffle(const int64_t* off, int64_t n_patches, const int64_t* roff, const uint32_t* rnd,
                     int do_shuffle, int32_t* perm, int32_t* patch_of, int64_t s_begin, int64_t s_count,
-                    cudaStream_t s);
+                    int64_t max_patch_points, cudaStream_t s);
 void launch_gather_stream(const int64_t* off, const int32_t* patch_of, const int32_t* perm, const double* x1,
                           const double* x2, const double* y, int64_t s_begin, int64_t s_count, double* fx1,
                           double* fx2, double* fy, cudaStream_t s);

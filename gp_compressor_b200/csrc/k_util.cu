@@ -133,14 +133,47 @@ __global__ void patch_of_kernel(const int64_t* __restrict__ off, int64_t n_patch
 }
 
 // sparse_gp::shuffle, sparse_gp.hpp:42-56: for i = n-1..1: r = rand() % i; swap(ind[i], ind[r]).
-// One thread per patch (the swap chain is sequential); rnd[roff[p] - roff0 + t] is draw t.
+// rnd[roff[p] - roff[0] + t] is draw t of patch p.  Two kernels share the work by patch size:
+//  * n <= SHUF_SMEM_MAX: one warp per patch, index array and r_i = draw_i % i in shared memory; every lane
+//    computes its share of the modulos, lane 0 walks the (inherently serial) swap chain at shared-memory latency;
+//  * larger patches: one thread per patch, swaps in global memory.
+constexpr int SHUF_SMEM_MAX = 1024;
+
+__global__ void __launch_bounds__(32) shuffle_warp_kernel(const int64_t* __restrict__ off, int64_t n_patches,
+                                                          const int64_t* __restrict__ roff, const uint32_t* __restrict__ rnd,
+                                                          int32_t* __restrict__ perm) {
+    __shared__ int ind[SHUF_SMEM_MAX];
+    __shared__ int rr[SHUF_SMEM_MAX];
+    const int64_t p = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int64_t o = off[p];
+    const int n = (int)(off[p + 1] - o);
+    if (n < 2 || n > SHUF_SMEM_MAX) return;
+    const uint32_t* r = rnd + (roff[p] - roff[0]);
+    for (int i = lane; i < n; i += 32) {
+        ind[i] = i;
+        if (i > 0) rr[i] = (int)(r[n - 1 - i] % (uint32_t)i);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        for (int i = n - 1; i > 0; --i) {
+            const int j = rr[i];
+            const int a = ind[i], b = ind[j];
+            ind[i] = b;
+            ind[j] = a;
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) perm[o + i] = ind[i];
+}
+
 __global__ void shuffle_kernel(const int64_t* __restrict__ off, int64_t n_patches, const int64_t* __restrict__ roff,
                                const uint32_t* __restrict__ rnd, int32_t* __restrict__ perm) {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_patches) return;
     const int64_t o = off[p];
     const int n = (int)(off[p + 1] - o);
-    if (n < 2) return;
+    if (n <= SHUF_SMEM_MAX) return;  // handled by shuffle_warp_kernel
     const uint32_t* r = rnd + (roff[p] - roff[0]);
     int32_t* ind = perm + o;
     for (int i = n - 1; i > 0; --i) {
@@ -152,13 +185,18 @@ __global__ void shuffle_kernel(const int64_t* __restrict__ off, int64_t n_patche
 }
 
 void launch_shuffle(const int64_t* off, int64_t n_patches, const int64_t* roff, const uint32_t* rnd, int do_shuffle,
-                    int32_t* perm, int32_t* patch_of, int64_t s_begin, int64_t s_count, cudaStream_t s) {
+                    int32_t* perm, int32_t* patch_of, int64_t s_begin, int64_t s_count, int64_t max_patch_points,
+                    cudaStream_t s) {
     if (s_count <= 0 || n_patches <= 0) return;
     patch_of_kernel<<<(unsigned)((s_count + 255) / 256), 256, 0, s>>>(off, n_patches, s_begin, s_count, patch_of, perm);
     g_launches++;
     if (do_shuffle) {
-        shuffle_kernel<<<(unsigned)((n_patches + 127) / 128), 128, 0, s>>>(off, n_patches, roff, rnd, perm);
+        shuffle_warp_kernel<<<(unsigned)n_patches, 32, 0, s>>>(off, n_patches, roff, rnd, perm);
         g_launches++;
+        if (max_patch_points > SHUF_SMEM_MAX) {
+            shuffle_kernel<<<(unsigned)((n_patches + 127) / 128), 128, 0, s>>>(off, n_patches, roff, rnd, perm);
+            g_launches++;
+        }
     }
 }
 
