@@ -20,7 +20,7 @@ SYMBOLS = [
     "gpc_config_default", "gpc_create", "gpc_destroy", "gpc_last_error", "gpc_version", "gpc_compress",
     "gpc_upload_cloud", "gpc_compress_resident", "gpc_fit_patches", "gpc_decompress", "gpc_decompress_resident",
     "gpc_get_heights", "gpc_predict", "gpc_get_sizes", "gpc_get_stats", "gpc_get_patches", "gpc_get_assignment",
-    "gpc_get_params", "gpc_get_state", "gpc_set_params", "gpc_set_rand_offset", "gpc_get_stream", "gpc_debug_exp", "gpc_debug_rand", "gpc_debug_peak", "gpc_shard_range",
+    "gpc_get_params", "gpc_get_state", "gpc_set_params", "gpc_set_rand_offset", "gpc_get_stream", "gpc_debug_exp", "gpc_debug_rand", "gpc_debug_peak", "gpc_shard_range", "gpc_save", "gpc_load", "gpc_get_config",
 ]
 
 
@@ -85,6 +85,9 @@ def load():
     L.gpc_debug_exp.argtypes = [vp, vp, vp, i64]
     L.gpc_debug_rand.argtypes = [vp, u64, i64, vp]
     L.gpc_debug_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    L.gpc_save.argtypes = [vp, C.c_char_p, C.POINTER(i64)]
+    L.gpc_load.argtypes = [vp, C.c_char_p]
+    L.gpc_get_config.argtypes = [vp, C.POINTER(GpcConfig)]
     L.gpc_shard_range.argtypes = [vp, i64, C.c_int32, C.c_int32, C.POINTER(i64), C.POINTER(i64)]
     _LIB = L
     return L
@@ -283,6 +286,16 @@ class Handle:
         out = np.zeros_like(x)
         self._ck(load().gpc_debug_exp(self.h, _p(x), _p(out), x.size))
         return out
+
+    def save(self, path):
+        n = C.c_int64(0)
+        self._ck(load().gpc_save(self.h, str(path).encode(), C.byref(n)))
+        return n.value
+
+    def load_file(self, path):
+        self._ck(load().gpc_load(self.h, str(path).encode()))
+        self._ck(load().gpc_get_config(self.h, C.byref(self.cfg)))  # the file carries the decoder's configuration
+        return self.sizes()
 
     def debug_peak(self, kind):
         v = C.c_double(0)

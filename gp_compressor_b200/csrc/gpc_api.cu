@@ -965,6 +965,99 @@ int gpc_debug_exp(gpc_handle* h, const double* x, double* out, int64_t n) {
     return GPC_OK;
 }
 
+int gpc_save(gpc_handle* h, const char* path, int64_t* bytes_written) {
+    if (!h || !path) return GPC_ERR_INVALID;
+    if (!h->have_fit) return fail(h, GPC_ERR_STATE, "gpc_save before compress / fit");
+    if (!h->have_frames) return fail(h, GPC_ERR_STATE, "gpc_save needs patch frames (a compress on this handle)");
+    CK(cudaSetDevice(h->cfg.device));
+    const int64_t PL = h->patch_hi - h->patch_lo;
+    int rc = gpc_get_params(h, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);  // packs the parameters if needed
+    if (rc) return rc;
+    const int64_t T = h->n_bv_total;
+    std::vector<int32_t> nbv(PL);
+    std::vector<double> quat(PL * 4), mean(PL * 3), rgbm(PL * 3), b1(T), b2(T), al(T);
+    if (PL > 0) {
+        CK(cudaMemcpy(nbv.data(), h->nbv.p, PL * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(quat.data(), h->quat.as<double>() + 4 * h->patch_lo, PL * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(mean.data(), h->mean.as<double>() + 3 * h->patch_lo, PL * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(rgbm.data(), h->rgbmean.as<double>() + 3 * h->patch_lo, PL * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    if (T > 0) {
+        CK(cudaMemcpy(b1.data(), h->pb1.p, T * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(b2.data(), h->pb2.p, T * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(al.data(), h->palpha.p, T * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return fail(h, GPC_ERR_INVALID, std::string("cannot open ") + path);
+    const char magic[8] = {'G', 'P', 'C', 'B', '2', '0', '0', 0};
+    const uint32_t version = 1;
+    const gpc_config& c = h->cfg;
+    const double dcfg[5] = {c.res, c.s0, c.eps_tol, c.sigmaf_sq, c.l_sq};
+    const int32_t icfg[2] = {c.sz, c.capacity};
+    size_t ok = 1;
+    ok &= std::fwrite(magic, 8, 1, f) == 1;
+    ok &= std::fwrite(&version, 4, 1, f) == 1;
+    ok &= std::fwrite(dcfg, sizeof(dcfg), 1, f) == 1;
+    ok &= std::fwrite(icfg, sizeof(icfg), 1, f) == 1;
+    ok &= std::fwrite(&PL, 8, 1, f) == 1;
+    ok &= std::fwrite(&T, 8, 1, f) == 1;
+    auto put = [&](const void* p, size_t n) { if (n) ok &= std::fwrite(p, n, 1, f) == 1; };
+    put(nbv.data(), PL * sizeof(int32_t));
+    put(quat.data(), PL * 4 * sizeof(double));
+    put(mean.data(), PL * 3 * sizeof(double));
+    put(rgbm.data(), PL * 3 * sizeof(double));
+    put(b1.data(), T * sizeof(double));
+    put(b2.data(), T * sizeof(double));
+    put(al.data(), T * sizeof(double));
+    const long pos = std::ftell(f);
+    std::fclose(f);
+    if (!ok) return fail(h, GPC_ERR_INVALID, std::string("short write to ") + path);
+    if (bytes_written) *bytes_written = (int64_t)pos;
+    return GPC_OK;
+}
+
+int gpc_get_config(const gpc_handle* h, gpc_config* cfg) {
+    if (!h || !cfg) return GPC_ERR_INVALID;
+    *cfg = h->cfg;
+    return GPC_OK;
+}
+
+int gpc_load(gpc_handle* h, const char* path) {
+    if (!h || !path) return GPC_ERR_INVALID;
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return fail(h, GPC_ERR_INVALID, std::string("cannot open ") + path);
+    char magic[8];
+    uint32_t version = 0;
+    double dcfg[5];
+    int32_t icfg[2];
+    int64_t PL = 0, T = 0;
+    bool ok = std::fread(magic, 8, 1, f) == 1 && std::memcmp(magic, "GPCB200", 8) == 0;
+    ok = ok && std::fread(&version, 4, 1, f) == 1 && version == 1;
+    ok = ok && std::fread(dcfg, sizeof(dcfg), 1, f) == 1 && std::fread(icfg, sizeof(icfg), 1, f) == 1;
+    ok = ok && std::fread(&PL, 8, 1, f) == 1 && std::fread(&T, 8, 1, f) == 1 && PL >= 0 && T >= 0;
+    if (!ok) { std::fclose(f); return fail(h, GPC_ERR_INVALID, "not a gpc_b200 parameter file (or unsupported version)"); }
+    std::vector<int32_t> nbv(PL);
+    std::vector<double> quat(PL * 4), mean(PL * 3), rgbm(PL * 3), b1(T), b2(T), al(T);
+    auto get = [&](void* p, size_t n) { if (n) ok = ok && std::fread(p, n, 1, f) == 1; };
+    get(nbv.data(), PL * sizeof(int32_t));
+    get(quat.data(), PL * 4 * sizeof(double));
+    get(mean.data(), PL * 3 * sizeof(double));
+    get(rgbm.data(), PL * 3 * sizeof(double));
+    get(b1.data(), T * sizeof(double));
+    get(b2.data(), T * sizeof(double));
+    get(al.data(), T * sizeof(double));
+    std::fclose(f);
+    if (!ok) return fail(h, GPC_ERR_INVALID, "truncated parameter file");
+    int64_t sum = 0;
+    for (int32_t v : nbv) sum += v;
+    if (sum != T) return fail(h, GPC_ERR_INVALID, "inconsistent parameter file");
+    // the decoder's configuration comes from the file (the shard layout and device stay the handle's own)
+    h->cfg.res = dcfg[0]; h->cfg.s0 = dcfg[1]; h->cfg.eps_tol = dcfg[2]; h->cfg.sigmaf_sq = dcfg[3]; h->cfg.l_sq = dcfg[4];
+    h->cfg.sz = icfg[0]; h->cfg.capacity = icfg[1];
+    const double one = 0.0;
+    return gpc_set_params(h, PL, nbv.data(), T ? b1.data() : &one, T ? b2.data() : &one, T ? al.data() : &one, quat.data(), mean.data(), rgbm.data());
+}
+
 int gpc_debug_peak(gpc_handle* h, int kind, double* value) {
     if (!h || !value || kind < 0 || kind > 2) return GPC_ERR_INVALID;
     CK(cudaSetDevice(h->cfg.device));

@@ -138,6 +138,18 @@ int gpc_set_rand_offset(gpc_handle* h, uint64_t offset);
 /* the cudaStream_t every kernel and copy of this handle is issued on (for CUDA-event timing by the caller) */
 int gpc_get_stream(gpc_handle* h, void** stream);
 
+/* ---- wire format (next-row N3): what gp_compressor::save_compressed(name) ignores ---------------
+ * The reference's GP path has no on-disk format (save_compressed drops its file name,
+ * gp_compressor.cpp:21-27); the K-SVD codec's .pccode layout (dictionary_representation.cpp:173-248) is the
+ * model: little-endian header, then per-patch records.  gpc_save writes this shard's fitted patches
+ * (N, quaternion, mean, RGB mean, BV, alpha); gpc_load installs them into a handle so that gpc_decompress
+ * can run in another process.  File layout: "GPCB200\0" | u32 version | config (res, sz, capacity, s0,
+ * eps_tol, sigmaf_sq, l_sq) | i64 n_patches | i64 n_bv_total | nbv[i32] | quat[4 f64] | mean[3 f64] |
+ * rgbmean[3 f64] | bv1, bv2, alpha [f64, packed]. */
+int gpc_save(gpc_handle* h, const char* path, int64_t* bytes_written);
+int gpc_get_config(const gpc_handle* h, gpc_config* cfg);  /* the handle's current configuration (gpc_load updates it) */
+int gpc_load(gpc_handle* h, const char* path);
+
 /* ---- test hooks: the device versions of the canonical primitives ----------------------- */
 int gpc_debug_exp(gpc_handle* h, const double* x, double* out, int64_t n);
 int gpc_debug_rand(gpc_handle* h, uint64_t offset, int64_t n, uint32_t* out);

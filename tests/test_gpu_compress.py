@@ -189,3 +189,25 @@ def test_reconstruction_rmse_is_small(G):
         cnt += hi - lo
     rmse = np.sqrt(se / cnt)
     assert rmse < 0.01
+
+
+def test_wire_format_round_trip(G, oracle_mod, tmp_path):
+    """Next-row N3: save the fitted patches, load them into a fresh handle (another process would do the same),
+    decode: the cloud must be identical, and the file must be much smaller than the input cloud."""
+    cloud = synth.c3_dense_floor(40000, seed=8, side=1.0)  # ~400 points per patch: the regime the codec is meant for
+    cfg = dict(res=F32(0.1), sz=12, capacity=40)
+    a = G.Handle(**cfg)
+    a.compress(cloud)
+    want = a.decompress()
+    path = tmp_path / "patches.gpc"
+    nbytes = a.save(path)
+    assert nbytes == path.stat().st_size and 0 < nbytes < cloud.nbytes
+    b = G.Handle()            # default config: everything the decoder needs comes from the file
+    b.load_file(path)
+    assert b.cfg.sz == 12 and b.cfg.capacity == 40
+    got = b.decompress()
+    assert eq(got, want)
+    with pytest.raises(G.GpcError):
+        bad = tmp_path / "bad.gpc"
+        bad.write_bytes(b"not a parameter file")
+        G.Handle().load_file(bad)
