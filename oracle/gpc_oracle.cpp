@@ -182,23 +182,28 @@ struct SogpStats {
     }
 };
 
-// One sparse online GP, scalar output, 2-D input.  Dense symmetric C and Q with leading
-// dimension ld = capacity + 2.
+// One sparse online GP with D outputs (D = 1: sparse_gp, heights; D = 3: sparse_gp_field, RGB) and 2-D input.
+// Dense symmetric C and Q with leading dimension ld = capacity + 2; alpha is stored per output channel.
+// The recursion for C, Q and BV does not depend on the outputs; the two classes differ in alpha's width, in the
+// capacity score (sparse_gp_field.hpp:187) and in delete_bv's alpha update (sparse_gp_field.hpp:250-253).
 struct Sogp {
     SogpParams P;
-    int N = 0, ld = 0;
+    int N = 0, ld = 0, D = 1;
+    bool field = false;
     std::vector<double> alpha, C, Q, b1, b2, k, ck, e, sv, qs, cs, qc;
     std::vector<int> idx;
     SogpStats st;
     int flags = 0;  // bit0: NaN in C(0,0) seen (sparse_gp.hpp:245-247)
 
-    void init(const SogpParams& p, int maxn) {
+    void init(const SogpParams& p, int maxn, int dout = 1) {
         P = p;
+        D = dout;
+        field = dout > 1;
         ld = maxn + 2;
         N = 0;
         st = SogpStats();
         flags = 0;
-        alpha.assign(ld, 0.0);
+        alpha.assign((size_t)D * ld, 0.0);
         C.assign((size_t)ld * ld, 0.0);
         Q.assign((size_t)ld * ld, 0.0);
         b1.assign(ld, 0.0); b2.assign(ld, 0.0); k.assign(ld, 0.0); ck.assign(ld, 0.0);
@@ -208,6 +213,7 @@ struct Sogp {
     }
     double& c(int i, int j) { return C[(size_t)i * ld + j]; }
     double& q(int i, int j) { return Q[(size_t)i * ld + j]; }
+    double& al(int ch, int i) { return alpha[(size_t)ch * ld + i]; }
 
     // rbf_kernel.cpp:15-18 : p0 * exp(-0.5f/p1 * ||xi-xj||^2)
     inline double kern(double x1, double x2, double y1, double y2) const {
@@ -216,12 +222,12 @@ struct Sogp {
         return P.p0 * orc_exp_impl(P.cl * sq);
     }
 
-    // sparse_gp.hpp:252-295
+    // sparse_gp.hpp:252-295 / sparse_gp_field.hpp:224-263
     void delete_bv(int loc) {
         const int L = N - 1, M = N - 1;
         st.sumN2_del += (double)M * M;
-        double astar = alpha[loc];
-        alpha[loc] = alpha[L];
+        double astar[3] = {0, 0, 0};
+        for (int ch = 0; ch < D; ch++) { astar[ch] = al(ch, loc); al(ch, loc) = al(ch, L); }
         double cstar = c(loc, loc);
         for (int i = 0; i < N; i++) cs[i] = c(i, loc);
         cs[loc] = cs[L];
@@ -244,10 +250,16 @@ struct Sogp {
         // Appendix G section g (sparse_gp.hpp:283-288); per-element divisions of the
         // reference are restated as multiplications by the rounded reciprocals iq, iqc.
         double qcs = qstar + cstar;
-        double coef = astar / qcs;
-        for (int i = 0; i < M; i++) {
-            qc[i] = qs[i] + cs[i];
-            alpha[i] = alpha[i] - coef * qc[i];
+        for (int i = 0; i < M; i++) qc[i] = qs[i] + cs[i];
+        if (!field) {
+            double coef = astar[0] / qcs;   // alpha -= alphastar/(qstar + cstar)*(Qstar + Cstar)
+            for (int i = 0; i < M; i++) al(0, i) = al(0, i) - coef * qc[i];
+        } else {
+            // sparse_gp_field.hpp:250-253: qc = (qstar + cstar)*(Qstar + Cstar) — multiplied, as the reference has it
+            for (int i = 0; i < M; i++) {
+                double w = qcs * qc[i];
+                for (int ch = 0; ch < D; ch++) al(ch, i) = al(ch, i) - astar[ch] * w;
+            }
         }
         double iq = 1.0 / qstar, iqc = 1.0 / qcs;
         for (int i = 0; i < M; i++)
@@ -262,17 +274,18 @@ struct Sogp {
         b1[loc] = b1[L]; b2[loc] = b2[L]; idx[loc] = idx[L];
         // clear the dropped row/col so padded reads stay zero
         for (int i = 0; i < N; i++) { c(L, i) = 0; c(i, L) = 0; q(L, i) = 0; q(i, L) = 0; }
-        alpha[L] = 0; b1[L] = 0; b2[L] = 0; idx[L] = -1;
+        for (int ch = 0; ch < D; ch++) al(ch, L) = 0;
+        b1[L] = 0; b2[L] = 0; idx[L] = -1;
         N = M;
     }
 
-    // sparse_gp.hpp:89-249
-    void add(double x1, double x2, double y, int orig) {
+    // sparse_gp.hpp:89-249 / sparse_gp_field.hpp:59-222 ; y has D entries
+    void add(double x1, double x2, const double* y, int orig) {
         st.n_add++;
         const double kstar = P.p0;  // kernel(X,X) = p0*exp(-0) exactly
         if (N == 0) {
             double d = kstar + P.s20;
-            alpha[0] = y / d;
+            for (int ch = 0; ch < D; ch++) al(ch, 0) = y[ch] / d;
             c(0, 0) = -1.0 / d;
             q(0, 0) = 1.0 / kstar;
             b1[0] = x1; b2[0] = x2; idx[0] = orig;
@@ -284,12 +297,14 @@ struct Sogp {
         st.sumN += N;
         st.sumN2_common += (double)N * N;
         for (int i = 0; i < N; i++) k[i] = kern(x1, x2, b1[i], b2[i]);
-        double m = dot32(alpha.data(), k.data(), N);
+        double m[3] = {0, 0, 0};
+        for (int ch = 0; ch < D; ch++) m[ch] = dot32(&alpha[(size_t)ch * ld], k.data(), N);
         for (int i = 0; i < N; i++) ck[i] = row4(&C[(size_t)i * ld], k.data(), N);
         double s2 = kstar + dot32(k.data(), ck.data(), N);
         double den = P.s20 + s2;
-        double r = -1.0 / den;      // gaussian_noise.cpp:15-18
-        double qq = (y - m) / den;  // gaussian_noise.cpp:9-12
+        double r = -1.0 / den;      // gaussian_noise.cpp:15-18 / gaussian_noise_3d.cpp:16-19
+        double qq[3] = {0, 0, 0};
+        for (int ch = 0; ch < D; ch++) qq[ch] = (y[ch] - m[ch]) / den;  // gaussian_noise.cpp:9-12 / gaussian_noise_3d.cpp:10-13
         for (int i = 0; i < N; i++) e[i] = row4(&Q[(size_t)i * ld], k.data(), N);
         double gamma = kstar - dot32(k.data(), e.data(), N);
         if (gamma < TINY12) gamma = 0;
@@ -298,8 +313,10 @@ struct Sogp {
             st.sumN2_sparse += (double)N * N;
             double eta = 1.0 / (1.0 + gamma * r);
             for (int i = 0; i < N; i++) sv[i] = ck[i] + e[i];
-            double qe = qq * eta;
-            for (int i = 0; i < N; i++) alpha[i] = alpha[i] + sv[i] * qe;
+            for (int ch = 0; ch < D; ch++) {
+                double qe = qq[ch] * eta;
+                for (int i = 0; i < N; i++) al(ch, i) = al(ch, i) + sv[i] * qe;
+            }
             double re = r * eta;
             for (int i = 0; i < N; i++)
                 for (int j = 0; j < N; j++) c(i, j) = std::fma(re, sv[i] * sv[j], c(i, j));
@@ -308,8 +325,10 @@ struct Sogp {
             st.sumN2_full += (double)(N + 1) * (N + 1);
             for (int i = 0; i < N; i++) sv[i] = ck[i];
             sv[N] = 1.0;
-            for (int i = 0; i < N; i++) alpha[i] = alpha[i] + qq * sv[i];
-            alpha[N] = 0.0 + qq * sv[N];
+            for (int ch = 0; ch < D; ch++) {
+                for (int i = 0; i < N; i++) al(ch, i) = al(ch, i) + qq[ch] * sv[i];
+                al(ch, N) = 0.0 + qq[ch] * sv[N];
+            }
             for (int i = 0; i <= N; i++)
                 for (int j = 0; j <= N; j++) c(i, j) = std::fma(r, sv[i] * sv[j], c(i, j));
             b1[N] = x1; b2[N] = x2; idx[N] = orig;
@@ -319,12 +338,14 @@ struct Sogp {
                 for (int j = 0; j <= N; j++) q(i, j) = std::fma(ig, e[i] * e[j], q(i, j));
             N++;
         }
-        // capacity deletions (sparse_gp.hpp:206-223)
+        // capacity deletions (sparse_gp.hpp:206-223 / sparse_gp_field.hpp:181-197)
         while (N > P.capacity && P.capacity > 0) {
             double minscore = 0;
             int minloc = -1;
             for (int i = 0; i < N; i++) {
-                double score = alpha[i] * alpha[i] / (q(i, i) + c(i, i));
+                double num = al(0, i) * al(0, i);
+                if (D == 3) num = num + (al(1, i) * al(1, i) + al(2, i) * al(2, i));  // alpha.row(i).squaredNorm()
+                double score = num / (q(i, i) + c(i, i));
                 if (i == 0 || score < minscore) { minscore = score; minloc = i; }
             }
             delete_bv(minloc);
@@ -345,12 +366,20 @@ struct Sogp {
         }
         if (std::isnan(c(0, 0))) flags |= 1;
     }
+    void add(double x1, double x2, double y, int orig) { add(x1, x2, &y, orig); }
 
     // sparse_gp.hpp:312-351 (mean only; the caller discards sigma, gp_compressor.cpp:333)
     double predict(double x1, double x2) {
         if (N == 0) return 0.0;
         for (int i = 0; i < N; i++) k[i] = kern(x1, x2, b1[i], b2[i]);
         return row4(alpha.data(), k.data(), N);
+    }
+    // sparse_gp_field.hpp:284-320 (mean of every channel)
+    void predict_field(double x1, double x2, double* f) {
+        for (int ch = 0; ch < D; ch++) f[ch] = 0.0;
+        if (N == 0) return;
+        for (int i = 0; i < N; i++) k[i] = kern(x1, x2, b1[i], b2[i]);
+        for (int ch = 0; ch < D; ch++) f[ch] = row4(&alpha[(size_t)ch * ld], k.data(), N);
     }
     // predictive sigma as sparse_gp.hpp:329-347 (conf = false): sqrt(s20 + kstar + k'Ck)
     double predict_sigma(double x1, double x2) {
@@ -626,6 +655,9 @@ struct Config {
     int shuffle = 1;     // 0 disables sparse_gp::shuffle (matlab/sogp.m has none)
     int rgb_rand = 1;    // account for the RGB field GP's shuffle in the rand stream
     int threads = 1;
+    int rgb = 0;         // 1: also fit / decode the RGB field GP (sparse_gp_field, gp_compressor.cpp:163,334)
+    double rgb_s0 = (double)1e2f;       // sparse_gp_field.h:43
+    double rgb_eps_tol = (double)1e-4f; // sparse_gp_field.hpp:16
 };
 
 struct Oracle {
@@ -645,6 +677,12 @@ struct Oracle {
     std::vector<int32_t> st_idx;               // stream: original point index
     std::vector<double> st_x1, st_x2, st_y;    // stream: local coordinates (candidate order)
     std::vector<int32_t> st_perm;              // per patch shuffle permutation (stream-local)
+    std::vector<double> st_c;                  // stream: centred colours (r,g,b per point), gp_compressor.cpp:105
+    std::vector<int32_t> st_perm_rgb;          // the RGB field GP's own shuffle
+    std::vector<int32_t> rgb_nbv, rgb_bv_idx;  // RGB field GP results
+    std::vector<int64_t> rgb_bv_off;
+    std::vector<double> rgb_bv1, rgb_bv2, rgb_alpha;  // rgb_alpha: 3 per BV (r,g,b)
+    SogpStats stats_rgb;
     // ---- fit results ----
     std::vector<int32_t> nbv;                  // per patch
     std::vector<int64_t> bv_off;               // n_leaves+1
@@ -666,6 +704,12 @@ struct Oracle {
         p.cl = (double)(-0.5f) / cfg.l_sq;
         return p;
     }
+    SogpParams rgb_params() const {  // sparse_gp_field(capacity, s0 = 1e2f), eps_tol 1e-4f, same default kernel
+        SogpParams p = sogp_params();
+        p.s20 = cfg.rgb_s0;
+        p.eps_tol = cfg.rgb_eps_tol;
+        return p;
+    }
 
     // ---------------- project_cloud (gp_compressor.cpp:177-249) ----------------
     int project(const uint8_t* cloud32, int64_t n) {
@@ -681,7 +725,7 @@ struct Oracle {
         owner.assign(n, -1);
         leaf_code.clear(); leaf_center.clear(); leaf_ncand.clear(); leaf_R.clear();
         leaf_quat.clear(); leaf_mean.clear(); leaf_rgbmean.clear(); patch_off.assign(1, 0);
-        st_idx.clear(); st_x1.clear(); st_x2.clear(); st_y.clear();
+        st_idx.clear(); st_x1.clear(); st_x2.clear(); st_y.clear(); st_c.clear();
         n_leaves = 0; n_claimed = 0;
         if (!lat.defined) return 0;
         if (3 * lat.depth > 63) { err = "octree depth too large for a 64-bit Morton code"; return 2; }
@@ -827,6 +871,7 @@ struct Oracle {
         for (int64_t i = 0; i < NL; i++) patch_off[i + 1] = patch_off[i] + cnt[i + 1];
         n_claimed = patch_off[NL];
         st_idx.assign(n_claimed, 0); st_x1.assign(n_claimed, 0); st_x2.assign(n_claimed, 0); st_y.assign(n_claimed, 0);
+        st_c.assign(3 * n_claimed, 0);
         std::vector<double> st_h(n_claimed);
         {
             std::vector<int64_t> cur(patch_off.begin(), patch_off.end() - 1);
@@ -860,7 +905,10 @@ struct Oracle {
                 double cntd = (double)(hi - lo);
                 double mn = butterfly32(ph) / cntd;  // NaN for an empty patch, as in the reference
                 for (int ch = 0; ch < 3; ch++) leaf_rgbmean[i * 3 + ch] = butterfly32(pc[ch]) / cntd;
-                for (int64_t s = lo; s < hi; s++) st_y[s] = st_h[s] - mn;
+                for (int64_t s = lo; s < hi; s++) {
+                    st_y[s] = st_h[s] - mn;
+                    for (int ch = 0; ch < 3; ch++) st_c[3 * s + ch] = (double)RGB(st_idx[s], ch) - leaf_rgbmean[i * 3 + ch];
+                }
                 for (int d = 0; d < 3; d++)
                     leaf_mean[i * 3 + d] = (double)cen[a * 3 + d] + mn * Rl[a * 9 + d * 3 + 0];  // centre += mn*R.col(0)
             }
@@ -870,10 +918,14 @@ struct Oracle {
     }
 
     // ------------- train_processes (gp_compressor.cpp:121-175) on any patch stream -------------
-    int train(int64_t NP, const int64_t* off, const double* x1, const double* x2, const double* y, int dump) {
+    int train(int64_t NP, const int64_t* off, const double* x1, const double* x2, const double* y, int dump,
+              const double* colours = nullptr) {
         auto t0 = std::chrono::steady_clock::now();
         const SogpParams sp = sogp_params();
         const int64_t total = off[NP];
+        const bool do_rgb = cfg.rgb && colours != nullptr;
+        if (do_rgb && !(cfg.shuffle && cfg.rgb_rand)) { err = "rgb needs shuffle and rgb_rand"; return 3; }
+        st_perm_rgb.assign(do_rgb ? total : 0, 0);
         // rand stream: patch p's height shuffle starts after 2*(n_q-1) draws for every earlier
         // non-empty patch q (height GP then RGB field GP each shuffle; gp_compressor.cpp:162-163)
         st_perm.assign(total, 0);
@@ -886,14 +938,17 @@ struct Oracle {
                 if (n == 0) continue;
                 if (cfg.shuffle) {
                     shuffle_ref(ind, n, g);
-                    if (cfg.rgb_rand)
+                    for (int i = 0; i < n; i++) st_perm[off[p] + i] = ind[i];
+                    if (do_rgb) {  // RGB_gps[i].add_measurements(X, C): its own shuffle, gp_compressor.cpp:163
+                        shuffle_ref(ind, n, g);
+                        for (int i = 0; i < n; i++) st_perm_rgb[off[p] + i] = ind[i];
+                    } else if (cfg.rgb_rand) {
                         for (int i = n - 1; i > 0; --i) g.next();
+                    }
                     rand_offset += (uint64_t)(n - 1) * (cfg.rgb_rand ? 2 : 1);
                 } else {
-                    ind.resize(n);
-                    for (int i = 0; i < n; i++) ind[i] = i;
+                    for (int i = 0; i < n; i++) st_perm[off[p] + i] = i;
                 }
-                for (int i = 0; i < n; i++) st_perm[off[p] + i] = ind[i];
             }
         }
         nbv.assign(NP, 0);
@@ -931,6 +986,49 @@ struct Oracle {
         });
         stats = SogpStats();
         for (auto& s : tstats) stats.merge(s);
+        // ---- RGB field GP (sparse_gp_field<rbf_kernel, gaussian_noise_3d>), same points, own shuffle ----
+        rgb_nbv.assign(do_rgb ? NP : 0, 0);
+        rgb_bv_off.assign(NP + 1, 0);
+        rgb_bv_idx.clear(); rgb_bv1.clear(); rgb_bv2.clear(); rgb_alpha.clear();
+        stats_rgb = SogpStats();
+        if (do_rgb) {
+            const SogpParams rp = rgb_params();
+            std::vector<std::vector<double>> rA(NP), rB1(NP), rB2(NP);
+            std::vector<std::vector<int32_t>> rI(NP);
+            std::vector<SogpStats> rstats(std::max(1, nth));
+            parallel_for(NP, nth, [&](int tid, int64_t b, int64_t e) {
+                Sogp gp;
+                for (int64_t p = b; p < e; p++) {
+                    int n = (int)(off[p + 1] - off[p]);
+                    if (n == 0) continue;
+                    int maxn = (cap > 0) ? std::min(cap, n) : n;
+                    gp.init(rp, maxn, 3);
+                    const int64_t o = off[p];
+                    for (int t = 0; t < n; t++) {
+                        int s = st_perm_rgb[o + t];
+                        gp.add(x1[o + s], x2[o + s], &colours[3 * (o + s)], s);
+                    }
+                    rgb_nbv[p] = gp.N;
+                    rA[p].resize((size_t)3 * gp.N);
+                    for (int i = 0; i < gp.N; i++)
+                        for (int ch = 0; ch < 3; ch++) rA[p][3 * i + ch] = gp.al(ch, i);
+                    rB1[p].assign(gp.b1.begin(), gp.b1.begin() + gp.N);
+                    rB2[p].assign(gp.b2.begin(), gp.b2.begin() + gp.N);
+                    rI[p].assign(gp.idx.begin(), gp.idx.begin() + gp.N);
+                    rstats[tid].merge(gp.st);
+                }
+            });
+            for (auto& s : rstats) stats_rgb.merge(s);
+            for (int64_t p = 0; p < NP; p++) rgb_bv_off[p + 1] = rgb_bv_off[p] + rgb_nbv[p];
+            rgb_bv_idx.resize(rgb_bv_off[NP]); rgb_bv1.resize(rgb_bv_off[NP]); rgb_bv2.resize(rgb_bv_off[NP]);
+            rgb_alpha.resize(3 * rgb_bv_off[NP]);
+            for (int64_t p = 0; p < NP; p++) {
+                std::copy(rA[p].begin(), rA[p].end(), rgb_alpha.begin() + 3 * rgb_bv_off[p]);
+                std::copy(rB1[p].begin(), rB1[p].end(), rgb_bv1.begin() + rgb_bv_off[p]);
+                std::copy(rB2[p].begin(), rB2[p].end(), rgb_bv2.begin() + rgb_bv_off[p]);
+                std::copy(rI[p].begin(), rI[p].end(), rgb_bv_idx.begin() + rgb_bv_off[p]);
+            }
+        }
         bv_off.assign(NP + 1, 0);
         dump_off.assign(NP + 1, 0);
         for (int64_t p = 0; p < NP; p++) { bv_off[p + 1] = bv_off[p] + nbv[p]; dump_off[p + 1] = dump_off[p] + (dump ? (int64_t)nbv[p] * nbv[p] : 0); }
@@ -963,7 +1061,7 @@ struct Oracle {
         const bool have_frames = (int64_t)leaf_R.size() == NP * 9;
         std::atomic<double> sink(0.0);
         parallel_for(NP, cfg.threads, [&](int, int64_t b, int64_t e) {
-            Sogp gp;
+            Sogp gp, gc;
             double acc = 0;
             for (int64_t p = b; p < e; p++) {
                 int N = nbv[p];
@@ -976,6 +1074,16 @@ struct Oracle {
                 if (with_sigma && !dumpC.empty())
                     for (int i = 0; i < N; i++)
                         for (int j = 0; j < N; j++) gp.c(i, j) = dumpC[dump_off[p] + (size_t)i * N + j];
+                const bool have_rgb = (int64_t)rgb_nbv.size() == NP;
+                if (have_rgb) {
+                    const int NR = rgb_nbv[p];
+                    gc.init(rgb_params(), std::max(NR, 1), 3);
+                    gc.N = NR;
+                    for (int i = 0; i < NR; i++) {
+                        gc.b1[i] = rgb_bv1[rgb_bv_off[p] + i]; gc.b2[i] = rgb_bv2[rgb_bv_off[p] + i];
+                        for (int ch = 0; ch < 3; ch++) gc.al(ch, i) = rgb_alpha[3 * (rgb_bv_off[p] + i) + ch];
+                    }
+                }
                 double Rq[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, mean[3] = {0, 0, 0}, cm[3] = {0, 0, 0};
                 if (have_frames) {
                     quat_to_rot(&leaf_quat[p * 4], Rq);
@@ -998,9 +1106,11 @@ struct Oracle {
                             }
                             o[3] = 1.0f;
                             uint8_t* cb = out32 + 32 * (base + m) + 16;
-                            // colour = RGB field GP (row N1, not built yet) + RGB mean: DC term only
-                            cb[2] = (uint8_t)flatten_color(cm[0]); cb[1] = (uint8_t)flatten_color(cm[1]);
-                            cb[0] = (uint8_t)flatten_color(cm[2]); cb[3] = 255;
+                            // c = C_star.row(m) + RGB_means[i] (gp_compressor.cpp:367); without the field GP: mean only
+                            double cf[3] = {0, 0, 0};
+                            if (have_rgb) gc.predict_field(X0, X1, cf);
+                            cb[2] = (uint8_t)flatten_color(cf[0] + cm[0]); cb[1] = (uint8_t)flatten_color(cf[1] + cm[1]);
+                            cb[0] = (uint8_t)flatten_color(cf[2] + cm[2]); cb[3] = 255;
                             std::memset(out32 + 32 * (base + m) + 20, 0, 12);
                         }
                     }
@@ -1023,6 +1133,7 @@ extern "C" {
 struct orc_config {
     double res; int sz; int capacity; double s0; double eps_tol; double sigmaf_sq; double l_sq;
     int leaf_order; int shuffle; int rgb_rand; int threads;
+    int rgb; int pad; double rgb_s0; double rgb_eps_tol;
 };
 
 double orc_exp(double x) { return orc_exp_impl(x); }
@@ -1050,6 +1161,7 @@ void orc_config_default(orc_config* c) {
     c->res = d.res; c->sz = d.sz; c->capacity = d.capacity; c->s0 = d.s0; c->eps_tol = d.eps_tol;
     c->sigmaf_sq = d.sigmaf_sq; c->l_sq = d.l_sq; c->leaf_order = d.leaf_order; c->shuffle = d.shuffle;
     c->rgb_rand = d.rgb_rand; c->threads = d.threads;
+    c->rgb = d.rgb; c->pad = 0; c->rgb_s0 = d.rgb_s0; c->rgb_eps_tol = d.rgb_eps_tol;
 }
 
 void* orc_create(const orc_config* c) {
@@ -1058,6 +1170,7 @@ void* orc_create(const orc_config* c) {
     o->cfg.eps_tol = c->eps_tol; o->cfg.sigmaf_sq = c->sigmaf_sq; o->cfg.l_sq = c->l_sq;
     o->cfg.leaf_order = c->leaf_order; o->cfg.shuffle = c->shuffle; o->cfg.rgb_rand = c->rgb_rand;
     o->cfg.threads = c->threads < 1 ? 1 : c->threads;
+    o->cfg.rgb = c->rgb; o->cfg.rgb_s0 = c->rgb_s0; o->cfg.rgb_eps_tol = c->rgb_eps_tol;
     return o;
 }
 void orc_destroy(void* h) { delete (Oracle*)h; }
@@ -1070,7 +1183,7 @@ int orc_project(void* h, const void* cloud32, int64_t n) { return ((Oracle*)h)->
 // train on the projected stream (save_compressed = project + train)
 int orc_train_projected(void* h, int dump) {
     Oracle* o = (Oracle*)h;
-    return o->train(o->n_leaves, o->patch_off.data(), o->st_x1.data(), o->st_x2.data(), o->st_y.data(), dump);
+    return o->train(o->n_leaves, o->patch_off.data(), o->st_x1.data(), o->st_x2.data(), o->st_y.data(), dump, o->st_c.data());
 }
 int orc_compress(void* h, const void* cloud32, int64_t n, int dump) {
     int rc = orc_project(h, cloud32, n);
@@ -1082,6 +1195,14 @@ int orc_fit_patches(void* h, int64_t NP, const int64_t* off, const double* x1, c
     Oracle* o = (Oracle*)h;
     o->leaf_R.clear();
     return o->train(NP, off, x1, x2, y, dump);
+}
+// the same with per-point colours (3 per point, centred by the caller): also fits the RGB field GPs when cfg.rgb
+int orc_fit_patches_rgb(void* h, int64_t NP, const int64_t* off, const double* x1, const double* x2, const double* y,
+                        const double* colours, int dump) {
+    Oracle* o = (Oracle*)h;
+    o->leaf_R.clear();
+    o->n_claimed = off[NP];
+    return o->train(NP, off, x1, x2, y, dump, colours);
 }
 // inject fitted parameters (decode-only configurations)
 int orc_set_params(void* h, int64_t NP, const int32_t* nbv, const double* bv1, const double* bv2, const double* alpha,
@@ -1162,6 +1283,14 @@ const void* orc_ptr(void* h, const char* name) {
     if (n == "dumpC") return o->dumpC.data();
     if (n == "dumpQ") return o->dumpQ.data();
     if (n == "dump_off") return o->dump_off.data();
+    if (n == "st_c") return o->st_c.data();
+    if (n == "st_perm_rgb") return o->st_perm_rgb.data();
+    if (n == "rgb_nbv") return o->rgb_nbv.data();
+    if (n == "rgb_bv_off") return o->rgb_bv_off.data();
+    if (n == "rgb_bv_idx") return o->rgb_bv_idx.data();
+    if (n == "rgb_bv1") return o->rgb_bv1.data();
+    if (n == "rgb_bv2") return o->rgb_bv2.data();
+    if (n == "rgb_alpha") return o->rgb_alpha.data();
     return nullptr;
 }
 struct orc_stats {
@@ -1176,6 +1305,16 @@ void orc_get_stats(void* h, orc_stats* s) {
     s->sumN2_common = o->stats.sumN2_common; s->sumN2_sparse = o->stats.sumN2_sparse; s->sumN2_full = o->stats.sumN2_full;
     s->sumN2_del = o->stats.sumN2_del; s->t_project = o->t_project; s->t_train = o->t_train; s->t_decode = o->t_decode;
 }
+
+void orc_get_stats_rgb(void* h, orc_stats* s) {
+    Oracle* o = (Oracle*)h;
+    std::memset(s, 0, sizeof(*s));
+    s->n_add = o->stats_rgb.n_add; s->n_first = o->stats_rgb.n_first; s->n_sparse = o->stats_rgb.n_sparse; s->n_full = o->stats_rgb.n_full;
+    s->n_del_cap = o->stats_rgb.n_del_cap; s->n_del_geo = o->stats_rgb.n_del_geo; s->sumN = o->stats_rgb.sumN;
+    s->sumN2_common = o->stats_rgb.sumN2_common; s->sumN2_sparse = o->stats_rgb.sumN2_sparse; s->sumN2_full = o->stats_rgb.sumN2_full;
+    s->sumN2_del = o->stats_rgb.sumN2_del;
+}
+int64_t orc_rgb_bv_total(void* h) { Oracle* o = (Oracle*)h; return o->rgb_bv_off.empty() ? 0 : o->rgb_bv_off.back(); }
 
 // helpers exported for unit tests
 void orc_rotation_from_sums(const double sums[10], const double c[3], double R[9]) {

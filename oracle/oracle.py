@@ -16,7 +16,8 @@ _LIB = None
 class OrcConfig(C.Structure):
     _fields_ = [("res", C.c_double), ("sz", C.c_int), ("capacity", C.c_int), ("s0", C.c_double),
                 ("eps_tol", C.c_double), ("sigmaf_sq", C.c_double), ("l_sq", C.c_double),
-                ("leaf_order", C.c_int), ("shuffle", C.c_int), ("rgb_rand", C.c_int), ("threads", C.c_int)]
+                ("leaf_order", C.c_int), ("shuffle", C.c_int), ("rgb_rand", C.c_int), ("threads", C.c_int),
+                ("rgb", C.c_int), ("pad", C.c_int), ("rgb_s0", C.c_double), ("rgb_eps_tol", C.c_double)]
 
 
 class OrcSizes(C.Structure):
@@ -57,6 +58,7 @@ def lib():
         L.orc_train_projected.argtypes = [C.c_void_p, C.c_int]
         L.orc_compress.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
         L.orc_fit_patches.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 4 + [C.c_int]
+        L.orc_fit_patches_rgb.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_int]
         L.orc_set_params.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
         L.orc_decode.restype = C.c_int64
         L.orc_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -65,6 +67,9 @@ def lib():
         L.orc_ptr.restype = C.c_void_p
         L.orc_ptr.argtypes = [C.c_void_p, C.c_char_p]
         L.orc_get_stats.argtypes = [C.c_void_p, C.POINTER(OrcStats)]
+        L.orc_get_stats_rgb.argtypes = [C.c_void_p, C.POINTER(OrcStats)]
+        L.orc_rgb_bv_total.restype = C.c_int64
+        L.orc_rgb_bv_total.argtypes = [C.c_void_p]
         L.orc_rand_stream.argtypes = [C.c_uint64, C.c_int64, C.c_void_p]
         L.orc_shuffles.argtypes = [C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p]
         L.orc_exp_array.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
@@ -139,8 +144,9 @@ class Oracle:
 
     def __init__(self, res=float(np.float32(0.1)), sz=10, capacity=100, s0=float(np.float32(1e-1)),
                  eps_tol=float(np.float32(1e-6)), sigmaf_sq=100.0, l_sq=1.0, leaf_order=0, shuffle=1,
-                 rgb_rand=1, threads=1):
-        self.cfg = OrcConfig(res, sz, capacity, s0, eps_tol, sigmaf_sq, l_sq, leaf_order, shuffle, rgb_rand, threads)
+                 rgb_rand=1, threads=1, rgb=0, rgb_s0=float(np.float32(1e2)), rgb_eps_tol=float(np.float32(1e-4))):
+        self.cfg = OrcConfig(res, sz, capacity, s0, eps_tol, sigmaf_sq, l_sq, leaf_order, shuffle, rgb_rand, threads, rgb, 0, rgb_s0,
+                             rgb_eps_tol)
         self.h = lib().orc_create(C.byref(self.cfg))
         self._np = 0
 
@@ -168,6 +174,21 @@ class Oracle:
         s = OrcStats()
         lib().orc_get_stats(self.h, C.byref(s))
         return {n: getattr(s, n) for n, _ in OrcStats._fields_}
+
+    def stats_rgb(self):
+        s = OrcStats()
+        lib().orc_get_stats_rgb(self.h, C.byref(s))
+        return {n: getattr(s, n) for n, _ in OrcStats._fields_}
+
+    def rgb_result(self):
+        """RGB field GP (sparse_gp_field) parameters of the last compress with rgb=1."""
+        NP = self._np
+        T = lib().orc_rgb_bv_total(self.h)
+        S = self.sizes().n_claimed
+        return {"nbv": self._arr("rgb_nbv", np.int32, NP), "bv_off": self._arr("rgb_bv_off", np.int64, NP + 1),
+                "bv_idx": self._arr("rgb_bv_idx", np.int32, T), "bv1": self._arr("rgb_bv1", np.float64, T),
+                "bv2": self._arr("rgb_bv2", np.float64, T), "alpha": self._arr("rgb_alpha", np.float64, 3 * T),
+                "perm": self._arr("st_perm_rgb", np.int32, S), "colours": self._arr("st_c", np.float64, 3 * S)}
 
     def _arr(self, name, dtype, n):
         ptr = lib().orc_ptr(self.h, name.encode())
@@ -200,11 +221,15 @@ class Oracle:
         self._np = self.sizes().n_leaves
         return self.fit_result(dump)
 
-    def fit_patches(self, off, x1, x2, y, dump=False):
+    def fit_patches(self, off, x1, x2, y, dump=False, colours=None):
         off = np.ascontiguousarray(off, dtype=np.int64)
         x1, x2, y = (np.ascontiguousarray(a, dtype=np.float64) for a in (x1, x2, y))
         self._np = off.size - 1
         self._ntot = int(off[-1])
+        if colours is not None:
+            colours = np.ascontiguousarray(colours, dtype=np.float64).reshape(-1, 3)
+            self._check(lib().orc_fit_patches_rgb(self.h, self._np, _p(off), _p(x1), _p(x2), _p(y), _p(colours), int(dump)))
+            return self.fit_result(dump, ntot=self._ntot)
         self._check(lib().orc_fit_patches(self.h, self._np, _p(off), _p(x1), _p(x2), _p(y), int(dump)))
         return self.fit_result(dump, ntot=self._ntot)
 

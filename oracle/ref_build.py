@@ -14,8 +14,10 @@ def build():
     if not os.path.isdir(REF):
         return None
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    srcs = [os.path.join(HERE, "ref_sogp.cpp"), os.path.join(REF, "rbf_kernel.cpp"), os.path.join(REF, "gaussian_noise.cpp")]
-    deps = srcs + [os.path.join(HERE, "eigen_shim", "Eigen", "Dense"), os.path.join(REF, "sparse_gp.hpp"), os.path.join(REF, "sparse_gp.h")]
+    srcs = [os.path.join(HERE, "ref_sogp.cpp"), os.path.join(REF, "rbf_kernel.cpp"), os.path.join(REF, "gaussian_noise.cpp"),
+            os.path.join(REF, "gaussian_noise_3d.cpp")]
+    deps = srcs + [os.path.join(HERE, "eigen_shim", "Eigen", "Dense"), os.path.join(REF, "sparse_gp.hpp"), os.path.join(REF, "sparse_gp.h"),
+                   os.path.join(REF, "sparse_gp_field.hpp"), os.path.join(REF, "sparse_gp_field.h")]
     if os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
     cmd = ["g++", "-O2", "-std=c++11", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-I" + os.path.join(HERE, "eigen_shim"), "-I" + REF] + srcs + ["-o", OUT]

@@ -18,12 +18,15 @@
 #define private public
 #define protected public
 #include "sparse_gp.h"
+#include "sparse_gp_field.h"
 #undef private
 #undef protected
 #include "gaussian_noise.h"
+#include "gaussian_noise_3d.h"
 #include "rbf_kernel.h"
 
 typedef sparse_gp<rbf_kernel, gaussian_noise> ref_gp;
+typedef sparse_gp_field<rbf_kernel, gaussian_noise_3d> ref_gp_field;
 
 extern "C" {
 
@@ -56,6 +59,36 @@ int ref_sogp_fit(int n, const double* x1, const double* x2, const double* y, int
         Eigen::VectorXd f, sg;
         gp.predict_measurements(f, Xs, sg);
         for (int i = 0; i < n_pred; i++) { f_star[i] = f(i); sigma[i] = sg(i); }
+    }
+    return N;
+}
+
+// The RGB field GP of the reference (sparse_gp_field.hpp): Y is n x 3 row-major.  alpha out: 3 per BV.
+int ref_field_fit(int n, const double* x1, const double* x2, const double* Y, int capacity, double s0, double sigmaf_sq,
+                  double l_sq, double eps_tol, unsigned long long rand_offset, int max_n, double* alpha3, double* bv1, double* bv2,
+                  int n_pred, const double* px1, const double* px2, double* f_star3) {
+    srand(1);
+    for (unsigned long long i = 0; i < rand_offset; i++) rand();
+    ref_gp_field gp(capacity, s0);
+    gp.kernel.param()(0) = sigmaf_sq;
+    gp.kernel.param()(1) = l_sq;
+    gp.eps_tol = eps_tol;
+    Eigen::MatrixXd X(n, 2), C(n, 3);
+    for (int i = 0; i < n; i++) { X(i, 0) = x1[i]; X(i, 1) = x2[i]; for (int c = 0; c < 3; c++) C(i, c) = Y[3 * i + c]; }
+    gp.add_measurements(X, C);
+    const int N = gp.size();
+    if (N > max_n) return -N;
+    for (int i = 0; i < N; i++) {
+        for (int c = 0; c < 3; c++) alpha3[3 * i + c] = gp.alpha(i, c);
+        bv1[i] = gp.BV(0, i);
+        bv2[i] = gp.BV(1, i);
+    }
+    if (n_pred > 0) {
+        Eigen::MatrixXd Xs(n_pred, 2), F;
+        for (int i = 0; i < n_pred; i++) { Xs(i, 0) = px1[i]; Xs(i, 1) = px2[i]; }
+        Eigen::VectorXd sg;
+        gp.predict_measurements(F, Xs, sg);
+        for (int i = 0; i < n_pred; i++) for (int c = 0; c < 3; c++) f_star3[3 * i + c] = F(i, c);
     }
     return N;
 }

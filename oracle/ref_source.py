@@ -25,6 +25,9 @@ def lib():
         L.ref_sogp_fit.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                    C.c_ulonglong, C.c_int] + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 4
         L.ref_shuffle.argtypes = [C.c_int, C.c_ulonglong, C.c_void_p]
+        L.ref_field_fit.restype = C.c_int
+        L.ref_field_fit.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                    C.c_ulonglong, C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3
         L.ref_kernel.restype = C.c_double
         L.ref_kernel.argtypes = [C.c_double] * 6
         _LIB = L
@@ -53,6 +56,25 @@ def fit(x1, x2, y, capacity=100, s0=float(np.float32(1e-1)), sigmaf_sq=100.0, l_
     assert N >= 0
     return dict(N=N, alpha=alpha[:N].copy(), bv1=b1[:N].copy(), bv2=b2[:N].copy(), C=Cm[:N * N].reshape(N, N).copy(),
                 Q=Qm[:N * N].reshape(N, N).copy(), f=f, sigma=sg)
+
+
+def field_fit(x1, x2, Y, capacity=100, s0=float(np.float32(1e2)), sigmaf_sq=100.0, l_sq=1.0, eps_tol=float(np.float32(1e-4)),
+              rand_offset=0, pred=None):
+    """sparse_gp_field<rbf_kernel, gaussian_noise_3d>(capacity, s0).add_measurements(X, Y) of the reference itself."""
+    x1, x2 = (np.ascontiguousarray(a, dtype=np.float64) for a in (x1, x2))
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1, 3)
+    n = x1.size
+    mx = (capacity if capacity > 0 else n) + 2
+    alpha, b1, b2 = np.zeros(3 * mx), np.zeros(mx), np.zeros(mx)
+    if pred is None:
+        pred = np.zeros((0, 2))
+    pred = np.ascontiguousarray(pred, dtype=np.float64).reshape(-1, 2)
+    p1, p2 = np.ascontiguousarray(pred[:, 0]), np.ascontiguousarray(pred[:, 1])
+    f = np.zeros(3 * pred.shape[0])
+    N = lib().ref_field_fit(n, _p(x1), _p(x2), _p(Y), capacity, s0, sigmaf_sq, l_sq, eps_tol, rand_offset, mx, _p(alpha), _p(b1), _p(b2),
+                            pred.shape[0], _p(p1), _p(p2), _p(f))
+    assert N >= 0
+    return dict(N=N, alpha=alpha[:3 * N].reshape(N, 3).copy(), bv1=b1[:N].copy(), bv2=b2[:N].copy(), f=f.reshape(-1, 3))
 
 
 def shuffle(n, rand_offset=0):

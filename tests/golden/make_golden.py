@@ -34,6 +34,19 @@ def main():
                            sigma=r["sigma"], meta=np.array([n, cap, 7 * k, r["N"]], dtype=np.int64),
                            hyper=np.array([hyp["sigmaf_sq"], hyp["l_sq"], hyp["s0"]])).items():
             out[f"{name}/{key}"] = v
+    # RGB field GP (sparse_gp_field.hpp) of the reference: defaults (capacity never binds) and a capacity-bound case
+    for name, n, cap, hyp in [("field_ref_defaults", 400, 100, dict(sigmaf_sq=100.0, l_sq=1.0, s0=float(np.float32(1e2)))),
+                              ("field_cap8", 300, 8, dict(sigmaf_sq=1.0, l_sq=(0.1 / 12) ** 2, s0=1e-2))]:
+        rng = np.random.default_rng(len(name))
+        x1 = rng.uniform(-0.05, 0.05, n)
+        x2 = rng.uniform(-0.05, 0.05, n)
+        Y = np.stack([50 * np.sin(40 * x1), 30 * np.cos(30 * x2), 20 * np.sin(30 * (x1 + x2))], axis=1) + rng.normal(0, 1, (n, 3))
+        pred = rng.uniform(-0.05, 0.05, (25, 2))
+        r = R.field_fit(x1, x2, Y, capacity=cap, rand_offset=n - 1, pred=pred, eps_tol=float(np.float32(1e-4)), **hyp)
+        for key, v in dict(x1=x1, x2=x2, Y=Y, pred=pred, alpha=r["alpha"], bv1=r["bv1"], bv2=r["bv2"], f=r["f"],
+                           meta=np.array([n, cap, n - 1, r["N"]], dtype=np.int64),
+                           hyper=np.array([hyp["sigmaf_sq"], hyp["l_sq"], hyp["s0"]])).items():
+            out[f"{name}/{key}"] = v
     out["shuffle_n57_off3"] = R.shuffle(57, 3)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_sogp.npz"), **out)
     print("wrote", len(out), "arrays")

@@ -14,7 +14,8 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = np.load(os.path.join(ROOT, "tests", "golden", "ref_sogp.npz"))
-CASES = sorted({k.split("/")[0] for k in GOLD.files if "/" in k})
+CASES = sorted({k.split("/")[0] for k in GOLD.files if "/" in k and not k.startswith("field_")})
+FIELD_CASES = sorted({k.split("/")[0] for k in GOLD.files if k.startswith("field_")})
 
 
 def bv_indices(x1, x2, b1, b2):
@@ -87,3 +88,22 @@ def test_live_reference_source(oracle_mod):
         g = dict(x1=x1, x2=x2, y=y, pred=pred, alpha=ref["alpha"], bv1=ref["bv1"], bv2=ref["bv2"], C=ref["C"], Q=ref["Q"], f=ref["f"],
                  meta=np.array([n, cap, 5 * trial, ref["N"]]), hyper=np.array([p0, l_sq, s0]))
         check_against(oracle_mod, g)
+
+
+@pytest.mark.parametrize("name", FIELD_CASES)
+def test_oracle_field_gp_matches_reference_source_vectors(oracle_mod, name):
+    """RGB field GP (next-row N1): the oracle's 3-output SOGP against the reference's own sparse_gp_field.hpp,
+    including its delete_bv (which multiplies where sparse_gp divides, sparse_gp_field.hpp:250)."""
+    g = {k.split("/")[1]: GOLD[k] for k in GOLD.files if k.startswith(name + "/")}
+    n, cap, roff, N = (int(v) for v in g["meta"])
+    p0, l_sq, s0 = (float(v) for v in g["hyper"])
+    o = oracle_mod.Oracle(capacity=cap, sigmaf_sq=p0, l_sq=l_sq, rgb=1, rgb_s0=s0)
+    # the height GP shuffles first (n - 1 draws), then the field GP: the golden run started at offset n - 1
+    o.set_rand_offset(roff - (n - 1))
+    o.fit_patches([0, n], g["x1"], g["x2"], np.zeros(n), colours=g["Y"])
+    r = o.rgb_result()
+    assert int(r["nbv"][0]) == N
+    assert np.array_equal(r["bv1"], g["bv1"]) and np.array_equal(r["bv2"], g["bv2"])   # same BVs in the same slots
+    a = r["alpha"].reshape(N, 3)
+    tol = 1e-3 if l_sq >= 1.0 else 1e-9   # reference defaults are ill-conditioned; the capacity-bound case is exact to rounding
+    assert np.abs(a - g["alpha"]).max() <= tol * np.abs(g["alpha"]).max()
