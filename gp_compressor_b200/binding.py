@@ -20,7 +20,7 @@ SYMBOLS = [
     "gpc_config_default", "gpc_create", "gpc_destroy", "gpc_last_error", "gpc_version", "gpc_compress",
     "gpc_upload_cloud", "gpc_compress_resident", "gpc_fit_patches", "gpc_decompress", "gpc_decompress_resident",
     "gpc_get_heights", "gpc_predict", "gpc_get_sizes", "gpc_get_stats", "gpc_get_patches", "gpc_get_assignment",
-    "gpc_get_params", "gpc_get_state", "gpc_set_params", "gpc_set_rand_offset", "gpc_get_stream", "gpc_debug_exp", "gpc_debug_rand", "gpc_debug_peak", "gpc_shard_range", "gpc_save", "gpc_load", "gpc_get_config",
+    "gpc_get_params", "gpc_get_params_rgb", "gpc_get_state", "gpc_set_params", "gpc_set_rand_offset", "gpc_get_stream", "gpc_debug_exp", "gpc_debug_rand", "gpc_debug_peak", "gpc_shard_range", "gpc_save", "gpc_load", "gpc_get_config",
 ]
 
 
@@ -28,7 +28,8 @@ class GpcConfig(C.Structure):
     _fields_ = [("res", C.c_double), ("sz", C.c_int32), ("capacity", C.c_int32), ("s0", C.c_double),
                 ("eps_tol", C.c_double), ("sigmaf_sq", C.c_double), ("l_sq", C.c_double), ("leaf_order", C.c_int32),
                 ("shuffle", C.c_int32), ("rgb_rand", C.c_int32), ("device", C.c_int32), ("shard_rank", C.c_int32),
-                ("shard_count", C.c_int32), ("keep_state", C.c_int32)]
+                ("shard_count", C.c_int32), ("keep_state", C.c_int32), ("rgb", C.c_int32), ("rgb_s0", C.c_double),
+                ("rgb_eps_tol", C.c_double)]
 
 
 class GpcSizes(C.Structure):
@@ -40,12 +41,13 @@ class GpcSizes(C.Structure):
 _STAT_U64 = ["n_add", "n_first", "n_sparse", "n_full", "n_del_cap", "n_del_geo", "sum_n", "sum_n2_common",
              "sum_n2_sparse", "sum_n2_full", "sum_n2_del"]
 _STAT_MS = ["ms_h2d", "ms_lattice", "ms_keys", "ms_sort", "ms_leaves", "ms_rotation", "ms_claim", "ms_group",
-            "ms_shuffle", "ms_fit", "ms_d2h", "ms_predict", "ms_total"]
+            "ms_shuffle", "ms_fit", "ms_d2h", "ms_predict", "ms_total", "ms_fit_rgb"]
+_STAT_RGB = ["rgb_n_sparse", "rgb_n_full", "rgb_n_del_cap", "rgb_n_del_geo", "rgb_sum_n2_common"]
 
 
 class GpcStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in _STAT_U64] + [("escalated", C.c_uint64 * 4), ("kernel_launches", C.c_uint64)] + \
-               [(n, C.c_float) for n in _STAT_MS]
+               [(n, C.c_uint64) for n in _STAT_RGB] + [(n, C.c_float) for n in _STAT_MS]
 
 
 def load():
@@ -79,6 +81,7 @@ def load():
     L.gpc_get_assignment.argtypes = [vp] + [vp] * 6
     L.gpc_get_params.argtypes = [vp] + [vp] * 7
     L.gpc_get_state.argtypes = [vp, i64, vp, vp]
+    L.gpc_get_params_rgb.argtypes = [vp] + [vp] * 7 + [C.POINTER(i64)]
     L.gpc_set_params.argtypes = [vp, i64] + [vp] * 7
     L.gpc_set_rand_offset.argtypes = [vp, u64]
     L.gpc_get_stream.argtypes = [vp, C.POINTER(vp)]
@@ -211,7 +214,7 @@ class Handle:
     def stats(self):
         s = GpcStats()
         self._ck(load().gpc_get_stats(self.h, C.byref(s)))
-        d = {n: getattr(s, n) for n in _STAT_U64 + _STAT_MS + ["kernel_launches"]}
+        d = {n: getattr(s, n) for n in _STAT_U64 + _STAT_MS + _STAT_RGB + ["kernel_launches"]}
         d["escalated"] = list(s.escalated)
         return d
 
@@ -224,6 +227,19 @@ class Handle:
         self._ck(load().gpc_get_params(self.h, _p(r["nbv"]), _p(r["bv_off"]), _p(r["bv_idx"]), _p(r["bv1"]),
                                        _p(r["bv2"]), _p(r["alpha"]), _p(r["flags"])))
         r["patch_lo"], r["patch_hi"] = s.patch_lo, s.patch_hi
+        return r
+
+    def params_rgb(self):
+        """RGB field GP parameters of this shard (gpc_config.rgb = 1)."""
+        s = self.sizes()
+        PL = s.patch_hi - s.patch_lo
+        tot = C.c_int64(0)
+        self._ck(load().gpc_get_params_rgb(self.h, None, None, None, None, None, None, None, C.byref(tot)))
+        T = tot.value
+        r = dict(nbv=np.zeros(PL, np.int32), bv_off=np.zeros(PL + 1, np.int64), bv_idx=np.zeros(T, np.int32), bv1=np.zeros(T), bv2=np.zeros(T),
+                 alpha=np.zeros(3 * T), perm=np.zeros(s.n_claimed, np.int32))
+        self._ck(load().gpc_get_params_rgb(self.h, _p(r["nbv"]), _p(r["bv_off"]), _p(r["bv_idx"]), _p(r["bv1"]), _p(r["bv2"]), _p(r["alpha"]),
+                                           _p(r["perm"]), C.byref(tot)))
         return r
 
     def params_into(self, nbv_ptr, bv_off_ptr, idx_ptr, bv1_ptr, bv2_ptr, alpha_ptr, flags_ptr):

@@ -35,6 +35,9 @@ struct gpc_handle {
     DevBuf nbv, flags, alpha, b1, b2, bidx, dumpC, dumpQ, queue0, queue1, qcount, kstats, hand0, hand1, spill;
     DevBuf nonempty, slot, out32, heights;
     DevBuf bv_off, palpha, pb1, pb2, pidx;      // packed copies of the fitted parameters (what leaves for the host)
+    // RGB field GP (gpc_config.rgb): its own shuffle, fit stream and parameters
+    DevBuf perm_rgb, fcr, fcg, fcb, r_nbv, r_flags, r_alpha0, r_alpha1, r_alpha2, r_b1, r_b2, r_bidx, kstats_rgb;
+    bool have_rgb = false;
     DevBuf quat, mean, rgbmean, Rm, center, code, ncand, owner, st_idx;
     DevBuf tmpA, tmpB, tmpC;
     // binning scratch
@@ -102,6 +105,47 @@ void shard_range(const std::vector<int64_t>& off, int r, int c, int64_t* lo, int
     *hi = bound(r + 1);
 }
 
+// Runs the SOGP bucket chain for one family of processes (dout 1: heights, dout 3: RGB field).
+int run_buckets(gpc_handle* h, SogpArgs& a, int need_ld, int64_t PL, int64_t lo, uint64_t* escalated) {
+    cudaStream_t st = h->stream;
+    int64_t work = PL;
+    const int32_t* ids = nullptr;
+    a.spill = nullptr;
+    int step = 0;
+    for (int b = 0; b < 5 && work > 0; b = sogp_next_bucket(b, a.dout), step++) {
+        const int bl = sogp_bucket_ld(b);
+        const bool final_bucket = need_ld <= bl;
+        a.ld = final_bucket ? need_ld : bl;
+        a.patch_ids = ids;
+        a.first_patch = lo;
+        a.n_work = (int)work;
+        DevBuf& q = (step & 1) ? h->queue1 : h->queue0;
+        DevBuf& ho = (step & 1) ? h->hand1 : h->hand0;
+        DevBuf& hi_ = (step & 1) ? h->hand0 : h->hand1;
+        a.queue = final_bucket ? nullptr : q.as<int32_t>();
+        a.queue_count = h->qcount.as<int32_t>() + b;
+        a.handoff_in = (step > 0) ? hi_.as<double>() : nullptr;
+        a.handoff_out = nullptr;
+        if (!final_bucket) {
+            CK(ho.reserve((size_t)work * sogp_handoff_slot_bytes(b, a.dout)));
+            a.handoff_out = ho.as<double>();
+        }
+        if (b == 4) {
+            CK(h->spill.reserve((size_t)work * sogp_spill_bytes_per_patch()));
+            a.spill = h->spill.as<double>();
+        }
+        CK(launch_sogp_fit(b, a, st));
+        if (final_bucket) break;
+        int32_t qn = 0;
+        CK(cudaMemcpyAsync(&qn, h->qcount.as<int32_t>() + b, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (escalated && b < 4) escalated[b] = (uint64_t)qn;
+        work = qn;
+        ids = q.as<int32_t>();
+    }
+    return GPC_OK;
+}
+
 // Shuffle + SOGP fit of patches [patch_lo, patch_hi) over the stream held in h->off/x1/x2/y.
 int run_fit(gpc_handle* h, StageTimer& tm) {
     const gpc_config& c = h->cfg;
@@ -151,7 +195,7 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
             launch_rand_stream(h->rand_offset + draws_lo, nd, h->rnd.as<uint32_t>(), st);
         }
         launch_shuffle(h->off.as<int64_t>() + lo, PL, h->roff.as<int64_t>() + lo, h->rnd.as<uint32_t>(), c.shuffle,
-                       h->perm.as<int32_t>(), h->patch_of.as<int32_t>(), h->s_begin, h->s_count, max_np, st);
+                       h->perm.as<int32_t>(), h->patch_of.as<int32_t>(), h->s_begin, h->s_count, max_np, 0, st);
         launch_gather_stream(h->off.as<int64_t>() + lo, h->patch_of.as<int32_t>(), h->perm.as<int32_t>(),
                              h->x1.as<double>(), h->x2.as<double>(), h->y.as<double>(), h->s_begin, h->s_count,
                              h->fx1.as<double>(), h->fx2.as<double>(), h->fy.as<double>(), st);
@@ -180,53 +224,74 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
     CK(cudaMemsetAsync(h->qcount.p, 0, 8 * sizeof(int32_t), st));
     SogpArgs a;
     a.off = h->off.as<int64_t>();
-    a.fx1 = h->fx1.as<double>(); a.fx2 = h->fx2.as<double>(); a.fy = h->fy.as<double>();
+    a.fx1 = h->fx1.as<double>(); a.fx2 = h->fx2.as<double>();
+    a.fy[0] = h->fy.as<double>(); a.fy[1] = a.fy[2] = nullptr;
+    a.dout = 1;
     a.forig = h->perm.as<int32_t>();
     a.capacity = cap;
     a.s20 = c.s0; a.eps_tol = c.eps_tol; a.p0 = c.sigmaf_sq; a.cl = kernel_cl(c);
     a.out_first = lo;
     a.nbv = h->nbv.as<int32_t>(); a.flags = h->flags.as<int32_t>();
-    a.o_alpha = h->alpha.as<double>(); a.o_b1 = h->b1.as<double>(); a.o_b2 = h->b2.as<double>();
+    a.o_alpha[0] = h->alpha.as<double>(); a.o_alpha[1] = a.o_alpha[2] = nullptr;
+    a.o_b1 = h->b1.as<double>(); a.o_b2 = h->b2.as<double>();
     a.o_idx = h->bidx.as<int32_t>();
     a.dumpC = c.keep_state ? h->dumpC.as<double>() : nullptr;
     a.dumpQ = c.keep_state ? h->dumpQ.as<double>() : nullptr;
     a.stats = h->kstats.as<unsigned long long>();
-    int64_t work = PL;
-    const int32_t* ids = nullptr;
-    a.spill = nullptr;
-    for (int b = 0; b < 5 && work > 0; b++) {
-        const int bl = sogp_bucket_ld(b);
-        const bool final_bucket = need_ld <= bl;
-        a.ld = final_bucket ? need_ld : bl;
-        a.patch_ids = ids;
-        a.first_patch = lo;
-        a.n_work = (int)work;
-        DevBuf& q = (b & 1) ? h->queue1 : h->queue0;
-        DevBuf& ho = (b & 1) ? h->hand1 : h->hand0;
-        DevBuf& hi_ = (b & 1) ? h->hand0 : h->hand1;
-        a.queue = final_bucket ? nullptr : q.as<int32_t>();
-        a.queue_count = h->qcount.as<int32_t>() + b;
-        a.handoff_in = (b > 0) ? hi_.as<double>() : nullptr;
-        a.handoff_out = nullptr;
-        if (!final_bucket) {
-            CK(ho.reserve((size_t)work * sogp_handoff_slot_bytes(b)));
-            a.handoff_out = ho.as<double>();
-        }
-        if (b == 4) {
-            CK(h->spill.reserve((size_t)work * sogp_spill_bytes_per_patch()));
-            a.spill = h->spill.as<double>();
-        }
-        CK(launch_sogp_fit(b, a, st));
-        if (final_bucket) break;
-        int32_t qn = 0;
-        CK(cudaMemcpyAsync(&qn, h->qcount.as<int32_t>() + b, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if (b < 4) h->stats.escalated[b] = (uint64_t)qn;
-        work = qn;
-        ids = q.as<int32_t>();
+    {
+        int rc = run_buckets(h, a, need_ld, PL, lo, h->stats.escalated);
+        if (rc) return rc;
     }
     size_t t2 = tm.mark();
     tm.span(&h->stats.ms_fit, t1, t2);
+    // ---- RGB field GP (sparse_gp_field<rbf_kernel, gaussian_noise_3d>): same points, own shuffle, 3 outputs ----
+    h->have_rgb = false;
+    if (c.rgb && h->have_binning) {
+        if (!(c.shuffle && c.rgb_rand)) return fail(h, GPC_ERR_INVALID, "rgb = 1 needs shuffle = 1 and rgb_rand = 1");
+        const int64_t Sa = std::max<int64_t>(S, 1);
+        CK(h->perm_rgb.reserve(Sa * sizeof(int32_t)));
+        CK(h->fcr.reserve(Sa * sizeof(double)));
+        CK(h->fcg.reserve(Sa * sizeof(double)));
+        CK(h->fcb.reserve(Sa * sizeof(double)));
+        CK(h->r_nbv.reserve(PLa * sizeof(int32_t)));
+        CK(h->r_flags.reserve(PLa * sizeof(int32_t)));
+        CK(h->r_alpha0.reserve(PLa * cap * sizeof(double)));
+        CK(h->r_alpha1.reserve(PLa * cap * sizeof(double)));
+        CK(h->r_alpha2.reserve(PLa * cap * sizeof(double)));
+        CK(h->r_b1.reserve(PLa * cap * sizeof(double)));
+        CK(h->r_b2.reserve(PLa * cap * sizeof(double)));
+        CK(h->r_bidx.reserve(PLa * cap * sizeof(int32_t)));
+        CK(h->kstats_rgb.reserve(16 * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(h->kstats_rgb.p, 0, 16 * sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(h->qcount.p, 0, 8 * sizeof(int32_t), st));
+        if (PL > 0 && h->s_count > 0) {
+            launch_shuffle(h->off.as<int64_t>() + lo, PL, h->roff.as<int64_t>() + lo, h->rnd.as<uint32_t>(), 1, h->perm_rgb.as<int32_t>(),
+                           h->patch_of.as<int32_t>(), h->s_begin, h->s_count, max_np, 1, st);
+            // the height fit is done with fx1 / fx2: reuse them for the field GP's order
+            launch_gather_rgb_stream(h->off.as<int64_t>() + lo, h->patch_of.as<int32_t>(), h->perm_rgb.as<int32_t>(), h->x1.as<double>(),
+                                     h->x2.as<double>(), h->rgb.as<uint32_t>(), h->rgbmean.as<double>(), lo, h->s_begin, h->s_count,
+                                     h->fx1.as<double>(), h->fx2.as<double>(), h->fcr.as<double>(), h->fcg.as<double>(),
+                                     h->fcb.as<double>(), st);
+        }
+        SogpArgs r = a;
+        r.fy[0] = h->fcr.as<double>(); r.fy[1] = h->fcg.as<double>(); r.fy[2] = h->fcb.as<double>();
+        r.dout = 3;
+        r.forig = h->perm_rgb.as<int32_t>();
+        r.s20 = c.rgb_s0; r.eps_tol = c.rgb_eps_tol;
+        r.nbv = h->r_nbv.as<int32_t>(); r.flags = h->r_flags.as<int32_t>();
+        r.o_alpha[0] = h->r_alpha0.as<double>(); r.o_alpha[1] = h->r_alpha1.as<double>(); r.o_alpha[2] = h->r_alpha2.as<double>();
+        r.o_b1 = h->r_b1.as<double>(); r.o_b2 = h->r_b2.as<double>();
+        r.o_idx = h->r_bidx.as<int32_t>();
+        r.dumpC = r.dumpQ = nullptr;
+        r.stats = h->kstats_rgb.as<unsigned long long>();
+        {
+            int rc = run_buckets(h, r, need_ld, PL, lo, nullptr);
+            if (rc) return rc;
+        }
+        h->have_rgb = true;
+        size_t t2b = tm.mark();
+        tm.span(&h->stats.ms_fit_rgb, t2, t2b);
+    }
     // pack the parameters on the device: what the host fetches is sum(nbv) entries, not capacity per patch
     CK(h->bv_off.reserve((PLa + 1) * sizeof(int64_t)));
     CK(h->nonempty.reserve((PLa + 1) * sizeof(int64_t)));
@@ -256,6 +321,11 @@ int read_fit_stats(gpc_handle* h) {
     gpc_stats& s = h->stats;
     s.n_add = k[0]; s.n_first = k[1]; s.n_sparse = k[2]; s.n_full = k[3]; s.n_del_cap = k[4]; s.n_del_geo = k[5];
     s.sum_n = k[6]; s.sum_n2_common = k[7]; s.sum_n2_sparse = k[8]; s.sum_n2_full = k[9]; s.sum_n2_del = k[10];
+    if (h->have_rgb) {
+        CK(cudaMemcpyAsync(k, h->kstats_rgb.p, sizeof(k), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        s.rgb_n_sparse = k[2]; s.rgb_n_full = k[3]; s.rgb_n_del_cap = k[4]; s.rgb_n_del_geo = k[5]; s.rgb_sum_n2_common = k[7];
+    }
     return GPC_OK;
 }
 
@@ -294,6 +364,13 @@ int run_decode(gpc_handle* h, bool want_cloud, bool want_heights, StageTimer& tm
         a.rgbmean = h->rgbmean.as<double>() + 3 * h->patch_lo;
     } else {
         a.quat = a.mean = a.rgbmean = nullptr;
+    }
+    a.rgb_nbv = nullptr;
+    a.rgb_alpha[0] = a.rgb_alpha[1] = a.rgb_alpha[2] = a.rgb_b1 = a.rgb_b2 = nullptr;
+    if (h->have_rgb && h->have_frames) {
+        a.rgb_nbv = h->r_nbv.as<int32_t>();
+        a.rgb_alpha[0] = h->r_alpha0.as<double>(); a.rgb_alpha[1] = h->r_alpha1.as<double>(); a.rgb_alpha[2] = h->r_alpha2.as<double>();
+        a.rgb_b1 = h->r_b1.as<double>(); a.rgb_b2 = h->r_b2.as<double>();
     }
     a.res = c.res; a.sz = c.sz; a.p0 = c.sigmaf_sq; a.cl = kernel_cl(c);
     a.out32 = want_cloud ? h->out32.as<uint8_t>() : nullptr;
@@ -548,6 +625,9 @@ int gpc_config_default(gpc_config* c) {
     c->shard_rank = 0;
     c->shard_count = 1;
     c->keep_state = 0;
+    c->rgb = 0;                      // next-row N1, opt-in
+    c->rgb_s0 = (double)1e2f;        // sparse_gp_field.h:43
+    c->rgb_eps_tol = (double)1e-4f;  // sparse_gp_field.hpp:16
     return GPC_OK;
 }
 
@@ -581,7 +661,8 @@ void gpc_destroy(gpc_handle* h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->cloud, &h->off, &h->x1, &h->x2, &h->y, &h->perm, &h->patch_of, &h->fx1, &h->fx2, &h->fy, &h->draws,
                       &h->roff, &h->rnd, &h->scan_tmp, &h->small, &h->nbv, &h->flags, &h->alpha, &h->b1, &h->b2, &h->bidx,
-                      &h->dumpC, &h->dumpQ, &h->queue0, &h->queue1, &h->hand0, &h->hand1, &h->spill, &h->qcount, &h->kstats, &h->bv_off, &h->palpha, &h->pb1, &h->pb2, &h->pidx, &h->nonempty, &h->slot, &h->out32,
+                      &h->dumpC, &h->dumpQ, &h->queue0, &h->queue1, &h->hand0, &h->hand1, &h->spill, &h->qcount, &h->kstats, &h->bv_off, &h->palpha, &h->pb1, &h->pb2, &h->pidx, &h->perm_rgb, &h->fcr, &h->fcg, &h->fcb, &h->r_nbv, &h->r_flags,
+                      &h->r_alpha0, &h->r_alpha1, &h->r_alpha2, &h->r_b1, &h->r_b2, &h->r_bidx, &h->kstats_rgb, &h->nonempty, &h->slot, &h->out32,
                       &h->heights, &h->quat, &h->mean, &h->rgbmean, &h->Rm, &h->center, &h->code, &h->ncand, &h->owner,
                       &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
                       &h->ovals2, &h->sort_tmp, &h->flags64, &h->ex, &h->leaf_of, &h->leaf_start, &h->leaf_code_a, &h->spt,
@@ -634,6 +715,7 @@ int gpc_fit_patches(gpc_handle* h, int64_t P, const int64_t* off, const double* 
     h->n_in = S;
     h->have_frames = false;
     h->have_binning = false;
+    h->have_rgb = false;
     int rc = run_fit(h, tm);
     if (rc) return rc;
     size_t tC = tm.mark();
@@ -839,6 +921,57 @@ int gpc_get_params(gpc_handle* h, int32_t* nbv, int64_t* bv_off, int32_t* bv_ind
     return GPC_OK;
 }
 
+int gpc_get_params_rgb(gpc_handle* h, int32_t* nbv, int64_t* bv_off, int32_t* bv_index, double* bv1, double* bv2, double* alpha3,
+                       int32_t* perm, int64_t* n_bv_total_rgb) {
+    if (!h) return GPC_ERR_INVALID;
+    if (!h->have_rgb) return fail(h, GPC_ERR_STATE, "no RGB field GP held by the handle (gpc_config.rgb = 1 and a compress are needed)");
+    CK(cudaSetDevice(h->cfg.device));
+    const int64_t PL = h->patch_hi - h->patch_lo;
+    const int cap = h->cfg.capacity;
+    std::vector<int32_t> nb(PL);
+    if (PL > 0) CK(cudaMemcpy(nb.data(), h->r_nbv.p, PL * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    std::vector<int64_t> bo(PL + 1, 0);
+    for (int64_t p = 0; p < PL; p++) bo[p + 1] = bo[p] + nb[p];
+    if (n_bv_total_rgb) *n_bv_total_rgb = bo[PL];
+    if (nbv) std::memcpy(nbv, nb.data(), PL * sizeof(int32_t));
+    if (bv_off) std::memcpy(bv_off, bo.data(), (PL + 1) * sizeof(int64_t));
+    // results of a next-row feature: a plain strided copy + host compaction is enough here
+    auto fetch = [&](const DevBuf& src, size_t esz, std::vector<uint8_t>& tmp) -> int {
+        tmp.resize((size_t)std::max<int64_t>(PL, 1) * cap * esz);
+        if (PL > 0) CK(cudaMemcpy(tmp.data(), src.p, (size_t)PL * cap * esz, cudaMemcpyDeviceToHost));
+        return GPC_OK;
+    };
+    std::vector<uint8_t> t0, t1, t2;
+    int rc;
+    if (bv_index) {
+        if ((rc = fetch(h->r_bidx, 4, t0))) return rc;
+        for (int64_t p = 0; p < PL; p++) std::memcpy(bv_index + bo[p], t0.data() + (size_t)p * cap * 4, (size_t)nb[p] * 4);
+    }
+    if (bv1) {
+        if ((rc = fetch(h->r_b1, 8, t0))) return rc;
+        for (int64_t p = 0; p < PL; p++) std::memcpy(bv1 + bo[p], t0.data() + (size_t)p * cap * 8, (size_t)nb[p] * 8);
+    }
+    if (bv2) {
+        if ((rc = fetch(h->r_b2, 8, t0))) return rc;
+        for (int64_t p = 0; p < PL; p++) std::memcpy(bv2 + bo[p], t0.data() + (size_t)p * cap * 8, (size_t)nb[p] * 8);
+    }
+    if (alpha3) {
+        if ((rc = fetch(h->r_alpha0, 8, t0)) || (rc = fetch(h->r_alpha1, 8, t1)) || (rc = fetch(h->r_alpha2, 8, t2))) return rc;
+        const double *a0 = (const double*)t0.data(), *a1 = (const double*)t1.data(), *a2 = (const double*)t2.data();
+        for (int64_t p = 0; p < PL; p++)
+            for (int i = 0; i < nb[p]; i++) {
+                alpha3[3 * (bo[p] + i) + 0] = a0[p * cap + i];
+                alpha3[3 * (bo[p] + i) + 1] = a1[p * cap + i];
+                alpha3[3 * (bo[p] + i) + 2] = a2[p * cap + i];
+            }
+    }
+    if (perm && h->s_count) {
+        std::memset(perm, 0xff, h->n_claimed * sizeof(int32_t));
+        CK(cudaMemcpy(perm + h->s_begin, h->perm_rgb.as<int32_t>() + h->s_begin, h->s_count * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    }
+    return GPC_OK;
+}
+
 int gpc_get_state(gpc_handle* h, int64_t patch, double* C, double* Q) {
     if (!h) return GPC_ERR_INVALID;
     if (!h->have_fit || !h->cfg.keep_state) return fail(h, GPC_ERR_STATE, "gpc_get_state needs a fit made with keep_state");
@@ -900,6 +1033,7 @@ int gpc_set_params(gpc_handle* h, int64_t P, const int32_t* nbv, const double* b
     h->patch_hi = hi;
     h->have_fit = true;
     h->have_binning = false;
+    h->have_rgb = false;
     h->n_bv_total = -1;
     h->params_packed = false;
     return GPC_OK;

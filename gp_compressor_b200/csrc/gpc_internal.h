@@ -92,7 +92,10 @@ void launch_patch_draws(const int64_t* off, int64_t n_patches, int mult, int64_t
 // perm (patch-local) for every patch; rnd holds the stream starting at the handle's offset
 void launch_shuffle(const int64_t* off, int64_t n_patches, const int64_t* roff, const uint32_t* rnd,
                     int do_shuffle, int32_t* perm, int32_t* patch_of, int64_t s_begin, int64_t s_count,
-                    int64_t max_patch_points, cudaStream_t s);
+                    int64_t max_patch_points, int second, cudaStream_t s);
+void launch_gather_rgb_stream(const int64_t* off, const int32_t* patch_of, const int32_t* perm, const double* x1, const double* x2,
+                              const uint32_t* rgb, const double* rgbmean, int64_t first_patch, int64_t s_begin, int64_t s_count,
+                              double* fx1, double* fx2, double* fr, double* fg, double* fb, cudaStream_t s);
 void launch_gather_stream(const int64_t* off, const int32_t* patch_of, const int32_t* perm, const double* x1,
                           const double* x2, const double* y, int64_t s_begin, int64_t s_count, double* fx1,
                           double* fx2, double* fy, cudaStream_t s);
@@ -100,7 +103,9 @@ void launch_gather_stream(const int64_t* off, const int32_t* patch_of, const int
 // ---- K7: SOGP fit ---------------------------------------------------------------------
 struct SogpArgs {
     const int64_t* off;      // n_patches + 1 stream offsets (global patch numbering)
-    const double *fx1, *fx2, *fy;  // fit stream in add order (already shuffled)
+    const double *fx1, *fx2;       // fit stream in add order (already shuffled)
+    const double* fy[3];           // outputs: heights (dout 1) or centred r,g,b (dout 3)
+    int dout;
     const int32_t* forig;    // patch-local original position of each stream element
     const int32_t* patch_ids;  // patches to process (nullptr: first_patch + blockIdx.x)
     int64_t first_patch;
@@ -112,7 +117,8 @@ struct SogpArgs {
     int64_t out_first;
     int32_t* nbv;
     int32_t* flags;
-    double *o_alpha, *o_b1, *o_b2;
+    double* o_alpha[3];
+    double *o_b1, *o_b2;
     int32_t* o_idx;
     double *dumpC, *dumpQ;   // optional, (patch - out_first) * capacity^2
     int32_t* queue;          // overflow queue for the next bucket (nullptr: overflow impossible)
@@ -124,7 +130,8 @@ struct SogpArgs {
 };
 // bucket b supports ld <= {16, 32, 64, 118, 202}; bucket 4 keeps its state in global memory
 int sogp_bucket_ld(int bucket);
-size_t sogp_handoff_slot_bytes(int bucket);
+size_t sogp_handoff_slot_bytes(int bucket, int dout);
+int sogp_next_bucket(int bucket, int dout);
 size_t sogp_spill_bytes_per_patch();
 cudaError_t launch_sogp_fit(int bucket, const SogpArgs& a, cudaStream_t s);
 
@@ -136,6 +143,9 @@ struct PredictArgs {
     int stride;                  // parameter stride per patch (capacity)
     const double *alpha, *b1, *b2;
     const double *quat, *mean, *rgbmean;  // may be nullptr (identity frame)
+    // RGB field GP (may be nullptr): per patch nbv, alpha[3], BVs with the same stride
+    const int32_t* rgb_nbv;
+    const double *rgb_alpha[3], *rgb_b1, *rgb_b2;
     double res;
     int sz;
     double p0, cl;

@@ -47,21 +47,33 @@ __global__ void __launch_bounds__(PRED_T) predict_grid_kernel(PredictArgs a) {
     double* al = sm;
     double* b1 = al + N;
     double* b2 = b1 + N;
-    __shared__ double R[9], mean[3];
+    // RGB field GP of the patch (sparse_gp_field::predict, sparse_gp_field.hpp:284-320): its own BVs, 3 alphas
+    const int NR = a.rgb_nbv ? a.rgb_nbv[p] : 0;
+    double* ra0 = b2 + N;
+    double* ra1 = ra0 + NR;
+    double* ra2 = ra1 + NR;
+    double* rb1 = ra2 + NR;
+    double* rb2 = rb1 + NR;
+    __shared__ double R[9], mean[3], cmean[3];
     __shared__ unsigned int rgba;
     const int t = threadIdx.x;
     const int64_t pb = p * a.stride;
     for (int i = t; i < N; i += PRED_T) { al[i] = a.alpha[pb + i]; b1[i] = a.b1[pb + i]; b2[i] = a.b2[pb + i]; }
+    for (int i = t; i < NR; i += PRED_T) {
+        ra0[i] = a.rgb_alpha[0][pb + i]; ra1[i] = a.rgb_alpha[1][pb + i]; ra2[i] = a.rgb_alpha[2][pb + i];
+        rb1[i] = a.rgb_b1[pb + i]; rb2[i] = a.rgb_b2[pb + i];
+    }
     if (t == 0) {
         if (a.quat) {
             quat_to_rot(a.quat + 4 * p, R);
-            for (int d = 0; d < 3; d++) mean[d] = a.mean[3 * p + d];
+            for (int d = 0; d < 3; d++) { mean[d] = a.mean[3 * p + d]; cmean[d] = a.rgbmean[3 * p + d]; }
             unsigned int r = flatten_color(a.rgbmean[3 * p + 0]), g = flatten_color(a.rgbmean[3 * p + 1]),
                          b = flatten_color(a.rgbmean[3 * p + 2]);
             rgba = b | (g << 8) | (r << 16) | (255u << 24);
         } else {
             for (int d = 0; d < 9; d++) R[d] = (d % 4 == 0) ? 1.0 : 0.0;
             mean[0] = mean[1] = mean[2] = 0.0;
+            cmean[0] = cmean[1] = cmean[2] = 0.0;
             rgba = 255u << 24;
         }
     }
@@ -94,9 +106,25 @@ __global__ void __launch_bounds__(PRED_T) predict_grid_kernel(PredictArgs a) {
                 double v = __dadd_rn(__dadd_rn(__dmul_rn(R[d * 3 + 0], f), __dmul_rn(R[d * 3 + 1], X0)), __dmul_rn(R[d * 3 + 2], X1));
                 o[d] = (float)__dadd_rn(v, mean[d]);
             }
+            unsigned int col = rgba;
+            if (a.rgb_nbv) {  // c = C_star.row(m) + RGB_means[i], gp_compressor.cpp:367
+                double c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0};
+                for (int i = 0; i < NR; i++) {
+                    const double k = rbf(X0, X1, rb1[i], rb2[i], a.p0, a.cl);
+                    c0[i & 3] = fma(ra0[i], k, c0[i & 3]);
+                    c1[i & 3] = fma(ra1[i], k, c1[i & 3]);
+                    c2[i & 3] = fma(ra2[i], k, c2[i & 3]);
+                }
+                const double fr = __dadd_rn(__dadd_rn(c0[0], c0[1]), __dadd_rn(c0[2], c0[3]));
+                const double fg = __dadd_rn(__dadd_rn(c1[0], c1[1]), __dadd_rn(c1[2], c1[3]));
+                const double fb = __dadd_rn(__dadd_rn(c2[0], c2[1]), __dadd_rn(c2[2], c2[3]));
+                const unsigned int rr = flatten_color(__dadd_rn(fr, cmean[0])), gg = flatten_color(__dadd_rn(fg, cmean[1])),
+                                   bb = flatten_color(__dadd_rn(fb, cmean[2]));
+                col = bb | (gg << 8) | (rr << 16) | (255u << 24);
+            }
             float4* dst = reinterpret_cast<float4*>(a.out32 + (size_t)(base + m) * GPC_POINT_BYTES);
             dst[0] = make_float4(o[0], o[1], o[2], 1.0f);
-            dst[1] = make_float4(__uint_as_float(rgba), 0.0f, 0.0f, 0.0f);
+            dst[1] = make_float4(__uint_as_float(col), 0.0f, 0.0f, 0.0f);
         }
     }
 }
@@ -142,7 +170,7 @@ __global__ void __launch_bounds__(128) predict_points_kernel(const double* __res
 
 void launch_predict_grid(const PredictArgs& a, cudaStream_t s) {
     if (a.n_patches <= 0) return;
-    size_t smem = (size_t)3 * a.stride * sizeof(double);
+    size_t smem = (size_t)8 * a.stride * sizeof(double);
     predict_grid_kernel<<<(unsigned)a.n_patches, PRED_T, smem, s>>>(a);
     g_launches++;
 }

@@ -31,7 +31,8 @@ namespace {
 
 constexpr int NCNT = 10;  // first sparse full dcap dgeo sumn n2c n2s n2f n2d
 
-__host__ __device__ constexpr int slot_doubles(int ld) { return 2 + NCNT + 3 * ld + 2 * ld * ld + (ld + 1) / 2; }
+// hand-off slot: header (2) | counters | alpha[dout][ld] | b1[ld] | b2[ld] | C[ld*ld] | Q[ld*ld] | bidx[ld] (ints)
+__host__ __device__ constexpr int slot_doubles(int ld, int dout = 1) { return 2 + NCNT + (2 + dout) * ld + 2 * ld * ld + (ld + 1) / 2; }
 
 struct Counters {
     unsigned long long c[NCNT];
@@ -91,11 +92,14 @@ __device__ __forceinline__ int warp_first_min(double sc, int idx, double* minsco
 constexpr int W_N = 16;    // N + 1 <= 16
 constexpr int W_LD = 18;
 
-struct __align__(16) StagedPoint { double x1, x2, y; int orig, pad; };
+template <int DOUT>
+struct __align__(16) StagedPointT { double x1, x2, y[DOUT]; int orig, pad; };
+typedef StagedPointT<1> StagedPoint;
+template <int DOUT>
 struct WarpSmem {
     double C[W_N * W_LD], Q[W_N * W_LD];
     double kv[W_N], sv[W_N], ev[W_N];
-    StagedPoint pts[32];          // the next 32 points of the patch's stream, loaded coalesced
+    StagedPointT<DOUT> pts[32];   // the next 32 points of the patch's stream, loaded coalesced
     unsigned long long cnt[NCNT];
 };
 
@@ -139,8 +143,11 @@ __device__ __forceinline__ double row4_contig(const double* row, const double* k
     return __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
 }
 
-__global__ void __launch_bounds__(32, 32) sogp_fit_warp_kernel(SogpArgs a) {
-    __shared__ __align__(16) WarpSmem sm;
+// DOUT = 1: sparse_gp (heights).  DOUT = 3: sparse_gp_field (RGB): alpha has three columns, the capacity score is
+// |alpha_i|^2 / (Q_ii + C_ii) (sparse_gp_field.hpp:187) and delete_bv updates alpha with alphastar * ((q*+c*)(Qs+Cs)) (:250-253).
+template <int DOUT>
+__global__ void __launch_bounds__(32, DOUT == 1 ? 32 : 20) sogp_fit_warp_kernel(SogpArgs a) {
+    __shared__ __align__(16) WarpSmem<DOUT> sm;
     double* const C = sm.C;
     double* const Q = sm.Q;
     const int lane = threadIdx.x;
@@ -160,7 +167,9 @@ __global__ void __launch_bounds__(32, 32) sogp_fit_warp_kernel(SogpArgs a) {
     __syncwarp();
     const double kstar = a.p0, s20 = a.s20, p0 = a.p0, cl = a.cl, eps_tol = a.eps_tol;
     const int cap = a.capacity, ldmax = a.ld;
-    double alpha = 0.0, b1 = 0.0, b2 = 0.0;  // lane l < 16 owns entry l
+    double alpha[DOUT], b1 = 0.0, b2 = 0.0;  // lane l < 16 owns entry l
+#pragma unroll
+    for (int c = 0; c < DOUT; c++) alpha[c] = 0.0;
     int bidx = -1;
     int N = 0;
     unsigned int run = 0;  // sparse points at the current N, folded into sm.cnt when N changes
@@ -170,26 +179,31 @@ __global__ void __launch_bounds__(32, 32) sogp_fit_warp_kernel(SogpArgs a) {
 
     const double* const gx1 = a.fx1 + o;
     const double* const gx2 = a.fx2 + o;
-    const double* const gy = a.fy + o;
+    const double* gy[DOUT];
+#pragma unroll
+    for (int c = 0; c < DOUT; c++) gy[c] = a.fy[c] + o;
     const int32_t* const go = a.forig + o;
     for (int tt = 0; tt < n; ++tt) {
         if ((tt & 31) == 0) {  // stage the next 32 points: one coalesced load per lane
             __syncwarp();
             const int i = tt + lane;
             if (i < n) {
-                StagedPoint sp;
-                sp.x1 = gx1[i]; sp.x2 = gx2[i]; sp.y = gy[i]; sp.orig = go[i]; sp.pad = 0;
+                StagedPointT<DOUT> sp;
+                sp.x1 = gx1[i]; sp.x2 = gx2[i]; sp.orig = go[i]; sp.pad = 0;
+#pragma unroll
+                for (int c = 0; c < DOUT; c++) sp.y[c] = gy[c][i];
                 sm.pts[lane] = sp;
             }
             __syncwarp();
         }
-        const StagedPoint pt = sm.pts[tt & 31];
-        const double x1 = pt.x1, x2 = pt.x2, y = pt.y;
+        const StagedPointT<DOUT> pt = sm.pts[tt & 31];
+        const double x1 = pt.x1, x2 = pt.x2;
         const int orig = pt.orig;
         if (N == 0) {  // sparse_gp.hpp:100-110
             if (lane == 0) {
                 const double d = __dadd_rn(kstar, s20);
-                alpha = __ddiv_rn(y, d);
+#pragma unroll
+                for (int c = 0; c < DOUT; c++) alpha[c] = __ddiv_rn(pt.y[c], d);
                 C[0] = __ddiv_rn(-1.0, d);
                 Q[0] = __ddiv_rn(1.0, kstar);
                 b1 = x1; b2 = x2; bidx = orig;
@@ -210,19 +224,24 @@ __global__ void __launch_bounds__(32, 32) sogp_fit_warp_kernel(SogpArgs a) {
         if (r < N) rv = row4_padded16(Mrow, sm.kv, N);
         const double el = __shfl_down_sync(0xffffffffu, rv, 16);
         // m = alpha'k, k'Ck, k'e_hat: one product per lane, shared butterfly
-        double pm = act ? fma(alpha, kl, 0.0) : 0.0;
+        double pm[DOUT];
+#pragma unroll
+        for (int c = 0; c < DOUT; c++) pm[c] = act ? fma(alpha[c], kl, 0.0) : 0.0;
         double pc = act ? fma(kl, rv, 0.0) : 0.0;
         double pe = act ? fma(kl, el, 0.0) : 0.0;
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
-            pm = __dadd_rn(pm, shfl_xor_d(pm, off));
+#pragma unroll
+            for (int c = 0; c < DOUT; c++) pm[c] = __dadd_rn(pm[c], shfl_xor_d(pm[c], off));
             pc = __dadd_rn(pc, shfl_xor_d(pc, off));
             pe = __dadd_rn(pe, shfl_xor_d(pe, off));
         }
         const double s2 = __dadd_rn(kstar, pc);
         const double den = __dadd_rn(s20, s2);
         const double rr = __ddiv_rn(-1.0, den);               // gaussian_noise.cpp:15-18
-        const double q = __ddiv_rn(__dadd_rn(y, -pm), den);   // gaussian_noise.cpp:9-12
+        double q[DOUT];                                       // gaussian_noise.cpp:9-12 / gaussian_noise_3d.cpp:10-13
+#pragma unroll
+        for (int c = 0; c < DOUT; c++) q[c] = __ddiv_rn(__dadd_rn(pt.y[c], -pm[c]), den);
         double gamma = __dadd_rn(kstar, -pe);                 // :144
         if (gamma < tiny12()) gamma = 0.0;
         if (gamma < eps_tol) {
@@ -231,7 +250,10 @@ __global__ void __launch_bounds__(32, 32) sogp_fit_warp_kernel(SogpArgs a) {
             const double eta = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn(gamma, rr)));
             const double sh = act ? __dadd_rn(rv, el) : 0.0;
             if (lane < W_N) sm.sv[lane] = sh;  // zero beyond N: pad columns stay exact zeros below
-            if (act) alpha = __dadd_rn(alpha, __dmul_rn(sh, __dmul_rn(q, eta)));
+            if (act) {
+#pragma unroll
+                for (int c = 0; c < DOUT; c++) alpha[c] = __dadd_rn(alpha[c], __dmul_rn(sh, __dmul_rn(q[c], eta)));
+            }
             __syncwarp();
             const double re = __dmul_rn(rr, eta);
             if (r < N) {
@@ -261,7 +283,7 @@ __global__ void __launch_bounds__(32, 32) sogp_fit_warp_kernel(SogpArgs a) {
             int pos = 0;
             if (lane == 0) pos = atomicAdd(a.queue_count, 1);
             pos = __shfl_sync(0xffffffffu, pos, 0);
-            double* slot = a.handoff_out + (size_t)pos * slot_doubles(W_N);
+            double* slot = a.handoff_out + (size_t)pos * slot_doubles(W_N, DOUT);
             __syncwarp();
             if (lane == 0) {
                 a.queue[pos] = (int32_t)patch;
@@ -271,13 +293,15 @@ __global__ void __launch_bounds__(32, 32) sogp_fit_warp_kernel(SogpArgs a) {
             }
             double* v = slot + 2 + NCNT;
             if (lane < W_N) {
-                v[lane] = alpha; v[W_N + lane] = b1; v[2 * W_N + lane] = b2;
-                reinterpret_cast<int*>(v + 3 * W_N + 2 * W_N * W_N)[lane] = bidx;
+#pragma unroll
+                for (int c = 0; c < DOUT; c++) v[c * W_N + lane] = alpha[c];
+                v[DOUT * W_N + lane] = b1; v[(DOUT + 1) * W_N + lane] = b2;
+                reinterpret_cast<int*>(v + (DOUT + 2) * W_N + 2 * W_N * W_N)[lane] = bidx;
             }
             for (int e = lane; e < W_N * W_N; e += 32) {
                 const int j = e / W_N, i = e - j * W_N;
-                v[3 * W_N + e] = C[i * W_LD + j];
-                v[3 * W_N + W_N * W_N + e] = Q[i * W_LD + j];
+                v[(DOUT + 2) * W_N + e] = C[i * W_LD + j];
+                v[(DOUT + 2) * W_N + W_N * W_N + e] = Q[i * W_LD + j];
             }
             return;
         }
@@ -287,12 +311,14 @@ __global__ void __launch_bounds__(32, 32) sogp_fit_warp_kernel(SogpArgs a) {
         if (act) {
             sm.sv[lane] = rv;
             sm.ev[lane] = el;
-            alpha = __dadd_rn(alpha, __dmul_rn(q, rv));
+#pragma unroll
+            for (int c = 0; c < DOUT; c++) alpha[c] = __dadd_rn(alpha[c], __dmul_rn(q[c], rv));
         }
         if (lane == N) {
             sm.sv[N] = 1.0;
             sm.ev[N] = -1.0;
-            alpha = __dadd_rn(0.0, __dmul_rn(q, 1.0));
+#pragma unroll
+            for (int c = 0; c < DOUT; c++) alpha[c] = __dadd_rn(0.0, __dmul_rn(q[c], 1.0));
             b1 = x1; b2 = x2; bidx = orig;
         }
         __syncwarp();
@@ -317,7 +343,9 @@ __global__ void __launch_bounds__(32, 32) sogp_fit_warp_kernel(SogpArgs a) {
                 double sc = 0.0;
                 if (lane < N) {
                     const double qii = Q[lane * W_LD + lane];
-                    sc = (phase == 0) ? __ddiv_rn(__dmul_rn(alpha, alpha), __dadd_rn(qii, C[lane * W_LD + lane])) : __ddiv_rn(1.0, qii);
+                    double num = __dmul_rn(alpha[0], alpha[0]);
+                    if (DOUT == 3) num = __dadd_rn(num, __dadd_rn(__dmul_rn(alpha[DOUT > 1 ? 1 : 0], alpha[DOUT > 1 ? 1 : 0]), __dmul_rn(alpha[DOUT > 2 ? 2 : 0], alpha[DOUT > 2 ? 2 : 0])));
+                    sc = (phase == 0) ? __ddiv_rn(num, __dadd_rn(qii, C[lane * W_LD + lane])) : __ddiv_rn(1.0, qii);
                 }
                 if (phase == 1) {
                     // exact shortcut: the scan deletes iff score_0 is not NaN and some score is < 1e-9f
@@ -338,13 +366,14 @@ __global__ void __launch_bounds__(32, 32) sogp_fit_warp_kernel(SogpArgs a) {
                     repc = C[L * W_LD + src]; repq = Q[L * W_LD + src];
                 }
                 const double cstar = C[loc * W_LD + loc], qstar = Q[loc * W_LD + loc];
-                const double astar = __shfl_sync(0xffffffffu, alpha, loc);
-                const double aL = __shfl_sync(0xffffffffu, alpha, L);
+                double astar[DOUT], aL[DOUT];
+#pragma unroll
+                for (int c = 0; c < DOUT; c++) { astar[c] = __shfl_sync(0xffffffffu, alpha[c], loc); aL[c] = __shfl_sync(0xffffffffu, alpha[c], L); }
                 const double b1L = __shfl_sync(0xffffffffu, b1, L), b2L = __shfl_sync(0xffffffffu, b2, L);
                 const int idL = __shfl_sync(0xffffffffu, bidx, L);
                 __syncwarp();
                 const double qcs = __dadd_rn(qstar, cstar);
-                const double coef = __ddiv_rn(astar, qcs);
+                const double coef = (DOUT == 1) ? __ddiv_rn(astar[0], qcs) : 0.0;
                 const double iq = __ddiv_rn(1.0, qstar), iqc = __ddiv_rn(1.0, qcs);
                 if (lane < N) {
                     if (lane < M) {
@@ -354,14 +383,22 @@ __global__ void __launch_bounds__(32, 32) sogp_fit_warp_kernel(SogpArgs a) {
                             if (lane == loc) { b1 = b1L; b2 = b2L; bidx = idL; }
                         }
                         const double qci = __dadd_rn(qsi, csi);
-                        const double ai = (lane == loc) ? aL : alpha;
-                        alpha = __dadd_rn(ai, -__dmul_rn(coef, qci));
+#pragma unroll
+                        for (int c = 0; c < DOUT; c++) {
+                            const double ai = (lane == loc) ? aL[c] : alpha[c];
+                            alpha[c] = (DOUT == 1) ? __dadd_rn(ai, -__dmul_rn(coef, qci))
+                                                   : __dadd_rn(ai, -__dmul_rn(astar[c], __dmul_rn(qcs, qci)));
+                        }
                         sm.sv[lane] = qsi;   // Qstar
                         sm.ev[lane] = qci;   // Qstar + Cstar
                     }
                     C[L * W_LD + lane] = 0.0; C[lane * W_LD + L] = 0.0;
                     Q[L * W_LD + lane] = 0.0; Q[lane * W_LD + L] = 0.0;
-                    if (lane == L) { alpha = 0.0; b1 = 0.0; b2 = 0.0; bidx = -1; }
+                    if (lane == L) {
+#pragma unroll
+                        for (int c = 0; c < DOUT; c++) alpha[c] = 0.0;
+                        b1 = 0.0; b2 = 0.0; bidx = -1;
+                    }
                 }
                 __syncwarp();
                 if (r < M) {
@@ -393,7 +430,8 @@ __global__ void __launch_bounds__(32, 32) sogp_fit_warp_kernel(SogpArgs a) {
     }
     const int64_t ob = op * cap;
     if (lane < N) {
-        a.o_alpha[ob + lane] = alpha;
+#pragma unroll
+        for (int c = 0; c < DOUT; c++) a.o_alpha[c][ob + lane] = alpha[c];
         a.o_b1[ob + lane] = b1;
         a.o_b2[ob + lane] = b2;
         a.o_idx[ob + lane] = bidx;
@@ -487,7 +525,7 @@ __global__ void __launch_bounds__(64, 10) sogp_fit_pair_kernel(SogpArgs a) {
     }
     const double* const gx1 = a.fx1 + o;
     const double* const gx2 = a.fx2 + o;
-    const double* const gy = a.fy + o;
+    const double* const gy = a.fy[0] + o;
     const int32_t* const go = a.forig + o;
     const bool w0l0 = (t == 0);
 
@@ -497,13 +535,13 @@ __global__ void __launch_bounds__(64, 10) sogp_fit_pair_kernel(SogpArgs a) {
             const int i = (tt & ~31) + lane;
             if (i < n) {
                 StagedPoint sp;
-                sp.x1 = gx1[i]; sp.x2 = gx2[i]; sp.y = gy[i]; sp.orig = go[i]; sp.pad = 0;
+                sp.x1 = gx1[i]; sp.x2 = gx2[i]; sp.y[0] = gy[i]; sp.orig = go[i]; sp.pad = 0;
                 sm.pts[mat][lane] = sp;
             }
             __syncwarp();
         }
         const StagedPoint pt = sm.pts[mat][tt & 31];
-        const double x1 = pt.x1, x2 = pt.x2, y = pt.y;
+        const double x1 = pt.x1, x2 = pt.x2, y = pt.y[0];
         const int orig = pt.orig;
         if (N == 0) {  // sparse_gp.hpp:100-110
             const double d = __dadd_rn(kstar, s20);
@@ -724,7 +762,7 @@ __global__ void __launch_bounds__(64, 10) sogp_fit_pair_kernel(SogpArgs a) {
     }
     const int64_t ob = op * cap;
     if (mat == 0 && lane < N) {
-        a.o_alpha[ob + lane] = alpha;
+        a.o_alpha[0][ob + lane] = alpha;
         a.o_b1[ob + lane] = b1;
         a.o_b2[ob + lane] = b2;
         a.o_idx[ob + lane] = bidx;
@@ -742,23 +780,24 @@ __global__ void __launch_bounds__(64, 10) sogp_fit_pair_kernel(SogpArgs a) {
 // =====================================================================================
 // Buckets 1-3: NT = 2*RB threads per patch, LD constexpr
 // =====================================================================================
-template <int LD>
+template <int LD, int DOUT>
 struct Smem {
     double* base;
-    static constexpr int kDoubles = 2 * LD * LD + 9 * LD + 8;
+    static constexpr int V = 2 * LD * LD;                      // start of the vectors
+    static constexpr int kDoubles = V + (8 + DOUT) * LD + 16;
     __device__ __forceinline__ double* C() const { return base; }
     __device__ __forceinline__ double* Q() const { return base + LD * LD; }
-    __device__ __forceinline__ double* alpha() const { return base + 2 * LD * LD; }
-    __device__ __forceinline__ double* b1() const { return base + 2 * LD * LD + LD; }
-    __device__ __forceinline__ double* b2() const { return base + 2 * LD * LD + 2 * LD; }
-    __device__ __forceinline__ double* kv() const { return base + 2 * LD * LD + 3 * LD; }
-    __device__ __forceinline__ double* ck() const { return base + 2 * LD * LD + 4 * LD; }
-    __device__ __forceinline__ double* ev() const { return base + 2 * LD * LD + 5 * LD; }
-    __device__ __forceinline__ double* sv() const { return base + 2 * LD * LD + 6 * LD; }
-    __device__ __forceinline__ double* qsv() const { return base + 2 * LD * LD + 7 * LD; }
-    __device__ __forceinline__ double* qcv() const { return base + 2 * LD * LD + 8 * LD; }
-    __device__ __forceinline__ double* scv() const { return kv(); }                          // deletion scores (k is dead by then)
-    __device__ __forceinline__ double* scal() const { return base + 2 * LD * LD + 9 * LD; }  // CTA-wide scalars
+    __device__ __forceinline__ double* alpha(int c = 0) const { return base + V + c * LD; }
+    __device__ __forceinline__ double* b1() const { return base + V + DOUT * LD; }
+    __device__ __forceinline__ double* b2() const { return base + V + (DOUT + 1) * LD; }
+    __device__ __forceinline__ double* kv() const { return base + V + (DOUT + 2) * LD; }
+    __device__ __forceinline__ double* ck() const { return base + V + (DOUT + 3) * LD; }
+    __device__ __forceinline__ double* ev() const { return base + V + (DOUT + 4) * LD; }
+    __device__ __forceinline__ double* sv() const { return base + V + (DOUT + 5) * LD; }
+    __device__ __forceinline__ double* qsv() const { return base + V + (DOUT + 6) * LD; }
+    __device__ __forceinline__ double* qcv() const { return base + V + (DOUT + 7) * LD; }
+    __device__ __forceinline__ double* scv() const { return kv(); }                               // deletion scores (k is dead by then)
+    __device__ __forceinline__ double* scal() const { return base + V + (8 + DOUT) * LD; }        // 16 CTA-wide scalars
     __device__ __forceinline__ int* bidx() const { return reinterpret_cast<int*>(base + kDoubles); }
 };
 
@@ -766,14 +805,19 @@ struct Smem {
 // shared memory with the "first strict minimum" rule.  MODE 0: alpha_i^2 / (Q_ii + C_ii) (sparse_gp.hpp:213);
 // MODE 1: 1 / Q_ii with the exact shortcut "delete iff score_0 is not NaN and some score < 1e-9f" (:229-236).
 // Contains block barriers: must be reached by all threads.  Returns loc, or -1 when MODE 1 finds nothing to delete.
-template <int LD, int MODE>
-__device__ __forceinline__ int block_argmin(const Smem<LD>& s, int N, int t, int lane) {
+template <int LD, int DOUT, int MODE>
+__device__ __forceinline__ int block_argmin(const Smem<LD, DOUT>& s, int N, int t, int lane) {
     double sc = 0.0;
     if (t < N) {
         const double qii = s.Q()[t * LD + t];
         if (MODE == 0) {
-            const double al = s.alpha()[t];
-            sc = __ddiv_rn(__dmul_rn(al, al), __dadd_rn(qii, s.C()[t * LD + t]));
+            const double a0 = s.alpha(0)[t];
+            double num = __dmul_rn(a0, a0);
+            if (DOUT == 3) {  // alpha.row(i).squaredNorm(), sparse_gp_field.hpp:187
+                const double a1 = s.alpha(DOUT > 1 ? 1 : 0)[t], a2 = s.alpha(DOUT > 2 ? 2 : 0)[t];
+                num = __dadd_rn(num, __dadd_rn(__dmul_rn(a1, a1), __dmul_rn(a2, a2)));
+            }
+            sc = __ddiv_rn(num, __dadd_rn(qii, s.C()[t * LD + t]));
         } else {
             sc = __ddiv_rn(1.0, qii);
         }
@@ -803,15 +847,18 @@ __device__ __forceinline__ int block_argmin(const Smem<LD>& s, int N, int t, int
 
 // sparse_gp::delete_bv, sparse_gp.hpp:252-295.  Uniform across the CTA; ends with a barrier.
 // The three divisions are done by warp 0 only and published through scal[4..6].
-template <int LD, int RB, int NT>
-__device__ __forceinline__ void delete_bv(const Smem<LD>& s, int& N, int loc, int t) {
+template <int LD, int RB, int NT, int DOUT>
+__device__ __forceinline__ void delete_bv(const Smem<LD, DOUT>& s, int& N, int loc, int t) {
     const int L = N - 1, M = N - 1;
     const int lane_ = t & 31, w_ = t >> 5;
     const int irow = 16 * (w_ % (RB / 16)) + (lane_ & 15);
     const int jq = 2 * (w_ / (RB / 16)) + (lane_ >> 4);
     double* const C = s.C();
     double* const Q = s.Q();
-    double csi = 0, qsi = 0, repc = 0, repq = 0, ai = 0, nb1 = 0, nb2 = 0;
+    double csi = 0, qsi = 0, repc = 0, repq = 0, nb1 = 0, nb2 = 0;
+    double ai[DOUT];
+#pragma unroll
+    for (int c = 0; c < DOUT; c++) ai[c] = 0.0;
     int nidx = -1;
     if (t < N) {
         const int src = (t == loc) ? L : t;  // Cs(loc) = Cs(L), Crep(loc) = Crep(L), alpha(loc) = alpha(L)
@@ -819,19 +866,31 @@ __device__ __forceinline__ void delete_bv(const Smem<LD>& s, int& N, int loc, in
         qsi = Q[loc * LD + src];
         repc = C[L * LD + src];
         repq = Q[L * LD + src];
-        ai = s.alpha()[src];
+#pragma unroll
+        for (int c = 0; c < DOUT; c++) ai[c] = s.alpha(c)[src];
         if (t == loc) { nb1 = s.b1()[L]; nb2 = s.b2()[L]; nidx = s.bidx()[L]; }
     }
-    double coef0 = 0.0, iq0 = 0.0, iqc0 = 0.0;
+    // scal[8] = 1/q*, [9] = 1/(q*+c*), [10] = q*+c*, [11..] = alpha* / (q*+c*) (sparse_gp) or alpha* (sparse_gp_field)
+    double coef0[DOUT], iq0 = 0.0, iqc0 = 0.0, qcs0 = 0.0;
+#pragma unroll
+    for (int c = 0; c < DOUT; c++) coef0[c] = 0.0;
     if (w_ == 0) {
-        const double cstar = C[loc * LD + loc], qstar = Q[loc * LD + loc], astar = s.alpha()[loc];
-        const double qcs = __dadd_rn(qstar, cstar);
-        coef0 = __ddiv_rn(astar, qcs);
+        const double cstar = C[loc * LD + loc], qstar = Q[loc * LD + loc];
+        qcs0 = __dadd_rn(qstar, cstar);
+#pragma unroll
+        for (int c = 0; c < DOUT; c++) {
+            const double astar = s.alpha(c)[loc];
+            coef0[c] = (DOUT == 1) ? __ddiv_rn(astar, qcs0) : astar;
+        }
         iq0 = __ddiv_rn(1.0, qstar);
-        iqc0 = __ddiv_rn(1.0, qcs);
+        iqc0 = __ddiv_rn(1.0, qcs0);
     }
     __syncthreads();  // every read of the old state is done
-    if (t == 0) { s.scal()[4] = coef0; s.scal()[5] = iq0; s.scal()[6] = iqc0; }
+    if (t == 0) {
+        s.scal()[8] = iq0; s.scal()[9] = iqc0; s.scal()[10] = qcs0;
+#pragma unroll
+        for (int c = 0; c < DOUT; c++) s.scal()[11 + c] = coef0[c];
+    }
     double qci = 0.0;
     if (t < N) {
         if (t < M) {
@@ -846,11 +905,23 @@ __device__ __forceinline__ void delete_bv(const Smem<LD>& s, int& N, int loc, in
         }
         C[L * LD + t] = 0.0; C[t * LD + L] = 0.0;
         Q[L * LD + t] = 0.0; Q[t * LD + L] = 0.0;
-        if (t == L) { s.alpha()[L] = 0.0; s.b1()[L] = 0.0; s.b2()[L] = 0.0; s.bidx()[L] = -1; }
+        if (t == L) {
+#pragma unroll
+            for (int c = 0; c < DOUT; c++) s.alpha(c)[L] = 0.0;
+            s.b1()[L] = 0.0; s.b2()[L] = 0.0; s.bidx()[L] = -1;
+        }
     }
     __syncthreads();
-    const double coef = s.scal()[4], iq = s.scal()[5], iqc = s.scal()[6];
-    if (t < M) s.alpha()[t] = __dadd_rn(ai, -__dmul_rn(coef, qci));
+    const double iq = s.scal()[8], iqc = s.scal()[9];
+    if (t < M) {
+        const double qcs = s.scal()[10];
+#pragma unroll
+        for (int c = 0; c < DOUT; c++) {
+            const double cf = s.scal()[11 + c];
+            s.alpha(c)[t] = (DOUT == 1) ? __dadd_rn(ai[c], -__dmul_rn(cf, qci))                       // sparse_gp.hpp:285
+                                        : __dadd_rn(ai[c], -__dmul_rn(cf, __dmul_rn(qcs, qci)));      // sparse_gp_field.hpp:250-253
+        }
+    }
     if (irow < M) {
         const double qi = s.qsv()[irow], ci = s.qcv()[irow];
         for (int j = jq; j < M; j += 4) {
@@ -866,13 +937,13 @@ __device__ __forceinline__ void delete_bv(const Smem<LD>& s, int& N, int loc, in
     __syncthreads();
 }
 
-template <int LD, int RB, int NT, int LD_IN, bool SPILL>
+template <int LD, int RB, int NT, int LD_IN, bool SPILL, int DOUT>
 __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
     extern __shared__ double smem_dyn[];
     // SPILL: the state lives in a per-CTA slice of global memory (L2-resident) instead of shared memory;
     // block barriers order the accesses exactly as they do for shared memory.
-    double* const smem_d = SPILL ? a.spill + (size_t)blockIdx.x * (Smem<LD>::kDoubles + LD) : smem_dyn;
-    const Smem<LD> s{smem_d};
+    double* const smem_d = SPILL ? a.spill + (size_t)blockIdx.x * (Smem<LD, DOUT>::kDoubles + LD) : smem_dyn;
+    const Smem<LD, DOUT> s{smem_d};
     double* const C = s.C();
     double* const Q = s.Q();
     // NT = 4*RB threads.  A warp covers 16 rows: lanes 0-15 and 16-31 hold the same rows and split the columns.
@@ -891,7 +962,7 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
         if (t == 0) { a.nbv[op] = 0; a.flags[op] = 0; }
         return;
     }
-    for (int i = t; i < Smem<LD>::kDoubles; i += NT) smem_d[i] = 0.0;
+    for (int i = t; i < Smem<LD, DOUT>::kDoubles; i += NT) smem_d[i] = 0.0;
     for (int i = t; i < LD; i += NT) s.bidx()[i] = -1;
     __syncthreads();
 
@@ -901,37 +972,47 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
     Counters cnt;
     cnt.init();
     if (a.handoff_in) {  // resume a patch that outgrew the previous bucket
-        const double* slot = a.handoff_in + (size_t)blockIdx.x * slot_doubles(LD_IN);
+        const double* slot = a.handoff_in + (size_t)blockIdx.x * slot_doubles(LD_IN, DOUT);
         N = reinterpret_cast<const int*>(slot)[0];
         tt0 = reinterpret_cast<const int*>(slot)[1];
 #pragma unroll
         for (int i = 0; i < NCNT; i++) cnt.c[i] = reinterpret_cast<const unsigned long long*>(slot + 2)[i];
         const double* v = slot + 2 + NCNT;
         for (int i = t; i < LD_IN; i += NT) {
-            s.alpha()[i] = v[i]; s.b1()[i] = v[LD_IN + i]; s.b2()[i] = v[2 * LD_IN + i];
-            s.bidx()[i] = reinterpret_cast<const int*>(v + 3 * LD_IN + 2 * LD_IN * LD_IN)[i];
+#pragma unroll
+            for (int c = 0; c < DOUT; c++) s.alpha(c)[i] = v[c * LD_IN + i];
+            s.b1()[i] = v[DOUT * LD_IN + i]; s.b2()[i] = v[(DOUT + 1) * LD_IN + i];
+            s.bidx()[i] = reinterpret_cast<const int*>(v + (DOUT + 2) * LD_IN + 2 * LD_IN * LD_IN)[i];
         }
         for (int e = t; e < LD_IN * LD_IN; e += NT) {
             const int j = e / LD_IN, i = e - j * LD_IN;
-            C[j * LD + i] = v[3 * LD_IN + e];
-            Q[j * LD + i] = v[3 * LD_IN + LD_IN * LD_IN + e];
+            C[j * LD + i] = v[(DOUT + 2) * LD_IN + e];
+            Q[j * LD + i] = v[(DOUT + 2) * LD_IN + LD_IN * LD_IN + e];
         }
         __syncthreads();
     }
 
-    double nx1 = a.fx1[o + tt0], nx2 = a.fx2[o + tt0], ny = a.fy[o + tt0];
+    double nx1 = a.fx1[o + tt0], nx2 = a.fx2[o + tt0], ny[DOUT];
+#pragma unroll
+    for (int c = 0; c < DOUT; c++) ny[c] = a.fy[c][o + tt0];
     int norig = a.forig[o + tt0];
     for (int tt = tt0; tt < n; ++tt) {
-        const double x1 = nx1, x2 = nx2, y = ny;
+        const double x1 = nx1, x2 = nx2;
+        double y[DOUT];
+#pragma unroll
+        for (int c = 0; c < DOUT; c++) y[c] = ny[c];
         const int orig = norig;
         if (tt + 1 < n) {  // prefetch the next point of the stream
-            nx1 = a.fx1[o + tt + 1]; nx2 = a.fx2[o + tt + 1]; ny = a.fy[o + tt + 1];
+            nx1 = a.fx1[o + tt + 1]; nx2 = a.fx2[o + tt + 1];
+#pragma unroll
+            for (int c = 0; c < DOUT; c++) ny[c] = a.fy[c][o + tt + 1];
             norig = a.forig[o + tt + 1];
         }
         if (N == 0) {  // sparse_gp.hpp:100-110
             if (t == 0) {
                 const double d = __dadd_rn(kstar, s20);
-                s.alpha()[0] = __ddiv_rn(y, d);
+#pragma unroll
+                for (int c = 0; c < DOUT; c++) s.alpha(c)[0] = __ddiv_rn(y[c], d);
                 C[0] = __ddiv_rn(-1.0, d);
                 Q[0] = __ddiv_rn(1.0, kstar);
                 s.b1()[0] = x1; s.b2()[0] = x2; s.bidx()[0] = orig;
@@ -958,8 +1039,13 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
             const double rv = __dadd_rn(pr, shfl_xor_d(pr, 16));       // canonical (a0+a1)+(a2+a3)
             if (irow < N && half == 0) (mat ? s.ev() : s.ck())[irow] = rv;
         }
-        double m = 0.0;
-        if (w == 0) m = warp_dot32(s.alpha(), s.kv(), N, lane);
+        double m[DOUT];
+#pragma unroll
+        for (int c = 0; c < DOUT; c++) m[c] = 0.0;
+        if (w == 0) {
+#pragma unroll
+            for (int c = 0; c < DOUT; c++) m[c] = warp_dot32(s.alpha(c), s.kv(), N, lane);
+        }
         __syncthreads();
         // every warp: k'Ck and k'e_hat (cheap, no division) -> gamma and the sparse / full decision
         double kck = 0.0, ke = 0.0;
@@ -976,22 +1062,31 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
         double gamma = __dadd_rn(kstar, -ke);                 // sparse_gp.hpp:144
         if (gamma < tiny12()) gamma = 0.0;
         const bool sparse = gamma < eps_tol;
-        // warp 0 alone does the divisions and publishes them: scal[0] = r, [1] = q, [2] = q*eta | -, [3] = r*eta | 1/gamma
+        // warp 0 alone does the divisions and publishes them:
+        // scal[0] = r, [1] = r*eta (sparse) | 1/gamma (full), [2..2+DOUT) = q_c, [5..5+DOUT) = q_c*eta (sparse)
         if (w == 0) {
             const double s2 = __dadd_rn(kstar, kck);
             const double den = __dadd_rn(s20, s2);
             const double rr = __ddiv_rn(-1.0, den);               // gaussian_noise.cpp:15-18
-            const double q = __ddiv_rn(__dadd_rn(y, -m), den);    // gaussian_noise.cpp:9-12
-            double c2, c3;
+            double q[DOUT], qe[DOUT];
+#pragma unroll
+            for (int c = 0; c < DOUT; c++) q[c] = __ddiv_rn(__dadd_rn(y[c], -m[c]), den);    // gaussian_noise.cpp:9-12
+            double c3;
             if (sparse) {
                 const double eta = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn(gamma, rr)));
-                c2 = __dmul_rn(q, eta);
+#pragma unroll
+                for (int c = 0; c < DOUT; c++) qe[c] = __dmul_rn(q[c], eta);
                 c3 = __dmul_rn(rr, eta);
             } else {
-                c2 = 0.0;
+#pragma unroll
+                for (int c = 0; c < DOUT; c++) qe[c] = 0.0;
                 c3 = __ddiv_rn(1.0, gamma);
             }
-            if (lane == 0) { s.scal()[0] = rr; s.scal()[1] = q; s.scal()[2] = c2; s.scal()[3] = c3; }
+            if (lane == 0) {
+                s.scal()[0] = rr; s.scal()[1] = c3;
+#pragma unroll
+                for (int c = 0; c < DOUT; c++) { s.scal()[2 + c] = q[c]; s.scal()[5 + c] = qe[c]; }
+            }
         }
         if (sparse) {
             // sparse update (sparse_gp.hpp:155-163)
@@ -1002,8 +1097,11 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
                 s.sv()[t] = sh;
             }
             __syncthreads();
-            const double qe = s.scal()[2], re = s.scal()[3];
-            if (t < N) s.alpha()[t] = __dadd_rn(s.alpha()[t], __dmul_rn(sh, qe));
+            const double re = s.scal()[1];
+            if (t < N) {
+#pragma unroll
+                for (int c = 0; c < DOUT; c++) s.alpha(c)[t] = __dadd_rn(s.alpha(c)[t], __dmul_rn(sh, s.scal()[5 + c]));
+            }
             if (irow < N) {
                 const double si = s.sv()[irow];
                 for (int j = jq; j < N; j += 4) {
@@ -1020,7 +1118,7 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
             if (t == 0) spos = atomicAdd(a.queue_count, 1);
             __syncthreads();
             const int pos = spos;
-            double* slot = a.handoff_out + (size_t)pos * slot_doubles(LD);
+            double* slot = a.handoff_out + (size_t)pos * slot_doubles(LD, DOUT);
             if (t == 0) {
                 a.queue[pos] = (int32_t)patch;
                 reinterpret_cast<int*>(slot)[0] = N;
@@ -1029,10 +1127,12 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
             }
             double* v = slot + 2 + NCNT;
             for (int i = t; i < LD; i += NT) {
-                v[i] = s.alpha()[i]; v[LD + i] = s.b1()[i]; v[2 * LD + i] = s.b2()[i];
-                reinterpret_cast<int*>(v + 3 * LD + 2 * LD * LD)[i] = s.bidx()[i];
+#pragma unroll
+                for (int c = 0; c < DOUT; c++) v[c * LD + i] = s.alpha(c)[i];
+                v[DOUT * LD + i] = s.b1()[i]; v[(DOUT + 1) * LD + i] = s.b2()[i];
+                reinterpret_cast<int*>(v + (DOUT + 2) * LD + 2 * LD * LD)[i] = s.bidx()[i];
             }
-            for (int i = t; i < LD * LD; i += NT) { v[3 * LD + i] = C[i]; v[3 * LD + LD * LD + i] = Q[i]; }
+            for (int i = t; i < LD * LD; i += NT) { v[(DOUT + 2) * LD + i] = C[i]; v[(DOUT + 2) * LD + LD * LD + i] = Q[i]; }
             return;
         }
         cnt.full(N);
@@ -1048,9 +1148,15 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
         }
         __syncthreads();
         {
-            const double rr = s.scal()[0], q = s.scal()[1], ig = s.scal()[3];
-            if (t < N) s.alpha()[t] = __dadd_rn(s.alpha()[t], __dmul_rn(q, sct));
-            if (t == N) s.alpha()[N] = __dadd_rn(0.0, __dmul_rn(q, 1.0));
+            const double rr = s.scal()[0], ig = s.scal()[1];
+            if (t <= N) {
+#pragma unroll
+                for (int c = 0; c < DOUT; c++) {
+                    const double q = s.scal()[2 + c];
+                    if (t < N) s.alpha(c)[t] = __dadd_rn(s.alpha(c)[t], __dmul_rn(q, sct));
+                    else s.alpha(c)[N] = __dadd_rn(0.0, __dmul_rn(q, 1.0));
+                }
+            }
             const int N1 = N + 1;
             if (irow < N1) {
                 const double si = s.sv()[irow], ei = s.ev()[irow];
@@ -1065,17 +1171,17 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
         __syncthreads();
         // capacity deletions (sparse_gp.hpp:206-223)
         while (N > cap) {
-            const int loc = block_argmin<LD, 0>(s, N, t, lane);
+            const int loc = block_argmin<LD, DOUT, 0>(s, N, t, lane);
             cnt.c[9] += (unsigned long long)(N - 1) * (N - 1);
-            delete_bv<LD, RB, NT>(s, N, loc, t);
+            delete_bv<LD, RB, NT, DOUT>(s, N, loc, t);
             cnt.c[3]++;
         }
         // geometric deletions (sparse_gp.hpp:226-242)
         while (N > 1) {
-            const int loc = block_argmin<LD, 1>(s, N, t, lane);
+            const int loc = block_argmin<LD, DOUT, 1>(s, N, t, lane);
             if (loc < 0) break;
             cnt.c[9] += (unsigned long long)(N - 1) * (N - 1);
-            delete_bv<LD, RB, NT>(s, N, loc, t);
+            delete_bv<LD, RB, NT, DOUT>(s, N, loc, t);
             cnt.c[4]++;
         }
     }
@@ -1090,7 +1196,8 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
     }
     const int64_t ob = op * cap;
     for (int i = t; i < N; i += NT) {
-        a.o_alpha[ob + i] = s.alpha()[i];
+#pragma unroll
+        for (int c = 0; c < DOUT; c++) a.o_alpha[c][ob + i] = s.alpha(c)[i];
         a.o_b1[ob + i] = s.b1()[i];
         a.o_b2[ob + i] = s.b2()[i];
         a.o_idx[ob + i] = s.bidx()[i];
@@ -1105,19 +1212,19 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
     }
 }
 
-template <int LD>
-constexpr size_t cta_smem_bytes() { return (size_t)Smem<LD>::kDoubles * sizeof(double) + (size_t)LD * sizeof(int); }
+template <int LD, int DOUT>
+constexpr size_t cta_smem_bytes() { return (size_t)Smem<LD, DOUT>::kDoubles * sizeof(double) + (size_t)LD * sizeof(int); }
 
-template <int LD, int RB, int NT, int LD_IN, bool SPILL>
+template <int LD, int RB, int NT, int LD_IN, bool SPILL, int DOUT>
 cudaError_t launch_cta_bucket(const SogpArgs& a, cudaStream_t st) {
-    constexpr size_t smem = SPILL ? 0 : cta_smem_bytes<LD>();
+    constexpr size_t smem = SPILL ? 0 : cta_smem_bytes<LD, DOUT>();
     static bool configured = false;
     if (smem > 48 * 1024 && !configured) {
-        cudaError_t e = cudaFuncSetAttribute(sogp_fit_kernel<LD, RB, NT, LD_IN, SPILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(sogp_fit_kernel<LD, RB, NT, LD_IN, SPILL, DOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    sogp_fit_kernel<LD, RB, NT, LD_IN, SPILL><<<a.n_work, NT, smem, st>>>(a);
+    sogp_fit_kernel<LD, RB, NT, LD_IN, SPILL, DOUT><<<a.n_work, NT, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -1128,23 +1235,40 @@ int sogp_bucket_ld(int bucket) {
     return lds[bucket];
 }
 
-size_t sogp_spill_bytes_per_patch() { return (size_t)(2 * 202 * 202 + 11 * 202 + 8) * sizeof(double); }
 
-size_t sogp_handoff_slot_bytes(int bucket) { return (size_t)slot_doubles(sogp_bucket_ld(bucket)) * sizeof(double); }
+size_t sogp_handoff_slot_bytes(int bucket, int dout) { return (size_t)slot_doubles(sogp_bucket_ld(bucket), dout) * sizeof(double); }
+
+size_t sogp_spill_bytes_per_patch() { return (size_t)(2 * 202 * 202 + 13 * 202 + 16) * sizeof(double); }
+
+// Height GPs (dout 1) use buckets 0,1,2,3,4; the RGB field GPs (dout 3) use 0,2,4 (bucket 2 resumes bucket-0 slots,
+// bucket 4 resumes bucket-2 slots): under the reference's field hyper-parameters N stays below 16 anyway.
+int sogp_next_bucket(int bucket, int dout) {
+    if (dout == 1) return bucket + 1;
+    return bucket == 0 ? 2 : 4;
+}
 
 cudaError_t launch_sogp_fit(int bucket, const SogpArgs& a, cudaStream_t st) {
     if (a.n_work <= 0) return cudaSuccess;
     g_launches++;
+    if (a.dout == 3) {
+        switch (bucket) {
+            case 0:
+                sogp_fit_warp_kernel<3><<<a.n_work, 32, 0, st>>>(a);
+                return cudaGetLastError();
+            case 2: return launch_cta_bucket<64, 64, 256, 16, false, 3>(a, st);
+            default: return launch_cta_bucket<202, 256, 1024, 64, true, 3>(a, st);
+        }
+    }
     switch (bucket) {
         case 0:
-            sogp_fit_warp_kernel<<<a.n_work, 32, 0, st>>>(a);
+            sogp_fit_warp_kernel<1><<<a.n_work, 32, 0, st>>>(a);
             return cudaGetLastError();
         case 1:
             sogp_fit_pair_kernel<<<a.n_work, 64, 0, st>>>(a);
             return cudaGetLastError();
-        case 2: return launch_cta_bucket<64, 64, 256, 32, false>(a, st);
-        case 3: return launch_cta_bucket<118, 128, 512, 64, false>(a, st);
-        default: return launch_cta_bucket<202, 256, 1024, 118, true>(a, st);
+        case 2: return launch_cta_bucket<64, 64, 256, 32, false, 1>(a, st);
+        case 3: return launch_cta_bucket<118, 128, 512, 64, false, 1>(a, st);
+        default: return launch_cta_bucket<202, 256, 1024, 118, true, 1>(a, st);
     }
 }
 

@@ -141,15 +141,20 @@ constexpr int SHUF_SMEM_MAX = 1024;
 
 __global__ void __launch_bounds__(32) shuffle_warp_kernel(const int64_t* __restrict__ off, int64_t n_patches,
                                                           const int64_t* __restrict__ roff, const uint32_t* __restrict__ rnd,
-                                                          int32_t* __restrict__ perm) {
+                                                          int second, int32_t* __restrict__ perm) {
     __shared__ int ind[SHUF_SMEM_MAX];
     __shared__ int rr[SHUF_SMEM_MAX];
     const int64_t p = blockIdx.x;
     const int lane = threadIdx.x;
     const int64_t o = off[p];
     const int n = (int)(off[p + 1] - o);
-    if (n < 2 || n > SHUF_SMEM_MAX) return;
-    const uint32_t* r = rnd + (roff[p] - roff[0]);
+    if (n > SHUF_SMEM_MAX) return;
+    if (n < 2) {
+        if (n == 1 && lane == 0) perm[o] = 0;
+        return;
+    }
+    // the RGB field GP shuffles right after the height GP: its draws follow the patch's first n - 1
+    const uint32_t* r = rnd + (roff[p] - roff[0]) + (second ? (n - 1) : 0);
     for (int i = lane; i < n; i += 32) {
         ind[i] = i;
         if (i > 0) rr[i] = (int)(r[n - 1 - i] % (uint32_t)i);
@@ -168,14 +173,16 @@ __global__ void __launch_bounds__(32) shuffle_warp_kernel(const int64_t* __restr
 }
 
 __global__ void shuffle_kernel(const int64_t* __restrict__ off, int64_t n_patches, const int64_t* __restrict__ roff,
-                               const uint32_t* __restrict__ rnd, int32_t* __restrict__ perm) {
+                               const uint32_t* __restrict__ rnd, int second, int32_t* __restrict__ perm) {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_patches) return;
     const int64_t o = off[p];
     const int n = (int)(off[p + 1] - o);
     if (n <= SHUF_SMEM_MAX) return;  // handled by shuffle_warp_kernel
-    const uint32_t* r = rnd + (roff[p] - roff[0]);
+    const uint32_t* r = rnd + (roff[p] - roff[0]) + (second ? (n - 1) : 0);
     int32_t* ind = perm + o;
+    if (second)
+        for (int i = 0; i < n; i++) ind[i] = i;
     for (int i = n - 1; i > 0; --i) {
         uint32_t rr = r[n - 1 - i] % (uint32_t)i;
         int32_t a = ind[i], b = ind[rr];
@@ -186,15 +193,17 @@ __global__ void shuffle_kernel(const int64_t* __restrict__ off, int64_t n_patche
 
 void launch_shuffle(const int64_t* off, int64_t n_patches, const int64_t* roff, const uint32_t* rnd, int do_shuffle,
                     int32_t* perm, int32_t* patch_of, int64_t s_begin, int64_t s_count, int64_t max_patch_points,
-                    cudaStream_t s) {
+                    int second, cudaStream_t s) {
     if (s_count <= 0 || n_patches <= 0) return;
-    patch_of_kernel<<<(unsigned)((s_count + 255) / 256), 256, 0, s>>>(off, n_patches, s_begin, s_count, patch_of, perm);
-    g_launches++;
+    if (!second) {  // the second (RGB) shuffle reuses patch_of; its kernels initialise perm themselves
+        patch_of_kernel<<<(unsigned)((s_count + 255) / 256), 256, 0, s>>>(off, n_patches, s_begin, s_count, patch_of, perm);
+        g_launches++;
+    }
     if (do_shuffle) {
-        shuffle_warp_kernel<<<(unsigned)n_patches, 32, 0, s>>>(off, n_patches, roff, rnd, perm);
+        shuffle_warp_kernel<<<(unsigned)n_patches, 32, 0, s>>>(off, n_patches, roff, rnd, second, perm);
         g_launches++;
         if (max_patch_points > SHUF_SMEM_MAX) {
-            shuffle_kernel<<<(unsigned)((n_patches + 127) / 128), 128, 0, s>>>(off, n_patches, roff, rnd, perm);
+            shuffle_kernel<<<(unsigned)((n_patches + 127) / 128), 128, 0, s>>>(off, n_patches, roff, rnd, second, perm);
             g_launches++;
         }
     }
@@ -219,6 +228,36 @@ void launch_gather_stream(const int64_t* off, const int32_t* patch_of, const int
                           double* fy, cudaStream_t s) {
     if (s_count <= 0) return;
     gather_stream_kernel<<<(unsigned)((s_count + 255) / 256), 256, 0, s>>>(off, patch_of, perm, x1, x2, y, s_begin, s_count, fx1, fx2, fy);
+    g_launches++;
+}
+
+// RGB field GP stream in its own add order: local coordinates and colours centred on the patch mean
+// (p.second -= c_mn, gp_compressor.cpp:105).  rgb holds the b,g,r,a bytes of each claimed point.
+__global__ void gather_rgb_stream_kernel(const int64_t* __restrict__ off, const int32_t* __restrict__ patch_of,
+                                         const int32_t* __restrict__ perm, const double* __restrict__ x1,
+                                         const double* __restrict__ x2, const uint32_t* __restrict__ rgb,
+                                         const double* __restrict__ rgbmean, int64_t first_patch, int64_t s_begin,
+                                         int64_t s_count, double* __restrict__ fx1, double* __restrict__ fx2,
+                                         double* __restrict__ fr, double* __restrict__ fg, double* __restrict__ fb) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= s_count) return;
+    s += s_begin;
+    const int64_t pl = patch_of[s];
+    const int64_t src = off[pl] + perm[s];
+    const double* mean = rgbmean + 3 * (first_patch + pl);
+    const uint32_t c = rgb[src];
+    fx1[s] = x1[src];
+    fx2[s] = x2[src];
+    fr[s] = __dadd_rn((double)((c >> 16) & 255u), -mean[0]);
+    fg[s] = __dadd_rn((double)((c >> 8) & 255u), -mean[1]);
+    fb[s] = __dadd_rn((double)(c & 255u), -mean[2]);
+}
+void launch_gather_rgb_stream(const int64_t* off, const int32_t* patch_of, const int32_t* perm, const double* x1, const double* x2,
+                              const uint32_t* rgb, const double* rgbmean, int64_t first_patch, int64_t s_begin, int64_t s_count,
+                              double* fx1, double* fx2, double* fr, double* fg, double* fb, cudaStream_t s) {
+    if (s_count <= 0) return;
+    gather_rgb_stream_kernel<<<(unsigned)((s_count + 255) / 256), 256, 0, s>>>(off, patch_of, perm, x1, x2, rgb, rgbmean, first_patch,
+                                                                             s_begin, s_count, fx1, fx2, fr, fg, fb);
     g_launches++;
 }
 

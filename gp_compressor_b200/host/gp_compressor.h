@@ -28,6 +28,7 @@ public:
         gpc_config_default(&cfg_);
         cfg_.res = res;
         cfg_.sz = sz;
+        cfg_.rgb = 1;  // the reference always fits the RGB field GP next to the height GP (gp_compressor.cpp:163)
     }
     ~gp_compressor() { if (gpu_) gpc_destroy(gpu_); }
     gp_compressor(const gp_compressor&) = delete;

@@ -51,6 +51,9 @@ typedef struct gpc_config {
     int32_t shard_rank; /* this handle fits / decodes patches of shard shard_rank ...                   */
     int32_t shard_count;/* ... out of shard_count contiguous ranges of the patch visiting order (1)     */
     int32_t keep_state; /* 1: keep dense C and Q per patch (gpc_get_state, predictive variance)         */
+    int32_t rgb;        /* 1: also fit / decode the RGB field GP, sparse_gp_field (gp_compressor.cpp:163,334)  */
+    double rgb_s0;      /* sparse_gp_field(capacity, s0), sparse_gp_field.h:43 (1e2f)                        */
+    double rgb_eps_tol; /* sparse_gp_field ctor literal, sparse_gp_field.hpp:16 (1e-4f)                      */
 } gpc_config;
 
 typedef struct gpc_sizes {
@@ -74,8 +77,9 @@ typedef struct gpc_stats {
     uint64_t sum_n, sum_n2_common, sum_n2_sparse, sum_n2_full, sum_n2_del;
     uint64_t escalated[4];      /* patches that left SOGP bucket b for a larger one */
     uint64_t kernel_launches;   /* kernels launched by the last compress / decompress */
+    uint64_t rgb_n_sparse, rgb_n_full, rgb_n_del_cap, rgb_n_del_geo, rgb_sum_n2_common;  /* RGB field GP events */
     float ms_h2d, ms_lattice, ms_keys, ms_sort, ms_leaves, ms_rotation, ms_claim, ms_group,
-          ms_shuffle, ms_fit, ms_d2h, ms_predict, ms_total;
+          ms_shuffle, ms_fit, ms_d2h, ms_predict, ms_total, ms_fit_rgb;
 } gpc_stats;
 
 /* ---- lifetime ---------------------------------------------------------------------- */
@@ -130,6 +134,10 @@ int gpc_get_assignment(gpc_handle* h, int32_t* owner, int32_t* stream_index,
 int gpc_get_params(gpc_handle* h, int32_t* nbv, int64_t* bv_off, int32_t* bv_index,
                    double* bv1, double* bv2, double* alpha, int32_t* flags);
 int gpc_get_state(gpc_handle* h, int64_t patch, double* C, double* Q);  /* N x N, row-major */
+/* RGB field GP (next-row N1, gpc_config.rgb): per patch nbv, BVs and alpha (3 per BV: r, g, b), packed like gpc_get_params;
+ * perm = the field GP's own shuffle.  n_bv_total_rgb is returned through the last argument. */
+int gpc_get_params_rgb(gpc_handle* h, int32_t* nbv, int64_t* bv_off, int32_t* bv_index, double* bv1, double* bv2, double* alpha3,
+                       int32_t* perm, int64_t* n_bv_total_rgb);
 /* decode-only use: install fitted parameters (and optionally frames) from the host */
 int gpc_set_params(gpc_handle* h, int64_t n_patches, const int32_t* nbv, const double* bv1,
                    const double* bv2, const double* alpha, const double* quat4,

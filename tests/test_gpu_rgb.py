@@ -1,0 +1,68 @@
+"""Next-row N1 on the GPU: the RGB field GP (sparse_gp_field<rbf_kernel, gaussian_noise_3d>) fitted next to the height
+GP (gp_compressor.cpp:163) and evaluated at decode (gp_compressor.cpp:334,367-371), against the CPU oracle (which is itself
+pinned against the reference's own sparse_gp_field.hpp, tests/test_oracle_vs_reference_source.py).  Bit-exact bar."""
+import numpy as np
+import pytest
+
+from gp_compressor_b200 import synth
+
+pytestmark = pytest.mark.gpu
+F32 = lambda v: float(np.float32(v))
+
+
+def run(cloud, **cfg):
+    import gp_compressor_b200 as G
+    from oracle import oracle as O
+    h = G.Handle(rgb=1, **cfg)
+    h.compress(cloud)
+    o = O.Oracle(rgb=1, **cfg)
+    want_h = o.compress(cloud)
+    want = o.rgb_result()
+    got = h.params_rgb()
+    assert np.array_equal(got["perm"], want["perm"])
+    assert np.array_equal(got["nbv"], want["nbv"]) and np.array_equal(got["bv_idx"], want["bv_idx"])
+    assert np.array_equal(got["bv1"], want["bv1"]) and np.array_equal(got["bv2"], want["bv2"])
+    assert np.array_equal(got["alpha"], want["alpha"], equal_nan=True)
+    # the height GP is untouched by the extra work
+    assert np.array_equal(h.params()["alpha"], want_h["alpha"])
+    gs, os_ = h.stats(), o.stats_rgb()
+    assert (gs["rgb_n_sparse"], gs["rgb_n_full"], gs["rgb_n_del_cap"], gs["rgb_n_del_geo"]) == \
+           (os_["n_sparse"], os_["n_full"], os_["n_del_cap"], os_["n_del_geo"])
+    assert gs["rgb_sum_n2_common"] == os_["sumN2_common"]
+    assert h.sizes().rand_offset == o.rand_offset()
+    cloud_o, _ = o.decode(want_heights=False)
+    cloud_g = h.decompress()
+    assert np.array_equal(cloud_g, cloud_o)
+    return h, o, cloud_g
+
+
+def test_rgb_reference_defaults():
+    """Reference configuration: capacity 100, s0 = 1e2f, eps_tol = 1e-4f (the field GP keeps ~4-6 BVs)."""
+    cloud = synth.c1_planar_bumps(30000, seed=1)
+    h, o, dec = run(cloud, res=F32(0.15), sz=8, capacity=100)
+    # colours are no longer constant inside a patch
+    rgb = dec[:, 16:19].reshape(-1, 64, 3).astype(int)
+    assert (rgb.max(axis=1) - rgb.min(axis=1)).max() > 0
+
+
+def test_rgb_capacity_bound_and_bucket_chain():
+    """A hyper-set under which the field GP grows: exercises its delete_bv variant and the 0 -> 2 bucket hand-off."""
+    cloud = synth.c3_dense_floor(30000, seed=5, side=1.0)
+    hyp = synth.hyper_bind(F32(0.1))
+    run(cloud, res=F32(0.1), sz=4, capacity=12, rgb_s0=1e-2, sigmaf_sq=hyp["sigmaf_sq"], l_sq=hyp["l_sq"], s0=hyp["s0"])
+    run(cloud, res=F32(0.1), sz=4, capacity=40, rgb_s0=1e-2, sigmaf_sq=hyp["sigmaf_sq"], l_sq=hyp["l_sq"], s0=hyp["s0"])
+
+
+def test_rgb_sharded_matches_single():
+    import gp_compressor_b200 as G
+    cloud = synth.c2_indoor(20000, seed=3)
+    cfg = dict(res=F32(0.1), sz=5, capacity=30, rgb=1)
+    whole = G.Handle(**cfg)
+    whole.compress(cloud)
+    want = whole.decompress()
+    parts = []
+    for r in range(3):
+        h = G.Handle(shard_rank=r, shard_count=3, **cfg)
+        h.compress(cloud)
+        parts.append(h.decompress())
+    assert np.array_equal(np.concatenate(parts), want)

@@ -41,7 +41,7 @@ def test_driver_matches_ctypes_path(tmp_path):
     out = subprocess.run([exe, str(path), str(dec_path)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     lines = dict(l.split(" ", 1) for l in out.stdout.splitlines() if l.split(" ")[0] in ("CLOUD", "SOGP", "KSVD_SHELL"))
-    h = G.Handle(res=float(np.float32(0.15)), sz=20)  # the literals of test_gp_compress.cpp:21
+    h = G.Handle(res=float(np.float32(0.15)), sz=20, rgb=1)  # the literals of test_gp_compress.cpp:21; the shell enables the RGB GP
     h.compress(cloud)
     dec = h.decompress()
     dec_cpp = np.fromfile(dec_path, dtype=np.uint8).reshape(-1, 32)
