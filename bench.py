@@ -35,7 +35,18 @@ sys.path.insert(0, ROOT)
 F32 = lambda v: float(np.float32(v))
 
 
+RGB = False
+
+
 def workload(name, points, seed_shift=0):
+    cloud, cfg, desc = _workload(name, points, seed_shift)
+    if RGB:
+        cfg = dict(cfg, rgb=1)
+        desc += ", + RGB field GP (N1)"
+    return cloud, cfg, desc
+
+
+def _workload(name, points, seed_shift=0):
     from gp_compressor_b200 import synth
     if name in ("c2", "c2bind"):
         n = points or 5_000_000
@@ -172,7 +183,10 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--points", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rgb", action="store_true", help="also fit / decode the RGB field GP (next-row N1), in both arms")
     args = ap.parse_args()
+    global RGB
+    RGB = args.rgb
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -292,7 +306,7 @@ def main():
 
     # ---- roofline of the dominant stage --------------------------------------------------------
     peak, peak_src = measured_peaks()
-    stage_ms = {k: v / K for k, v in stage_acc.items() if k not in ("ms_total", "ms_h2d", "ms_d2h")}
+    stage_ms = {k: v / K for k, v in stage_acc.items() if k not in ("ms_total", "ms_h2d", "ms_d2h") and (v > 0 or k != "ms_fit_rgb")}
     dom = max(stage_ms, key=stage_ms.get)
     n_valid = n  # all points finite in the synthetic clouds
     models = stage_models(n, n_valid, sizes.n_claimed, sizes.depth, sizes.n_patches, fit_stats, cfg["capacity"])

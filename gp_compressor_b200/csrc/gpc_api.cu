@@ -246,6 +246,7 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
     tm.span(&h->stats.ms_fit, t1, t2);
     // ---- RGB field GP (sparse_gp_field<rbf_kernel, gaussian_noise_3d>): same points, own shuffle, 3 outputs ----
     h->have_rgb = false;
+    size_t t_pack0 = t2;
     if (c.rgb && h->have_binning) {
         if (!(c.shuffle && c.rgb_rand)) return fail(h, GPC_ERR_INVALID, "rgb = 1 needs shuffle = 1 and rgb_rand = 1");
         const int64_t Sa = std::max<int64_t>(S, 1);
@@ -291,6 +292,7 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
         h->have_rgb = true;
         size_t t2b = tm.mark();
         tm.span(&h->stats.ms_fit_rgb, t2, t2b);
+        t_pack0 = t2b;
     }
     // pack the parameters on the device: what the host fetches is sum(nbv) entries, not capacity per patch
     CK(h->bv_off.reserve((PLa + 1) * sizeof(int64_t)));
@@ -308,7 +310,7 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
     CK(cudaStreamSynchronize(st));
     h->n_bv_total = tot;
     size_t t3 = tm.mark();
-    tm.span(&h->stats.ms_group, t2, t3);
+    tm.span(&h->stats.ms_group, t_pack0, t3);
     h->have_fit = true;
     h->params_packed = true;
     return GPC_OK;
