@@ -1126,8 +1126,31 @@ int gpc_save(gpc_handle* h, const char* path, int64_t* bytes_written) {
     FILE* f = std::fopen(path, "wb");
     if (!f) return fail(h, GPC_ERR_INVALID, std::string("cannot open ") + path);
     const char magic[8] = {'G', 'P', 'C', 'B', '2', '0', '0', 0};
-    const uint32_t version = 1;
+    const uint32_t version = 2;
     const gpc_config& c = h->cfg;
+    // RGB field GP block (version 2): strided device arrays -> packed host arrays
+    const int32_t has_rgb = h->have_rgb ? 1 : 0;
+    std::vector<int32_t> rnbv(has_rgb ? PL : 0);
+    std::vector<double> rb1, rb2, ra;
+    int64_t TR = 0;
+    if (has_rgb && PL > 0) {
+        const int cap = c.capacity;
+        CK(cudaMemcpy(rnbv.data(), h->r_nbv.p, PL * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        for (int32_t v : rnbv) TR += v;
+        std::vector<double> t((size_t)PL * cap);
+        auto pack = [&](const DevBuf& src, std::vector<double>& dst, int stride3, int ch) -> int {
+            CK(cudaMemcpy(t.data(), src.p, t.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            int64_t o = 0;
+            for (int64_t p = 0; p < PL; p++)
+                for (int i = 0; i < rnbv[p]; i++, o++) dst[(size_t)o * stride3 + ch] = t[(size_t)p * cap + i];
+            return GPC_OK;
+        };
+        rb1.resize(TR); rb2.resize(TR); ra.resize(3 * TR);
+        int rc2;
+        if ((rc2 = pack(h->r_b1, rb1, 1, 0)) || (rc2 = pack(h->r_b2, rb2, 1, 0)) || (rc2 = pack(h->r_alpha0, ra, 3, 0)) ||
+            (rc2 = pack(h->r_alpha1, ra, 3, 1)) || (rc2 = pack(h->r_alpha2, ra, 3, 2)))
+            return rc2;
+    }
     const double dcfg[5] = {c.res, c.s0, c.eps_tol, c.sigmaf_sq, c.l_sq};
     const int32_t icfg[2] = {c.sz, c.capacity};
     size_t ok = 1;
@@ -1145,6 +1168,14 @@ int gpc_save(gpc_handle* h, const char* path, int64_t* bytes_written) {
     put(b1.data(), T * sizeof(double));
     put(b2.data(), T * sizeof(double));
     put(al.data(), T * sizeof(double));
+    const double rcfg[2] = {c.rgb_s0, c.rgb_eps_tol};
+    put(&has_rgb, sizeof(has_rgb));
+    put(rcfg, sizeof(rcfg));
+    put(&TR, sizeof(TR));
+    put(rnbv.data(), rnbv.size() * sizeof(int32_t));
+    put(rb1.data(), rb1.size() * sizeof(double));
+    put(rb2.data(), rb2.size() * sizeof(double));
+    put(ra.data(), ra.size() * sizeof(double));
     const long pos = std::ftell(f);
     std::fclose(f);
     if (!ok) return fail(h, GPC_ERR_INVALID, std::string("short write to ") + path);
@@ -1168,7 +1199,7 @@ int gpc_load(gpc_handle* h, const char* path) {
     int32_t icfg[2];
     int64_t PL = 0, T = 0;
     bool ok = std::fread(magic, 8, 1, f) == 1 && std::memcmp(magic, "GPCB200", 8) == 0;
-    ok = ok && std::fread(&version, 4, 1, f) == 1 && version == 1;
+    ok = ok && std::fread(&version, 4, 1, f) == 1 && (version == 1 || version == 2);
     ok = ok && std::fread(dcfg, sizeof(dcfg), 1, f) == 1 && std::fread(icfg, sizeof(icfg), 1, f) == 1;
     ok = ok && std::fread(&PL, 8, 1, f) == 1 && std::fread(&T, 8, 1, f) == 1 && PL >= 0 && T >= 0;
     if (!ok) { std::fclose(f); return fail(h, GPC_ERR_INVALID, "not a gpc_b200 parameter file (or unsupported version)"); }
@@ -1182,6 +1213,23 @@ int gpc_load(gpc_handle* h, const char* path) {
     get(b1.data(), T * sizeof(double));
     get(b2.data(), T * sizeof(double));
     get(al.data(), T * sizeof(double));
+    int32_t has_rgb = 0;
+    double rcfg[2] = {h->cfg.rgb_s0, h->cfg.rgb_eps_tol};
+    int64_t TR = 0;
+    std::vector<int32_t> rnbv;
+    std::vector<double> rb1, rb2, ra;
+    if (ok && version >= 2) {
+        get(&has_rgb, sizeof(has_rgb));
+        get(rcfg, sizeof(rcfg));
+        get(&TR, sizeof(TR));
+        if (ok && has_rgb && TR >= 0) {
+            rnbv.resize(PL); rb1.resize(TR); rb2.resize(TR); ra.resize(3 * TR);
+            get(rnbv.data(), PL * sizeof(int32_t));
+            get(rb1.data(), TR * sizeof(double));
+            get(rb2.data(), TR * sizeof(double));
+            get(ra.data(), 3 * TR * sizeof(double));
+        }
+    }
     std::fclose(f);
     if (!ok) return fail(h, GPC_ERR_INVALID, "truncated parameter file");
     int64_t sum = 0;
@@ -1190,8 +1238,35 @@ int gpc_load(gpc_handle* h, const char* path) {
     // the decoder's configuration comes from the file (the shard layout and device stay the handle's own)
     h->cfg.res = dcfg[0]; h->cfg.s0 = dcfg[1]; h->cfg.eps_tol = dcfg[2]; h->cfg.sigmaf_sq = dcfg[3]; h->cfg.l_sq = dcfg[4];
     h->cfg.sz = icfg[0]; h->cfg.capacity = icfg[1];
+    h->cfg.rgb_s0 = rcfg[0]; h->cfg.rgb_eps_tol = rcfg[1];
+    h->cfg.rgb = has_rgb;
     const double one = 0.0;
-    return gpc_set_params(h, PL, nbv.data(), T ? b1.data() : &one, T ? b2.data() : &one, T ? al.data() : &one, quat.data(), mean.data(), rgbm.data());
+    int rc = gpc_set_params(h, PL, nbv.data(), T ? b1.data() : &one, T ? b2.data() : &one, T ? al.data() : &one, quat.data(), mean.data(),
+                            rgbm.data());
+    if (rc || !has_rgb) return rc;
+    // install the RGB field GP of this shard's patch range (strided by capacity, like the fitted arrays)
+    const int cap = h->cfg.capacity;
+    const int64_t lo = h->patch_lo, hi = h->patch_hi, PLs = hi - lo, PLa = std::max<int64_t>(PLs, 1);
+    std::vector<int64_t> ro(PL + 1, 0);
+    for (int64_t p = 0; p < PL; p++) {
+        if (rnbv[p] < 0 || rnbv[p] > cap) return fail(h, GPC_ERR_INVALID, "inconsistent RGB block in the parameter file");
+        ro[p + 1] = ro[p] + rnbv[p];
+    }
+    if (ro[PL] != TR) return fail(h, GPC_ERR_INVALID, "inconsistent RGB block in the parameter file");
+    DevBuf* dst[5] = {&h->r_b1, &h->r_b2, &h->r_alpha0, &h->r_alpha1, &h->r_alpha2};
+    std::vector<double> t((size_t)PLa * cap);
+    for (int k = 0; k < 5; k++) {
+        std::fill(t.begin(), t.end(), 0.0);
+        for (int64_t p = lo; p < hi; p++)
+            for (int i = 0; i < rnbv[p]; i++)
+                t[(size_t)(p - lo) * cap + i] = (k == 0) ? rb1[ro[p] + i] : (k == 1) ? rb2[ro[p] + i] : ra[3 * (ro[p] + i) + (k - 2)];
+        CK(dst[k]->reserve(t.size() * sizeof(double)));
+        CK(cudaMemcpy(dst[k]->p, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    CK(h->r_nbv.reserve(PLa * sizeof(int32_t)));
+    if (PLs > 0) CK(cudaMemcpy(h->r_nbv.p, rnbv.data() + lo, PLs * sizeof(int32_t), cudaMemcpyHostToDevice));
+    h->have_rgb = true;
+    return GPC_OK;
 }
 
 int gpc_debug_peak(gpc_handle* h, int kind, double* value) {

@@ -153,7 +153,8 @@ int gpc_get_stream(gpc_handle* h, void** stream);
  * (N, quaternion, mean, RGB mean, BV, alpha); gpc_load installs them into a handle so that gpc_decompress
  * can run in another process.  File layout: "GPCB200\0" | u32 version | config (res, sz, capacity, s0,
  * eps_tol, sigmaf_sq, l_sq) | i64 n_patches | i64 n_bv_total | nbv[i32] | quat[4 f64] | mean[3 f64] |
- * rgbmean[3 f64] | bv1, bv2, alpha [f64, packed]. */
+ * rgbmean[3 f64] | bv1, bv2, alpha [f64, packed] | (version 2) i32 has_rgb | rgb_s0, rgb_eps_tol | i64 n_bv_rgb |
+ * rgb nbv[i32] | rgb bv1, bv2 [f64] | rgb alpha [3 f64 per BV]. */
 int gpc_save(gpc_handle* h, const char* path, int64_t* bytes_written);
 int gpc_get_config(const gpc_handle* h, gpc_config* cfg);  /* the handle's current configuration (gpc_load updates it) */
 int gpc_load(gpc_handle* h, const char* path);

@@ -66,3 +66,16 @@ def test_rgb_sharded_matches_single():
         h.compress(cloud)
         parts.append(h.decompress())
     assert np.array_equal(np.concatenate(parts), want)
+
+
+def test_rgb_survives_the_wire_format(tmp_path):
+    import gp_compressor_b200 as G
+    cloud = synth.c1_planar_bumps(15000, seed=2)
+    a = G.Handle(res=F32(0.15), sz=6, capacity=50, rgb=1)
+    a.compress(cloud)
+    want = a.decompress()
+    a.save(tmp_path / "p.gpc")
+    b = G.Handle()
+    b.load_file(tmp_path / "p.gpc")
+    assert b.cfg.rgb == 1
+    assert np.array_equal(b.decompress(), want)
