@@ -327,6 +327,12 @@ def main():
                 "peak": (smem_peak if f2 >= f1 else fp64_peak) / 1e9, "unit": "GB/s" if f2 >= f1 else "GFLOP/s", "frac": max(f1, f2),
                 "traffic": None, "peak_source": "measured here: independent DFMA chains %.1f TFLOP/s, conflict-free LDS.128 %.1f TB/s (gpc_debug_peak)" % (fp64_peak / 1e12, smem_peak / 1e12), "stage_ms": stage_ms[dom],
                 "fp64_frac": f1, "smem_frac": f2, "mean_n": fit_stats["sum_n"] / max(1, fit_stats["n_add"] - fit_stats["n_first"])}
+        if args.workload == "c2" and not args.points and not RGB:
+            # one `ncu --set full` capture of the same command (profiles/r1h_summary.md): bucket-0 warp kernel, per launch
+            roof["traffic"] = 158.2e6
+            roof["note"] = ("N ~ 10 under the reference hyper-parameters: the kernel is instruction-issue bound (ncu: 74 % issue-slot "
+                            "utilisation, 64 regs, 32 warps/SM, ~25 % of instructions are FP64 math), so neither roofline is the constraint; "
+                            "with capacity binding (--workload c2bind) the same kernels reach 0.23 of the LDS.128 roofline")
     elif dom == "ms_predict":
         fl = n_dec * (37.0 * (sizes.n_bv_total / max(1, n_dec / (cfg["sz"] ** 2))) + 18)
         sec = stage_ms[dom] * 1e-3
