@@ -1218,11 +1218,9 @@ constexpr size_t cta_smem_bytes() { return (size_t)Smem<LD, DOUT>::kDoubles * si
 template <int LD, int RB, int NT, int LD_IN, bool SPILL, int DOUT>
 cudaError_t launch_cta_bucket(const SogpArgs& a, cudaStream_t st) {
     constexpr size_t smem = SPILL ? 0 : cta_smem_bytes<LD, DOUT>();
-    static bool configured = false;
-    if (smem > 48 * 1024 && !configured) {
+    if (smem > 48 * 1024) {  // per device and cheap: set on every launch (handles may live on different GPUs)
         cudaError_t e = cudaFuncSetAttribute(sogp_fit_kernel<LD, RB, NT, LD_IN, SPILL, DOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     sogp_fit_kernel<LD, RB, NT, LD_IN, SPILL, DOUT><<<a.n_work, NT, smem, st>>>(a);
     return cudaGetLastError();

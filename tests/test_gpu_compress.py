@@ -211,3 +211,18 @@ def test_wire_format_round_trip(G, oracle_mod, tmp_path):
         bad = tmp_path / "bad.gpc"
         bad.write_bytes(b"not a parameter file")
         G.Handle().load_file(bad)
+
+
+def test_handle_reuse_across_different_clouds(G, oracle_mod):
+    """One handle, clouds of different sizes and extents in sequence (buffers are grow-only and reused)."""
+    cfg = dict(res=F32(0.1), sz=4, capacity=30)
+    h = G.Handle(**cfg)
+    o = oracle_mod.Oracle(**cfg)
+    for cloud in (synth.c2_indoor(30000, seed=1), synth.c1_planar_bumps(4000, seed=2), synth.c2_indoor(60000, seed=3),
+                  synth.pack_cloud(np.array([[5.0, 5.0, 5.0]])), synth.c3_dense_floor(20000, seed=4, side=1.0)):
+        h.compress(cloud)
+        want = o.compress(cloud)
+        assert eq(h.assignment()["owner"], o.binning()["owner"])
+        assert eq(h.params()["alpha"], want["alpha"])
+        co, _ = o.decode(want_heights=False)
+        assert eq(h.decompress(), co)
