@@ -154,41 +154,34 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
     if (c.capacity < 1) return fail(h, GPC_ERR_INVALID, "capacity must be >= 1 (the reference's -1 / 0 modes are not built)");
     const int need_ld = c.capacity + 1;
     if (need_ld > sogp_bucket_ld(4)) return fail(h, GPC_ERR_INVALID, "capacity > 201 is not supported");
-    // shard bounds from the host copy of the offsets
-    std::vector<int64_t> hoff(P + 1);
-    CK(cudaMemcpyAsync(hoff.data(), h->off.p, (P + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    h->n_claimed = hoff[P];
-    shard_range(hoff, c.shard_rank, c.shard_count, &h->patch_lo, &h->patch_hi);
-    const int64_t lo = h->patch_lo, hi = h->patch_hi, PL = hi - lo;
-    h->s_begin = hoff[lo];
-    h->s_count = hoff[hi] - hoff[lo];
-    const int64_t S = h->n_claimed;
+    // shard bounds, rand-stream window and the largest patch: computed on the device, nine scalars come back
     size_t t0 = tm.mark();
-    // rand stream bookkeeping (all patches: the stream is global across patches)
     const int mult = c.shuffle ? (c.rgb_rand ? 2 : 1) : 0;
-    uint64_t draws_lo = 0, draws_hi = 0, draws_all = 0;
-    int64_t max_np = 0;
-    for (int64_t p = 0; p < P; p++) {
-        int64_t n = hoff[p + 1] - hoff[p];
-        if (n > max_np) max_np = n;
-        uint64_t d = n > 0 ? (uint64_t)(n - 1) * mult : 0;
-        if (p == lo) draws_lo = draws_all;
-        draws_all += d;
-        if (p + 1 == hi) draws_hi = draws_all;
-    }
-    if (PL == 0) draws_hi = draws_lo;
+    CK(h->draws.reserve((P + 1) * sizeof(int64_t)));
+    CK(h->roff.reserve((P + 2) * sizeof(int64_t)));
+    CK(h->scan_tmp.reserve(scan_tmp_bytes(P + 1)));
+    CK(h->small.reserve(256));
+    int64_t* d_plan = h->small.as<int64_t>() + 8;
+    launch_fit_plan(h->off.as<int64_t>(), P, mult, c.shard_rank, c.shard_count, h->draws.as<int64_t>(), h->roff.as<int64_t>(),
+                    h->scan_tmp.p, d_plan, st);
+    int64_t plan[9];
+    CK(cudaMemcpyAsync(plan, d_plan, sizeof(plan), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    h->n_claimed = plan[0];
+    h->patch_lo = plan[1];
+    h->patch_hi = plan[2];
+    const int64_t lo = h->patch_lo, hi = h->patch_hi, PL = hi - lo;
+    h->s_begin = plan[3];
+    h->s_count = plan[4] - plan[3];
+    const int64_t S = h->n_claimed;
+    const uint64_t draws_lo = (uint64_t)plan[5], draws_hi = (uint64_t)plan[6], draws_all = (uint64_t)plan[7];
+    const int64_t max_np = plan[8];
     CK(h->perm.reserve(std::max<int64_t>(S, 1) * sizeof(int32_t)));
     CK(h->patch_of.reserve(std::max<int64_t>(S, 1) * sizeof(int32_t)));
     CK(h->fx1.reserve(std::max<int64_t>(S, 1) * sizeof(double)));
     CK(h->fx2.reserve(std::max<int64_t>(S, 1) * sizeof(double)));
     CK(h->fy.reserve(std::max<int64_t>(S, 1) * sizeof(double)));
     if (PL > 0 && h->s_count > 0) {
-        CK(h->draws.reserve((P + 1) * sizeof(int64_t)));
-        CK(h->roff.reserve((P + 2) * sizeof(int64_t)));
-        CK(h->scan_tmp.reserve(scan_tmp_bytes(P + 1)));
-        launch_patch_draws(h->off.as<int64_t>(), P, mult, h->draws.as<int64_t>(), st);
-        launch_exclusive_scan_i64(h->draws.as<int64_t>(), h->roff.as<int64_t>(), P, h->scan_tmp.p, st);
         const int64_t nd = (int64_t)(draws_hi - draws_lo);
         if (c.shuffle && nd > 0) {
             CK(h->rnd.reserve(nd * sizeof(uint32_t)));
@@ -447,7 +440,7 @@ int run_binning(gpc_handle* h, StageTimer& tm) {
     const uint8_t* cloud = h->cloud.as<uint8_t>();
     if (n > 0x7fffffff) return fail(h, GPC_ERR_INVALID, "more than 2^31-1 points");
     h->have_binning = h->have_frames = h->have_fit = false;
-    CK(h->small.reserve(64));
+    CK(h->small.reserve(256));
     unsigned long long* d_best = h->small.as<unsigned long long>();  // [0] index, [1..2] the point (4 floats)
     unsigned long long* d_nvalid = d_best + 4;
     // ---- lattice replay ----

@@ -88,7 +88,9 @@ void launch_exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, void*
 
 // ---- K6b/c: per-patch shuffle and gather into the fit stream -------------------------------
 // draws[p] = (n_p > 0 ? (n_p - 1) * mult : 0)
-void launch_patch_draws(const int64_t* off, int64_t n_patches, int mult, int64_t* draws, cudaStream_t s);
+// draws[p] + exclusive scan roff[0..P] + plan9 = { n_claimed, lo, hi, off[lo], off[hi], roff[lo], roff[hi], roff[P], max n_p }
+void launch_fit_plan(const int64_t* off, int64_t n_patches, int mult, int rank, int count, int64_t* draws, int64_t* roff, void* scan_tmp,
+                     int64_t* plan9, cudaStream_t s);
 // perm (patch-local) for every patch; rnd holds the stream starting at the handle's offset
 void launch_shuffle(const int64_t* off, int64_t n_patches, const int64_t* roff, const uint32_t* rnd,
                     int do_shuffle, int32_t* perm, int32_t* patch_of, int64_t s_begin, int64_t s_count,

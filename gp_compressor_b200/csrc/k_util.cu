@@ -103,15 +103,57 @@ void launch_exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, void*
 // rand() draws per patch: the height GP shuffles n_p points with n_p - 1 draws, then the
 // RGB field GP does the same (gp_compressor.cpp:162-163), so mult = 2 in the full path.
 // ------------------------------------------------------------------------------------
-__global__ void patch_draws_kernel(const int64_t* __restrict__ off, int64_t n_patches, int mult, int64_t* __restrict__ draws) {
+__global__ void patch_draws_kernel(const int64_t* __restrict__ off, int64_t n_patches, int mult, int64_t* __restrict__ draws,
+                                   unsigned long long* __restrict__ max_np) {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_patches) return;
-    int64_t n = off[p + 1] - off[p];
-    draws[p] = (n > 0) ? (n - 1) * mult : 0;
+    int64_t n = 0;
+    if (p < n_patches) {
+        n = off[p + 1] - off[p];
+        draws[p] = (n > 0) ? (n - 1) * mult : 0;
+    }
+    // largest patch (selects the shuffle kernel): warp max, one atomic per warp
+    unsigned long long m = (unsigned long long)n;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        unsigned long long v = __shfl_xor_sync(0xffffffffu, m, o);
+        m = v > m ? v : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(max_np, m);
 }
-void launch_patch_draws(const int64_t* off, int64_t n_patches, int mult, int64_t* draws, cudaStream_t s) {
-    if (n_patches <= 0) return;
-    patch_draws_kernel<<<(unsigned)((n_patches + 255) / 256), 256, 0, s>>>(off, n_patches, mult, draws);
+
+// Shard bounds and the rand-stream window of the shard, on the device (no per-patch work on the host):
+// plan = { n_claimed, lo, hi, off[lo], off[hi], roff[lo], roff[hi], roff[P] }.  Same rule as gpc_shard_range:
+// bound k = first p with off[p] >= floor(total * k / count).
+__global__ void fit_plan_kernel(const int64_t* __restrict__ off, const int64_t* __restrict__ roff, int64_t P, int rank, int count,
+                                int64_t* __restrict__ plan) {
+    const int64_t total = off[P];
+    int64_t b[2];
+    for (int e = 0; e < 2; e++) {
+        const int k = rank + e;
+        if (k <= 0) { b[e] = 0; continue; }
+        if (k >= count) { b[e] = P; continue; }
+        const int64_t target = (total / count) * k + ((total % count) * k) / count;
+        int64_t lo = 0, hi = P;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) / 2;
+            if (off[mid] >= target) hi = mid; else lo = mid + 1;
+        }
+        b[e] = lo;
+    }
+    plan[0] = total; plan[1] = b[0]; plan[2] = b[1]; plan[3] = off[b[0]]; plan[4] = off[b[1]];
+    plan[5] = roff[b[0]]; plan[6] = roff[b[1]]; plan[7] = roff[P];
+}
+
+void launch_fit_plan(const int64_t* off, int64_t n_patches, int mult, int rank, int count, int64_t* draws, int64_t* roff, void* scan_tmp,
+                     int64_t* plan9, cudaStream_t s) {
+    cudaMemsetAsync(plan9 + 8, 0, sizeof(int64_t), s);
+    if (n_patches > 0) {
+        patch_draws_kernel<<<(unsigned)((n_patches + 255) / 256), 256, 0, s>>>(off, n_patches, mult, draws,
+                                                                             reinterpret_cast<unsigned long long*>(plan9 + 8));
+        g_launches++;
+    }
+    launch_exclusive_scan_i64(draws, roff, n_patches, scan_tmp, s);
+    fit_plan_kernel<<<1, 1, 0, s>>>(off, roff, n_patches, rank, count, plan9);
     g_launches++;
 }
 
