@@ -226,3 +226,14 @@ def test_handle_reuse_across_different_clouds(G, oracle_mod):
         assert eq(h.params()["alpha"], want["alpha"])
         co, _ = o.decode(want_heights=False)
         assert eq(h.decompress(), co)
+
+
+def test_extreme_coordinates_and_depth_overflow(G, oracle_mod):
+    rng = np.random.default_rng(2)
+    # far from the origin and negative: float spacing ~ 0.06 at 1e6, still a valid lattice
+    xyz = rng.uniform(-1, 1, (4000, 3)) * [3, 3, 0.05] + [-1.0e5, 2.0e5, 50.0]
+    compare_all(G, oracle_mod, synth.pack_cloud(xyz), res=F32(0.25), capacity=10)
+    # an extent / resolution ratio beyond 2^21 voxels per axis cannot be keyed in 63 bits: clean error, no crash
+    far = synth.pack_cloud(np.array([[0.0, 0.0, 0.0], [1.0e6, 0.0, 0.0]]))
+    with pytest.raises(G.GpcError):
+        G.Handle(res=F32(0.01)).compress(far)

@@ -79,3 +79,15 @@ def test_rgb_survives_the_wire_format(tmp_path):
     b.load_file(tmp_path / "p.gpc")
     assert b.cfg.rgb == 1
     assert np.array_equal(b.decompress(), want)
+
+
+def test_large_patches_use_the_global_shuffle_path():
+    """Patches with more than 1024 points take the thread-per-patch global-memory shuffle (both the height GP's and the
+    RGB field GP's), smaller ones the shared-memory warp shuffle: mix both in one cloud."""
+    rng = np.random.default_rng(3)
+    dense = rng.uniform(0.0, 0.19, (9000, 3)) * [1, 1, 0.05]          # ~4 voxels with > 2000 points each
+    sparse = rng.uniform(1.0, 3.0, (3000, 3)) * [1, 1, 0.02]
+    xyz = np.concatenate([dense, sparse])[rng.permutation(12000)]
+    rgb = rng.integers(0, 256, (12000, 3)).astype(np.uint8)
+    h, o, _ = run(synth.pack_cloud(xyz, rgb), res=F32(0.1), sz=3, capacity=20)
+    assert np.diff(h.patches(frames=False, binning=False)["patch_off"]).max() > 1024
