@@ -39,7 +39,7 @@ struct gpc_handle {
     DevBuf perm_rgb, fcr, fcg, fcb, r_nbv, r_flags, r_alpha0, r_alpha1, r_alpha2, r_b1, r_b2, r_bidx, kstats_rgb;
     bool have_rgb = false;
     DevBuf quat, mean, rgbmean, Rm, center, code, ncand, owner, st_idx;
-    DevBuf tmpA, tmpB, tmpC;
+    DevBuf tmpA, tmpB, tmpC, lat_state;
     // binning scratch
     DevBuf keys, keys2, vals, vals2, ovals, ovals2, sort_tmp, flags64, ex, leaf_of, leaf_start, leaf_code_a, spt, nbr, nnbr,
         center_a, Rm_a, ncand_a, pt0, pt1, pt2, hbuf, rgb, leaf_sums;
@@ -377,55 +377,6 @@ int run_decode(gpc_handle* h, bool want_cloud, bool want_heights, StageTimer& tm
     return GPC_OK;
 }
 
-// ---- PCL OctreePointCloud::adoptBoundingBoxToPoint / getKeyBitSize for one point [RECALLED PCL 1.7] ----
-// Scalar control logic on the host (a handful of doubles per growth event); the search for the
-// point that triggers each event runs on the device (first_violation_kernel).
-struct HostLattice {
-    double mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
-    double res = 0;
-    unsigned depth = 0;
-    bool defined = false;
-};
-
-void lattice_adopt(HostLattice& L, const float* p) {
-    const float minValue = std::numeric_limits<float>::epsilon();
-    for (;;) {
-        bool lo[3], up[3];
-        for (int a = 0; a < 3; a++) { lo[a] = (double)p[a] < L.mn[a]; up[a] = (double)p[a] >= L.mx[a]; }
-        if (L.defined && !(lo[0] || lo[1] || lo[2] || up[0] || up[1] || up[2])) break;
-        if (L.defined) {
-            double side = (double)(1u << L.depth) * L.res;
-            for (int a = 0; a < 3; a++)
-                if (!up[a]) L.mn[a] -= side;
-            L.depth++;
-            side = (double)(1u << L.depth) * L.res - minValue;
-            for (int a = 0; a < 3; a++) L.mx[a] = L.mn[a] + side;
-            if (L.depth > 30) break;
-        } else {
-            for (int a = 0; a < 3; a++) { L.mn[a] = (double)p[a] - L.res / 2; L.mx[a] = (double)p[a] + L.res / 2; }
-            unsigned mk[3];
-            for (int a = 0; a < 3; a++) mk[a] = (unsigned)((L.mx[a] - L.mn[a]) / L.res);
-            unsigned maxv = std::max(std::max(std::max(mk[0], mk[1]), mk[2]), 2u);
-            L.depth = (unsigned)std::ceil(std::log((double)maxv) / std::log(2.0) - minValue);
-            double side = (double)(1u << L.depth) * L.res - minValue;
-            for (int a = 0; a < 3; a++) {
-                double over = (side - (L.mx[a] - L.mn[a])) / 2.0;
-                L.mn[a] -= over;
-                L.mx[a] += over;
-            }
-            L.defined = true;
-        }
-    }
-}
-
-LatticeDev to_dev(const HostLattice& L) {
-    LatticeDev d;
-    for (int a = 0; a < 3; a++) { d.mn[a] = L.mn[a]; d.mx[a] = L.mx[a]; }
-    d.res = L.res;
-    d.depth = L.depth;
-    return d;
-}
-
 int bits_for(uint64_t v) {  // bits needed to represent values 0..v
     int b = 1;
     while (b < 64 && (v >> b)) b++;
@@ -441,26 +392,29 @@ int run_binning(gpc_handle* h, StageTimer& tm) {
     if (n > 0x7fffffff) return fail(h, GPC_ERR_INVALID, "more than 2^31-1 points");
     h->have_binning = h->have_frames = h->have_fit = false;
     CK(h->small.reserve(256));
-    unsigned long long* d_best = h->small.as<unsigned long long>();  // [0] index, [1..2] the point (4 floats)
-    unsigned long long* d_nvalid = d_best + 4;
-    // ---- lattice replay ----
+    unsigned long long* d_nvalid = h->small.as<unsigned long long>() + 4;
+    // ---- lattice replay: search + adopt on the device, the host only polls "found" ----
     size_t t0 = tm.mark();
-    HostLattice L;
-    L.res = c.res;
+    CK(h->lat_state.reserve(sizeof(LatticeState)));
+    LatticeState L0;
+    std::memset(&L0, 0, sizeof(L0));
+    L0.lat.res = c.res;
+    L0.best = ~0ull;
+    CK(cudaMemcpyAsync(h->lat_state.p, &L0, sizeof(L0), cudaMemcpyHostToDevice, st));
+    LatticeState Lh = L0;
     int64_t start = 0;
     for (;;) {
-        launch_first_violation(cloud, n, start, to_dev(L), L.defined ? 1 : 0, d_best, st);
-        unsigned long long rb[3] = {0, 0, 0};
-        CK(cudaMemcpyAsync(rb, d_best, sizeof(rb), cudaMemcpyDeviceToHost, st));
+        launch_lattice_step(cloud, n, n - start, h->lat_state.as<LatticeState>(), st);
+        CK(cudaMemcpyAsync(&Lh, h->lat_state.p, sizeof(Lh), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        const unsigned long long best = rb[0];
-        if (best == ~0ull) break;
-        float p[4];
-        std::memcpy(p, &rb[1], sizeof(p));
-        lattice_adopt(L, p);
-        if (L.depth > 21) return fail(h, GPC_ERR_OVERFLOW, "octree deeper than 21 levels: res too small for the cloud extent");
-        start = (int64_t)best + 1;
+        if (!Lh.found) break;
+        if (Lh.lat.depth > 21) return fail(h, GPC_ERR_OVERFLOW, "octree deeper than 21 levels: res too small for the cloud extent");
+        start = Lh.start;
     }
+    struct { unsigned depth; bool defined; double mn[3]; } L;
+    L.depth = Lh.lat.depth;
+    L.defined = Lh.defined != 0;
+    for (int a = 0; a < 3; a++) L.mn[a] = Lh.lat.mn[a];
     h->depth = L.depth;
     for (int a = 0; a < 3; a++) h->lattice_min[a] = L.mn[a];
     size_t t1 = tm.mark();
@@ -475,7 +429,7 @@ int run_binning(gpc_handle* h, StageTimer& tm) {
         h->have_binning = h->have_frames = true;
         return GPC_OK;
     }
-    const LatticeDev lat = to_dev(L);
+    const LatticeDev lat = Lh.lat;
     // ---- keys + Morton sort ----
     CK(h->keys.reserve(n * sizeof(uint64_t)));
     CK(h->keys2.reserve(n * sizeof(uint64_t)));
@@ -659,7 +613,7 @@ void gpc_destroy(gpc_handle* h) {
                       &h->dumpC, &h->dumpQ, &h->queue0, &h->queue1, &h->hand0, &h->hand1, &h->spill, &h->qcount, &h->kstats, &h->bv_off, &h->palpha, &h->pb1, &h->pb2, &h->pidx, &h->perm_rgb, &h->fcr, &h->fcg, &h->fcb, &h->r_nbv, &h->r_flags,
                       &h->r_alpha0, &h->r_alpha1, &h->r_alpha2, &h->r_b1, &h->r_b2, &h->r_bidx, &h->kstats_rgb, &h->nonempty, &h->slot, &h->out32,
                       &h->heights, &h->quat, &h->mean, &h->rgbmean, &h->Rm, &h->center, &h->code, &h->ncand, &h->owner,
-                      &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
+                      &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->lat_state, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
                       &h->ovals2, &h->sort_tmp, &h->flags64, &h->ex, &h->leaf_of, &h->leaf_start, &h->leaf_code_a, &h->spt,
                       &h->nbr, &h->nnbr, &h->center_a, &h->Rm_a, &h->ncand_a, &h->pt0, &h->pt1, &h->pt2, &h->hbuf, &h->rgb, &h->leaf_sums};
     for (DevBuf* b : bufs) b->release();

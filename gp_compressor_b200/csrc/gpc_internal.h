@@ -42,8 +42,15 @@ struct LatticeDev {          // PCL octree bounding box (doubles), voxel size an
     double res;
     uint32_t depth;
 };
-void launch_first_violation(const uint8_t* cloud, int64_t n, int64_t start, const LatticeDev& lat, int defined,
-                            unsigned long long* best, cudaStream_t s);
+struct LatticeState {        // device-resident state of the lattice replay
+    LatticeDev lat;
+    unsigned long long best; // index of the point found by the current search (~0: none)
+    int64_t start;           // first index the next search looks at
+    int32_t defined;         // PCL bounding_box_defined_
+    int32_t found;           // 1 if the last step adopted a point
+};
+// searches points [st->start, n) (tiles_hint = how many points can still matter) and grows the box for the first violator
+void launch_lattice_step(const uint8_t* cloud, int64_t n, int64_t tiles_hint, LatticeState* st, cudaStream_t s);
 void launch_point_keys(const uint8_t* cloud, int64_t n, const LatticeDev& lat, uint64_t* keys, uint32_t* vals, cudaStream_t s);
 void launch_count_valid(const uint64_t* sorted_keys, int64_t n, uint32_t depth, unsigned long long* n_valid, cudaStream_t s);
 size_t radix_sort_tmp_bytes(int64_t n);

@@ -47,20 +47,25 @@ __device__ __forceinline__ uint64_t morton(uint32_t kx, uint32_t ky, uint32_t kz
     return (spread3(kx) << 2) | (spread3(ky) << 1) | spread3(kz);
 }
 
-// ---- lattice replay: first point (index >= start) that is finite and, when the box is
-// defined, violates [mn, mx)  (PCL adoptBoundingBoxToPoint) ---------------------------------
-__global__ void __launch_bounds__(256) first_violation_kernel(const uint8_t* __restrict__ cloud, int64_t n, int64_t start,
-                                                              LatticeDev lat, int defined,
-                                                              unsigned long long* __restrict__ best) {
+// ---- lattice replay (PCL OctreePointCloud::addPointsFromInputCloud -> adoptBoundingBoxToPoint) -------------
+// The bounding box lives in device memory (LatticeState).  Per growth event: (1) every CTA scans its tile of
+// the cloud for the first finite point at index >= state.start that violates [mn, mx) (or any finite point while
+// the box is undefined); (2) one thread grows the box for that point exactly as PCL does [RECALLED PCL 1.7:
+// adoptBoundingBoxToPoint / getKeyBitSize] and advances state.start.  The host only polls state.best.
+__global__ void __launch_bounds__(256) first_violation_kernel(const uint8_t* __restrict__ cloud, int64_t n, LatticeState* __restrict__ st) {
     __shared__ unsigned long long sbest;
     __shared__ int skip;
+    const int64_t start = st->start;
     const int64_t tile = (int64_t)blockIdx.x * 4096;
     if (threadIdx.x == 0) {
         sbest = ~0ull;
-        skip = (unsigned long long)(start + tile) >= *(volatile unsigned long long*)best;  // an earlier hit exists
+        skip = (start + tile >= n) || (unsigned long long)(start + tile) >= *(volatile unsigned long long*)&st->best;  // an earlier hit exists
     }
     __syncthreads();
     if (skip) return;
+    const int defined = st->defined;
+    const double mn0 = st->lat.mn[0], mn1 = st->lat.mn[1], mn2 = st->lat.mn[2];
+    const double mx0 = st->lat.mx[0], mx1 = st->lat.mx[1], mx2 = st->lat.mx[2];
     unsigned long long mine = ~0ull;
     for (int r = 0; r < 16; r++) {
         int64_t i = start + tile + r * 256 + threadIdx.x;
@@ -70,22 +75,58 @@ __global__ void __launch_bounds__(256) first_violation_kernel(const uint8_t* __r
         bool hit = !defined;
         if (defined) {
             const double x = p.x, y = p.y, z = p.z;
-            hit = x < lat.mn[0] || y < lat.mn[1] || z < lat.mn[2] || x >= lat.mx[0] || y >= lat.mx[1] || z >= lat.mx[2];
+            hit = x < mn0 || y < mn1 || z < mn2 || x >= mx0 || y >= mx1 || z >= mx2;
         }
         if (hit) { mine = (unsigned long long)i; break; }
     }
     if (mine != ~0ull) atomicMin(&sbest, mine);
     __syncthreads();
-    if (threadIdx.x == 0 && sbest != ~0ull) atomicMin(best, sbest);
+    if (threadIdx.x == 0 && sbest != ~0ull) atomicMin(&st->best, sbest);
 }
 
-// copies the winning point next to the index so that the host needs one read-back per growth event
-__global__ void fetch_violator_kernel(const uint8_t* __restrict__ cloud, unsigned long long* __restrict__ best) {
-    const unsigned long long b = best[0];
+__global__ void lattice_adopt_kernel(const uint8_t* __restrict__ cloud, LatticeState* __restrict__ st) {
+    const unsigned long long b = st->best;
+    st->found = (b != ~0ull) ? 1 : 0;
     if (b == ~0ull) return;
-    const float4 p = *reinterpret_cast<const float4*>(cloud + (int64_t)b * GPC_POINT_BYTES);
-    float* o = reinterpret_cast<float*>(best + 1);
-    o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = 0.0f;
+    const float4 pt = *reinterpret_cast<const float4*>(cloud + (int64_t)b * GPC_POINT_BYTES);
+    const float p[3] = {pt.x, pt.y, pt.z};
+    LatticeDev& L = st->lat;
+    const float minValue = 1.1920929e-07f;  // std::numeric_limits<float>::epsilon()
+    for (;;) {
+        bool lo[3], up[3];
+        for (int a = 0; a < 3; a++) { lo[a] = (double)p[a] < L.mn[a]; up[a] = (double)p[a] >= L.mx[a]; }
+        if (st->defined && !(lo[0] || lo[1] || lo[2] || up[0] || up[1] || up[2])) break;
+        if (st->defined) {
+            double side = __dmul_rn((double)(1u << L.depth), L.res);
+            for (int a = 0; a < 3; a++)
+                if (!up[a]) L.mn[a] = __dadd_rn(L.mn[a], -side);
+            L.depth++;
+            side = __dadd_rn(__dmul_rn((double)(1u << L.depth), L.res), -(double)minValue);
+            for (int a = 0; a < 3; a++) L.mx[a] = __dadd_rn(L.mn[a], side);
+            if (L.depth > 30) break;
+        } else {
+            const double hr = __ddiv_rn(L.res, 2.0);
+            for (int a = 0; a < 3; a++) { L.mn[a] = __dadd_rn((double)p[a], -hr); L.mx[a] = __dadd_rn((double)p[a], hr); }
+            // getKeyBitSize(): max_voxels = max(keys, 2) = 2 for a box of one voxel, depth = ceil(log2(2) - eps) = 1
+            unsigned maxv = 2u;
+            for (int a = 0; a < 3; a++) {
+                const unsigned mk = __double2uint_rz(__ddiv_rn(__dadd_rn(L.mx[a], -L.mn[a]), L.res));
+                maxv = mk > maxv ? mk : maxv;
+            }
+            unsigned depth = 0;
+            while ((1u << depth) < maxv) depth++;  // == ceil(log2(maxv) - float eps) for integer maxv >= 2
+            L.depth = depth;
+            const double side = __dadd_rn(__dmul_rn((double)(1u << L.depth), L.res), -(double)minValue);
+            for (int a = 0; a < 3; a++) {
+                const double over = __ddiv_rn(__dadd_rn(side, -__dadd_rn(L.mx[a], -L.mn[a])), 2.0);
+                L.mn[a] = __dadd_rn(L.mn[a], -over);
+                L.mx[a] = __dadd_rn(L.mx[a], over);
+            }
+            st->defined = 1;
+        }
+    }
+    st->start = (int64_t)b + 1;
+    st->best = ~0ull;
 }
 
 // ---- K1: voxel key -> Morton code (PCL genOctreeKeyforPoint) --------------------------------
@@ -511,13 +552,12 @@ __global__ void __launch_bounds__(128) patch_frames_kernel(const int64_t* __rest
 
 }  // namespace
 
-void launch_first_violation(const uint8_t* cloud, int64_t n, int64_t start, const LatticeDev& lat, int defined,
-                            unsigned long long* best, cudaStream_t s) {
-    cudaMemsetAsync(best, 0xff, sizeof(unsigned long long), s);
-    if (start >= n) return;
-    int64_t tiles = (n - start + 4095) / 4096;
-    first_violation_kernel<<<(unsigned)tiles, 256, 0, s>>>(cloud, n, start, lat, defined, best);
-    fetch_violator_kernel<<<1, 1, 0, s>>>(cloud, best);
+// one growth event of the lattice replay (search + adopt); st->found tells the host whether anything happened
+void launch_lattice_step(const uint8_t* cloud, int64_t n, int64_t tiles_hint, LatticeState* st, cudaStream_t s) {
+    int64_t tiles = (tiles_hint + 4095) / 4096;
+    if (tiles < 1) tiles = 1;
+    first_violation_kernel<<<(unsigned)tiles, 256, 0, s>>>(cloud, n, st);
+    lattice_adopt_kernel<<<1, 1, 0, s>>>(cloud, st);
     g_launches += 2;
 }
 
