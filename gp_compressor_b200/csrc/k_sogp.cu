@@ -223,25 +223,29 @@ __global__ void __launch_bounds__(32, DOUT == 1 ? 32 : 20) sogp_fit_warp_kernel(
         double rv = 0.0;
         if (r < N) rv = row4_padded16(Mrow, sm.kv, N);
         const double el = __shfl_down_sync(0xffffffffu, rv, 16);
-        // m = alpha'k, k'Ck, k'e_hat: one product per lane, shared butterfly
+        // m = alpha'k, k'Ck, k'e_hat.  N <= 16, so the canonical dot32 has zeros in partials 16..31 and its first
+        // butterfly step is the identity: a 4-step butterfly over 16 lanes gives the same bits.  The lower half-warp
+        // reduces k'Ck while the upper one reduces k'e_hat = k'Qk (its lanes own the Q rows); alpha'k rides along.
         double pm[DOUT];
 #pragma unroll
         for (int c = 0; c < DOUT; c++) pm[c] = act ? fma(alpha[c], kl, 0.0) : 0.0;
-        double pc = act ? fma(kl, rv, 0.0) : 0.0;
-        double pe = act ? fma(kl, el, 0.0) : 0.0;
+        double p2 = (r < N) ? fma(sm.kv[r], rv, 0.0) : 0.0;
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
+        for (int off = 8; off >= 1; off >>= 1) {
 #pragma unroll
             for (int c = 0; c < DOUT; c++) pm[c] = __dadd_rn(pm[c], shfl_xor_d(pm[c], off));
-            pc = __dadd_rn(pc, shfl_xor_d(pc, off));
-            pe = __dadd_rn(pe, shfl_xor_d(pe, off));
+            p2 = __dadd_rn(p2, shfl_xor_d(p2, off));
         }
+        const double pc = __shfl_sync(0xffffffffu, p2, 0), pe = __shfl_sync(0xffffffffu, p2, 16);
         const double s2 = __dadd_rn(kstar, pc);
         const double den = __dadd_rn(s20, s2);
-        const double rr = __ddiv_rn(-1.0, den);               // gaussian_noise.cpp:15-18
-        double q[DOUT];                                       // gaussian_noise.cpp:9-12 / gaussian_noise_3d.cpp:10-13
+        // one division for two quotients: the upper half-warp computes r = -1/den (gaussian_noise.cpp:15-18), the
+        // lower one q = (y - m)/den (gaussian_noise.cpp:9-12 / gaussian_noise_3d.cpp:10-13); q is only read by lanes < 16
+        double q[DOUT];
+        q[0] = __ddiv_rn(mat ? -1.0 : __dadd_rn(pt.y[0], -pm[0]), den);
+        const double rr = __shfl_sync(0xffffffffu, q[0], 16);
 #pragma unroll
-        for (int c = 0; c < DOUT; c++) q[c] = __ddiv_rn(__dadd_rn(pt.y[c], -pm[c]), den);
+        for (int c = 1; c < DOUT; c++) q[c] = __ddiv_rn(__dadd_rn(pt.y[c], -pm[c]), den);
         double gamma = __dadd_rn(kstar, -pe);                 // :144
         if (gamma < tiny12()) gamma = 0.0;
         if (gamma < eps_tol) {
