@@ -339,10 +339,15 @@ int run_decode(gpc_handle* h, bool want_cloud, bool want_heights, StageTimer& tm
     CK(h->nonempty.reserve((PL + 1) * sizeof(int64_t)));
     CK(h->slot.reserve((PL + 2) * sizeof(int64_t)));
     CK(h->scan_tmp.reserve(scan_tmp_bytes(PL + 1)));
-    launch_flag_nonempty(h->nbv.as<int32_t>(), PL, h->nonempty.as<int64_t>(), st);
+    const bool with_rgb = h->have_rgb && h->have_frames;
+    CK(h->small.reserve(256));
+    int32_t* d_maxes = h->small.as<int32_t>() + 48;
+    launch_flag_nonempty(h->nbv.as<int32_t>(), with_rgb ? h->r_nbv.as<int32_t>() : nullptr, PL, h->nonempty.as<int64_t>(), d_maxes, st);
     launch_exclusive_scan_i64(h->nonempty.as<int64_t>(), h->slot.as<int64_t>(), PL, h->scan_tmp.p, st);
     int64_t n_nonempty = 0;
+    int32_t maxes[2] = {0, 0};
     CK(cudaMemcpyAsync(&n_nonempty, h->slot.as<int64_t>() + PL, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(maxes, d_maxes, sizeof(maxes), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     h->n_decoded = n_nonempty * g2;
     if (want_cloud) CK(h->out32.reserve(std::max<int64_t>(h->n_decoded, 1) * GPC_POINT_BYTES));
@@ -362,15 +367,17 @@ int run_decode(gpc_handle* h, bool want_cloud, bool want_heights, StageTimer& tm
     }
     a.rgb_nbv = nullptr;
     a.rgb_alpha[0] = a.rgb_alpha[1] = a.rgb_alpha[2] = a.rgb_b1 = a.rgb_b2 = nullptr;
-    if (h->have_rgb && h->have_frames) {
+    if (with_rgb) {
         a.rgb_nbv = h->r_nbv.as<int32_t>();
         a.rgb_alpha[0] = h->r_alpha0.as<double>(); a.rgb_alpha[1] = h->r_alpha1.as<double>(); a.rgb_alpha[2] = h->r_alpha2.as<double>();
         a.rgb_b1 = h->r_b1.as<double>(); a.rgb_b2 = h->r_b2.as<double>();
     }
+    a.nmax = std::max(maxes[0], 1); a.nrmax = with_rgb ? std::max(maxes[1], 1) : 0;
     a.res = c.res; a.sz = c.sz; a.p0 = c.sigmaf_sq; a.cl = kernel_cl(c);
     a.out32 = want_cloud ? h->out32.as<uint8_t>() : nullptr;
     a.heights = want_heights ? h->heights.as<double>() : nullptr;
-    launch_predict_grid(a, st);
+    if (launch_predict_grid(a, st) != cudaSuccess)
+        return fail(h, GPC_ERR_INVALID, "decode: sz x capacity too large for the shared-memory kernel tables");
     CK(cudaGetLastError());
     size_t t1 = tm.mark();
     tm.span(&h->stats.ms_predict, t0, t1);

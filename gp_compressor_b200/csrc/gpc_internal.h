@@ -160,12 +160,16 @@ struct PredictArgs {
     double p0, cl;
     uint8_t* out32;              // may be nullptr
     double* heights;             // may be nullptr
+    int nmax, nrmax;             // largest BV count of the height / RGB GPs (table sizing)
+    int rows, rowsP, nblk;       // set by launch_predict_grid: grid rows per block, padded, blocks per patch
+    int group_doubles;           // shared-memory doubles per patch block
+    int64_t n_groups;            // n_patches * nblk
 };
 void launch_compact_params(const int32_t* nbv, int64_t n_patches, int stride, const double* alpha, const double* b1,
                            const double* b2, const int32_t* idx, int64_t* widened, int64_t* bv_off, void* scan_tmp,
                            double* palpha, double* pb1, double* pb2, int32_t* pidx, cudaStream_t s);
-void launch_flag_nonempty(const int32_t* nbv, int64_t n, int64_t* flags, cudaStream_t s);
-void launch_predict_grid(const PredictArgs& a, cudaStream_t s);
+void launch_flag_nonempty(const int32_t* nbv, const int32_t* rgb_nbv, int64_t n, int64_t* flags, int32_t* maxes, cudaStream_t s);
+cudaError_t launch_predict_grid(const PredictArgs& a, cudaStream_t s);
 void launch_predict_points(const double* alpha, const double* b1, const double* b2, int N, const double* C,
                            double p0, double cl, double s20, const double* X, int64_t m, double* f,
                            double* sigma, cudaStream_t s);

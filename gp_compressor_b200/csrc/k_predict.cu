@@ -5,11 +5,16 @@
 // also computes the predictive variance k' C k per grid point and throws it away
 // (gp_compressor.cpp:333 never reads V_star); this kernel computes the mean only.
 //
-// One CTA per non-empty patch: alpha and BV staged in shared memory, each thread owns
-// grid points m = t, t + NT, ... (y outer, x inner as in :320-332), evaluates N RBF
-// kernels with the canonical 4-partial dot, applies the patch frame (rotation rebuilt
-// from the stored quaternion as Eigen's toRotationMatrix does, :339) and writes one
-// 32-byte PointXYZRGB record with two 16-byte stores.
+// The grid is a lattice, so the RBF kernel is evaluated separably: per patch and basis vector i the kernel
+// builds the tables  Ex_i[a] = p0 * exp(cl (X0_a - b1_i)^2)  and  Ey_i[b] = exp(cl (X1_b - b2_i)^2)  (N (sz + rows)
+// exps instead of N sz^2) and takes  k_i(a, b) = Ex_i[a] * Ey_i[b]  — within 3 ulp of the reference's
+// p0 * exp(cl ((X0-b1)^2 + (X1-b2)^2)); the oracle restates the same arithmetic, so outputs are bit-identical to it.
+// One CTA per (patch, block of grid rows): tables in shared memory, each thread owns R consecutive rows of one
+// column (y outer, x inner as in :320-332), accumulates the canonical 4-partial dot with one DMUL + one DFMA per
+// basis vector and point, applies the patch frame (rotation rebuilt from the stored quaternion as Eigen's
+// toRotationMatrix does, :339) and writes one 32-byte PointXYZRGB record with two 16-byte stores.
+#include <algorithm>
+
 #include "gpc_device.cuh"
 #include "gpc_internal.h"
 
@@ -39,92 +44,178 @@ __device__ __forceinline__ void quat_to_rot(const double* q, double* R) {
     R[6] = __dadd_rn(txz, -twy); R[7] = __dadd_rn(tyz, twx); R[8] = __dadd_rn(1.0, -__dadd_rn(txx, tyy));
 }
 
-__global__ void __launch_bounds__(PRED_T) predict_grid_kernel(PredictArgs a) {
-    extern __shared__ double sm[];
-    const int64_t p = blockIdx.x;
+// One (patch, block of grid rows) per group of G threads: G = 32 (four independent warps per CTA, for small grids)
+// or G = PRED_T.  Each thread owns R consecutive rows of one grid column.
+template <int R, int G>
+__global__ void __launch_bounds__(PRED_T, R == 1 ? 8 : 3) predict_grid_kernel(PredictArgs a) {
+    extern __shared__ double sm_all[];
+    const int64_t gi = (int64_t)blockIdx.x * (PRED_T / G) + threadIdx.x / G;
+    if (gi >= a.n_groups) return;
+    const int64_t p = gi / a.nblk;
+    const int rb = (int)(gi - p * a.nblk);
     const int N = a.nbv[p];
     if (N == 0) return;  // gp_compressor.cpp:299
-    double* al = sm;
-    double* b1 = al + N;
-    double* b2 = b1 + N;
     // RGB field GP of the patch (sparse_gp_field::predict, sparse_gp_field.hpp:284-320): its own BVs, 3 alphas
     const int NR = a.rgb_nbv ? a.rgb_nbv[p] : 0;
-    double* ra0 = b2 + N;
+    const int sz = a.sz, rowsP = a.rowsP;
+    const int row0 = rb * a.rows;
+    const int rows_here = min(a.rows, sz - row0);
+    double* sm = sm_all + (size_t)(threadIdx.x / G) * a.group_doubles;
+    double* Rm = sm;                 // 9 rotation entries, mean[3] at 9, cmean[3] at 12, packed mean colour at 15
+    double* mean = Rm + 9;
+    double* cmean = Rm + 12;
+    double* Ey = sm + 16;            // first: 16-byte aligned rows for the paired loads (rowsP is even when R > 1)
+    double* Xs = Ey + (size_t)N * rowsP;  // X0 per grid column
+    double* Ys = Xs + sz;            // X1 per grid row of this block
+    double* al = Ys + rowsP;
+    double* sb1 = al + N;
+    double* sb2 = sb1 + N;
+    double* Ex = sb2 + N;
+    double* ra0 = Ex + (size_t)N * sz;
     double* ra1 = ra0 + NR;
     double* ra2 = ra1 + NR;
     double* rb1 = ra2 + NR;
     double* rb2 = rb1 + NR;
-    __shared__ double R[9], mean[3], cmean[3];
-    __shared__ unsigned int rgba;
-    const int t = threadIdx.x;
+    double* REx = rb2 + NR;
+    double* REy = REx + (size_t)NR * sz;
+    const int t = threadIdx.x % G;
     const int64_t pb = p * a.stride;
-    for (int i = t; i < N; i += PRED_T) { al[i] = a.alpha[pb + i]; b1[i] = a.b1[pb + i]; b2[i] = a.b2[pb + i]; }
-    for (int i = t; i < NR; i += PRED_T) {
+    const double dsz = (double)sz;
+    // res*((double(x) + 0.5f)/double(sz) - 0.5f), gp_compressor.cpp:326-327
+    for (int i = t; i < sz; i += G) Xs[i] = __dmul_rn(a.res, __dadd_rn(__ddiv_rn(__dadd_rn((double)i, 0.5), dsz), -0.5));
+    for (int i = t; i < rowsP; i += G)
+        Ys[i] = __dmul_rn(a.res, __dadd_rn(__ddiv_rn(__dadd_rn((double)(row0 + i), 0.5), dsz), -0.5));
+    for (int i = t; i < N; i += G) { al[i] = a.alpha[pb + i]; sb1[i] = a.b1[pb + i]; sb2[i] = a.b2[pb + i]; }
+    for (int i = t; i < NR; i += G) {
         ra0[i] = a.rgb_alpha[0][pb + i]; ra1[i] = a.rgb_alpha[1][pb + i]; ra2[i] = a.rgb_alpha[2][pb + i];
         rb1[i] = a.rgb_b1[pb + i]; rb2[i] = a.rgb_b2[pb + i];
     }
-    if (t == 0) {
+    if (t == G - 1) {
+        unsigned int rgba = 255u << 24;
         if (a.quat) {
-            quat_to_rot(a.quat + 4 * p, R);
+            quat_to_rot(a.quat + 4 * p, Rm);
             for (int d = 0; d < 3; d++) { mean[d] = a.mean[3 * p + d]; cmean[d] = a.rgbmean[3 * p + d]; }
             unsigned int r = flatten_color(a.rgbmean[3 * p + 0]), g = flatten_color(a.rgbmean[3 * p + 1]),
                          b = flatten_color(a.rgbmean[3 * p + 2]);
             rgba = b | (g << 8) | (r << 16) | (255u << 24);
         } else {
-            for (int d = 0; d < 9; d++) R[d] = (d % 4 == 0) ? 1.0 : 0.0;
+            for (int d = 0; d < 9; d++) Rm[d] = (d % 4 == 0) ? 1.0 : 0.0;
             mean[0] = mean[1] = mean[2] = 0.0;
             cmean[0] = cmean[1] = cmean[2] = 0.0;
-            rgba = 255u << 24;
         }
+        reinterpret_cast<unsigned int*>(Rm + 15)[0] = rgba;
     }
-    __syncthreads();
-    const int sz = a.sz, g2 = sz * sz;
-    const int64_t base = a.slot[p] * g2;
-    const double dsz = (double)sz;
-    for (int m = t; m < g2; m += PRED_T) {
-        const int yy = m / sz, xx = m - yy * sz;
-        // res*((double(x) + 0.5f)/double(sz) - 0.5f), gp_compressor.cpp:326-327
-        const double X0 = __dmul_rn(a.res, __dadd_rn(__ddiv_rn(__dadd_rn((double)xx, 0.5), dsz), -0.5));
-        const double X1 = __dmul_rn(a.res, __dadd_rn(__ddiv_rn(__dadd_rn((double)yy, 0.5), dsz), -0.5));
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (G == 32) __syncwarp(); else __syncthreads();
+    // separable kernel tables
+    for (int e = t; e < N * sz; e += G) {
+        const int i = e / sz, c = e - i * sz;
+        const double d = __dadd_rn(Xs[c], -sb1[i]);
+        Ex[e] = __dmul_rn(a.p0, gpc_exp_nonpos(__dmul_rn(a.cl, __dmul_rn(d, d))));
+    }
+    for (int e = t; e < N * rowsP; e += G) {
+        const int i = e / rowsP, c = e - i * rowsP;
+        const double d = __dadd_rn(Ys[c], -sb2[i]);
+        Ey[e] = (c < rows_here) ? gpc_exp_nonpos(__dmul_rn(a.cl, __dmul_rn(d, d))) : 0.0;
+    }
+    for (int e = t; e < NR * sz; e += G) {
+        const int i = e / sz, c = e - i * sz;
+        const double d = __dadd_rn(Xs[c], -rb1[i]);
+        REx[e] = __dmul_rn(a.p0, gpc_exp_nonpos(__dmul_rn(a.cl, __dmul_rn(d, d))));
+    }
+    for (int e = t; e < NR * rowsP; e += G) {
+        const int i = e / rowsP, c = e - i * rowsP;
+        const double d = __dadd_rn(Ys[c], -rb2[i]);
+        REy[e] = (c < rows_here) ? gpc_exp_nonpos(__dmul_rn(a.cl, __dmul_rn(d, d))) : 0.0;
+    }
+    if (G == 32) __syncwarp(); else __syncthreads();
+    const unsigned int rgba = reinterpret_cast<const unsigned int*>(Rm + 15)[0];
+    const int g2 = sz * sz;
+    const int64_t base = a.slot[p] * g2 + (int64_t)row0 * sz;
+    const int ngroups = sz * ((rows_here + R - 1) / R);
+    for (int g = t; g < ngroups; g += G) {
+        const int yq = g / sz, xx = g - yq * sz;
+        const int yl0 = yq * R;
+        double acc[R][4];
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0;
+        const double* ex = Ex + xx;
+        const double* ey = Ey + yl0;
         int i = 0;
         for (; i + 3 < N; i += 4) {
-            a0 = fma(al[i], rbf(X0, X1, b1[i], b2[i], a.p0, a.cl), a0);
-            a1 = fma(al[i + 1], rbf(X0, X1, b1[i + 1], b2[i + 1], a.p0, a.cl), a1);
-            a2 = fma(al[i + 2], rbf(X0, X1, b1[i + 2], b2[i + 2], a.p0, a.cl), a2);
-            a3 = fma(al[i + 3], rbf(X0, X1, b1[i + 3], b2[i + 3], a.p0, a.cl), a3);
-        }
-        if (i < N) a0 = fma(al[i], rbf(X0, X1, b1[i], b2[i], a.p0, a.cl), a0);
-        if (i + 1 < N) a1 = fma(al[i + 1], rbf(X0, X1, b1[i + 1], b2[i + 1], a.p0, a.cl), a1);
-        if (i + 2 < N) a2 = fma(al[i + 2], rbf(X0, X1, b1[i + 2], b2[i + 2], a.p0, a.cl), a2);
-        const double f = __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
-        if (a.heights) a.heights[base + m] = f;
-        if (a.out32) {
-            float o[3];
 #pragma unroll
-            for (int d = 0; d < 3; d++) {
-                double v = __dadd_rn(__dadd_rn(__dmul_rn(R[d * 3 + 0], f), __dmul_rn(R[d * 3 + 1], X0)), __dmul_rn(R[d * 3 + 2], X1));
-                o[d] = (float)__dadd_rn(v, mean[d]);
-            }
-            unsigned int col = rgba;
-            if (a.rgb_nbv) {  // c = C_star.row(m) + RGB_means[i], gp_compressor.cpp:367
-                double c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0};
-                for (int i = 0; i < NR; i++) {
-                    const double k = rbf(X0, X1, rb1[i], rb2[i], a.p0, a.cl);
-                    c0[i & 3] = fma(ra0[i], k, c0[i & 3]);
-                    c1[i & 3] = fma(ra1[i], k, c1[i & 3]);
-                    c2[i & 3] = fma(ra2[i], k, c2[i & 3]);
+            for (int u = 0; u < 4; u++) {
+                const double e = ex[(i + u) * sz], w = al[i + u];
+                double eyv[R];
+                if (R % 2 == 0) {  // rowsP and yl0 are multiples of R: 16-byte aligned pairs
+#pragma unroll
+                    for (int r = 0; r < R; r += 2) {
+                        const double2 v = *reinterpret_cast<const double2*>(ey + (i + u) * rowsP + r);
+                        eyv[r] = v.x; eyv[r + 1 < R ? r + 1 : r] = v.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; r++) eyv[r] = ey[(i + u) * rowsP + r];
                 }
-                const double fr = __dadd_rn(__dadd_rn(c0[0], c0[1]), __dadd_rn(c0[2], c0[3]));
-                const double fg = __dadd_rn(__dadd_rn(c1[0], c1[1]), __dadd_rn(c1[2], c1[3]));
-                const double fb = __dadd_rn(__dadd_rn(c2[0], c2[1]), __dadd_rn(c2[2], c2[3]));
-                const unsigned int rr = flatten_color(__dadd_rn(fr, cmean[0])), gg = flatten_color(__dadd_rn(fg, cmean[1])),
-                                   bb = flatten_color(__dadd_rn(fb, cmean[2]));
-                col = bb | (gg << 8) | (rr << 16) | (255u << 24);
+#pragma unroll
+                for (int r = 0; r < R; r++) acc[r][u] = fma(w, __dmul_rn(e, eyv[r]), acc[r][u]);
             }
-            float4* dst = reinterpret_cast<float4*>(a.out32 + (size_t)(base + m) * GPC_POINT_BYTES);
-            dst[0] = make_float4(o[0], o[1], o[2], 1.0f);
-            dst[1] = make_float4(__uint_as_float(col), 0.0f, 0.0f, 0.0f);
+        }
+#pragma unroll
+        for (int u = 0; u < 3; u++)
+            if (i + u < N) {
+                const double e = ex[(i + u) * sz], w = al[i + u];
+#pragma unroll
+                for (int r = 0; r < R; r++) acc[r][u] = fma(w, __dmul_rn(e, ey[(i + u) * rowsP + r]), acc[r][u]);
+            }
+        const double X0 = Xs[xx];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (yl0 + r >= rows_here) break;
+            const int m = (yl0 + r) * sz + xx;
+            const double X1 = Ys[yl0 + r];
+            const double f = __dadd_rn(__dadd_rn(acc[r][0], acc[r][1]), __dadd_rn(acc[r][2], acc[r][3]));
+            if (a.heights) a.heights[base + m] = f;
+            if (a.out32) {
+                float o[3];
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    double v = __dadd_rn(__dadd_rn(__dmul_rn(Rm[d * 3 + 0], f), __dmul_rn(Rm[d * 3 + 1], X0)), __dmul_rn(Rm[d * 3 + 2], X1));
+                    o[d] = (float)__dadd_rn(v, mean[d]);
+                }
+                unsigned int col = rgba;
+                if (a.rgb_nbv) {  // c = C_star.row(m) + RGB_means[i], gp_compressor.cpp:367
+                    double c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0};
+                    const double* rex = REx + xx;
+                    const double* rey = REy + yl0 + r;
+                    int j = 0;
+                    for (; j + 3 < NR; j += 4) {
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const double k = __dmul_rn(rex[(j + u) * sz], rey[(j + u) * rowsP]);
+                            c0[u] = fma(ra0[j + u], k, c0[u]);
+                            c1[u] = fma(ra1[j + u], k, c1[u]);
+                            c2[u] = fma(ra2[j + u], k, c2[u]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 3; u++)
+                        if (j + u < NR) {
+                            const double k = __dmul_rn(rex[(j + u) * sz], rey[(j + u) * rowsP]);
+                            c0[u] = fma(ra0[j + u], k, c0[u]);
+                            c1[u] = fma(ra1[j + u], k, c1[u]);
+                            c2[u] = fma(ra2[j + u], k, c2[u]);
+                        }
+                    const double fr = __dadd_rn(__dadd_rn(c0[0], c0[1]), __dadd_rn(c0[2], c0[3]));
+                    const double fg = __dadd_rn(__dadd_rn(c1[0], c1[1]), __dadd_rn(c1[2], c1[3]));
+                    const double fb = __dadd_rn(__dadd_rn(c2[0], c2[1]), __dadd_rn(c2[2], c2[3]));
+                    const unsigned int rr = flatten_color(__dadd_rn(fr, cmean[0])), gg = flatten_color(__dadd_rn(fg, cmean[1])),
+                                       bb = flatten_color(__dadd_rn(fb, cmean[2]));
+                    col = bb | (gg << 8) | (rr << 16) | (255u << 24);
+                }
+                float4* dst = reinterpret_cast<float4*>(a.out32 + (size_t)(base + m) * GPC_POINT_BYTES);
+                dst[0] = make_float4(o[0], o[1], o[2], 1.0f);
+                dst[1] = make_float4(__uint_as_float(col), 0.0f, 0.0f, 0.0f);
+            }
         }
     }
 }
@@ -168,11 +259,58 @@ __global__ void __launch_bounds__(128) predict_points_kernel(const double* __res
 
 }  // namespace
 
-void launch_predict_grid(const PredictArgs& a, cudaStream_t s) {
-    if (a.n_patches <= 0) return;
-    size_t smem = (size_t)8 * a.stride * sizeof(double);
-    predict_grid_kernel<<<(unsigned)a.n_patches, PRED_T, smem, s>>>(a);
+template <int R, int G>
+static cudaError_t launch_grid_variant(const PredictArgs& a, size_t smem, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(predict_grid_kernel<R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int per_cta = PRED_T / G;
+    const int64_t grid = (a.n_groups + per_cta - 1) / per_cta;
+    if (grid > 0x7fffffff) return cudaErrorInvalidConfiguration;
+    predict_grid_kernel<R, G><<<(unsigned)grid, PRED_T, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+// Picks the thread-group shape and the rows-per-block split so that the tables of nmax (+ nrmax) basis vectors fit in
+// shared memory; returns cudaErrorInvalidConfiguration if even one row block does not fit.
+cudaError_t launch_predict_grid(const PredictArgs& a0, cudaStream_t s) {
+    if (a0.n_patches <= 0) return cudaSuccess;
+    PredictArgs a = a0;
+    const int nb = a.nmax + a.nrmax;
+    const bool small = a.sz <= 16;           // warp per patch, four patches per CTA
+    const int R = (a.sz > 32) ? 8 : 1;
+    const int per_cta = small ? PRED_T / 32 : 1;
+    const int64_t budget = (int64_t)(small ? 48 : 220) * 1024 / (int64_t)sizeof(double) / per_cta;
+    // doubles per block: frame[16] + Xs[sz] + Ys[rowsP] + (alpha, b1, b2)[nmax] + (3 alpha, b1, b2)[nrmax] + nb (sz + rowsP)
+    const int64_t fixed = 16 + (int64_t)a.sz + 3 * (int64_t)a.nmax + 5 * (int64_t)a.nrmax + (int64_t)nb * a.sz;
+    int64_t rmax = (budget - fixed) / (nb + 1);
+    if (small && rmax < a.sz) {  // tables too large for four patches per CTA: use the CTA-wide shape
+        PredictArgs b = a0;
+        b.sz = a0.sz;
+        const int64_t budget2 = (int64_t)220 * 1024 / (int64_t)sizeof(double);
+        rmax = (budget2 - fixed) / (nb + 1);
+        if (rmax < 1) return cudaErrorInvalidConfiguration;
+        a.rows = (int)std::min<int64_t>(rmax, a.sz);
+        a.rowsP = a.rows;
+        a.nblk = (a.sz + a.rows - 1) / a.rows;
+        a.group_doubles = (int)(fixed + (int64_t)(nb + 1) * a.rowsP);
+        a.n_groups = a.n_patches * a.nblk;
+        g_launches++;
+        return launch_grid_variant<1, PRED_T>(a, (size_t)a.group_doubles * sizeof(double), s);
+    }
+    if (rmax < 1) return cudaErrorInvalidConfiguration;
+    int rows = (int)std::min<int64_t>(rmax, a.sz);
+    if (R > 1 && rows >= R) rows -= rows % R;
+    a.rows = rows;
+    a.nblk = (a.sz + rows - 1) / rows;
+    a.rowsP = (rows + R - 1) / R * R;
+    a.group_doubles = (int)(fixed + (int64_t)(nb + 1) * a.rowsP);
+    a.group_doubles += a.group_doubles & 1;  // keep every block 16-byte aligned
+    a.n_groups = a.n_patches * a.nblk;
+    const size_t smem = (size_t)a.group_doubles * per_cta * sizeof(double);
     g_launches++;
+    if (small) return launch_grid_variant<1, 32>(a, smem, s);
+    if (R == 8) return launch_grid_variant<8, PRED_T>(a, smem, s);
+    return launch_grid_variant<1, PRED_T>(a, smem, s);
 }
 
 void launch_predict_points(const double* alpha, const double* b1, const double* b2, int N, const double* C, double p0,

@@ -303,13 +303,27 @@ void launch_gather_rgb_stream(const int64_t* off, const int32_t* patch_of, const
     g_launches++;
 }
 
-__global__ void flag_nonempty_kernel(const int32_t* __restrict__ nbv, int64_t n, int64_t* __restrict__ flags) {
+// flags[i] = patch i holds a GP; maxes[0/1] = largest BV count of the height / RGB GPs (sizes the decode tables)
+__global__ void __launch_bounds__(256) flag_nonempty_kernel(const int32_t* __restrict__ nbv, const int32_t* __restrict__ rgb_nbv,
+                                                            int64_t n, int64_t* __restrict__ flags, int32_t* __restrict__ maxes) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) flags[i] = nbv[i] > 0 ? 1 : 0;
+    int m0 = 0, m1 = 0;
+    if (i < n) {
+        m0 = nbv[i];
+        flags[i] = m0 > 0 ? 1 : 0;
+        if (rgb_nbv) m1 = rgb_nbv[i];
+    }
+    m0 = __reduce_max_sync(0xffffffffu, m0);
+    m1 = __reduce_max_sync(0xffffffffu, m1);
+    if ((threadIdx.x & 31) == 0) {
+        if (m0 > 0) atomicMax(maxes, m0);
+        if (m1 > 0) atomicMax(maxes + 1, m1);
+    }
 }
-void launch_flag_nonempty(const int32_t* nbv, int64_t n, int64_t* flags, cudaStream_t s) {
+void launch_flag_nonempty(const int32_t* nbv, const int32_t* rgb_nbv, int64_t n, int64_t* flags, int32_t* maxes, cudaStream_t s) {
+    cudaMemsetAsync(maxes, 0, 2 * sizeof(int32_t), s);
     if (n <= 0) return;
-    flag_nonempty_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(nbv, n, flags);
+    flag_nonempty_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(nbv, rgb_nbv, n, flags, maxes);
     g_launches++;
 }
 

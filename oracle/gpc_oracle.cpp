@@ -381,6 +381,24 @@ struct Sogp {
         for (int i = 0; i < N; i++) k[i] = kern(x1, x2, b1[i], b2[i]);
         for (int ch = 0; ch < D; ch++) f[ch] = row4(&alpha[(size_t)ch * ld], k.data(), N);
     }
+    // Grid decode (gp_compressor.cpp:320-334): the query points form a lattice, so the product path evaluates the RBF
+    // kernel separably, k_i(a, b) = (p0 exp(cl (X0_a - b1_i)^2)) * exp(cl (X1_b - b2_i)^2), which is within 3 ulp of
+    // kern(); this is its restatement (test_oracle_kat pins the distance to the direct form).
+    void grid_tables(const double* Xs, int nx, const double* Ys, int ny, std::vector<double>& Ex, std::vector<double>& Ey) const {
+        Ex.resize((size_t)std::max(N, 1) * nx);
+        Ey.resize((size_t)std::max(N, 1) * ny);
+        for (int i = 0; i < N; i++) {
+            for (int a = 0; a < nx; a++) { const double d = Xs[a] - b1[i]; Ex[(size_t)i * nx + a] = P.p0 * orc_exp_impl(P.cl * (d * d)); }
+            for (int b = 0; b < ny; b++) { const double d = Ys[b] - b2[i]; Ey[(size_t)i * ny + b] = orc_exp_impl(P.cl * (d * d)); }
+        }
+    }
+    void grid_k(const std::vector<double>& Ex, int nx, int a, const std::vector<double>& Ey, int ny, int b) {
+        for (int i = 0; i < N; i++) k[i] = Ex[(size_t)i * nx + a] * Ey[(size_t)i * ny + b];
+    }
+    double predict_grid() const { return N == 0 ? 0.0 : row4(alpha.data(), k.data(), N); }
+    void predict_field_grid(double* f) const {
+        for (int ch = 0; ch < D; ch++) f[ch] = (N == 0) ? 0.0 : row4(&alpha[(size_t)ch * ld], k.data(), N);
+    }
     // predictive sigma as sparse_gp.hpp:329-347 (conf = false): sqrt(s20 + kstar + k'Ck)
     double predict_sigma(double x1, double x2) {
         const double kstar = P.p0;
@@ -1062,6 +1080,7 @@ struct Oracle {
         std::atomic<double> sink(0.0);
         parallel_for(NP, cfg.threads, [&](int, int64_t b, int64_t e) {
             Sogp gp, gc;
+            std::vector<double> Xg(sz), Ex, Ey, REx, REy;
             double acc = 0;
             for (int64_t p = b; p < e; p++) {
                 int N = nbv[p];
@@ -1091,11 +1110,15 @@ struct Oracle {
                 }
                 int64_t base = slot[p] * g2;
                 int64_t m = 0;
+                for (int a = 0; a < sz; a++) Xg[a] = cfg.res * (((double)a + 0.5f) / (double)sz - 0.5f);
+                gp.grid_tables(Xg.data(), sz, Xg.data(), sz, Ex, Ey);
+                if (have_rgb) gc.grid_tables(Xg.data(), sz, Xg.data(), sz, REx, REy);
                 for (int yy = 0; yy < sz; yy++)
                     for (int xx = 0; xx < sz; xx++, m++) {
-                        double X0 = cfg.res * (((double)xx + 0.5f) / (double)sz - 0.5f);
-                        double X1 = cfg.res * (((double)yy + 0.5f) / (double)sz - 0.5f);
-                        double f = gp.predict(X0, X1);
+                        double X0 = Xg[xx];
+                        double X1 = Xg[yy];
+                        gp.grid_k(Ex, sz, xx, Ey, sz, yy);
+                        double f = gp.predict_grid();
                         if (with_sigma) acc += gp.predict_sigma(X0, X1);  // the work the reference discards
                         if (heights) heights[base + m] = f;
                         if (out32) {
@@ -1108,7 +1131,7 @@ struct Oracle {
                             uint8_t* cb = out32 + 32 * (base + m) + 16;
                             // c = C_star.row(m) + RGB_means[i] (gp_compressor.cpp:367); without the field GP: mean only
                             double cf[3] = {0, 0, 0};
-                            if (have_rgb) gc.predict_field(X0, X1, cf);
+                            if (have_rgb) { gc.grid_k(REx, sz, xx, REy, sz, yy); gc.predict_field_grid(cf); }
                             cb[2] = (uint8_t)flatten_color(cf[0] + cm[0]); cb[1] = (uint8_t)flatten_color(cf[1] + cm[1]);
                             cb[0] = (uint8_t)flatten_color(cf[2] + cm[2]); cb[3] = 255;
                             std::memset(out32 + 32 * (base + m) + 20, 0, 12);

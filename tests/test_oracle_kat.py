@@ -149,3 +149,50 @@ def test_rand_stream_accounting_across_patches(oracle_mod):
         pos += 2 * (n - 1)
     assert o.rand_offset() == pos
     assert r["nbv"][1] == 0
+
+
+def test_separable_grid_decode_matches_direct_kernel(oracle_mod):
+    """Grid decode evaluates the RBF separably, k = (p0 e^{cl dx^2}) e^{cl dy^2}; the reference computes
+    p0 exp(cl (dx^2 + dy^2)) with libm (rbf_kernel.cpp:15-18, sparse_gp.hpp:320-327).  Pin the distance: a kernel
+    value with exponent argument z differs by at most (3 + 2|z|) ulp -- the conditioning of exp at z, which the direct
+    form's own rounding of z has too -- and heights by < 1e-12 of sum|alpha_i| p0 (tolerance of the path: 1e-9)."""
+    rng = np.random.default_rng(11)
+    res, sz = float(np.float32(0.15)), 20
+    p0, l_sq, s0 = 1.0, (res / 6.0) ** 2, 1e-3
+    P, npts = 6, 120
+    off = np.arange(P + 1, dtype=np.int64) * npts
+    x1 = rng.uniform(-res / 2, res / 2, P * npts)
+    x2 = rng.uniform(-res / 2, res / 2, P * npts)
+    y = 0.02 * np.sin(40 * x1) * np.cos(30 * x2) + 1e-4 * rng.standard_normal(P * npts)
+    o = oracle_mod.Oracle(res=res, sz=sz, capacity=25, sigmaf_sq=p0, l_sq=l_sq, s0=s0)
+    o.fit_patches(off, x1, x2, y)
+    r = o.fit_result()
+    _, heights = o.decode(want_cloud=False)
+    heights = heights.reshape(P, sz, sz)
+    grid = res * ((np.arange(sz, dtype=np.float64) + 0.5) / sz - 0.5)          # gp_compressor.cpp:326-327
+    cl = float(np.float32(-0.5)) / l_sq
+    bo = np.concatenate([[0], np.cumsum(r["nbv"])])
+    worst_ulp, worst_h = 0.0, 0.0
+    for p in range(P):
+        sl = slice(bo[p], bo[p + 1])
+        b1, b2, al = r["bv1"][sl], r["bv2"][sl], r["alpha"][sl]
+        assert len(al) >= 5
+        ref = np.zeros((sz, sz))
+        for yy in range(sz):
+            for xx in range(sz):
+                acc = 0.0
+                for i in range(len(al)):
+                    d1, d2 = grid[xx] - b1[i], grid[yy] - b2[i]
+                    kd = p0 * math.exp(cl * (d1 * d1 + d2 * d2))
+                    ks = (p0 * math.exp(cl * (d1 * d1))) * math.exp(cl * (d2 * d2))
+                    z = abs(cl * (d1 * d1 + d2 * d2))
+                    worst_ulp = max(worst_ulp, abs(ks - kd) / math.ulp(kd) / (3.0 + 2.0 * z))
+                    acc += al[i] * kd
+                ref[yy, xx] = acc
+        scale = np.abs(al).sum() * p0
+        worst_h = max(worst_h, float(np.abs(heights[p] - ref).max() / scale))
+    assert worst_ulp <= 1.0
+    assert worst_h < 1e-12
+    # and the point-wise predict (direct form) agrees with the grid decode to the same level
+    f = o.predict(0, np.stack(np.meshgrid(grid, grid), -1).reshape(-1, 2))
+    assert np.abs(f - heights[0].ravel()).max() <= 1e-12 * np.abs(r["alpha"][:r["nbv"][0]]).sum() * p0

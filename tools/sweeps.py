@@ -45,18 +45,24 @@ def c4(n_patches, nbv, sz=64):
     for it in range(3):
         n = h.decompress_resident()
         best = min(best, h.stats()["ms_predict"])
-    flops = n * (37.0 * nbv + 18)
-    print(f"| {n_patches} | {nbv} | {sz}x{sz} | {n} | {best:.2f} | {n / (best * 1e-3):.3e} | {flops / (best * 1e-3) / 1e12:.2f} | {flops / (best * 1e-3) / fp64_peak:.3f} | {n * 32 / (best * 1e-3) / 1e9:.0f} |")
+    # separable decode: per grid point 1 DMUL + 1 DFMA (3 flop) per BV + 36 for the frame; per patch 2 sz N exps (34 flop each)
+    flops = n * (3.0 * nbv + 36) + n_patches * 2.0 * sz * nbv * 37.0
+    hbm = float(G.measured_peaks().get("hbm_gbs", 6451.5)) if hasattr(G, "measured_peaks") else 6451.5
+    gbs = n * 32 / (best * 1e-3) / 1e9
+    print(f"| {n_patches} | {nbv} | {sz}x{sz} | {n} | {best:.2f} | {n / (best * 1e-3):.3e} | {flops / (best * 1e-3) / 1e12:.2f} | {flops / (best * 1e-3) / fp64_peak:.3f} | {gbs:.0f} | {gbs / hbm:.3f} |")
     h.close()
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "c4":
+        c4(125_000, 30); c4(125_000, 100); c4(250_000, 30); c4(125_000, 30, sz=10)
+        sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[1] == "c3":
         c3(1_000_000, 3.2, caps=tuple(int(v) for v in sys.argv[2:]))
         sys.exit(0)
     c3(1_000_000, 3.2)
     print("\n### C4 decode only (per-GPU share of the 1M-patch configuration), REF kernel, 1 x B200\n")
-    print("| patches | BVs/patch | grid | output pts | predict ms | grid pts/s | TFLOP/s (37N+18 per pt) | frac of FP64 peak | output GB/s |")
-    print("|---|---|---|---|---|---|---|---|---|")
+    print("| patches | BVs/patch | grid | output pts | predict ms | grid pts/s | TFLOP/s (alg.) | frac of FP64 peak | output GB/s | frac of HBM peak |")
+    print("|---|---|---|---|---|---|---|---|---|---|")
     c4(125_000, 30)
     c4(125_000, 100)
     c4(250_000, 30)
