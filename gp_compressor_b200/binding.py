@@ -19,7 +19,7 @@ GPC_OK = 0
 SYMBOLS = [
     "gpc_config_default", "gpc_create", "gpc_destroy", "gpc_last_error", "gpc_version", "gpc_compress",
     "gpc_upload_cloud", "gpc_compress_resident", "gpc_fit_patches", "gpc_decompress", "gpc_decompress_resident",
-    "gpc_get_heights", "gpc_predict", "gpc_get_sizes", "gpc_get_stats", "gpc_get_patches", "gpc_get_assignment",
+    "gpc_get_heights", "gpc_predict", "gpc_evaluate_patches", "gpc_get_sizes", "gpc_get_stats", "gpc_get_patches", "gpc_get_assignment",
     "gpc_get_params", "gpc_get_params_rgb", "gpc_get_state", "gpc_set_params", "gpc_set_rand_offset", "gpc_get_stream", "gpc_debug_exp", "gpc_debug_rand", "gpc_debug_peak", "gpc_shard_range", "gpc_save", "gpc_load", "gpc_get_config",
 ]
 
@@ -41,7 +41,7 @@ class GpcSizes(C.Structure):
 _STAT_U64 = ["n_add", "n_first", "n_sparse", "n_full", "n_del_cap", "n_del_geo", "sum_n", "sum_n2_common",
              "sum_n2_sparse", "sum_n2_full", "sum_n2_del"]
 _STAT_MS = ["ms_h2d", "ms_lattice", "ms_keys", "ms_sort", "ms_leaves", "ms_rotation", "ms_claim", "ms_group",
-            "ms_shuffle", "ms_fit", "ms_d2h", "ms_predict", "ms_total", "ms_fit_rgb"]
+            "ms_shuffle", "ms_fit", "ms_d2h", "ms_predict", "ms_total", "ms_fit_rgb", "ms_evaluate", "pad_"]
 _STAT_RGB = ["rgb_n_sparse", "rgb_n_full", "rgb_n_del_cap", "rgb_n_del_geo", "rgb_sum_n2_common"]
 
 
@@ -75,6 +75,7 @@ def load():
     L.gpc_decompress_resident.argtypes = [vp, C.POINTER(i64)]
     L.gpc_get_heights.argtypes = [vp, vp, i64]
     L.gpc_predict.argtypes = [vp, i64, vp, i64, vp, vp]
+    L.gpc_evaluate_patches.argtypes = [vp, i64, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp]
     L.gpc_get_sizes.argtypes = [vp, C.POINTER(GpcSizes)]
     L.gpc_get_stats.argtypes = [vp, C.POINTER(GpcStats)]
     L.gpc_get_patches.argtypes = [vp] + [vp] * 8
@@ -204,6 +205,20 @@ class Handle:
         sg = np.zeros(X.shape[0]) if sigma else None
         self._ck(load().gpc_predict(self.h, patch, _p(X), X.shape[0], _p(f), _p(sg)))
         return (f, sg) if sigma else f
+
+    def evaluate(self, off, x1, x2, y=None, conf=False, want=("f", "sigma", "lik", "dX")):
+        """gpc_evaluate_patches: batched predict (sigma / conf), likelihood and likelihood gradient over the first
+        len(off) - 1 patches of this shard; needs keep_state=1."""
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        x1, x2 = (np.ascontiguousarray(a, dtype=np.float64) for a in (x1, x2))
+        yy = None if y is None else np.ascontiguousarray(y, dtype=np.float64)
+        m = x1.size
+        out = dict(f=np.zeros(m) if "f" in want else None, sigma=np.zeros(m) if "sigma" in want else None,
+                   lik=np.zeros(m) if "lik" in want and yy is not None else None,
+                   dX=np.zeros((m, 3)) if "dX" in want and yy is not None else None)
+        self._ck(load().gpc_evaluate_patches(self.h, off.size - 1, _p(off), _p(x1), _p(x2), _p(yy), int(conf), _p(out["f"]),
+                                             _p(out["sigma"]), _p(out["lik"]), _p(out["dX"])))
+        return {k: v for k, v in out.items() if v is not None}
 
     # ---- results ----------------------------------------------------------------------
     def sizes(self):

@@ -39,7 +39,7 @@ struct gpc_handle {
     DevBuf perm_rgb, fcr, fcg, fcb, r_nbv, r_flags, r_alpha0, r_alpha1, r_alpha2, r_b1, r_b2, r_bidx, kstats_rgb;
     bool have_rgb = false;
     DevBuf quat, mean, rgbmean, Rm, center, code, ncand, owner, st_idx;
-    DevBuf tmpA, tmpB, tmpC, lat_state;
+    DevBuf tmpA, tmpB, tmpC, lat_state, ev_in, ev_out;
     // binning scratch
     DevBuf keys, keys2, vals, vals2, ovals, ovals2, sort_tmp, flags64, ex, leaf_of, leaf_start, leaf_code_a, spt, nbr, nnbr,
         center_a, Rm_a, ncand_a, pt0, pt1, pt2, hbuf, rgb, leaf_sums;
@@ -620,7 +620,7 @@ void gpc_destroy(gpc_handle* h) {
                       &h->dumpC, &h->dumpQ, &h->queue0, &h->queue1, &h->hand0, &h->hand1, &h->spill, &h->qcount, &h->kstats, &h->bv_off, &h->palpha, &h->pb1, &h->pb2, &h->pidx, &h->perm_rgb, &h->fcr, &h->fcg, &h->fcb, &h->r_nbv, &h->r_flags,
                       &h->r_alpha0, &h->r_alpha1, &h->r_alpha2, &h->r_b1, &h->r_b2, &h->r_bidx, &h->kstats_rgb, &h->nonempty, &h->slot, &h->out32,
                       &h->heights, &h->quat, &h->mean, &h->rgbmean, &h->Rm, &h->center, &h->code, &h->ncand, &h->owner,
-                      &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->lat_state, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
+                      &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->lat_state, &h->ev_in, &h->ev_out, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
                       &h->ovals2, &h->sort_tmp, &h->flags64, &h->ex, &h->leaf_of, &h->leaf_start, &h->leaf_code_a, &h->spt,
                       &h->nbr, &h->nnbr, &h->center_a, &h->Rm_a, &h->ncand_a, &h->pt0, &h->pt1, &h->pt2, &h->hbuf, &h->rgb, &h->leaf_sums};
     for (DevBuf* b : bufs) b->release();
@@ -789,6 +789,9 @@ int gpc_get_heights(gpc_handle* h, double* out, int64_t capacity) {
     return GPC_OK;
 }
 
+static int evaluate_impl(gpc_handle* h, int64_t op0, int64_t P, const int64_t* off, const double* x1, const double* x2, const double* y,
+                         int conf, double* f, double* sigma, double* lik, double* dX);
+
 int gpc_predict(gpc_handle* h, int64_t patch, const double* X, int64_t m, double* f, double* sigma) {
     if (!h || m < 0 || (m > 0 && (!X || !f))) return GPC_ERR_INVALID;
     if (!h->have_fit) return fail(h, GPC_ERR_STATE, "predict before fit");
@@ -798,22 +801,97 @@ int gpc_predict(gpc_handle* h, int64_t patch, const double* X, int64_t m, double
     if (m == 0) return GPC_OK;
     const gpc_config& c = h->cfg;
     const int64_t op = patch - h->patch_lo;
+    if (sigma) {  // mean and sigma from the batched evaluation kernel (K9)
+        std::vector<double> x1(m), x2(m);
+        for (int64_t i = 0; i < m; i++) { x1[i] = X[2 * i]; x2[i] = X[2 * i + 1]; }
+        const int64_t off[2] = {0, m};
+        return evaluate_impl(h, op, 1, off, x1.data(), x2.data(), nullptr, 0, f, sigma, nullptr, nullptr);
+    }
     int32_t N = 0;
     CK(cudaMemcpy(&N, h->nbv.as<int32_t>() + op, sizeof(int32_t), cudaMemcpyDeviceToHost));
     CK(h->tmpA.reserve(2 * m * sizeof(double)));
     CK(h->tmpB.reserve(m * sizeof(double)));
-    CK(h->tmpC.reserve(m * sizeof(double)));
     CK(cudaMemcpyAsync(h->tmpA.p, X, 2 * m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     launch_predict_points(h->alpha.as<double>() + op * c.capacity, h->b1.as<double>() + op * c.capacity,
-                          h->b2.as<double>() + op * c.capacity, N,
-                          sigma ? h->dumpC.as<double>() + op * (int64_t)c.capacity * c.capacity : nullptr, c.sigmaf_sq,
-                          kernel_cl(c), c.s0, h->tmpA.as<double>(), m, h->tmpB.as<double>(),
-                          sigma ? h->tmpC.as<double>() : nullptr, h->stream);
+                          h->b2.as<double>() + op * c.capacity, N, c.sigmaf_sq, kernel_cl(c), h->tmpA.as<double>(), m,
+                          h->tmpB.as<double>(), h->stream);
     CK(cudaMemcpyAsync(f, h->tmpB.p, m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (sigma) CK(cudaMemcpyAsync(sigma, h->tmpC.p, m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
     return GPC_OK;
+}
+
+// patches [op0, op0 + P) of this shard (local indices)
+static int evaluate_impl(gpc_handle* h, int64_t op0, int64_t P, const int64_t* off, const double* x1, const double* x2, const double* y,
+                         int conf, double* f, double* sigma, double* lik, double* dX) {
+    if (!h || P < 0 || (P > 0 && !off)) return GPC_ERR_INVALID;
+    if (!h->have_fit || !h->cfg.keep_state || !h->dumpC.p)
+        return fail(h, GPC_ERR_STATE, "sigma / likelihood evaluation needs a fit made with gpc_config.keep_state");
+    if (op0 < 0 || op0 + P > h->patch_hi - h->patch_lo) return fail(h, GPC_ERR_INVALID, "more patches than this shard holds");
+    if (P == 0) return GPC_OK;
+    const int64_t m = off[P];
+    if (off[0] != 0 || m < 0) return fail(h, GPC_ERR_INVALID, "offsets must start at 0 and be non-decreasing");
+    for (int64_t p = 0; p < P; p++)
+        if (off[p + 1] < off[p]) return fail(h, GPC_ERR_INVALID, "offsets must start at 0 and be non-decreasing");
+    if (m > 0 && (!x1 || !x2 || ((lik || dX) && !y))) return GPC_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    if (m == 0) return GPC_OK;
+    const gpc_config& c = h->cfg;
+    cudaStream_t st = h->stream;
+    const size_t in_bytes = (size_t)(P + 1) * sizeof(int64_t) + 3 * (size_t)m * sizeof(double);
+    CK(h->ev_in.reserve(in_bytes));
+    CK(h->ev_out.reserve(6 * (size_t)m * sizeof(double)));
+    int64_t* d_off = h->ev_in.as<int64_t>();
+    double* d_x1 = reinterpret_cast<double*>(d_off + P + 1);
+    double* d_x2 = d_x1 + m;
+    double* d_y = d_x2 + m;
+    double* d_f = h->ev_out.as<double>();
+    double* d_sg = d_f + m;
+    double* d_lk = d_sg + m;
+    double* d_dx = d_lk + m;
+    CK(cudaMemcpyAsync(d_off, off, (size_t)(P + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_x1, x1, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_x2, x2, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (y) CK(cudaMemcpyAsync(d_y, y, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, st));
+    // largest BV count (sizes the shared-memory tiles)
+    CK(h->small.reserve(256));
+    CK(h->nonempty.reserve((P + 1) * sizeof(int64_t)));
+    int32_t* d_maxes = h->small.as<int32_t>() + 48;
+    launch_flag_nonempty(h->nbv.as<int32_t>() + op0, nullptr, P, h->nonempty.as<int64_t>(), d_maxes, st);
+    int32_t maxes[2] = {0, 0};
+    CK(cudaMemcpyAsync(maxes, d_maxes, sizeof(maxes), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    EvalArgs a;
+    a.n_patches = P;
+    a.nbv = h->nbv.as<int32_t>() + op0;
+    a.off = d_off;
+    a.stride = c.capacity;
+    a.nmax = maxes[0];
+    a.alpha = h->alpha.as<double>() + op0 * c.capacity; a.b1 = h->b1.as<double>() + op0 * c.capacity;
+    a.b2 = h->b2.as<double>() + op0 * c.capacity; a.C = h->dumpC.as<double>() + op0 * (int64_t)c.capacity * c.capacity;
+    a.x1 = d_x1; a.x2 = d_x2; a.y = y ? d_y : nullptr;
+    a.p0 = c.sigmaf_sq; a.cl = kernel_cl(c); a.c1 = (-c.sigmaf_sq) / c.l_sq; a.s20 = c.s0;
+    a.conf = conf;
+    a.f = f ? d_f : nullptr; a.sigma = sigma ? d_sg : nullptr; a.lik = lik ? d_lk : nullptr; a.dX = dX ? d_dx : nullptr;
+    StageTimer tm(h);
+    h->stats.ms_evaluate = 0;
+    size_t t0 = tm.mark();
+    if (launch_evaluate(a, st) != cudaSuccess) return fail(h, GPC_ERR_CUDA, "evaluate kernel launch failed");
+    size_t t1 = tm.mark();
+    tm.span(&h->stats.ms_evaluate, t0, t1);
+    if (f) CK(cudaMemcpyAsync(f, d_f, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (sigma) CK(cudaMemcpyAsync(sigma, d_sg, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (lik) CK(cudaMemcpyAsync(lik, d_lk, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (dX) CK(cudaMemcpyAsync(dX, d_dx, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    tm.resolve();
+    return GPC_OK;
+}
+
+int gpc_evaluate_patches(gpc_handle* h, int64_t P, const int64_t* off, const double* x1, const double* x2, const double* y,
+                         int conf, double* f, double* sigma, double* lik, double* dX) {
+    return evaluate_impl(h, 0, P, off, x1, x2, y, conf, f, sigma, lik, dX);
 }
 
 int gpc_get_sizes(gpc_handle* h, gpc_sizes* s) {

@@ -170,9 +170,23 @@ void launch_compact_params(const int32_t* nbv, int64_t n_patches, int stride, co
                            double* palpha, double* pb1, double* pb2, int32_t* pidx, cudaStream_t s);
 void launch_flag_nonempty(const int32_t* nbv, const int32_t* rgb_nbv, int64_t n, int64_t* flags, int32_t* maxes, cudaStream_t s);
 cudaError_t launch_predict_grid(const PredictArgs& a, cudaStream_t s);
-void launch_predict_points(const double* alpha, const double* b1, const double* b2, int N, const double* C,
-                           double p0, double cl, double s20, const double* X, int64_t m, double* f,
-                           double* sigma, cudaStream_t s);
+
+// K9 (k_evaluate.cu): batched predict with sigma / conf, likelihood and likelihood gradient
+struct EvalArgs {
+    int64_t n_patches;
+    const int32_t* nbv;
+    const int64_t* off;            // n_patches + 1 offsets into the query arrays
+    int stride;                    // parameter stride per patch (capacity); C at patch * stride^2, packed N x N
+    int nmax;                      // largest nbv among the patches
+    const double *alpha, *b1, *b2, *C;
+    const double *x1, *x2, *y;     // y may be nullptr
+    double p0, cl, c1, s20;        // c1 = -p0 / p1 (rbf_kernel.cpp:44)
+    int conf;
+    double *f, *sigma, *lik, *dX;  // any may be nullptr
+};
+cudaError_t launch_evaluate(const EvalArgs& a, cudaStream_t s);
+void launch_predict_points(const double* alpha, const double* b1, const double* b2, int N, double p0, double cl, const double* X,
+                           int64_t m, double* f, cudaStream_t s);
 cudaError_t measure_peak(int kind, int sm_count, cudaStream_t s, double* value);
 void launch_debug_exp(const double* x, double* out, int64_t n, cudaStream_t s);
 

@@ -1,0 +1,217 @@
+// k_evaluate.cu — K9: batched GP evaluation with uncertainty, likelihood and likelihood gradient (next rows N2 / N4).
+//
+// Replaces, for every fitted patch and a ragged set of query points per patch:
+//   sparse_gp::predict_measurements with sigma / conf   /root/reference/src/sparse_gp.hpp:299-351
+//   sparse_gp::compute_likelihoods -> likelihood          sparse_gp.hpp:407-425
+//   sparse_gp::compute_derivatives -> likelihood_dx       sparse_gp.hpp:459-502 (+ rbf_kernel::kernel_dx, rbf_kernel.cpp:38-46)
+// which the reference runs one point at a time (gp_registration.cpp:175-194).
+//
+// One CTA per patch, tiles of 32 query points.  Per tile: (1) K = p0 E, E = exp(cl |x - BV_i|^2) for the N x 32
+// pairs; (2) CK = C K as a register-tiled product (each thread: 4 rows x 4 points, or 1 x 4 for small N), C read
+// by columns from shared memory (from global memory when N^2 does not fit); (3) the six O(N) sums per point
+// (k'Ck, kdx'Ck, kdy'Ck, alpha'k, alpha'kdx, alpha'kdy) as canonical row4 dots, one warp per group of sums;
+// (4) the scalar epilogue of predict / likelihood / likelihood_dx.  Same operation order as oracle Sogp::evaluate.
+#include <algorithm>
+
+#include "gpc_device.cuh"
+#include "gpc_internal.h"
+
+namespace gpc {
+
+namespace {
+
+constexpr int EV_T = 32;     // points per tile
+constexpr int EV_NT = 128;   // threads per CTA
+
+// canonical row4 over a strided column: sum_i a(i) * b(i), partial i & 3, (a0 + a1) + (a2 + a3)
+template <class FA, class FB>
+__device__ __forceinline__ double row4_fn(int n, FA a, FB b) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int i = 0;
+    for (; i + 3 < n; i += 4) {
+        s0 = fma(a(i), b(i), s0);
+        s1 = fma(a(i + 1), b(i + 1), s1);
+        s2 = fma(a(i + 2), b(i + 2), s2);
+        s3 = fma(a(i + 3), b(i + 3), s3);
+    }
+    if (i < n) s0 = fma(a(i), b(i), s0);
+    if (i + 1 < n) s1 = fma(a(i + 1), b(i + 1), s1);
+    if (i + 2 < n) s2 = fma(a(i + 2), b(i + 2), s2);
+    return __dadd_rn(__dadd_rn(s0, s1), __dadd_rn(s2, s3));
+}
+
+template <int RPT, bool CSMEM>
+__global__ void __launch_bounds__(EV_NT) evaluate_kernel(EvalArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    const int64_t p = blockIdx.x;
+    const int N = a.nbv[p];
+    const int64_t o = a.off[p];
+    const int n = (int)(a.off[p + 1] - o);
+    if (n == 0) return;
+    const int t = threadIdx.x;
+    const int LDC = (N + 3) & ~3;
+    // layout: K, E, CK [N x 32] | red [6 x 32] | xs, ys, yv [32] | al, b1, b2 [N] | C [N x LDC]
+    double* K = sm;
+    double* E = K + (size_t)N * EV_T;
+    double* CK = E + (size_t)N * EV_T;
+    double* red = CK + (size_t)N * EV_T;
+    double* xs = red + 6 * EV_T;
+    double* ys = xs + EV_T;
+    double* yv = ys + EV_T;
+    double* al = yv + EV_T;
+    double* b1 = al + N;
+    double* b2 = b1 + N;
+    double* Cs = b2 + N + ((3 * N) & 1);  // 16-byte aligned
+    const int64_t pb = p * a.stride;
+    const double* Cg = a.C + p * (int64_t)a.stride * a.stride;  // packed N x N
+    for (int i = t; i < N; i += EV_NT) { al[i] = a.alpha[pb + i]; b1[i] = a.b1[pb + i]; b2[i] = a.b2[pb + i]; }
+    if (CSMEM) {
+        for (int e = t; e < N * LDC; e += EV_NT) {
+            const int j = e / LDC, i = e - j * LDC;
+            Cs[e] = (i < N) ? Cg[(size_t)j * N + i] : 0.0;
+        }
+    }
+    const double kstar = a.p0, s20 = a.s20, c1 = a.c1;
+    for (int tile = 0; tile < n; tile += EV_T) {
+        __syncthreads();
+        if (t < EV_T) {
+            const int q = tile + t;
+            xs[t] = (q < n) ? a.x1[o + q] : 0.0;
+            ys[t] = (q < n) ? a.x2[o + q] : 0.0;
+            yv[t] = (q < n && a.y) ? a.y[o + q] : 0.0;
+        }
+        __syncthreads();
+        // (1) kernel values
+        for (int e = t; e < N * EV_T; e += EV_NT) {
+            const int i = e / EV_T, tt = e - i * EV_T;
+            const double d1 = __dadd_rn(xs[tt], -b1[i]), d2 = __dadd_rn(ys[tt], -b2[i]);
+            const double ex = gpc_exp_nonpos(__dmul_rn(a.cl, __dadd_rn(__dmul_rn(d1, d1), __dmul_rn(d2, d2))));
+            E[e] = ex;
+            K[e] = __dmul_rn(a.p0, ex);
+        }
+        __syncthreads();
+        // (2) CK(i, tt) = sum_j C(j, i) K(j, tt), j ascending, one fma chain per entry
+        {
+            const int pg = t & 7, rg = t >> 3;   // 8 point groups of 4, 16 row groups
+            for (int i0 = rg * RPT; i0 < N; i0 += 16 * RPT) {
+                double acc[RPT][4];
+#pragma unroll
+                for (int r = 0; r < RPT; r++) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0;
+                for (int j = 0; j < N; j++) {
+                    const double2 k01 = *reinterpret_cast<const double2*>(K + j * EV_T + 4 * pg);
+                    const double2 k23 = *reinterpret_cast<const double2*>(K + j * EV_T + 4 * pg + 2);
+                    double cv[RPT];
+                    if (CSMEM) {
+                        if (RPT == 4) {
+                            const double2 c01 = *reinterpret_cast<const double2*>(Cs + j * LDC + i0);
+                            const double2 c23 = *reinterpret_cast<const double2*>(Cs + j * LDC + i0 + 2);
+                            cv[0] = c01.x; cv[RPT > 1 ? 1 : 0] = c01.y; cv[RPT > 2 ? 2 : 0] = c23.x; cv[RPT > 3 ? 3 : 0] = c23.y;
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < RPT; r++) cv[r] = Cs[j * LDC + i0 + r];
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < RPT; r++) cv[r] = (i0 + r < N) ? __ldg(Cg + (size_t)j * N + i0 + r) : 0.0;
+                    }
+#pragma unroll
+                    for (int r = 0; r < RPT; r++) {
+                        acc[r][0] = fma(cv[r], k01.x, acc[r][0]);
+                        acc[r][1] = fma(cv[r], k01.y, acc[r][1]);
+                        acc[r][2] = fma(cv[r], k23.x, acc[r][2]);
+                        acc[r][3] = fma(cv[r], k23.y, acc[r][3]);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < RPT; r++)
+                    if (i0 + r < N) {
+                        *reinterpret_cast<double2*>(CK + (i0 + r) * EV_T + 4 * pg) = make_double2(acc[r][0], acc[r][1]);
+                        *reinterpret_cast<double2*>(CK + (i0 + r) * EV_T + 4 * pg + 2) = make_double2(acc[r][2], acc[r][3]);
+                    }
+            }
+        }
+        __syncthreads();
+        // (3) the six sums, one warp per group
+        {
+            const int w = t >> 5, tt = t & 31;
+            const double x1 = xs[tt], x2 = ys[tt];
+            auto kf = [&](int i) { return K[i * EV_T + tt]; };
+            auto ckf = [&](int i) { return CK[i * EV_T + tt]; };
+            auto alf = [&](int i) { return al[i]; };
+            auto kxf = [&](int i) { return __dmul_rn(__dmul_rn(c1, __dadd_rn(x1, -b1[i])), E[i * EV_T + tt]); };
+            auto kyf = [&](int i) { return __dmul_rn(__dmul_rn(c1, __dadd_rn(x2, -b2[i])), E[i * EV_T + tt]); };
+            if (w == 0) red[0 * EV_T + tt] = row4_fn(N, kf, ckf);
+            else if (w == 1) red[1 * EV_T + tt] = row4_fn(N, kxf, ckf);
+            else if (w == 2) red[2 * EV_T + tt] = row4_fn(N, kyf, ckf);
+            else {
+                red[3 * EV_T + tt] = row4_fn(N, alf, kf);
+                red[4 * EV_T + tt] = row4_fn(N, alf, kxf);
+                red[5 * EV_T + tt] = row4_fn(N, alf, kyf);
+            }
+        }
+        __syncthreads();
+        // (4) epilogue
+        if (t < EV_T && tile + t < n) {
+            const int64_t q = o + tile + t;
+            const double kCk = red[t], sx = red[EV_T + t], sy = red[2 * EV_T + t];
+            const double mu = red[3 * EV_T + t], ax = red[4 * EV_T + t], ay = red[5 * EV_T + t];
+            // predict, sparse_gp.hpp:329-349
+            double var = __dadd_rn(__dadd_rn(s20, kstar), kCk);
+            const double var_l = var;
+            if (var < 0.0) var = 0.0;
+            if (a.f) a.f[q] = mu;
+            if (a.sigma)
+                a.sigma[q] = a.conf ? __dmul_rn(100.0, __dadd_rn(1.0, -__ddiv_rn(var, __dadd_rn(kstar, s20)))) : __dsqrt_rn(var);
+            const double off = __dadd_rn(yv[t], -mu);
+            if (a.lik) {  // :424
+                const double two_pi = 6.283185307179586;
+                const double ex = gpc_exp(__dmul_rn(__dmul_rn(__ddiv_rn(-0.5, var_l), off), off));
+                a.lik[q] = __dmul_rn(__ddiv_rn(1.0, __dsqrt_rn(__dmul_rn(two_pi, var_l))), ex);
+            }
+            if (a.dX) {  // :487-499
+                const double var_d = __dadd_rn(__dadd_rn(s20, kCk), kstar);
+                const double sdx[2] = {__dmul_rn(2.0, sx), __dmul_rn(2.0, sy)};
+                const double ad[2] = {ax, ay};
+                const double sq = __dsqrt_rn(var_d);
+                const double vs = __dmul_rn(var_d, sq);
+                const double exppart = __dmul_rn(__ddiv_rn(0.5, vs), gpc_exp(__dmul_rn(__dmul_rn(__ddiv_rn(-0.5, var_d), off), off)));
+                a.dX[3 * q] = __dmul_rn(__dmul_rn(__ddiv_rn(-1.0, vs), off), exppart);
+#pragma unroll
+                for (int d = 0; d < 2; d++) {
+                    const double first = -sdx[d];
+                    const double second = __dmul_rn(__dmul_rn(2.0, ad[d]), off);
+                    const double third = __dmul_rn(__dmul_rn(__ddiv_rn(sdx[d], var_d), off), off);
+                    a.dX[3 * q + 1 + d] = __dmul_rn(exppart, __dadd_rn(__dadd_rn(first, second), third));
+                }
+            }
+        }
+    }
+}
+
+template <int RPT, bool CSMEM>
+cudaError_t launch_variant(const EvalArgs& a, size_t smem, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(evaluate_kernel<RPT, CSMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    evaluate_kernel<RPT, CSMEM><<<(unsigned)a.n_patches, EV_NT, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_evaluate(const EvalArgs& a, cudaStream_t s) {
+    if (a.n_patches <= 0) return cudaSuccess;
+    const int64_t N = std::max(a.nmax, 1);
+    const int64_t LDC = (N + 3) & ~(int64_t)3;
+    const int64_t base = 3 * N * EV_T + 6 * EV_T + 3 * EV_T + 3 * N + 1;
+    const int64_t with_c = base + N * LDC;
+    const int64_t budget = 220 * 1024 / (int64_t)sizeof(double);
+    g_launches++;
+    if (with_c <= budget) {
+        const size_t smem = (size_t)with_c * sizeof(double);
+        return N > 32 ? launch_variant<4, true>(a, smem, s) : launch_variant<1, true>(a, smem, s);
+    }
+    if (base > budget) return cudaErrorInvalidConfiguration;
+    return launch_variant<4, false>(a, (size_t)base * sizeof(double), s);
+}
+
+}  // namespace gpc

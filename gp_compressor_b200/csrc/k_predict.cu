@@ -220,41 +220,16 @@ __global__ void __launch_bounds__(PRED_T, R == 1 ? 8 : 3) predict_grid_kernel(Pr
     }
 }
 
-// sparse_gp::predict at arbitrary points of one patch (sparse_gp.hpp:312-351), optional sigma
+// sparse_gp::predict at arbitrary points of one patch (sparse_gp.hpp:312-327): the mean.  Sigma / conf come from K9.
 __global__ void __launch_bounds__(128) predict_points_kernel(const double* __restrict__ alpha, const double* __restrict__ b1,
-                                                             const double* __restrict__ b2, int N, const double* __restrict__ C,
-                                                             double p0, double cl, double s20, const double* __restrict__ X,
-                                                             int64_t m, double* __restrict__ f, double* __restrict__ sigma) {
+                                                             const double* __restrict__ b2, int N, double p0, double cl,
+                                                             const double* __restrict__ X, int64_t m, double* __restrict__ f) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= m) return;
     const double x1 = X[2 * t], x2 = X[2 * t + 1];
-    if (N == 0) {
-        f[t] = 0.0;
-        if (sigma) sigma[t] = sqrt(__dadd_rn(p0, s20));
-        return;
-    }
     double a[4] = {0.0, 0.0, 0.0, 0.0};
     for (int i = 0; i < N; i++) a[i & 3] = fma(alpha[i], rbf(x1, x2, b1[i], b2[i], p0, cl), a[i & 3]);
     f[t] = __dadd_rn(__dadd_rn(a[0], a[1]), __dadd_rn(a[2], a[3]));
-    if (sigma) {
-        // sqrt(s20 + kstar + k'Ck): canonical order = dot32 over i of k_i * row4(C_i, k)
-        double part[32];
-        for (int l = 0; l < 32; l++) part[l] = 0.0;
-        for (int i = 0; i < N; i++) {
-            double r[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int j = 0; j < N; j++) r[j & 3] = fma(C[(size_t)i * N + j], rbf(x1, x2, b1[j], b2[j], p0, cl), r[j & 3]);
-            double ck = __dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3]));
-            part[i & 31] = fma(rbf(x1, x2, b1[i], b2[i], p0, cl), ck, part[i & 31]);
-        }
-        for (int off = 16; off >= 1; off >>= 1) {
-            double tmp[32];
-            for (int l = 0; l < 32; l++) tmp[l] = __dadd_rn(part[l], part[l ^ off]);
-            for (int l = 0; l < 32; l++) part[l] = tmp[l];
-        }
-        double sg = __dadd_rn(__dadd_rn(s20, p0), part[0]);
-        if (sg < 0.0) sg = 0.0;
-        sigma[t] = sqrt(sg);
-    }
 }
 
 }  // namespace
@@ -313,10 +288,10 @@ cudaError_t launch_predict_grid(const PredictArgs& a0, cudaStream_t s) {
     return launch_grid_variant<1, PRED_T>(a, smem, s);
 }
 
-void launch_predict_points(const double* alpha, const double* b1, const double* b2, int N, const double* C, double p0,
-                           double cl, double s20, const double* X, int64_t m, double* f, double* sigma, cudaStream_t s) {
+void launch_predict_points(const double* alpha, const double* b1, const double* b2, int N, double p0, double cl, const double* X,
+                           int64_t m, double* f, cudaStream_t s) {
     if (m <= 0) return;
-    predict_points_kernel<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(alpha, b1, b2, N, C, p0, cl, s20, X, m, f, sigma);
+    predict_points_kernel<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(alpha, b1, b2, N, p0, cl, X, m, f);
 }
 
 }  // namespace gpc

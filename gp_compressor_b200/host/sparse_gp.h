@@ -44,6 +44,7 @@ public:
         cfg_.sigmaf_sq = kernel.sigmaf_sq;
         cfg_.l_sq = kernel.l_sq;
         cfg_.rgb_rand = 0;  // a stand-alone process consumes only its own shuffle draws
+        cfg_.keep_state = 1;  // C is kept: predict_measurements returns sigma, likelihoods and derivatives need it
     }
     ~sparse_gp() { if (h_) gpc_destroy(h_); }
     sparse_gp(const sparse_gp&) = delete;
@@ -66,14 +67,34 @@ public:
     }
     // void predict_measurements(VectorXd& f_star, const MatrixXd& X_star, VectorXd& sigconf, bool conf = false), :299-308
     void predict_measurements(Eigen::VectorXd& f_star, const Eigen::MatrixXd& X_star, Eigen::VectorXd& sigconf, bool conf = false) {
-        if (conf) throw std::runtime_error("sparse_gp: confidence output is not built (row N2)");
         if (!fitted_) throw std::runtime_error("sparse_gp::predict_measurements before add_measurements");
         const long m = X_star.rows();
-        std::vector<double> rm((size_t)2 * m);
-        for (long i = 0; i < m; i++) { rm[2 * i] = X_star(i, 0); rm[2 * i + 1] = X_star(i, 1); }
         f_star.resize(m);
         sigconf.resize(m);
-        check(gpc_predict(h_, 0, rm.data(), m, f_star.data(), cfg_.keep_state ? sigconf.data() : nullptr));
+        const int64_t off[2] = {0, (int64_t)m};
+        check(gpc_evaluate_patches(h_, 1, off, X_star.data(), X_star.data() + m, nullptr, conf ? 1 : 0, f_star.data(), sigconf.data(),
+                                   nullptr, nullptr));
+    }
+    // void compute_likelihoods(VectorXd& l, const MatrixXd& X, const VectorXd& y), sparse_gp.hpp:414-420
+    void compute_likelihoods(Eigen::VectorXd& l, const Eigen::MatrixXd& X, const Eigen::VectorXd& y) {
+        if (!fitted_) throw std::runtime_error("sparse_gp::compute_likelihoods before add_measurements");
+        if (X.cols() != 2 || X.rows() != y.rows()) throw std::invalid_argument("sparse_gp::compute_likelihoods: X must be n x 2, y n");
+        const long m = X.rows();
+        l.resize(m);
+        const int64_t off[2] = {0, (int64_t)m};
+        check(gpc_evaluate_patches(h_, 1, off, X.data(), X.data() + m, y.data(), 0, nullptr, nullptr, l.data(), nullptr));
+    }
+    // void compute_derivatives(MatrixXd& dX /* n x 3 */, const MatrixXd& X, const VectorXd& y), sparse_gp.hpp:459-468
+    void compute_derivatives(Eigen::MatrixXd& dX, const Eigen::MatrixXd& X, const Eigen::VectorXd& y) {
+        if (!fitted_) throw std::runtime_error("sparse_gp::compute_derivatives before add_measurements");
+        if (X.cols() != 2 || X.rows() != y.rows()) throw std::invalid_argument("sparse_gp::compute_derivatives: X must be n x 2, y n");
+        const long m = X.rows();
+        std::vector<double> rows((size_t)3 * m);
+        const int64_t off[2] = {0, (int64_t)m};
+        check(gpc_evaluate_patches(h_, 1, off, X.data(), X.data() + m, y.data(), 0, nullptr, nullptr, nullptr, rows.data()));
+        dX.resize(m, 3);
+        for (long i = 0; i < m; i++)
+            for (int c = 0; c < 3; c++) dX(i, c) = rows[3 * i + c];
     }
     int size() { return size_; }                       // sparse_gp.hpp:36-39
     void reset() { if (h_) { gpc_destroy(h_); h_ = nullptr; } size_ = 0; fitted_ = false; }

@@ -79,7 +79,7 @@ typedef struct gpc_stats {
     uint64_t kernel_launches;   /* kernels launched by the last compress / decompress */
     uint64_t rgb_n_sparse, rgb_n_full, rgb_n_del_cap, rgb_n_del_geo, rgb_sum_n2_common;  /* RGB field GP events */
     float ms_h2d, ms_lattice, ms_keys, ms_sort, ms_leaves, ms_rotation, ms_claim, ms_group,
-          ms_shuffle, ms_fit, ms_d2h, ms_predict, ms_total, ms_fit_rgb;
+          ms_shuffle, ms_fit, ms_d2h, ms_predict, ms_total, ms_fit_rgb, ms_evaluate, pad_;
 } gpc_stats;
 
 /* ---- lifetime ---------------------------------------------------------------------- */
@@ -116,6 +116,18 @@ int gpc_get_heights(gpc_handle* h, double* heights_host, int64_t capacity);
  * on one patch (gp_index) at m arbitrary local coordinates X (m x 2, row-major).
  * sigma may be NULL; when given it needs keep_state (conf = false branch, :346). */
 int gpc_predict(gpc_handle* h, int64_t patch, const double* X, int64_t m, double* f, double* sigma);
+
+/* Next rows N2 / N4: batched evaluation of the fitted height GPs at ragged per-patch point sets -- what
+ * gp_registration::compute_transformation (gp_registration.cpp:175-194) asks of every patch, one point at a time:
+ *   f      sparse_gp::predict_measurements mean                         sparse_gp.hpp:299-351
+ *   sigma  its sigconf output: conf == 0 sqrt(s20 + k** + k'Ck), conf != 0 the 0..100 confidence (:340-346)
+ *   lik    sparse_gp::compute_likelihoods -> likelihood                 sparse_gp.hpp:407-425
+ *   dX     sparse_gp::compute_derivatives -> likelihood_dx, 3 per point sparse_gp.hpp:459-502, rbf_kernel.cpp:38-46
+ * Patches are the first P of this shard (local indices), points of patch p are [off[p], off[p+1]) of x1 / x2 / y
+ * (host arrays; y may be NULL when lik and dX are NULL).  Outputs are host arrays and may be NULL.  Needs a fit made
+ * with gpc_config.keep_state (the C matrices).  Device time of the kernel: gpc_stats.ms_evaluate. */
+int gpc_evaluate_patches(gpc_handle* h, int64_t P, const int64_t* off, const double* x1, const double* x2, const double* y,
+                         int conf, double* f, double* sigma, double* lik, double* dX);
 
 /* ---- results ---------------------------------------------------------------------------
  * Any output pointer may be NULL.  Per-patch arrays are indexed by gp_index over ALL

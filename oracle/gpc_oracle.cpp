@@ -399,15 +399,57 @@ struct Sogp {
     void predict_field_grid(double* f) const {
         for (int ch = 0; ch < D; ch++) f[ch] = (N == 0) ? 0.0 : row4(&alpha[(size_t)ch * ld], k.data(), N);
     }
-    // predictive sigma as sparse_gp.hpp:329-347 (conf = false): sqrt(s20 + kstar + k'Ck)
-    double predict_sigma(double x1, double x2) {
+    // ---- next rows N2 / N4: sparse_gp::predict with sigma / conf (sparse_gp.hpp:312-351), likelihood (:407-425) and
+    // likelihood_dx (:472-502, with rbf_kernel::kernel_dx rbf_kernel.cpp:38-46) at one point.  Canonical order:
+    // (C k)_i = sequential fma over j of C(j, i) k_j; every O(N) sum is a row4.  out: f, sigma, conf, lik, dx[3].
+    void evaluate(double x1, double x2, double y, double* out) {
+        std::vector<double> kx(std::max(N, 1)), ky(std::max(N, 1));
         const double kstar = P.p0;
-        if (N == 0) return std::sqrt(kstar + P.s20);
-        for (int i = 0; i < N; i++) k[i] = kern(x1, x2, b1[i], b2[i]);
-        for (int i = 0; i < N; i++) ck[i] = row4(&C[(size_t)i * ld], k.data(), N);
-        double s = (P.s20 + kstar) + dot32(k.data(), ck.data(), N);
-        if (s < 0) s = 0;
-        return std::sqrt(s);
+        const double c1 = (-P.p0) / P.p1;                       // -p(0)/p(1), rbf_kernel.cpp:44
+        for (int i = 0; i < N; i++) {
+            const double d1 = x1 - b1[i], d2 = x2 - b2[i];
+            const double e = orc_exp_impl(P.cl * (d1 * d1 + d2 * d2));
+            k[i] = P.p0 * e;
+            kx[i] = (c1 * d1) * e;
+            ky[i] = (c1 * d2) * e;
+        }
+        for (int i = 0; i < N; i++) {
+            double a = 0.0;
+            for (int j = 0; j < N; j++) a = std::fma(C[(size_t)j * ld + i], k[j], a);
+            ck[i] = a;
+        }
+        const double kCk = N ? row4(k.data(), ck.data(), N) : 0.0;
+        const double sx = N ? row4(kx.data(), ck.data(), N) : 0.0, sy = N ? row4(ky.data(), ck.data(), N) : 0.0;
+        const double mu = N ? row4(alpha.data(), k.data(), N) : 0.0;
+        const double ax = N ? row4(alpha.data(), kx.data(), N) : 0.0, ay = N ? row4(alpha.data(), ky.data(), N) : 0.0;
+        // predict (:329-349)
+        double var = (P.s20 + kstar) + kCk;
+        const double var_l = var;                                 // likelihood (:421) has no clamp
+        if (var < 0) var = 0;
+        out[0] = mu;
+        out[1] = std::sqrt(var);
+        out[2] = 100.0 * (1.0 - var / (kstar + P.s20));
+        // likelihood (:424)
+        const double off = y - mu;
+        out[3] = (1.0 / std::sqrt((2.0 * M_PI) * var_l)) * orc_exp_impl(((-0.5 / var_l) * off) * off);
+        // likelihood_dx (:487-499)
+        const double var_d = (P.s20 + kCk) + kstar;
+        const double sdx[2] = {2.0 * sx, 2.0 * sy};
+        const double sq = std::sqrt(var_d);
+        const double vs = var_d * sq;
+        const double exppart = (0.5 / vs) * orc_exp_impl(((-0.5 / var_d) * off) * off);
+        const double ad[2] = {ax, ay};
+        out[4] = ((-1.0 / vs) * off) * exppart;
+        for (int d = 0; d < 2; d++) {
+            const double first = -sdx[d], second = (2.0 * ad[d]) * off, third = ((sdx[d] / var_d) * off) * off;
+            out[5 + d] = exppart * ((first + second) + third);
+        }
+    }
+    // predictive sigma as sparse_gp.hpp:329-347 (conf = false): sqrt(s20 + kstar + k'Ck), the evaluate() arithmetic
+    double predict_sigma(double x1, double x2) {
+        double r[7];
+        evaluate(x1, x2, 0.0, r);
+        return r[1];
     }
 };
 
@@ -1249,6 +1291,33 @@ int64_t orc_decode(void* h, void* out32, double* heights, int with_sigma) {
     return ((Oracle*)h)->decode_into((uint8_t*)out32, heights, with_sigma);
 }
 // predict at arbitrary local coordinates for one patch
+// Batched evaluation over fitted patches (needs the C dump): out arrays may be null.  conf: 0 sigma, 1 confidence.
+int orc_evaluate(void* h, int64_t P, const int64_t* off, const double* x1, const double* x2, const double* y, int conf,
+                 double* f, double* sigma, double* lik, double* dX) {
+    Oracle* o = (Oracle*)h;
+    if (P < 0 || P > (int64_t)o->nbv.size()) return 1;
+    Sogp gp;
+    for (int64_t p = 0; p < P; p++) {
+        const int N = o->nbv[p];
+        if (N > 0 && o->dumpC.empty()) return 1;
+        gp.init(o->sogp_params(), std::max(N, 1));
+        gp.N = N;
+        for (int i = 0; i < N; i++) {
+            gp.alpha[i] = o->alpha[o->bv_off[p] + i]; gp.b1[i] = o->bv1[o->bv_off[p] + i]; gp.b2[i] = o->bv2[o->bv_off[p] + i];
+            for (int j = 0; j < N; j++) gp.c(i, j) = o->dumpC[o->dump_off[p] + (size_t)i * N + j];
+        }
+        for (int64_t t = off[p]; t < off[p + 1]; t++) {
+            double r[7];
+            gp.evaluate(x1[t], x2[t], y ? y[t] : 0.0, r);
+            if (f) f[t] = r[0];
+            if (sigma) sigma[t] = conf ? r[2] : r[1];
+            if (lik) lik[t] = r[3];
+            if (dX) { dX[3 * t] = r[4]; dX[3 * t + 1] = r[5]; dX[3 * t + 2] = r[6]; }
+        }
+    }
+    return 0;
+}
+
 int orc_predict(void* h, int64_t patch, const double* X, int64_t m, double* f, double* sigma) {
     Oracle* o = (Oracle*)h;
     if (patch < 0 || patch >= (int64_t)o->nbv.size()) return 1;

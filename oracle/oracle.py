@@ -63,6 +63,8 @@ def lib():
         L.orc_decode.restype = C.c_int64
         L.orc_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_predict.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.orc_evaluate.restype = C.c_int
+        L.orc_evaluate.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4
         L.orc_get_sizes.argtypes = [C.c_void_p, C.POINTER(OrcSizes)]
         L.orc_ptr.restype = C.c_void_p
         L.orc_ptr.argtypes = [C.c_void_p, C.c_char_p]
@@ -268,6 +270,16 @@ class Oracle:
         m = lib().orc_decode(self.h, _p(cloud) if want_cloud else None, _p(heights) if want_heights else None, int(with_sigma))
         assert m == n
         return cloud, heights
+
+    def evaluate(self, off, x1, x2, y, conf=False):
+        """Batched predict (sigma or conf) / likelihood / likelihood_dx over the fitted patches; needs fit(dump=True)."""
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        x1, x2, y = (np.ascontiguousarray(a, dtype=np.float64) for a in (x1, x2, y))
+        m = x1.size
+        f, sg, lk, dX = np.zeros(m), np.zeros(m), np.zeros(m), np.zeros(3 * m)
+        rc = lib().orc_evaluate(self.h, off.size - 1, _p(off), _p(x1), _p(x2), _p(y), int(conf), _p(f), _p(sg), _p(lk), _p(dX))
+        assert rc == 0, "orc_evaluate needs the state dump (fit with dump=True)"
+        return dict(f=f, sigma=sg, lik=lk, dX=dX.reshape(m, 3))
 
     def predict(self, patch, X, sigma=False):
         X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, 2)

@@ -93,6 +93,37 @@ int ref_field_fit(int n, const double* x1, const double* x2, const double* Y, in
     return N;
 }
 
+// Fit, then the reference's own predict_measurements (sigma and conf modes, sparse_gp.hpp:299-351),
+// compute_likelihoods (:414-420) and compute_derivatives (:459-468) at the given points.
+int ref_sogp_evaluate(int n, const double* x1, const double* x2, const double* y, int capacity, double s0, double sigmaf_sq,
+                      double l_sq, double eps_tol, unsigned long long rand_offset, int m, const double* ex1, const double* ex2,
+                      const double* ey, double* f, double* sigma, double* conf, double* lik, double* dX) {
+    srand(1);
+    for (unsigned long long i = 0; i < rand_offset; i++) rand();
+    ref_gp gp(capacity, s0);
+    gp.kernel.param()(0) = sigmaf_sq;
+    gp.kernel.param()(1) = l_sq;
+    gp.eps_tol = eps_tol;
+    Eigen::MatrixXd X(n, 2);
+    Eigen::VectorXd Y(n);
+    for (int i = 0; i < n; i++) { X(i, 0) = x1[i]; X(i, 1) = x2[i]; Y(i) = y[i]; }
+    if (n > 0) gp.add_measurements(X, Y);
+    Eigen::MatrixXd Xs(m, 2);
+    Eigen::VectorXd Ys(m);
+    for (int i = 0; i < m; i++) { Xs(i, 0) = ex1[i]; Xs(i, 1) = ex2[i]; Ys(i) = ey[i]; }
+    Eigen::VectorXd fs, sg, cf, l;
+    Eigen::MatrixXd D;
+    gp.predict_measurements(fs, Xs, sg, false);
+    gp.predict_measurements(fs, Xs, cf, true);
+    gp.compute_likelihoods(l, Xs, Ys);
+    gp.compute_derivatives(D, Xs, Ys);
+    for (int i = 0; i < m; i++) {
+        f[i] = fs(i); sigma[i] = sg(i); conf[i] = cf(i); lik[i] = l(i);
+        for (int c = 0; c < 3; c++) dX[3 * i + c] = D(i, c);
+    }
+    return gp.size();
+}
+
 // sparse_gp::shuffle alone (sparse_gp.hpp:42-56) over the real rand()
 void ref_shuffle(int n, unsigned long long rand_offset, int* out) {
     srand(1);

@@ -40,6 +40,14 @@ int main(int argc, char** argv) {
         Eigen::VectorXd fs, sg;
         gp.predict_measurements(fs, Xs, sg);
         std::printf("SOGP %d %.17g\n", gp.size(), fs(0));
+        // rows N2 / N4 through the same shell: sigma, confidence, likelihood, likelihood gradient
+        Eigen::VectorXd cf, lk, ys(1);
+        Eigen::MatrixXd dX;
+        ys(0) = 0.004;
+        gp.predict_measurements(fs, Xs, cf, true);
+        gp.compute_likelihoods(lk, Xs, ys);
+        gp.compute_derivatives(dX, Xs, ys);
+        std::printf("EVAL %.17g %.17g %.17g %.17g %.17g %.17g\n", sg(0), cf(0), lk(0), dX(0, 0), dX(0, 1), dX(0, 2));
         bool threw = false;
         try { pointcloud_decompressor d; d.load_compressed("x"); } catch (const std::exception&) { threw = true; }
         std::printf("KSVD_SHELL %d\n", (int)threw);

@@ -47,6 +47,22 @@ def main():
                            meta=np.array([n, cap, n - 1, r["N"]], dtype=np.int64),
                            hyper=np.array([hyp["sigmaf_sq"], hyp["l_sq"], hyp["s0"]])).items():
             out[f"{name}/{key}"] = v
+    # rows N2 / N4: the reference's predict_measurements (sigma, conf), compute_likelihoods and compute_derivatives
+    for name, n, cap, hyp in [("eval_cap12", 300, 12, dict(sigmaf_sq=1.0, l_sq=(0.1 / 12) ** 2, s0=1e-4)),
+                              ("eval_cap40", 700, 40, dict(sigmaf_sq=2.0, l_sq=4e-4, s0=1e-3)),
+                              ("eval_empty", 0, 10, dict(sigmaf_sq=1.5, l_sq=1e-3, s0=1e-2))]:
+        rng = np.random.default_rng(len(name) + n)
+        x1 = rng.uniform(-0.05, 0.05, n)
+        x2 = rng.uniform(-0.05, 0.05, n)
+        fn = lambda a, b: 0.02 * np.sin(40 * a) * np.cos(30 * b) + 0.5 * a
+        y = fn(x1, x2) + rng.normal(0, 0.003, n)
+        ex = rng.uniform(-0.05, 0.05, (40, 2))
+        ey = fn(ex[:, 0], ex[:, 1]) + rng.normal(0, 0.01, 40)
+        r = R.evaluate(x1, x2, y, ex, ey, capacity=cap, rand_offset=3, **hyp)
+        for key, v in dict(x1=x1, x2=x2, y=y, ex=ex, ey=ey, f=r["f"], sigma=r["sigma"], conf=r["conf"], lik=r["lik"], dX=r["dX"],
+                           meta=np.array([n, cap, 3, r["N"]], dtype=np.int64),
+                           hyper=np.array([hyp["sigmaf_sq"], hyp["l_sq"], hyp["s0"]])).items():
+            out[f"{name}/{key}"] = v
     out["shuffle_n57_off3"] = R.shuffle(57, 3)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_sogp.npz"), **out)
     print("wrote", len(out), "arrays")

@@ -10,7 +10,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = np.load(os.path.join(ROOT, "tests", "golden", "ref_sogp.npz"))
-CASES = sorted({k.split("/")[0] for k in GOLD.files if "/" in k and not k.startswith("field_")})
+CASES = sorted({k.split("/")[0] for k in GOLD.files if "/" in k and not k.startswith(("field_", "eval_"))})
+EVAL_CASES = sorted({k.split("/")[0] for k in GOLD.files if k.startswith("eval_")})
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -31,3 +32,20 @@ def test_cuda_sogp_matches_reference_source_vectors(name):
         assert np.abs(f - g["f"]).max() <= 1e-6 * np.abs(g["f"]).max()
     else:
         assert np.abs(f - g["f"]).max() <= 2e-4
+
+
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_cuda_evaluate_matches_reference_source_vectors(name):
+    """Rows N2 / N4 through the C ABI (gpc_evaluate_patches) against the reference's own predict_measurements /
+    compute_likelihoods / compute_derivatives outputs."""
+    import gp_compressor_b200 as G
+    from test_oracle_vs_reference_source import check_eval, eval_tol
+    g = {k.split("/")[1]: GOLD[k] for k in GOLD.files if k.startswith(name + "/")}
+    n, cap, roff, N = (int(v) for v in g["meta"])
+    p0, l_sq, s0 = (float(v) for v in g["hyper"])
+    h = G.Handle(capacity=cap, sigmaf_sq=p0, l_sq=l_sq, s0=s0, rgb_rand=0, keep_state=1)
+    h.set_rand_offset(roff)
+    h.fit_patches([0, n], g["x1"], g["x2"], g["y"])
+    assert int(h.params()["nbv"][0]) == N
+    q = ([0, g["ex"].shape[0]], g["ex"][:, 0].copy(), g["ex"][:, 1].copy(), g["ey"])
+    check_eval(h.evaluate(*q), h.evaluate(*q, conf=True), g, eval_tol(name))

@@ -40,7 +40,7 @@ def test_driver_matches_ctypes_path(tmp_path):
     dec_path = tmp_path / "decoded.bin"
     out = subprocess.run([exe, str(path), str(dec_path)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
-    lines = dict(l.split(" ", 1) for l in out.stdout.splitlines() if l.split(" ")[0] in ("CLOUD", "SOGP", "KSVD_SHELL"))
+    lines = dict(l.split(" ", 1) for l in out.stdout.splitlines() if l.split(" ")[0] in ("CLOUD", "SOGP", "EVAL", "KSVD_SHELL"))
     h = G.Handle(res=float(np.float32(0.15)), sz=20, rgb=1)  # the literals of test_gp_compress.cpp:21; the shell enables the RGB GP
     h.compress(cloud)
     dec = h.decompress()
@@ -50,3 +50,12 @@ def test_driver_matches_ctypes_path(tmp_path):
     nb, f = lines["SOGP"].split()
     assert int(nb) == 2 and abs(float(f) - 0.0050018719900836684) < 1e-10   # SURVEY.md section 4 known answer
     assert lines["KSVD_SHELL"].strip() == "1"
+    # predict_measurements (sigma, conf) / compute_likelihoods / compute_derivatives of the shell == the ctypes path
+    g = G.Handle(capacity=2, s0=float(np.float32(1e-1)), shuffle=0, rgb_rand=0, keep_state=1)
+    pts = np.array([[0, 0, .01], [.05, 0, .02], [0, .05, -.01], [.05, .05, 0]])
+    g.fit_patches(np.array([0, 4]), pts[:, 0].copy(), pts[:, 1].copy(), pts[:, 2].copy())
+    q = (np.array([0, 1]), np.array([0.025]), np.array([0.025]), np.array([0.004]))
+    e, ec = g.evaluate(*q), g.evaluate(*q, conf=True)
+    want = [e["sigma"][0], ec["sigma"][0], e["lik"][0], *e["dX"][0]]
+    got = [float(v) for v in lines["EVAL"].split()]
+    assert got == [float(repr(float(w))) for w in want]

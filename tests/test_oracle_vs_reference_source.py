@@ -14,7 +14,8 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = np.load(os.path.join(ROOT, "tests", "golden", "ref_sogp.npz"))
-CASES = sorted({k.split("/")[0] for k in GOLD.files if "/" in k and not k.startswith("field_")})
+CASES = sorted({k.split("/")[0] for k in GOLD.files if "/" in k and not k.startswith(("field_", "eval_"))})
+EVAL_CASES = sorted({k.split("/")[0] for k in GOLD.files if k.startswith("eval_")})
 FIELD_CASES = sorted({k.split("/")[0] for k in GOLD.files if k.startswith("field_")})
 
 
@@ -107,3 +108,33 @@ def test_oracle_field_gp_matches_reference_source_vectors(oracle_mod, name):
     a = r["alpha"].reshape(N, 3)
     tol = 1e-3 if l_sq >= 1.0 else 1e-9   # reference defaults are ill-conditioned; the capacity-bound case is exact to rounding
     assert np.abs(a - g["alpha"]).max() <= tol * np.abs(g["alpha"]).max()
+
+
+def check_eval(e, ec, g, tol=1e-9):
+    """e / ec: evaluate outputs (sigma / conf mode) of the oracle or the CUDA path; g: golden arrays of the reference.
+    tol: 1e-9 (the path tolerance) where the fitted state itself agrees to rounding level; the 700-point capacity-40
+    case inherits the 5e-6 state agreement of its fit (see check_against)."""
+    np.testing.assert_allclose(e["f"], g["f"], rtol=tol, atol=tol * np.abs(g["f"]).max())
+    np.testing.assert_allclose(e["sigma"], g["sigma"], rtol=tol)
+    np.testing.assert_allclose(ec["sigma"], g["conf"], rtol=tol, atol=tol * 100)
+    np.testing.assert_allclose(e["lik"], g["lik"], rtol=10 * tol)
+    np.testing.assert_allclose(e["dX"], g["dX"], rtol=10 * tol, atol=tol * np.abs(g["dX"]).max())
+
+
+def eval_tol(name):
+    return 2e-5 if name == "eval_cap40" else 1e-9
+
+
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_oracle_evaluate_matches_reference_source_vectors(oracle_mod, name):
+    """Rows N2 / N4: predict with sigma / conf (sparse_gp.hpp:299-351), likelihood (:407-425) and likelihood_dx
+    (:472-502) of the reference's own source against the oracle, on the reference's own fit of the same patch."""
+    g = {k.split("/")[1]: GOLD[k] for k in GOLD.files if k.startswith(name + "/")}
+    n, cap, roff, N = (int(v) for v in g["meta"])
+    p0, l_sq, s0 = (float(v) for v in g["hyper"])
+    o = oracle_mod.Oracle(capacity=cap, sigmaf_sq=p0, l_sq=l_sq, s0=s0, rgb_rand=0)
+    o.set_rand_offset(roff)
+    r = o.fit_patches([0, n], g["x1"], g["x2"], g["y"], dump=True)
+    assert int(r["nbv"][0]) == N
+    q = ([0, g["ex"].shape[0]], g["ex"][:, 0].copy(), g["ex"][:, 1].copy(), g["ey"])
+    check_eval(o.evaluate(*q), o.evaluate(*q, conf=True), g, eval_tol(name))

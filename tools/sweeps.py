@@ -52,7 +52,34 @@ def c4(n_patches, nbv, sz=64):
     print(f"| {n_patches} | {nbv} | {sz}x{sz} | {n} | {best:.2f} | {n / (best * 1e-3):.3e} | {flops / (best * 1e-3) / 1e12:.2f} | {flops / (best * 1e-3) / fp64_peak:.3f} | {gbs:.0f} | {gbs / hbm:.3f} |")
     h.close()
 
+def ev(n_patches, cap, n_fit=300, n_query=256, res=0.1):
+    """K9 (rows N2 / N4): batched predict + sigma + likelihood + gradient at n_query points per patch."""
+    rng = np.random.default_rng(cap)
+    off = np.arange(n_patches + 1, dtype=np.int64) * n_fit
+    x1 = rng.uniform(-res / 2, res / 2, n_patches * n_fit); x2 = rng.uniform(-res / 2, res / 2, n_patches * n_fit)
+    y = 0.02 * np.sin(40 * x1) * np.cos(30 * x2) + rng.normal(0, 0.003, x1.size)
+    h = G.Handle(capacity=cap, keep_state=1, sigmaf_sq=1.0, l_sq=(res / 12.0) ** 2, s0=1e-4)
+    h.fit_patches(off, x1, x2, y)
+    nbv = h.params()["nbv"].astype(np.float64)
+    qoff = np.arange(n_patches + 1, dtype=np.int64) * n_query
+    q1 = rng.uniform(-res / 2, res / 2, n_patches * n_query); q2 = rng.uniform(-res / 2, res / 2, n_patches * n_query)
+    qy = 0.02 * np.sin(40 * q1) * np.cos(30 * q2)
+    fp64_peak = h.debug_peak(0)
+    best = 1e9
+    for it in range(3):
+        h.evaluate(qoff, q1, q2, qy)
+        best = min(best, h.stats()["ms_evaluate"])
+    flops = float((n_query * (2 * nbv * nbv + 49 * nbv + 60)).sum())
+    m = n_patches * n_query
+    print(f"| {n_patches} | {cap} | {nbv.mean():.1f} | {m} | {best:.2f} | {m / (best * 1e-3):.3e} | {flops / (best * 1e-3) / 1e12:.2f} | {flops / (best * 1e-3) / fp64_peak:.3f} |")
+    h.close()
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "eval":
+        print("| patches | capacity | mean BV | query pts | evaluate ms | pts/s | TFLOP/s (2N^2+49N+60 per pt) | frac of FP64 peak |")
+        print("|---|---|---|---|---|---|---|---|")
+        ev(20000, 12); ev(20000, 30); ev(10000, 60); ev(5000, 100); ev(2000, 150)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "c4":
         c4(125_000, 30); c4(125_000, 100); c4(250_000, 30); c4(125_000, 30, sz=10)
         sys.exit(0)
