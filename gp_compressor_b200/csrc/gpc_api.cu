@@ -39,7 +39,7 @@ struct gpc_handle {
     DevBuf perm_rgb, fcr, fcg, fcb, r_nbv, r_flags, r_alpha0, r_alpha1, r_alpha2, r_b1, r_b2, r_bidx, kstats_rgb;
     bool have_rgb = false;
     DevBuf quat, mean, rgbmean, Rm, center, code, ncand, owner, st_idx;
-    DevBuf tmpA, tmpB, tmpC, lat_state, ev_in, ev_out;
+    DevBuf tmpA, tmpB, tmpC, lat_state, ev_in, ev_out, size_ids, size_hist;
     // binning scratch
     DevBuf keys, keys2, vals, vals2, ovals, ovals2, sort_tmp, flags64, ex, leaf_of, leaf_start, leaf_code_a, spt, nbr, nnbr,
         center_a, Rm_a, ncand_a, pt0, pt1, pt2, hbuf, rgb, leaf_sums;
@@ -109,7 +109,7 @@ void shard_range(const std::vector<int64_t>& off, int r, int c, int64_t* lo, int
 int run_buckets(gpc_handle* h, SogpArgs& a, int need_ld, int64_t PL, int64_t lo, uint64_t* escalated) {
     cudaStream_t st = h->stream;
     int64_t work = PL;
-    const int32_t* ids = nullptr;
+    const int32_t* ids = h->size_ids.as<int32_t>();  // bucket 0 visits the patches by decreasing size (see launch_size_order)
     a.spill = nullptr;
     int step = 0;
     for (int b = 0; b < 5 && work > 0; b = sogp_next_bucket(b, a.dout), step++) {
@@ -232,6 +232,9 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
     a.dumpQ = c.keep_state ? h->dumpQ.as<double>() : nullptr;
     a.stats = h->kstats.as<unsigned long long>();
     {
+        CK(h->size_ids.reserve((size_t)PL * sizeof(int32_t)));
+        CK(h->size_hist.reserve(1024 * sizeof(int32_t)));
+        launch_size_order(h->off.as<int64_t>(), lo, PL, h->size_hist.as<int32_t>(), h->size_ids.as<int32_t>(), st);
         int rc = run_buckets(h, a, need_ld, PL, lo, h->stats.escalated);
         if (rc) return rc;
     }
@@ -620,7 +623,7 @@ void gpc_destroy(gpc_handle* h) {
                       &h->dumpC, &h->dumpQ, &h->queue0, &h->queue1, &h->hand0, &h->hand1, &h->spill, &h->qcount, &h->kstats, &h->bv_off, &h->palpha, &h->pb1, &h->pb2, &h->pidx, &h->perm_rgb, &h->fcr, &h->fcg, &h->fcb, &h->r_nbv, &h->r_flags,
                       &h->r_alpha0, &h->r_alpha1, &h->r_alpha2, &h->r_b1, &h->r_b2, &h->r_bidx, &h->kstats_rgb, &h->nonempty, &h->slot, &h->out32,
                       &h->heights, &h->quat, &h->mean, &h->rgbmean, &h->Rm, &h->center, &h->code, &h->ncand, &h->owner,
-                      &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->lat_state, &h->ev_in, &h->ev_out, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
+                      &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->lat_state, &h->ev_in, &h->ev_out, &h->size_ids, &h->size_hist, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
                       &h->ovals2, &h->sort_tmp, &h->flags64, &h->ex, &h->leaf_of, &h->leaf_start, &h->leaf_code_a, &h->spt,
                       &h->nbr, &h->nnbr, &h->center_a, &h->Rm_a, &h->ncand_a, &h->pt0, &h->pt1, &h->pt2, &h->hbuf, &h->rgb, &h->leaf_sums};
     for (DevBuf* b : bufs) b->release();

@@ -9,10 +9,10 @@
 // State per CTA in shared memory: C and Q (LD x LD doubles each, bitwise symmetric, so
 // "row i" is read as the contiguous column i: conflict-free), plus work vectors.
 //
-// Bucket 0 (N + 1 <= 16): ONE WARP per patch.  Lane l < 16 owns index l of alpha / BV / k in
-// registers; lanes 0-15 compute rows of C k, lanes 16-31 rows of Q k; the three dot products
-// are one product per lane and one shared butterfly; rank-1 updates split columns between
-// the two half-warps.  No block barrier, only __syncwarp.
+// Bucket 0 (N + 1 <= 16): TWO PATCHES per warp, one per half-warp.  Lane r of a half-warp owns index r of
+// alpha / BV / k in registers and row r of C and of Q in shared memory; the three dot products are one product
+// per lane and a 4-step butterfly; patches are visited by decreasing size so that the two halves of a warp have
+// (almost) equal streams.  No block barrier, only __syncwarp on the half-warp's own mask.
 // Buckets 2-4 (LD 64 / 118 / 202): NT = 4*RB threads.  A warp covers 16 rows of one matrix for the matvec
 // (its two half-warps split the canonical partial sums and combine them with one shuffle); for rank-1 /
 // rank-2 updates a thread owns one row and every fourth column; the dot products are computed redundantly
@@ -85,9 +85,9 @@ __device__ __forceinline__ int warp_first_min(double sc, int idx, double* minsco
 }
 
 // =====================================================================================
-// Bucket 0: one warp per patch.  Rows are contiguous (row r at r * W_LD, W_LD = 18: the
-// two pad columns keep 16-byte alignment and make the 128-bit row loads of a quarter-warp
-// hit distinct banks).  C and Q are bitwise symmetric, so row r == column r.
+// Bucket 0 layout: rows are contiguous (row r at r * W_LD, W_LD = 18: the two pad columns keep
+// 16-byte alignment and make the 128-bit row loads of a quarter-warp hit distinct banks).
+// C and Q are bitwise symmetric, so row r == column r.
 // =====================================================================================
 constexpr int W_N = 16;    // N + 1 <= 16
 constexpr int W_LD = 18;
@@ -95,32 +95,6 @@ constexpr int W_LD = 18;
 template <int DOUT>
 struct __align__(16) StagedPointT { double x1, x2, y[DOUT]; int orig, pad; };
 typedef StagedPointT<1> StagedPoint;
-template <int DOUT>
-struct WarpSmem {
-    double C[W_N * W_LD], Q[W_N * W_LD];
-    double kv[W_N], sv[W_N], ev[W_N];
-    StagedPointT<DOUT> pts[32];   // the next 32 points of the patch's stream, loaded coalesced
-    unsigned long long cnt[NCNT];
-};
-
-// (M k)_r for a contiguous, zero-padded row: groups of 4 columns up to ceil(n/4)*4.  Pad columns hold
-// exact zeros and k is finite, so the extra terms leave the accumulators (never -0) bit-unchanged:
-// the result equals the canonical row4 over n columns.
-__device__ __forceinline__ double row4_padded16(const double* row, const double* k, int n) {
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-    for (int g = 0; g < 4; g++) {
-        if (4 * g < n) {
-            const double2 m01 = *reinterpret_cast<const double2*>(row + 4 * g), m23 = *reinterpret_cast<const double2*>(row + 4 * g + 2);
-            const double2 k01 = *reinterpret_cast<const double2*>(k + 4 * g), k23 = *reinterpret_cast<const double2*>(k + 4 * g + 2);
-            a0 = fma(m01.x, k01.x, a0);
-            a1 = fma(m01.y, k01.y, a1);
-            a2 = fma(m23.x, k23.x, a2);
-            a3 = fma(m23.y, k23.y, a3);
-        }
-    }
-    return __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
-}
 
 // canonical row4 over a contiguous row with 128-bit loads: identical operation order
 __device__ __forceinline__ double row4_contig(const double* row, const double* k, int n) {
@@ -143,37 +117,101 @@ __device__ __forceinline__ double row4_contig(const double* row, const double* k
     return __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
 }
 
+// =====================================================================================
+// Bucket 0, packed: TWO PATCHES per warp, one per half-warp.  With N + 1 <= 16 a full warp per patch leaves most
+// lanes of every scalar step (exp, divisions, butterflies) idle; here lane r of a half-warp owns index r of
+// alpha / BV / k AND row r of both C and Q, so the per-point instruction stream serves two patches.  The halves run
+// independently (own masks for every shuffle / sync, own control flow); they share instructions whenever they are
+// on the same path, which is the sparse update almost always.  Same arithmetic and operation order as every bucket:
+// the 16 partial products of a dot reduce with a 4-step butterfly (the canonical dot32 with zeros in partials 16-31).
+// =====================================================================================
+__device__ __forceinline__ double shfl16_xor(unsigned gm, double v, int off) { return __shfl_xor_sync(gm, v, off, 16); }
+__device__ __forceinline__ double shfl16(unsigned gm, double v, int src) { return __shfl_sync(gm, v, src, 16); }
+
+// first strict minimum over the 16 lanes of a half-warp (see warp_first_min)
+__device__ __forceinline__ int half_first_min(unsigned gm, double sc, int idx, double* minscore) {
+    const bool valid = idx != 0x7fffffff;
+    const bool isn = sc != sc;
+    const int nan0 = __any_sync(gm, valid && isn && idx == 0);
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    const double v = (valid && !isn) ? sc : inf;
+    double m = v;
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) m = fmin(m, shfl16_xor(gm, m, off));
+    int cand = (valid && !isn && v == m) ? idx : 0x7fffffff;
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) cand = min(cand, __shfl_xor_sync(gm, cand, off, 16));
+    if (nan0) {
+        *minscore = __longlong_as_double(0x7ff8000000000000LL);
+        return 0;
+    }
+    *minscore = m;
+    return cand;
+}
+
+template <int DOUT>
+struct HalfSmem {
+    double C[W_N * W_LD], Q[W_N * W_LD];
+    double kv[W_N], sv[W_N], ev[W_N];
+    StagedPointT<DOUT> pts[16];
+    unsigned long long cnt[NCNT];
+};
+
+// (C k)_r and (Q k)_r for contiguous zero-padded rows, k loaded once (see row4_padded16)
+__device__ __forceinline__ void row4x2_padded16(const double* crow, const double* qrow, const double* k, int n, double* rc, double* rq) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        if (4 * g < n) {
+            const double2 k01 = *reinterpret_cast<const double2*>(k + 4 * g), k23 = *reinterpret_cast<const double2*>(k + 4 * g + 2);
+            const double2 c01 = *reinterpret_cast<const double2*>(crow + 4 * g), c23 = *reinterpret_cast<const double2*>(crow + 4 * g + 2);
+            const double2 q01 = *reinterpret_cast<const double2*>(qrow + 4 * g), q23 = *reinterpret_cast<const double2*>(qrow + 4 * g + 2);
+            a0 = fma(c01.x, k01.x, a0); a1 = fma(c01.y, k01.y, a1); a2 = fma(c23.x, k23.x, a2); a3 = fma(c23.y, k23.y, a3);
+            b0 = fma(q01.x, k01.x, b0); b1 = fma(q01.y, k01.y, b1); b2 = fma(q23.x, k23.x, b2); b3 = fma(q23.y, k23.y, b3);
+        }
+    }
+    *rc = __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
+    *rq = __dadd_rn(__dadd_rn(b0, b1), __dadd_rn(b2, b3));
+}
+
 // DOUT = 1: sparse_gp (heights).  DOUT = 3: sparse_gp_field (RGB): alpha has three columns, the capacity score is
 // |alpha_i|^2 / (Q_ii + C_ii) (sparse_gp_field.hpp:187) and delete_bv updates alpha with alphastar * ((q*+c*)(Qs+Cs)) (:250-253).
 template <int DOUT>
-__global__ void __launch_bounds__(32, DOUT == 1 ? 32 : 20) sogp_fit_warp_kernel(SogpArgs a) {
-    __shared__ __align__(16) WarpSmem<DOUT> sm;
+__global__ void __launch_bounds__(32, DOUT == 1 ? 20 : 16) sogp_fit_half_kernel(SogpArgs a) {
+    __shared__ __align__(16) HalfSmem<DOUT> sm2[2];
+    const int lane = threadIdx.x;
+    const int half = lane >> 4, r = lane & 15;
+    const unsigned gm = 0xffffu << (16 * half);
+    const int64_t w = 2 * (int64_t)blockIdx.x + half;
+    if (w >= a.n_work) return;
+    HalfSmem<DOUT>& sm = sm2[half];
     double* const C = sm.C;
     double* const Q = sm.Q;
-    const int lane = threadIdx.x;
-    const int r = lane & 15, mat = lane >> 4;
-    const int64_t patch = a.patch_ids ? (int64_t)a.patch_ids[blockIdx.x] : a.first_patch + blockIdx.x;
+    const int64_t patch = a.patch_ids ? (int64_t)a.patch_ids[w] : a.first_patch + w;
     const int64_t o = a.off[patch];
     const int n = (int)(a.off[patch + 1] - o);
     const int64_t op = patch - a.out_first;
     if (n == 0) {
-        if (lane == 0) { a.nbv[op] = 0; a.flags[op] = 0; }
+        if (r == 0) { a.nbv[op] = 0; a.flags[op] = 0; }
         return;
     }
 #pragma unroll
-    for (int i = 0; i < W_N * W_LD / 32; i++) { C[lane + 32 * i] = 0.0; Q[lane + 32 * i] = 0.0; }
-    if (lane < NCNT) sm.cnt[lane] = 0;
-    if (lane < W_N) { sm.kv[lane] = 0.0; sm.sv[lane] = 0.0; sm.ev[lane] = 0.0; }  // pad terms must be finite
-    __syncwarp();
+    for (int i = 0; i < W_N * W_LD / 16; i++) { C[r + 16 * i] = 0.0; Q[r + 16 * i] = 0.0; }
+    if (r < NCNT) sm.cnt[r] = 0;
+    sm.kv[r] = 0.0; sm.sv[r] = 0.0; sm.ev[r] = 0.0;  // pad terms must be finite
+    __syncwarp(gm);
     const double kstar = a.p0, s20 = a.s20, p0 = a.p0, cl = a.cl, eps_tol = a.eps_tol;
     const int cap = a.capacity, ldmax = a.ld;
-    double alpha[DOUT], b1 = 0.0, b2 = 0.0;  // lane l < 16 owns entry l
+    double alpha[DOUT], b1 = 0.0, b2 = 0.0;  // lane r owns entry r
 #pragma unroll
     for (int c = 0; c < DOUT; c++) alpha[c] = 0.0;
     int bidx = -1;
     int N = 0;
     unsigned int run = 0;  // sparse points at the current N, folded into sm.cnt when N changes
-    double* const Mrow = (mat ? Q : C) + r * W_LD;
+    // k of the NEXT point is computed ahead, while this point's dependent chain (matvec, butterflies, divisions) runs:
+    // it only depends on the BV set, which a sparse update leaves alone.  After a full update it is recomputed.
+    double kl_next = 0.0;
+    bool have_next = false;
     double* const Crow = C + r * W_LD;
     double* const Qrow = Q + r * W_LD;
 
@@ -184,23 +222,23 @@ __global__ void __launch_bounds__(32, DOUT == 1 ? 32 : 20) sogp_fit_warp_kernel(
     for (int c = 0; c < DOUT; c++) gy[c] = a.fy[c] + o;
     const int32_t* const go = a.forig + o;
     for (int tt = 0; tt < n; ++tt) {
-        if ((tt & 31) == 0) {  // stage the next 32 points: one coalesced load per lane
-            __syncwarp();
-            const int i = tt + lane;
+        if ((tt & 15) == 0) {  // stage the next 16 points: one coalesced load per lane
+            __syncwarp(gm);
+            const int i = tt + r;
             if (i < n) {
                 StagedPointT<DOUT> sp;
                 sp.x1 = gx1[i]; sp.x2 = gx2[i]; sp.orig = go[i]; sp.pad = 0;
 #pragma unroll
                 for (int c = 0; c < DOUT; c++) sp.y[c] = gy[c][i];
-                sm.pts[lane] = sp;
+                sm.pts[r] = sp;
             }
-            __syncwarp();
+            __syncwarp(gm);
         }
-        const StagedPointT<DOUT> pt = sm.pts[tt & 31];
+        const StagedPointT<DOUT> pt = sm.pts[tt & 15];
         const double x1 = pt.x1, x2 = pt.x2;
         const int orig = pt.orig;
         if (N == 0) {  // sparse_gp.hpp:100-110
-            if (lane == 0) {
+            if (r == 0) {
                 const double d = __dadd_rn(kstar, s20);
 #pragma unroll
                 for (int c = 0; c < DOUT; c++) alpha[c] = __ddiv_rn(pt.y[c], d);
@@ -210,42 +248,51 @@ __global__ void __launch_bounds__(32, DOUT == 1 ? 32 : 20) sogp_fit_warp_kernel(
                 sm.cnt[0]++;
             }
             N = 1;
-            __syncwarp();
+            __syncwarp(gm);
             continue;
         }
         // k = K(x, BV) (:119); lanes >= N hold zeros
-        const bool act = lane < N;
-        double kl = rbf(x1, x2, b1, b2, p0, cl);
+        const bool act = r < N;
+        double kl = have_next ? kl_next : rbf(x1, x2, b1, b2, p0, cl);
         kl = act ? kl : 0.0;
-        if (act) sm.kv[lane] = kl;
-        __syncwarp();
-        // lanes 0-15: (C k)_r ; lanes 16-31: (Q k)_r = e_hat_r   (:122, :140)
-        double rv = 0.0;
-        if (r < N) rv = row4_padded16(Mrow, sm.kv, N);
-        const double el = __shfl_down_sync(0xffffffffu, rv, 16);
-        // m = alpha'k, k'Ck, k'e_hat.  N <= 16, so the canonical dot32 has zeros in partials 16..31 and its first
-        // butterfly step is the identity: a 4-step butterfly over 16 lanes gives the same bits.  The lower half-warp
-        // reduces k'Ck while the upper one reduces k'e_hat = k'Qk (its lanes own the Q rows); alpha'k rides along.
+        if (act) sm.kv[r] = kl;
+        __syncwarp(gm);
+        have_next = ((tt + 1) & 15) != 0 && tt + 1 < n;   // the next point is already staged
+        // (C k)_r and (Q k)_r = e_hat_r   (:122, :140)
+        double rv = 0.0, el = 0.0;
+        if (act) row4x2_padded16(Crow, Qrow, sm.kv, N, &rv, &el);
+        // m = alpha'k, k'Ck, k'e_hat: one product per lane, 4-step butterflies over the half-warp
         double pm[DOUT];
 #pragma unroll
         for (int c = 0; c < DOUT; c++) pm[c] = act ? fma(alpha[c], kl, 0.0) : 0.0;
-        double p2 = (r < N) ? fma(sm.kv[r], rv, 0.0) : 0.0;
+        double pc = act ? fma(kl, rv, 0.0) : 0.0;
+        double pe = act ? fma(kl, el, 0.0) : 0.0;
 #pragma unroll
         for (int off = 8; off >= 1; off >>= 1) {
 #pragma unroll
-            for (int c = 0; c < DOUT; c++) pm[c] = __dadd_rn(pm[c], shfl_xor_d(pm[c], off));
-            p2 = __dadd_rn(p2, shfl_xor_d(p2, off));
+            for (int c = 0; c < DOUT; c++) pm[c] = __dadd_rn(pm[c], shfl16_xor(gm, pm[c], off));
+            pc = __dadd_rn(pc, shfl16_xor(gm, pc, off));
+            pe = __dadd_rn(pe, shfl16_xor(gm, pe, off));
+            if (off == 8) {
+                // unconditional (a stale slot is read when the next point is not staged; the value is then ignored) and
+                // placed inside the butterfly's basic block: the exp chain overlaps the shuffle latency
+                const double nx1 = sm.pts[(tt + 1) & 15].x1, nx2 = sm.pts[(tt + 1) & 15].x2;
+                kl_next = rbf(nx1, nx2, b1, b2, p0, cl);
+            }
         }
-        const double pc = __shfl_sync(0xffffffffu, p2, 0), pe = __shfl_sync(0xffffffffu, p2, 16);
         const double s2 = __dadd_rn(kstar, pc);
         const double den = __dadd_rn(s20, s2);
-        // one division for two quotients: the upper half-warp computes r = -1/den (gaussian_noise.cpp:15-18), the
-        // lower one q = (y - m)/den (gaussian_noise.cpp:9-12 / gaussian_noise_3d.cpp:10-13); q is only read by lanes < 16
+        // one division for two quotients: lanes 8-15 compute r = -1/den (gaussian_noise.cpp:15-18), lanes 0-7
+        // q = (y - m)/den (gaussian_noise.cpp:9-12 / gaussian_noise_3d.cpp:10-13)
         double q[DOUT];
-        q[0] = __ddiv_rn(mat ? -1.0 : __dadd_rn(pt.y[0], -pm[0]), den);
-        const double rr = __shfl_sync(0xffffffffu, q[0], 16);
+        {
+            const double t = __ddiv_rn((r & 8) ? -1.0 : __dadd_rn(pt.y[0], -pm[0]), den);
+            q[0] = shfl16(gm, t, 0);
 #pragma unroll
-        for (int c = 1; c < DOUT; c++) q[c] = __ddiv_rn(__dadd_rn(pt.y[c], -pm[c]), den);
+            for (int c = 1; c < DOUT; c++) q[c] = __ddiv_rn(__dadd_rn(pt.y[c], -pm[c]), den);
+            pm[0] = shfl16(gm, t, 8);  // reuse the register: r
+        }
+        const double rr = pm[0];
         double gamma = __dadd_rn(kstar, -pe);                 // :144
         if (gamma < tiny12()) gamma = 0.0;
         if (gamma < eps_tol) {
@@ -253,24 +300,22 @@ __global__ void __launch_bounds__(32, DOUT == 1 ? 32 : 20) sogp_fit_warp_kernel(
             run++;
             const double eta = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn(gamma, rr)));
             const double sh = act ? __dadd_rn(rv, el) : 0.0;
-            if (lane < W_N) sm.sv[lane] = sh;  // zero beyond N: pad columns stay exact zeros below
+            sm.sv[r] = sh;  // zero beyond N: pad columns stay exact zeros below
             if (act) {
 #pragma unroll
                 for (int c = 0; c < DOUT; c++) alpha[c] = __dadd_rn(alpha[c], __dmul_rn(sh, __dmul_rn(q[c], eta)));
             }
-            __syncwarp();
+            __syncwarp(gm);
             const double re = __dmul_rn(rr, eta);
-            if (r < N) {
-                const double si = sm.sv[r];
-                // column pairs (j, j+1): half-warp 0 takes j = 0,4,8,12; half-warp 1 takes j = 2,6,10,14
+            if (act) {
 #pragma unroll
-                for (int p4 = 0; p4 < 4; p4++) {
-                    const int j = 2 * mat + 4 * p4;
+                for (int p8 = 0; p8 < 8; p8++) {
+                    const int j = 2 * p8;
                     if (j < N) {
                         double2 c = *reinterpret_cast<double2*>(Crow + j);
                         const double2 s2v = *reinterpret_cast<const double2*>(sm.sv + j);
-                        c.x = fma(re, __dmul_rn(si, s2v.x), c.x);
-                        if (j + 1 < N) c.y = fma(re, __dmul_rn(si, s2v.y), c.y);
+                        c.x = fma(re, __dmul_rn(sh, s2v.x), c.x);
+                        if (j + 1 < N) c.y = fma(re, __dmul_rn(sh, s2v.y), c.y);
                         *reinterpret_cast<double2*>(Crow + j) = c;
                     }
                 }
@@ -278,150 +323,149 @@ __global__ void __launch_bounds__(32, DOUT == 1 ? 32 : 20) sogp_fit_warp_kernel(
             continue;  // Q and N unchanged: neither deletion loop can fire
         }
         // full update (:164-203)
-        if (lane == 0) {
+        have_next = false;  // the BV set changes
+        if (r == 0) {
             const unsigned long long n2 = (unsigned long long)N * N;
             sm.cnt[1] += run; sm.cnt[5] += (unsigned long long)run * N; sm.cnt[6] += run * n2; sm.cnt[7] += run * n2;
         }
         run = 0;
         if (N + 1 > ldmax) {  // does not fit this bucket: hand the state to the next one
             int pos = 0;
-            if (lane == 0) pos = atomicAdd(a.queue_count, 1);
-            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if (r == 0) pos = atomicAdd(a.queue_count, 1);
+            pos = __shfl_sync(gm, pos, 0, 16);
             double* slot = a.handoff_out + (size_t)pos * slot_doubles(W_N, DOUT);
-            __syncwarp();
-            if (lane == 0) {
+            __syncwarp(gm);
+            if (r == 0) {
                 a.queue[pos] = (int32_t)patch;
                 reinterpret_cast<int*>(slot)[0] = N;
                 reinterpret_cast<int*>(slot)[1] = tt;
                 for (int i = 0; i < NCNT; i++) reinterpret_cast<unsigned long long*>(slot + 2)[i] = sm.cnt[i];
             }
             double* v = slot + 2 + NCNT;
-            if (lane < W_N) {
 #pragma unroll
-                for (int c = 0; c < DOUT; c++) v[c * W_N + lane] = alpha[c];
-                v[DOUT * W_N + lane] = b1; v[(DOUT + 1) * W_N + lane] = b2;
-                reinterpret_cast<int*>(v + (DOUT + 2) * W_N + 2 * W_N * W_N)[lane] = bidx;
-            }
-            for (int e = lane; e < W_N * W_N; e += 32) {
+            for (int c = 0; c < DOUT; c++) v[c * W_N + r] = alpha[c];
+            v[DOUT * W_N + r] = b1; v[(DOUT + 1) * W_N + r] = b2;
+            reinterpret_cast<int*>(v + (DOUT + 2) * W_N + 2 * W_N * W_N)[r] = bidx;
+            for (int e = r; e < W_N * W_N; e += 16) {
                 const int j = e / W_N, i = e - j * W_N;
                 v[(DOUT + 2) * W_N + e] = C[i * W_LD + j];
                 v[(DOUT + 2) * W_N + W_N * W_N + e] = Q[i * W_LD + j];
             }
             return;
         }
-        if (lane == 0) {
+        if (r == 0) {
             sm.cnt[2]++; sm.cnt[5] += N; sm.cnt[6] += (unsigned long long)N * N; sm.cnt[8] += (unsigned long long)(N + 1) * (N + 1);
         }
         if (act) {
-            sm.sv[lane] = rv;
-            sm.ev[lane] = el;
+            sm.sv[r] = rv;
+            sm.ev[r] = el;
 #pragma unroll
             for (int c = 0; c < DOUT; c++) alpha[c] = __dadd_rn(alpha[c], __dmul_rn(q[c], rv));
         }
-        if (lane == N) {
+        if (r == N) {
             sm.sv[N] = 1.0;
             sm.ev[N] = -1.0;
 #pragma unroll
             for (int c = 0; c < DOUT; c++) alpha[c] = __dadd_rn(0.0, __dmul_rn(q[c], 1.0));
             b1 = x1; b2 = x2; bidx = orig;
         }
-        __syncwarp();
+        __syncwarp(gm);
         {
             const double ig = __ddiv_rn(1.0, gamma);
             const int N1 = N + 1;
             if (r < N1) {
                 const double si = sm.sv[r], ei = sm.ev[r];
-                for (int j = mat; j < N1; j += 2) {
+                for (int j = 0; j < N1; j++) {
                     Crow[j] = fma(rr, __dmul_rn(si, sm.sv[j]), Crow[j]);
                     Qrow[j] = fma(ig, __dmul_rn(ei, sm.ev[j]), Qrow[j]);
                 }
             }
             N = N1;
         }
-        __syncwarp();
+        __syncwarp(gm);
         // capacity deletions (:206-223) then geometric deletions (:226-242)
         double minscore = 0.0;
         for (int phase = 0; phase < 2; phase++) {
             for (;;) {
                 if (phase == 0 ? !(N > cap) : !(minscore < geo9() && N > 1)) break;
                 double sc = 0.0;
-                if (lane < N) {
-                    const double qii = Q[lane * W_LD + lane];
+                if (r < N) {
+                    const double qii = Q[r * W_LD + r];
                     double num = __dmul_rn(alpha[0], alpha[0]);
                     if (DOUT == 3) num = __dadd_rn(num, __dadd_rn(__dmul_rn(alpha[DOUT > 1 ? 1 : 0], alpha[DOUT > 1 ? 1 : 0]), __dmul_rn(alpha[DOUT > 2 ? 2 : 0], alpha[DOUT > 2 ? 2 : 0])));
-                    sc = (phase == 0) ? __ddiv_rn(num, __dadd_rn(qii, C[lane * W_LD + lane])) : __ddiv_rn(1.0, qii);
+                    sc = (phase == 0) ? __ddiv_rn(num, __dadd_rn(qii, C[r * W_LD + r])) : __ddiv_rn(1.0, qii);
                 }
                 if (phase == 1) {
                     // exact shortcut: the scan deletes iff score_0 is not NaN and some score is < 1e-9f
-                    const bool hit = __any_sync(0xffffffffu, lane < N && sc < geo9());
-                    const bool nan0 = __any_sync(0xffffffffu, lane == 0 && sc != sc);
+                    const bool hit = __any_sync(gm, r < N && sc < geo9());
+                    const bool nan0 = __any_sync(gm, r == 0 && sc != sc);
                     if (!hit || nan0) { minscore = geo9(); break; }
                 }
                 double best;
-                const int loc = warp_first_min(sc, lane < N ? lane : 0x7fffffff, &best);
+                const int loc = half_first_min(gm, sc, r < N ? r : 0x7fffffff, &best);
                 if (phase == 1) minscore = best;
                 // ---- delete_bv(loc), :252-295 ----
                 const int L = N - 1, M = N - 1;
-                if (lane == 0) { sm.cnt[9] += (unsigned long long)M * M; sm.cnt[phase == 0 ? 3 : 4]++; }
+                if (r == 0) { sm.cnt[9] += (unsigned long long)M * M; sm.cnt[phase == 0 ? 3 : 4]++; }
                 double csi = 0, qsi = 0, repc = 0, repq = 0;
-                const int src = (lane == loc) ? L : lane;
-                if (lane < N) {
+                const int src = (r == loc) ? L : r;
+                if (r < N) {
                     csi = C[loc * W_LD + src]; qsi = Q[loc * W_LD + src];
                     repc = C[L * W_LD + src]; repq = Q[L * W_LD + src];
                 }
                 const double cstar = C[loc * W_LD + loc], qstar = Q[loc * W_LD + loc];
                 double astar[DOUT], aL[DOUT];
 #pragma unroll
-                for (int c = 0; c < DOUT; c++) { astar[c] = __shfl_sync(0xffffffffu, alpha[c], loc); aL[c] = __shfl_sync(0xffffffffu, alpha[c], L); }
-                const double b1L = __shfl_sync(0xffffffffu, b1, L), b2L = __shfl_sync(0xffffffffu, b2, L);
-                const int idL = __shfl_sync(0xffffffffu, bidx, L);
-                __syncwarp();
+                for (int c = 0; c < DOUT; c++) { astar[c] = shfl16(gm, alpha[c], loc); aL[c] = shfl16(gm, alpha[c], L); }
+                const double b1L = shfl16(gm, b1, L), b2L = shfl16(gm, b2, L);
+                const int idL = __shfl_sync(gm, bidx, L, 16);
+                __syncwarp(gm);
                 const double qcs = __dadd_rn(qstar, cstar);
                 const double coef = (DOUT == 1) ? __ddiv_rn(astar[0], qcs) : 0.0;
                 const double iq = __ddiv_rn(1.0, qstar), iqc = __ddiv_rn(1.0, qcs);
-                if (lane < N) {
-                    if (lane < M) {
+                if (r < N) {
+                    if (r < M) {
                         if (loc != L) {
-                            C[loc * W_LD + lane] = repc; C[lane * W_LD + loc] = repc;
-                            Q[loc * W_LD + lane] = repq; Q[lane * W_LD + loc] = repq;
-                            if (lane == loc) { b1 = b1L; b2 = b2L; bidx = idL; }
+                            C[loc * W_LD + r] = repc; C[r * W_LD + loc] = repc;
+                            Q[loc * W_LD + r] = repq; Q[r * W_LD + loc] = repq;
+                            if (r == loc) { b1 = b1L; b2 = b2L; bidx = idL; }
                         }
                         const double qci = __dadd_rn(qsi, csi);
 #pragma unroll
                         for (int c = 0; c < DOUT; c++) {
-                            const double ai = (lane == loc) ? aL[c] : alpha[c];
+                            const double ai = (r == loc) ? aL[c] : alpha[c];
                             alpha[c] = (DOUT == 1) ? __dadd_rn(ai, -__dmul_rn(coef, qci))
                                                    : __dadd_rn(ai, -__dmul_rn(astar[c], __dmul_rn(qcs, qci)));
                         }
-                        sm.sv[lane] = qsi;   // Qstar
-                        sm.ev[lane] = qci;   // Qstar + Cstar
+                        sm.sv[r] = qsi;   // Qstar
+                        sm.ev[r] = qci;   // Qstar + Cstar
                     }
-                    C[L * W_LD + lane] = 0.0; C[lane * W_LD + L] = 0.0;
-                    Q[L * W_LD + lane] = 0.0; Q[lane * W_LD + L] = 0.0;
-                    if (lane == L) {
+                    C[L * W_LD + r] = 0.0; C[r * W_LD + L] = 0.0;
+                    Q[L * W_LD + r] = 0.0; Q[r * W_LD + L] = 0.0;
+                    if (r == L) {
 #pragma unroll
                         for (int c = 0; c < DOUT; c++) alpha[c] = 0.0;
                         b1 = 0.0; b2 = 0.0; bidx = -1;
                     }
                 }
-                __syncwarp();
+                __syncwarp(gm);
                 if (r < M) {
                     const double qi = sm.sv[r], ci = sm.ev[r];
-                    for (int j = mat; j < M; j += 2) {
+                    for (int j = 0; j < M; j++) {
                         const double u = __dmul_rn(qi, sm.sv[j]);
                         const double v = __dmul_rn(ci, sm.ev[j]);
-                        const double w = fma(u, iq, -__dmul_rn(v, iqc));
-                        Crow[j] = __dadd_rn(Crow[j], w);
+                        const double wv = fma(u, iq, -__dmul_rn(v, iqc));
+                        Crow[j] = __dadd_rn(Crow[j], wv);
                         Qrow[j] = fma(-u, iq, Qrow[j]);
                     }
                 }
                 N = M;
-                __syncwarp();
+                __syncwarp(gm);
             }
         }
     }
-    __syncwarp();
-    if (lane == 0) {
+    __syncwarp(gm);
+    if (r == 0) {
         const unsigned long long n2 = (unsigned long long)N * N;
         sm.cnt[1] += run; sm.cnt[5] += (unsigned long long)run * N; sm.cnt[6] += run * n2; sm.cnt[7] += run * n2;
         a.nbv[op] = N;
@@ -433,16 +477,16 @@ __global__ void __launch_bounds__(32, DOUT == 1 ? 32 : 20) sogp_fit_warp_kernel(
             if (sm.cnt[i]) atomicAdd(st + 1 + i, sm.cnt[i]);
     }
     const int64_t ob = op * cap;
-    if (lane < N) {
+    if (r < N) {
 #pragma unroll
-        for (int c = 0; c < DOUT; c++) a.o_alpha[c][ob + lane] = alpha[c];
-        a.o_b1[ob + lane] = b1;
-        a.o_b2[ob + lane] = b2;
-        a.o_idx[ob + lane] = bidx;
+        for (int c = 0; c < DOUT; c++) a.o_alpha[c][ob + r] = alpha[c];
+        a.o_b1[ob + r] = b1;
+        a.o_b2[ob + r] = b2;
+        a.o_idx[ob + r] = bidx;
     }
     if (a.dumpC) {
         const int64_t od = op * (int64_t)cap * cap;
-        for (int e = lane; e < N * N; e += 32) {
+        for (int e = r; e < N * N; e += 16) {
             const int i = e / N, j = e - i * N;
             a.dumpC[od + e] = C[i * W_LD + j];
             a.dumpQ[od + e] = Q[i * W_LD + j];
@@ -1255,7 +1299,7 @@ cudaError_t launch_sogp_fit(int bucket, const SogpArgs& a, cudaStream_t st) {
     if (a.dout == 3) {
         switch (bucket) {
             case 0:
-                sogp_fit_warp_kernel<3><<<a.n_work, 32, 0, st>>>(a);
+                sogp_fit_half_kernel<3><<<(a.n_work + 1) / 2, 32, 0, st>>>(a);
                 return cudaGetLastError();
             case 2: return launch_cta_bucket<64, 64, 256, 16, false, 3>(a, st);
             default: return launch_cta_bucket<202, 256, 1024, 64, true, 3>(a, st);
@@ -1263,7 +1307,7 @@ cudaError_t launch_sogp_fit(int bucket, const SogpArgs& a, cudaStream_t st) {
     }
     switch (bucket) {
         case 0:
-            sogp_fit_warp_kernel<1><<<a.n_work, 32, 0, st>>>(a);
+            sogp_fit_half_kernel<1><<<(a.n_work + 1) / 2, 32, 0, st>>>(a);
             return cudaGetLastError();
         case 1:
             sogp_fit_pair_kernel<<<a.n_work, 64, 0, st>>>(a);

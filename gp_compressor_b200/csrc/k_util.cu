@@ -327,6 +327,46 @@ void launch_flag_nonempty(const int32_t* nbv, const int32_t* rgb_nbv, int64_t n,
     g_launches++;
 }
 
+// ---- patch ids of [lo, lo + n) ordered by decreasing point count (counting sort over min(count, 1023)) ----------
+// The bucket-0 SOGP kernel packs two patches per warp: neighbours in this order have (almost) equal lengths, and the
+// longest patches start first.  The order within one count is arbitrary; results do not depend on it.
+__global__ void __launch_bounds__(256) size_hist_kernel(const int64_t* __restrict__ off, int64_t lo, int64_t n, int32_t* __restrict__ hist) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t c = off[lo + i + 1] - off[lo + i];
+    atomicAdd(hist + (1023 - (int)(c < 1023 ? c : 1023)), 1);
+}
+__global__ void __launch_bounds__(1024) size_scan_kernel(int32_t* __restrict__ hist) {
+    __shared__ int32_t s[1024];
+    const int t = threadIdx.x;
+    const int32_t v = hist[t];
+    s[t] = v;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const int32_t u = (t >= d) ? s[t - d] : 0;
+        __syncthreads();
+        s[t] += u;
+        __syncthreads();
+    }
+    hist[t] = s[t] - v;  // exclusive: the bin's cursor
+}
+__global__ void __launch_bounds__(256) size_scatter_kernel(const int64_t* __restrict__ off, int64_t lo, int64_t n, int32_t* __restrict__ cursor,
+                                                           int32_t* __restrict__ ids) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t c = off[lo + i + 1] - off[lo + i];
+    const int pos = atomicAdd(cursor + (1023 - (int)(c < 1023 ? c : 1023)), 1);
+    ids[pos] = (int32_t)(lo + i);
+}
+void launch_size_order(const int64_t* off, int64_t lo, int64_t n, int32_t* hist1024, int32_t* ids, cudaStream_t s) {
+    if (n <= 0) return;
+    cudaMemsetAsync(hist1024, 0, 1024 * sizeof(int32_t), s);
+    size_hist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(off, lo, n, hist1024);
+    size_scan_kernel<<<1, 1024, 0, s>>>(hist1024);
+    size_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(off, lo, n, hist1024, ids);
+    g_launches += 3;
+}
+
 // nbv (int32) -> int64 for the scan
 __global__ void widen_i32_kernel(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
