@@ -187,11 +187,13 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
             CK(h->rnd.reserve(nd * sizeof(uint32_t)));
             launch_rand_stream(h->rand_offset + draws_lo, nd, h->rnd.as<uint32_t>(), st);
         }
-        launch_shuffle(h->off.as<int64_t>() + lo, PL, h->roff.as<int64_t>() + lo, h->rnd.as<uint32_t>(), c.shuffle,
-                       h->perm.as<int32_t>(), h->patch_of.as<int32_t>(), h->s_begin, h->s_count, max_np, 0, st);
-        launch_gather_stream(h->off.as<int64_t>() + lo, h->patch_of.as<int32_t>(), h->perm.as<int32_t>(),
-                             h->x1.as<double>(), h->x2.as<double>(), h->y.as<double>(), h->s_begin, h->s_count,
-                             h->fx1.as<double>(), h->fx2.as<double>(), h->fy.as<double>(), st);
+        ShuffleGatherArgs sg;
+        sg.off = h->off.as<int64_t>() + lo; sg.n_patches = PL; sg.roff = h->roff.as<int64_t>() + lo; sg.rnd = h->rnd.as<uint32_t>();
+        sg.do_shuffle = c.shuffle; sg.is_rgb = 0; sg.first_patch = lo; sg.s_begin = h->s_begin; sg.s_count = h->s_count;
+        sg.x1 = h->x1.as<double>(); sg.x2 = h->x2.as<double>(); sg.y = h->y.as<double>(); sg.rgb = nullptr; sg.rgbmean = nullptr;
+        sg.perm = h->perm.as<int32_t>();
+        sg.fx1 = h->fx1.as<double>(); sg.fx2 = h->fx2.as<double>(); sg.f0 = h->fy.as<double>(); sg.f1 = sg.f2 = nullptr;
+        launch_shuffle_gather(sg, max_np, h->patch_of.as<int32_t>(), st);
     }
     h->rand_offset += draws_all;
     size_t t1 = tm.mark();
@@ -262,13 +264,16 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
         CK(cudaMemsetAsync(h->kstats_rgb.p, 0, 16 * sizeof(unsigned long long), st));
         CK(cudaMemsetAsync(h->qcount.p, 0, 8 * sizeof(int32_t), st));
         if (PL > 0 && h->s_count > 0) {
-            launch_shuffle(h->off.as<int64_t>() + lo, PL, h->roff.as<int64_t>() + lo, h->rnd.as<uint32_t>(), 1, h->perm_rgb.as<int32_t>(),
-                           h->patch_of.as<int32_t>(), h->s_begin, h->s_count, max_np, 1, st);
             // the height fit is done with fx1 / fx2: reuse them for the field GP's order
-            launch_gather_rgb_stream(h->off.as<int64_t>() + lo, h->patch_of.as<int32_t>(), h->perm_rgb.as<int32_t>(), h->x1.as<double>(),
-                                     h->x2.as<double>(), h->rgb.as<uint32_t>(), h->rgbmean.as<double>(), lo, h->s_begin, h->s_count,
-                                     h->fx1.as<double>(), h->fx2.as<double>(), h->fcr.as<double>(), h->fcg.as<double>(),
-                                     h->fcb.as<double>(), st);
+            ShuffleGatherArgs sg;
+            sg.off = h->off.as<int64_t>() + lo; sg.n_patches = PL; sg.roff = h->roff.as<int64_t>() + lo; sg.rnd = h->rnd.as<uint32_t>();
+            sg.do_shuffle = c.shuffle && c.rgb_rand; sg.is_rgb = 1; sg.first_patch = lo; sg.s_begin = h->s_begin; sg.s_count = h->s_count;
+            sg.x1 = h->x1.as<double>(); sg.x2 = h->x2.as<double>(); sg.y = nullptr; sg.rgb = h->rgb.as<uint32_t>();
+            sg.rgbmean = h->rgbmean.as<double>();
+            sg.perm = h->perm_rgb.as<int32_t>();
+            sg.fx1 = h->fx1.as<double>(); sg.fx2 = h->fx2.as<double>();
+            sg.f0 = h->fcr.as<double>(); sg.f1 = h->fcg.as<double>(); sg.f2 = h->fcb.as<double>();
+            launch_shuffle_gather(sg, max_np, h->patch_of.as<int32_t>(), st);
         }
         SogpArgs r = a;
         r.fy[0] = h->fcr.as<double>(); r.fy[1] = h->fcg.as<double>(); r.fy[2] = h->fcb.as<double>();
@@ -414,11 +419,12 @@ int run_binning(gpc_handle* h, StageTimer& tm) {
     LatticeState Lh = L0;
     int64_t start = 0;
     for (;;) {
-        launch_lattice_step(cloud, n, n - start, h->lat_state.as<LatticeState>(), st);
+        // six growth events per round trip; once nothing violates the box the remaining steps are no-ops
+        for (int k = 0; k < 6; k++) launch_lattice_step(cloud, n, n - start, h->lat_state.as<LatticeState>(), st);
         CK(cudaMemcpyAsync(&Lh, h->lat_state.p, sizeof(Lh), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        if (!Lh.found) break;
         if (Lh.lat.depth > 21) return fail(h, GPC_ERR_OVERFLOW, "octree deeper than 21 levels: res too small for the cloud extent");
+        if (!Lh.found) break;
         start = Lh.start;
     }
     struct { unsigned depth; bool defined; double mn[3]; } L;

@@ -101,9 +101,22 @@ void launch_size_order(const int64_t* off, int64_t lo, int64_t n, int32_t* hist1
 void launch_fit_plan(const int64_t* off, int64_t n_patches, int mult, int rank, int count, int64_t* draws, int64_t* roff, void* scan_tmp,
                      int64_t* plan9, cudaStream_t s);
 // perm (patch-local) for every patch; rnd holds the stream starting at the handle's offset
-void launch_shuffle(const int64_t* off, int64_t n_patches, const int64_t* roff, const uint32_t* rnd,
-                    int do_shuffle, int32_t* perm, int32_t* patch_of, int64_t s_begin, int64_t s_count,
-                    int64_t max_patch_points, int second, cudaStream_t s);
+struct ShuffleGatherArgs {
+    const int64_t* off;          // patch offsets of this shard's first patch onwards (n_patches + 1)
+    int64_t n_patches;
+    const int64_t* roff;         // rand-draw offsets, same base
+    const uint32_t* rnd;         // the shard's window of the rand() stream
+    int do_shuffle;
+    int is_rgb;                  // 0: height stream (f0 = y); 1: the field GP's second shuffle and colour streams (f0..f2)
+    int64_t first_patch;         // absolute index of off[0]'s patch (rgbmean lookup)
+    int64_t s_begin, s_count;    // the shard's window of the claimed-point stream
+    const double *x1, *x2, *y;   // grouped points
+    const uint32_t* rgb;         // b,g,r,a bytes per grouped point
+    const double* rgbmean;       // 3 per patch (absolute patch index)
+    int32_t* perm;               // out: local index of the point added at each stream position
+    double *fx1, *fx2, *f0, *f1, *f2;
+};
+void launch_shuffle_gather(const ShuffleGatherArgs& a, int64_t max_patch_points, int32_t* patch_of, cudaStream_t s);
 void launch_gather_rgb_stream(const int64_t* off, const int32_t* patch_of, const int32_t* perm, const double* x1, const double* x2,
                               const uint32_t* rgb, const double* rgbmean, int64_t first_patch, int64_t s_begin, int64_t s_count,
                               double* fx1, double* fx2, double* fr, double* fg, double* fb, cudaStream_t s);

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) first_violation_kernel(const uint8_t* __r
     const int64_t tile = (int64_t)blockIdx.x * 4096;
     if (threadIdx.x == 0) {
         sbest = ~0ull;
-        skip = (start + tile >= n) || (unsigned long long)(start + tile) >= *(volatile unsigned long long*)&st->best;  // an earlier hit exists
+        skip = (start >= n - tile) || (unsigned long long)(start + tile) >= *(volatile unsigned long long*)&st->best;  // an earlier hit exists
     }
     __syncthreads();
     if (skip) return;
@@ -85,9 +85,16 @@ __global__ void __launch_bounds__(256) first_violation_kernel(const uint8_t* __r
 }
 
 __global__ void lattice_adopt_kernel(const uint8_t* __restrict__ cloud, LatticeState* __restrict__ st) {
+    if (st->defined && st->lat.depth > 21) {  // the host rejects this cloud; do not grow further
+        st->start = 0x7fffffffffffffffLL;
+        return;
+    }
     const unsigned long long b = st->best;
     st->found = (b != ~0ull) ? 1 : 0;
-    if (b == ~0ull) return;
+    if (b == ~0ull) {  // every remaining point lies inside the box: later searches of the same batch exit at once
+        st->start = 0x7fffffffffffffffLL;
+        return;
+    }
     const float4 pt = *reinterpret_cast<const float4*>(cloud + (int64_t)b * GPC_POINT_BYTES);
     const float p[3] = {pt.x, pt.y, pt.z};
     LatticeDev& L = st->lat;

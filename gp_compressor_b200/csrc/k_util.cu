@@ -233,24 +233,6 @@ __global__ void shuffle_kernel(const int64_t* __restrict__ off, int64_t n_patche
     }
 }
 
-void launch_shuffle(const int64_t* off, int64_t n_patches, const int64_t* roff, const uint32_t* rnd, int do_shuffle,
-                    int32_t* perm, int32_t* patch_of, int64_t s_begin, int64_t s_count, int64_t max_patch_points,
-                    int second, cudaStream_t s) {
-    if (s_count <= 0 || n_patches <= 0) return;
-    if (!second) {  // the second (RGB) shuffle reuses patch_of; its kernels initialise perm themselves
-        patch_of_kernel<<<(unsigned)((s_count + 255) / 256), 256, 0, s>>>(off, n_patches, s_begin, s_count, patch_of, perm);
-        g_launches++;
-    }
-    if (do_shuffle) {
-        shuffle_warp_kernel<<<(unsigned)n_patches, 32, 0, s>>>(off, n_patches, roff, rnd, second, perm);
-        g_launches++;
-        if (max_patch_points > SHUF_SMEM_MAX) {
-            shuffle_kernel<<<(unsigned)((n_patches + 127) / 128), 128, 0, s>>>(off, n_patches, roff, rnd, second, perm);
-            g_launches++;
-        }
-    }
-}
-
 // fit stream in add order: element t of patch p is point perm[off[p] + t]
 __global__ void gather_stream_kernel(const int64_t* __restrict__ off, const int32_t* __restrict__ patch_of,
                                      const int32_t* __restrict__ perm, const double* __restrict__ x1,
@@ -325,6 +307,82 @@ void launch_flag_nonempty(const int32_t* nbv, const int32_t* rgb_nbv, int64_t n,
     if (n <= 0) return;
     flag_nonempty_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(nbv, rgb_nbv, n, flags, maxes);
     g_launches++;
+}
+
+// Fused shuffle + gather for patches of up to SHUF_SMEM_MAX points (the common case): the permutation never leaves
+// shared memory before the fit streams are written in add order.  RGB: the field GP's own shuffle (the draws after the
+// patch's first n - 1) and its colour stream centred on the patch mean (p.second -= c_mn, gp_compressor.cpp:105).
+template <bool RGB>
+__global__ void __launch_bounds__(32) shuffle_gather_warp_kernel(ShuffleGatherArgs a) {
+    __shared__ int ind[SHUF_SMEM_MAX];
+    __shared__ int rr[SHUF_SMEM_MAX];
+    const int64_t p = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int64_t o = a.off[p];
+    const int n = (int)(a.off[p + 1] - o);
+    if (n == 0) return;
+    if (a.do_shuffle && n >= 2) {
+        const uint32_t* r = a.rnd + (a.roff[p] - a.roff[0]) + (RGB ? (n - 1) : 0);
+        for (int i = lane; i < n; i += 32) {
+            ind[i] = i;
+            if (i > 0) rr[i] = (int)(r[n - 1 - i] % (uint32_t)i);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            for (int i = n - 1; i > 0; --i) {
+                const int j = rr[i];
+                const int x = ind[i], y = ind[j];
+                ind[i] = y;
+                ind[j] = x;
+            }
+        }
+        __syncwarp();
+    } else {
+        for (int i = lane; i < n; i += 32) ind[i] = i;
+        __syncwarp();
+    }
+    double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+    if (RGB) { m0 = a.rgbmean[3 * (a.first_patch + p)]; m1 = a.rgbmean[3 * (a.first_patch + p) + 1]; m2 = a.rgbmean[3 * (a.first_patch + p) + 2]; }
+    for (int i = lane; i < n; i += 32) {
+        const int k = ind[i];
+        const int64_t src = o + k, dst = o + i;
+        a.perm[dst] = k;
+        a.fx1[dst] = a.x1[src];
+        a.fx2[dst] = a.x2[src];
+        if (RGB) {
+            const uint32_t c = a.rgb[src];
+            a.f0[dst] = __dadd_rn((double)((c >> 16) & 255u), -m0);
+            a.f1[dst] = __dadd_rn((double)((c >> 8) & 255u), -m1);
+            a.f2[dst] = __dadd_rn((double)(c & 255u), -m2);
+        } else {
+            a.f0[dst] = a.y[src];
+        }
+    }
+}
+
+// Shuffle (sparse_gp::shuffle, sparse_gp.hpp:42-56) and fit-stream gather of one shard.  Patches of more than
+// SHUF_SMEM_MAX points (rare) take the separate global-memory kernels.
+void launch_shuffle_gather(const ShuffleGatherArgs& a, int64_t max_patch_points, int32_t* patch_of, cudaStream_t s) {
+    if (a.s_count <= 0 || a.n_patches <= 0) return;
+    if (max_patch_points <= SHUF_SMEM_MAX) {
+        if (a.is_rgb) shuffle_gather_warp_kernel<true><<<(unsigned)a.n_patches, 32, 0, s>>>(a);
+        else shuffle_gather_warp_kernel<false><<<(unsigned)a.n_patches, 32, 0, s>>>(a);
+        g_launches++;
+        return;
+    }
+    const int second = a.is_rgb ? 1 : 0;
+    patch_of_kernel<<<(unsigned)((a.s_count + 255) / 256), 256, 0, s>>>(a.off, a.n_patches, a.s_begin, a.s_count, patch_of, a.perm);
+    g_launches++;
+    if (a.do_shuffle) {
+        shuffle_warp_kernel<<<(unsigned)a.n_patches, 32, 0, s>>>(a.off, a.n_patches, a.roff, a.rnd, second, a.perm);
+        shuffle_kernel<<<(unsigned)((a.n_patches + 127) / 128), 128, 0, s>>>(a.off, a.n_patches, a.roff, a.rnd, second, a.perm);
+        g_launches += 2;
+    }
+    if (a.is_rgb)
+        launch_gather_rgb_stream(a.off, patch_of, a.perm, a.x1, a.x2, a.rgb, a.rgbmean, a.first_patch, a.s_begin, a.s_count, a.fx1, a.fx2,
+                                 a.f0, a.f1, a.f2, s);
+    else
+        launch_gather_stream(a.off, patch_of, a.perm, a.x1, a.x2, a.y, a.s_begin, a.s_count, a.fx1, a.fx2, a.f0, s);
 }
 
 // ---- patch ids of [lo, lo + n) ordered by decreasing point count (counting sort over min(count, 1023)) ----------
