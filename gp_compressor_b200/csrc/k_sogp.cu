@@ -985,6 +985,94 @@ __device__ __forceinline__ void delete_bv(const Smem<LD, DOUT>& s, int& N, int l
     __syncthreads();
 }
 
+// delete_bv for any thread count (used by the rare paths of the fused kernel): the matrix update strides over elements.
+// The three divisions are done by warp 0 only and published through scal[4..6].
+template <int LD, int NT, int DOUT>
+__device__ __forceinline__ void delete_bv_any(const Smem<LD, DOUT>& s, int& N, int loc, int t) {
+    const int L = N - 1, M = N - 1;
+    const int lane_ = t & 31, w_ = t >> 5;
+    double* const C = s.C();
+    double* const Q = s.Q();
+    double csi = 0, qsi = 0, repc = 0, repq = 0, nb1 = 0, nb2 = 0;
+    double ai[DOUT];
+#pragma unroll
+    for (int c = 0; c < DOUT; c++) ai[c] = 0.0;
+    int nidx = -1;
+    if (t < N) {
+        const int src = (t == loc) ? L : t;  // Cs(loc) = Cs(L), Crep(loc) = Crep(L), alpha(loc) = alpha(L)
+        csi = C[loc * LD + src];
+        qsi = Q[loc * LD + src];
+        repc = C[L * LD + src];
+        repq = Q[L * LD + src];
+#pragma unroll
+        for (int c = 0; c < DOUT; c++) ai[c] = s.alpha(c)[src];
+        if (t == loc) { nb1 = s.b1()[L]; nb2 = s.b2()[L]; nidx = s.bidx()[L]; }
+    }
+    // scal[8] = 1/q*, [9] = 1/(q*+c*), [10] = q*+c*, [11..] = alpha* / (q*+c*) (sparse_gp) or alpha* (sparse_gp_field)
+    double coef0[DOUT], iq0 = 0.0, iqc0 = 0.0, qcs0 = 0.0;
+#pragma unroll
+    for (int c = 0; c < DOUT; c++) coef0[c] = 0.0;
+    if (w_ == 0) {
+        const double cstar = C[loc * LD + loc], qstar = Q[loc * LD + loc];
+        qcs0 = __dadd_rn(qstar, cstar);
+#pragma unroll
+        for (int c = 0; c < DOUT; c++) {
+            const double astar = s.alpha(c)[loc];
+            coef0[c] = (DOUT == 1) ? __ddiv_rn(astar, qcs0) : astar;
+        }
+        iq0 = __ddiv_rn(1.0, qstar);
+        iqc0 = __ddiv_rn(1.0, qcs0);
+    }
+    __syncthreads();  // every read of the old state is done
+    if (t == 0) {
+        s.scal()[8] = iq0; s.scal()[9] = iqc0; s.scal()[10] = qcs0;
+#pragma unroll
+        for (int c = 0; c < DOUT; c++) s.scal()[11 + c] = coef0[c];
+    }
+    double qci = 0.0;
+    if (t < N) {
+        if (t < M) {
+            if (loc != L) {
+                C[loc * LD + t] = repc; C[t * LD + loc] = repc;
+                Q[loc * LD + t] = repq; Q[t * LD + loc] = repq;
+                if (t == loc) { s.b1()[loc] = nb1; s.b2()[loc] = nb2; s.bidx()[loc] = nidx; }
+            }
+            qci = __dadd_rn(qsi, csi);
+            s.qsv()[t] = qsi;
+            s.qcv()[t] = qci;
+        }
+        C[L * LD + t] = 0.0; C[t * LD + L] = 0.0;
+        Q[L * LD + t] = 0.0; Q[t * LD + L] = 0.0;
+        if (t == L) {
+#pragma unroll
+            for (int c = 0; c < DOUT; c++) s.alpha(c)[L] = 0.0;
+            s.b1()[L] = 0.0; s.b2()[L] = 0.0; s.bidx()[L] = -1;
+        }
+    }
+    __syncthreads();
+    const double iq = s.scal()[8], iqc = s.scal()[9];
+    if (t < M) {
+        const double qcs = s.scal()[10];
+#pragma unroll
+        for (int c = 0; c < DOUT; c++) {
+            const double cf = s.scal()[11 + c];
+            s.alpha(c)[t] = (DOUT == 1) ? __dadd_rn(ai[c], -__dmul_rn(cf, qci))                       // sparse_gp.hpp:285
+                                        : __dadd_rn(ai[c], -__dmul_rn(cf, __dmul_rn(qcs, qci)));      // sparse_gp_field.hpp:250-253
+        }
+    }
+    for (int e = t; e < M * M; e += NT) {
+        const int j = e / M, irow = e - j * M;
+        const int idx = j * LD + irow;
+        const double u = __dmul_rn(s.qsv()[irow], s.qsv()[j]);
+        const double v = __dmul_rn(s.qcv()[irow], s.qcv()[j]);
+        const double w = fma(u, iq, -__dmul_rn(v, iqc));
+        C[idx] = __dadd_rn(C[idx], w);
+        Q[idx] = fma(-u, iq, Q[idx]);
+    }
+    N = M;
+    __syncthreads();
+}
+
 template <int LD, int RB, int NT, int LD_IN, bool SPILL, int DOUT>
 __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
     extern __shared__ double smem_dyn[];
@@ -1260,6 +1348,451 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
     }
 }
 
+// =====================================================================================
+// Buckets 2-3, fused (height GP, state in shared memory).  The update of point t and the two matvecs C k, Q k of
+// point t + 1 share ONE pass over the matrices: every element is read once, brought up to date, written once and
+// multiplied into the next point's row sums while it is still in a register.  A full update that is followed by a
+// capacity deletion never materialises the (N+1) x (N+1) matrices: the deletion index is decided first from the
+// O(N) quantities (updated alpha and updated diagonals), then each element takes the rank-1 update and the three
+// outer products of delete_bv in one go.  Per capacity-bound point this moves 32 N^2 bytes of shared memory instead
+// of 80 N^2 and needs 6 block barriers instead of 11.  Every element still receives exactly the operations, in the
+// order, of sparse_gp::add / delete_bv as every other bucket performs them, so results are bit-identical.
+//
+// A warp covers 16 rows x 4 column classes: lane = 8 * jq + rp owns rows (16 w + 2 rp, + 1) as 128-bit pairs and the
+// columns j = jq (mod 4), i.e. the canonical row4 partial a_jq of its rows; two shuffles give (a0 + a1) + (a2 + a3).
+// Rare events (geometric deletions, the hand-off to a larger bucket) first bring the matrices up to date with a
+// pass without matvec and then run the step-by-step code of the generic kernel.
+// =====================================================================================
+enum { OP_NONE = 0, OP_SPARSE = 1, OP_FULL = 2, OP_FULL_DEL = 3 };
+
+template <int LD>
+struct FusedVecs {   // beyond Smem<LD, 1>: k of the next point, permuted update vectors
+    double* base;
+    __device__ __forceinline__ double* kn() const { return base; }
+    __device__ __forceinline__ double* svp() const { return base + LD; }
+    __device__ __forceinline__ double* evp() const { return base + 2 * LD; }
+    static constexpr int kDoubles = 3 * LD;
+};
+
+// first strict minimum of scv[0..n) (sparse_gp.hpp:210-217); every warp computes it redundantly
+__device__ __forceinline__ int scan_first_min(const double* scv, int n, int lane) {
+    double best = 0.0;
+    int bi = 0x7fffffff;
+    bool nan0 = false;
+    for (int i = lane; i < n; i += 32) {
+        const double v = scv[i];
+        if (v != v) {
+            if (i == 0) nan0 = true;
+            continue;
+        }
+        if (bi == 0x7fffffff || v < best) { best = v; bi = i; }
+    }
+    if (nan0) { best = __longlong_as_double(0x7ff8000000000000LL); bi = 0; }
+    double ms;
+    return warp_first_min(best, bi, &ms);
+}
+
+struct FusedOp {
+    double c0, c1, iq, iqc;   // SPARSE: c0 = r eta.  FULL / FULL_DEL: c0 = r, c1 = 1/gamma.  FULL_DEL: 1/q*, 1/(q*+c*)
+    int loc;
+};
+
+// One pass over the leading nf x nf blocks of C and Q: apply OP, optionally accumulate the row sums with kn.
+// sv / ev: update vectors indexed by the FINAL position (already permuted for FULL_DEL); qs / qc: the deletion's
+// Qstar and Qstar + Cstar.  Writes ck / ek (the row sums) when do_mv.
+template <int LD, int OP>
+__device__ __forceinline__ void fused_pass(double* __restrict__ C, double* __restrict__ Q, int nf, const FusedOp op,
+                                           const double* __restrict__ sv, const double* __restrict__ ev,
+                                           const double* __restrict__ qs, const double* __restrict__ qc,
+                                           const double* __restrict__ kn, bool do_mv, double* __restrict__ ck,
+                                           double* __restrict__ ek, int t) {
+    const int lane = t & 31, w = t >> 5;
+    const int rp = lane & 7, jq = lane >> 3;
+    const int r0 = 16 * w + 2 * rp;
+    double ac0 = 0.0, ac1 = 0.0, aq0 = 0.0, aq1 = 0.0;
+    if (r0 < nf) {
+        const bool two = r0 + 1 < nf;
+        double s0 = 0, s1 = 0, e0 = 0, e1 = 0, qs0 = 0, qs1 = 0, qc0 = 0, qc1 = 0;
+        if (OP != OP_NONE) { s0 = sv[r0]; s1 = two ? sv[r0 + 1] : 0.0; }
+        if (OP == OP_FULL || OP == OP_FULL_DEL) { e0 = ev[r0]; e1 = two ? ev[r0 + 1] : 0.0; }
+        if (OP == OP_FULL_DEL) { qs0 = qs[r0]; qc0 = qc[r0]; qs1 = two ? qs[r0 + 1] : 0.0; qc1 = two ? qc[r0 + 1] : 0.0; }
+        const bool keep0 = r0 != op.loc, keep1 = r0 + 1 != op.loc;
+        for (int j = jq; j < nf; j += 4) {
+            const int idx = j * LD + r0;
+            double2 c = *reinterpret_cast<const double2*>(C + idx);
+            double2 q = *reinterpret_cast<const double2*>(Q + idx);
+            const double cy_old = c.y, qy_old = q.y;
+            if (OP == OP_SPARSE) {
+                const double sj = sv[j];
+                c.x = fma(op.c0, __dmul_rn(s0, sj), c.x);
+                c.y = fma(op.c0, __dmul_rn(s1, sj), c.y);
+            } else if (OP == OP_FULL) {
+                const double sj = sv[j], ej = ev[j];
+                c.x = fma(op.c0, __dmul_rn(s0, sj), c.x);
+                c.y = fma(op.c0, __dmul_rn(s1, sj), c.y);
+                q.x = fma(op.c1, __dmul_rn(e0, ej), q.x);
+                q.y = fma(op.c1, __dmul_rn(e1, ej), q.y);
+            } else if (OP == OP_FULL_DEL) {
+                const double sj = sv[j], ej = ev[j], qsj = qs[j], qcj = qc[j];
+                const bool keepj = j != op.loc;
+                // the source of row / column loc is the new point's row, which is zero before the update
+                const double cx = (keep0 && keepj) ? c.x : 0.0, cy = (keep1 && keepj) ? c.y : 0.0;
+                const double qx = (keep0 && keepj) ? q.x : 0.0, qy = (keep1 && keepj) ? q.y : 0.0;
+                const double c1x = fma(op.c0, __dmul_rn(s0, sj), cx), c1y = fma(op.c0, __dmul_rn(s1, sj), cy);
+                const double q1x = fma(op.c1, __dmul_rn(e0, ej), qx), q1y = fma(op.c1, __dmul_rn(e1, ej), qy);
+                const double ux = __dmul_rn(qs0, qsj), uy = __dmul_rn(qs1, qsj);
+                const double vx = __dmul_rn(qc0, qcj), vy = __dmul_rn(qc1, qcj);
+                c.x = __dadd_rn(c1x, fma(ux, op.iq, -__dmul_rn(vx, op.iqc)));
+                c.y = __dadd_rn(c1y, fma(uy, op.iq, -__dmul_rn(vy, op.iqc)));
+                q.x = fma(-ux, op.iq, q1x);
+                q.y = fma(-uy, op.iq, q1y);
+            }
+            if (!two) { c.y = cy_old; q.y = qy_old; }  // the pad row stays zero
+            if (OP != OP_NONE) *reinterpret_cast<double2*>(C + idx) = c;
+            if (OP == OP_FULL || OP == OP_FULL_DEL) *reinterpret_cast<double2*>(Q + idx) = q;
+            if (do_mv) {
+                const double kj = kn[j];
+                ac0 = fma(c.x, kj, ac0); ac1 = fma(c.y, kj, ac1);
+                aq0 = fma(q.x, kj, aq0); aq1 = fma(q.y, kj, aq1);
+            }
+        }
+    }
+    if (do_mv) {  // (a0 + a1) + (a2 + a3): classes 0/1 and 2/3 differ in lane bit 3, the pairs in lane bit 4
+        ac0 = __dadd_rn(ac0, shfl_xor_d(ac0, 8)); ac1 = __dadd_rn(ac1, shfl_xor_d(ac1, 8));
+        aq0 = __dadd_rn(aq0, shfl_xor_d(aq0, 8)); aq1 = __dadd_rn(aq1, shfl_xor_d(aq1, 8));
+        ac0 = __dadd_rn(ac0, shfl_xor_d(ac0, 16)); ac1 = __dadd_rn(ac1, shfl_xor_d(ac1, 16));
+        aq0 = __dadd_rn(aq0, shfl_xor_d(aq0, 16)); aq1 = __dadd_rn(aq1, shfl_xor_d(aq1, 16));
+        if (jq == 0 && r0 < nf) {
+            ck[r0] = ac0; ek[r0] = aq0;
+            if (r0 + 1 < nf) { ck[r0 + 1] = ac1; ek[r0 + 1] = aq1; }
+        }
+    }
+}
+
+// LD: storage leading dimension (even; rows 16-byte aligned); NT = 32 * ceil(LD / 16) threads; LD_IN: leading dimension
+// of the hand-off slots this bucket resumes; LD_OUT: of the slots it writes when a patch outgrows a.ld.
+template <int LD, int NT, int LD_IN, int LD_OUT>
+__global__ void __launch_bounds__(NT) sogp_fit_fused_kernel(SogpArgs a) {
+    constexpr int DOUT = 1;
+    static_assert(LD % 2 == 0 && NT * 16 >= 32 * LD && NT >= LD + 1, "thread mapping");
+    extern __shared__ double smem_dyn[];
+    const Smem<LD, 1> s{smem_dyn};
+    // vectors after the Smem block and its bidx ints (LD ints = LD/2 doubles)
+    const FusedVecs<LD> fv{smem_dyn + Smem<LD, 1>::kDoubles + LD / 2};
+    double* const C = s.C();
+    double* const Q = s.Q();
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int64_t patch = a.patch_ids ? (int64_t)a.patch_ids[blockIdx.x] : a.first_patch + blockIdx.x;
+    const int64_t o = a.off[patch];
+    const int n = (int)(a.off[patch + 1] - o);
+    const int64_t op_ = patch - a.out_first;
+    if (n == 0) {
+        if (t == 0) { a.nbv[op_] = 0; a.flags[op_] = 0; }
+        return;
+    }
+    for (int i = t; i < Smem<LD, 1>::kDoubles + LD / 2 + FusedVecs<LD>::kDoubles; i += NT) smem_dyn[i] = 0.0;
+    __syncthreads();
+    for (int i = t; i < LD; i += NT) s.bidx()[i] = -1;
+    __syncthreads();
+
+    const double kstar = a.p0, s20 = a.s20, p0 = a.p0, cl = a.cl, eps_tol = a.eps_tol;
+    const int cap = a.capacity, ldmax = a.ld;
+    int N = 0, tt0 = 0;
+    Counters cnt;
+    cnt.init();
+    if (a.handoff_in) {  // resume a patch that outgrew the previous bucket
+        const double* slot = a.handoff_in + (size_t)blockIdx.x * slot_doubles(LD_IN, DOUT);
+        N = reinterpret_cast<const int*>(slot)[0];
+        tt0 = reinterpret_cast<const int*>(slot)[1];
+#pragma unroll
+        for (int i = 0; i < NCNT; i++) cnt.c[i] = reinterpret_cast<const unsigned long long*>(slot + 2)[i];
+        const double* v = slot + 2 + NCNT;
+        for (int i = t; i < LD_IN; i += NT) {
+            s.alpha(0)[i] = v[i];
+            s.b1()[i] = v[DOUT * LD_IN + i]; s.b2()[i] = v[(DOUT + 1) * LD_IN + i];
+            s.bidx()[i] = reinterpret_cast<const int*>(v + (DOUT + 2) * LD_IN + 2 * LD_IN * LD_IN)[i];
+        }
+        for (int e = t; e < LD_IN * LD_IN; e += NT) {
+            const int j = e / LD_IN, i = e - j * LD_IN;
+            C[j * LD + i] = v[(DOUT + 2) * LD_IN + e];
+            Q[j * LD + i] = v[(DOUT + 2) * LD_IN + LD_IN * LD_IN + e];
+        }
+        __syncthreads();
+    }
+    // k of the current point and of the next one alternate between two buffers
+    double* kcur = s.kv();
+    double* knext = fv.kn();
+    bool have_mv = false;
+    FusedOp fo;
+    fo.c0 = fo.c1 = fo.iq = fo.iqc = 0.0;
+    fo.loc = -1;
+
+    double nx1 = a.fx1[o + tt0], nx2 = a.fx2[o + tt0], ny = a.fy[0][o + tt0];
+    int norig = a.forig[o + tt0];
+    for (int tt = tt0; tt < n; ++tt) {
+        const double x1 = nx1, x2 = nx2, y = ny;
+        const int orig = norig;
+        const bool last = tt + 1 == n;
+        if (!last) {  // prefetch the next point of the stream
+            nx1 = a.fx1[o + tt + 1]; nx2 = a.fx2[o + tt + 1]; ny = a.fy[0][o + tt + 1];
+            norig = a.forig[o + tt + 1];
+        }
+        if (N == 0) {  // sparse_gp.hpp:100-110
+            if (t == 0) {
+                const double d = __dadd_rn(kstar, s20);
+                s.alpha(0)[0] = __ddiv_rn(y, d);
+                C[0] = __ddiv_rn(-1.0, d);
+                Q[0] = __ddiv_rn(1.0, kstar);
+                s.b1()[0] = x1; s.b2()[0] = x2; s.bidx()[0] = orig;
+            }
+            N = 1;
+            cnt.c[0]++;
+            have_mv = false;
+            __syncthreads();
+            continue;
+        }
+        if (!have_mv) {  // first point after the start, a resume or a rare event: k and the matvecs on their own
+            if (t < N) kcur[t] = rbf(x1, x2, s.b1()[t], s.b2()[t], p0, cl);
+            __syncthreads();
+            fused_pass<LD, OP_NONE>(C, Q, N, fo, nullptr, nullptr, nullptr, nullptr, kcur, true, s.ck(), s.ev(), t);
+            __syncthreads();
+        }
+        // every warp: k'Ck and k'e_hat -> gamma and the sparse / full decision; warp 0: m = alpha'k and the divisions
+        double kck = 0.0, ke = 0.0;
+        for (int j = lane; j < N; j += 32) {
+            const double kj = kcur[j];
+            kck = fma(kj, s.ck()[j], kck);
+            ke = fma(kj, s.ev()[j], ke);
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            kck = __dadd_rn(kck, shfl_xor_d(kck, off));
+            ke = __dadd_rn(ke, shfl_xor_d(ke, off));
+        }
+        double gamma = __dadd_rn(kstar, -ke);                 // sparse_gp.hpp:144
+        if (gamma < tiny12()) gamma = 0.0;
+        const bool sparse = gamma < eps_tol;
+        // scal[0] = r, [1] = r*eta (sparse) | 1/gamma (full), [2] = q, [5] = q*eta (sparse)
+        if (w == 0) {
+            const double m = warp_dot32(s.alpha(0), kcur, N, lane);
+            const double s2 = __dadd_rn(kstar, kck);
+            const double den = __dadd_rn(s20, s2);
+            const double rr = __ddiv_rn(-1.0, den);               // gaussian_noise.cpp:15-18
+            const double q = __ddiv_rn(__dadd_rn(y, -m), den);    // gaussian_noise.cpp:9-12
+            double qe = 0.0, c3;
+            if (sparse) {
+                const double eta = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn(gamma, rr)));
+                qe = __dmul_rn(q, eta);
+                c3 = __dmul_rn(rr, eta);
+            } else {
+                c3 = __ddiv_rn(1.0, gamma);
+            }
+            if (lane == 0) { s.scal()[0] = rr; s.scal()[1] = c3; s.scal()[2] = q; s.scal()[5] = qe; }
+        }
+        if (sparse) {
+            // sparse update (sparse_gp.hpp:155-163) fused with the next point's matvecs
+            cnt.run++;
+            double sh = 0.0;
+            if (t < N) {
+                sh = __dadd_rn(s.ck()[t], s.ev()[t]);
+                s.sv()[t] = sh;
+                if (!last) knext[t] = rbf(nx1, nx2, s.b1()[t], s.b2()[t], p0, cl);
+            }
+            __syncthreads();
+            fo.c0 = s.scal()[1];
+            if (t < N) s.alpha(0)[t] = __dadd_rn(s.alpha(0)[t], __dmul_rn(sh, s.scal()[5]));
+            fused_pass<LD, OP_SPARSE>(C, Q, N, fo, s.sv(), nullptr, nullptr, nullptr, knext, !last, s.ck(), s.ev(), t);
+            __syncthreads();
+            have_mv = !last;
+            { double* tmp = kcur; kcur = knext; knext = tmp; }
+            continue;  // Q and N unchanged: neither deletion loop can fire
+        }
+        // full update (sparse_gp.hpp:164-203)
+        cnt.flush(N);
+        if (N + 1 > ldmax) {  // does not fit this bucket: hand the state to the next one (the matrices are up to date)
+            __shared__ int spos;
+            if (t == 0) spos = atomicAdd(a.queue_count, 1);
+            __syncthreads();
+            const int pos = spos;
+            double* slot = a.handoff_out + (size_t)pos * slot_doubles(LD_OUT, DOUT);
+            if (t == 0) {
+                a.queue[pos] = (int32_t)patch;
+                reinterpret_cast<int*>(slot)[0] = N;
+                reinterpret_cast<int*>(slot)[1] = tt;
+                for (int i = 0; i < NCNT; i++) reinterpret_cast<unsigned long long*>(slot + 2)[i] = cnt.c[i];
+            }
+            double* v = slot + 2 + NCNT;
+            for (int i = t; i < LD_OUT; i += NT) {
+                v[i] = s.alpha(0)[i];
+                v[DOUT * LD_OUT + i] = s.b1()[i]; v[(DOUT + 1) * LD_OUT + i] = s.b2()[i];
+                reinterpret_cast<int*>(v + (DOUT + 2) * LD_OUT + 2 * LD_OUT * LD_OUT)[i] = s.bidx()[i];
+            }
+            for (int e = t; e < LD_OUT * LD_OUT; e += NT) {
+                const int j = e / LD_OUT, i = e - j * LD_OUT;
+                v[(DOUT + 2) * LD_OUT + e] = C[j * LD + i];
+                v[(DOUT + 2) * LD_OUT + LD_OUT * LD_OUT + e] = Q[j * LD + i];
+            }
+            return;
+        }
+        cnt.full(N);
+        const int N1 = N + 1;
+        double sct = 0.0;
+        if (t < N) {
+            sct = s.ck()[t];
+            s.sv()[t] = sct;
+        }
+        if (t == N) {
+            s.sv()[N] = 1.0;
+            s.ev()[N] = -1.0;
+            s.b1()[N] = x1; s.b2()[N] = x2; s.bidx()[N] = orig;
+        }
+        __syncthreads();
+        const double rr = s.scal()[0], ig = s.scal()[1];
+        fo.c0 = rr; fo.c1 = ig;
+        // alpha after the full update, and the diagonals of the updated C and Q (O(N), no matrix pass yet)
+        double a1 = 0.0, dc = 0.0, dq = 0.0;
+        if (t < N1) {
+            const double q = s.scal()[2];
+            a1 = (t < N) ? __dadd_rn(s.alpha(0)[t], __dmul_rn(q, sct)) : __dadd_rn(0.0, __dmul_rn(q, 1.0));
+            s.alpha(0)[t] = a1;
+            const double st_ = s.sv()[t], et_ = s.ev()[t];
+            dc = fma(rr, __dmul_rn(st_, st_), C[t * LD + t]);
+            dq = fma(ig, __dmul_rn(et_, et_), Q[t * LD + t]);
+        }
+        if (N1 <= cap) {
+            // no capacity deletion; geometric deletions (sparse_gp.hpp:226-242) are decided on the updated diagonal
+            const int geo = __syncthreads_or(t < N1 && __ddiv_rn(1.0, dq) < geo9());
+            N = N1;
+            if (geo) {  // rare: bring the matrices up to date, then the step-by-step loop
+                fused_pass<LD, OP_FULL>(C, Q, N, fo, s.sv(), s.ev(), nullptr, nullptr, knext, false, s.ck(), s.ev(), t);
+                __syncthreads();
+                while (N > 1) {
+                    const int loc = block_argmin<LD, DOUT, 1>(s, N, t, lane);
+                    if (loc < 0) break;
+                    cnt.c[9] += (unsigned long long)(N - 1) * (N - 1);
+                    delete_bv_any<LD, NT, DOUT>(s, N, loc, t);
+                    cnt.c[4]++;
+                }
+                have_mv = false;
+                continue;
+            }
+            if (!last && t < N) knext[t] = rbf(nx1, nx2, s.b1()[t], s.b2()[t], p0, cl);
+            __syncthreads();
+            // ek aliases ev: the pass reads ev[j] for all j while lanes jq == 0 write ek[r0] at its end, after the
+            // shuffles that every lane of the warp reaches only when its own loop is done; other warps may still be
+            // reading ev, so the row sums go to sv / qsv first and are copied below
+            fused_pass<LD, OP_FULL>(C, Q, N, fo, s.sv(), s.ev(), nullptr, nullptr, knext, !last, s.qsv(), s.qcv(), t);
+            __syncthreads();
+            if (!last && t < N) { s.ck()[t] = s.qsv()[t]; s.ev()[t] = s.qcv()[t]; }
+            __syncthreads();
+            have_mv = !last;
+            { double* tmp = kcur; kcur = knext; knext = tmp; }
+            continue;
+        }
+        // capacity deletion (sparse_gp.hpp:206-223): scores from the updated alpha and diagonals, then ONE pass
+        if (t < N1) s.scv()[t] = __ddiv_rn(__dmul_rn(a1, a1), __dadd_rn(dq, dc));
+        __syncthreads();
+        const int loc = scan_first_min(s.scv(), N1, lane);
+        const int L = N, M = N;   // the new point sits at index L; M entries remain
+        cnt.c[9] += (unsigned long long)M * M;
+        cnt.c[3]++;
+        fo.loc = loc;
+        double ai = 0.0, qsi = 0.0, qci = 0.0, dqn = 0.0;
+        if (t < M) {
+            const int src = (t == loc) ? L : t;  // the last entry moves into the deleted slot
+            const double cold = (src == L || loc == L) ? 0.0 : C[src * LD + loc];
+            const double qold = (src == L || loc == L) ? 0.0 : Q[src * LD + loc];
+            const double ssrc = s.sv()[src], esrc = s.ev()[src];
+            const double csi = fma(rr, __dmul_rn(s.sv()[loc], ssrc), cold);   // row loc of the updated C, permuted
+            qsi = fma(ig, __dmul_rn(s.ev()[loc], esrc), qold);
+            qci = __dadd_rn(qsi, csi);
+            ai = s.alpha(0)[src];
+            // diagonal of the updated Q at the source position: feeds the geometric test on the final Q
+            const double qdd = (src == L) ? 0.0 : Q[src * LD + src];
+            dqn = fma(ig, __dmul_rn(esrc, esrc), qdd);
+            fv.svp()[t] = ssrc;
+            fv.evp()[t] = esrc;
+        }
+        if (w == 0) {
+            const double cll = (loc == L) ? 0.0 : C[loc * LD + loc], qll = (loc == L) ? 0.0 : Q[loc * LD + loc];
+            const double sl = s.sv()[loc], el = s.ev()[loc];
+            const double cstar = fma(rr, __dmul_rn(sl, sl), cll), qstar = fma(ig, __dmul_rn(el, el), qll);
+            const double qcs = __dadd_rn(qstar, cstar);
+            const double coef = __ddiv_rn(s.alpha(0)[loc], qcs);
+            const double iq = __ddiv_rn(1.0, qstar), iqc = __ddiv_rn(1.0, qcs);
+            if (lane == 0) { s.scal()[8] = iq; s.scal()[9] = iqc; s.scal()[11] = coef; }
+        }
+        __syncthreads();  // every read of alpha / sv / ev by index src is done
+        fo.iq = s.scal()[8]; fo.iqc = s.scal()[9];
+        if (t < M) {
+            s.alpha(0)[t] = __dadd_rn(ai, -__dmul_rn(s.scal()[11], qci));   // sparse_gp.hpp:285
+            s.qsv()[t] = qsi;
+            s.qcv()[t] = qci;
+            if (t == loc && loc != L) { s.b1()[loc] = x1; s.b2()[loc] = x2; s.bidx()[loc] = orig; }
+            dqn = fma(-__dmul_rn(qsi, qsi), fo.iq, dqn);   // Q_tt after the deletion
+        }
+        if (t == L) { s.alpha(0)[L] = 0.0; s.b1()[L] = 0.0; s.b2()[L] = 0.0; s.bidx()[L] = -1; }
+        const int geo = __syncthreads_or(t < M && M > 1 && __ddiv_rn(1.0, dqn) < geo9());
+        if (!last && !geo && t < M) knext[t] = rbf(nx1, nx2, s.b1()[t], s.b2()[t], p0, cl);
+        __syncthreads();
+        fused_pass<LD, OP_FULL_DEL>(C, Q, M, fo, fv.svp(), fv.evp(), s.qsv(), s.qcv(), knext, !last && !geo, s.ck(), s.ev(), t);
+        N = M;
+        fo.loc = -1;
+        __syncthreads();
+        if (geo) {  // rare: geometric deletions on the up-to-date state (sparse_gp.hpp:226-242)
+            while (N > 1) {
+                const int l2 = block_argmin<LD, DOUT, 1>(s, N, t, lane);
+                if (l2 < 0) break;
+                cnt.c[9] += (unsigned long long)(N - 1) * (N - 1);
+                delete_bv_any<LD, NT, DOUT>(s, N, l2, t);
+                cnt.c[4]++;
+            }
+            have_mv = false;
+            continue;
+        }
+        have_mv = !last;
+        { double* tmp = kcur; kcur = knext; knext = tmp; }
+    }
+    cnt.flush(N);
+    __syncthreads();
+    // results
+    if (t == 0) {
+        a.nbv[op_] = N;
+        const double c00 = C[0];
+        a.flags[op_] = (c00 != c00) ? 1 : 0;
+        publish(a, cnt, n);
+    }
+    const int64_t ob = op_ * cap;
+    for (int i = t; i < N; i += NT) {
+        a.o_alpha[0][ob + i] = s.alpha(0)[i];
+        a.o_b1[ob + i] = s.b1()[i];
+        a.o_b2[ob + i] = s.b2()[i];
+        a.o_idx[ob + i] = s.bidx()[i];
+    }
+    if (a.dumpC) {
+        const int64_t od = op_ * (int64_t)cap * cap;
+        for (int e = t; e < N * N; e += NT) {
+            const int i = e / N, j = e - i * N;
+            a.dumpC[od + e] = C[j * LD + i];
+            a.dumpQ[od + e] = Q[j * LD + i];
+        }
+    }
+}
+
+template <int LD>
+constexpr size_t fused_smem_bytes() { return (size_t)(Smem<LD, 1>::kDoubles + LD / 2 + FusedVecs<LD>::kDoubles) * sizeof(double); }
+
+template <int LD, int NT, int LD_IN, int LD_OUT>
+cudaError_t launch_fused_bucket(const SogpArgs& a, cudaStream_t st) {
+    constexpr size_t smem = fused_smem_bytes<LD>();
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(sogp_fit_fused_kernel<LD, NT, LD_IN, LD_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    sogp_fit_fused_kernel<LD, NT, LD_IN, LD_OUT><<<a.n_work, NT, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 template <int LD, int DOUT>
 constexpr size_t cta_smem_bytes() { return (size_t)Smem<LD, DOUT>::kDoubles * sizeof(double) + (size_t)LD * sizeof(int); }
 
@@ -1312,8 +1845,10 @@ cudaError_t launch_sogp_fit(int bucket, const SogpArgs& a, cudaStream_t st) {
         case 1:
             sogp_fit_pair_kernel<<<a.n_work, 64, 0, st>>>(a);
             return cudaGetLastError();
-        case 2: return launch_cta_bucket<64, 64, 256, 32, false, 1>(a, st);
-        case 3: return launch_cta_bucket<118, 128, 512, 64, false, 1>(a, st);
+        case 2: return launch_fused_bucket<72, 160, 32, 64>(a, st);
+        case 3:
+            if (a.ld <= 104) return launch_fused_bucket<104, 224, 64, 104>(a, st);
+            return launch_cta_bucket<118, 128, 512, 64, false, 1>(a, st);
         default: return launch_cta_bucket<202, 256, 1024, 118, true, 1>(a, st);
     }
 }
