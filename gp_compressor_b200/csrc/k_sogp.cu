@@ -375,9 +375,17 @@ __global__ void __launch_bounds__(32, DOUT == 1 ? 20 : 16) sogp_fit_half_kernel(
             const int N1 = N + 1;
             if (r < N1) {
                 const double si = sm.sv[r], ei = sm.ev[r];
-                for (int j = 0; j < N1; j++) {
-                    Crow[j] = fma(rr, __dmul_rn(si, sm.sv[j]), Crow[j]);
-                    Qrow[j] = fma(ig, __dmul_rn(ei, sm.ev[j]), Qrow[j]);
+                for (int j = 0; j < N1; j += 2) {  // column pairs; the pad column (j + 1 == N1) stays zero
+                    double2 c = *reinterpret_cast<double2*>(Crow + j), q = *reinterpret_cast<double2*>(Qrow + j);
+                    const double2 s2v = *reinterpret_cast<const double2*>(sm.sv + j), e2v = *reinterpret_cast<const double2*>(sm.ev + j);
+                    c.x = fma(rr, __dmul_rn(si, s2v.x), c.x);
+                    q.x = fma(ig, __dmul_rn(ei, e2v.x), q.x);
+                    if (j + 1 < N1) {
+                        c.y = fma(rr, __dmul_rn(si, s2v.y), c.y);
+                        q.y = fma(ig, __dmul_rn(ei, e2v.y), q.y);
+                    }
+                    *reinterpret_cast<double2*>(Crow + j) = c;
+                    *reinterpret_cast<double2*>(Qrow + j) = q;
                 }
             }
             N = N1;
@@ -451,12 +459,19 @@ __global__ void __launch_bounds__(32, DOUT == 1 ? 20 : 16) sogp_fit_half_kernel(
                 __syncwarp(gm);
                 if (r < M) {
                     const double qi = sm.sv[r], ci = sm.ev[r];
-                    for (int j = 0; j < M; j++) {
-                        const double u = __dmul_rn(qi, sm.sv[j]);
-                        const double v = __dmul_rn(ci, sm.ev[j]);
-                        const double wv = fma(u, iq, -__dmul_rn(v, iqc));
-                        Crow[j] = __dadd_rn(Crow[j], wv);
-                        Qrow[j] = fma(-u, iq, Qrow[j]);
+                    for (int j = 0; j < M; j += 2) {  // column pairs; the pad column (j + 1 == M) stays zero
+                        double2 c = *reinterpret_cast<double2*>(Crow + j), q = *reinterpret_cast<double2*>(Qrow + j);
+                        const double2 s2v = *reinterpret_cast<const double2*>(sm.sv + j), e2v = *reinterpret_cast<const double2*>(sm.ev + j);
+                        const double u0 = __dmul_rn(qi, s2v.x), v0 = __dmul_rn(ci, e2v.x);
+                        c.x = __dadd_rn(c.x, fma(u0, iq, -__dmul_rn(v0, iqc)));
+                        q.x = fma(-u0, iq, q.x);
+                        if (j + 1 < M) {
+                            const double u1 = __dmul_rn(qi, s2v.y), v1 = __dmul_rn(ci, e2v.y);
+                            c.y = __dadd_rn(c.y, fma(u1, iq, -__dmul_rn(v1, iqc)));
+                            q.y = fma(-u1, iq, q.y);
+                        }
+                        *reinterpret_cast<double2*>(Crow + j) = c;
+                        *reinterpret_cast<double2*>(Qrow + j) = q;
                     }
                 }
                 N = M;
@@ -1358,8 +1373,8 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
 // of 80 N^2 and needs 6 block barriers instead of 11.  Every element still receives exactly the operations, in the
 // order, of sparse_gp::add / delete_bv as every other bucket performs them, so results are bit-identical.
 //
-// A warp covers 16 rows x 4 column classes: lane = 8 * jq + rp owns rows (16 w + 2 rp, + 1) as 128-bit pairs and the
-// columns j = jq (mod 4), i.e. the canonical row4 partial a_jq of its rows; two shuffles give (a0 + a1) + (a2 + a3).
+// A warp covers 8 rows x 4 column classes: lane = 8 * jq + rp owns row 8 w + rp and the columns j = jq (mod 4), i.e.
+// the canonical row4 partial a_jq of its row; two shuffles give (a0 + a1) + (a2 + a3).
 // Rare events (geometric deletions, the hand-off to a larger bucket) first bring the matrices up to date with a
 // pass without matvec and then run the step-by-step code of the generic kernel.
 // =====================================================================================
@@ -1400,6 +1415,8 @@ struct FusedOp {
 // One pass over the leading nf x nf blocks of C and Q: apply OP, optionally accumulate the row sums with kn.
 // sv / ev: update vectors indexed by the FINAL position (already permuted for FULL_DEL); qs / qc: the deletion's
 // Qstar and Qstar + Cstar.  Writes ck / ek (the row sums) when do_mv.
+// One row per thread: lane = 8 * jq + rp owns row 8 w + rp and the columns j = jq (mod 4); with LD = 8 (mod 16) the
+// four 64-byte segments of a warp access fall on disjoint banks in pairs (two wavefronts for 256 bytes).
 template <int LD, int OP>
 __device__ __forceinline__ void fused_pass(double* __restrict__ C, double* __restrict__ Q, int nf, const FusedOp op,
                                            const double* __restrict__ sv, const double* __restrict__ ev,
@@ -1408,73 +1425,59 @@ __device__ __forceinline__ void fused_pass(double* __restrict__ C, double* __res
                                            double* __restrict__ ek, int t) {
     const int lane = t & 31, w = t >> 5;
     const int rp = lane & 7, jq = lane >> 3;
-    const int r0 = 16 * w + 2 * rp;
-    double ac0 = 0.0, ac1 = 0.0, aq0 = 0.0, aq1 = 0.0;
+    const int r0 = 8 * w + rp;
+    double ac = 0.0, aq = 0.0;
     if (r0 < nf) {
-        const bool two = r0 + 1 < nf;
-        double s0 = 0, s1 = 0, e0 = 0, e1 = 0, qs0 = 0, qs1 = 0, qc0 = 0, qc1 = 0;
-        if (OP != OP_NONE) { s0 = sv[r0]; s1 = two ? sv[r0 + 1] : 0.0; }
-        if (OP == OP_FULL || OP == OP_FULL_DEL) { e0 = ev[r0]; e1 = two ? ev[r0 + 1] : 0.0; }
-        if (OP == OP_FULL_DEL) { qs0 = qs[r0]; qc0 = qc[r0]; qs1 = two ? qs[r0 + 1] : 0.0; qc1 = two ? qc[r0 + 1] : 0.0; }
-        const bool keep0 = r0 != op.loc, keep1 = r0 + 1 != op.loc;
+        double s0 = 0, e0 = 0, qs0 = 0, qc0 = 0;
+        if (OP != OP_NONE) s0 = sv[r0];
+        if (OP == OP_FULL || OP == OP_FULL_DEL) e0 = ev[r0];
+        if (OP == OP_FULL_DEL) { qs0 = qs[r0]; qc0 = qc[r0]; }
+        const bool keep0 = r0 != op.loc;
+#pragma unroll 4
         for (int j = jq; j < nf; j += 4) {
             const int idx = j * LD + r0;
-            double2 c = *reinterpret_cast<const double2*>(C + idx);
-            double2 q = *reinterpret_cast<const double2*>(Q + idx);
-            const double cy_old = c.y, qy_old = q.y;
+            double c = C[idx];
+            double q = Q[idx];
             if (OP == OP_SPARSE) {
-                const double sj = sv[j];
-                c.x = fma(op.c0, __dmul_rn(s0, sj), c.x);
-                c.y = fma(op.c0, __dmul_rn(s1, sj), c.y);
+                c = fma(op.c0, __dmul_rn(s0, sv[j]), c);
             } else if (OP == OP_FULL) {
-                const double sj = sv[j], ej = ev[j];
-                c.x = fma(op.c0, __dmul_rn(s0, sj), c.x);
-                c.y = fma(op.c0, __dmul_rn(s1, sj), c.y);
-                q.x = fma(op.c1, __dmul_rn(e0, ej), q.x);
-                q.y = fma(op.c1, __dmul_rn(e1, ej), q.y);
+                c = fma(op.c0, __dmul_rn(s0, sv[j]), c);
+                q = fma(op.c1, __dmul_rn(e0, ev[j]), q);
             } else if (OP == OP_FULL_DEL) {
                 const double sj = sv[j], ej = ev[j], qsj = qs[j], qcj = qc[j];
-                const bool keepj = j != op.loc;
                 // the source of row / column loc is the new point's row, which is zero before the update
-                const double cx = (keep0 && keepj) ? c.x : 0.0, cy = (keep1 && keepj) ? c.y : 0.0;
-                const double qx = (keep0 && keepj) ? q.x : 0.0, qy = (keep1 && keepj) ? q.y : 0.0;
-                const double c1x = fma(op.c0, __dmul_rn(s0, sj), cx), c1y = fma(op.c0, __dmul_rn(s1, sj), cy);
-                const double q1x = fma(op.c1, __dmul_rn(e0, ej), qx), q1y = fma(op.c1, __dmul_rn(e1, ej), qy);
-                const double ux = __dmul_rn(qs0, qsj), uy = __dmul_rn(qs1, qsj);
-                const double vx = __dmul_rn(qc0, qcj), vy = __dmul_rn(qc1, qcj);
-                c.x = __dadd_rn(c1x, fma(ux, op.iq, -__dmul_rn(vx, op.iqc)));
-                c.y = __dadd_rn(c1y, fma(uy, op.iq, -__dmul_rn(vy, op.iqc)));
-                q.x = fma(-ux, op.iq, q1x);
-                q.y = fma(-uy, op.iq, q1y);
+                const bool keep = keep0 && j != op.loc;
+                const double c1 = fma(op.c0, __dmul_rn(s0, sj), keep ? c : 0.0);
+                const double q1 = fma(op.c1, __dmul_rn(e0, ej), keep ? q : 0.0);
+                const double u = __dmul_rn(qs0, qsj);
+                const double v = __dmul_rn(qc0, qcj);
+                c = __dadd_rn(c1, fma(u, op.iq, -__dmul_rn(v, op.iqc)));
+                q = fma(-u, op.iq, q1);
             }
-            if (!two) { c.y = cy_old; q.y = qy_old; }  // the pad row stays zero
-            if (OP != OP_NONE) *reinterpret_cast<double2*>(C + idx) = c;
-            if (OP == OP_FULL || OP == OP_FULL_DEL) *reinterpret_cast<double2*>(Q + idx) = q;
+            if (OP != OP_NONE) C[idx] = c;
+            if (OP == OP_FULL || OP == OP_FULL_DEL) Q[idx] = q;
             if (do_mv) {
                 const double kj = kn[j];
-                ac0 = fma(c.x, kj, ac0); ac1 = fma(c.y, kj, ac1);
-                aq0 = fma(q.x, kj, aq0); aq1 = fma(q.y, kj, aq1);
+                ac = fma(c, kj, ac);
+                aq = fma(q, kj, aq);
             }
         }
     }
     if (do_mv) {  // (a0 + a1) + (a2 + a3): classes 0/1 and 2/3 differ in lane bit 3, the pairs in lane bit 4
-        ac0 = __dadd_rn(ac0, shfl_xor_d(ac0, 8)); ac1 = __dadd_rn(ac1, shfl_xor_d(ac1, 8));
-        aq0 = __dadd_rn(aq0, shfl_xor_d(aq0, 8)); aq1 = __dadd_rn(aq1, shfl_xor_d(aq1, 8));
-        ac0 = __dadd_rn(ac0, shfl_xor_d(ac0, 16)); ac1 = __dadd_rn(ac1, shfl_xor_d(ac1, 16));
-        aq0 = __dadd_rn(aq0, shfl_xor_d(aq0, 16)); aq1 = __dadd_rn(aq1, shfl_xor_d(aq1, 16));
-        if (jq == 0 && r0 < nf) {
-            ck[r0] = ac0; ek[r0] = aq0;
-            if (r0 + 1 < nf) { ck[r0 + 1] = ac1; ek[r0 + 1] = aq1; }
-        }
+        ac = __dadd_rn(ac, shfl_xor_d(ac, 8));
+        aq = __dadd_rn(aq, shfl_xor_d(aq, 8));
+        ac = __dadd_rn(ac, shfl_xor_d(ac, 16));
+        aq = __dadd_rn(aq, shfl_xor_d(aq, 16));
+        if (jq == 0 && r0 < nf) { ck[r0] = ac; ek[r0] = aq; }
     }
 }
 
-// LD: storage leading dimension (even; rows 16-byte aligned); NT = 32 * ceil(LD / 16) threads; LD_IN: leading dimension
+// LD: storage leading dimension (= 8 mod 16, see fused_pass); NT = 32 * ceil(LD / 8) threads; LD_IN: leading dimension
 // of the hand-off slots this bucket resumes; LD_OUT: of the slots it writes when a patch outgrows a.ld.
 template <int LD, int NT, int LD_IN, int LD_OUT>
 __global__ void __launch_bounds__(NT) sogp_fit_fused_kernel(SogpArgs a) {
     constexpr int DOUT = 1;
-    static_assert(LD % 2 == 0 && NT * 16 >= 32 * LD && NT >= LD + 1, "thread mapping");
+    static_assert(LD % 16 == 8 && NT * 8 >= 32 * LD && NT >= LD + 1, "thread mapping");
     extern __shared__ double smem_dyn[];
     const Smem<LD, 1> s{smem_dyn};
     // vectors after the Smem block and its bidx ints (LD ints = LD/2 doubles)
@@ -1845,9 +1848,9 @@ cudaError_t launch_sogp_fit(int bucket, const SogpArgs& a, cudaStream_t st) {
         case 1:
             sogp_fit_pair_kernel<<<a.n_work, 64, 0, st>>>(a);
             return cudaGetLastError();
-        case 2: return launch_fused_bucket<72, 160, 32, 64>(a, st);
+        case 2: return launch_fused_bucket<72, 288, 32, 64>(a, st);
         case 3:
-            if (a.ld <= 104) return launch_fused_bucket<104, 224, 64, 104>(a, st);
+            if (a.ld <= 104) return launch_fused_bucket<104, 416, 64, 104>(a, st);
             return launch_cta_bucket<118, 128, 512, 64, false, 1>(a, st);
         default: return launch_cta_bucket<202, 256, 1024, 118, true, 1>(a, st);
     }
