@@ -210,3 +210,19 @@ def test_errors(G):
         G.Handle(capacity=202).fit_patches([0, 1], [0.0], [0.0], [0.0])
     with pytest.raises(G.GpcError):
         G.Handle().decompress_resident()
+
+
+@pytest.mark.parametrize("cap", [50, 90])
+def test_geometric_deletions_in_the_fused_buckets(G, oracle_mod, cap):
+    """Near-duplicate points with a tiny novelty threshold: full updates with huge 1/gamma, so 1/Q_ii drops below 1e-9f
+    and the geometric deletion loop (sparse_gp.hpp:226-242) fires while N is in the fused buckets (N > 32) -- the rare
+    path of sogp_fit_fused_kernel, which first brings C and Q up to date and then runs the step-by-step deletion."""
+    off, x1, x2, y = make_patches(40 + cap, [500])
+    rng = np.random.default_rng(cap)
+    src = rng.integers(0, 250, 120)
+    x1[250:370] = x1[src] + rng.uniform(-1, 1, 120) * 3e-7
+    x2[250:370] = x2[src] + rng.uniform(-1, 1, 120) * 3e-7
+    cfg = dict(capacity=cap, sigmaf_sq=1.0, l_sq=(0.1 / 14.0) ** 2, s0=1e-6, eps_tol=1e-14, shuffle=0)
+    h, o, got, want = check_fit(G, oracle_mod, off, x1, x2, y, **cfg)
+    st = o.stats()
+    assert st["n_del_geo"] > 0 and int(want["nbv"][0]) > 32
