@@ -18,7 +18,7 @@ GPC_OK = 0
 # every symbol include/gpc.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "gpc_config_default", "gpc_create", "gpc_destroy", "gpc_last_error", "gpc_version", "gpc_compress",
-    "gpc_upload_cloud", "gpc_compress_resident", "gpc_fit_patches", "gpc_decompress", "gpc_decompress_resident",
+    "gpc_upload_cloud", "gpc_compress_resident", "gpc_compress_shard_begin", "gpc_compress_shard_finish", "gpc_fit_patches", "gpc_decompress", "gpc_decompress_resident",
     "gpc_get_heights", "gpc_predict", "gpc_evaluate_patches", "gpc_get_sizes", "gpc_get_stats", "gpc_get_patches", "gpc_get_assignment",
     "gpc_get_params", "gpc_get_params_rgb", "gpc_get_state", "gpc_set_params", "gpc_set_rand_offset", "gpc_get_stream", "gpc_debug_exp", "gpc_debug_rand", "gpc_debug_peak", "gpc_shard_range", "gpc_save", "gpc_load", "gpc_get_config",
 ]
@@ -75,6 +75,8 @@ def load():
     L.gpc_decompress_resident.argtypes = [vp, C.POINTER(i64)]
     L.gpc_get_heights.argtypes = [vp, vp, i64]
     L.gpc_predict.argtypes = [vp, i64, vp, i64, vp, vp]
+    L.gpc_compress_shard_begin.argtypes = [vp, vp, i64, vp, vp]
+    L.gpc_compress_shard_finish.argtypes = [vp, i64, C.c_uint64, i64, C.c_uint64]
     L.gpc_evaluate_patches.argtypes = [vp, i64, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp]
     L.gpc_get_sizes.argtypes = [vp, C.POINTER(GpcSizes)]
     L.gpc_get_stats.argtypes = [vp, C.POINTER(GpcStats)]
@@ -154,6 +156,20 @@ class Handle:
     def compress(self, cloud32):
         assert cloud32.dtype == np.uint8 and cloud32.ndim == 2 and cloud32.shape[1] == 32 and cloud32.flags.c_contiguous
         self._ck(load().gpc_compress(self.h, _p(cloud32), cloud32.shape[0]))
+
+    def compress_shard_begin(self, cloud32=None):
+        """First phase of the sharded-binning compress; returns (owned_patches, owned_draws) for the all-gather."""
+        op, od = C.c_int64(0), C.c_uint64(0)
+        if cloud32 is None:
+            rc = load().gpc_compress_shard_begin(self.h, None, 0, C.byref(op), C.byref(od))
+        else:
+            assert cloud32.dtype == np.uint8 and cloud32.ndim == 2 and cloud32.shape[1] == 32 and cloud32.flags.c_contiguous
+            rc = load().gpc_compress_shard_begin(self.h, _p(cloud32), cloud32.shape[0], C.byref(op), C.byref(od))
+        self._ck(rc)
+        return int(op.value), int(od.value)
+
+    def compress_shard_finish(self, patches_before, draws_before, patches_total, draws_total):
+        self._ck(load().gpc_compress_shard_finish(self.h, patches_before, draws_before, patches_total, draws_total))
 
     def upload_cloud(self, cloud32):
         assert cloud32.dtype == np.uint8 and cloud32.ndim == 2 and cloud32.shape[1] == 32 and cloud32.flags.c_contiguous

@@ -40,7 +40,14 @@ struct gpc_handle {
     DevBuf perm_rgb, fcr, fcg, fcb, r_nbv, r_flags, r_alpha0, r_alpha1, r_alpha2, r_b1, r_b2, r_bidx, kstats_rgb;
     bool have_rgb = false;
     DevBuf quat, mean, rgbmean, Rm, center, code, ncand, owner, st_idx;
-    DevBuf tmpA, tmpB, tmpC, lat_state, ev_in, ev_out, size_ids, size_hist;
+    DevBuf tmpA, tmpB, tmpC, lat_state, ev_in, ev_out, size_ids, size_hist, sel_cloud, sel_idx, coarse_hist;
+    // sharded binning (gpc_compress_shard_begin / _finish): this shard's patches are local indices [own_lo, own_hi) of a
+    // binning that holds the shard's key range plus its halo; global patch index = local + gshift
+    bool shard_mode = false;
+    int64_t own_lo = 0, own_hi = 0, gshift = 0, patches_total = 0, n_sel = 0;
+    uint64_t draws_before = 0, draws_total = 0, draws_owned = 0;
+    int shard_cb = 0;
+    int64_t shard_pos_lo = 0, shard_pos_hi = 0;
     // binning scratch
     DevBuf keys, keys2, vals, vals2, ovals, ovals2, sort_tmp, flags64, ex, leaf_of, leaf_start, leaf_code_a, spt, nbr, nnbr,
         center_a, Rm_a, ncand_a, pt0, pt1, pt2, hbuf, rgb, leaf_sums;
@@ -163,8 +170,8 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
     CK(h->scan_tmp.reserve(scan_tmp_bytes(P + 1)));
     CK(h->small.reserve(256));
     int64_t* d_plan = h->small.as<int64_t>() + 8;
-    launch_fit_plan(h->off.as<int64_t>(), P, mult, c.shard_rank, c.shard_count, h->draws.as<int64_t>(), h->roff.as<int64_t>(),
-                    h->scan_tmp.p, d_plan, st);
+    launch_fit_plan(h->off.as<int64_t>(), P, mult, c.shard_rank, c.shard_count, h->shard_mode ? h->own_lo : -1, h->own_hi,
+                    h->draws.as<int64_t>(), h->roff.as<int64_t>(), h->scan_tmp.p, d_plan, st);
     int64_t plan[9];
     CK(cudaMemcpyAsync(plan, d_plan, sizeof(plan), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -175,7 +182,11 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
     h->s_begin = plan[3];
     h->s_count = plan[4] - plan[3];
     const int64_t S = h->n_claimed;
-    const uint64_t draws_lo = (uint64_t)plan[5], draws_hi = (uint64_t)plan[6], draws_all = (uint64_t)plan[7];
+    // replicated binning: the shard's window of the global draw sequence comes from the prefix over all patches;
+    // sharded binning: the draws of the earlier shards come from the all-gather between begin and finish
+    const uint64_t draws_lo = h->shard_mode ? h->draws_before : (uint64_t)plan[5];
+    const uint64_t draws_hi = draws_lo + (uint64_t)(plan[6] - plan[5]);
+    const uint64_t draws_all = h->shard_mode ? h->draws_total : (uint64_t)plan[7];
     const int64_t max_np = plan[8];
     CK(h->perm.reserve(std::max<int64_t>(S, 1) * sizeof(int32_t)));
     CK(h->patch_of.reserve(std::max<int64_t>(S, 1) * sizeof(int32_t)));
@@ -400,11 +411,13 @@ int bits_for(uint64_t v) {  // bits needed to represent values 0..v
 }
 
 // project_cloud (gp_compressor.cpp:177-249) on the resident cloud: fills off/x1/x2/y and frames.
-int run_binning(gpc_handle* h, StageTimer& tm) {
+// sharded: bin only the points within three voxels of this rank's range of the visiting order (gpc_compress_shard_begin)
+int run_binning(gpc_handle* h, StageTimer& tm, bool sharded = false) {
     const gpc_config& c = h->cfg;
     cudaStream_t st = h->stream;
-    const int64_t n = h->n_in;
+    int64_t n = h->n_in;
     const uint8_t* cloud = h->cloud.as<uint8_t>();
+    h->shard_mode = false;
     if (n > 0x7fffffff) return fail(h, GPC_ERR_INVALID, "more than 2^31-1 points");
     h->have_binning = h->have_frames = h->have_fit = false;
     CK(h->small.reserve(256));
@@ -447,6 +460,71 @@ int run_binning(gpc_handle* h, StageTimer& tm) {
         return GPC_OK;
     }
     const LatticeDev lat = Lh.lat;
+    if (sharded) {
+        // ---- the rank's range of the visiting order, from a coarse key histogram of the WHOLE cloud (identical on every
+        // rank: integer counts), then the points within the halo of that range, compacted into a private cloud ----
+        const int depth = (int)L.depth;
+        const int cb = std::min(15, 3 * (depth - 3));   // coarse cells of side >= 8 voxels
+        CK(h->keys.reserve(n * sizeof(uint64_t)));
+        CK(h->vals.reserve(n * sizeof(uint32_t)));
+        launch_point_keys(cloud, n, lat, h->keys.as<uint64_t>(), h->vals.as<uint32_t>(), st);
+        int64_t pos_lo = 0, pos_hi = 0;
+        if (cb < 3) {  // lattice too small to cut: rank 0 takes everything
+            h->shard_cb = 0;
+            pos_lo = 0; pos_hi = (c.shard_rank == 0) ? 1 : 0;
+        } else {
+            h->shard_cb = cb;
+            const int64_t ncell = 1ll << cb;
+            CK(h->coarse_hist.reserve(ncell * sizeof(unsigned int)));
+            launch_coarse_hist(h->keys.as<uint64_t>(), n, depth, cb, h->coarse_hist.as<unsigned int>(), st);
+            std::vector<unsigned int> hist(ncell);
+            CK(cudaMemcpyAsync(hist.data(), h->coarse_hist.p, ncell * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            int64_t total = 0;
+            for (int64_t i = 0; i < ncell; i++) total += hist[i];
+            // bound k = first visiting position whose cumulative count reaches floor(total * k / count)
+            int64_t bound[2] = {0, ncell};
+            for (int e = 0; e < 2; e++) {
+                const int k = c.shard_rank + e;
+                if (k <= 0) { bound[e] = 0; continue; }
+                if (k >= c.shard_count) { bound[e] = ncell; continue; }
+                const int64_t target = (total / c.shard_count) * k + ((total % c.shard_count) * k) / c.shard_count;
+                int64_t cum = 0, pos = 0;
+                for (; pos < ncell; pos++) {
+                    if (cum >= target) break;
+                    cum += hist[c.leaf_order == 0 ? ncell - 1 - pos : pos];
+                }
+                bound[e] = pos;
+            }
+            pos_lo = bound[0]; pos_hi = bound[1];
+        }
+        h->shard_pos_lo = pos_lo; h->shard_pos_hi = pos_hi;
+        CK(h->flags64.reserve((n + 1) * sizeof(int64_t)));
+        CK(h->ex.reserve((n + 1) * sizeof(int64_t)));
+        CK(h->scan_tmp.reserve(scan_tmp_bytes(n)));
+        if (h->shard_cb == 0) {
+            CK(cudaMemsetAsync(h->flags64.p, 0, n * sizeof(int64_t), st));
+            if (pos_hi > pos_lo) launch_shard_select(h->keys.as<uint64_t>(), n, depth, 0, c.leaf_order, 0, 1, h->flags64.as<int64_t>(), st);
+        } else {
+            launch_shard_select(h->keys.as<uint64_t>(), n, depth, cb, c.leaf_order, pos_lo, pos_hi, h->flags64.as<int64_t>(), st);
+        }
+        launch_exclusive_scan_i64(h->flags64.as<int64_t>(), h->ex.as<int64_t>(), n, h->scan_tmp.p, st);
+        int64_t n_sel = 0;
+        CK(cudaMemcpyAsync(&n_sel, h->ex.as<int64_t>() + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(h->sel_cloud.reserve(std::max<int64_t>(n_sel, 1) * GPC_POINT_BYTES));
+        CK(h->sel_idx.reserve(std::max<int64_t>(n_sel, 1) * sizeof(int32_t)));
+        launch_shard_compact(cloud, h->ex.as<int64_t>(), n, h->sel_cloud.as<uint8_t>(), h->sel_idx.as<int32_t>(), st);
+        h->n_sel = n_sel;
+        h->shard_mode = true;
+        cloud = h->sel_cloud.as<uint8_t>();
+        n = n_sel;
+        if (n == 0) {
+            CK(cudaMemsetAsync(h->off.p, 0, sizeof(int64_t), st));
+            h->have_binning = h->have_frames = true;
+            return GPC_OK;
+        }
+    }
     // ---- keys + Morton sort ----
     CK(h->keys.reserve(n * sizeof(uint64_t)));
     CK(h->keys2.reserve(n * sizeof(uint64_t)));
@@ -630,7 +708,7 @@ void gpc_destroy(gpc_handle* h) {
                       &h->dumpC, &h->dumpQ, &h->queue0, &h->queue1, &h->hand0, &h->hand1, &h->spill, &h->qcount, &h->kstats, &h->bv_off, &h->palpha, &h->pb1, &h->pb2, &h->pidx, &h->perm_rgb, &h->fcr, &h->fcg, &h->fcb, &h->r_nbv, &h->r_flags,
                       &h->r_alpha0, &h->r_alpha1, &h->r_alpha2, &h->r_b1, &h->r_b2, &h->r_bidx, &h->kstats_rgb, &h->nonempty, &h->slot, &h->out32,
                       &h->heights, &h->quat, &h->mean, &h->rgbmean, &h->Rm, &h->center, &h->code, &h->ncand, &h->owner,
-                      &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->lat_state, &h->ev_in, &h->ev_out, &h->size_ids, &h->size_hist, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
+                      &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->lat_state, &h->ev_in, &h->ev_out, &h->size_ids, &h->size_hist, &h->sel_cloud, &h->sel_idx, &h->coarse_hist, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
                       &h->ovals2, &h->sort_tmp, &h->flags64, &h->ex, &h->leaf_of, &h->leaf_start, &h->leaf_code_a, &h->spt,
                       &h->nbr, &h->nnbr, &h->center_a, &h->Rm_a, &h->ncand_a, &h->pt0, &h->pt1, &h->pt2, &h->hbuf, &h->rgb, &h->leaf_sums};
     for (DevBuf* b : bufs) b->release();
@@ -656,6 +734,7 @@ int gpc_set_rand_offset(gpc_handle* h, uint64_t offset) {
 int gpc_fit_patches(gpc_handle* h, int64_t P, const int64_t* off, const double* x1, const double* x2, const double* y) {
     if (!h || P < 0 || !off) return GPC_ERR_INVALID;
     CK(cudaSetDevice(h->cfg.device));
+    h->shard_mode = false;
     if (off[0] != 0) return fail(h, GPC_ERR_INVALID, "off[0] must be 0");
     for (int64_t p = 0; p < P; p++)
         if (off[p + 1] < off[p] || off[p + 1] - off[p] > 0x7fffffff) return fail(h, GPC_ERR_INVALID, "offsets must be non-decreasing");
@@ -748,6 +827,99 @@ int gpc_compress(gpc_handle* h, const void* cloud, int64_t n) {
     return GPC_OK;
 }
 
+int gpc_compress_shard_begin(gpc_handle* h, const void* cloud, int64_t n, int64_t* owned_patches, uint64_t* owned_draws) {
+    if (!h || n < 0 || !owned_patches || !owned_draws) return GPC_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    reset_stats(h);
+    StageTimer tm(h);
+    size_t tA = tm.mark();
+    if (cloud) {
+        CK(h->cloud.reserve(std::max<int64_t>(n, 1) * GPC_POINT_BYTES));
+        if (n > 0) CK(cudaMemcpyAsync(h->cloud.p, cloud, n * GPC_POINT_BYTES, cudaMemcpyHostToDevice, h->stream));
+        h->n_in = n;
+        h->have_cloud = true;
+    } else if (!h->have_cloud) {
+        return fail(h, GPC_ERR_STATE, "gpc_compress_shard_begin without a cloud: pass one or call gpc_upload_cloud first");
+    }
+    size_t tB = tm.mark();
+    tm.span(&h->stats.ms_h2d, tA, tB);
+    int rc = run_binning(h, tm, true);
+    if (rc) return rc;
+    h->shard_mode = true;
+    h->own_lo = h->own_hi = 0;
+    h->draws_owned = 0;
+    const gpc_config& c = h->cfg;
+    cudaStream_t st = h->stream;
+    const int64_t P = h->n_patches;
+    if (P > 0) {
+        CK(h->small.reserve(256));
+        int64_t* d_rng = h->small.as<int64_t>() + 20;
+        launch_owned_range(h->code.as<uint64_t>(), P, (int)h->depth, h->shard_cb, c.leaf_order, h->shard_pos_lo, h->shard_pos_hi, d_rng, st);
+        int64_t rng[2] = {0, 0};
+        CK(cudaMemcpyAsync(rng, d_rng, sizeof(rng), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        h->own_lo = rng[0]; h->own_hi = rng[1];
+        const int mult = c.shuffle ? (c.rgb_rand ? 2 : 1) : 0;
+        CK(h->draws.reserve((P + 1) * sizeof(int64_t)));
+        CK(h->roff.reserve((P + 2) * sizeof(int64_t)));
+        CK(h->scan_tmp.reserve(scan_tmp_bytes(P + 1)));
+        int64_t* d_plan = h->small.as<int64_t>() + 8;
+        launch_fit_plan(h->off.as<int64_t>(), P, mult, c.shard_rank, c.shard_count, h->own_lo, h->own_hi, h->draws.as<int64_t>(),
+                        h->roff.as<int64_t>(), h->scan_tmp.p, d_plan, st);
+        int64_t plan[9];
+        CK(cudaMemcpyAsync(plan, d_plan, sizeof(plan), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        h->draws_owned = (uint64_t)(plan[6] - plan[5]);
+    }
+    *owned_patches = h->own_hi - h->own_lo;
+    *owned_draws = h->draws_owned;
+    size_t tC = tm.mark();
+    tm.span(&h->stats.ms_total, tA, tC);
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    tm.resolve();
+    h->stats.kernel_launches = g_launches;
+    return GPC_OK;
+}
+
+int gpc_compress_shard_finish(gpc_handle* h, int64_t patches_before, uint64_t draws_before, int64_t patches_total, uint64_t draws_total) {
+    if (!h || patches_before < 0 || patches_total < patches_before) return GPC_ERR_INVALID;
+    if (!h->shard_mode || !h->have_binning) return fail(h, GPC_ERR_STATE, "gpc_compress_shard_finish without gpc_compress_shard_begin");
+    CK(cudaSetDevice(h->cfg.device));
+    StageTimer tm(h);
+    size_t tA = tm.mark();
+    h->gshift = patches_before - h->own_lo;
+    h->patches_total = patches_total;
+    h->draws_before = draws_before;
+    h->draws_total = draws_total;
+    int rc;
+    if (h->n_patches == 0) {
+        h->patch_lo = h->patch_hi = 0;
+        h->s_begin = h->s_count = 0;
+        h->have_fit = true;
+        h->n_bv_total = 0;
+        h->params_packed = false;
+        h->have_rgb = false;
+        CK(h->nbv.reserve(sizeof(int32_t)));
+        h->rand_offset += draws_total;
+    } else if ((rc = run_fit(h, tm))) {
+        return rc;
+    }
+    size_t tC = tm.mark();
+    {   // the two phases add up in ms_total
+        float before = h->stats.ms_total;
+        h->stats.ms_total = 0;
+        tm.span(&h->stats.ms_total, tA, tC);
+        if (h->n_patches > 0 && (rc = read_fit_stats(h))) return rc;
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaGetLastError());
+        tm.resolve();
+        h->stats.ms_total += before;
+    }
+    h->stats.kernel_launches = g_launches;
+    return GPC_OK;
+}
+
 int gpc_decompress_resident(gpc_handle* h, int64_t* n_out) {
     if (!h) return GPC_ERR_INVALID;
     CK(cudaSetDevice(h->cfg.device));
@@ -805,6 +977,7 @@ static int evaluate_impl(gpc_handle* h, int64_t op0, int64_t P, const int64_t* o
 int gpc_predict(gpc_handle* h, int64_t patch, const double* X, int64_t m, double* f, double* sigma) {
     if (!h || m < 0 || (m > 0 && (!X || !f))) return GPC_ERR_INVALID;
     if (!h->have_fit) return fail(h, GPC_ERR_STATE, "predict before fit");
+    if (h->shard_mode) patch -= h->gshift;  // global -> local index of the sharded binning
     if (patch < h->patch_lo || patch >= h->patch_hi) return fail(h, GPC_ERR_INVALID, "patch outside this shard");
     if (sigma && !h->cfg.keep_state) return fail(h, GPC_ERR_INVALID, "sigma needs gpc_config.keep_state");
     CK(cudaSetDevice(h->cfg.device));
@@ -911,9 +1084,10 @@ int gpc_get_sizes(gpc_handle* h, gpc_sizes* s) {
         int rc = gpc_get_params(h, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
         if (rc) return rc;
     }
-    s->n_in = h->n_in; s->n_patches = h->n_patches; s->n_claimed = h->n_claimed;
+    s->n_in = h->n_in; s->n_patches = h->shard_mode ? h->patches_total : h->n_patches; s->n_claimed = h->n_claimed;
     s->n_bv_total = h->have_fit ? h->n_bv_total : 0;
-    s->patch_lo = h->patch_lo; s->patch_hi = h->patch_hi; s->n_decoded = h->n_decoded;
+    const int64_t gs = h->shard_mode ? h->gshift : 0;
+    s->patch_lo = h->patch_lo + gs; s->patch_hi = h->patch_hi + gs; s->n_decoded = h->n_decoded;
     s->rand_offset = h->rand_offset;
     for (int a = 0; a < 3; a++) s->lattice_min[a] = h->lattice_min[a];
     s->depth = h->depth; s->pad = 0;
@@ -1019,6 +1193,7 @@ int gpc_get_params_rgb(gpc_handle* h, int32_t* nbv, int64_t* bv_off, int32_t* bv
 int gpc_get_state(gpc_handle* h, int64_t patch, double* C, double* Q) {
     if (!h) return GPC_ERR_INVALID;
     if (!h->have_fit || !h->cfg.keep_state) return fail(h, GPC_ERR_STATE, "gpc_get_state needs a fit made with keep_state");
+    if (h->shard_mode) patch -= h->gshift;
     if (patch < h->patch_lo || patch >= h->patch_hi) return fail(h, GPC_ERR_INVALID, "patch outside this shard");
     CK(cudaSetDevice(h->cfg.device));
     const int64_t op = patch - h->patch_lo;
@@ -1034,6 +1209,7 @@ int gpc_set_params(gpc_handle* h, int64_t P, const int32_t* nbv, const double* b
                    const double* quat4, const double* mean3, const double* rgbmean3) {
     if (!h || P < 0 || !nbv || !bv1 || !bv2 || !alpha) return GPC_ERR_INVALID;
     CK(cudaSetDevice(h->cfg.device));
+    h->shard_mode = false;
     const int cap = h->cfg.capacity;
     std::vector<int64_t> off(P + 1, 0);
     for (int64_t p = 0; p < P; p++) {
@@ -1086,6 +1262,7 @@ int gpc_set_params(gpc_handle* h, int64_t P, const int32_t* nbv, const double* b
 int gpc_get_patches(gpc_handle* h, uint64_t* code, float* center3, int32_t* n_candidates, double* R9, double* quat4,
                     double* mean3, double* rgbmean3, int64_t* patch_off) {
     if (!h) return GPC_ERR_INVALID;
+    if (h->shard_mode) return fail(h, GPC_ERR_STATE, "patch-level arrays are local to the shard after gpc_compress_shard_*: use gpc_get_params / gpc_decompress");
     CK(cudaSetDevice(h->cfg.device));
     const int64_t P = h->n_patches;
     if (patch_off) {
@@ -1110,6 +1287,7 @@ int gpc_get_patches(gpc_handle* h, uint64_t* code, float* center3, int32_t* n_ca
 
 int gpc_get_assignment(gpc_handle* h, int32_t* owner, int32_t* stream_index, double* x1, double* x2, double* y, int32_t* perm) {
     if (!h) return GPC_ERR_INVALID;
+    if (h->shard_mode) return fail(h, GPC_ERR_STATE, "point-level arrays are local to the shard after gpc_compress_shard_*");
     CK(cudaSetDevice(h->cfg.device));
     const int64_t S = h->n_claimed;
     if (owner || stream_index) {
@@ -1314,6 +1492,7 @@ int gpc_load(gpc_handle* h, const char* path) {
 int gpc_debug_peak(gpc_handle* h, int kind, double* value) {
     if (!h || !value || kind < 0 || kind > 2) return GPC_ERR_INVALID;
     CK(cudaSetDevice(h->cfg.device));
+    h->shard_mode = false;
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
     CK(measure_peak(kind, sms, h->stream, value));

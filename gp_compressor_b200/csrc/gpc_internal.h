@@ -51,6 +51,13 @@ struct LatticeState {        // device-resident state of the lattice replay
 };
 // searches points [st->start, n) (tiles_hint = how many points can still matter) and grows the box for the first violator
 void launch_lattice_step(const uint8_t* cloud, int64_t n, int64_t tiles_hint, LatticeState* st, cudaStream_t s);
+// sharded binning (k_binning.cu): coarse key histogram, halo selection, compaction, owned patch range
+void launch_coarse_hist(const uint64_t* keys, int64_t n, int depth, int cb, unsigned int* hist, cudaStream_t s);
+void launch_shard_select(const uint64_t* keys, int64_t n, int depth, int cb, int leaf_order, int64_t pos_lo, int64_t pos_hi,
+                         int64_t* flags, cudaStream_t s);
+void launch_shard_compact(const uint8_t* cloud, const int64_t* ex, int64_t n, uint8_t* sel_cloud, int32_t* sel_idx, cudaStream_t s);
+void launch_owned_range(const uint64_t* code, int64_t P, int depth, int cb, int leaf_order, int64_t pos_lo, int64_t pos_hi, int64_t* out2,
+                        cudaStream_t s);
 void launch_point_keys(const uint8_t* cloud, int64_t n, const LatticeDev& lat, uint64_t* keys, uint32_t* vals, cudaStream_t s);
 void launch_count_valid(const uint64_t* sorted_keys, int64_t n, uint32_t depth, unsigned long long* n_valid, cudaStream_t s);
 size_t radix_sort_tmp_bytes(int64_t n);
@@ -98,8 +105,8 @@ void launch_exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, void*
 // draws[p] + exclusive scan roff[0..P] + plan9 = { n_claimed, lo, hi, off[lo], off[hi], roff[lo], roff[hi], roff[P], max n_p }
 // ids[0..n): patches lo..lo+n-1 by decreasing point count; hist1024: 1024 ints of scratch
 void launch_size_order(const int64_t* off, int64_t lo, int64_t n, int32_t* hist1024, int32_t* ids, cudaStream_t s);
-void launch_fit_plan(const int64_t* off, int64_t n_patches, int mult, int rank, int count, int64_t* draws, int64_t* roff, void* scan_tmp,
-                     int64_t* plan9, cudaStream_t s);
+void launch_fit_plan(const int64_t* off, int64_t n_patches, int mult, int rank, int count, int64_t fixed_lo, int64_t fixed_hi,
+                     int64_t* draws, int64_t* roff, void* scan_tmp, int64_t* plan9, cudaStream_t s);
 // perm (patch-local) for every patch; rnd holds the stream starting at the handle's offset
 struct ShuffleGatherArgs {
     const int64_t* off;          // patch offsets of this shard's first patch onwards (n_patches + 1)

@@ -568,6 +568,103 @@ void launch_lattice_step(const uint8_t* cloud, int64_t n, int64_t tiles_hint, La
     g_launches += 2;
 }
 
+// ---- sharded binning (strong scaling of one cloud) -------------------------------------------------
+// Every rank holds the whole cloud.  The Morton keys of all points are cut into `count` contiguous ranges of the
+// visiting order (aligned to coarse octree cells of side >= 8 voxels, chosen from a coarse key histogram that every
+// rank computes identically); a rank bins only the points within HALO = 3 voxels of its own range: a patch's claimed
+// set depends on the frames of the leaves within two rings, and those on the points within three.
+constexpr int SHARD_HALO = 3;
+
+__global__ void __launch_bounds__(256) coarse_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int depth3, int cb,
+                                                          unsigned int* __restrict__ hist) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t k = keys[i];
+    if (k >> depth3) return;  // non-finite point
+    atomicAdd(hist + (unsigned)(k >> (depth3 - cb)), 1u);
+}
+
+// flags[i] = 1 if point i lies within SHARD_HALO voxels of a coarse cell whose visiting position is in [pos_lo, pos_hi)
+__global__ void __launch_bounds__(256) shard_select_kernel(const uint64_t* __restrict__ keys, int64_t n, int depth, int cb,
+                                                           int leaf_order, int64_t pos_lo, int64_t pos_hi,
+                                                           int64_t* __restrict__ flags) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t k = keys[i];
+    int sel = 0;
+    if (!(k >> (3 * depth))) {
+        const int cshift = depth - cb / 3;  // voxels per coarse cell side = 2^cshift >= 8 > 2 * HALO
+        const int64_t kmax = (1ll << depth) - 1, ncell = 1ll << cb;
+        const int64_t vx = compact3(k >> 2), vy = compact3(k >> 1), vz = compact3(k);
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            int64_t x = vx + ((c & 4) ? SHARD_HALO : -SHARD_HALO), y = vy + ((c & 2) ? SHARD_HALO : -SHARD_HALO),
+                    z = vz + ((c & 1) ? SHARD_HALO : -SHARD_HALO);
+            x = x < 0 ? 0 : (x > kmax ? kmax : x);
+            y = y < 0 ? 0 : (y > kmax ? kmax : y);
+            z = z < 0 ? 0 : (z > kmax ? kmax : z);
+            const int64_t cell = (int64_t)morton((uint32_t)(x >> cshift), (uint32_t)(y >> cshift), (uint32_t)(z >> cshift));
+            const int64_t pos = leaf_order == 0 ? ncell - 1 - cell : cell;
+            sel |= (pos >= pos_lo && pos < pos_hi) ? 1 : 0;
+        }
+    }
+    flags[i] = sel;
+}
+
+__global__ void __launch_bounds__(256) shard_compact_kernel(const uint8_t* __restrict__ cloud, const int64_t* __restrict__ ex, int64_t n,
+                                                            uint8_t* __restrict__ sel_cloud, int32_t* __restrict__ sel_idx) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t d = ex[i];
+    if (ex[i + 1] == d) return;
+    const float4* src = reinterpret_cast<const float4*>(cloud + i * GPC_POINT_BYTES);
+    float4* dst = reinterpret_cast<float4*>(sel_cloud + d * GPC_POINT_BYTES);
+    dst[0] = src[0];
+    dst[1] = src[1];
+    sel_idx[d] = (int32_t)i;
+}
+
+// patches are in visiting order, so the visiting position of their coarse cell is non-decreasing:
+// out[0] = first patch with position >= pos_lo, out[1] = first with position >= pos_hi
+__global__ void owned_range_kernel(const uint64_t* __restrict__ code, int64_t P, int depth3, int cb, int leaf_order, int64_t pos_lo,
+                                   int64_t pos_hi, int64_t* __restrict__ out) {
+    const int64_t ncell = 1ll << cb;
+    for (int e = 0; e < 2; e++) {
+        const int64_t target = e ? pos_hi : pos_lo;
+        int64_t lo = 0, hi = P;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            const int64_t cell = (int64_t)(code[mid] >> (depth3 - cb));
+            const int64_t pos = leaf_order == 0 ? ncell - 1 - cell : cell;
+            if (pos >= target) hi = mid; else lo = mid + 1;
+        }
+        out[e] = lo;
+    }
+}
+
+void launch_coarse_hist(const uint64_t* keys, int64_t n, int depth, int cb, unsigned int* hist, cudaStream_t s) {
+    cudaMemsetAsync(hist, 0, ((size_t)1 << cb) * sizeof(unsigned int), s);
+    if (n <= 0) return;
+    coarse_hist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(keys, n, 3 * depth, cb, hist);
+    g_launches++;
+}
+void launch_shard_select(const uint64_t* keys, int64_t n, int depth, int cb, int leaf_order, int64_t pos_lo, int64_t pos_hi,
+                         int64_t* flags, cudaStream_t s) {
+    if (n <= 0) return;
+    shard_select_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(keys, n, depth, cb, leaf_order, pos_lo, pos_hi, flags);
+    g_launches++;
+}
+void launch_shard_compact(const uint8_t* cloud, const int64_t* ex, int64_t n, uint8_t* sel_cloud, int32_t* sel_idx, cudaStream_t s) {
+    if (n <= 0) return;
+    shard_compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cloud, ex, n, sel_cloud, sel_idx);
+    g_launches++;
+}
+void launch_owned_range(const uint64_t* code, int64_t P, int depth, int cb, int leaf_order, int64_t pos_lo, int64_t pos_hi, int64_t* out2,
+                        cudaStream_t s) {
+    owned_range_kernel<<<1, 1, 0, s>>>(code, P, 3 * depth, cb, leaf_order, pos_lo, pos_hi, out2);
+    g_launches++;
+}
+
 void launch_point_keys(const uint8_t* cloud, int64_t n, const LatticeDev& lat, uint64_t* keys, uint32_t* vals, cudaStream_t s) {
     if (n <= 0) return;
     point_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cloud, n, lat, keys, vals);

@@ -125,10 +125,11 @@ __global__ void patch_draws_kernel(const int64_t* __restrict__ off, int64_t n_pa
 // plan = { n_claimed, lo, hi, off[lo], off[hi], roff[lo], roff[hi], roff[P] }.  Same rule as gpc_shard_range:
 // bound k = first p with off[p] >= floor(total * k / count).
 __global__ void fit_plan_kernel(const int64_t* __restrict__ off, const int64_t* __restrict__ roff, int64_t P, int rank, int count,
-                                int64_t* __restrict__ plan) {
+                                int64_t fixed_lo, int64_t fixed_hi, int64_t* __restrict__ plan) {
     const int64_t total = off[P];
     int64_t b[2];
     for (int e = 0; e < 2; e++) {
+        if (fixed_lo >= 0) { b[e] = e ? fixed_hi : fixed_lo; continue; }  // sharded binning: the owned range is given
         const int k = rank + e;
         if (k <= 0) { b[e] = 0; continue; }
         if (k >= count) { b[e] = P; continue; }
@@ -144,8 +145,8 @@ __global__ void fit_plan_kernel(const int64_t* __restrict__ off, const int64_t* 
     plan[5] = roff[b[0]]; plan[6] = roff[b[1]]; plan[7] = roff[P];
 }
 
-void launch_fit_plan(const int64_t* off, int64_t n_patches, int mult, int rank, int count, int64_t* draws, int64_t* roff, void* scan_tmp,
-                     int64_t* plan9, cudaStream_t s) {
+void launch_fit_plan(const int64_t* off, int64_t n_patches, int mult, int rank, int count, int64_t fixed_lo, int64_t fixed_hi,
+                     int64_t* draws, int64_t* roff, void* scan_tmp, int64_t* plan9, cudaStream_t s) {
     cudaMemsetAsync(plan9 + 8, 0, sizeof(int64_t), s);
     if (n_patches > 0) {
         patch_draws_kernel<<<(unsigned)((n_patches + 255) / 256), 256, 0, s>>>(off, n_patches, mult, draws,
@@ -153,7 +154,7 @@ void launch_fit_plan(const int64_t* off, int64_t n_patches, int mult, int rank, 
         g_launches++;
     }
     launch_exclusive_scan_i64(draws, roff, n_patches, scan_tmp, s);
-    fit_plan_kernel<<<1, 1, 0, s>>>(off, roff, n_patches, rank, count, plan9);
+    fit_plan_kernel<<<1, 1, 0, s>>>(off, roff, n_patches, rank, count, fixed_lo, fixed_hi, plan9);
     g_launches++;
 }
 

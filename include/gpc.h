@@ -104,6 +104,21 @@ int gpc_compress_resident(gpc_handle* h);
 int gpc_fit_patches(gpc_handle* h, int64_t n_patches, const int64_t* off,
                     const double* x1, const double* x2, const double* y);
 
+/* Strong scaling of ONE cloud over several GPUs (replaces nothing in the reference, which is
+ * single-threaded): every rank passes the same cloud (or NULL to use the cloud of gpc_upload_cloud) with
+ * gpc_config.shard_rank / shard_count set.  begin replays the lattice on the whole cloud, cuts the visiting order
+ * (gp_compressor.cpp:204-205) into shard_count ranges of coarse octree cells -- identically on every rank, from a
+ * coarse Morton-key histogram -- and bins only the points within three voxels of the rank's own range (a patch's
+ * claimed set depends on the leaf frames within two rings and those on the points within three), so the sort /
+ * rotation / claim stages shrink with the shard count.  It returns how many patches and rand() draws the rank owns.
+ * The ranks then all-gather those two integers (the one exchange of the path) and call finish with the sums over
+ * the earlier ranks and over all ranks; finish shuffles and fits the owned patches.  Afterwards gpc_get_sizes
+ * reports global patch indices; gpc_get_params / gpc_get_params_rgb / gpc_decompress / gpc_save cover the owned range,
+ * and concatenating the ranks' outputs in rank order equals the single-GPU result bit for bit. */
+int gpc_compress_shard_begin(gpc_handle* h, const void* cloud, int64_t n, int64_t* owned_patches, uint64_t* owned_draws);
+int gpc_compress_shard_finish(gpc_handle* h, int64_t patches_before, uint64_t draws_before, int64_t patches_total,
+                              uint64_t draws_total);
+
 /* ---- decompress: gp_compressor::load_compressed, gp_compressor.cpp:267-386 ------------
  * Writes sz*sz points per non-empty patch, patches in gp_index order.  out may be NULL
  * (device-only run, result stays in HBM).  capacity_points guards the host buffer. */
