@@ -109,6 +109,13 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def shard_prefix(all_counts, rank):
+    """The arguments of gpc_compress_shard_finish from the all-gathered (owned_patches, owned_draws) pairs of every rank
+    (rank order = visiting order): (patches_before, draws_before, patches_total, draws_total).  Host arithmetic only."""
+    a = np.asarray(all_counts, dtype=np.int64).reshape(-1, 2)
+    return int(a[:rank, 0].sum()), int(a[:rank, 1].sum()), int(a[:, 0].sum()), int(a[:, 1].sum())
+
+
 def shard_range(off, rank, count):
     """Patches [lo, hi) owned by shard `rank` of `count` (host arithmetic only, no GPU needed)."""
     off = np.ascontiguousarray(off, dtype=np.int64)

@@ -46,8 +46,7 @@ struct gpc_handle {
     bool shard_mode = false;
     int64_t own_lo = 0, own_hi = 0, gshift = 0, patches_total = 0, n_sel = 0;
     uint64_t draws_before = 0, draws_total = 0, draws_owned = 0;
-    int shard_cb = 0;
-    int64_t shard_pos_lo = 0, shard_pos_hi = 0;
+
     // binning scratch
     DevBuf keys, keys2, vals, vals2, ovals, ovals2, sort_tmp, flags64, ex, leaf_of, leaf_start, leaf_code_a, spt, nbr, nnbr,
         center_a, Rm_a, ncand_a, pt0, pt1, pt2, hbuf, rgb, leaf_sums;
@@ -461,53 +460,29 @@ int run_binning(gpc_handle* h, StageTimer& tm, bool sharded = false) {
     }
     const LatticeDev lat = Lh.lat;
     if (sharded) {
-        // ---- the rank's range of the visiting order, from a coarse key histogram of the WHOLE cloud (identical on every
-        // rank: integer counts), then the points within the halo of that range, compacted into a private cloud ----
+        // ---- the rank's key range: quantiles of a sorted key sample of the WHOLE cloud (identical on every rank), then
+        // the points within the halo of that range, compacted into a private cloud.  No host round trip until n_sel. ----
         const int depth = (int)L.depth;
-        const int cb = std::min(15, 3 * (depth - 3));   // coarse cells of side >= 8 voxels
         CK(h->keys.reserve(n * sizeof(uint64_t)));
         CK(h->vals.reserve(n * sizeof(uint32_t)));
         launch_point_keys(cloud, n, lat, h->keys.as<uint64_t>(), h->vals.as<uint32_t>(), st);
-        int64_t pos_lo = 0, pos_hi = 0;
-        if (cb < 3) {  // lattice too small to cut: rank 0 takes everything
-            h->shard_cb = 0;
-            pos_lo = 0; pos_hi = (c.shard_rank == 0) ? 1 : 0;
-        } else {
-            h->shard_cb = cb;
-            const int64_t ncell = 1ll << cb;
-            CK(h->coarse_hist.reserve(ncell * sizeof(unsigned int)));
-            launch_coarse_hist(h->keys.as<uint64_t>(), n, depth, cb, h->coarse_hist.as<unsigned int>(), st);
-            std::vector<unsigned int> hist(ncell);
-            CK(cudaMemcpyAsync(hist.data(), h->coarse_hist.p, ncell * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            int64_t total = 0;
-            for (int64_t i = 0; i < ncell; i++) total += hist[i];
-            // bound k = first visiting position whose cumulative count reaches floor(total * k / count)
-            int64_t bound[2] = {0, ncell};
-            for (int e = 0; e < 2; e++) {
-                const int k = c.shard_rank + e;
-                if (k <= 0) { bound[e] = 0; continue; }
-                if (k >= c.shard_count) { bound[e] = ncell; continue; }
-                const int64_t target = (total / c.shard_count) * k + ((total % c.shard_count) * k) / c.shard_count;
-                int64_t cum = 0, pos = 0;
-                for (; pos < ncell; pos++) {
-                    if (cum >= target) break;
-                    cum += hist[c.leaf_order == 0 ? ncell - 1 - pos : pos];
-                }
-                bound[e] = pos;
-            }
-            pos_lo = bound[0]; pos_hi = bound[1];
-        }
-        h->shard_pos_lo = pos_lo; h->shard_pos_hi = pos_hi;
+        const int64_t stride = std::max<int64_t>(1, n >> 20);
+        const int64_t m = (n + stride - 1) / stride;
+        CK(h->coarse_hist.reserve((size_t)m * 2 * (sizeof(uint64_t) + sizeof(uint32_t)) + 64));
+        uint64_t* smp = h->coarse_hist.as<uint64_t>();
+        uint64_t* smp2 = smp + m;
+        uint32_t* dv = reinterpret_cast<uint32_t*>(smp2 + m);
+        uint32_t* dv2 = dv + m;
+        CK(h->sort_tmp.reserve(radix_sort_tmp_bytes(std::max(n, m))));
+        launch_shard_sample(h->keys.as<uint64_t>(), n, stride, m, smp, dv, st);
+        const int which_s = launch_radix_sort(smp, dv, smp2, dv2, m, 3 * depth + 1, h->sort_tmp.p, st);
+        CK(h->small.reserve(256));
+        uint64_t* d_range = h->small.as<uint64_t>() + 22;
+        launch_shard_splitters(which_s ? smp2 : smp, m, depth, c.shard_rank, c.shard_count, c.leaf_order, d_range, st);
         CK(h->flags64.reserve((n + 1) * sizeof(int64_t)));
         CK(h->ex.reserve((n + 1) * sizeof(int64_t)));
         CK(h->scan_tmp.reserve(scan_tmp_bytes(n)));
-        if (h->shard_cb == 0) {
-            CK(cudaMemsetAsync(h->flags64.p, 0, n * sizeof(int64_t), st));
-            if (pos_hi > pos_lo) launch_shard_select(h->keys.as<uint64_t>(), n, depth, 0, c.leaf_order, 0, 1, h->flags64.as<int64_t>(), st);
-        } else {
-            launch_shard_select(h->keys.as<uint64_t>(), n, depth, cb, c.leaf_order, pos_lo, pos_hi, h->flags64.as<int64_t>(), st);
-        }
+        launch_shard_select(h->keys.as<uint64_t>(), n, depth, d_range, h->flags64.as<int64_t>(), st);
         launch_exclusive_scan_i64(h->flags64.as<int64_t>(), h->ex.as<int64_t>(), n, h->scan_tmp.p, st);
         int64_t n_sel = 0;
         CK(cudaMemcpyAsync(&n_sel, h->ex.as<int64_t>() + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -854,7 +829,7 @@ int gpc_compress_shard_begin(gpc_handle* h, const void* cloud, int64_t n, int64_
     if (P > 0) {
         CK(h->small.reserve(256));
         int64_t* d_rng = h->small.as<int64_t>() + 20;
-        launch_owned_range(h->code.as<uint64_t>(), P, (int)h->depth, h->shard_cb, c.leaf_order, h->shard_pos_lo, h->shard_pos_hi, d_rng, st);
+        launch_owned_range(h->code.as<uint64_t>(), P, c.leaf_order, h->small.as<uint64_t>() + 22, d_rng, st);
         int64_t rng[2] = {0, 0};
         CK(cudaMemcpyAsync(rng, d_rng, sizeof(rng), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));

@@ -51,13 +51,13 @@ struct LatticeState {        // device-resident state of the lattice replay
 };
 // searches points [st->start, n) (tiles_hint = how many points can still matter) and grows the box for the first violator
 void launch_lattice_step(const uint8_t* cloud, int64_t n, int64_t tiles_hint, LatticeState* st, cudaStream_t s);
-// sharded binning (k_binning.cu): coarse key histogram, halo selection, compaction, owned patch range
-void launch_coarse_hist(const uint64_t* keys, int64_t n, int depth, int cb, unsigned int* hist, cudaStream_t s);
-void launch_shard_select(const uint64_t* keys, int64_t n, int depth, int cb, int leaf_order, int64_t pos_lo, int64_t pos_hi,
-                         int64_t* flags, cudaStream_t s);
+// sharded binning (k_binning.cu): key sample -> splitters -> halo selection -> compaction -> owned patch range
+void launch_shard_sample(const uint64_t* keys, int64_t n, int64_t stride, int64_t m, uint64_t* sample, uint32_t* dummy, cudaStream_t s);
+void launch_shard_splitters(const uint64_t* sorted, int64_t m, int depth, int rank, int count, int leaf_order, uint64_t* range2,
+                            cudaStream_t s);
+void launch_shard_select(const uint64_t* keys, int64_t n, int depth, const uint64_t* range2, int64_t* flags, cudaStream_t s);
 void launch_shard_compact(const uint8_t* cloud, const int64_t* ex, int64_t n, uint8_t* sel_cloud, int32_t* sel_idx, cudaStream_t s);
-void launch_owned_range(const uint64_t* code, int64_t P, int depth, int cb, int leaf_order, int64_t pos_lo, int64_t pos_hi, int64_t* out2,
-                        cudaStream_t s);
+void launch_owned_range(const uint64_t* code, int64_t P, int leaf_order, const uint64_t* range2, int64_t* out2, cudaStream_t s);
 void launch_point_keys(const uint8_t* cloud, int64_t n, const LatticeDev& lat, uint64_t* keys, uint32_t* vals, cudaStream_t s);
 void launch_count_valid(const uint64_t* sorted_keys, int64_t n, uint32_t depth, unsigned long long* n_valid, cudaStream_t s);
 size_t radix_sort_tmp_bytes(int64_t n);

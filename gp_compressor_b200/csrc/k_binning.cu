@@ -569,32 +569,53 @@ void launch_lattice_step(const uint8_t* cloud, int64_t n, int64_t tiles_hint, La
 }
 
 // ---- sharded binning (strong scaling of one cloud) -------------------------------------------------
-// Every rank holds the whole cloud.  The Morton keys of all points are cut into `count` contiguous ranges of the
-// visiting order (aligned to coarse octree cells of side >= 8 voxels, chosen from a coarse key histogram that every
-// rank computes identically); a rank bins only the points within HALO = 3 voxels of its own range: a patch's claimed
-// set depends on the frames of the leaves within two rings, and those on the points within three.
+// Every rank holds the whole cloud.  The Morton keys are cut into `count` contiguous ranges of about equal point counts
+// (splitters = quantiles of a sorted key sample, rounded down to blocks of 8 x 8 x 8 voxels; identical on every rank:
+// integer work on identical input); a rank bins only the points within HALO = 3 voxels of its own range: a patch's
+// claimed set depends on the frames of the leaves within two rings, and those on the points within three.
 constexpr int SHARD_HALO = 3;
+constexpr int SHARD_BLOCK_BITS = 9;   // 8^3 voxels: wider than the 7-voxel halo box, so its 8 corners meet every block it touches
 
-__global__ void __launch_bounds__(256) coarse_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int depth3, int cb,
-                                                          unsigned int* __restrict__ hist) {
+__global__ void __launch_bounds__(256) shard_sample_kernel(const uint64_t* __restrict__ keys, int64_t n, int64_t stride, int64_t m,
+                                                           uint64_t* __restrict__ sample, uint32_t* __restrict__ dummy) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint64_t k = keys[i];
-    if (k >> depth3) return;  // non-finite point
-    atomicAdd(hist + (unsigned)(k >> (depth3 - cb)), 1u);
+    if (i >= m) return;
+    sample[i] = keys[i * stride];
+    dummy[i] = 0u;
 }
 
-// flags[i] = 1 if point i lies within SHARD_HALO voxels of a coarse cell whose visiting position is in [pos_lo, pos_hi)
-__global__ void __launch_bounds__(256) shard_select_kernel(const uint64_t* __restrict__ keys, int64_t n, int depth, int cb,
-                                                           int leaf_order, int64_t pos_lo, int64_t pos_hi,
-                                                           int64_t* __restrict__ flags) {
+// range[0..1] = [klo, khi): the key range of `rank` in the visiting order (leaf_order 0 visits keys in descending order)
+__global__ void shard_splitters_kernel(const uint64_t* __restrict__ sorted, int64_t m, int depth3, int rank, int count, int leaf_order,
+                                       uint64_t* __restrict__ range) {
+    const uint64_t invalid = 1ull << depth3;
+    int64_t lo = 0, hi = m;  // number of finite samples
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (sorted[mid] < invalid) lo = mid + 1; else hi = mid;
+    }
+    const int64_t mv = lo;
+    const int ja = leaf_order == 0 ? count - 1 - rank : rank;   // ascending index of the rank's range
+    uint64_t k[2];
+    for (int e = 0; e < 2; e++) {
+        const int j = ja + e;
+        if (j <= 0) k[e] = 0;
+        else if (j >= count) k[e] = invalid;
+        else if (mv == 0) k[e] = invalid;
+        else k[e] = (sorted[(mv / count) * j + ((mv % count) * j) / count] >> SHARD_BLOCK_BITS) << SHARD_BLOCK_BITS;
+    }
+    range[0] = k[0];
+    range[1] = k[1] < k[0] ? k[0] : k[1];
+}
+
+// flags[i] = 1 if point i lies within SHARD_HALO voxels of a block of the rank's key range
+__global__ void __launch_bounds__(256) shard_select_kernel(const uint64_t* __restrict__ keys, int64_t n, int depth,
+                                                           const uint64_t* __restrict__ range, int64_t* __restrict__ flags) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint64_t k = keys[i];
+    const uint64_t k = keys[i], klo = range[0], khi = range[1];
     int sel = 0;
     if (!(k >> (3 * depth))) {
-        const int cshift = depth - cb / 3;  // voxels per coarse cell side = 2^cshift >= 8 > 2 * HALO
-        const int64_t kmax = (1ll << depth) - 1, ncell = 1ll << cb;
+        const int64_t kmax = (1ll << depth) - 1;
         const int64_t vx = compact3(k >> 2), vy = compact3(k >> 1), vz = compact3(k);
 #pragma unroll
         for (int c = 0; c < 8; c++) {
@@ -603,9 +624,8 @@ __global__ void __launch_bounds__(256) shard_select_kernel(const uint64_t* __res
             x = x < 0 ? 0 : (x > kmax ? kmax : x);
             y = y < 0 ? 0 : (y > kmax ? kmax : y);
             z = z < 0 ? 0 : (z > kmax ? kmax : z);
-            const int64_t cell = (int64_t)morton((uint32_t)(x >> cshift), (uint32_t)(y >> cshift), (uint32_t)(z >> cshift));
-            const int64_t pos = leaf_order == 0 ? ncell - 1 - cell : cell;
-            sel |= (pos >= pos_lo && pos < pos_hi) ? 1 : 0;
+            const uint64_t kc = morton((uint32_t)x, (uint32_t)y, (uint32_t)z);
+            sel |= (kc >= klo && kc < khi) ? 1 : 0;
         }
     }
     flags[i] = sel;
@@ -624,34 +644,36 @@ __global__ void __launch_bounds__(256) shard_compact_kernel(const uint8_t* __res
     sel_idx[d] = (int32_t)i;
 }
 
-// patches are in visiting order, so the visiting position of their coarse cell is non-decreasing:
-// out[0] = first patch with position >= pos_lo, out[1] = first with position >= pos_hi
-__global__ void owned_range_kernel(const uint64_t* __restrict__ code, int64_t P, int depth3, int cb, int leaf_order, int64_t pos_lo,
-                                   int64_t pos_hi, int64_t* __restrict__ out) {
-    const int64_t ncell = 1ll << cb;
+// patches are in visiting order: out[0] = first patch inside the key range, out[1] = first patch behind it
+__global__ void owned_range_kernel(const uint64_t* __restrict__ code, int64_t P, int leaf_order, const uint64_t* __restrict__ range,
+                                   int64_t* __restrict__ out) {
+    const uint64_t klo = range[0], khi = range[1];
     for (int e = 0; e < 2; e++) {
-        const int64_t target = e ? pos_hi : pos_lo;
         int64_t lo = 0, hi = P;
         while (lo < hi) {
             const int64_t mid = (lo + hi) >> 1;
-            const int64_t cell = (int64_t)(code[mid] >> (depth3 - cb));
-            const int64_t pos = leaf_order == 0 ? ncell - 1 - cell : cell;
-            if (pos >= target) hi = mid; else lo = mid + 1;
+            const uint64_t c = code[mid];
+            // ascending: before the range while c < klo (e = 0) / c < khi (e = 1); descending: while c >= khi / c >= klo
+            const bool before = leaf_order == 0 ? (e == 0 ? c >= khi : c >= klo) : (e == 0 ? c < klo : c < khi);
+            if (before) lo = mid + 1; else hi = mid;
         }
         out[e] = lo;
     }
 }
 
-void launch_coarse_hist(const uint64_t* keys, int64_t n, int depth, int cb, unsigned int* hist, cudaStream_t s) {
-    cudaMemsetAsync(hist, 0, ((size_t)1 << cb) * sizeof(unsigned int), s);
-    if (n <= 0) return;
-    coarse_hist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(keys, n, 3 * depth, cb, hist);
+void launch_shard_sample(const uint64_t* keys, int64_t n, int64_t stride, int64_t m, uint64_t* sample, uint32_t* dummy, cudaStream_t s) {
+    if (m <= 0) return;
+    shard_sample_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(keys, n, stride, m, sample, dummy);
     g_launches++;
 }
-void launch_shard_select(const uint64_t* keys, int64_t n, int depth, int cb, int leaf_order, int64_t pos_lo, int64_t pos_hi,
-                         int64_t* flags, cudaStream_t s) {
+void launch_shard_splitters(const uint64_t* sorted, int64_t m, int depth, int rank, int count, int leaf_order, uint64_t* range2,
+                            cudaStream_t s) {
+    shard_splitters_kernel<<<1, 1, 0, s>>>(sorted, m, 3 * depth, rank, count, leaf_order, range2);
+    g_launches++;
+}
+void launch_shard_select(const uint64_t* keys, int64_t n, int depth, const uint64_t* range2, int64_t* flags, cudaStream_t s) {
     if (n <= 0) return;
-    shard_select_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(keys, n, depth, cb, leaf_order, pos_lo, pos_hi, flags);
+    shard_select_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(keys, n, depth, range2, flags);
     g_launches++;
 }
 void launch_shard_compact(const uint8_t* cloud, const int64_t* ex, int64_t n, uint8_t* sel_cloud, int32_t* sel_idx, cudaStream_t s) {
@@ -659,9 +681,8 @@ void launch_shard_compact(const uint8_t* cloud, const int64_t* ex, int64_t n, ui
     shard_compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cloud, ex, n, sel_cloud, sel_idx);
     g_launches++;
 }
-void launch_owned_range(const uint64_t* code, int64_t P, int depth, int cb, int leaf_order, int64_t pos_lo, int64_t pos_hi, int64_t* out2,
-                        cudaStream_t s) {
-    owned_range_kernel<<<1, 1, 0, s>>>(code, P, 3 * depth, cb, leaf_order, pos_lo, pos_hi, out2);
+void launch_owned_range(const uint64_t* code, int64_t P, int leaf_order, const uint64_t* range2, int64_t* out2, cudaStream_t s) {
+    owned_range_kernel<<<1, 1, 0, s>>>(code, P, leaf_order, range2, out2);
     g_launches++;
 }
 

@@ -98,3 +98,40 @@ def test_bench_reference_arm_under_torchrun():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["n_gpus"] == 2
+
+
+def _prefix_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gp_compressor_b200 import binding
+    # what gpc_compress_shard_begin returns on each rank (owned patches, owned rand() draws); the one exchange of the path
+    mine = torch.tensor([[1000 + 37 * rank, 2 * (5000 + 11 * rank)]], dtype=torch.int64)
+    allc = [torch.zeros(1, 2, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(allc, mine)
+    pre = binding.shard_prefix(torch.cat(allc).numpy(), rank)
+    outs = [None] * world
+    dist.all_gather_object(outs, pre)
+    if rank == 0:
+        q.put(outs)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_binning_exchange_prefixes():
+    """Host logic of the sharded-binning compress at world_size 2 (gloo): after one all-gather of two integers every rank
+    knows the global index of its first patch, its window of the rand() stream and the totals."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 400) + 17
+    ps = [ctx.Process(target=_prefix_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    outs = q.get(timeout=120)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert outs[0] == (0, 0, 2037, 20022)
+    assert outs[1] == (1000, 10000, 2037, 20022)
