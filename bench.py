@@ -362,13 +362,17 @@ def main():
                 "traffic": None, "peak_source": "measured here: independent DFMA chains %.1f TFLOP/s, conflict-free LDS.128 %.1f TB/s (gpc_debug_peak)" % (fp64_peak / 1e12, smem_peak / 1e12), "stage_ms": stage_ms[dom],
                 "fp64_frac": f1, "smem_frac": f2, "mean_n": fit_stats["sum_n"] / max(1, fit_stats["n_add"] - fit_stats["n_first"])}
         if args.workload == "c2" and not args.points and not RGB:
-            # one `ncu --set full` capture of the same command (profiles/r1h_summary.md): bucket-0 warp kernel, per launch
-            roof["traffic"] = 158.2e6
-            roof["note"] = ("N ~ 10 under the reference hyper-parameters: the kernel is instruction-issue bound (ncu: 74 % issue-slot "
-                            "utilisation, 64 regs, 32 warps/SM, ~25 % of instructions are FP64 math), so neither roofline is the constraint; "
-                            "with capacity binding (--workload c2bind) the same kernels reach 0.23 of the LDS.128 roofline")
+            # one `ncu --set full` capture of the same command (profiles/r1k_sogp_half_and_fused.md): bucket-0 kernel, per launch
+            roof["traffic"] = 156.9e6
+            roof["ncu"] = {"sm__pipe_fp64_cycles_active_pct": 36.6, "smsp__issue_active_pct": 61.1, "warps_per_sm": 18.2,
+                           "warp_instructions_per_point": 227, "source": "profiles/r1k_sogp_half_and_fused.md (captured once, not live)"}
+            roof["note"] = ("achieved / frac are ALGORITHMIC bytes and flops over the live stage time.  N ~ 10 under the reference "
+                            "hyper-parameters: the bucket-0 kernel (two patches per warp) is bound by dependent-instruction latency at "
+                            "18 warps/SM (ncu: FP64 pipe 37 % busy, issue slots 61 %), so neither roofline is the constraint; with "
+                            "capacity binding the SOGP kernels reach 0.16-0.26 of the LDS.128 roofline (profiles/r1_sweeps.md)")
     elif dom == "ms_predict":
-        fl = n_dec * (37.0 * (sizes.n_bv_total / max(1, n_dec / (cfg["sz"] ** 2))) + 18)
+        npatch = max(1, n_dec / (cfg["sz"] ** 2))
+        fl = n_dec * (3.0 * (sizes.n_bv_total / npatch) + 36) + 2.0 * cfg["sz"] * sizes.n_bv_total * 37.0   # separable tables
         sec = stage_ms[dom] * 1e-3
         fp64_peak = h.debug_peak(0)
         roof = {"kernel": "predict_grid_kernel (K8)", "bound": "fp64", "achieved": fl / sec / 1e9, "peak": fp64_peak / 1e9, "unit": "GFLOP/s",
