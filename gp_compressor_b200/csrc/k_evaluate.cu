@@ -9,7 +9,7 @@
 // One CTA per patch, tiles of 32 query points.  Per tile: (1) K = p0 E, E = exp(cl |x - BV_i|^2) for the N x 32
 // pairs; (2) CK = C K as a register-tiled product (each thread: 4 rows x 4 points, or 1 x 4 for small N), C read
 // by columns from shared memory (from global memory when N^2 does not fit); (3) the six O(N) sums per point
-// (k'Ck, kdx'Ck, kdy'Ck, alpha'k, alpha'kdx, alpha'kdy) as canonical row4 dots, one warp per group of sums;
+// (k'Ck, kdx'Ck, kdy'Ck, alpha'k, alpha'kdx, alpha'kdy) as canonical row4 dots, one warp per pair of sums;
 // (4) the scalar epilogue of predict / likelihood / likelihood_dx.  Same operation order as oracle Sogp::evaluate.
 #include <algorithm>
 
@@ -22,23 +22,6 @@ namespace {
 
 constexpr int EV_T = 32;     // points per tile
 constexpr int EV_NT = 128;   // threads per CTA
-
-// canonical row4 over a strided column: sum_i a(i) * b(i), partial i & 3, (a0 + a1) + (a2 + a3)
-template <class FA, class FB>
-__device__ __forceinline__ double row4_fn(int n, FA a, FB b) {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int i = 0;
-    for (; i + 3 < n; i += 4) {
-        s0 = fma(a(i), b(i), s0);
-        s1 = fma(a(i + 1), b(i + 1), s1);
-        s2 = fma(a(i + 2), b(i + 2), s2);
-        s3 = fma(a(i + 3), b(i + 3), s3);
-    }
-    if (i < n) s0 = fma(a(i), b(i), s0);
-    if (i + 1 < n) s1 = fma(a(i + 1), b(i + 1), s1);
-    if (i + 2 < n) s2 = fma(a(i + 2), b(i + 2), s2);
-    return __dadd_rn(__dadd_rn(s0, s1), __dadd_rn(s2, s3));
-}
 
 template <int RPT, bool CSMEM>
 __global__ void __launch_bounds__(EV_NT) evaluate_kernel(EvalArgs a) {
@@ -131,22 +114,30 @@ __global__ void __launch_bounds__(EV_NT) evaluate_kernel(EvalArgs a) {
             }
         }
         __syncthreads();
-        // (3) the six sums, one warp per group
+        // (3) the six sums: warps 0-2 take a pair each (k'Ck + alpha'k, kdx'Ck + alpha'kdx, kdy'Ck + alpha'kdy), sharing
+        // the loads of their first factor; every sum is its own canonical row4
         {
             const int w = t >> 5, tt = t & 31;
             const double x1 = xs[tt], x2 = ys[tt];
-            auto kf = [&](int i) { return K[i * EV_T + tt]; };
-            auto ckf = [&](int i) { return CK[i * EV_T + tt]; };
-            auto alf = [&](int i) { return al[i]; };
-            auto kxf = [&](int i) { return __dmul_rn(__dmul_rn(c1, __dadd_rn(x1, -b1[i])), E[i * EV_T + tt]); };
-            auto kyf = [&](int i) { return __dmul_rn(__dmul_rn(c1, __dadd_rn(x2, -b2[i])), E[i * EV_T + tt]); };
-            if (w == 0) red[0 * EV_T + tt] = row4_fn(N, kf, ckf);
-            else if (w == 1) red[1 * EV_T + tt] = row4_fn(N, kxf, ckf);
-            else if (w == 2) red[2 * EV_T + tt] = row4_fn(N, kyf, ckf);
-            else {
-                red[3 * EV_T + tt] = row4_fn(N, alf, kf);
-                red[4 * EV_T + tt] = row4_fn(N, alf, kxf);
-                red[5 * EV_T + tt] = row4_fn(N, alf, kyf);
+            if (w < 3) {
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1_ = 0.0, b2_ = 0.0, b3 = 0.0;
+                auto fac = [&](int i) {
+                    if (w == 0) return K[i * EV_T + tt];
+                    const double d = (w == 1) ? __dadd_rn(x1, -b1[i]) : __dadd_rn(x2, -b2[i]);
+                    return __dmul_rn(__dmul_rn(c1, d), E[i * EV_T + tt]);
+                };
+                int i = 0;
+                for (; i + 3 < N; i += 4) {
+                    const double f0 = fac(i), f1 = fac(i + 1), f2 = fac(i + 2), f3 = fac(i + 3);
+                    a0 = fma(f0, CK[i * EV_T + tt], a0); a1 = fma(f1, CK[(i + 1) * EV_T + tt], a1);
+                    a2 = fma(f2, CK[(i + 2) * EV_T + tt], a2); a3 = fma(f3, CK[(i + 3) * EV_T + tt], a3);
+                    b0 = fma(al[i], f0, b0); b1_ = fma(al[i + 1], f1, b1_); b2_ = fma(al[i + 2], f2, b2_); b3 = fma(al[i + 3], f3, b3);
+                }
+                if (i < N) { const double f = fac(i); a0 = fma(f, CK[i * EV_T + tt], a0); b0 = fma(al[i], f, b0); }
+                if (i + 1 < N) { const double f = fac(i + 1); a1 = fma(f, CK[(i + 1) * EV_T + tt], a1); b1_ = fma(al[i + 1], f, b1_); }
+                if (i + 2 < N) { const double f = fac(i + 2); a2 = fma(f, CK[(i + 2) * EV_T + tt], a2); b2_ = fma(al[i + 2], f, b2_); }
+                red[w * EV_T + tt] = __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
+                red[(3 + w) * EV_T + tt] = __dadd_rn(__dadd_rn(b0, b1_), __dadd_rn(b2_, b3));
             }
         }
         __syncthreads();
