@@ -22,6 +22,8 @@
 // writes its complete state (N, next point, counters, alpha, BV, C, Q) to a hand-off slot and
 // queues the patch; the next bucket's kernel resumes from that state — no work is redone
 // and the arithmetic is the same in every bucket.
+#include <type_traits>
+
 #include "gpc_device.cuh"
 #include "gpc_internal.h"
 
@@ -868,8 +870,8 @@ struct Smem {
 // shared memory with the "first strict minimum" rule.  MODE 0: alpha_i^2 / (Q_ii + C_ii) (sparse_gp.hpp:213);
 // MODE 1: 1 / Q_ii with the exact shortcut "delete iff score_0 is not NaN and some score < 1e-9f" (:229-236).
 // Contains block barriers: must be reached by all threads.  Returns loc, or -1 when MODE 1 finds nothing to delete.
-template <int LD, int DOUT, int MODE>
-__device__ __forceinline__ int block_argmin(const Smem<LD, DOUT>& s, int N, int t, int lane) {
+template <int LD, int DOUT, int MODE, class S>
+__device__ __forceinline__ int block_argmin(const S& s, int N, int t, int lane) {
     double sc = 0.0;
     if (t < N) {
         const double qii = s.Q()[t * LD + t];
@@ -1002,8 +1004,8 @@ __device__ __forceinline__ void delete_bv(const Smem<LD, DOUT>& s, int& N, int l
 
 // delete_bv for any thread count (used by the rare paths of the fused kernel): the matrix update strides over elements.
 // The three divisions are done by warp 0 only and published through scal[4..6].
-template <int LD, int NT, int DOUT>
-__device__ __forceinline__ void delete_bv_any(const Smem<LD, DOUT>& s, int& N, int loc, int t) {
+template <int LD, int NT, int DOUT, class S>
+__device__ __forceinline__ void delete_bv_any(const S& s, int& N, int loc, int t) {
     const int L = N - 1, M = N - 1;
     const int lane_ = t & 31, w_ = t >> 5;
     double* const C = s.C();
@@ -1380,6 +1382,28 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
 // =====================================================================================
 enum { OP_NONE = 0, OP_SPARSE = 1, OP_FULL = 2, OP_FULL_DEL = 3 };
 
+// Smem<LD, 1> with the matrices elsewhere (bucket 4: C and Q in a per-CTA slice of global memory, vectors in shared memory)
+template <int LD>
+struct SmemSplit {
+    double* base;   // vectors, laid out as in Smem<LD, 1> behind its matrices
+    double* mat;    // C | Q
+    static constexpr int kVecDoubles = (8 + 1) * LD + 16;
+    __device__ __forceinline__ double* C() const { return mat; }
+    __device__ __forceinline__ double* Q() const { return mat + LD * LD; }
+    __device__ __forceinline__ double* alpha(int c = 0) const { return base + c * LD; }
+    __device__ __forceinline__ double* b1() const { return base + LD; }
+    __device__ __forceinline__ double* b2() const { return base + 2 * LD; }
+    __device__ __forceinline__ double* kv() const { return base + 3 * LD; }
+    __device__ __forceinline__ double* ck() const { return base + 4 * LD; }
+    __device__ __forceinline__ double* ev() const { return base + 5 * LD; }
+    __device__ __forceinline__ double* sv() const { return base + 6 * LD; }
+    __device__ __forceinline__ double* qsv() const { return base + 7 * LD; }
+    __device__ __forceinline__ double* qcv() const { return base + 8 * LD; }
+    __device__ __forceinline__ double* scv() const { return kv(); }
+    __device__ __forceinline__ double* scal() const { return base + 9 * LD; }
+    __device__ __forceinline__ int* bidx() const { return reinterpret_cast<int*>(base + kVecDoubles); }
+};
+
 template <int LD>
 struct FusedVecs {   // beyond Smem<LD, 1>: k of the next point, permuted update vectors
     double* base;
@@ -1474,14 +1498,20 @@ __device__ __forceinline__ void fused_pass(double* __restrict__ C, double* __res
 
 // LD: storage leading dimension (= 8 mod 16, see fused_pass); NT = 32 * ceil(LD / 8) threads; LD_IN: leading dimension
 // of the hand-off slots this bucket resumes; LD_OUT: of the slots it writes when a patch outgrows a.ld.
-template <int LD, int NT, int LD_IN, int LD_OUT>
+template <int LD, int NT, int LD_IN, int LD_OUT, bool SPILL>
 __global__ void __launch_bounds__(NT) sogp_fit_fused_kernel(SogpArgs a) {
     constexpr int DOUT = 1;
     static_assert(LD % 16 == 8 && NT * 8 >= 32 * LD && NT >= LD + 1, "thread mapping");
     extern __shared__ double smem_dyn[];
-    const Smem<LD, 1> s{smem_dyn};
-    // vectors after the Smem block and its bidx ints (LD ints = LD/2 doubles)
-    const FusedVecs<LD> fv{smem_dyn + Smem<LD, 1>::kDoubles + LD / 2};
+    // SPILL (bucket 4): C and Q live in a per-CTA slice of global memory (L2-resident); the fused pass touches every
+    // element once per point there too, and the block barriers order the accesses as they do for shared memory
+    typedef typename std::conditional<SPILL, SmemSplit<LD>, Smem<LD, 1>>::type State;
+    constexpr int kStateDoubles = SPILL ? SmemSplit<LD>::kVecDoubles : Smem<LD, 1>::kDoubles;   // what lives in shared memory
+    State s;
+    s.base = smem_dyn;
+    if constexpr (SPILL) s.mat = a.spill + (size_t)blockIdx.x * (2 * LD * LD);
+    // vectors after the state block and its bidx ints (LD ints = LD/2 doubles)
+    const FusedVecs<LD> fv{smem_dyn + kStateDoubles + LD / 2};
     double* const C = s.C();
     double* const Q = s.Q();
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -1493,7 +1523,9 @@ __global__ void __launch_bounds__(NT) sogp_fit_fused_kernel(SogpArgs a) {
         if (t == 0) { a.nbv[op_] = 0; a.flags[op_] = 0; }
         return;
     }
-    for (int i = t; i < Smem<LD, 1>::kDoubles + LD / 2 + FusedVecs<LD>::kDoubles; i += NT) smem_dyn[i] = 0.0;
+    for (int i = t; i < kStateDoubles + LD / 2 + FusedVecs<LD>::kDoubles; i += NT) smem_dyn[i] = 0.0;
+    if constexpr (SPILL)
+        for (int i = t; i < 2 * LD * LD; i += NT) s.mat[i] = 0.0;
     __syncthreads();
     for (int i = t; i < LD; i += NT) s.bidx()[i] = -1;
     __syncthreads();
@@ -1782,17 +1814,19 @@ __global__ void __launch_bounds__(NT) sogp_fit_fused_kernel(SogpArgs a) {
     }
 }
 
-template <int LD>
-constexpr size_t fused_smem_bytes() { return (size_t)(Smem<LD, 1>::kDoubles + LD / 2 + FusedVecs<LD>::kDoubles) * sizeof(double); }
+template <int LD, bool SPILL>
+constexpr size_t fused_smem_bytes() {
+    return (size_t)((SPILL ? SmemSplit<LD>::kVecDoubles : Smem<LD, 1>::kDoubles) + LD / 2 + FusedVecs<LD>::kDoubles) * sizeof(double);
+}
 
-template <int LD, int NT, int LD_IN, int LD_OUT>
+template <int LD, int NT, int LD_IN, int LD_OUT, bool SPILL = false>
 cudaError_t launch_fused_bucket(const SogpArgs& a, cudaStream_t st) {
-    constexpr size_t smem = fused_smem_bytes<LD>();
+    constexpr size_t smem = fused_smem_bytes<LD, SPILL>();
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(sogp_fit_fused_kernel<LD, NT, LD_IN, LD_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(sogp_fit_fused_kernel<LD, NT, LD_IN, LD_OUT, SPILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    sogp_fit_fused_kernel<LD, NT, LD_IN, LD_OUT><<<a.n_work, NT, smem, st>>>(a);
+    sogp_fit_fused_kernel<LD, NT, LD_IN, LD_OUT, SPILL><<<a.n_work, NT, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -1820,7 +1854,7 @@ int sogp_bucket_ld(int bucket) {
 
 size_t sogp_handoff_slot_bytes(int bucket, int dout) { return (size_t)slot_doubles(sogp_bucket_ld(bucket), dout) * sizeof(double); }
 
-size_t sogp_spill_bytes_per_patch() { return (size_t)(2 * 202 * 202 + 13 * 202 + 16) * sizeof(double); }
+size_t sogp_spill_bytes_per_patch() { return (size_t)(2 * 216 * 216) * sizeof(double); }  // >= the generic kernel's (2 * 202^2 + 13 * 202 + 16)
 
 // Height GPs (dout 1) use buckets 0,1,2,3,4; the RGB field GPs (dout 3) use 0,2,4 (bucket 2 resumes bucket-0 slots,
 // bucket 4 resumes bucket-2 slots): under the reference's field hyper-parameters N stays below 16 anyway.
@@ -1852,7 +1886,7 @@ cudaError_t launch_sogp_fit(int bucket, const SogpArgs& a, cudaStream_t st) {
         case 3:
             if (a.ld <= 104) return launch_fused_bucket<104, 416, 64, 104>(a, st);
             return launch_cta_bucket<118, 128, 512, 64, false, 1>(a, st);
-        default: return launch_cta_bucket<202, 256, 1024, 118, true, 1>(a, st);
+        default: return launch_fused_bucket<216, 864, 118, 216, true>(a, st);
     }
 }
 
