@@ -18,7 +18,7 @@ GPC_OK = 0
 # every symbol include/gpc.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "gpc_config_default", "gpc_create", "gpc_destroy", "gpc_last_error", "gpc_version", "gpc_compress",
-    "gpc_upload_cloud", "gpc_compress_resident", "gpc_compress_shard_begin", "gpc_compress_shard_finish", "gpc_fit_patches", "gpc_decompress", "gpc_decompress_resident",
+    "gpc_upload_cloud", "gpc_compress_resident", "gpc_add_measurements", "gpc_compress_shard_begin", "gpc_compress_shard_finish", "gpc_fit_patches", "gpc_decompress", "gpc_decompress_resident",
     "gpc_get_heights", "gpc_predict", "gpc_evaluate_patches", "gpc_get_sizes", "gpc_get_stats", "gpc_get_patches", "gpc_get_assignment",
     "gpc_get_params", "gpc_get_params_rgb", "gpc_get_state", "gpc_set_params", "gpc_set_rand_offset", "gpc_get_stream", "gpc_debug_exp", "gpc_debug_rand", "gpc_debug_peak", "gpc_shard_range", "gpc_save", "gpc_load", "gpc_get_config",
 ]
@@ -75,6 +75,7 @@ def load():
     L.gpc_decompress_resident.argtypes = [vp, C.POINTER(i64)]
     L.gpc_get_heights.argtypes = [vp, vp, i64]
     L.gpc_predict.argtypes = [vp, i64, vp, i64, vp, vp]
+    L.gpc_add_measurements.argtypes = [vp, i64, vp, vp, vp, vp]
     L.gpc_compress_shard_begin.argtypes = [vp, vp, i64, vp, vp]
     L.gpc_compress_shard_finish.argtypes = [vp, i64, C.c_uint64, i64, C.c_uint64]
     L.gpc_evaluate_patches.argtypes = [vp, i64, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp]
@@ -195,6 +196,12 @@ class Handle:
         off = np.ascontiguousarray(off, dtype=np.int64)
         x1, x2, y = (np.ascontiguousarray(a, dtype=np.float64) for a in (x1, x2, y))
         self._ck(load().gpc_fit_patches(self.h, off.size - 1, _p(off), _p(x1), _p(x2), _p(y)))
+
+    def add_measurements(self, off, x1, x2, y):
+        """gpc_add_measurements: more points for the patches of the previous fit (keep_state=1), state continued."""
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        x1, x2, y = (np.ascontiguousarray(a, dtype=np.float64) for a in (x1, x2, y))
+        self._ck(load().gpc_add_measurements(self.h, off.size - 1, _p(off), _p(x1), _p(x2), _p(y)))
 
     # ---- decompress -----------------------------------------------------------------
     def decompress(self, out=None):

@@ -40,7 +40,7 @@ struct gpc_handle {
     DevBuf perm_rgb, fcr, fcg, fcb, r_nbv, r_flags, r_alpha0, r_alpha1, r_alpha2, r_b1, r_b2, r_bidx, kstats_rgb;
     bool have_rgb = false;
     DevBuf quat, mean, rgbmean, Rm, center, code, ncand, owner, st_idx;
-    DevBuf tmpA, tmpB, tmpC, lat_state, ev_in, ev_out, size_ids, size_hist, sel_cloud, sel_idx, coarse_hist;
+    DevBuf tmpA, tmpB, tmpC, lat_state, ev_in, ev_out, size_ids, size_hist, sel_cloud, sel_idx, coarse_hist, fed, forig, cont_q, cont_slots;
     // sharded binning (gpc_compress_shard_begin / _finish): this shard's patches are local indices [own_lo, own_hi) of a
     // binning that holds the shard's key range plus its halo; global patch index = local + gshift
     bool shard_mode = false;
@@ -113,13 +113,14 @@ void shard_range(const std::vector<int64_t>& off, int r, int c, int64_t* lo, int
 }
 
 // Runs the SOGP bucket chain for one family of processes (dout 1: heights, dout 3: RGB field).
-int run_buckets(gpc_handle* h, SogpArgs& a, int need_ld, int64_t PL, int64_t lo, uint64_t* escalated) {
+// One chain of buckets: `work` patches (ids) start in bucket b0 -- from scratch (b0 = 0) or from the state slots
+// hand_in of bucket b0 - 1's format (continued fits) -- and climb to larger buckets as they outgrow them.
+int run_buckets(gpc_handle* h, SogpArgs& a, int need_ld, int64_t lo, uint64_t* escalated, int b0, int64_t work, const int32_t* ids,
+                const double* hand_in) {
     cudaStream_t st = h->stream;
-    int64_t work = PL;
-    const int32_t* ids = h->size_ids.as<int32_t>();  // bucket 0 visits the patches by decreasing size (see launch_size_order)
     a.spill = nullptr;
     int step = 0;
-    for (int b = 0; b < 5 && work > 0; b = sogp_next_bucket(b, a.dout), step++) {
+    for (int b = b0; b < 5 && work > 0; b = sogp_next_bucket(b, a.dout), step++) {
         const int bl = sogp_bucket_ld(b);
         const bool final_bucket = need_ld <= bl;
         a.ld = final_bucket ? need_ld : bl;
@@ -131,7 +132,7 @@ int run_buckets(gpc_handle* h, SogpArgs& a, int need_ld, int64_t PL, int64_t lo,
         DevBuf& hi_ = (step & 1) ? h->hand0 : h->hand1;
         a.queue = final_bucket ? nullptr : q.as<int32_t>();
         a.queue_count = h->qcount.as<int32_t>() + b;
-        a.handoff_in = (step > 0) ? hi_.as<double>() : nullptr;
+        a.handoff_in = (step > 0) ? hi_.as<double>() : hand_in;
         a.handoff_out = nullptr;
         if (!final_bucket) {
             CK(ho.reserve((size_t)work * sogp_handoff_slot_bytes(b, a.dout)));
@@ -154,7 +155,8 @@ int run_buckets(gpc_handle* h, SogpArgs& a, int need_ld, int64_t PL, int64_t lo,
 }
 
 // Shuffle + SOGP fit of patches [patch_lo, patch_hi) over the stream held in h->off/x1/x2/y.
-int run_fit(gpc_handle* h, StageTimer& tm) {
+// cont: continue the kept state of every patch with the new stream (gpc_add_measurements)
+int run_fit(gpc_handle* h, StageTimer& tm, bool cont = false) {
     const gpc_config& c = h->cfg;
     cudaStream_t st = h->stream;
     const int64_t P = h->n_patches;
@@ -203,9 +205,17 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
         sg.do_shuffle = c.shuffle; sg.is_rgb = 0; sg.first_patch = lo; sg.s_begin = h->s_begin; sg.s_count = h->s_count;
         sg.x1 = h->x1.as<double>(); sg.x2 = h->x2.as<double>(); sg.y = h->y.as<double>(); sg.rgb = nullptr; sg.rgbmean = nullptr;
         sg.perm = h->perm.as<int32_t>();
+        sg.forig = nullptr; sg.orig_base = nullptr;
+        if (cont) {  // BV indices of a continued fit count from the points fed before
+            CK(h->forig.reserve(std::max<int64_t>(S, 1) * sizeof(int32_t)));
+            sg.forig = h->forig.as<int32_t>();
+            sg.orig_base = h->fed.as<int64_t>() + lo;
+        }
         sg.fx1 = h->fx1.as<double>(); sg.fx2 = h->fx2.as<double>(); sg.f0 = h->fy.as<double>(); sg.f1 = sg.f2 = nullptr;
         launch_shuffle_gather(sg, max_np, h->patch_of.as<int32_t>(), st);
     }
+    CK(h->fed.reserve(std::max<int64_t>(P, 1) * sizeof(int64_t)));
+    launch_fed_update(h->off.as<int64_t>(), P, cont ? 1 : 0, h->fed.as<int64_t>(), st);
     h->rand_offset += draws_all;
     size_t t1 = tm.mark();
     tm.span(&h->stats.ms_shuffle, t0, t1);
@@ -233,7 +243,7 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
     a.fx1 = h->fx1.as<double>(); a.fx2 = h->fx2.as<double>();
     a.fy[0] = h->fy.as<double>(); a.fy[1] = a.fy[2] = nullptr;
     a.dout = 1;
-    a.forig = h->perm.as<int32_t>();
+    a.forig = cont ? h->forig.as<int32_t>() : h->perm.as<int32_t>();
     a.capacity = cap;
     a.s20 = c.s0; a.eps_tol = c.eps_tol; a.p0 = c.sigmaf_sq; a.cl = kernel_cl(c);
     a.out_first = lo;
@@ -244,12 +254,32 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
     a.dumpC = c.keep_state ? h->dumpC.as<double>() : nullptr;
     a.dumpQ = c.keep_state ? h->dumpQ.as<double>() : nullptr;
     a.stats = h->kstats.as<unsigned long long>();
-    {
+    if (!cont) {
         CK(h->size_ids.reserve((size_t)PL * sizeof(int32_t)));
         CK(h->size_hist.reserve(1024 * sizeof(int32_t)));
         launch_size_order(h->off.as<int64_t>(), lo, PL, h->size_hist.as<int32_t>(), h->size_ids.as<int32_t>(), st);
-        int rc = run_buckets(h, a, need_ld, PL, lo, h->stats.escalated);
+        int rc = run_buckets(h, a, need_ld, lo, h->stats.escalated, 0, PL, h->size_ids.as<int32_t>(), nullptr);
         if (rc) return rc;
+    } else {
+        // patches with new points, by the size of their kept state: one chain of buckets per slot format
+        CK(h->cont_q.reserve((size_t)(4 * PLa + 8) * sizeof(int32_t)));
+        int32_t* d_cnt = h->cont_q.as<int32_t>() + 4 * PLa;
+        launch_continue_partition(h->off.as<int64_t>(), h->nbv.as<int32_t>(), lo, PL, h->cont_q.as<int32_t>(), d_cnt, st);
+        int32_t cnt4[4] = {0, 0, 0, 0};
+        CK(cudaMemcpyAsync(cnt4, d_cnt, sizeof(cnt4), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int b0 = 1; b0 <= 4; b0++) {
+            const int64_t work = cnt4[b0 - 1];
+            if (work == 0) continue;
+            const int32_t* ids = h->cont_q.as<int32_t>() + (int64_t)(b0 - 1) * PL;
+            CK(h->cont_slots.reserve((size_t)work * sogp_handoff_slot_bytes(b0 - 1, 1)));
+            CK(launch_state_to_slots(b0, ids, work, lo, cap, h->nbv.as<int32_t>(), h->alpha.as<double>(), h->b1.as<double>(),
+                                     h->b2.as<double>(), h->bidx.as<int32_t>(), h->dumpC.as<double>(), h->dumpQ.as<double>(),
+                                     h->cont_slots.as<double>(), st));
+            CK(cudaMemsetAsync(h->qcount.p, 0, 8 * sizeof(int32_t), st));
+            int rc = run_buckets(h, a, need_ld, lo, nullptr, b0, work, ids, h->cont_slots.as<double>());
+            if (rc) return rc;
+        }
     }
     size_t t2 = tm.mark();
     tm.span(&h->stats.ms_fit, t1, t2);
@@ -282,6 +312,7 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
             sg.x1 = h->x1.as<double>(); sg.x2 = h->x2.as<double>(); sg.y = nullptr; sg.rgb = h->rgb.as<uint32_t>();
             sg.rgbmean = h->rgbmean.as<double>();
             sg.perm = h->perm_rgb.as<int32_t>();
+            sg.forig = nullptr; sg.orig_base = nullptr;
             sg.fx1 = h->fx1.as<double>(); sg.fx2 = h->fx2.as<double>();
             sg.f0 = h->fcr.as<double>(); sg.f1 = h->fcg.as<double>(); sg.f2 = h->fcb.as<double>();
             launch_shuffle_gather(sg, max_np, h->patch_of.as<int32_t>(), st);
@@ -298,7 +329,7 @@ int run_fit(gpc_handle* h, StageTimer& tm) {
         r.dumpC = r.dumpQ = nullptr;
         r.stats = h->kstats_rgb.as<unsigned long long>();
         {
-            int rc = run_buckets(h, r, need_ld, PL, lo, nullptr);
+            int rc = run_buckets(h, r, need_ld, lo, nullptr, 0, PL, h->size_ids.as<int32_t>(), nullptr);
             if (rc) return rc;
         }
         h->have_rgb = true;
@@ -683,7 +714,7 @@ void gpc_destroy(gpc_handle* h) {
                       &h->dumpC, &h->dumpQ, &h->queue0, &h->queue1, &h->hand0, &h->hand1, &h->spill, &h->qcount, &h->kstats, &h->bv_off, &h->palpha, &h->pb1, &h->pb2, &h->pidx, &h->perm_rgb, &h->fcr, &h->fcg, &h->fcb, &h->r_nbv, &h->r_flags,
                       &h->r_alpha0, &h->r_alpha1, &h->r_alpha2, &h->r_b1, &h->r_b2, &h->r_bidx, &h->kstats_rgb, &h->nonempty, &h->slot, &h->out32,
                       &h->heights, &h->quat, &h->mean, &h->rgbmean, &h->Rm, &h->center, &h->code, &h->ncand, &h->owner,
-                      &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->lat_state, &h->ev_in, &h->ev_out, &h->size_ids, &h->size_hist, &h->sel_cloud, &h->sel_idx, &h->coarse_hist, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
+                      &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->lat_state, &h->ev_in, &h->ev_out, &h->size_ids, &h->size_hist, &h->sel_cloud, &h->sel_idx, &h->coarse_hist, &h->fed, &h->forig, &h->cont_q, &h->cont_slots, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
                       &h->ovals2, &h->sort_tmp, &h->flags64, &h->ex, &h->leaf_of, &h->leaf_start, &h->leaf_code_a, &h->spt,
                       &h->nbr, &h->nnbr, &h->center_a, &h->Rm_a, &h->ncand_a, &h->pt0, &h->pt1, &h->pt2, &h->hbuf, &h->rgb, &h->leaf_sums};
     for (DevBuf* b : bufs) b->release();
@@ -706,9 +737,17 @@ int gpc_set_rand_offset(gpc_handle* h, uint64_t offset) {
     return GPC_OK;
 }
 
-int gpc_fit_patches(gpc_handle* h, int64_t P, const int64_t* off, const double* x1, const double* x2, const double* y) {
+static int fit_patches_impl(gpc_handle* h, int64_t P, const int64_t* off, const double* x1, const double* x2, const double* y, bool cont) {
     if (!h || P < 0 || !off) return GPC_ERR_INVALID;
     CK(cudaSetDevice(h->cfg.device));
+    if (cont) {
+        if (!h->have_fit || !h->cfg.keep_state || !h->dumpC.p)
+            return fail(h, GPC_ERR_STATE, "gpc_add_measurements needs a previous fit on this handle made with gpc_config.keep_state");
+        if (h->shard_mode || h->cfg.shard_count != 1 || P != h->n_patches || h->patch_lo != 0 || h->patch_hi != h->n_patches)
+            return fail(h, GPC_ERR_INVALID, "gpc_add_measurements: same patches as the previous fit, one shard");
+        if (h->cfg.rgb && h->have_rgb) return fail(h, GPC_ERR_INVALID, "gpc_add_measurements continues the height GPs only (rgb = 0)");
+        if (h->cfg.capacity > 117) return fail(h, GPC_ERR_INVALID, "gpc_add_measurements supports capacity <= 117");
+    }
     h->shard_mode = false;
     if (off[0] != 0) return fail(h, GPC_ERR_INVALID, "off[0] must be 0");
     for (int64_t p = 0; p < P; p++)
@@ -733,10 +772,13 @@ int gpc_fit_patches(gpc_handle* h, int64_t P, const int64_t* off, const double* 
     tm.span(&h->stats.ms_h2d, tA, tB);
     h->n_patches = P;
     h->n_in = S;
-    h->have_frames = false;
-    h->have_binning = false;
+    if (!cont) {
+        h->have_frames = false;
+        h->have_binning = false;
+    }
+    h->have_binning = false;   // the point-level arrays of a compress no longer describe the stream
     h->have_rgb = false;
-    int rc = run_fit(h, tm);
+    int rc = run_fit(h, tm, cont);
     if (rc) return rc;
     size_t tC = tm.mark();
     tm.span(&h->stats.ms_total, tA, tC);
@@ -746,6 +788,14 @@ int gpc_fit_patches(gpc_handle* h, int64_t P, const int64_t* off, const double* 
     tm.resolve();
     h->stats.kernel_launches = g_launches;
     return GPC_OK;
+}
+
+int gpc_fit_patches(gpc_handle* h, int64_t P, const int64_t* off, const double* x1, const double* x2, const double* y) {
+    return fit_patches_impl(h, P, off, x1, x2, y, false);
+}
+
+int gpc_add_measurements(gpc_handle* h, int64_t P, const int64_t* off, const double* x1, const double* x2, const double* y) {
+    return fit_patches_impl(h, P, off, x1, x2, y, true);
 }
 
 int gpc_upload_cloud(gpc_handle* h, const void* cloud, int64_t n) {

@@ -104,6 +104,7 @@ void launch_exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, void*
 // draws[p] = (n_p > 0 ? (n_p - 1) * mult : 0)
 // draws[p] + exclusive scan roff[0..P] + plan9 = { n_claimed, lo, hi, off[lo], off[hi], roff[lo], roff[hi], roff[P], max n_p }
 // ids[0..n): patches lo..lo+n-1 by decreasing point count; hist1024: 1024 ints of scratch
+void launch_fed_update(const int64_t* off, int64_t n, int accumulate, int64_t* fed, cudaStream_t s);
 void launch_size_order(const int64_t* off, int64_t lo, int64_t n, int32_t* hist1024, int32_t* ids, cudaStream_t s);
 void launch_fit_plan(const int64_t* off, int64_t n_patches, int mult, int rank, int count, int64_t fixed_lo, int64_t fixed_hi,
                      int64_t* draws, int64_t* roff, void* scan_tmp, int64_t* plan9, cudaStream_t s);
@@ -121,6 +122,8 @@ struct ShuffleGatherArgs {
     const uint32_t* rgb;         // b,g,r,a bytes per grouped point
     const double* rgbmean;       // 3 per patch (absolute patch index)
     int32_t* perm;               // out: local index of the point added at each stream position
+    int32_t* forig;              // optional: perm + orig_base[patch] (continued fits: index in the concatenated streams)
+    const int64_t* orig_base;    // points fed to each patch before this call (same base as off), with forig
     double *fx1, *fx2, *f0, *f1, *f2;
 };
 void launch_shuffle_gather(const ShuffleGatherArgs& a, int64_t max_patch_points, int32_t* patch_of, cudaStream_t s);
@@ -164,6 +167,11 @@ int sogp_bucket_ld(int bucket);
 size_t sogp_handoff_slot_bytes(int bucket, int dout);
 int sogp_next_bucket(int bucket, int dout);
 size_t sogp_spill_bytes_per_patch();
+void launch_continue_partition(const int64_t* off, const int32_t* nbv, int64_t lo, int64_t n, int32_t* queues, int32_t* counts4,
+                               cudaStream_t s);
+cudaError_t launch_state_to_slots(int b0, const int32_t* ids, int64_t n_work, int64_t out_first, int cap, const int32_t* nbv,
+                                  const double* alpha, const double* b1, const double* b2, const int32_t* bidx, const double* dumpC,
+                                  const double* dumpQ, double* slots, cudaStream_t s);
 cudaError_t launch_sogp_fit(int bucket, const SogpArgs& a, cudaStream_t s);
 
 // ---- K8: grid prediction ----------------------------------------------------------------

@@ -1846,6 +1846,72 @@ cudaError_t launch_cta_bucket(const SogpArgs& a, cudaStream_t st) {
 
 }  // namespace
 
+// ---- continued fits (sparse_gp::add_measurements called again, sparse_gp.hpp:59-86) ---------------------------------
+// The kept state of a patch (alpha, BV, C, Q of the previous fit) is written as a hand-off slot of the smallest format
+// that holds it; the bucket that resumes that format continues the recursion on the new points.
+__global__ void continue_partition_kernel(const int64_t* __restrict__ off, const int32_t* __restrict__ nbv, int64_t lo, int64_t n,
+                                          int32_t* __restrict__ queues, int32_t* __restrict__ counts) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (off[lo + i + 1] == off[lo + i]) return;  // no new points: the patch keeps its state
+    const int N = nbv[i];
+    const int b0 = N <= 16 ? 1 : (N <= 32 ? 2 : (N <= 64 ? 3 : 4));
+    const int pos = atomicAdd(counts + (b0 - 1), 1);
+    queues[(int64_t)(b0 - 1) * n + pos] = (int32_t)(lo + i);
+}
+
+// one CTA per queued patch: slot q of format LDS <- state of patch ids[q]
+template <int LDS>
+__global__ void __launch_bounds__(128) state_to_slot_kernel(const int32_t* __restrict__ ids, int64_t out_first, int cap,
+                                                            const int32_t* __restrict__ nbv, const double* __restrict__ alpha,
+                                                            const double* __restrict__ b1, const double* __restrict__ b2,
+                                                            const int32_t* __restrict__ bidx, const double* __restrict__ dumpC,
+                                                            const double* __restrict__ dumpQ, double* __restrict__ slots) {
+    const int64_t op = (int64_t)ids[blockIdx.x] - out_first;
+    const int N = nbv[op];
+    double* slot = slots + (size_t)blockIdx.x * slot_doubles(LDS, 1);
+    const int t = threadIdx.x;
+    if (t == 0) { reinterpret_cast<int*>(slot)[0] = N; reinterpret_cast<int*>(slot)[1] = 0; }
+    if (t < NCNT) reinterpret_cast<unsigned long long*>(slot + 2)[t] = 0ull;
+    double* v = slot + 2 + NCNT;
+    const int64_t ob = op * cap, od = op * (int64_t)cap * cap;
+    for (int i = t; i < LDS; i += 128) {
+        v[i] = i < N ? alpha[ob + i] : 0.0;
+        v[LDS + i] = i < N ? b1[ob + i] : 0.0;
+        v[2 * LDS + i] = i < N ? b2[ob + i] : 0.0;
+        reinterpret_cast<int*>(v + 3 * LDS + 2 * LDS * LDS)[i] = i < N ? bidx[ob + i] : -1;
+    }
+    for (int e = t; e < LDS * LDS; e += 128) {
+        const int j = e / LDS, i = e - j * LDS;   // slot element e = (row i, column j)
+        const bool in = i < N && j < N;
+        v[3 * LDS + e] = in ? dumpC[od + (size_t)i * N + j] : 0.0;
+        v[3 * LDS + LDS * LDS + e] = in ? dumpQ[od + (size_t)i * N + j] : 0.0;
+    }
+}
+
+void launch_continue_partition(const int64_t* off, const int32_t* nbv, int64_t lo, int64_t n, int32_t* queues, int32_t* counts4,
+                               cudaStream_t s) {
+    cudaMemsetAsync(counts4, 0, 4 * sizeof(int32_t), s);
+    if (n <= 0) return;
+    continue_partition_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(off, nbv, lo, n, queues, counts4);
+    g_launches++;
+}
+
+// start bucket b0 in 1..4 resumes slots of bucket b0 - 1's format
+cudaError_t launch_state_to_slots(int b0, const int32_t* ids, int64_t n_work, int64_t out_first, int cap, const int32_t* nbv,
+                                  const double* alpha, const double* b1, const double* b2, const int32_t* bidx, const double* dumpC,
+                                  const double* dumpQ, double* slots, cudaStream_t s) {
+    if (n_work <= 0) return cudaSuccess;
+    g_launches++;
+    switch (b0) {
+        case 1: state_to_slot_kernel<16><<<(unsigned)n_work, 128, 0, s>>>(ids, out_first, cap, nbv, alpha, b1, b2, bidx, dumpC, dumpQ, slots); break;
+        case 2: state_to_slot_kernel<32><<<(unsigned)n_work, 128, 0, s>>>(ids, out_first, cap, nbv, alpha, b1, b2, bidx, dumpC, dumpQ, slots); break;
+        case 3: state_to_slot_kernel<64><<<(unsigned)n_work, 128, 0, s>>>(ids, out_first, cap, nbv, alpha, b1, b2, bidx, dumpC, dumpQ, slots); break;
+        default: state_to_slot_kernel<118><<<(unsigned)n_work, 128, 0, s>>>(ids, out_first, cap, nbv, alpha, b1, b2, bidx, dumpC, dumpQ, slots); break;
+    }
+    return cudaGetLastError();
+}
+
 int sogp_bucket_ld(int bucket) {
     static const int lds[5] = {16, 32, 64, 118, 202};
     return lds[bucket];

@@ -310,6 +310,24 @@ void launch_flag_nonempty(const int32_t* nbv, const int32_t* rgb_nbv, int64_t n,
     g_launches++;
 }
 
+// points fed to each patch so far: fed[p] = (accumulate ? fed[p] : 0) + off[p + 1] - off[p]
+__global__ void fed_update_kernel(const int64_t* __restrict__ off, int64_t n, int accumulate, int64_t* __restrict__ fed) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) fed[p] = (accumulate ? fed[p] : 0) + off[p + 1] - off[p];
+}
+void launch_fed_update(const int64_t* off, int64_t n, int accumulate, int64_t* fed, cudaStream_t s) {
+    if (n <= 0) return;
+    fed_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(off, n, accumulate, fed);
+    g_launches++;
+}
+__global__ void forig_kernel(const int32_t* __restrict__ patch_of, const int32_t* __restrict__ perm, const int64_t* __restrict__ orig_base,
+                             int64_t s_begin, int64_t s_count, int32_t* __restrict__ forig) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= s_count) return;
+    s += s_begin;
+    forig[s] = perm[s] + (int32_t)orig_base[patch_of[s]];
+}
+
 // Fused shuffle + gather for patches of up to SHUF_SMEM_MAX points (the common case): the permutation never leaves
 // shared memory before the fit streams are written in add order.  RGB: the field GP's own shuffle (the draws after the
 // patch's first n - 1) and its colour stream centred on the patch mean (p.second -= c_mn, gp_compressor.cpp:105).
@@ -348,6 +366,7 @@ __global__ void __launch_bounds__(32) shuffle_gather_warp_kernel(ShuffleGatherAr
         const int k = ind[i];
         const int64_t src = o + k, dst = o + i;
         a.perm[dst] = k;
+        if (a.forig) a.forig[dst] = k + (int32_t)a.orig_base[p];
         a.fx1[dst] = a.x1[src];
         a.fx2[dst] = a.x2[src];
         if (RGB) {
@@ -384,6 +403,10 @@ void launch_shuffle_gather(const ShuffleGatherArgs& a, int64_t max_patch_points,
                                  a.f0, a.f1, a.f2, s);
     else
         launch_gather_stream(a.off, patch_of, a.perm, a.x1, a.x2, a.y, a.s_begin, a.s_count, a.fx1, a.fx2, a.f0, s);
+    if (a.forig) {
+        forig_kernel<<<(unsigned)((a.s_count + 255) / 256), 256, 0, s>>>(patch_of, a.perm, a.orig_base, a.s_begin, a.s_count, a.forig);
+        g_launches++;
+    }
 }
 
 // ---- patch ids of [lo, lo + n) ordered by decreasing point count (counting sort over min(count, 1023)) ----------

@@ -51,15 +51,14 @@ public:
     sparse_gp& operator=(const sparse_gp&) = delete;
     gpc_config& config() { return cfg_; }
 
-    // void add_measurements(const MatrixXd& X /* n x 2 */, const VectorXd& y), sparse_gp.hpp:59-86.
-    // The reference accumulates across calls; the device entry fits a whole stream at once, so a second
-    // call on a fitted process is rejected instead of silently refitting.
+    // void add_measurements(const MatrixXd& X /* n x 2 */, const VectorXd& y), sparse_gp.hpp:59-86.  Like the reference,
+    // a second call adds to the fitted process (gpc_add_measurements continues the kept state).
     void add_measurements(const Eigen::MatrixXd& X, const Eigen::VectorXd& y) {
-        if (fitted_) throw std::runtime_error("sparse_gp: incremental add_measurements is not built (row N4); reset() first");
         if (X.cols() != 2 || X.rows() != y.rows()) throw std::invalid_argument("sparse_gp::add_measurements: X must be n x 2, y n");
         open();
         const int64_t off[2] = {0, (int64_t)X.rows()};
-        check(gpc_fit_patches(h_, 1, off, X.data(), X.data() + X.rows(), y.data()));  // column-major: col 0 then col 1
+        if (fitted_) check(gpc_add_measurements(h_, 1, off, X.data(), X.data() + X.rows(), y.data()));
+        else check(gpc_fit_patches(h_, 1, off, X.data(), X.data() + X.rows(), y.data()));  // column-major: col 0 then col 1
         int32_t n = 0;
         check(gpc_get_params(h_, &n, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
         size_ = n;

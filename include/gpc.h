@@ -104,6 +104,14 @@ int gpc_compress_resident(gpc_handle* h);
 int gpc_fit_patches(gpc_handle* h, int64_t n_patches, const int64_t* off,
                     const double* x1, const double* x2, const double* y);
 
+/* sparse_gp::add_measurements called AGAIN on fitted processes: the reference accumulates (sparse_gp.hpp:59-86 appends to
+ * the existing BV / alpha / C / Q state; gp_mapping.cpp:338 adds every new cloud to the patch GPs).  The new points of
+ * each patch are shuffled with the next rand() draws and the recursion continues from the kept state (the previous fit
+ * and this handle need gpc_config.keep_state; same P as that fit, shard_count 1, rgb 0, capacity <= 117).  Patches
+ * without new points keep their state.  BV indices (gpc_get_params) of points chosen from this call count on from the
+ * points fed to the patch before. */
+int gpc_add_measurements(gpc_handle* h, int64_t P, const int64_t* off, const double* x1, const double* x2, const double* y);
+
 /* Strong scaling of ONE cloud over several GPUs (replaces nothing in the reference, which is
  * single-threaded): every rank passes the same cloud (or NULL to use the cloud of gpc_upload_cloud) with
  * gpc_config.shard_rank / shard_count set.  begin replays the lattice on the whole cloud, cuts the visiting order

@@ -745,6 +745,7 @@ struct Oracle {
     SogpStats stats_rgb;
     // ---- fit results ----
     std::vector<int32_t> nbv;                  // per patch
+    std::vector<int64_t> fed;                  // points fed to each patch's height GP so far (continued fits)
     std::vector<int64_t> bv_off;               // n_leaves+1
     std::vector<int32_t> bv_idx;               // patch-local stream position of each BV
     std::vector<double> bv1, bv2, alpha;
@@ -978,12 +979,24 @@ struct Oracle {
     }
 
     // ------------- train_processes (gp_compressor.cpp:121-175) on any patch stream -------------
+    // cont: sparse_gp::add_measurements called again on the fitted processes (sparse_gp.hpp:59-86 accumulates): the new
+    // points of every patch are shuffled with the next rand() draws and added to the kept state (needs dump on both calls)
     int train(int64_t NP, const int64_t* off, const double* x1, const double* x2, const double* y, int dump,
-              const double* colours = nullptr) {
+              const double* colours = nullptr, bool cont = false) {
         auto t0 = std::chrono::steady_clock::now();
         const SogpParams sp = sogp_params();
         const int64_t total = off[NP];
         const bool do_rgb = cfg.rgb && colours != nullptr;
+        std::vector<int32_t> o_nbv, o_idx, o_flags;
+        std::vector<int64_t> o_bvoff, o_dumpoff;
+        std::vector<double> o_alpha, o_b1, o_b2, o_C, o_Q;
+        if (cont) {
+            if (do_rgb || !dump || (int64_t)nbv.size() != NP || dump_off.empty() || (int64_t)fed.size() != NP) { err = "continued fit needs a previous height-only fit of the same patches with dump"; return 4; }
+            o_nbv = nbv; o_idx = bv_idx; o_flags = fit_flags; o_bvoff = bv_off; o_dumpoff = dump_off;
+            o_alpha = alpha; o_b1 = bv1; o_b2 = bv2; o_C = dumpC; o_Q = dumpQ;
+        } else {
+            fed.assign(NP, 0);
+        }
         if (do_rgb && !(cfg.shuffle && cfg.rgb_rand)) { err = "rgb needs shuffle and rgb_rand"; return 3; }
         st_perm_rgb.assign(do_rgb ? total : 0, 0);
         // rand stream: patch p's height shuffle starts after 2*(n_q-1) draws for every earlier
@@ -1022,13 +1035,31 @@ struct Oracle {
             Sogp gp;
             for (int64_t p = b; p < e; p++) {
                 int n = (int)(off[p + 1] - off[p]);
-                if (n == 0) continue;
+                if (n == 0 && !(cont && o_nbv[p] > 0)) continue;
                 int maxn = (cap > 0) ? std::min(cap, n) : n;
-                gp.init(sp, maxn);
+                int base = 0;
+                if (cont) {  // resume from the kept state
+                    const int N0 = o_nbv[p];
+                    maxn = (cap > 0) ? cap : N0 + n;
+                    gp.init(sp, std::max(maxn, 1));
+                    gp.N = N0;
+                    gp.flags = o_flags[p];
+                    for (int i = 0; i < N0; i++) {
+                        gp.alpha[i] = o_alpha[o_bvoff[p] + i]; gp.b1[i] = o_b1[o_bvoff[p] + i]; gp.b2[i] = o_b2[o_bvoff[p] + i];
+                        gp.idx[i] = o_idx[o_bvoff[p] + i];
+                        for (int j = 0; j < N0; j++) {
+                            gp.c(i, j) = o_C[o_dumpoff[p] + (size_t)i * N0 + j];
+                            gp.q(i, j) = o_Q[o_dumpoff[p] + (size_t)i * N0 + j];
+                        }
+                    }
+                    base = (int)fed[p];
+                } else {
+                    gp.init(sp, maxn);
+                }
                 const int64_t o = off[p];
                 for (int t = 0; t < n; t++) {
                     int s = st_perm[o + t];
-                    gp.add(x1[o + s], x2[o + s], y[o + s], s);
+                    gp.add(x1[o + s], x2[o + s], y[o + s], base + s);
                 }
                 nbv[p] = gp.N;
                 fit_flags[p] = gp.flags;
@@ -1046,6 +1077,7 @@ struct Oracle {
         });
         stats = SogpStats();
         for (auto& s : tstats) stats.merge(s);
+        for (int64_t p = 0; p < NP; p++) fed[p] += off[p + 1] - off[p];
         // ---- RGB field GP (sparse_gp_field<rbf_kernel, gaussian_noise_3d>), same points, own shuffle ----
         rgb_nbv.assign(do_rgb ? NP : 0, 0);
         rgb_bv_off.assign(NP + 1, 0);
@@ -1260,6 +1292,11 @@ int orc_fit_patches(void* h, int64_t NP, const int64_t* off, const double* x1, c
     Oracle* o = (Oracle*)h;
     o->leaf_R.clear();
     return o->train(NP, off, x1, x2, y, dump);
+}
+// sparse_gp::add_measurements again on the fitted patches (continues the kept state; both fits with dump)
+int orc_add_measurements(void* h, int64_t NP, const int64_t* off, const double* x1, const double* x2, const double* y) {
+    Oracle* o = (Oracle*)h;
+    return o->train(NP, off, x1, x2, y, 1, nullptr, true);
 }
 // the same with per-point colours (3 per point, centred by the caller): also fits the RGB field GPs when cfg.rgb
 int orc_fit_patches_rgb(void* h, int64_t NP, const int64_t* off, const double* x1, const double* x2, const double* y,

@@ -63,6 +63,8 @@ def lib():
         L.orc_decode.restype = C.c_int64
         L.orc_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_predict.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.orc_add_measurements.restype = C.c_int
+        L.orc_add_measurements.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 4
         L.orc_evaluate.restype = C.c_int
         L.orc_evaluate.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4
         L.orc_get_sizes.argtypes = [C.c_void_p, C.POINTER(OrcSizes)]
@@ -234,6 +236,15 @@ class Oracle:
             return self.fit_result(dump, ntot=self._ntot)
         self._check(lib().orc_fit_patches(self.h, self._np, _p(off), _p(x1), _p(x2), _p(y), int(dump)))
         return self.fit_result(dump, ntot=self._ntot)
+
+    def add_measurements(self, off, x1, x2, y):
+        """sparse_gp::add_measurements again on the patches of the previous fit_patches(dump=True): continues the state."""
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        x1, x2, y = (np.ascontiguousarray(a, dtype=np.float64) for a in (x1, x2, y))
+        assert off.size - 1 == self._np
+        self._ntot = int(off[-1])
+        self._check(lib().orc_add_measurements(self.h, self._np, _p(off), _p(x1), _p(x2), _p(y)))
+        return self.fit_result(True, ntot=self._ntot)
 
     def fit_result(self, dump=False, ntot=None):
         s = self.sizes()

@@ -124,6 +124,38 @@ int ref_sogp_evaluate(int n, const double* x1, const double* x2, const double* y
     return gp.size();
 }
 
+// add_measurements called twice on one process (the reference accumulates, sparse_gp.hpp:59-86): state after both
+int ref_sogp_fit_twice(int n1, int n2, const double* x1, const double* x2, const double* y, int capacity, double s0, double sigmaf_sq,
+                       double l_sq, double eps_tol, unsigned long long rand_offset, int max_n, double* alpha, double* bv1, double* bv2,
+                       double* C, double* Q) {
+    srand(1);
+    for (unsigned long long i = 0; i < rand_offset; i++) rand();
+    ref_gp gp(capacity, s0);
+    gp.kernel.param()(0) = sigmaf_sq;
+    gp.kernel.param()(1) = l_sq;
+    gp.eps_tol = eps_tol;
+    int done = 0;
+    for (int part = 0; part < 2; part++) {
+        const int n = part ? n2 : n1;
+        if (n > 0) {
+            Eigen::MatrixXd X(n, 2);
+            Eigen::VectorXd Y(n);
+            for (int i = 0; i < n; i++) { X(i, 0) = x1[done + i]; X(i, 1) = x2[done + i]; Y(i) = y[done + i]; }
+            gp.add_measurements(X, Y);
+        }
+        done += n;
+    }
+    const int N = gp.size();
+    if (N > max_n) return -N;
+    for (int i = 0; i < N; i++) {
+        alpha[i] = gp.alpha(i);
+        bv1[i] = gp.BV(0, i);
+        bv2[i] = gp.BV(1, i);
+        for (int j = 0; j < N; j++) { C[i * N + j] = gp.C(i, j); Q[i * N + j] = gp.Q(i, j); }
+    }
+    return N;
+}
+
 // sparse_gp::shuffle alone (sparse_gp.hpp:42-56) over the real rand()
 void ref_shuffle(int n, unsigned long long rand_offset, int* out) {
     srand(1);

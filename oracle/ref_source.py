@@ -31,6 +31,9 @@ def lib():
         L.ref_sogp_evaluate.restype = C.c_int
         L.ref_sogp_evaluate.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                         C.c_ulonglong, C.c_int] + [C.c_void_p] * 8
+        L.ref_sogp_fit_twice.restype = C.c_int
+        L.ref_sogp_fit_twice.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double,
+                                         C.c_double, C.c_ulonglong, C.c_int] + [C.c_void_p] * 5
         L.ref_kernel.restype = C.c_double
         L.ref_kernel.argtypes = [C.c_double] * 6
         _LIB = L
@@ -73,6 +76,21 @@ def evaluate(x1, x2, y, ex, ey, capacity=100, s0=float(np.float32(1e-1)), sigmaf
     N = lib().ref_sogp_evaluate(x1.size, _p(x1), _p(x2), _p(y), capacity, s0, sigmaf_sq, l_sq, eps_tol, rand_offset, m, _p(e1), _p(e2),
                                 _p(ey), _p(f), _p(sg), _p(cf), _p(lk), _p(dX))
     return dict(N=N, f=f, sigma=sg, conf=cf, lik=lk, dX=dX.reshape(m, 3))
+
+
+def fit_twice(x1, x2, y, n1, capacity=100, s0=float(np.float32(1e-1)), sigmaf_sq=100.0, l_sq=1.0, eps_tol=float(np.float32(1e-6)),
+              rand_offset=0):
+    """Two successive add_measurements calls (the first n1 points, then the rest) on one process of the reference."""
+    x1, x2, y = (np.ascontiguousarray(a, dtype=np.float64) for a in (x1, x2, y))
+    n = x1.size
+    mx = (capacity if capacity > 0 else n) + 2
+    alpha, b1, b2 = np.zeros(mx), np.zeros(mx), np.zeros(mx)
+    Cm, Qm = np.zeros(mx * mx), np.zeros(mx * mx)
+    N = lib().ref_sogp_fit_twice(n1, n - n1, _p(x1), _p(x2), _p(y), capacity, s0, sigmaf_sq, l_sq, eps_tol, rand_offset, mx, _p(alpha),
+                                 _p(b1), _p(b2), _p(Cm), _p(Qm))
+    assert N >= 0
+    return dict(N=N, alpha=alpha[:N].copy(), bv1=b1[:N].copy(), bv2=b2[:N].copy(), C=Cm[:N * N].reshape(N, N).copy(),
+                Q=Qm[:N * N].reshape(N, N).copy())
 
 
 def field_fit(x1, x2, Y, capacity=100, s0=float(np.float32(1e2)), sigmaf_sq=100.0, l_sq=1.0, eps_tol=float(np.float32(1e-4)),

@@ -48,6 +48,14 @@ int main(int argc, char** argv) {
         gp.compute_likelihoods(lk, Xs, ys);
         gp.compute_derivatives(dX, Xs, ys);
         std::printf("EVAL %.17g %.17g %.17g %.17g %.17g %.17g\n", sg(0), cf(0), lk(0), dX(0, 0), dX(0, 1), dX(0, 2));
+        // a second add_measurements accumulates, as in the reference (sparse_gp.hpp:59-86)
+        Eigen::MatrixXd X2(3, 2);
+        Eigen::VectorXd y2(3);
+        const double more[3][3] = {{.02, .03, .015}, {.04, .01, .005}, {.01, .04, -.002}};
+        for (int i = 0; i < 3; i++) { X2(i, 0) = more[i][0]; X2(i, 1) = more[i][1]; y2(i) = more[i][2]; }
+        gp.add_measurements(X2, y2);
+        gp.predict_measurements(fs, Xs, sg);
+        std::printf("SOGP2 %d %.17g %.17g\n", gp.size(), fs(0), sg(0));
         bool threw = false;
         try { pointcloud_decompressor d; d.load_compressed("x"); } catch (const std::exception&) { threw = true; }
         std::printf("KSVD_SHELL %d\n", (int)threw);

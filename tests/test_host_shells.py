@@ -40,7 +40,7 @@ def test_driver_matches_ctypes_path(tmp_path):
     dec_path = tmp_path / "decoded.bin"
     out = subprocess.run([exe, str(path), str(dec_path)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
-    lines = dict(l.split(" ", 1) for l in out.stdout.splitlines() if l.split(" ")[0] in ("CLOUD", "SOGP", "EVAL", "KSVD_SHELL"))
+    lines = dict(l.split(" ", 1) for l in out.stdout.splitlines() if l.split(" ")[0] in ("CLOUD", "SOGP", "SOGP2", "EVAL", "KSVD_SHELL"))
     h = G.Handle(res=float(np.float32(0.15)), sz=20, rgb=1)  # the literals of test_gp_compress.cpp:21; the shell enables the RGB GP
     h.compress(cloud)
     dec = h.decompress()
@@ -59,3 +59,9 @@ def test_driver_matches_ctypes_path(tmp_path):
     want = [e["sigma"][0], ec["sigma"][0], e["lik"][0], *e["dX"][0]]
     got = [float(v) for v in lines["EVAL"].split()]
     assert got == [float(repr(float(w))) for w in want]
+    # the shell's second add_measurements == gpc_add_measurements through ctypes
+    more = np.array([[.02, .03, .015], [.04, .01, .005], [.01, .04, -.002]])
+    g.add_measurements(np.array([0, 3]), more[:, 0].copy(), more[:, 1].copy(), more[:, 2].copy())
+    f2, s2 = g.predict(0, np.array([[0.025, 0.025]]), sigma=True)
+    nb2, ff, ss = lines["SOGP2"].split()
+    assert int(nb2) == int(g.params()["nbv"][0]) and float(ff) == float(repr(float(f2[0]))) and float(ss) == float(repr(float(s2[0])))
