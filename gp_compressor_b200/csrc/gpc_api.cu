@@ -40,7 +40,9 @@ struct gpc_handle {
     DevBuf perm_rgb, fcr, fcg, fcb, r_nbv, r_flags, r_alpha0, r_alpha1, r_alpha2, r_b1, r_b2, r_bidx, kstats_rgb;
     bool have_rgb = false;
     DevBuf quat, mean, rgbmean, Rm, center, code, ncand, owner, st_idx;
-    DevBuf tmpA, tmpB, tmpC, lat_state, ev_in, ev_out, size_ids, size_hist, sel_cloud, sel_idx, coarse_hist, fed, forig, cont_q, cont_slots;
+    DevBuf tmpA, tmpB, tmpC, lat_state, ev_in, ev_out, size_ids, size_hist, sel_cloud, sel_idx, coarse_hist, fed, forig, cont_q, cont_slots, queueB, handB;
+    cudaStream_t stream2 = nullptr;   // side stream: the bucket-1 chain of the largest patches runs beside bucket 0 of the rest
+    cudaEvent_t ev_a = nullptr, ev_a2 = nullptr;
     // sharded binning (gpc_compress_shard_begin / _finish): this shard's patches are local indices [own_lo, own_hi) of a
     // binning that holds the shard's key range plus its halo; global patch index = local + gshift
     bool shard_mode = false;
@@ -116,10 +118,10 @@ void shard_range(const std::vector<int64_t>& off, int r, int c, int64_t* lo, int
 // One chain of buckets: `work` patches (ids) start in bucket b0 -- from scratch (b0 = 0) or from the state slots
 // hand_in of bucket b0 - 1's format (continued fits) -- and climb to larger buckets as they outgrow them.
 int run_buckets(gpc_handle* h, SogpArgs& a, int need_ld, int64_t lo, uint64_t* escalated, int b0, int64_t work, const int32_t* ids,
-                const double* hand_in) {
-    cudaStream_t st = h->stream;
+                const double* hand_in, int step0 = 0, cudaStream_t st = nullptr) {
+    if (!st) st = h->stream;
     a.spill = nullptr;
-    int step = 0;
+    int step = step0;   // parity picks the queue / hand-off buffers a bucket writes (the other pair is being read)
     for (int b = b0; b < 5 && work > 0; b = sogp_next_bucket(b, a.dout), step++) {
         const int bl = sogp_bucket_ld(b);
         const bool final_bucket = need_ld <= bl;
@@ -132,7 +134,7 @@ int run_buckets(gpc_handle* h, SogpArgs& a, int need_ld, int64_t lo, uint64_t* e
         DevBuf& hi_ = (step & 1) ? h->hand0 : h->hand1;
         a.queue = final_bucket ? nullptr : q.as<int32_t>();
         a.queue_count = h->qcount.as<int32_t>() + b;
-        a.handoff_in = (step > 0) ? hi_.as<double>() : hand_in;
+        a.handoff_in = (step > step0) ? hi_.as<double>() : hand_in;
         a.handoff_out = nullptr;
         if (!final_bucket) {
             CK(ho.reserve((size_t)work * sogp_handoff_slot_bytes(b, a.dout)));
@@ -147,7 +149,7 @@ int run_buckets(gpc_handle* h, SogpArgs& a, int need_ld, int64_t lo, uint64_t* e
         int32_t qn = 0;
         CK(cudaMemcpyAsync(&qn, h->qcount.as<int32_t>() + b, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        if (escalated && b < 4) escalated[b] = (uint64_t)qn;
+        if (escalated && b < 4) escalated[b] += (uint64_t)qn;
         work = qn;
         ids = q.as<int32_t>();
     }
@@ -258,8 +260,43 @@ int run_fit(gpc_handle* h, StageTimer& tm, bool cont = false) {
         CK(h->size_ids.reserve((size_t)PL * sizeof(int32_t)));
         CK(h->size_hist.reserve(1024 * sizeof(int32_t)));
         launch_size_order(h->off.as<int64_t>(), lo, PL, h->size_hist.as<int32_t>(), h->size_ids.as<int32_t>(), st);
-        int rc = run_buckets(h, a, need_ld, lo, h->stats.escalated, 0, PL, h->size_ids.as<int32_t>(), nullptr);
-        if (rc) return rc;
+        if (need_ld > sogp_bucket_ld(0) && PL >= 4096) {
+            // Patches that outgrow bucket 0 are mostly the large ones, and their bucket-1 kernel runs at low occupancy.
+            // Bucket 0 is therefore launched in two parts that run concurrently (the largest quarter of the patches on a
+            // high-priority side stream); the bucket-1 chain of part A then runs beside the rest of part B, and part B's
+            // (short) chain follows.
+            const int64_t nA = ((PL / 4) + 1) & ~(int64_t)1, nB = PL - nA;
+            CK(h->hand0.reserve((size_t)nA * sogp_handoff_slot_bytes(0, 1)));
+            CK(h->handB.reserve((size_t)nB * sogp_handoff_slot_bytes(0, 1)));
+            CK(h->queueB.reserve((size_t)nB * sizeof(int32_t)));
+            SogpArgs a0 = a;
+            a0.spill = nullptr; a0.ld = sogp_bucket_ld(0); a0.first_patch = lo; a0.handoff_in = nullptr;
+            a0.patch_ids = h->size_ids.as<int32_t>(); a0.n_work = (int)nA;
+            a0.queue = h->queue0.as<int32_t>(); a0.queue_count = h->qcount.as<int32_t>() + 0; a0.handoff_out = h->hand0.as<double>();
+            // part A on the high-priority side stream, part B on the main stream: both start now, A's CTAs are placed first
+            CK(cudaEventRecord(h->ev_a, st));
+            CK(cudaStreamWaitEvent(h->stream2, h->ev_a, 0));
+            CK(launch_sogp_fit(0, a0, h->stream2));
+            a0.patch_ids = h->size_ids.as<int32_t>() + nA; a0.n_work = (int)nB;
+            a0.queue = h->queueB.as<int32_t>(); a0.queue_count = h->qcount.as<int32_t>() + 5; a0.handoff_out = h->handB.as<double>();
+            CK(launch_sogp_fit(0, a0, st));
+            int32_t qnA = 0, qnB = 0;
+            CK(cudaMemcpyAsync(&qnA, h->qcount.as<int32_t>() + 0, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream2));
+            CK(cudaStreamSynchronize(h->stream2));
+            int rc = run_buckets(h, a, need_ld, lo, h->stats.escalated, 1, qnA, h->queue0.as<int32_t>(), h->hand0.as<double>(), 1, h->stream2);
+            if (rc) return rc;
+            CK(cudaEventRecord(h->ev_a2, h->stream2));
+            CK(cudaMemcpyAsync(&qnB, h->qcount.as<int32_t>() + 5, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            h->stats.escalated[0] += (uint64_t)qnA + (uint64_t)qnB;
+            CK(cudaStreamWaitEvent(st, h->ev_a2, 0));
+            CK(cudaMemsetAsync(h->qcount.as<int32_t>() + 1, 0, 4 * sizeof(int32_t), st));
+            rc = run_buckets(h, a, need_ld, lo, h->stats.escalated, 1, qnB, h->queueB.as<int32_t>(), h->handB.as<double>(), 1, st);
+            if (rc) return rc;
+        } else {
+            int rc = run_buckets(h, a, need_ld, lo, h->stats.escalated, 0, PL, h->size_ids.as<int32_t>(), nullptr);
+            if (rc) return rc;
+        }
     } else {
         // patches with new points, by the size of their kept state: one chain of buckets per slot format
         CK(h->cont_q.reserve((size_t)(4 * PLa + 8) * sizeof(int32_t)));
@@ -697,6 +734,15 @@ int gpc_create(const gpc_config* cfg, gpc_handle** out) {
     h->cfg = *cfg;
     std::memset(&h->stats, 0, sizeof(h->stats));
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return GPC_ERR_CUDA; }
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_a2, cudaEventDisableTiming) != cudaSuccess) {
+        cudaStreamDestroy(h->stream);
+        delete h;
+        return GPC_ERR_CUDA;
+    }
     static RandTables tables;
     static bool tables_ready = false;
     if (!tables_ready) { rand_tables_init(&tables); tables_ready = true; }
@@ -714,11 +760,14 @@ void gpc_destroy(gpc_handle* h) {
                       &h->dumpC, &h->dumpQ, &h->queue0, &h->queue1, &h->hand0, &h->hand1, &h->spill, &h->qcount, &h->kstats, &h->bv_off, &h->palpha, &h->pb1, &h->pb2, &h->pidx, &h->perm_rgb, &h->fcr, &h->fcg, &h->fcb, &h->r_nbv, &h->r_flags,
                       &h->r_alpha0, &h->r_alpha1, &h->r_alpha2, &h->r_b1, &h->r_b2, &h->r_bidx, &h->kstats_rgb, &h->nonempty, &h->slot, &h->out32,
                       &h->heights, &h->quat, &h->mean, &h->rgbmean, &h->Rm, &h->center, &h->code, &h->ncand, &h->owner,
-                      &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->lat_state, &h->ev_in, &h->ev_out, &h->size_ids, &h->size_hist, &h->sel_cloud, &h->sel_idx, &h->coarse_hist, &h->fed, &h->forig, &h->cont_q, &h->cont_slots, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
+                      &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->lat_state, &h->ev_in, &h->ev_out, &h->size_ids, &h->size_hist, &h->sel_cloud, &h->sel_idx, &h->coarse_hist, &h->fed, &h->forig, &h->cont_q, &h->cont_slots, &h->queueB, &h->handB, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
                       &h->ovals2, &h->sort_tmp, &h->flags64, &h->ex, &h->leaf_of, &h->leaf_start, &h->leaf_code_a, &h->spt,
                       &h->nbr, &h->nnbr, &h->center_a, &h->Rm_a, &h->ncand_a, &h->pt0, &h->pt1, &h->pt2, &h->hbuf, &h->rgb, &h->leaf_sums};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    if (h->ev_a) cudaEventDestroy(h->ev_a);
+    if (h->ev_a2) cudaEventDestroy(h->ev_a2);
+    if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
     cudaStreamDestroy(h->stream);
     delete h;
 }
