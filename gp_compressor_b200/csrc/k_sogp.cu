@@ -13,10 +13,12 @@
 // alpha / BV / k in registers and row r of C and of Q in shared memory; the three dot products are one product
 // per lane and a 4-step butterfly; patches are visited by decreasing size so that the two halves of a warp have
 // (almost) equal streams.  No block barrier, only __syncwarp on the half-warp's own mask.
-// Buckets 2-4 (LD 64 / 118 / 202): NT = 4*RB threads.  A warp covers 16 rows of one matrix for the matvec
-// (its two half-warps split the canonical partial sums and combine them with one shuffle); for rank-1 /
-// rank-2 updates a thread owns one row and every fourth column; the dot products are computed redundantly
-// by every warp (no broadcast barrier).
+// Bucket 1 (N + 1 <= 32): two warps per patch, warp 0 owns C and warp 1 owns Q (sogp_fit_pair_kernel).
+// Buckets 2-4 (N + 1 <= 64 / 104 / 202), height GP: sogp_fit_fused_kernel -- the update of a point and the two matvecs
+// of the next one share ONE pass over C and Q (in shared memory; in a global-memory slice for bucket 4), and a capacity
+// deletion is folded into that pass.  The step-by-step kernel sogp_fit_kernel (NT = 4*RB threads, a warp covers 16
+// rows for the matvec, a thread one row and every fourth column for the updates) serves the RGB field GP (three
+// outputs) and capacity 104..117.
 //
 // Every patch starts in bucket 0.  When a full update would not fit the bucket, the CTA
 // writes its complete state (N, next point, counters, alpha, BV, C, Q) to a hand-off slot and
