@@ -63,3 +63,52 @@ def test_binning_invariants(oracle_mod, seed, n, order):
     if P > 0:
         R = b["leaf_R"].reshape(P, 3, 3)
         assert np.abs(np.einsum("pij,pkj->pik", R, R) - np.eye(3)).max() < 1e-12
+
+
+@settings(max_examples=20, deadline=None)
+@given(seed=st.integers(0, 10_000), n=st.integers(2, 250), cut=st.floats(0.0, 1.0), cap=st.integers(1, 40))
+def test_continued_fit_equals_one_fit_without_shuffle(oracle_mod, seed, n, cut, cap):
+    """sparse_gp::add_measurements accumulates (sparse_gp.hpp:59-86): with the shuffle off, feeding the points in two calls
+    gives exactly the state of one call, whatever the cut."""
+    rng = np.random.default_rng(seed)
+    res = 0.1
+    x1 = rng.uniform(-res / 2, res / 2, n)
+    x2 = rng.uniform(-res / 2, res / 2, n)
+    y = 0.02 * np.sin(40 * x1) * np.cos(30 * x2) + rng.normal(0, 0.003, n)
+    hyp = synth.hyper_bind(res)
+    n1 = int(round(cut * n))
+    a = oracle_mod.Oracle(capacity=cap, shuffle=0, **hyp)
+    ra = a.fit_patches([0, n], x1, x2, y, dump=True)
+    b = oracle_mod.Oracle(capacity=cap, shuffle=0, **hyp)
+    b.fit_patches([0, n1], x1[:n1], x2[:n1], y[:n1], dump=True)
+    rb = b.add_measurements([0, n - n1], x1[n1:], x2[n1:], y[n1:])
+    for k in ("nbv", "bv_idx", "bv1", "bv2", "alpha", "C", "Q"):
+        assert np.array_equal(ra[k], rb[k]), k
+
+
+@settings(max_examples=20, deadline=None)
+@given(seed=st.integers(0, 10_000), n=st.integers(0, 200), cap=st.integers(1, 30), m=st.integers(1, 40))
+def test_evaluate_invariants(oracle_mod, seed, n, cap, m):
+    """Rows N2 / N4: sigma = sqrt(variance) >= 0 and never above the prior's, confidence in [0, 100], likelihood a
+    density value, the mean equals predict, and at a BV with tiny noise the fit interpolates."""
+    rng = np.random.default_rng(seed)
+    res = 0.1
+    x1 = rng.uniform(-res / 2, res / 2, n)
+    x2 = rng.uniform(-res / 2, res / 2, n)
+    y = 0.02 * np.sin(40 * x1) * np.cos(30 * x2) + rng.normal(0, 0.003, n)
+    hyp = synth.hyper_bind(res)
+    o = oracle_mod.Oracle(capacity=cap, **hyp)
+    o.fit_patches([0, n], x1, x2, y, dump=True)
+    q1 = rng.uniform(-res / 2, res / 2, m)
+    q2 = rng.uniform(-res / 2, res / 2, m)
+    qy = rng.normal(0, 0.02, m)
+    e = o.evaluate([0, m], q1, q2, qy)
+    c = o.evaluate([0, m], q1, q2, qy, conf=True)
+    prior = np.sqrt(hyp["sigmaf_sq"] + hyp["s0"])
+    assert np.all(e["sigma"] >= 0) and np.all(e["sigma"] <= prior * (1 + 1e-12))
+    assert np.all(c["sigma"] >= -1e-9) and np.all(c["sigma"] <= 100.0)
+    assert np.all(np.isfinite(e["lik"])) and np.all(e["lik"] >= 0)
+    assert np.all(np.isfinite(e["dX"]))
+    assert np.array_equal(e["f"], o.predict(0, np.stack([q1, q2], 1)))
+    if n == 0:
+        assert np.all(e["f"] == 0) and np.all(e["sigma"] == prior) and np.all(c["sigma"] == 0)
