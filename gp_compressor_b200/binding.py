@@ -19,7 +19,7 @@ GPC_OK = 0
 SYMBOLS = [
     "gpc_config_default", "gpc_create", "gpc_destroy", "gpc_last_error", "gpc_version", "gpc_compress",
     "gpc_upload_cloud", "gpc_compress_resident", "gpc_add_measurements", "gpc_compress_shard_begin", "gpc_compress_shard_finish", "gpc_fit_patches", "gpc_decompress", "gpc_decompress_resident",
-    "gpc_get_heights", "gpc_predict", "gpc_evaluate_patches", "gpc_get_sizes", "gpc_get_stats", "gpc_get_patches", "gpc_get_assignment",
+    "gpc_get_heights", "gpc_predict", "gpc_evaluate_patches", "gpc_evaluate_patches_rgb", "gpc_get_sizes", "gpc_get_stats", "gpc_get_patches", "gpc_get_assignment",
     "gpc_get_params", "gpc_get_params_rgb", "gpc_get_state", "gpc_set_params", "gpc_set_rand_offset", "gpc_get_stream", "gpc_debug_exp", "gpc_debug_rand", "gpc_debug_peak", "gpc_shard_range", "gpc_save", "gpc_load", "gpc_get_config",
 ]
 
@@ -79,6 +79,7 @@ def load():
     L.gpc_compress_shard_begin.argtypes = [vp, vp, i64, vp, vp]
     L.gpc_compress_shard_finish.argtypes = [vp, i64, C.c_uint64, i64, C.c_uint64]
     L.gpc_evaluate_patches.argtypes = [vp, i64, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp]
+    L.gpc_evaluate_patches_rgb.argtypes = [vp, i64, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp]
     L.gpc_get_sizes.argtypes = [vp, C.POINTER(GpcSizes)]
     L.gpc_get_stats.argtypes = [vp, C.POINTER(GpcStats)]
     L.gpc_get_patches.argtypes = [vp] + [vp] * 8
@@ -249,6 +250,17 @@ class Handle:
         self._ck(load().gpc_evaluate_patches(self.h, off.size - 1, _p(off), _p(x1), _p(x2), _p(yy), int(conf), _p(out["f"]),
                                              _p(out["sigma"]), _p(out["lik"]), _p(out["dX"])))
         return {k: v for k, v in out.items() if v is not None}
+
+    def evaluate_rgb(self, off, x1, x2, Y, conf=False):
+        """gpc_evaluate_patches_rgb: the RGB field GPs (rgb=1, keep_state=1); Y is m x 3 (colours centred on the patch mean)."""
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        x1, x2 = (np.ascontiguousarray(a, dtype=np.float64) for a in (x1, x2))
+        Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1, 3)
+        m = x1.size
+        out = dict(f=np.zeros((m, 3)), sigma=np.zeros(m), lik=np.zeros(m), dX=np.zeros((m, 3)))
+        self._ck(load().gpc_evaluate_patches_rgb(self.h, off.size - 1, _p(off), _p(x1), _p(x2), _p(Y), int(conf), _p(out["f"]),
+                                                 _p(out["sigma"]), _p(out["lik"]), _p(out["dX"])))
+        return out
 
     # ---- results ----------------------------------------------------------------------
     def sizes(self):

@@ -40,7 +40,7 @@ struct gpc_handle {
     DevBuf perm_rgb, fcr, fcg, fcb, r_nbv, r_flags, r_alpha0, r_alpha1, r_alpha2, r_b1, r_b2, r_bidx, kstats_rgb;
     bool have_rgb = false;
     DevBuf quat, mean, rgbmean, Rm, center, code, ncand, owner, st_idx;
-    DevBuf tmpA, tmpB, tmpC, lat_state, ev_in, ev_out, size_ids, size_hist, sel_cloud, sel_idx, coarse_hist, fed, forig, cont_q, cont_slots, queueB, handB;
+    DevBuf tmpA, tmpB, tmpC, lat_state, ev_in, ev_out, size_ids, size_hist, sel_cloud, sel_idx, coarse_hist, fed, forig, cont_q, cont_slots, queueB, handB, r_dumpC, r_dumpQ;
     cudaStream_t stream2 = nullptr;   // side stream: the bucket-1 chain of the largest patches runs beside bucket 0 of the rest
     cudaEvent_t ev_a = nullptr, ev_a2 = nullptr;
     // sharded binning (gpc_compress_shard_begin / _finish): this shard's patches are local indices [own_lo, own_hi) of a
@@ -364,6 +364,11 @@ int run_fit(gpc_handle* h, StageTimer& tm, bool cont = false) {
         r.o_b1 = h->r_b1.as<double>(); r.o_b2 = h->r_b2.as<double>();
         r.o_idx = h->r_bidx.as<int32_t>();
         r.dumpC = r.dumpQ = nullptr;
+        if (c.keep_state) {  // C of the field GPs (sigma / likelihood / gradient of the colours, gpc_evaluate_patches_rgb)
+            CK(h->r_dumpC.reserve(PLa * (size_t)cap * cap * sizeof(double)));
+            CK(h->r_dumpQ.reserve(PLa * (size_t)cap * cap * sizeof(double)));
+            r.dumpC = h->r_dumpC.as<double>(); r.dumpQ = h->r_dumpQ.as<double>();
+        }
         r.stats = h->kstats_rgb.as<unsigned long long>();
         {
             int rc = run_buckets(h, r, need_ld, lo, nullptr, 0, PL, h->size_ids.as<int32_t>(), nullptr);
@@ -760,7 +765,7 @@ void gpc_destroy(gpc_handle* h) {
                       &h->dumpC, &h->dumpQ, &h->queue0, &h->queue1, &h->hand0, &h->hand1, &h->spill, &h->qcount, &h->kstats, &h->bv_off, &h->palpha, &h->pb1, &h->pb2, &h->pidx, &h->perm_rgb, &h->fcr, &h->fcg, &h->fcb, &h->r_nbv, &h->r_flags,
                       &h->r_alpha0, &h->r_alpha1, &h->r_alpha2, &h->r_b1, &h->r_b2, &h->r_bidx, &h->kstats_rgb, &h->nonempty, &h->slot, &h->out32,
                       &h->heights, &h->quat, &h->mean, &h->rgbmean, &h->Rm, &h->center, &h->code, &h->ncand, &h->owner,
-                      &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->lat_state, &h->ev_in, &h->ev_out, &h->size_ids, &h->size_hist, &h->sel_cloud, &h->sel_idx, &h->coarse_hist, &h->fed, &h->forig, &h->cont_q, &h->cont_slots, &h->queueB, &h->handB, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
+                      &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->lat_state, &h->ev_in, &h->ev_out, &h->size_ids, &h->size_hist, &h->sel_cloud, &h->sel_idx, &h->coarse_hist, &h->fed, &h->forig, &h->cont_q, &h->cont_slots, &h->queueB, &h->handB, &h->r_dumpC, &h->r_dumpQ, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
                       &h->ovals2, &h->sort_tmp, &h->flags64, &h->ex, &h->leaf_of, &h->leaf_start, &h->leaf_code_a, &h->spt,
                       &h->nbr, &h->nnbr, &h->center_a, &h->Rm_a, &h->ncand_a, &h->pt0, &h->pt1, &h->pt2, &h->hbuf, &h->rgb, &h->leaf_sums};
     for (DevBuf* b : bufs) b->release();
@@ -1046,7 +1051,7 @@ int gpc_get_heights(gpc_handle* h, double* out, int64_t capacity) {
 }
 
 static int evaluate_impl(gpc_handle* h, int64_t op0, int64_t P, const int64_t* off, const double* x1, const double* x2, const double* y,
-                         int conf, double* f, double* sigma, double* lik, double* dX);
+                         int conf, double* f, double* sigma, double* lik, double* dX, int dout = 1);
 
 int gpc_predict(gpc_handle* h, int64_t patch, const double* X, int64_t m, double* f, double* sigma) {
     if (!h || m < 0 || (m > 0 && (!X || !f))) return GPC_ERR_INVALID;
@@ -1080,10 +1085,12 @@ int gpc_predict(gpc_handle* h, int64_t patch, const double* X, int64_t m, double
 
 // patches [op0, op0 + P) of this shard (local indices)
 static int evaluate_impl(gpc_handle* h, int64_t op0, int64_t P, const int64_t* off, const double* x1, const double* x2, const double* y,
-                         int conf, double* f, double* sigma, double* lik, double* dX) {
+                         int conf, double* f, double* sigma, double* lik, double* dX, int dout) {
     if (!h || P < 0 || (P > 0 && !off)) return GPC_ERR_INVALID;
     if (!h->have_fit || !h->cfg.keep_state || !h->dumpC.p)
         return fail(h, GPC_ERR_STATE, "sigma / likelihood evaluation needs a fit made with gpc_config.keep_state");
+    if (dout == 3 && (!h->have_rgb || !h->r_dumpC.p))
+        return fail(h, GPC_ERR_STATE, "gpc_evaluate_patches_rgb needs a compress with gpc_config.rgb = 1 and keep_state = 1");
     if (op0 < 0 || op0 + P > h->patch_hi - h->patch_lo) return fail(h, GPC_ERR_INVALID, "more patches than this shard holds");
     if (P == 0) return GPC_OK;
     const int64_t m = off[P];
@@ -1095,39 +1102,50 @@ static int evaluate_impl(gpc_handle* h, int64_t op0, int64_t P, const int64_t* o
     if (m == 0) return GPC_OK;
     const gpc_config& c = h->cfg;
     cudaStream_t st = h->stream;
-    const size_t in_bytes = (size_t)(P + 1) * sizeof(int64_t) + 3 * (size_t)m * sizeof(double);
+    const size_t in_bytes = (size_t)(P + 1) * sizeof(int64_t) + (2 + (size_t)dout) * (size_t)m * sizeof(double);
     CK(h->ev_in.reserve(in_bytes));
-    CK(h->ev_out.reserve(6 * (size_t)m * sizeof(double)));
+    CK(h->ev_out.reserve((5 + (size_t)dout) * (size_t)m * sizeof(double)));
     int64_t* d_off = h->ev_in.as<int64_t>();
     double* d_x1 = reinterpret_cast<double*>(d_off + P + 1);
     double* d_x2 = d_x1 + m;
     double* d_y = d_x2 + m;
     double* d_f = h->ev_out.as<double>();
-    double* d_sg = d_f + m;
+    double* d_sg = d_f + (size_t)dout * m;
     double* d_lk = d_sg + m;
     double* d_dx = d_lk + m;
     CK(cudaMemcpyAsync(d_off, off, (size_t)(P + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_x1, x1, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_x2, x2, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (y) CK(cudaMemcpyAsync(d_y, y, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (y) CK(cudaMemcpyAsync(d_y, y, (size_t)dout * m * sizeof(double), cudaMemcpyHostToDevice, st));
     // largest BV count (sizes the shared-memory tiles)
     CK(h->small.reserve(256));
     CK(h->nonempty.reserve((P + 1) * sizeof(int64_t)));
     int32_t* d_maxes = h->small.as<int32_t>() + 48;
-    launch_flag_nonempty(h->nbv.as<int32_t>() + op0, nullptr, P, h->nonempty.as<int64_t>(), d_maxes, st);
+    const int32_t* nbv_d = (dout == 3 ? h->r_nbv.as<int32_t>() : h->nbv.as<int32_t>()) + op0;
+    launch_flag_nonempty(nbv_d, nullptr, P, h->nonempty.as<int64_t>(), d_maxes, st);
     int32_t maxes[2] = {0, 0};
     CK(cudaMemcpyAsync(maxes, d_maxes, sizeof(maxes), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     EvalArgs a;
     a.n_patches = P;
-    a.nbv = h->nbv.as<int32_t>() + op0;
+    a.nbv = nbv_d;
     a.off = d_off;
     a.stride = c.capacity;
     a.nmax = maxes[0];
-    a.alpha = h->alpha.as<double>() + op0 * c.capacity; a.b1 = h->b1.as<double>() + op0 * c.capacity;
-    a.b2 = h->b2.as<double>() + op0 * c.capacity; a.C = h->dumpC.as<double>() + op0 * (int64_t)c.capacity * c.capacity;
+    a.dout = dout;
+    const int64_t oo = op0 * c.capacity, oc = op0 * (int64_t)c.capacity * c.capacity;
+    if (dout == 3) {
+        a.alpha[0] = h->r_alpha0.as<double>() + oo; a.alpha[1] = h->r_alpha1.as<double>() + oo; a.alpha[2] = h->r_alpha2.as<double>() + oo;
+        a.b1 = h->r_b1.as<double>() + oo; a.b2 = h->r_b2.as<double>() + oo; a.C = h->r_dumpC.as<double>() + oc;
+        a.s20 = c.rgb_s0;
+    } else {
+        a.alpha[0] = h->alpha.as<double>() + oo; a.alpha[1] = a.alpha[2] = nullptr;
+        a.b1 = h->b1.as<double>() + oo; a.b2 = h->b2.as<double>() + oo; a.C = h->dumpC.as<double>() + oc;
+        a.s20 = c.s0;
+    }
     a.x1 = d_x1; a.x2 = d_x2; a.y = y ? d_y : nullptr;
-    a.p0 = c.sigmaf_sq; a.cl = kernel_cl(c); a.c1 = (-c.sigmaf_sq) / c.l_sq; a.s20 = c.s0;
+    a.p0 = c.sigmaf_sq; a.cl = kernel_cl(c); a.c1 = (-c.sigmaf_sq) / c.l_sq;
+    a.pow2pi3 = std::pow(2.0 * M_PI, 3.0);   // pow(2.0f*M_PI, double(y.rows())), sparse_gp_field.hpp:350
     a.conf = conf;
     a.f = f ? d_f : nullptr; a.sigma = sigma ? d_sg : nullptr; a.lik = lik ? d_lk : nullptr; a.dX = dX ? d_dx : nullptr;
     StageTimer tm(h);
@@ -1136,7 +1154,7 @@ static int evaluate_impl(gpc_handle* h, int64_t op0, int64_t P, const int64_t* o
     if (launch_evaluate(a, st) != cudaSuccess) return fail(h, GPC_ERR_CUDA, "evaluate kernel launch failed");
     size_t t1 = tm.mark();
     tm.span(&h->stats.ms_evaluate, t0, t1);
-    if (f) CK(cudaMemcpyAsync(f, d_f, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (f) CK(cudaMemcpyAsync(f, d_f, (size_t)dout * m * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (sigma) CK(cudaMemcpyAsync(sigma, d_sg, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (lik) CK(cudaMemcpyAsync(lik, d_lk, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (dX) CK(cudaMemcpyAsync(dX, d_dx, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1149,6 +1167,11 @@ static int evaluate_impl(gpc_handle* h, int64_t op0, int64_t P, const int64_t* o
 int gpc_evaluate_patches(gpc_handle* h, int64_t P, const int64_t* off, const double* x1, const double* x2, const double* y,
                          int conf, double* f, double* sigma, double* lik, double* dX) {
     return evaluate_impl(h, 0, P, off, x1, x2, y, conf, f, sigma, lik, dX);
+}
+
+int gpc_evaluate_patches_rgb(gpc_handle* h, int64_t P, const int64_t* off, const double* x1, const double* x2, const double* y3,
+                             int conf, double* f3, double* sigma, double* lik, double* dX) {
+    return evaluate_impl(h, 0, P, off, x1, x2, y3, conf, f3, sigma, lik, dX, 3);
 }
 
 int gpc_get_sizes(gpc_handle* h, gpc_sizes* s) {

@@ -208,9 +208,12 @@ struct EvalArgs {
     const int64_t* off;            // n_patches + 1 offsets into the query arrays
     int stride;                    // parameter stride per patch (capacity); C at patch * stride^2, packed N x N
     int nmax;                      // largest nbv among the patches
-    const double *alpha, *b1, *b2, *C;
+    int dout;                      // 1: height GP, 3: RGB field GP (y, f: dout values per point)
+    const double* alpha[3];
+    const double *b1, *b2, *C;
     const double *x1, *x2, *y;     // y may be nullptr
     double p0, cl, c1, s20;        // c1 = -p0 / p1 (rbf_kernel.cpp:44)
+    double pow2pi3;                // pow(2 pi, 3): the field GP's density normalisation (sparse_gp_field.hpp:350)
     int conf;
     double *f, *sigma, *lik, *dX;  // any may be nullptr
 };

@@ -23,7 +23,9 @@ namespace {
 constexpr int EV_T = 32;     // points per tile
 constexpr int EV_NT = 128;   // threads per CTA
 
-template <int RPT, bool CSMEM>
+// DOUT = 1: sparse_gp (heights).  DOUT = 3: sparse_gp_field (RGB), sparse_gp_field.hpp:267-393: three alpha columns, the
+// residual is a 3-vector (squaredNorm in the exponent, pow(2 pi, 3) in the density), dX[0] = 0.
+template <int RPT, bool CSMEM, int DOUT>
 __global__ void __launch_bounds__(EV_NT) evaluate_kernel(EvalArgs a) {
     extern __shared__ __align__(16) double sm[];
     const int64_t p = blockIdx.x;
@@ -33,21 +35,26 @@ __global__ void __launch_bounds__(EV_NT) evaluate_kernel(EvalArgs a) {
     if (n == 0) return;
     const int t = threadIdx.x;
     const int LDC = (N + 3) & ~3;
-    // layout: K, E, CK [N x 32] | red [6 x 32] | xs, ys, yv [32] | al, b1, b2 [N] | C [N x LDC]
+    // layout: K, E, CK [N x 32] | red [(3 + 3 DOUT) x 32] | xs, ys [32], yv [DOUT x 32] | al [DOUT x N], b1, b2 [N] | C [N x LDC]
     double* K = sm;
     double* E = K + (size_t)N * EV_T;
     double* CK = E + (size_t)N * EV_T;
     double* red = CK + (size_t)N * EV_T;
-    double* xs = red + 6 * EV_T;
+    constexpr int NRED = 3 + 3 * DOUT;
+    double* xs = red + NRED * EV_T;
     double* ys = xs + EV_T;
     double* yv = ys + EV_T;
-    double* al = yv + EV_T;
-    double* b1 = al + N;
+    double* al = yv + DOUT * EV_T;
+    double* b1 = al + DOUT * N;
     double* b2 = b1 + N;
-    double* Cs = b2 + N + ((3 * N) & 1);  // 16-byte aligned
+    double* Cs = b2 + N + (((DOUT + 2) * N + NRED * EV_T + DOUT * EV_T) & 1);  // 16-byte aligned
     const int64_t pb = p * a.stride;
     const double* Cg = a.C + p * (int64_t)a.stride * a.stride;  // packed N x N
-    for (int i = t; i < N; i += EV_NT) { al[i] = a.alpha[pb + i]; b1[i] = a.b1[pb + i]; b2[i] = a.b2[pb + i]; }
+    for (int i = t; i < N; i += EV_NT) {
+#pragma unroll
+        for (int c = 0; c < DOUT; c++) al[c * N + i] = a.alpha[c][pb + i];
+        b1[i] = a.b1[pb + i]; b2[i] = a.b2[pb + i];
+    }
     if (CSMEM) {
         for (int e = t; e < N * LDC; e += EV_NT) {
             const int j = e / LDC, i = e - j * LDC;
@@ -61,7 +68,8 @@ __global__ void __launch_bounds__(EV_NT) evaluate_kernel(EvalArgs a) {
             const int q = tile + t;
             xs[t] = (q < n) ? a.x1[o + q] : 0.0;
             ys[t] = (q < n) ? a.x2[o + q] : 0.0;
-            yv[t] = (q < n && a.y) ? a.y[o + q] : 0.0;
+#pragma unroll
+            for (int c = 0; c < DOUT; c++) yv[c * EV_T + t] = (q < n && a.y) ? a.y[(o + q) * DOUT + c] : 0.0;
         }
         __syncthreads();
         // (1) kernel values
@@ -120,7 +128,10 @@ __global__ void __launch_bounds__(EV_NT) evaluate_kernel(EvalArgs a) {
             const int w = t >> 5, tt = t & 31;
             const double x1 = xs[tt], x2 = ys[tt];
             if (w < 3) {
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1_ = 0.0, b2_ = 0.0, b3 = 0.0;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                double bb[DOUT][4];
+#pragma unroll
+                for (int c = 0; c < DOUT; c++) bb[c][0] = bb[c][1] = bb[c][2] = bb[c][3] = 0.0;
                 auto fac = [&](int i) {
                     if (w == 0) return K[i * EV_T + tt];
                     const double d = (w == 1) ? __dadd_rn(x1, -b1[i]) : __dadd_rn(x2, -b2[i]);
@@ -131,13 +142,28 @@ __global__ void __launch_bounds__(EV_NT) evaluate_kernel(EvalArgs a) {
                     const double f0 = fac(i), f1 = fac(i + 1), f2 = fac(i + 2), f3 = fac(i + 3);
                     a0 = fma(f0, CK[i * EV_T + tt], a0); a1 = fma(f1, CK[(i + 1) * EV_T + tt], a1);
                     a2 = fma(f2, CK[(i + 2) * EV_T + tt], a2); a3 = fma(f3, CK[(i + 3) * EV_T + tt], a3);
-                    b0 = fma(al[i], f0, b0); b1_ = fma(al[i + 1], f1, b1_); b2_ = fma(al[i + 2], f2, b2_); b3 = fma(al[i + 3], f3, b3);
+#pragma unroll
+                    for (int c = 0; c < DOUT; c++) {
+                        const double* ac = al + c * N;
+                        bb[c][0] = fma(ac[i], f0, bb[c][0]); bb[c][1] = fma(ac[i + 1], f1, bb[c][1]);
+                        bb[c][2] = fma(ac[i + 2], f2, bb[c][2]); bb[c][3] = fma(ac[i + 3], f3, bb[c][3]);
+                    }
                 }
-                if (i < N) { const double f = fac(i); a0 = fma(f, CK[i * EV_T + tt], a0); b0 = fma(al[i], f, b0); }
-                if (i + 1 < N) { const double f = fac(i + 1); a1 = fma(f, CK[(i + 1) * EV_T + tt], a1); b1_ = fma(al[i + 1], f, b1_); }
-                if (i + 2 < N) { const double f = fac(i + 2); a2 = fma(f, CK[(i + 2) * EV_T + tt], a2); b2_ = fma(al[i + 2], f, b2_); }
+#pragma unroll
+                for (int u = 0; u < 3; u++)
+                    if (i + u < N) {
+                        const double f = fac(i + u);
+                        if (u == 0) a0 = fma(f, CK[(i + u) * EV_T + tt], a0);
+                        if (u == 1) a1 = fma(f, CK[(i + u) * EV_T + tt], a1);
+                        if (u == 2) a2 = fma(f, CK[(i + u) * EV_T + tt], a2);
+#pragma unroll
+                        for (int c = 0; c < DOUT; c++) bb[c][u] = fma(al[c * N + i + u], f, bb[c][u]);
+                    }
+                // red rows: 0..2 = k'Ck, kdx'Ck, kdy'Ck; 3 + 3 c + w = alpha_c' (k | kdx | kdy)
                 red[w * EV_T + tt] = __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
-                red[(3 + w) * EV_T + tt] = __dadd_rn(__dadd_rn(b0, b1_), __dadd_rn(b2_, b3));
+#pragma unroll
+                for (int c = 0; c < DOUT; c++)
+                    red[(3 + 3 * c + w) * EV_T + tt] = __dadd_rn(__dadd_rn(bb[c][0], bb[c][1]), __dadd_rn(bb[c][2], bb[c][3]));
             }
         }
         __syncthreads();
@@ -145,33 +171,54 @@ __global__ void __launch_bounds__(EV_NT) evaluate_kernel(EvalArgs a) {
         if (t < EV_T && tile + t < n) {
             const int64_t q = o + tile + t;
             const double kCk = red[t], sx = red[EV_T + t], sy = red[2 * EV_T + t];
-            const double mu = red[3 * EV_T + t], ax = red[4 * EV_T + t], ay = red[5 * EV_T + t];
-            // predict, sparse_gp.hpp:329-349
+            double mu[DOUT], ax[DOUT], ay[DOUT], off[DOUT];
+#pragma unroll
+            for (int c = 0; c < DOUT; c++) {
+                mu[c] = red[(3 + 3 * c) * EV_T + t]; ax[c] = red[(4 + 3 * c) * EV_T + t]; ay[c] = red[(5 + 3 * c) * EV_T + t];
+                off[c] = __dadd_rn(yv[c * EV_T + t], -mu[c]);
+            }
+            // predict, sparse_gp.hpp:329-349 / sparse_gp_field.hpp:296-318
             double var = __dadd_rn(__dadd_rn(s20, kstar), kCk);
             const double var_l = var;
             if (var < 0.0) var = 0.0;
-            if (a.f) a.f[q] = mu;
+            if (a.f) {
+#pragma unroll
+                for (int c = 0; c < DOUT; c++) a.f[q * DOUT + c] = mu[c];
+            }
             if (a.sigma)
                 a.sigma[q] = a.conf ? __dmul_rn(100.0, __dadd_rn(1.0, -__ddiv_rn(var, __dadd_rn(kstar, s20)))) : __dsqrt_rn(var);
-            const double off = __dadd_rn(yv[t], -mu);
-            if (a.lik) {  // :424
-                const double two_pi = 6.283185307179586;
-                const double ex = gpc_exp(__dmul_rn(__dmul_rn(__ddiv_rn(-0.5, var_l), off), off));
-                a.lik[q] = __dmul_rn(__ddiv_rn(1.0, __dsqrt_rn(__dmul_rn(two_pi, var_l))), ex);
+            // the residual enters as off^2 (scalar: ((-0.5/var) off) off, :424 / :495) or as squaredNorm (field, :350 / :383)
+            double sqn = 0.0;
+            if (DOUT == 3) sqn = __dadd_rn(__dadd_rn(__dmul_rn(off[0], off[0]), __dmul_rn(off[DOUT > 1 ? 1 : 0], off[DOUT > 1 ? 1 : 0])),
+                                           __dmul_rn(off[DOUT > 2 ? 2 : 0], off[DOUT > 2 ? 2 : 0]));
+            if (a.lik) {
+                const double arg = (DOUT == 1) ? __dmul_rn(__dmul_rn(__ddiv_rn(-0.5, var_l), off[0]), off[0])
+                                               : __dmul_rn(__ddiv_rn(-0.5, var_l), sqn);
+                const double norm = (DOUT == 1) ? 6.283185307179586 : a.pow2pi3;
+                a.lik[q] = __dmul_rn(__ddiv_rn(1.0, __dsqrt_rn(__dmul_rn(norm, var_l))), gpc_exp(arg));
             }
-            if (a.dX) {  // :487-499
+            if (a.dX) {  // sparse_gp.hpp:487-499 / sparse_gp_field.hpp:378-390
                 const double var_d = __dadd_rn(__dadd_rn(s20, kCk), kstar);
                 const double sdx[2] = {__dmul_rn(2.0, sx), __dmul_rn(2.0, sy)};
-                const double ad[2] = {ax, ay};
                 const double sq = __dsqrt_rn(var_d);
                 const double vs = __dmul_rn(var_d, sq);
-                const double exppart = __dmul_rn(__ddiv_rn(0.5, vs), gpc_exp(__dmul_rn(__dmul_rn(__ddiv_rn(-0.5, var_d), off), off)));
-                a.dX[3 * q] = __dmul_rn(__dmul_rn(__ddiv_rn(-1.0, vs), off), exppart);
+                const double arg = (DOUT == 1) ? __dmul_rn(__dmul_rn(__ddiv_rn(-0.5, var_d), off[0]), off[0])
+                                               : __dmul_rn(__ddiv_rn(-0.5, var_d), sqn);
+                const double exppart = __dmul_rn(__ddiv_rn(0.5, vs), gpc_exp(arg));
+                a.dX[3 * q] = (DOUT == 1) ? __dmul_rn(__dmul_rn(__ddiv_rn(-1.0, vs), off[0]), exppart) : 0.0;
 #pragma unroll
                 for (int d = 0; d < 2; d++) {
+                    const double* A = d ? ay : ax;
                     const double first = -sdx[d];
-                    const double second = __dmul_rn(__dmul_rn(2.0, ad[d]), off);
-                    const double third = __dmul_rn(__dmul_rn(__ddiv_rn(sdx[d], var_d), off), off);
+                    double second, third;
+                    if (DOUT == 1) {
+                        second = __dmul_rn(__dmul_rn(2.0, A[0]), off[0]);
+                        third = __dmul_rn(__dmul_rn(__ddiv_rn(sdx[d], var_d), off[0]), off[0]);
+                    } else {
+                        second = __dmul_rn(2.0, __dadd_rn(__dadd_rn(__dmul_rn(A[0], off[0]), __dmul_rn(A[DOUT > 1 ? 1 : 0], off[DOUT > 1 ? 1 : 0])),
+                                                          __dmul_rn(A[DOUT > 2 ? 2 : 0], off[DOUT > 2 ? 2 : 0])));
+                        third = __dmul_rn(__ddiv_rn(sdx[d], var_d), sqn);
+                    }
                     a.dX[3 * q + 1 + d] = __dmul_rn(exppart, __dadd_rn(__dadd_rn(first, second), third));
                 }
             }
@@ -179,30 +226,35 @@ __global__ void __launch_bounds__(EV_NT) evaluate_kernel(EvalArgs a) {
     }
 }
 
-template <int RPT, bool CSMEM>
+template <int RPT, bool CSMEM, int DOUT>
 cudaError_t launch_variant(const EvalArgs& a, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(evaluate_kernel<RPT, CSMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(evaluate_kernel<RPT, CSMEM, DOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    evaluate_kernel<RPT, CSMEM><<<(unsigned)a.n_patches, EV_NT, smem, s>>>(a);
+    evaluate_kernel<RPT, CSMEM, DOUT><<<(unsigned)a.n_patches, EV_NT, smem, s>>>(a);
     return cudaGetLastError();
+}
+
+template <int DOUT>
+cudaError_t launch_evaluate_d(const EvalArgs& a, cudaStream_t s) {
+    const int64_t N = std::max(a.nmax, 1);
+    const int64_t LDC = (N + 3) & ~(int64_t)3;
+    const int64_t base = 3 * N * EV_T + (3 + 3 * DOUT) * EV_T + (2 + DOUT) * EV_T + (DOUT + 2) * N + 1;
+    const int64_t with_c = base + N * LDC;
+    const int64_t budget = 220 * 1024 / (int64_t)sizeof(double);
+    if (with_c <= budget) {
+        const size_t smem = (size_t)with_c * sizeof(double);
+        return N > 32 ? launch_variant<4, true, DOUT>(a, smem, s) : launch_variant<1, true, DOUT>(a, smem, s);
+    }
+    if (base > budget) return cudaErrorInvalidConfiguration;
+    return launch_variant<4, false, DOUT>(a, (size_t)base * sizeof(double), s);
 }
 
 }  // namespace
 
 cudaError_t launch_evaluate(const EvalArgs& a, cudaStream_t s) {
     if (a.n_patches <= 0) return cudaSuccess;
-    const int64_t N = std::max(a.nmax, 1);
-    const int64_t LDC = (N + 3) & ~(int64_t)3;
-    const int64_t base = 3 * N * EV_T + 6 * EV_T + 3 * EV_T + 3 * N + 1;
-    const int64_t with_c = base + N * LDC;
-    const int64_t budget = 220 * 1024 / (int64_t)sizeof(double);
     g_launches++;
-    if (with_c <= budget) {
-        const size_t smem = (size_t)with_c * sizeof(double);
-        return N > 32 ? launch_variant<4, true>(a, smem, s) : launch_variant<1, true>(a, smem, s);
-    }
-    if (base > budget) return cudaErrorInvalidConfiguration;
-    return launch_variant<4, false>(a, (size_t)base * sizeof(double), s);
+    return a.dout == 3 ? launch_evaluate_d<3>(a, s) : launch_evaluate_d<1>(a, s);
 }
 
 }  // namespace gpc

@@ -152,6 +152,13 @@ int gpc_predict(gpc_handle* h, int64_t patch, const double* X, int64_t m, double
 int gpc_evaluate_patches(gpc_handle* h, int64_t P, const int64_t* off, const double* x1, const double* x2, const double* y,
                          int conf, double* f, double* sigma, double* lik, double* dX);
 
+/* The same for the RGB field GPs (gpc_config.rgb = 1 and keep_state = 1 at compress time): sparse_gp_field::
+ * predict_measurements with sigconf / conf (sparse_gp_field.hpp:267-320), compute_likelihoods (:322-351) and
+ * compute_derivatives (:353-393), which gp_registration.cpp:177,194 calls beside the height GP's.  y3 and f3 hold three
+ * values per point (the colours centred on the patch mean, as the fit saw them); dX three per point with dX[0] = 0. */
+int gpc_evaluate_patches_rgb(gpc_handle* h, int64_t P, const int64_t* off, const double* x1, const double* x2, const double* y3,
+                             int conf, double* f3, double* sigma, double* lik, double* dX);
+
 /* ---- results ---------------------------------------------------------------------------
  * Any output pointer may be NULL.  Per-patch arrays are indexed by gp_index over ALL
  * patches (frames are computed on every shard); fitted parameters cover this shard only

@@ -445,6 +445,55 @@ struct Sogp {
             out[5 + d] = exppart * ((first + second) + third);
         }
     }
+    // The same for the RGB field GP (D = 3): sparse_gp_field::predict with sigma / conf (sparse_gp_field.hpp:284-320),
+    // likelihood (:333-351) and likelihood_dx (:367-393).  y: 3 values.  out: f[3], sigma, conf, lik, dx[3] (dx[0] = 0).
+    void evaluate_field(double x1, double x2, const double* y, double* out) {
+        std::vector<double> kx(std::max(N, 1)), ky(std::max(N, 1));
+        const double kstar = P.p0;
+        const double c1 = (-P.p0) / P.p1;
+        for (int i = 0; i < N; i++) {
+            const double d1 = x1 - b1[i], d2 = x2 - b2[i];
+            const double e = orc_exp_impl(P.cl * (d1 * d1 + d2 * d2));
+            k[i] = P.p0 * e;
+            kx[i] = (c1 * d1) * e;
+            ky[i] = (c1 * d2) * e;
+        }
+        for (int i = 0; i < N; i++) {
+            double a = 0.0;
+            for (int j = 0; j < N; j++) a = std::fma(C[(size_t)j * ld + i], k[j], a);
+            ck[i] = a;
+        }
+        const double kCk = N ? row4(k.data(), ck.data(), N) : 0.0;
+        const double sx = N ? row4(kx.data(), ck.data(), N) : 0.0, sy = N ? row4(ky.data(), ck.data(), N) : 0.0;
+        double mu[3], ax[3], ay[3], off[3];
+        for (int c = 0; c < 3; c++) {
+            const double* a = &alpha[(size_t)c * ld];
+            mu[c] = N ? row4(a, k.data(), N) : 0.0;
+            ax[c] = N ? row4(a, kx.data(), N) : 0.0;
+            ay[c] = N ? row4(a, ky.data(), N) : 0.0;
+            off[c] = y[c] - mu[c];
+            out[c] = mu[c];
+        }
+        double var = (P.s20 + kstar) + kCk;
+        const double var_l = var;
+        if (var < 0) var = 0;
+        out[3] = std::sqrt(var);
+        out[4] = 100.0 * (1.0 - var / (kstar + P.s20));
+        const double sqn = (off[0] * off[0] + off[1] * off[1]) + off[2] * off[2];      // squaredNorm
+        const double pow2pi3 = std::pow(2.0 * M_PI, 3.0);                               // pow(2.0f*M_PI, double(y.rows()))
+        out[5] = (1.0 / std::sqrt(pow2pi3 * var_l)) * orc_exp_impl((-0.5 / var_l) * sqn);
+        const double var_d = (P.s20 + kCk) + kstar;
+        const double sdx[2] = {2.0 * sx, 2.0 * sy};
+        const double sq = std::sqrt(var_d);
+        const double exppart = (0.5 / (var_d * sq)) * orc_exp_impl((-0.5 / var_d) * sqn);
+        out[6] = 0.0;
+        for (int d = 0; d < 2; d++) {
+            const double* A = d ? ay : ax;
+            const double second = 2.0 * ((A[0] * off[0] + A[1] * off[1]) + A[2] * off[2]);
+            const double third = (sdx[d] / var_d) * sqn;
+            out[7 + d] = exppart * ((-sdx[d] + second) + third);
+        }
+    }
     // predictive sigma as sparse_gp.hpp:329-347 (conf = false): sqrt(s20 + kstar + k'Ck), the evaluate() arithmetic
     double predict_sigma(double x1, double x2) {
         double r[7];
@@ -742,6 +791,8 @@ struct Oracle {
     std::vector<int32_t> rgb_nbv, rgb_bv_idx;  // RGB field GP results
     std::vector<int64_t> rgb_bv_off;
     std::vector<double> rgb_bv1, rgb_bv2, rgb_alpha;  // rgb_alpha: 3 per BV (r,g,b)
+    std::vector<double> rgb_dumpC;             // optional dense C of the field GPs (N*N per patch)
+    std::vector<int64_t> rgb_dump_off;
     SogpStats stats_rgb;
     // ---- fit results ----
     std::vector<int32_t> nbv;                  // per patch
@@ -1085,7 +1136,7 @@ struct Oracle {
         stats_rgb = SogpStats();
         if (do_rgb) {
             const SogpParams rp = rgb_params();
-            std::vector<std::vector<double>> rA(NP), rB1(NP), rB2(NP);
+            std::vector<std::vector<double>> rA(NP), rB1(NP), rB2(NP), rC(NP);
             std::vector<std::vector<int32_t>> rI(NP);
             std::vector<SogpStats> rstats(std::max(1, nth));
             parallel_for(NP, nth, [&](int tid, int64_t b, int64_t e) {
@@ -1107,11 +1158,21 @@ struct Oracle {
                     rB1[p].assign(gp.b1.begin(), gp.b1.begin() + gp.N);
                     rB2[p].assign(gp.b2.begin(), gp.b2.begin() + gp.N);
                     rI[p].assign(gp.idx.begin(), gp.idx.begin() + gp.N);
+                    if (dump) {
+                        rC[p].resize((size_t)gp.N * gp.N);
+                        for (int i = 0; i < gp.N; i++)
+                            for (int j = 0; j < gp.N; j++) rC[p][(size_t)i * gp.N + j] = gp.c(i, j);
+                    }
                     rstats[tid].merge(gp.st);
                 }
             });
             for (auto& s : rstats) stats_rgb.merge(s);
             for (int64_t p = 0; p < NP; p++) rgb_bv_off[p + 1] = rgb_bv_off[p] + rgb_nbv[p];
+            rgb_dump_off.assign(NP + 1, 0);
+            for (int64_t p = 0; p < NP; p++) rgb_dump_off[p + 1] = rgb_dump_off[p] + (dump ? (int64_t)rgb_nbv[p] * rgb_nbv[p] : 0);
+            rgb_dumpC.resize(rgb_dump_off[NP]);
+            if (dump)
+                for (int64_t p = 0; p < NP; p++) std::copy(rC[p].begin(), rC[p].end(), rgb_dumpC.begin() + rgb_dump_off[p]);
             rgb_bv_idx.resize(rgb_bv_off[NP]); rgb_bv1.resize(rgb_bv_off[NP]); rgb_bv2.resize(rgb_bv_off[NP]);
             rgb_alpha.resize(3 * rgb_bv_off[NP]);
             for (int64_t p = 0; p < NP; p++) {
@@ -1350,6 +1411,35 @@ int orc_evaluate(void* h, int64_t P, const int64_t* off, const double* x1, const
             if (sigma) sigma[t] = conf ? r[2] : r[1];
             if (lik) lik[t] = r[3];
             if (dX) { dX[3 * t] = r[4]; dX[3 * t + 1] = r[5]; dX[3 * t + 2] = r[6]; }
+        }
+    }
+    return 0;
+}
+
+// The RGB field GPs of the previous fit (with colours and dump): y = 3 values per point; f = 3 per point, dX = 3 per point
+int orc_evaluate_rgb(void* h, int64_t P, const int64_t* off, const double* x1, const double* x2, const double* y3, int conf,
+                     double* f3, double* sigma, double* lik, double* dX) {
+    Oracle* o = (Oracle*)h;
+    if (P < 0 || P > (int64_t)o->rgb_nbv.size()) return 1;
+    Sogp gp;
+    const double zero3[3] = {0, 0, 0};
+    for (int64_t p = 0; p < P; p++) {
+        const int N = o->rgb_nbv[p];
+        if (N > 0 && o->rgb_dumpC.empty()) return 1;
+        gp.init(o->rgb_params(), std::max(N, 1), 3);
+        gp.N = N;
+        for (int i = 0; i < N; i++) {
+            gp.b1[i] = o->rgb_bv1[o->rgb_bv_off[p] + i]; gp.b2[i] = o->rgb_bv2[o->rgb_bv_off[p] + i];
+            for (int ch = 0; ch < 3; ch++) gp.al(ch, i) = o->rgb_alpha[3 * (o->rgb_bv_off[p] + i) + ch];
+            for (int j = 0; j < N; j++) gp.c(i, j) = o->rgb_dumpC[o->rgb_dump_off[p] + (size_t)i * N + j];
+        }
+        for (int64_t t = off[p]; t < off[p + 1]; t++) {
+            double r[9];
+            gp.evaluate_field(x1[t], x2[t], y3 ? &y3[3 * t] : zero3, r);
+            if (f3) { f3[3 * t] = r[0]; f3[3 * t + 1] = r[1]; f3[3 * t + 2] = r[2]; }
+            if (sigma) sigma[t] = conf ? r[4] : r[3];
+            if (lik) lik[t] = r[5];
+            if (dX) { dX[3 * t] = r[6]; dX[3 * t + 1] = r[7]; dX[3 * t + 2] = r[8]; }
         }
     }
     return 0;

@@ -65,6 +65,8 @@ def lib():
         L.orc_predict.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.orc_add_measurements.restype = C.c_int
         L.orc_add_measurements.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 4
+        L.orc_evaluate_rgb.restype = C.c_int
+        L.orc_evaluate_rgb.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4
         L.orc_evaluate.restype = C.c_int
         L.orc_evaluate.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4
         L.orc_get_sizes.argtypes = [C.c_void_p, C.POINTER(OrcSizes)]
@@ -291,6 +293,17 @@ class Oracle:
         rc = lib().orc_evaluate(self.h, off.size - 1, _p(off), _p(x1), _p(x2), _p(y), int(conf), _p(f), _p(sg), _p(lk), _p(dX))
         assert rc == 0, "orc_evaluate needs the state dump (fit with dump=True)"
         return dict(f=f, sigma=sg, lik=lk, dX=dX.reshape(m, 3))
+
+    def evaluate_rgb(self, off, x1, x2, Y, conf=False):
+        """The same for the RGB field GPs of the previous fit_patches(colours=..., dump=True): Y is m x 3."""
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        x1, x2 = (np.ascontiguousarray(a, dtype=np.float64) for a in (x1, x2))
+        Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1, 3)
+        m = x1.size
+        f, sg, lk, dX = np.zeros(3 * m), np.zeros(m), np.zeros(m), np.zeros(3 * m)
+        rc = lib().orc_evaluate_rgb(self.h, off.size - 1, _p(off), _p(x1), _p(x2), _p(Y), int(conf), _p(f), _p(sg), _p(lk), _p(dX))
+        assert rc == 0, "orc_evaluate_rgb needs the field GPs' state dump (fit with colours and dump=True)"
+        return dict(f=f.reshape(m, 3), sigma=sg, lik=lk, dX=dX.reshape(m, 3))
 
     def predict(self, patch, X, sigma=False):
         X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, 2)

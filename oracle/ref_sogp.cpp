@@ -156,6 +156,34 @@ int ref_sogp_fit_twice(int n1, int n2, const double* x1, const double* x2, const
     return N;
 }
 
+// Field GP: fit, then the reference's own predict_measurements (sigma and conf), compute_likelihoods and
+// compute_derivatives (sparse_gp_field.hpp:267-393) at the given points.  Y / EY: 3 per point, row-major.
+int ref_field_evaluate(int n, const double* x1, const double* x2, const double* Y, int capacity, double s0, double sigmaf_sq,
+                       double l_sq, double eps_tol, unsigned long long rand_offset, int m, const double* ex1, const double* ex2,
+                       const double* EY, double* f3, double* sigma, double* conf, double* lik, double* dX) {
+    srand(1);
+    for (unsigned long long i = 0; i < rand_offset; i++) rand();
+    ref_gp_field gp(capacity, s0);
+    gp.kernel.param()(0) = sigmaf_sq;
+    gp.kernel.param()(1) = l_sq;
+    gp.eps_tol = eps_tol;
+    Eigen::MatrixXd X(n, 2), C(n, 3);
+    for (int i = 0; i < n; i++) { X(i, 0) = x1[i]; X(i, 1) = x2[i]; for (int c = 0; c < 3; c++) C(i, c) = Y[3 * i + c]; }
+    if (n > 0) gp.add_measurements(X, C);
+    Eigen::MatrixXd Xs(m, 2), Ys(m, 3), F, D;
+    for (int i = 0; i < m; i++) { Xs(i, 0) = ex1[i]; Xs(i, 1) = ex2[i]; for (int c = 0; c < 3; c++) Ys(i, c) = EY[3 * i + c]; }
+    Eigen::VectorXd sg, cf, l;
+    gp.predict_measurements(F, Xs, sg, false);
+    gp.predict_measurements(F, Xs, cf, true);
+    gp.compute_likelihoods(l, Xs, Ys);
+    gp.compute_derivatives(D, Xs, Ys);
+    for (int i = 0; i < m; i++) {
+        sigma[i] = sg(i); conf[i] = cf(i); lik[i] = l(i);
+        for (int c = 0; c < 3; c++) { f3[3 * i + c] = F(i, c); dX[3 * i + c] = D(i, c); }
+    }
+    return gp.size();
+}
+
 // sparse_gp::shuffle alone (sparse_gp.hpp:42-56) over the real rand()
 void ref_shuffle(int n, unsigned long long rand_offset, int* out) {
     srand(1);

@@ -34,6 +34,9 @@ def lib():
         L.ref_sogp_fit_twice.restype = C.c_int
         L.ref_sogp_fit_twice.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double,
                                          C.c_double, C.c_ulonglong, C.c_int] + [C.c_void_p] * 5
+        L.ref_field_evaluate.restype = C.c_int
+        L.ref_field_evaluate.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                         C.c_ulonglong, C.c_int] + [C.c_void_p] * 8
         L.ref_kernel.restype = C.c_double
         L.ref_kernel.argtypes = [C.c_double] * 6
         _LIB = L
@@ -91,6 +94,21 @@ def fit_twice(x1, x2, y, n1, capacity=100, s0=float(np.float32(1e-1)), sigmaf_sq
     assert N >= 0
     return dict(N=N, alpha=alpha[:N].copy(), bv1=b1[:N].copy(), bv2=b2[:N].copy(), C=Cm[:N * N].reshape(N, N).copy(),
                 Q=Qm[:N * N].reshape(N, N).copy())
+
+
+def field_evaluate(x1, x2, Y, ex, EY, capacity=100, s0=float(np.float32(1e2)), sigmaf_sq=100.0, l_sq=1.0,
+                   eps_tol=float(np.float32(1e-4)), rand_offset=0):
+    """Field GP: fit, then the reference's predict_measurements (sigma / conf), compute_likelihoods, compute_derivatives."""
+    x1, x2 = (np.ascontiguousarray(a, dtype=np.float64) for a in (x1, x2))
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1, 3)
+    ex = np.ascontiguousarray(ex, dtype=np.float64).reshape(-1, 2)
+    EY = np.ascontiguousarray(EY, dtype=np.float64).reshape(-1, 3)
+    m = ex.shape[0]
+    e1, e2 = np.ascontiguousarray(ex[:, 0]), np.ascontiguousarray(ex[:, 1])
+    f, sg, cf, lk, dX = np.zeros(3 * m), np.zeros(m), np.zeros(m), np.zeros(m), np.zeros(3 * m)
+    N = lib().ref_field_evaluate(x1.size, _p(x1), _p(x2), _p(Y), capacity, s0, sigmaf_sq, l_sq, eps_tol, rand_offset, m, _p(e1), _p(e2),
+                                 _p(EY), _p(f), _p(sg), _p(cf), _p(lk), _p(dX))
+    return dict(N=N, f=f.reshape(m, 3), sigma=sg, conf=cf, lik=lk, dX=dX.reshape(m, 3))
 
 
 def field_fit(x1, x2, Y, capacity=100, s0=float(np.float32(1e2)), sigmaf_sq=100.0, l_sq=1.0, eps_tol=float(np.float32(1e-4)),

@@ -91,3 +91,45 @@ def test_large_patches_use_the_global_shuffle_path():
     rgb = rng.integers(0, 256, (12000, 3)).astype(np.uint8)
     h, o, _ = run(synth.pack_cloud(xyz, rgb), res=F32(0.1), sz=3, capacity=20)
     assert np.diff(h.patches(frames=False, binning=False)["patch_off"]).max() > 1024
+
+
+@pytest.mark.parametrize("regime", ["reference", "grown"])
+def test_rgb_field_gp_evaluation_matches_oracle(regime):
+    """sparse_gp_field::predict_measurements (sigma / conf), compute_likelihoods, compute_derivatives
+    (sparse_gp_field.hpp:267-393; gp_registration.cpp:177,194) through gpc_evaluate_patches_rgb: bit-equal to the oracle,
+    whose restatement is pinned against the reference's own source in test_oracle_field_evaluate_matches_reference_source."""
+    import gp_compressor_b200 as G
+    from oracle import oracle as O
+    if regime == "reference":
+        cloud = synth.c1_planar_bumps(20000, seed=3)
+        cfg = dict(res=F32(0.15), sz=4, capacity=100)
+    else:
+        cloud = synth.c3_dense_floor(30000, seed=5, side=1.0)
+        hyp = synth.hyper_bind(F32(0.1))
+        cfg = dict(res=F32(0.1), sz=4, capacity=40, rgb_s0=1e-2, sigmaf_sq=hyp["sigmaf_sq"], l_sq=hyp["l_sq"], s0=hyp["s0"])
+    h = G.Handle(rgb=1, keep_state=1, **cfg)
+    h.compress(cloud)
+    o = O.Oracle(rgb=1, **cfg)
+    o.compress(cloud, dump=True)
+    P = int(h.sizes().n_patches)
+    rng = np.random.default_rng(7)
+    cnt = rng.integers(0, 12, P)
+    off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    m = int(off[-1])
+    half = cfg["res"] / 2
+    q1, q2 = rng.uniform(-half, half, m), rng.uniform(-half, half, m)
+    Y = rng.normal(0, 20, (m, 3))
+    for conf in (False, True):
+        g = h.evaluate_rgb(off, q1, q2, Y, conf=conf)
+        w = o.evaluate_rgb(off, q1, q2, Y, conf=conf)
+        for k in ("f", "sigma", "lik", "dX"):
+            assert np.array_equal(g[k], w[k], equal_nan=True), (k, conf)
+    assert np.all(g["dX"][:, 0] == 0)
+    # the height GPs of the same handle still evaluate as before
+    ge = h.evaluate(off, q1, q2, Y[:, 0].copy())
+    we = o.evaluate(off, q1, q2, Y[:, 0].copy())
+    assert np.array_equal(ge["dX"], we["dX"]) and np.array_equal(ge["sigma"], we["sigma"])
+    no_state = G.Handle(rgb=1, **cfg)
+    no_state.compress(cloud)
+    with pytest.raises(RuntimeError):
+        no_state.evaluate_rgb(off, q1, q2, Y)

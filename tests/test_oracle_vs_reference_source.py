@@ -138,3 +138,31 @@ def test_oracle_evaluate_matches_reference_source_vectors(oracle_mod, name):
     assert int(r["nbv"][0]) == N
     q = ([0, g["ex"].shape[0]], g["ex"][:, 0].copy(), g["ex"][:, 1].copy(), g["ey"])
     check_eval(o.evaluate(*q), o.evaluate(*q, conf=True), g, eval_tol(name))
+
+
+def test_oracle_field_evaluate_matches_reference_source(oracle_mod):
+    """The field GP's predict (sigma / conf), likelihood and likelihood_dx (sparse_gp_field.hpp:267-393) of the reference's
+    own source against the oracle's evaluate_field, on a fit both agree on."""
+    from oracle import ref_source as R
+    if not R.available():
+        pytest.skip("oracle/_ref not built (no /root/reference here and no prebuilt library)")
+    rng = np.random.default_rng(9)
+    for cap, s0 in ((8, 1e-2), (100, float(np.float32(1e2)))):
+        n, m = 200, 30
+        x1 = rng.uniform(-0.05, 0.05, n); x2 = rng.uniform(-0.05, 0.05, n)
+        Y = np.stack([50 * np.sin(40 * x1), 30 * np.cos(30 * x2), 20 * np.sin(30 * (x1 + x2))], 1) + rng.normal(0, 1, (n, 3))
+        hy = dict(capacity=cap, sigmaf_sq=1.0, l_sq=(0.1 / 12) ** 2)
+        ex = rng.uniform(-0.05, 0.05, (m, 2))
+        EY = np.stack([50 * np.sin(40 * ex[:, 0]), 30 * np.cos(30 * ex[:, 1]), 20 * np.sin(30 * ex.sum(1))], 1) + rng.normal(0, 3, (m, 3))
+        ref = R.field_evaluate(x1, x2, Y, ex, EY, s0=s0, rand_offset=n - 1, **hy)
+        o = oracle_mod.Oracle(rgb=1, rgb_s0=s0, **hy)
+        o.fit_patches([0, n], x1, x2, np.zeros(n), colours=Y, dump=True)
+        assert int(o.rgb_result()["nbv"][0]) == ref["N"]
+        e = o.evaluate_rgb([0, m], ex[:, 0].copy(), ex[:, 1].copy(), EY)
+        c = o.evaluate_rgb([0, m], ex[:, 0].copy(), ex[:, 1].copy(), EY, conf=True)
+        tol = 1e-8
+        np.testing.assert_allclose(e["f"], ref["f"], rtol=tol, atol=tol * np.abs(ref["f"]).max())
+        np.testing.assert_allclose(e["sigma"], ref["sigma"], rtol=tol)
+        np.testing.assert_allclose(c["sigma"], ref["conf"], rtol=tol, atol=tol * 100)
+        np.testing.assert_allclose(e["lik"], ref["lik"], rtol=100 * tol, atol=1e-300)
+        np.testing.assert_allclose(e["dX"], ref["dX"], rtol=100 * tol, atol=tol * np.abs(ref["dX"]).max() + 1e-300)
