@@ -121,3 +121,22 @@ def test_add_measurements_errors():
     h.fit_patches(off, x1, x2, y)
     with pytest.raises(RuntimeError):                          # different number of patches
         h.add_measurements(off[:2], x1[:50], x2[:50], y[:50])
+
+
+@pytest.mark.gpu
+def test_add_measurements_with_large_patches(oracle_mod):
+    """More than 1024 new points in a patch: the shuffle takes the global-memory path and the BV indices are offset there."""
+    import gp_compressor_b200 as G
+    cfg = dict(capacity=20, **bind())
+    h = G.Handle(keep_state=1, **cfg)
+    o = oracle_mod.Oracle(**cfg)
+    off, x1, x2, y = make(5, [1300, 40])
+    h.fit_patches(off, x1, x2, y)
+    o.fit_patches(off, x1, x2, y, dump=True)
+    off2, a1, a2, ay = make(6, [1500, 0])
+    h.add_measurements(off2, a1, a2, ay)
+    want = o.add_measurements(off2, a1, a2, ay)
+    got = h.params()
+    for k in ("nbv", "bv_idx", "bv1", "bv2", "alpha"):
+        assert np.array_equal(got[k], want[k]), k
+    assert got["bv_idx"].max() >= 1300
