@@ -15,34 +15,44 @@ namespace gpc {
 __device__ __forceinline__ double tiny12() { return (double)1e-12f; }
 __device__ __forceinline__ double geo9() { return (double)1e-9f; }
 
+// Constants of the canonical exp in constant memory: loaded as uniform-register pairs (LDCU.128) instead of two UMOV per
+// 64-bit literal and use.
+static __constant__ double GPC_EXPC[18] = {
+    1.4426950408889634,          // 0  1/ln2
+    6755399441055744.0,          // 1  1.5 * 2^52
+    -0x1.62e42fefa39efp-1,       // 2  -ln2_hi
+    -0x1.abc9e3b39803fp-56,      // 3  -ln2_lo
+    1.0 / 6227020800.0,          // 4  1/13!
+    1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0,
+    1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5,                     // 5..15
+    -6755399441055744.0,         // 16
+    0x1p-1020                    // 17
+};
+
 // Canonical exp: replaces glibc exp at rbf_kernel.cpp:17.  n = rint(x/ln2) by the
 // 1.5*2^52 trick, Cody-Waite reduction with two fma, degree-13 Taylor Horner with fma,
 // exponent insertion.  <= 1 ulp from libm.
 __device__ __forceinline__ double gpc_exp(double x) {
-    const double INV_LN2 = 1.4426950408889634;
-    const double MAGIC = 6755399441055744.0;
-    const double LN2_HI = 0x1.62e42fefa39efp-1;
-    const double LN2_LO = 0x1.abc9e3b39803fp-56;
     // the special cases (NaN, overflow, underflow) are selected at the end: no branches on the hot path
     const double xc = fmin(fmax(x, -746.0), 710.0);  // NaN -> -746 (fmax/fmin return the number)
-    double t = __dmul_rn(xc, INV_LN2);
-    double kd = __dadd_rn(t, MAGIC);
+    double t = __dmul_rn(xc, GPC_EXPC[0]);
+    double kd = __dadd_rn(t, GPC_EXPC[1]);
     int n = (int)(unsigned int)(unsigned long long)__double_as_longlong(kd);
-    kd = __dadd_rn(kd, -MAGIC);
-    double r = fma(kd, -LN2_HI, xc);
-    r = fma(kd, -LN2_LO, r);
-    double p = 1.0 / 6227020800.0;
-    p = fma(p, r, 1.0 / 479001600.0);
-    p = fma(p, r, 1.0 / 39916800.0);
-    p = fma(p, r, 1.0 / 3628800.0);
-    p = fma(p, r, 1.0 / 362880.0);
-    p = fma(p, r, 1.0 / 40320.0);
-    p = fma(p, r, 1.0 / 5040.0);
-    p = fma(p, r, 1.0 / 720.0);
-    p = fma(p, r, 1.0 / 120.0);
-    p = fma(p, r, 1.0 / 24.0);
-    p = fma(p, r, 1.0 / 6.0);
-    p = fma(p, r, 0.5);
+    kd = __dadd_rn(kd, GPC_EXPC[16]);
+    double r = fma(kd, GPC_EXPC[2], xc);
+    r = fma(kd, GPC_EXPC[3], r);
+    double p = GPC_EXPC[4];
+    p = fma(p, r, GPC_EXPC[5]);
+    p = fma(p, r, GPC_EXPC[6]);
+    p = fma(p, r, GPC_EXPC[7]);
+    p = fma(p, r, GPC_EXPC[8]);
+    p = fma(p, r, GPC_EXPC[9]);
+    p = fma(p, r, GPC_EXPC[10]);
+    p = fma(p, r, GPC_EXPC[11]);
+    p = fma(p, r, GPC_EXPC[12]);
+    p = fma(p, r, GPC_EXPC[13]);
+    p = fma(p, r, GPC_EXPC[14]);
+    p = fma(p, r, GPC_EXPC[15]);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
     const bool sub = n < -1020;           // subnormal result: scale in two exact steps
@@ -58,30 +68,26 @@ __device__ __forceinline__ double gpc_exp(double x) {
 
 // gpc_exp for arguments that are <= 0 or NaN (the RBF exponent): same arithmetic, fewer selects
 __device__ __forceinline__ double gpc_exp_nonpos(double x) {
-    const double INV_LN2 = 1.4426950408889634;
-    const double MAGIC = 6755399441055744.0;
-    const double LN2_HI = 0x1.62e42fefa39efp-1;
-    const double LN2_LO = 0x1.abc9e3b39803fp-56;
     const bool special = !(x >= -745.0);          // underflow to 0, or NaN
     const double xc = special ? -745.0 : x;
-    double t = __dmul_rn(xc, INV_LN2);
-    double kd = __dadd_rn(t, MAGIC);
+    double t = __dmul_rn(xc, GPC_EXPC[0]);
+    double kd = __dadd_rn(t, GPC_EXPC[1]);
     int n = (int)(unsigned int)(unsigned long long)__double_as_longlong(kd);
-    kd = __dadd_rn(kd, -MAGIC);
-    double r = fma(kd, -LN2_HI, xc);
-    r = fma(kd, -LN2_LO, r);
-    double p = 1.0 / 6227020800.0;
-    p = fma(p, r, 1.0 / 479001600.0);
-    p = fma(p, r, 1.0 / 39916800.0);
-    p = fma(p, r, 1.0 / 3628800.0);
-    p = fma(p, r, 1.0 / 362880.0);
-    p = fma(p, r, 1.0 / 40320.0);
-    p = fma(p, r, 1.0 / 5040.0);
-    p = fma(p, r, 1.0 / 720.0);
-    p = fma(p, r, 1.0 / 120.0);
-    p = fma(p, r, 1.0 / 24.0);
-    p = fma(p, r, 1.0 / 6.0);
-    p = fma(p, r, 0.5);
+    kd = __dadd_rn(kd, GPC_EXPC[16]);
+    double r = fma(kd, GPC_EXPC[2], xc);
+    r = fma(kd, GPC_EXPC[3], r);
+    double p = GPC_EXPC[4];
+    p = fma(p, r, GPC_EXPC[5]);
+    p = fma(p, r, GPC_EXPC[6]);
+    p = fma(p, r, GPC_EXPC[7]);
+    p = fma(p, r, GPC_EXPC[8]);
+    p = fma(p, r, GPC_EXPC[9]);
+    p = fma(p, r, GPC_EXPC[10]);
+    p = fma(p, r, GPC_EXPC[11]);
+    p = fma(p, r, GPC_EXPC[12]);
+    p = fma(p, r, GPC_EXPC[13]);
+    p = fma(p, r, GPC_EXPC[14]);
+    p = fma(p, r, GPC_EXPC[15]);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
     const bool sub = n < -1020;
