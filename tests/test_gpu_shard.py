@@ -96,3 +96,18 @@ def test_sharded_binning_bins_fewer_points_per_rank(G):
     assert max(claimed) < 0.45 * ref.sizes().n_claimed          # own range + halo, not the whole cloud
     with pytest.raises(RuntimeError):
         hs[0].patches()                                          # patch-level arrays are shard-local in this mode
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_sharded_binning_random_clouds(G, seed):
+    """Random slabs with NaNs, random resolution, shard count and leaf order: the halo / ownership logic at lattice edges."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(2000, 60000))
+    ext = rng.uniform(0.5, 6.0, 3) * [1, 1, 0.2]
+    xyz = (rng.uniform(-1, 1, (n, 3)) * ext + rng.uniform(-50, 50, 3)).astype(np.float32)
+    xyz[:, 2] += (0.05 * np.sin(3 * xyz[:, 0]) * np.cos(2 * xyz[:, 1])).astype(np.float32)
+    xyz[rng.random(n) < 0.01] = np.nan
+    cloud = synth.pack_cloud(xyz, rng.integers(0, 256, (n, 3)).astype(np.uint8))
+    res = F32(rng.choice([0.05, 0.1, 0.2, 0.4]))
+    world = int(rng.integers(2, 7))
+    check(G, cloud, (world,), res=res, sz=3, capacity=int(rng.integers(4, 30)), leaf_order=int(rng.integers(0, 2)))
