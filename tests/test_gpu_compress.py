@@ -237,3 +237,21 @@ def test_extreme_coordinates_and_depth_overflow(G, oracle_mod):
     far = synth.pack_cloud(np.array([[0.0, 0.0, 0.0], [1.0e6, 0.0, 0.0]]))
     with pytest.raises(G.GpcError):
         G.Handle(res=F32(0.01)).compress(far)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_clouds_whole_path(G, oracle_mod, seed):
+    """Random slabs with NaNs, random resolution / grid / capacity / hyper-set / leaf order: every intermediate and the
+    decoded cloud bit-equal to the oracle (compare_all)."""
+    rng = np.random.default_rng(500 + seed)
+    n = int(rng.integers(500, 40000))
+    ext = rng.uniform(0.3, 4.0, 3) * [1, 1, 0.15]
+    xyz = (rng.uniform(-1, 1, (n, 3)) * ext + rng.uniform(-20, 20, 3)).astype(np.float32)
+    xyz[:, 2] += (0.04 * np.sin(4 * xyz[:, 0]) * np.cos(3 * xyz[:, 1])).astype(np.float32)
+    xyz[rng.random(n) < 0.01] = np.nan
+    cloud = synth.pack_cloud(xyz, rng.integers(0, 256, (n, 3)).astype(np.uint8))
+    res = F32(rng.choice([0.05, 0.1, 0.2, 0.4]))
+    cfg = dict(res=res, sz=int(rng.integers(1, 9)), capacity=int(rng.integers(2, 70)), leaf_order=int(rng.integers(0, 2)))
+    if rng.random() < 0.5:
+        cfg.update(synth.hyper_bind(res))
+    compare_all(G, oracle_mod, cloud, **cfg)
