@@ -11,9 +11,13 @@
  * Point clouds are arrays of PCL PointXYZRGB records, 32 bytes each:
  *   float x, y, z, 1.0f | uint8 b, g, r, a | 12 bytes padding.
  *
- * Threading: one handle = one host thread = one CUDA device (gpc_config.device).
+ * Threading: one handle = one host thread = one CUDA device (gpc_config.device); several
+ * handles may work on one device from different threads (two clouds in flight hide the
+ * host-to-device copy of one behind the kernels of the other).
  * Multi-GPU runs use one process (or thread) and one handle per GPU; patches shard with
- * gpc_config.shard_rank / shard_count and no collective.
+ * gpc_config.shard_rank / shard_count and no collective, or -- one cloud, binning sharded as
+ * well -- with gpc_compress_shard_begin / _finish and one all-gather of two integers
+ * (see DESIGN.md section 5).
  */
 #ifndef GPC_H
 #define GPC_H
@@ -50,7 +54,7 @@ typedef struct gpc_config {
     int32_t device;     /* CUDA device ordinal                                                          */
     int32_t shard_rank; /* this handle fits / decodes patches of shard shard_rank ...                   */
     int32_t shard_count;/* ... out of shard_count contiguous ranges of the patch visiting order (1)     */
-    int32_t keep_state; /* 1: keep dense C and Q per patch (gpc_get_state, predictive variance)         */
+    int32_t keep_state; /* 1: keep dense C and Q per patch (gpc_get_state, gpc_evaluate_patches, gpc_add_measurements) */
     int32_t rgb;        /* 1: also fit / decode the RGB field GP, sparse_gp_field (gp_compressor.cpp:163,334)  */
     double rgb_s0;      /* sparse_gp_field(capacity, s0), sparse_gp_field.h:43 (1e2f)                        */
     double rgb_eps_tol; /* sparse_gp_field ctor literal, sparse_gp_field.hpp:16 (1e-4f)                      */
@@ -59,7 +63,8 @@ typedef struct gpc_config {
 typedef struct gpc_sizes {
     int64_t n_in;        /* points given to the last compress                                  */
     int64_t n_patches;   /* octree leaves = patches (gp_compressor.cpp:182), all shards        */
-    int64_t n_claimed;   /* points claimed by some patch (gp_compressor.cpp:88-97)             */
+    int64_t n_claimed;   /* points claimed by some patch (gp_compressor.cpp:88-97); after
+                            gpc_compress_shard_*: by the patches this shard binned (own + halo) */
     int64_t n_bv_total;  /* sum of basis-vector counts over this shard's patches               */
     int64_t patch_lo;    /* first patch (gp_index) of this shard                               */
     int64_t patch_hi;    /* one past the last patch of this shard                              */
@@ -77,6 +82,7 @@ typedef struct gpc_stats {
     uint64_t sum_n, sum_n2_common, sum_n2_sparse, sum_n2_full, sum_n2_del;
     uint64_t escalated[4];      /* patches that left SOGP bucket b for a larger one */
     uint64_t kernel_launches;   /* kernels launched by the last compress / decompress */
+    /* ms_evaluate: the kernel of the last gpc_evaluate_patches(_rgb) */
     uint64_t rgb_n_sparse, rgb_n_full, rgb_n_del_cap, rgb_n_del_geo, rgb_sum_n2_common;  /* RGB field GP events */
     float ms_h2d, ms_lattice, ms_keys, ms_sort, ms_leaves, ms_rotation, ms_claim, ms_group,
           ms_shuffle, ms_fit, ms_d2h, ms_predict, ms_total, ms_fit_rgb, ms_evaluate, pad_;
