@@ -338,6 +338,19 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- reconstruction RMSE: sqrt(mean over the claimed points of (y_local - f*(x_local))^2), metres, in the
+    # patch frames; the means of the fitted GPs at their own training points, outside every timed region, rank 0 only ----
+    rmse = None
+    try:
+        h.set_rand_offset(0)        # the reference's first call: the unseeded rand() stream from its start
+        h.compress_resident()
+        asg = h.assignment(binning=False)
+        poff = h.patches(frames=False, binning=False)["patch_off"]
+        fhat = h.evaluate(poff, asg["st_x1"], asg["st_x2"], want=("f",))["f"]
+        rmse = float(np.sqrt(np.mean((fhat - asg["st_y"]) ** 2))) if fhat.size else 0.0
+    except Exception as e:  # reported, never fatal for the timing line
+        rmse = "unavailable: %s" % e
+
     # ---- roofline of the dominant stage --------------------------------------------------------
     peak, peak_src = measured_peaks()
     stage_ms = {k: v / K for k, v in stage_acc.items() if k not in ("ms_total", "ms_h2d", "ms_d2h", "ms_evaluate", "pad_") and (v > 0 or k != "ms_fit_rgb")}
@@ -400,6 +413,7 @@ def main():
         "config": {"workload": desc, "per_gpu_points": n, "l2": "inputs larger than L2 (%.0f MB cloud + sort buffers per step)" % (n * 32 / 1e6),
                    "parallelism": "one cloud per GPU, patches independent, no collective"},
         "decompress": {"value": dec_value, "unit": "grid pts/s", "points_per_step": ndec_all},
+        "rmse_m": rmse,
         "compress_ms": 1e3 * comp_s / K, "decompress_ms": 1e3 * dec_s / K,
         "stages_ms": {k: round(v, 4) for k, v in sorted(stage_ms.items())},
         "patches": int(sizes.n_patches), "claimed": int(sizes.n_claimed), "mean_bv": sizes.n_bv_total / max(1, sizes.n_patches),

@@ -1087,10 +1087,12 @@ int gpc_predict(gpc_handle* h, int64_t patch, const double* X, int64_t m, double
 static int evaluate_impl(gpc_handle* h, int64_t op0, int64_t P, const int64_t* off, const double* x1, const double* x2, const double* y,
                          int conf, double* f, double* sigma, double* lik, double* dX, int dout) {
     if (!h || P < 0 || (P > 0 && !off)) return GPC_ERR_INVALID;
-    if (!h->have_fit || !h->cfg.keep_state || !h->dumpC.p)
+    const bool need_c = sigma || lik || dX;   // the mean alone needs no state
+    if (!h->have_fit) return fail(h, GPC_ERR_STATE, "evaluation before compress / fit");
+    if (need_c && (!h->cfg.keep_state || !h->dumpC.p))
         return fail(h, GPC_ERR_STATE, "sigma / likelihood evaluation needs a fit made with gpc_config.keep_state");
-    if (dout == 3 && (!h->have_rgb || !h->r_dumpC.p))
-        return fail(h, GPC_ERR_STATE, "gpc_evaluate_patches_rgb needs a compress with gpc_config.rgb = 1 and keep_state = 1");
+    if (dout == 3 && (!h->have_rgb || (need_c && !h->r_dumpC.p)))
+        return fail(h, GPC_ERR_STATE, "gpc_evaluate_patches_rgb needs a compress with gpc_config.rgb = 1 (and keep_state = 1 for sigma / likelihood)");
     if (op0 < 0 || op0 + P > h->patch_hi - h->patch_lo) return fail(h, GPC_ERR_INVALID, "more patches than this shard holds");
     if (P == 0) return GPC_OK;
     const int64_t m = off[P];
@@ -1136,11 +1138,11 @@ static int evaluate_impl(gpc_handle* h, int64_t op0, int64_t P, const int64_t* o
     const int64_t oo = op0 * c.capacity, oc = op0 * (int64_t)c.capacity * c.capacity;
     if (dout == 3) {
         a.alpha[0] = h->r_alpha0.as<double>() + oo; a.alpha[1] = h->r_alpha1.as<double>() + oo; a.alpha[2] = h->r_alpha2.as<double>() + oo;
-        a.b1 = h->r_b1.as<double>() + oo; a.b2 = h->r_b2.as<double>() + oo; a.C = h->r_dumpC.as<double>() + oc;
+        a.b1 = h->r_b1.as<double>() + oo; a.b2 = h->r_b2.as<double>() + oo; a.C = need_c ? h->r_dumpC.as<double>() + oc : nullptr;
         a.s20 = c.rgb_s0;
     } else {
         a.alpha[0] = h->alpha.as<double>() + oo; a.alpha[1] = a.alpha[2] = nullptr;
-        a.b1 = h->b1.as<double>() + oo; a.b2 = h->b2.as<double>() + oo; a.C = h->dumpC.as<double>() + oc;
+        a.b1 = h->b1.as<double>() + oo; a.b2 = h->b2.as<double>() + oo; a.C = need_c ? h->dumpC.as<double>() + oc : nullptr;
         a.s20 = c.s0;
     }
     a.x1 = d_x1; a.x2 = d_x2; a.y = y ? d_y : nullptr;

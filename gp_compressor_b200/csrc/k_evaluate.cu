@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(EV_NT) evaluate_kernel(EvalArgs a) {
         for (int c = 0; c < DOUT; c++) al[c * N + i] = a.alpha[c][pb + i];
         b1[i] = a.b1[pb + i]; b2[i] = a.b2[pb + i];
     }
-    if (CSMEM) {
+    const bool have_c = a.C != nullptr;   // mean only (no sigma / likelihood / gradient): C is neither needed nor read
+    if (CSMEM && have_c) {
         for (int e = t; e < N * LDC; e += EV_NT) {
             const int j = e / LDC, i = e - j * LDC;
             Cs[e] = (i < N) ? Cg[(size_t)j * N + i] : 0.0;
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(EV_NT) evaluate_kernel(EvalArgs a) {
         }
         __syncthreads();
         // (2) CK(i, tt) = sum_j C(j, i) K(j, tt), j ascending, one fma chain per entry
-        {
+        if (have_c) {
             const int pg = t & 7, rg = t >> 3;   // 8 point groups of 4, 16 row groups
             for (int i0 = rg * RPT; i0 < N; i0 += 16 * RPT) {
                 double acc[RPT][4];
