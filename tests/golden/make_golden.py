@@ -63,6 +63,32 @@ def main():
                            meta=np.array([n, cap, 3, r["N"]], dtype=np.int64),
                            hyper=np.array([hyp["sigmaf_sq"], hyp["l_sq"], hyp["s0"]])).items():
             out[f"{name}/{key}"] = v
+    # RGB field GP: the reference's predict_measurements (sigma, conf), compute_likelihoods, compute_derivatives
+    for name, n, cap, s0 in [("feval_cap8", 200, 8, 1e-2), ("feval_nodel", 60, 100, 1e-1)]:   # capacity-bound (the divergent delete_bv) / never deleting
+        rng = np.random.default_rng(len(name) + n)
+        x1 = rng.uniform(-0.05, 0.05, n)
+        x2 = rng.uniform(-0.05, 0.05, n)
+        Y = np.stack([50 * np.sin(40 * x1), 30 * np.cos(30 * x2), 20 * np.sin(30 * (x1 + x2))], axis=1) + rng.normal(0, 1, (n, 3))
+        ex = rng.uniform(-0.05, 0.05, (30, 2))
+        EY = np.stack([50 * np.sin(40 * ex[:, 0]), 30 * np.cos(30 * ex[:, 1]), 20 * np.sin(30 * ex.sum(1))], axis=1) + rng.normal(0, 3, (30, 3))
+        hyp = dict(sigmaf_sq=1.0, l_sq=(0.1 / 12) ** 2)
+        r = R.field_evaluate(x1, x2, Y, ex, EY, capacity=cap, s0=s0, rand_offset=n - 1, **hyp)
+        for key, v in dict(x1=x1, x2=x2, Y=Y, ex=ex, EY=EY, f=r["f"], sigma=r["sigma"], conf=r["conf"], lik=r["lik"], dX=r["dX"],
+                           meta=np.array([n, cap, n - 1, r["N"]], dtype=np.int64),
+                           hyper=np.array([hyp["sigmaf_sq"], hyp["l_sq"], s0])).items():
+            out[f"{name}/{key}"] = v
+    # add_measurements called twice on one process (the reference accumulates)
+    for name, n, n1, cap in [("cont_cap25", 400, 150, 25), ("cont_cap12", 300, 5, 12)]:
+        rng = np.random.default_rng(len(name) + n)
+        x1 = rng.uniform(-0.05, 0.05, n)
+        x2 = rng.uniform(-0.05, 0.05, n)
+        y = 0.02 * np.sin(40 * x1) * np.cos(30 * x2) + rng.normal(0, 0.003, n)
+        hyp = dict(sigmaf_sq=1.0, l_sq=(0.1 / 12) ** 2, s0=1e-4)
+        r = R.fit_twice(x1, x2, y, n1, capacity=cap, rand_offset=3, **hyp)
+        for key, v in dict(x1=x1, x2=x2, y=y, alpha=r["alpha"], bv1=r["bv1"], bv2=r["bv2"],
+                           meta=np.array([n, cap, 3, r["N"], n1], dtype=np.int64),
+                           hyper=np.array([hyp["sigmaf_sq"], hyp["l_sq"], hyp["s0"]])).items():
+            out[f"{name}/{key}"] = v
     out["shuffle_n57_off3"] = R.shuffle(57, 3)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_sogp.npz"), **out)
     print("wrote", len(out), "arrays")

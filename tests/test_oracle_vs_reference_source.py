@@ -14,7 +14,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = np.load(os.path.join(ROOT, "tests", "golden", "ref_sogp.npz"))
-CASES = sorted({k.split("/")[0] for k in GOLD.files if "/" in k and not k.startswith(("field_", "eval_"))})
+CASES = sorted({k.split("/")[0] for k in GOLD.files if "/" in k and not k.startswith(("field_", "eval_", "feval_", "cont_"))})
 EVAL_CASES = sorted({k.split("/")[0] for k in GOLD.files if k.startswith("eval_")})
 FIELD_CASES = sorted({k.split("/")[0] for k in GOLD.files if k.startswith("field_")})
 
@@ -166,3 +166,43 @@ def test_oracle_field_evaluate_matches_reference_source(oracle_mod):
         np.testing.assert_allclose(c["sigma"], ref["conf"], rtol=tol, atol=tol * 100)
         np.testing.assert_allclose(e["lik"], ref["lik"], rtol=100 * tol, atol=1e-300)
         np.testing.assert_allclose(e["dX"], ref["dX"], rtol=100 * tol, atol=tol * np.abs(ref["dX"]).max() + 1e-300)
+
+
+FEVAL_CASES = sorted({k.split("/")[0] for k in GOLD.files if k.startswith("feval_")})
+CONT_CASES = sorted({k.split("/")[0] for k in GOLD.files if k.startswith("cont_")})
+
+
+def check_feval(e, c, g, tol=1e-8):
+    np.testing.assert_allclose(e["f"], g["f"], rtol=tol, atol=tol * np.abs(g["f"]).max())
+    np.testing.assert_allclose(e["sigma"], g["sigma"], rtol=tol)
+    np.testing.assert_allclose(c["sigma"], g["conf"], rtol=tol, atol=tol * 100)
+    np.testing.assert_allclose(e["lik"], g["lik"], rtol=100 * tol, atol=1e-300)
+    np.testing.assert_allclose(e["dX"], g["dX"], rtol=100 * tol, atol=tol * np.abs(g["dX"]).max() + 1e-300)
+
+
+@pytest.mark.parametrize("name", FEVAL_CASES)
+def test_oracle_field_evaluate_matches_golden(oracle_mod, name):
+    g = {k.split("/")[1]: GOLD[k] for k in GOLD.files if k.startswith(name + "/")}
+    n, cap, roff, N = (int(v) for v in g["meta"])
+    p0, l_sq, s0 = (float(v) for v in g["hyper"])
+    o = oracle_mod.Oracle(capacity=cap, sigmaf_sq=p0, l_sq=l_sq, rgb=1, rgb_s0=s0)
+    o.set_rand_offset(roff - (n - 1))
+    o.fit_patches([0, n], g["x1"], g["x2"], np.zeros(n), colours=g["Y"], dump=True)
+    assert int(o.rgb_result()["nbv"][0]) == N
+    m = g["ex"].shape[0]
+    q = ([0, m], g["ex"][:, 0].copy(), g["ex"][:, 1].copy(), g["EY"])
+    check_feval(o.evaluate_rgb(*q), o.evaluate_rgb(*q, conf=True), g)
+
+
+@pytest.mark.parametrize("name", CONT_CASES)
+def test_oracle_continued_fit_matches_golden(oracle_mod, name):
+    g = {k.split("/")[1]: GOLD[k] for k in GOLD.files if k.startswith(name + "/")}
+    n, cap, roff, N, n1 = (int(v) for v in g["meta"])
+    p0, l_sq, s0 = (float(v) for v in g["hyper"])
+    o = oracle_mod.Oracle(capacity=cap, sigmaf_sq=p0, l_sq=l_sq, s0=s0, rgb_rand=0)
+    o.set_rand_offset(roff)
+    o.fit_patches([0, n1], g["x1"][:n1], g["x2"][:n1], g["y"][:n1], dump=True)
+    r = o.add_measurements([0, n - n1], g["x1"][n1:], g["x2"][n1:], g["y"][n1:])
+    assert int(r["nbv"][0]) == N
+    assert np.array_equal(r["bv1"], g["bv1"]) and np.array_equal(r["bv2"], g["bv2"])
+    assert np.abs(r["alpha"] - g["alpha"]).max() <= 5e-6 * np.abs(g["alpha"]).max()
