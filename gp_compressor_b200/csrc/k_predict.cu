@@ -46,8 +46,9 @@ __device__ __forceinline__ void quat_to_rot(const double* q, double* R) {
 
 // One (patch, block of grid rows) per group of G threads: G = 32 (four independent warps per CTA, for small grids)
 // or G = PRED_T.  Each thread owns R consecutive rows of one grid column.
-template <int R, int G>
-__global__ void __launch_bounds__(PRED_T, R == 1 ? 8 : 3) predict_grid_kernel(PredictArgs a) {
+// MINB: resident CTAs per SM the register budget is cut for (large-grid shape: 4 when the tables leave room for 4 CTAs, else 3)
+template <int R, int G, int MINB>
+__global__ void __launch_bounds__(PRED_T, MINB) predict_grid_kernel(PredictArgs a) {
     extern __shared__ double sm_all[];
     const int64_t gi = (int64_t)blockIdx.x * (PRED_T / G) + threadIdx.x / G;
     if (gi >= a.n_groups) return;
@@ -234,14 +235,14 @@ __global__ void __launch_bounds__(128) predict_points_kernel(const double* __res
 
 }  // namespace
 
-template <int R, int G>
+template <int R, int G, int MINB>
 static cudaError_t launch_grid_variant(const PredictArgs& a, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(predict_grid_kernel<R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(predict_grid_kernel<R, G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int per_cta = PRED_T / G;
     const int64_t grid = (a.n_groups + per_cta - 1) / per_cta;
     if (grid > 0x7fffffff) return cudaErrorInvalidConfiguration;
-    predict_grid_kernel<R, G><<<(unsigned)grid, PRED_T, smem, s>>>(a);
+    predict_grid_kernel<R, G, MINB><<<(unsigned)grid, PRED_T, smem, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -270,7 +271,7 @@ cudaError_t launch_predict_grid(const PredictArgs& a0, cudaStream_t s) {
         a.group_doubles = (int)(fixed + (int64_t)(nb + 1) * a.rowsP);
         a.n_groups = a.n_patches * a.nblk;
         g_launches++;
-        return launch_grid_variant<1, PRED_T>(a, (size_t)a.group_doubles * sizeof(double), s);
+        return launch_grid_variant<1, PRED_T, 8>(a, (size_t)a.group_doubles * sizeof(double), s);
     }
     if (rmax < 1) return cudaErrorInvalidConfiguration;
     int rows = (int)std::min<int64_t>(rmax, a.sz);
@@ -283,9 +284,9 @@ cudaError_t launch_predict_grid(const PredictArgs& a0, cudaStream_t s) {
     a.n_groups = a.n_patches * a.nblk;
     const size_t smem = (size_t)a.group_doubles * per_cta * sizeof(double);
     g_launches++;
-    if (small) return launch_grid_variant<1, 32>(a, smem, s);
-    if (R == 8) return launch_grid_variant<8, PRED_T>(a, smem, s);
-    return launch_grid_variant<1, PRED_T>(a, smem, s);
+    if (small) return launch_grid_variant<1, 32, 8>(a, smem, s);
+    if (R == 8) return smem <= 56 * 1024 ? launch_grid_variant<8, PRED_T, 4>(a, smem, s) : launch_grid_variant<8, PRED_T, 3>(a, smem, s);
+    return launch_grid_variant<1, PRED_T, 8>(a, smem, s);
 }
 
 void launch_predict_points(const double* alpha, const double* b1, const double* b2, int N, double p0, double cl, const double* X,
