@@ -68,6 +68,20 @@ int fail(gpc_handle* h, int code, const std::string& msg) {
             return fail(h, GPC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));           \
     } while (0)
 
+// Layout of gpc_handle::small, the 256-byte device block for the few scalars that travel between kernels and the host.
+struct SmallScratch {
+    unsigned long long pad0[4];
+    unsigned long long n_valid;      // count_valid_kernel
+    unsigned long long pad1[3];
+    int64_t plan[9];                 // fit_plan_kernel: n_claimed, lo, hi, off[lo], off[hi], roff[lo], roff[hi], roff[P], max patch
+    int64_t pad2[3];
+    int64_t owned_range[2];          // owned_range_kernel (sharded binning): first / one-past-last owned patch
+    uint64_t key_range[2];           // shard_splitters_kernel: [klo, khi) of this rank
+    int32_t maxes[2];                // flag_nonempty_kernel: largest BV count of the height / RGB GPs
+    int32_t pad3[14];
+};
+static_assert(sizeof(SmallScratch) == 256, "scratch layout");
+
 struct StageTimer {
     gpc_handle* h;
     size_t used = 0;
@@ -171,8 +185,8 @@ int run_fit(gpc_handle* h, StageTimer& tm, bool cont = false) {
     CK(h->draws.reserve((P + 1) * sizeof(int64_t)));
     CK(h->roff.reserve((P + 2) * sizeof(int64_t)));
     CK(h->scan_tmp.reserve(scan_tmp_bytes(P + 1)));
-    CK(h->small.reserve(256));
-    int64_t* d_plan = h->small.as<int64_t>() + 8;
+    CK(h->small.reserve(sizeof(SmallScratch)));
+    int64_t* d_plan = h->small.as<SmallScratch>()->plan;
     launch_fit_plan(h->off.as<int64_t>(), P, mult, c.shard_rank, c.shard_count, h->shard_mode ? h->own_lo : -1, h->own_hi,
                     h->draws.as<int64_t>(), h->roff.as<int64_t>(), h->scan_tmp.p, d_plan, st);
     int64_t plan[9];
@@ -432,8 +446,8 @@ int run_decode(gpc_handle* h, bool want_cloud, bool want_heights, StageTimer& tm
     CK(h->slot.reserve((PL + 2) * sizeof(int64_t)));
     CK(h->scan_tmp.reserve(scan_tmp_bytes(PL + 1)));
     const bool with_rgb = h->have_rgb && h->have_frames;
-    CK(h->small.reserve(256));
-    int32_t* d_maxes = h->small.as<int32_t>() + 48;
+    CK(h->small.reserve(sizeof(SmallScratch)));
+    int32_t* d_maxes = h->small.as<SmallScratch>()->maxes;
     launch_flag_nonempty(h->nbv.as<int32_t>(), with_rgb ? h->r_nbv.as<int32_t>() : nullptr, PL, h->nonempty.as<int64_t>(), d_maxes, st);
     launch_exclusive_scan_i64(h->nonempty.as<int64_t>(), h->slot.as<int64_t>(), PL, h->scan_tmp.p, st);
     int64_t n_nonempty = 0;
@@ -492,8 +506,8 @@ int run_binning(gpc_handle* h, StageTimer& tm, bool sharded = false) {
     h->shard_mode = false;
     if (n > 0x7fffffff) return fail(h, GPC_ERR_INVALID, "more than 2^31-1 points");
     h->have_binning = h->have_frames = h->have_fit = false;
-    CK(h->small.reserve(256));
-    unsigned long long* d_nvalid = h->small.as<unsigned long long>() + 4;
+    CK(h->small.reserve(sizeof(SmallScratch)));
+    unsigned long long* d_nvalid = &h->small.as<SmallScratch>()->n_valid;
     // ---- lattice replay: search + adopt on the device, the host only polls "found" ----
     size_t t0 = tm.mark();
     CK(h->lat_state.reserve(sizeof(LatticeState)));
@@ -549,8 +563,8 @@ int run_binning(gpc_handle* h, StageTimer& tm, bool sharded = false) {
         CK(h->sort_tmp.reserve(radix_sort_tmp_bytes(std::max(n, m))));
         launch_shard_sample(h->keys.as<uint64_t>(), n, stride, m, smp, dv, st);
         const int which_s = launch_radix_sort(smp, dv, smp2, dv2, m, 3 * depth + 1, h->sort_tmp.p, st);
-        CK(h->small.reserve(256));
-        uint64_t* d_range = h->small.as<uint64_t>() + 22;
+        CK(h->small.reserve(sizeof(SmallScratch)));
+        uint64_t* d_range = h->small.as<SmallScratch>()->key_range;
         launch_shard_splitters(which_s ? smp2 : smp, m, depth, c.shard_rank, c.shard_count, c.leaf_order, d_range, st);
         CK(h->flags64.reserve((n + 1) * sizeof(int64_t)));
         CK(h->ex.reserve((n + 1) * sizeof(int64_t)));
@@ -931,9 +945,9 @@ int gpc_compress_shard_begin(gpc_handle* h, const void* cloud, int64_t n, int64_
     cudaStream_t st = h->stream;
     const int64_t P = h->n_patches;
     if (P > 0) {
-        CK(h->small.reserve(256));
-        int64_t* d_rng = h->small.as<int64_t>() + 20;
-        launch_owned_range(h->code.as<uint64_t>(), P, c.leaf_order, h->small.as<uint64_t>() + 22, d_rng, st);
+        CK(h->small.reserve(sizeof(SmallScratch)));
+        int64_t* d_rng = h->small.as<SmallScratch>()->owned_range;
+        launch_owned_range(h->code.as<uint64_t>(), P, c.leaf_order, h->small.as<SmallScratch>()->key_range, d_rng, st);
         int64_t rng[2] = {0, 0};
         CK(cudaMemcpyAsync(rng, d_rng, sizeof(rng), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -942,7 +956,7 @@ int gpc_compress_shard_begin(gpc_handle* h, const void* cloud, int64_t n, int64_
         CK(h->draws.reserve((P + 1) * sizeof(int64_t)));
         CK(h->roff.reserve((P + 2) * sizeof(int64_t)));
         CK(h->scan_tmp.reserve(scan_tmp_bytes(P + 1)));
-        int64_t* d_plan = h->small.as<int64_t>() + 8;
+        int64_t* d_plan = h->small.as<SmallScratch>()->plan;
         launch_fit_plan(h->off.as<int64_t>(), P, mult, c.shard_rank, c.shard_count, h->own_lo, h->own_hi, h->draws.as<int64_t>(),
                         h->roff.as<int64_t>(), h->scan_tmp.p, d_plan, st);
         int64_t plan[9];
@@ -1120,9 +1134,9 @@ static int evaluate_impl(gpc_handle* h, int64_t op0, int64_t P, const int64_t* o
     CK(cudaMemcpyAsync(d_x2, x2, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, st));
     if (y) CK(cudaMemcpyAsync(d_y, y, (size_t)dout * m * sizeof(double), cudaMemcpyHostToDevice, st));
     // largest BV count (sizes the shared-memory tiles)
-    CK(h->small.reserve(256));
+    CK(h->small.reserve(sizeof(SmallScratch)));
     CK(h->nonempty.reserve((P + 1) * sizeof(int64_t)));
-    int32_t* d_maxes = h->small.as<int32_t>() + 48;
+    int32_t* d_maxes = h->small.as<SmallScratch>()->maxes;
     const int32_t* nbv_d = (dout == 3 ? h->r_nbv.as<int32_t>() : h->nbv.as<int32_t>()) + op0;
     launch_flag_nonempty(nbv_d, nullptr, P, h->nonempty.as<int64_t>(), d_maxes, st);
     int32_t maxes[2] = {0, 0};
