@@ -196,3 +196,38 @@ def test_separable_grid_decode_matches_direct_kernel(oracle_mod):
     # and the point-wise predict (direct form) agrees with the grid decode to the same level
     f = o.predict(0, np.stack(np.meshgrid(grid, grid), -1).reshape(-1, 2))
     assert np.abs(f - heights[0].ravel()).max() <= 1e-12 * np.abs(r["alpha"][:r["nbv"][0]]).sum() * p0
+
+
+@pytest.mark.parametrize("seed,res,order", [(1, 0.15, 0), (2, 0.1, 1), (3, 0.3, 0), (4, 0.07, 0)])
+def test_binning_matches_sequential_numpy_witness(oracle_mod, seed, res, order):
+    """Rows a-1 .. a-5: the oracle's order-free restatement of project_cloud against an independent, sequential numpy
+    restatement (tests/binning_numpy.py: point-by-point bounding-box growth, brute-force float32 radius search, numpy SVD
+    for the plane normal, greedy claim with an occupied array).  Lattice, leaves, visiting order, candidate counts, owners
+    and per-patch point order must be identical; local coordinates agree to the rounding of the two SVDs."""
+    from binning_numpy import project_cloud
+    from gp_compressor_b200 import synth
+    rng = np.random.default_rng(seed)
+    n = 1500
+    ext = np.array([1.2, 0.9, 0.12])
+    xyz = (rng.uniform(-1, 1, (n, 3)) * ext + rng.uniform(-5, 5, 3)).astype(np.float32)
+    xyz[:, 2] += (0.05 * np.sin(3 * xyz[:, 0]) * np.cos(2 * xyz[:, 1])).astype(np.float32)
+    xyz[rng.random(n) < 0.01] = np.nan
+    cloud = synth.pack_cloud(xyz, rng.integers(0, 256, (n, 3)).astype(np.uint8))
+    resf = float(np.float32(res))
+    o = oracle_mod.Oracle(res=resf, leaf_order=order, capacity=5)
+    b = o.project(cloud)
+    w = project_cloud(xyz, resf, leaf_order=order)
+    assert int(b["depth"]) == w["depth"]
+    assert np.array_equal(b["lattice_min"], w["lattice_min"])
+    assert np.array_equal(b["leaf_code"].astype(np.uint64), w["leaf_code"])
+    assert np.array_equal(b["leaf_ncand"], np.array(w["ncand"]))
+    assert np.array_equal(b["owner"], w["owner"])
+    off = b["patch_off"]
+    for p in range(len(w["stream"])):
+        sl = slice(off[p], off[p + 1])
+        assert np.array_equal(b["st_idx"][sl], w["stream"][p]), p
+        if w["stream"][p].size:
+            assert np.abs(b["st_x1"][sl] - w["x1"][p]).max() < 1e-9 and np.abs(b["st_x2"][sl] - w["x2"][p]).max() < 1e-9
+            assert np.abs(b["st_y"][sl] - w["y"][p]).max() < 1e-9
+            Rw = w["R"][p]
+            assert np.abs(b["leaf_R"].reshape(-1, 3, 3)[p] - Rw).max() < 1e-7
