@@ -231,3 +231,32 @@ def test_binning_matches_sequential_numpy_witness(oracle_mod, seed, res, order):
             assert np.abs(b["st_y"][sl] - w["y"][p]).max() < 1e-9
             Rw = w["R"][p]
             assert np.abs(b["leaf_R"].reshape(-1, 3, 3)[p] - Rw).max() < 1e-7
+
+
+def test_decode_frames_match_numpy(oracle_mod):
+    """load_compressed (gp_compressor.cpp:320-371): every decoded point is R [f, X0, X1]' + mean on the sz x sz lattice,
+    with R the patch rotation (through its stored quaternion) and the patch's mean colour; recomputed here in numpy from
+    the oracle's own frames and heights, independent of its quaternion code."""
+    from gp_compressor_b200 import synth
+    cloud = synth.c1_planar_bumps(6000, seed=5)
+    res, sz = float(np.float32(0.15)), 6
+    o = oracle_mod.Oracle(res=res, sz=sz, capacity=20)
+    o.compress(cloud)
+    b = o.binning()
+    dec, heights = o.decode()
+    nbv = o.fit_result()["nbv"]
+    keep = np.nonzero(nbv > 0)[0]
+    assert dec.shape[0] == keep.size * sz * sz
+    grid = res * ((np.arange(sz, dtype=np.float64) + np.float32(0.5)) / sz - np.float32(0.5))
+    X0, X1 = np.meshgrid(grid, grid)                       # y outer, x inner (:320-328)
+    R = b["leaf_R"].reshape(-1, 3, 3)[keep]
+    mean = b["leaf_mean"].reshape(-1, 3)[keep]
+    f = heights.reshape(keep.size, sz * sz)
+    local = np.stack([f, np.broadcast_to(X0.ravel(), f.shape), np.broadcast_to(X1.ravel(), f.shape)], axis=2)
+    want = np.einsum("pij,pmj->pmi", R, local) + mean[:, None, :]
+    got = dec[:, :12].copy().view(np.float32).reshape(keep.size, sz * sz, 3)
+    assert np.abs(got - want).max() < 2e-6 * max(1.0, np.abs(want).max())
+    rgb = dec[:, 16:19].reshape(keep.size, sz * sz, 3)
+    cm = np.clip(b["leaf_rgbmean"].reshape(-1, 3)[keep].astype(np.int64), 0, 255)     # flatten_colors on the mean colour
+    assert np.array_equal(rgb[:, 0, ::-1], cm)                                          # stored b, g, r
+    assert (rgb == rgb[:, :1, :]).all()
