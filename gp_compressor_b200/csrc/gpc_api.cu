@@ -106,6 +106,10 @@ struct StageTimer {
     }
 };
 
+// the bucket-0 SOGP kernel stages 16-point tiles with bulk copies from 16-byte aligned addresses and may read up to
+// 136 bytes past the last stream element (k_sogp.cu, HalfTile): every stream buffer ends with this much slack
+constexpr size_t STREAM_PAD = 256;
+
 double kernel_cl(const gpc_config& c) { return (double)(-0.5f) / c.l_sq; }  // -0.5f / p(1), rbf_kernel.cpp:17
 
 // Patches [lo, hi) of shard r out of c: contiguous ranges of the visiting order with about
@@ -205,11 +209,11 @@ int run_fit(gpc_handle* h, StageTimer& tm, bool cont = false) {
     const uint64_t draws_hi = draws_lo + (uint64_t)(plan[6] - plan[5]);
     const uint64_t draws_all = h->shard_mode ? h->draws_total : (uint64_t)plan[7];
     const int64_t max_np = plan[8];
-    CK(h->perm.reserve(std::max<int64_t>(S, 1) * sizeof(int32_t)));
+    CK(h->perm.reserve(std::max<int64_t>(S, 1) * sizeof(int32_t) + STREAM_PAD));
     CK(h->patch_of.reserve(std::max<int64_t>(S, 1) * sizeof(int32_t)));
-    CK(h->fx1.reserve(std::max<int64_t>(S, 1) * sizeof(double)));
-    CK(h->fx2.reserve(std::max<int64_t>(S, 1) * sizeof(double)));
-    CK(h->fy.reserve(std::max<int64_t>(S, 1) * sizeof(double)));
+    CK(h->fx1.reserve(std::max<int64_t>(S, 1) * sizeof(double) + STREAM_PAD));
+    CK(h->fx2.reserve(std::max<int64_t>(S, 1) * sizeof(double) + STREAM_PAD));
+    CK(h->fy.reserve(std::max<int64_t>(S, 1) * sizeof(double) + STREAM_PAD));
     if (PL > 0 && h->s_count > 0) {
         const int64_t nd = (int64_t)(draws_hi - draws_lo);
         if (c.shuffle && nd > 0) {
@@ -223,7 +227,7 @@ int run_fit(gpc_handle* h, StageTimer& tm, bool cont = false) {
         sg.perm = h->perm.as<int32_t>();
         sg.forig = nullptr; sg.orig_base = nullptr;
         if (cont) {  // BV indices of a continued fit count from the points fed before
-            CK(h->forig.reserve(std::max<int64_t>(S, 1) * sizeof(int32_t)));
+            CK(h->forig.reserve(std::max<int64_t>(S, 1) * sizeof(int32_t) + STREAM_PAD));
             sg.forig = h->forig.as<int32_t>();
             sg.orig_base = h->fed.as<int64_t>() + lo;
         }
@@ -340,10 +344,10 @@ int run_fit(gpc_handle* h, StageTimer& tm, bool cont = false) {
     if (c.rgb && h->have_binning) {
         if (!(c.shuffle && c.rgb_rand)) return fail(h, GPC_ERR_INVALID, "rgb = 1 needs shuffle = 1 and rgb_rand = 1");
         const int64_t Sa = std::max<int64_t>(S, 1);
-        CK(h->perm_rgb.reserve(Sa * sizeof(int32_t)));
-        CK(h->fcr.reserve(Sa * sizeof(double)));
-        CK(h->fcg.reserve(Sa * sizeof(double)));
-        CK(h->fcb.reserve(Sa * sizeof(double)));
+        CK(h->perm_rgb.reserve(Sa * sizeof(int32_t) + STREAM_PAD));
+        CK(h->fcr.reserve(Sa * sizeof(double) + STREAM_PAD));
+        CK(h->fcg.reserve(Sa * sizeof(double) + STREAM_PAD));
+        CK(h->fcb.reserve(Sa * sizeof(double) + STREAM_PAD));
         CK(h->r_nbv.reserve(PLa * sizeof(int32_t)));
         CK(h->r_flags.reserve(PLa * sizeof(int32_t)));
         CK(h->r_alpha0.reserve(PLa * cap * sizeof(double)));

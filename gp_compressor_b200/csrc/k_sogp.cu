@@ -153,57 +153,111 @@ __device__ __forceinline__ int half_first_min(unsigned gm, double sc, int idx, d
     return cand;
 }
 
+// ---- 1-D bulk-async copies (the TMA unit without a tensor map: UBLKCP in SASS) completing on an mbarrier --------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// One staged tile of the fit stream: 16 consecutive points of a patch.  Every array is filled by ONE bulk copy from the
+// 16-byte aligned address at or below the tile's first element (the copy engine needs 16-byte alignment and sizes), so
+// element j of the tile sits at index j + shift, shift = (o & 1) for the doubles and (o & 3) for the indices.
 template <int DOUT>
-struct HalfSmem {
-    double C[W_N * W_LD], Q[W_N * W_LD];
+struct __align__(16) HalfTile {
+    double x1[18], x2[18], y[DOUT][18];
+    int orig[20];
+};
+constexpr int TILE_PAD_BYTES = 256;  // the stream buffers end with at least this much slack (gpc_api.cu): tiles read past the end
+
+template <int DOUT>
+struct __align__(16) HalfSmem {
+    double Q[W_N * W_LD];  // homes of Q and C: authoritative while the rows are NOT in registers (full updates, deletions,
+    double C[W_N * W_LD];  // hand-off, final dump); during runs of sparse points lane r keeps row r of both in registers
     double kv[W_N], sv[W_N], ev[W_N];
-    StagedPointT<DOUT> pts[16];
-    unsigned long long cnt[NCNT];
+    HalfTile<DOUT> tile[2];
+    unsigned long long mbar[2];
 };
 
-// (C k)_r and (Q k)_r for contiguous zero-padded rows, k loaded once (see row4_padded16)
-__device__ __forceinline__ void row4x2_padded16(const double* crow, const double* qrow, const double* k, int n, double* rc, double* rq) {
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+template <int DOUT>
+__device__ __forceinline__ void issue_tile(HalfTile<DOUT>& t, unsigned long long* bar, const SogpArgs& a, int64_t pos) {
+    mbar_expect_tx(bar, (uint32_t)((2 + DOUT) * 144 + 80));
+    const int64_t pd = pos & ~(int64_t)1, pi = pos & ~(int64_t)3;
+    bulk_g2s(t.x1, a.fx1 + pd, 144, bar);
+    bulk_g2s(t.x2, a.fx2 + pd, 144, bar);
 #pragma unroll
-    for (int g = 0; g < 4; g++) {
-        if (4 * g < n) {
-            const double2 k01 = *reinterpret_cast<const double2*>(k + 4 * g), k23 = *reinterpret_cast<const double2*>(k + 4 * g + 2);
-            const double2 c01 = *reinterpret_cast<const double2*>(crow + 4 * g), c23 = *reinterpret_cast<const double2*>(crow + 4 * g + 2);
-            const double2 q01 = *reinterpret_cast<const double2*>(qrow + 4 * g), q23 = *reinterpret_cast<const double2*>(qrow + 4 * g + 2);
-            a0 = fma(c01.x, k01.x, a0); a1 = fma(c01.y, k01.y, a1); a2 = fma(c23.x, k23.x, a2); a3 = fma(c23.y, k23.y, a3);
-            b0 = fma(q01.x, k01.x, b0); b1 = fma(q01.y, k01.y, b1); b2 = fma(q23.x, k23.x, b2); b3 = fma(q23.y, k23.y, b3);
-        }
-    }
-    *rc = __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
-    *rq = __dadd_rn(__dadd_rn(b0, b1), __dadd_rn(b2, b3));
+    for (int c = 0; c < DOUT; c++) bulk_g2s(t.y[c], a.fy[c] + pd, 144, bar);
+    bulk_g2s(t.orig, a.forig + pi, 80, bar);
 }
+
+template <int V>
+struct IntC { static constexpr int value = V; };
 
 // DOUT = 1: sparse_gp (heights).  DOUT = 3: sparse_gp_field (RGB): alpha has three columns, the capacity score is
 // |alpha_i|^2 / (Q_ii + C_ii) (sparse_gp_field.hpp:187) and delete_bv updates alpha with alphastar * ((q*+c*)(Qs+Cs)) (:250-253).
+//
+// Structure (sparse_gp.hpp:119-162 is the loop; the arithmetic and its order are those of every other bucket):
+//  * A sparse update (:155-163), 93 % of the points under the reference hyper-parameters, changes only alpha and C and reads
+//    Q.  During runs of sparse points lane r keeps row r of C AND of Q in registers: the two matvecs C k, Q k and the rank-1
+//    update of C touch no shared memory beyond the broadcast of k and s_hat (16 doubles each).  The step is compiled once per
+//    number of occupied 4-column groups (N <= 8, 12, 16) so that it has no per-group predicates, and runs converged for
+//    both halves of the warp (full-mask shuffles).
+//  * The rare paths (full update, deletions, hand-off) spill the rows to their homes in shared memory and work there.
+//  * k of the next point is computed while this point's chain runs (it depends only on the BV set).
+//  * The point stream is staged 16 points at a time by bulk-async copies (TMA unit) into a double buffer, one tile ahead.
 template <int DOUT>
-__global__ void __launch_bounds__(32, DOUT == 1 ? 20 : 16) sogp_fit_half_kernel(SogpArgs a) {
+__global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
     __shared__ __align__(16) HalfSmem<DOUT> sm2[2];
     const int lane = threadIdx.x;
     const int half = lane >> 4, r = lane & 15;
     const unsigned gm = 0xffffu << (16 * half);
+    const unsigned FULL = 0xffffffffu;
     const int64_t w = 2 * (int64_t)blockIdx.x + half;
-    if (w >= a.n_work) return;
     HalfSmem<DOUT>& sm = sm2[half];
     double* const C = sm.C;
     double* const Q = sm.Q;
-    const int64_t patch = a.patch_ids ? (int64_t)a.patch_ids[w] : a.first_patch + w;
-    const int64_t o = a.off[patch];
-    const int n = (int)(a.off[patch + 1] - o);
-    const int64_t op = patch - a.out_first;
-    if (n == 0) {
-        if (r == 0) { a.nbv[op] = 0; a.flags[op] = 0; }
-        return;
+    int64_t patch = 0, o = 0, op = 0;
+    int n = 0;
+    if (w < a.n_work) {
+        patch = a.patch_ids ? (int64_t)a.patch_ids[w] : a.first_patch + w;
+        o = a.off[patch];
+        n = (int)(a.off[patch + 1] - o);
+        op = patch - a.out_first;
+        if (n == 0 && r == 0) { a.nbv[op] = 0; a.flags[op] = 0; }
     }
+    // a half without work stays in the loop with n = 0: every warp-level operation of the step names all 32 lanes
 #pragma unroll
     for (int i = 0; i < W_N * W_LD / 16; i++) { C[r + 16 * i] = 0.0; Q[r + 16 * i] = 0.0; }
-    if (r < NCNT) sm.cnt[r] = 0;
-    sm.kv[r] = 0.0; sm.sv[r] = 0.0; sm.ev[r] = 0.0;  // pad terms must be finite
-    __syncwarp(gm);
+    sm.kv[r] = 0.0; sm.sv[r] = 0.0; sm.ev[r] = 0.0;
+    if (r == 0) { mbar_init(&sm.mbar[0], 1); mbar_init(&sm.mbar[1], 1); }
+    __syncwarp();
+    int issued = 0, waited = 0;  // tiles issued / consumed (half-uniform)
+    if (n > 0) {
+        if (r == 0) issue_tile<DOUT>(sm.tile[0], &sm.mbar[0], a, o);
+        issued = 1;
+    }
+    const int sh1 = (int)(o & 1), sh3 = (int)(o & 3);
+    const int nmax = max(n, __shfl_xor_sync(FULL, n, 16));
     const double kstar = a.p0, s20 = a.s20, p0 = a.p0, cl = a.cl, eps_tol = a.eps_tol;
     const int cap = a.capacity, ldmax = a.ld;
     double alpha[DOUT], b1 = 0.0, b2 = 0.0;  // lane r owns entry r
@@ -211,140 +265,179 @@ __global__ void __launch_bounds__(32, DOUT == 1 ? 20 : 16) sogp_fit_half_kernel(
     for (int c = 0; c < DOUT; c++) alpha[c] = 0.0;
     int bidx = -1;
     int N = 0;
-    unsigned int run = 0;  // sparse points at the current N, folded into sm.cnt when N changes
-    // k of the NEXT point is computed ahead, while this point's dependent chain (matvec, butterflies, divisions) runs:
-    // it only depends on the BV set, which a sparse update leaves alone.  After a full update it is recomputed.
+    unsigned int run = 0;          // sparse points at the current N, folded into the counters when N changes
+    unsigned long long cnt = 0;    // lane r < NCNT owns event counter r
+    double creg[16], qreg[16];     // rows r of C and Q while inreg
+#pragma unroll
+    for (int j = 0; j < 16; j++) { creg[j] = 0.0; qreg[j] = 0.0; }
+    bool inreg = true, done = (n == 0), have_next = false;
     double kl_next = 0.0;
-    bool have_next = false;
     double* const Crow = C + r * W_LD;
     double* const Qrow = Q + r * W_LD;
 
-    const double* const gx1 = a.fx1 + o;
-    const double* const gx2 = a.fx2 + o;
-    const double* gy[DOUT];
-#pragma unroll
-    for (int c = 0; c < DOUT; c++) gy[c] = a.fy[c] + o;
-    const int32_t* const go = a.forig + o;
-    for (int tt = 0; tt < n; ++tt) {
-        if ((tt & 15) == 0) {  // stage the next 16 points: one coalesced load per lane
-            __syncwarp(gm);
-            const int i = tt + r;
-            if (i < n) {
-                StagedPointT<DOUT> sp;
-                sp.x1 = gx1[i]; sp.x2 = gx2[i]; sp.orig = go[i]; sp.pad = 0;
-#pragma unroll
-                for (int c = 0; c < DOUT; c++) sp.y[c] = gy[c][i];
-                sm.pts[r] = sp;
+    for (int tt = 0; tt < nmax; ++tt) {
+        const int s = tt & 15;
+        const bool live = !done && tt < n;
+        if (s == 0) {
+            __syncwarp();  // every lane is done with the buffer the next tile will land in
+            if (__all_sync(FULL, !live)) break;
+            if (live) {
+                const int kt = tt >> 4;
+                if (tt + 16 < n) {
+                    if (r == 0) issue_tile<DOUT>(sm.tile[(kt + 1) & 1], &sm.mbar[(kt + 1) & 1], a, o + tt + 16);
+                    issued++;
+                }
+                mbar_wait(&sm.mbar[kt & 1], (uint32_t)((kt >> 1) & 1));
+                waited++;
             }
-            __syncwarp(gm);
         }
-        const StagedPointT<DOUT> pt = sm.pts[tt & 15];
-        const double x1 = pt.x1, x2 = pt.x2;
-        const int orig = pt.orig;
-        if (N == 0) {  // sparse_gp.hpp:100-110
-            if (r == 0) {
-                const double d = __dadd_rn(kstar, s20);
+        const HalfTile<DOUT>& tl = sm.tile[(tt >> 4) & 1];
+        if (tt == 0) {  // sparse_gp.hpp:100-110 (both halves: a half has n == 0 or starts here)
+            if (live) {
+                if (r == 0) {
+                    const double d = __dadd_rn(kstar, s20);
 #pragma unroll
-                for (int c = 0; c < DOUT; c++) alpha[c] = __ddiv_rn(pt.y[c], d);
-                C[0] = __ddiv_rn(-1.0, d);
-                Q[0] = __ddiv_rn(1.0, kstar);
-                b1 = x1; b2 = x2; bidx = orig;
-                sm.cnt[0]++;
+                    for (int c = 0; c < DOUT; c++) alpha[c] = __ddiv_rn(tl.y[c][sh1], d);
+                    creg[0] = __ddiv_rn(-1.0, d);
+                    qreg[0] = __ddiv_rn(1.0, kstar);
+                    b1 = tl.x1[sh1]; b2 = tl.x2[sh1]; bidx = tl.orig[sh3];
+                    cnt++;
+                }
+                N = 1;
             }
-            N = 1;
-            __syncwarp(gm);
             continue;
         }
-        // k = K(x, BV) (:119); lanes >= N hold zeros
+        if (live && !inreg) {  // back from a full update: rows into registers
+#pragma unroll
+            for (int p = 0; p < 8; p++) {
+                const double2 c2 = *reinterpret_cast<const double2*>(Crow + 2 * p), q2 = *reinterpret_cast<const double2*>(Qrow + 2 * p);
+                creg[2 * p] = c2.x; creg[2 * p + 1] = c2.y;
+                qreg[2 * p] = q2.x; qreg[2 * p + 1] = q2.y;
+            }
+            inreg = true;
+        }
+        const int Nw = max(N, __shfl_xor_sync(FULL, N, 16));
         const bool act = r < N;
-        double kl = have_next ? kl_next : rbf(x1, x2, b1, b2, p0, cl);
+        // k = K(x, BV) (:119); lanes >= N hold zeros.  Usually computed during the previous point's chain.
+        double kl = kl_next;
+        if (live && !have_next) kl = rbf(tl.x1[s + sh1], tl.x2[s + sh1], b1, b2, p0, cl);
         kl = act ? kl : 0.0;
-        if (act) sm.kv[r] = kl;
-        __syncwarp(gm);
-        have_next = ((tt + 1) & 15) != 0 && tt + 1 < n;   // the next point is already staged
-        // (C k)_r and (Q k)_r = e_hat_r   (:122, :140)
-        double rv = 0.0, el = 0.0;
-        if (act) row4x2_padded16(Crow, Qrow, sm.kv, N, &rv, &el);
-        // m = alpha'k, k'Ck, k'e_hat: one product per lane, 4-step butterflies over the half-warp
-        double pm[DOUT];
+        sm.kv[r] = kl;
+        __syncwarp();
+        have_next = live && s != 15 && tt + 1 < n;   // the next point is staged in the same tile
+        const double nx1 = tl.x1[s + 1 + sh1], nx2 = tl.x2[s + 1 + sh1];  // (a stale slot when !have_next: value ignored)
+        double rv = 0.0, el = 0.0, q[DOUT], rr = 0.0, gamma = 0.0;
+        bool sp = false;
+        // one point of the recursion up to and including a sparse update, for NG occupied groups of four columns
+        auto step = [&](auto ngc) {
+            constexpr int NG = decltype(ngc)::value;
+            {
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
 #pragma unroll
-        for (int c = 0; c < DOUT; c++) pm[c] = act ? fma(alpha[c], kl, 0.0) : 0.0;
-        double pc = act ? fma(kl, rv, 0.0) : 0.0;
-        double pe = act ? fma(kl, el, 0.0) : 0.0;
-#pragma unroll
-        for (int off = 8; off >= 1; off >>= 1) {
-#pragma unroll
-            for (int c = 0; c < DOUT; c++) pm[c] = __dadd_rn(pm[c], shfl16_xor(gm, pm[c], off));
-            pc = __dadd_rn(pc, shfl16_xor(gm, pc, off));
-            pe = __dadd_rn(pe, shfl16_xor(gm, pe, off));
-            if (off == 8) {
-                // unconditional (a stale slot is read when the next point is not staged; the value is then ignored) and
-                // placed inside the butterfly's basic block: the exp chain overlaps the shuffle latency
-                const double nx1 = sm.pts[(tt + 1) & 15].x1, nx2 = sm.pts[(tt + 1) & 15].x2;
-                kl_next = rbf(nx1, nx2, b1, b2, p0, cl);
+                for (int g = 0; g < NG; g++) {
+                    const double2 k01 = *reinterpret_cast<const double2*>(sm.kv + 4 * g), k23 = *reinterpret_cast<const double2*>(sm.kv + 4 * g + 2);
+                    a0 = fma(creg[4 * g], k01.x, a0); a1 = fma(creg[4 * g + 1], k01.y, a1);
+                    a2 = fma(creg[4 * g + 2], k23.x, a2); a3 = fma(creg[4 * g + 3], k23.y, a3);
+                    e0 = fma(qreg[4 * g], k01.x, e0); e1 = fma(qreg[4 * g + 1], k01.y, e1);
+                    e2 = fma(qreg[4 * g + 2], k23.x, e2); e3 = fma(qreg[4 * g + 3], k23.y, e3);
+                }
+                rv = __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));   // (C k)_r  (:122); rows >= N are zero
+                el = __dadd_rn(__dadd_rn(e0, e1), __dadd_rn(e2, e3));   // (Q k)_r = e_hat_r  (:140)
             }
-        }
-        const double s2 = __dadd_rn(kstar, pc);
-        const double den = __dadd_rn(s20, s2);
-        // one division for two quotients: lanes 8-15 compute r = -1/den (gaussian_noise.cpp:15-18), lanes 0-7
-        // q = (y - m)/den (gaussian_noise.cpp:9-12 / gaussian_noise_3d.cpp:10-13)
-        double q[DOUT];
-        {
-            const double t = __ddiv_rn((r & 8) ? -1.0 : __dadd_rn(pt.y[0], -pm[0]), den);
-            q[0] = shfl16(gm, t, 0);
+            // k of the next point: independent of everything below, overlaps the butterflies and the divisions
+            kl_next = rbf(nx1, nx2, b1, b2, p0, cl);
+            // m = alpha'k, k'Ck, k'e_hat: one product per lane, 4-step butterflies over the half-warp
+            double pm[DOUT];
 #pragma unroll
-            for (int c = 1; c < DOUT; c++) q[c] = __ddiv_rn(__dadd_rn(pt.y[c], -pm[c]), den);
-            pm[0] = shfl16(gm, t, 8);  // reuse the register: r
-        }
-        const double rr = pm[0];
-        double gamma = __dadd_rn(kstar, -pe);                 // :144
-        if (gamma < tiny12()) gamma = 0.0;
-        if (gamma < eps_tol) {
-            // sparse update (:155-163)
-            run++;
-            const double eta = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn(gamma, rr)));
-            const double sh = act ? __dadd_rn(rv, el) : 0.0;
-            sm.sv[r] = sh;  // zero beyond N: pad columns stay exact zeros below
-            if (act) {
+            for (int c = 0; c < DOUT; c++) pm[c] = fma(alpha[c], kl, 0.0);
+            double pc = fma(kl, rv, 0.0);
+            double pe = fma(kl, el, 0.0);
 #pragma unroll
-                for (int c = 0; c < DOUT; c++) alpha[c] = __dadd_rn(alpha[c], __dmul_rn(sh, __dmul_rn(q[c], eta)));
+            for (int off = 8; off >= 1; off >>= 1) {
+#pragma unroll
+                for (int c = 0; c < DOUT; c++) pm[c] = __dadd_rn(pm[c], __shfl_xor_sync(FULL, pm[c], off));
+                pc = __dadd_rn(pc, __shfl_xor_sync(FULL, pc, off));
+                pe = __dadd_rn(pe, __shfl_xor_sync(FULL, pe, off));
             }
-            __syncwarp(gm);
-            const double re = __dmul_rn(rr, eta);
-            if (act) {
+            const double s2 = __dadd_rn(kstar, pc);
+            const double den = __dadd_rn(s20, s2);
+            // one division for two quotients: lanes 8-15 compute r = -1/den (gaussian_noise.cpp:15-18), lanes 0-7
+            // q = (y - m)/den (gaussian_noise.cpp:9-12 / gaussian_noise_3d.cpp:10-13)
+            {
+                const double t = __ddiv_rn((r & 8) ? -1.0 : __dadd_rn(tl.y[0][s + sh1], -pm[0]), den);
+                q[0] = __shfl_sync(FULL, t, lane & 16);
+                rr = __shfl_sync(FULL, t, (lane & 16) | 8);
 #pragma unroll
-                for (int p8 = 0; p8 < 8; p8++) {
-                    const int j = 2 * p8;
-                    if (j < N) {
-                        double2 c = *reinterpret_cast<double2*>(Crow + j);
-                        const double2 s2v = *reinterpret_cast<const double2*>(sm.sv + j);
-                        c.x = fma(re, __dmul_rn(sh, s2v.x), c.x);
-                        if (j + 1 < N) c.y = fma(re, __dmul_rn(sh, s2v.y), c.y);
-                        *reinterpret_cast<double2*>(Crow + j) = c;
+                for (int c = 1; c < DOUT; c++) q[c] = __ddiv_rn(__dadd_rn(tl.y[c][s + sh1], -pm[c]), den);
+            }
+            gamma = __dadd_rn(kstar, -pe);  // :144
+            if (gamma < tiny12()) gamma = 0.0;
+            sp = live && gamma < eps_tol;
+            double shv = 0.0, re = 0.0;
+            if (sp) {
+                // sparse update (:155-163)
+                run++;
+                const double eta = __drcp_rn(__dadd_rn(1.0, __dmul_rn(gamma, rr)));  // == 1 / (1 + gamma r), correctly rounded
+                shv = act ? __dadd_rn(rv, el) : 0.0;
+                sm.sv[r] = shv;  // zero beyond N
+                if (act) {
+#pragma unroll
+                    for (int c = 0; c < DOUT; c++) alpha[c] = __dadd_rn(alpha[c], __dmul_rn(shv, __dmul_rn(q[c], eta)));
+                }
+                re = __dmul_rn(rr, eta);
+            }
+            __syncwarp();
+            if (sp && act) {
+                // finite factors: a column beyond N gets fma(re, sh * 0, 0) = +0, so the pad columns stay exact zeros without
+                // per-column predicates; otherwise (state already inf / NaN) the columns are guarded one by one
+                const bool fin = ((__double2hiint(re) & 0x7ff00000) != 0x7ff00000) && ((__double2hiint(shv) & 0x7ff00000) != 0x7ff00000);
+                if (fin) {
+#pragma unroll
+                    for (int g = 0; g < NG; g++) {
+                        const double2 s01 = *reinterpret_cast<const double2*>(sm.sv + 4 * g), s23 = *reinterpret_cast<const double2*>(sm.sv + 4 * g + 2);
+                        creg[4 * g] = fma(re, __dmul_rn(shv, s01.x), creg[4 * g]);
+                        creg[4 * g + 1] = fma(re, __dmul_rn(shv, s01.y), creg[4 * g + 1]);
+                        creg[4 * g + 2] = fma(re, __dmul_rn(shv, s23.x), creg[4 * g + 2]);
+                        creg[4 * g + 3] = fma(re, __dmul_rn(shv, s23.y), creg[4 * g + 3]);
                     }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4 * NG; j++)
+                        if (j < N) creg[j] = fma(re, __dmul_rn(shv, sm.sv[j]), creg[j]);
                 }
             }
-            continue;  // Q and N unchanged: neither deletion loop can fire
+        };
+        if (Nw <= 8) step(IntC<2>());
+        else if (Nw <= 12) step(IntC<3>());
+        else step(IntC<4>());
+        if (!live || sp) continue;  // Q and N unchanged: neither deletion loop can fire
+        // ---- full update (:164-203), this half only; the rows go back to shared memory ----
+#pragma unroll
+        for (int p = 0; p < 8; p++) {
+            *reinterpret_cast<double2*>(Crow + 2 * p) = make_double2(creg[2 * p], creg[2 * p + 1]);
+            *reinterpret_cast<double2*>(Qrow + 2 * p) = make_double2(qreg[2 * p], qreg[2 * p + 1]);
         }
-        // full update (:164-203)
+        inreg = false;
         have_next = false;  // the BV set changes
-        if (r == 0) {
+        const double x1 = tl.x1[s + sh1], x2 = tl.x2[s + sh1];
+        const int orig = tl.orig[s + sh3];
+        {
             const unsigned long long n2 = (unsigned long long)N * N;
-            sm.cnt[1] += run; sm.cnt[5] += (unsigned long long)run * N; sm.cnt[6] += run * n2; sm.cnt[7] += run * n2;
+            cnt += (r == 1) ? (unsigned long long)run : (r == 5) ? (unsigned long long)run * N : (r == 6 || r == 7) ? run * n2 : 0ull;
         }
         run = 0;
+        __syncwarp(gm);
         if (N + 1 > ldmax) {  // does not fit this bucket: hand the state to the next one
             int pos = 0;
             if (r == 0) pos = atomicAdd(a.queue_count, 1);
             pos = __shfl_sync(gm, pos, 0, 16);
             double* slot = a.handoff_out + (size_t)pos * slot_doubles(W_N, DOUT);
-            __syncwarp(gm);
             if (r == 0) {
                 a.queue[pos] = (int32_t)patch;
                 reinterpret_cast<int*>(slot)[0] = N;
                 reinterpret_cast<int*>(slot)[1] = tt;
-                for (int i = 0; i < NCNT; i++) reinterpret_cast<unsigned long long*>(slot + 2)[i] = sm.cnt[i];
             }
+            if (r < NCNT) reinterpret_cast<unsigned long long*>(slot + 2)[r] = cnt;
             double* v = slot + 2 + NCNT;
 #pragma unroll
             for (int c = 0; c < DOUT; c++) v[c * W_N + r] = alpha[c];
@@ -355,11 +448,11 @@ __global__ void __launch_bounds__(32, DOUT == 1 ? 20 : 16) sogp_fit_half_kernel(
                 v[(DOUT + 2) * W_N + e] = C[i * W_LD + j];
                 v[(DOUT + 2) * W_N + W_N * W_N + e] = Q[i * W_LD + j];
             }
-            return;
+            done = true;
+            continue;
         }
-        if (r == 0) {
-            sm.cnt[2]++; sm.cnt[5] += N; sm.cnt[6] += (unsigned long long)N * N; sm.cnt[8] += (unsigned long long)(N + 1) * (N + 1);
-        }
+        cnt += (r == 2) ? 1ull : (r == 5) ? (unsigned long long)N : (r == 6) ? (unsigned long long)N * N
+                        : (r == 8) ? (unsigned long long)(N + 1) * (N + 1) : 0ull;
         if (act) {
             sm.sv[r] = rv;
             sm.ev[r] = el;
@@ -380,16 +473,16 @@ __global__ void __launch_bounds__(32, DOUT == 1 ? 20 : 16) sogp_fit_half_kernel(
             if (r < N1) {
                 const double si = sm.sv[r], ei = sm.ev[r];
                 for (int j = 0; j < N1; j += 2) {  // column pairs; the pad column (j + 1 == N1) stays zero
-                    double2 c = *reinterpret_cast<double2*>(Crow + j), q = *reinterpret_cast<double2*>(Qrow + j);
+                    double2 c = *reinterpret_cast<double2*>(Crow + j), qq = *reinterpret_cast<double2*>(Qrow + j);
                     const double2 s2v = *reinterpret_cast<const double2*>(sm.sv + j), e2v = *reinterpret_cast<const double2*>(sm.ev + j);
                     c.x = fma(rr, __dmul_rn(si, s2v.x), c.x);
-                    q.x = fma(ig, __dmul_rn(ei, e2v.x), q.x);
+                    qq.x = fma(ig, __dmul_rn(ei, e2v.x), qq.x);
                     if (j + 1 < N1) {
                         c.y = fma(rr, __dmul_rn(si, s2v.y), c.y);
-                        q.y = fma(ig, __dmul_rn(ei, e2v.y), q.y);
+                        qq.y = fma(ig, __dmul_rn(ei, e2v.y), qq.y);
                     }
                     *reinterpret_cast<double2*>(Crow + j) = c;
-                    *reinterpret_cast<double2*>(Qrow + j) = q;
+                    *reinterpret_cast<double2*>(Qrow + j) = qq;
                 }
             }
             N = N1;
@@ -418,7 +511,7 @@ __global__ void __launch_bounds__(32, DOUT == 1 ? 20 : 16) sogp_fit_half_kernel(
                 if (phase == 1) minscore = best;
                 // ---- delete_bv(loc), :252-295 ----
                 const int L = N - 1, M = N - 1;
-                if (r == 0) { sm.cnt[9] += (unsigned long long)M * M; sm.cnt[phase == 0 ? 3 : 4]++; }
+                cnt += (r == 9) ? (unsigned long long)M * M : (r == (phase == 0 ? 3 : 4)) ? 1ull : 0ull;
                 double csi = 0, qsi = 0, repc = 0, repq = 0;
                 const int src = (r == loc) ? L : r;
                 if (r < N) {
@@ -464,37 +557,48 @@ __global__ void __launch_bounds__(32, DOUT == 1 ? 20 : 16) sogp_fit_half_kernel(
                 if (r < M) {
                     const double qi = sm.sv[r], ci = sm.ev[r];
                     for (int j = 0; j < M; j += 2) {  // column pairs; the pad column (j + 1 == M) stays zero
-                        double2 c = *reinterpret_cast<double2*>(Crow + j), q = *reinterpret_cast<double2*>(Qrow + j);
+                        double2 c = *reinterpret_cast<double2*>(Crow + j), qq = *reinterpret_cast<double2*>(Qrow + j);
                         const double2 s2v = *reinterpret_cast<const double2*>(sm.sv + j), e2v = *reinterpret_cast<const double2*>(sm.ev + j);
                         const double u0 = __dmul_rn(qi, s2v.x), v0 = __dmul_rn(ci, e2v.x);
                         c.x = __dadd_rn(c.x, fma(u0, iq, -__dmul_rn(v0, iqc)));
-                        q.x = fma(-u0, iq, q.x);
+                        qq.x = fma(-u0, iq, qq.x);
                         if (j + 1 < M) {
                             const double u1 = __dmul_rn(qi, s2v.y), v1 = __dmul_rn(ci, e2v.y);
                             c.y = __dadd_rn(c.y, fma(u1, iq, -__dmul_rn(v1, iqc)));
-                            q.y = fma(-u1, iq, q.y);
+                            qq.y = fma(-u1, iq, qq.y);
                         }
                         *reinterpret_cast<double2*>(Crow + j) = c;
-                        *reinterpret_cast<double2*>(Qrow + j) = q;
+                        *reinterpret_cast<double2*>(Qrow + j) = qq;
                     }
                 }
                 N = M;
                 __syncwarp(gm);
             }
         }
+        __syncwarp(gm);
+    }
+    __syncwarp();
+    if (issued > waited) mbar_wait(&sm.mbar[waited & 1], (uint32_t)((waited >> 1) & 1));  // never leave with a copy in flight
+    if (w >= a.n_work || n == 0 || done) return;
+    if (inreg) {
+#pragma unroll
+        for (int p = 0; p < 8; p++) {
+            *reinterpret_cast<double2*>(Crow + 2 * p) = make_double2(creg[2 * p], creg[2 * p + 1]);
+            *reinterpret_cast<double2*>(Qrow + 2 * p) = make_double2(qreg[2 * p], qreg[2 * p + 1]);
+        }
+    }
+    {
+        const unsigned long long n2 = (unsigned long long)N * N;
+        cnt += (r == 1) ? (unsigned long long)run : (r == 5) ? (unsigned long long)run * N : (r == 6 || r == 7) ? run * n2 : 0ull;
     }
     __syncwarp(gm);
     if (r == 0) {
-        const unsigned long long n2 = (unsigned long long)N * N;
-        sm.cnt[1] += run; sm.cnt[5] += (unsigned long long)run * N; sm.cnt[6] += run * n2; sm.cnt[7] += run * n2;
         a.nbv[op] = N;
         const double c00 = C[0];
         a.flags[op] = (c00 != c00) ? 1 : 0;
-        unsigned long long* st = a.stats;
-        atomicAdd(st + 0, (unsigned long long)n);
-        for (int i = 0; i < NCNT; i++)
-            if (sm.cnt[i]) atomicAdd(st + 1 + i, sm.cnt[i]);
+        atomicAdd(a.stats + 0, (unsigned long long)n);
     }
+    if (r < NCNT && cnt) atomicAdd(a.stats + 1 + r, cnt);
     const int64_t ob = op * cap;
     if (r < N) {
 #pragma unroll
