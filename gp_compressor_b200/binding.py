@@ -29,7 +29,7 @@ class GpcConfig(C.Structure):
                 ("eps_tol", C.c_double), ("sigmaf_sq", C.c_double), ("l_sq", C.c_double), ("leaf_order", C.c_int32),
                 ("shuffle", C.c_int32), ("rgb_rand", C.c_int32), ("device", C.c_int32), ("shard_rank", C.c_int32),
                 ("shard_count", C.c_int32), ("keep_state", C.c_int32), ("rgb", C.c_int32), ("rgb_s0", C.c_double),
-                ("rgb_eps_tol", C.c_double)]
+                ("rgb_eps_tol", C.c_double), ("decode_separable", C.c_int32), ("pad0", C.c_int32)]
 
 
 class GpcSizes(C.Structure):

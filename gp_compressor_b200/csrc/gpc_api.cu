@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 
 #include "gpc_internal.h"
 
@@ -27,6 +28,8 @@ struct gpc_handle {
     uint32_t depth = 0;
     double lattice_min[3] = {0, 0, 0};
     bool have_fit = false, have_frames = false, have_binning = false, have_cloud = false, params_packed = false;
+    bool have_state = false;     // dumpC / dumpQ (and the fed counts) belong to the fit the handle holds
+    bool heights_valid = false;  // heights hold the grid of the last decompress
     int64_t s_begin = 0, s_count = 0;  // stream range of this shard
     // device buffers
     DevBuf cloud;                               // input cloud (n_in * 32)
@@ -415,6 +418,7 @@ int run_fit(gpc_handle* h, StageTimer& tm, bool cont = false) {
     size_t t3 = tm.mark();
     tm.span(&h->stats.ms_group, t_pack0, t3);
     h->have_fit = true;
+    h->have_state = c.keep_state != 0;
     h->params_packed = true;
     return GPC_OK;
 }
@@ -462,6 +466,7 @@ int run_decode(gpc_handle* h, bool want_cloud, bool want_heights, StageTimer& tm
     h->n_decoded = n_nonempty * g2;
     if (want_cloud) CK(h->out32.reserve(std::max<int64_t>(h->n_decoded, 1) * GPC_POINT_BYTES));
     if (want_heights) CK(h->heights.reserve(std::max<int64_t>(h->n_decoded, 1) * sizeof(double)));
+    h->heights_valid = want_heights;
     PredictArgs a;
     a.n_patches = PL;
     a.nbv = h->nbv.as<int32_t>();
@@ -484,6 +489,7 @@ int run_decode(gpc_handle* h, bool want_cloud, bool want_heights, StageTimer& tm
     }
     a.nmax = std::max(maxes[0], 1); a.nrmax = with_rgb ? std::max(maxes[1], 1) : 0;
     a.res = c.res; a.sz = c.sz; a.p0 = c.sigmaf_sq; a.cl = kernel_cl(c);
+    a.separable = c.decode_separable != 0;
     a.out32 = want_cloud ? h->out32.as<uint8_t>() : nullptr;
     a.heights = want_heights ? h->heights.as<double>() : nullptr;
     if (launch_predict_grid(a, st) != cudaSuccess)
@@ -738,6 +744,8 @@ int gpc_config_default(gpc_config* c) {
     c->rgb = 0;                      // next-row N1, opt-in
     c->rgb_s0 = (double)1e2f;        // sparse_gp_field.h:43
     c->rgb_eps_tol = (double)1e-4f;  // sparse_gp_field.hpp:16
+    c->decode_separable = 0;         // the reference's direct kernel evaluation
+    c->pad0 = 0;
     return GPC_OK;
 }
 
@@ -745,8 +753,8 @@ int gpc_create(const gpc_config* cfg, gpc_handle** out) {
     if (!cfg || !out) return GPC_ERR_INVALID;
     *out = nullptr;
     if (!(cfg->res > 0) || cfg->sz < 1 || cfg->shard_count < 1 || cfg->shard_rank < 0 || cfg->shard_rank >= cfg->shard_count ||
-        !(cfg->l_sq > 0))
-        return GPC_ERR_INVALID;
+        !(cfg->l_sq > 0) || cfg->capacity < 1 || cfg->capacity > 201 || !(cfg->s0 > 0) || !(cfg->sigmaf_sq > 0))
+        return GPC_ERR_INVALID;  // (the reference's unbounded capacity 0 / -1 modes are not built: DESIGN.md section 6)
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) return GPC_ERR_CUDA;
     if (cudaSetDevice(cfg->device) != cudaSuccess) return GPC_ERR_CUDA;
@@ -759,17 +767,23 @@ int gpc_create(const gpc_config* cfg, gpc_handle** out) {
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return GPC_ERR_CUDA; }
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    if (cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_a2, cudaEventDisableTiming) != cudaSuccess) {
+    auto bail = [&]() {
+        if (h->ev_a) cudaEventDestroy(h->ev_a);
+        if (h->ev_a2) cudaEventDestroy(h->ev_a2);
+        if (h->stream2) cudaStreamDestroy(h->stream2);
         cudaStreamDestroy(h->stream);
         delete h;
         return GPC_ERR_CUDA;
-    }
+    };
+    if (cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_a2, cudaEventDisableTiming) != cudaSuccess)
+        return bail();
+    // process-wide jump-ahead tables of the glibc rand() generator: built once, whichever thread creates a handle first
     static RandTables tables;
-    static bool tables_ready = false;
-    if (!tables_ready) { rand_tables_init(&tables); tables_ready = true; }
-    if (rand_upload_tables(&tables) != cudaSuccess) { cudaStreamDestroy(h->stream); delete h; return GPC_ERR_CUDA; }
+    static std::once_flag tables_once;
+    std::call_once(tables_once, [] { rand_tables_init(&tables); });
+    if (rand_upload_tables(&tables) != cudaSuccess) return bail();
     *out = h;
     return GPC_OK;
 }
@@ -813,7 +827,7 @@ static int fit_patches_impl(gpc_handle* h, int64_t P, const int64_t* off, const 
     if (!h || P < 0 || !off) return GPC_ERR_INVALID;
     CK(cudaSetDevice(h->cfg.device));
     if (cont) {
-        if (!h->have_fit || !h->cfg.keep_state || !h->dumpC.p)
+        if (!h->have_fit || !h->cfg.keep_state || !h->have_state || !h->dumpC.p)
             return fail(h, GPC_ERR_STATE, "gpc_add_measurements needs a previous fit on this handle made with gpc_config.keep_state");
         if (h->shard_mode || h->cfg.shard_count != 1 || P != h->n_patches || h->patch_lo != 0 || h->patch_hi != h->n_patches)
             return fail(h, GPC_ERR_INVALID, "gpc_add_measurements: same patches as the previous fit, one shard");
@@ -1062,6 +1076,7 @@ int gpc_decompress(gpc_handle* h, void* out, int64_t capacity_points, int64_t* n
 
 int gpc_get_heights(gpc_handle* h, double* out, int64_t capacity) {
     if (!h || !out) return GPC_ERR_INVALID;
+    if (!h->heights_valid) return fail(h, GPC_ERR_STATE, "heights are produced by gpc_decompress_resident: call it before gpc_get_heights");
     if (capacity < h->n_decoded) return fail(h, GPC_ERR_INVALID, "heights buffer too small");
     CK(cudaSetDevice(h->cfg.device));
     if (h->n_decoded > 0) CK(cudaMemcpy(out, h->heights.p, h->n_decoded * sizeof(double), cudaMemcpyDeviceToHost));
@@ -1107,7 +1122,7 @@ static int evaluate_impl(gpc_handle* h, int64_t op0, int64_t P, const int64_t* o
     if (!h || P < 0 || (P > 0 && !off)) return GPC_ERR_INVALID;
     const bool need_c = sigma || lik || dX;   // the mean alone needs no state
     if (!h->have_fit) return fail(h, GPC_ERR_STATE, "evaluation before compress / fit");
-    if (need_c && (!h->cfg.keep_state || !h->dumpC.p))
+    if (need_c && (!h->cfg.keep_state || !h->have_state || !h->dumpC.p))
         return fail(h, GPC_ERR_STATE, "sigma / likelihood evaluation needs a fit made with gpc_config.keep_state");
     if (dout == 3 && (!h->have_rgb || (need_c && !h->r_dumpC.p)))
         return fail(h, GPC_ERR_STATE, "gpc_evaluate_patches_rgb needs a compress with gpc_config.rgb = 1 (and keep_state = 1 for sigma / likelihood)");
@@ -1309,7 +1324,7 @@ int gpc_get_params_rgb(gpc_handle* h, int32_t* nbv, int64_t* bv_off, int32_t* bv
 
 int gpc_get_state(gpc_handle* h, int64_t patch, double* C, double* Q) {
     if (!h) return GPC_ERR_INVALID;
-    if (!h->have_fit || !h->cfg.keep_state) return fail(h, GPC_ERR_STATE, "gpc_get_state needs a fit made with keep_state");
+    if (!h->have_fit || !h->cfg.keep_state || !h->have_state) return fail(h, GPC_ERR_STATE, "gpc_get_state needs a fit made with keep_state");
     if (h->shard_mode) patch -= h->gshift;
     if (patch < h->patch_lo || patch >= h->patch_hi) return fail(h, GPC_ERR_INVALID, "patch outside this shard");
     CK(cudaSetDevice(h->cfg.device));
@@ -1373,6 +1388,12 @@ int gpc_set_params(gpc_handle* h, int64_t P, const int32_t* nbv, const double* b
     h->have_rgb = false;
     h->n_bv_total = -1;
     h->params_packed = false;
+    // nothing of an earlier fit survives: no claimed stream, no kept C / Q, no fed counts, no BV indices
+    h->n_claimed = 0; h->s_begin = 0; h->s_count = 0;
+    h->have_state = false;
+    h->heights_valid = false;
+    CK(h->bidx.reserve((size_t)PLa * cap * sizeof(int32_t)));
+    CK(cudaMemset(h->bidx.p, 0xff, (size_t)PLa * cap * sizeof(int32_t)));
     return GPC_OK;
 }
 
@@ -1526,10 +1547,13 @@ int gpc_get_config(const gpc_handle* h, gpc_config* cfg) {
     return GPC_OK;
 }
 
-int gpc_load(gpc_handle* h, const char* path) {
-    if (!h || !path) return GPC_ERR_INVALID;
+static int gpc_load_impl(gpc_handle* h, const char* path) {
     FILE* f = std::fopen(path, "rb");
     if (!f) return fail(h, GPC_ERR_INVALID, std::string("cannot open ") + path);
+    struct Closer { FILE* f; ~Closer() { if (f) std::fclose(f); } } closer{f};
+    std::fseek(f, 0, SEEK_END);
+    const int64_t fsize = (int64_t)std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
     char magic[8];
     uint32_t version = 0;
     double dcfg[5];
@@ -1539,7 +1563,15 @@ int gpc_load(gpc_handle* h, const char* path) {
     ok = ok && std::fread(&version, 4, 1, f) == 1 && (version == 1 || version == 2);
     ok = ok && std::fread(dcfg, sizeof(dcfg), 1, f) == 1 && std::fread(icfg, sizeof(icfg), 1, f) == 1;
     ok = ok && std::fread(&PL, 8, 1, f) == 1 && std::fread(&T, 8, 1, f) == 1 && PL >= 0 && T >= 0;
-    if (!ok) { std::fclose(f); return fail(h, GPC_ERR_INVALID, "not a gpc_b200 parameter file (or unsupported version)"); }
+    if (!ok) return fail(h, GPC_ERR_INVALID, "not a gpc_b200 parameter file (or unsupported version)");
+    // nothing of the handle is touched before the whole file has been read and checked
+    const double f_res = dcfg[0], f_s0 = dcfg[1], f_eps = dcfg[2], f_p0 = dcfg[3], f_lsq = dcfg[4];
+    const int32_t f_sz = icfg[0], f_cap = icfg[1];
+    if (!(f_res > 0) || !(f_lsq > 0) || f_sz < 1 || f_cap < 1 || f_cap > 201 || !(f_s0 == f_s0) || !(f_p0 == f_p0))
+        return fail(h, GPC_ERR_INVALID, "parameter file holds an invalid configuration (res, l_sq > 0, sz >= 1, 1 <= capacity <= 201)");
+    // sizes against the file length: 4 PL + 80 PL + 24 T bytes follow the header
+    if (PL > fsize / 84 + 1 || T > fsize / 24 + 1 || T > PL * (int64_t)f_cap)
+        return fail(h, GPC_ERR_INVALID, "parameter file: patch / basis-vector counts exceed the file size");
     std::vector<int32_t> nbv(PL);
     std::vector<double> quat(PL * 4), mean(PL * 3), rgbm(PL * 3), b1(T), b2(T), al(T);
     auto get = [&](void* p, size_t n) { if (n) ok = ok && std::fread(p, n, 1, f) == 1; };
@@ -1559,7 +1591,9 @@ int gpc_load(gpc_handle* h, const char* path) {
         get(&has_rgb, sizeof(has_rgb));
         get(rcfg, sizeof(rcfg));
         get(&TR, sizeof(TR));
-        if (ok && has_rgb && TR >= 0) {
+        if (ok && has_rgb) {
+            if (TR < 0 || TR > fsize / 40 + 1 || TR > PL * (int64_t)f_cap)
+                return fail(h, GPC_ERR_INVALID, "inconsistent RGB block in the parameter file");
             rnbv.resize(PL); rb1.resize(TR); rb2.resize(TR); ra.resize(3 * TR);
             get(rnbv.data(), PL * sizeof(int32_t));
             get(rb1.data(), TR * sizeof(double));
@@ -1567,29 +1601,37 @@ int gpc_load(gpc_handle* h, const char* path) {
             get(ra.data(), 3 * TR * sizeof(double));
         }
     }
-    std::fclose(f);
     if (!ok) return fail(h, GPC_ERR_INVALID, "truncated parameter file");
     int64_t sum = 0;
-    for (int32_t v : nbv) sum += v;
+    for (int32_t v : nbv) {
+        if (v < 0 || v > f_cap) return fail(h, GPC_ERR_INVALID, "inconsistent parameter file");
+        sum += v;
+    }
     if (sum != T) return fail(h, GPC_ERR_INVALID, "inconsistent parameter file");
-    // the decoder's configuration comes from the file (the shard layout and device stay the handle's own)
-    h->cfg.res = dcfg[0]; h->cfg.s0 = dcfg[1]; h->cfg.eps_tol = dcfg[2]; h->cfg.sigmaf_sq = dcfg[3]; h->cfg.l_sq = dcfg[4];
-    h->cfg.sz = icfg[0]; h->cfg.capacity = icfg[1];
+    std::vector<int64_t> ro(PL + 1, 0);
+    if (has_rgb) {
+        for (int64_t p = 0; p < PL; p++) {
+            if (rnbv[p] < 0 || rnbv[p] > f_cap) return fail(h, GPC_ERR_INVALID, "inconsistent RGB block in the parameter file");
+            ro[p + 1] = ro[p] + rnbv[p];
+        }
+        if (ro[PL] != TR) return fail(h, GPC_ERR_INVALID, "inconsistent RGB block in the parameter file");
+    }
+    // the decoder's configuration comes from the file (the shard layout and device stay the handle's own); committed only
+    // when the parameters are installed
+    const gpc_config saved = h->cfg;
+    h->cfg.res = f_res; h->cfg.s0 = f_s0; h->cfg.eps_tol = f_eps; h->cfg.sigmaf_sq = f_p0; h->cfg.l_sq = f_lsq;
+    h->cfg.sz = f_sz; h->cfg.capacity = f_cap;
     h->cfg.rgb_s0 = rcfg[0]; h->cfg.rgb_eps_tol = rcfg[1];
     h->cfg.rgb = has_rgb;
+    h->have_fit = false;  // whatever the handle held is gone from here on: its arrays are strided by the old capacity
     const double one = 0.0;
     int rc = gpc_set_params(h, PL, nbv.data(), T ? b1.data() : &one, T ? b2.data() : &one, T ? al.data() : &one, quat.data(), mean.data(),
                             rgbm.data());
-    if (rc || !has_rgb) return rc;
+    if (rc) { h->cfg = saved; h->have_fit = false; return rc; }
+    if (!has_rgb) return GPC_OK;
     // install the RGB field GP of this shard's patch range (strided by capacity, like the fitted arrays)
     const int cap = h->cfg.capacity;
     const int64_t lo = h->patch_lo, hi = h->patch_hi, PLs = hi - lo, PLa = std::max<int64_t>(PLs, 1);
-    std::vector<int64_t> ro(PL + 1, 0);
-    for (int64_t p = 0; p < PL; p++) {
-        if (rnbv[p] < 0 || rnbv[p] > cap) return fail(h, GPC_ERR_INVALID, "inconsistent RGB block in the parameter file");
-        ro[p + 1] = ro[p] + rnbv[p];
-    }
-    if (ro[PL] != TR) return fail(h, GPC_ERR_INVALID, "inconsistent RGB block in the parameter file");
     DevBuf* dst[5] = {&h->r_b1, &h->r_b2, &h->r_alpha0, &h->r_alpha1, &h->r_alpha2};
     std::vector<double> t((size_t)PLa * cap);
     for (int k = 0; k < 5; k++) {
@@ -1602,8 +1644,21 @@ int gpc_load(gpc_handle* h, const char* path) {
     }
     CK(h->r_nbv.reserve(PLa * sizeof(int32_t)));
     if (PLs > 0) CK(cudaMemcpy(h->r_nbv.p, rnbv.data() + lo, PLs * sizeof(int32_t), cudaMemcpyHostToDevice));
+    // a loaded file has no BV indices: gpc_get_params_rgb(bv_index) reports -1
+    CK(h->r_bidx.reserve((size_t)PLa * cap * sizeof(int32_t)));
+    CK(cudaMemset(h->r_bidx.p, 0xff, (size_t)PLa * cap * sizeof(int32_t)));
     h->have_rgb = true;
     return GPC_OK;
+}
+
+int gpc_load(gpc_handle* h, const char* path) {
+    if (!h || !path) return GPC_ERR_INVALID;
+    try {
+        return gpc_load_impl(h, path);
+    } catch (const std::exception& e) {  // e.g. bad_alloc on a hostile header: nothing crosses the C ABI
+        h->have_fit = false;
+        return fail(h, GPC_ERR_INVALID, std::string("gpc_load: ") + e.what());
+    }
 }
 
 int gpc_debug_peak(gpc_handle* h, int kind, double* value) {

@@ -188,6 +188,7 @@ struct PredictArgs {
     double res;
     int sz;
     double p0, cl;
+    bool separable;              // gpc_config.decode_separable: kernel tables instead of one exp per (grid point, BV)
     uint8_t* out32;              // may be nullptr
     double* heights;             // may be nullptr
     int nmax, nrmax;             // largest BV count of the height / RGB GPs (table sizing)

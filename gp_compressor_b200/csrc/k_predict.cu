@@ -47,7 +47,9 @@ __device__ __forceinline__ void quat_to_rot(const double* q, double* R) {
 // One (patch, block of grid rows) per group of G threads: G = 32 (four independent warps per CTA, for small grids)
 // or G = PRED_T.  Each thread owns R consecutive rows of one grid column.
 // MINB: resident CTAs per SM the register budget is cut for (large-grid shape: 4 when the tables leave room for 4 CTAs, else 3)
-template <int R, int G, int MINB>
+// DIRECT: k_i = rbf_kernel::kernel_function(x*, BV_i) = p0 exp(cl (dx^2 + dy^2)) per (grid point, BV), the reference's
+// arithmetic (rbf_kernel.cpp:15-18); otherwise the separable tables (gpc_config.decode_separable).
+template <int R, int G, int MINB, bool DIRECT>
 __global__ void __launch_bounds__(PRED_T, MINB) predict_grid_kernel(PredictArgs a) {
     extern __shared__ double sm_all[];
     const int64_t gi = (int64_t)blockIdx.x * (PRED_T / G) + threadIdx.x / G;
@@ -108,6 +110,7 @@ __global__ void __launch_bounds__(PRED_T, MINB) predict_grid_kernel(PredictArgs 
     }
     if (G == 32) __syncwarp(); else __syncthreads();
     // separable kernel tables
+    if (!DIRECT) {
     for (int e = t; e < N * sz; e += G) {
         const int i = e / sz, c = e - i * sz;
         const double d = __dadd_rn(Xs[c], -sb1[i]);
@@ -129,6 +132,7 @@ __global__ void __launch_bounds__(PRED_T, MINB) predict_grid_kernel(PredictArgs 
         REy[e] = (c < rows_here) ? gpc_exp_nonpos(__dmul_rn(a.cl, __dmul_rn(d, d))) : 0.0;
     }
     if (G == 32) __syncwarp(); else __syncthreads();
+    }
     const unsigned int rgba = reinterpret_cast<const unsigned int*>(Rm + 15)[0];
     const int g2 = sz * sz;
     const int64_t base = a.slot[p] * g2 + (int64_t)row0 * sz;
@@ -139,6 +143,28 @@ __global__ void __launch_bounds__(PRED_T, MINB) predict_grid_kernel(PredictArgs 
         double acc[R][4];
 #pragma unroll
         for (int r = 0; r < R; r++) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0;
+        if (DIRECT) {
+            const double gx = Xs[xx];
+            double gy[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) gy[r] = Ys[min(yl0 + r, rowsP - 1)];
+            int i = 0;
+            for (; i + 3 < N; i += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const double w = al[i + u], bx = sb1[i + u], by = sb2[i + u];
+#pragma unroll
+                    for (int r = 0; r < R; r++) acc[r][u] = fma(w, rbf(gx, gy[r], bx, by, a.p0, a.cl), acc[r][u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 3; u++)
+                if (i + u < N) {
+                    const double w = al[i + u], bx = sb1[i + u], by = sb2[i + u];
+#pragma unroll
+                    for (int r = 0; r < R; r++) acc[r][u] = fma(w, rbf(gx, gy[r], bx, by, a.p0, a.cl), acc[r][u]);
+                }
+        } else {
         const double* ex = Ex + xx;
         const double* ey = Ey + yl0;
         int i = 0;
@@ -168,6 +194,7 @@ __global__ void __launch_bounds__(PRED_T, MINB) predict_grid_kernel(PredictArgs 
 #pragma unroll
                 for (int r = 0; r < R; r++) acc[r][u] = fma(w, __dmul_rn(e, ey[(i + u) * rowsP + r]), acc[r][u]);
             }
+        }
         const double X0 = Xs[xx];
 #pragma unroll
         for (int r = 0; r < R; r++) {
@@ -186,6 +213,26 @@ __global__ void __launch_bounds__(PRED_T, MINB) predict_grid_kernel(PredictArgs 
                 unsigned int col = rgba;
                 if (a.rgb_nbv) {  // c = C_star.row(m) + RGB_means[i], gp_compressor.cpp:367
                     double c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0};
+                    if (DIRECT) {
+                        int j = 0;
+                        for (; j + 3 < NR; j += 4) {
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const double k = rbf(X0, X1, rb1[j + u], rb2[j + u], a.p0, a.cl);
+                                c0[u] = fma(ra0[j + u], k, c0[u]);
+                                c1[u] = fma(ra1[j + u], k, c1[u]);
+                                c2[u] = fma(ra2[j + u], k, c2[u]);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 3; u++)
+                            if (j + u < NR) {
+                                const double k = rbf(X0, X1, rb1[j + u], rb2[j + u], a.p0, a.cl);
+                                c0[u] = fma(ra0[j + u], k, c0[u]);
+                                c1[u] = fma(ra1[j + u], k, c1[u]);
+                                c2[u] = fma(ra2[j + u], k, c2[u]);
+                            }
+                    } else {
                     const double* rex = REx + xx;
                     const double* rey = REy + yl0 + r;
                     int j = 0;
@@ -206,6 +253,7 @@ __global__ void __launch_bounds__(PRED_T, MINB) predict_grid_kernel(PredictArgs 
                             c1[u] = fma(ra1[j + u], k, c1[u]);
                             c2[u] = fma(ra2[j + u], k, c2[u]);
                         }
+                    }
                     const double fr = __dadd_rn(__dadd_rn(c0[0], c0[1]), __dadd_rn(c0[2], c0[3]));
                     const double fg = __dadd_rn(__dadd_rn(c1[0], c1[1]), __dadd_rn(c1[2], c1[3]));
                     const double fb = __dadd_rn(__dadd_rn(c2[0], c2[1]), __dadd_rn(c2[2], c2[3]));
@@ -237,12 +285,18 @@ __global__ void __launch_bounds__(128) predict_points_kernel(const double* __res
 
 template <int R, int G, int MINB>
 static cudaError_t launch_grid_variant(const PredictArgs& a, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(predict_grid_kernel<R, G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     const int per_cta = PRED_T / G;
     const int64_t grid = (a.n_groups + per_cta - 1) / per_cta;
     if (grid > 0x7fffffff) return cudaErrorInvalidConfiguration;
-    predict_grid_kernel<R, G, MINB><<<(unsigned)grid, PRED_T, smem, s>>>(a);
+    if (a.separable) {
+        cudaError_t e = cudaFuncSetAttribute(predict_grid_kernel<R, G, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        predict_grid_kernel<R, G, MINB, false><<<(unsigned)grid, PRED_T, smem, s>>>(a);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(predict_grid_kernel<R, G, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        predict_grid_kernel<R, G, MINB, true><<<(unsigned)grid, PRED_T, smem, s>>>(a);
+    }
     return cudaGetLastError();
 }
 

@@ -216,13 +216,14 @@ struct IntC { static constexpr int value = V; };
 // DOUT = 1: sparse_gp (heights).  DOUT = 3: sparse_gp_field (RGB): alpha has three columns, the capacity score is
 // |alpha_i|^2 / (Q_ii + C_ii) (sparse_gp_field.hpp:187) and delete_bv updates alpha with alphastar * ((q*+c*)(Qs+Cs)) (:250-253).
 //
-// Structure (sparse_gp.hpp:119-162 is the loop; the arithmetic and its order are those of every other bucket):
-//  * A sparse update (:155-163), 93 % of the points under the reference hyper-parameters, changes only alpha and C and reads
-//    Q.  During runs of sparse points lane r keeps row r of C AND of Q in registers: the two matvecs C k, Q k and the rank-1
-//    update of C touch no shared memory beyond the broadcast of k and s_hat (16 doubles each).  The step is compiled once per
-//    number of occupied 4-column groups (N <= 8, 12, 16) so that it has no per-group predicates, and runs converged for
-//    both halves of the warp (full-mask shuffles).
-//  * The rare paths (full update, deletions, hand-off) spill the rows to their homes in shared memory and work there.
+// Structure (sparse_gp.hpp:119-203 is the loop; the arithmetic and its order are those of every other bucket):
+//  * Lane r keeps row r of C AND of Q in registers.  A sparse update (:155-163, 93 % of the points under the reference
+//    hyper-parameters) and a full update (:164-203) touch no shared memory beyond the broadcast of k, s and e_hat (16 doubles
+//    each): the rank-1 updates run over the zero-padded width, so the new row / column of a full update needs no indexing.
+//    The step is compiled once per number of occupied 4-column groups (N <= 8, 12, 16) so that it has no per-group
+//    predicates, and runs converged for both halves of the warp (full-mask shuffles).
+//  * Deletions and the hand-off to the next bucket (rare under the reference hyper-parameters) spill the rows to their
+//    homes in shared memory, work there, and reload.
 //  * k of the next point is computed while this point's chain runs (it depends only on the BV set).
 //  * The point stream is staged 16 points at a time by bulk-async copies (TMA unit) into a double buffer, one tile ahead.
 template <int DOUT>
@@ -264,20 +265,36 @@ __global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
 #pragma unroll
     for (int c = 0; c < DOUT; c++) alpha[c] = 0.0;
     int bidx = -1;
-    int N = 0;
+    int N = 0, Nw = 1;
     unsigned int run = 0;          // sparse points at the current N, folded into the counters when N changes
     unsigned long long cnt = 0;    // lane r < NCNT owns event counter r
-    double creg[16], qreg[16];     // rows r of C and Q while inreg
+    double creg[16], qreg[16];     // rows r of C and Q
+    double qd = 0.0;               // Q(r, r)
 #pragma unroll
     for (int j = 0; j < 16; j++) { creg[j] = 0.0; qreg[j] = 0.0; }
-    bool inreg = true, done = (n == 0), have_next = false;
+    int nl = n;                    // points of this half still to be processed here: 0 after a hand-off
+    bool have_next = false;
     double kl_next = 0.0;
     double* const Crow = C + r * W_LD;
     double* const Qrow = Q + r * W_LD;
+    const HalfTile<DOUT>* tlp = &sm.tile[0];
+
+    auto spill_rows = [&]() {
+#pragma unroll
+        for (int p = 0; p < 8; p++) {
+            *reinterpret_cast<double2*>(Crow + 2 * p) = make_double2(creg[2 * p], creg[2 * p + 1]);
+            *reinterpret_cast<double2*>(Qrow + 2 * p) = make_double2(qreg[2 * p], qreg[2 * p + 1]);
+        }
+    };
+    auto flush_run = [&]() {
+        const unsigned long long n2 = (unsigned long long)N * N;
+        cnt += (r == 1) ? (unsigned long long)run : (r == 5) ? (unsigned long long)run * N : (r == 6 || r == 7) ? run * n2 : 0ull;
+        run = 0;
+    };
 
     for (int tt = 0; tt < nmax; ++tt) {
         const int s = tt & 15;
-        const bool live = !done && tt < n;
+        const bool live = tt < nl;
         if (s == 0) {
             __syncwarp();  // every lane is done with the buffer the next tile will land in
             if (__all_sync(FULL, !live)) break;
@@ -289,9 +306,11 @@ __global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
                 }
                 mbar_wait(&sm.mbar[kt & 1], (uint32_t)((kt >> 1) & 1));
                 waited++;
+                tlp = &sm.tile[kt & 1];
+                have_next = false;
             }
         }
-        const HalfTile<DOUT>& tl = sm.tile[(tt >> 4) & 1];
+        const HalfTile<DOUT>& tl = *tlp;
         if (tt == 0) {  // sparse_gp.hpp:100-110 (both halves: a half has n == 0 or starts here)
             if (live) {
                 if (r == 0) {
@@ -300,6 +319,7 @@ __global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
                     for (int c = 0; c < DOUT; c++) alpha[c] = __ddiv_rn(tl.y[c][sh1], d);
                     creg[0] = __ddiv_rn(-1.0, d);
                     qreg[0] = __ddiv_rn(1.0, kstar);
+                    qd = qreg[0];
                     b1 = tl.x1[sh1]; b2 = tl.x2[sh1]; bidx = tl.orig[sh3];
                     cnt++;
                 }
@@ -307,16 +327,6 @@ __global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
             }
             continue;
         }
-        if (live && !inreg) {  // back from a full update: rows into registers
-#pragma unroll
-            for (int p = 0; p < 8; p++) {
-                const double2 c2 = *reinterpret_cast<const double2*>(Crow + 2 * p), q2 = *reinterpret_cast<const double2*>(Qrow + 2 * p);
-                creg[2 * p] = c2.x; creg[2 * p + 1] = c2.y;
-                qreg[2 * p] = q2.x; qreg[2 * p + 1] = q2.y;
-            }
-            inreg = true;
-        }
-        const int Nw = max(N, __shfl_xor_sync(FULL, N, 16));
         const bool act = r < N;
         // k = K(x, BV) (:119); lanes >= N hold zeros.  Usually computed during the previous point's chain.
         double kl = kl_next;
@@ -324,8 +334,7 @@ __global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
         kl = act ? kl : 0.0;
         sm.kv[r] = kl;
         __syncwarp();
-        have_next = live && s != 15 && tt + 1 < n;   // the next point is staged in the same tile
-        const double nx1 = tl.x1[s + 1 + sh1], nx2 = tl.x2[s + 1 + sh1];  // (a stale slot when !have_next: value ignored)
+        const double nx1 = tl.x1[s + 1 + sh1], nx2 = tl.x2[s + 1 + sh1];  // the next point of the tile (a stale slot at s == 15: value unused)
         double rv = 0.0, el = 0.0, q[DOUT], rr = 0.0, gamma = 0.0;
         bool sp = false;
         // one point of the recursion up to and including a sparse update, for NG occupied groups of four columns
@@ -410,187 +419,209 @@ __global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
         if (Nw <= 8) step(IntC<2>());
         else if (Nw <= 12) step(IntC<3>());
         else step(IntC<4>());
-        if (!live || sp) continue;  // Q and N unchanged: neither deletion loop can fire
-        // ---- full update (:164-203), this half only; the rows go back to shared memory ----
+        have_next = (s != 15);
+        const bool fu = live && !sp;
+        if (!__any_sync(FULL, fu)) continue;  // Q and N unchanged: neither deletion loop can fire
+        // ---- at least one half has a full update (:164-203) ----
+        bool fur = fu;
+        if (fu) {
+            flush_run();
+            if (N + 1 > ldmax) {  // does not fit this bucket: hand the state to the next one
+                spill_rows();
+                __syncwarp(gm);
+                int pos = 0;
+                if (r == 0) pos = atomicAdd(a.queue_count, 1);
+                pos = __shfl_sync(gm, pos, 0, 16);
+                double* slot = a.handoff_out + (size_t)pos * slot_doubles(W_N, DOUT);
+                if (r == 0) {
+                    a.queue[pos] = (int32_t)patch;
+                    reinterpret_cast<int*>(slot)[0] = N;
+                    reinterpret_cast<int*>(slot)[1] = tt;
+                }
+                if (r < NCNT) reinterpret_cast<unsigned long long*>(slot + 2)[r] = cnt;
+                double* v = slot + 2 + NCNT;
 #pragma unroll
-        for (int p = 0; p < 8; p++) {
-            *reinterpret_cast<double2*>(Crow + 2 * p) = make_double2(creg[2 * p], creg[2 * p + 1]);
-            *reinterpret_cast<double2*>(Qrow + 2 * p) = make_double2(qreg[2 * p], qreg[2 * p + 1]);
-        }
-        inreg = false;
-        have_next = false;  // the BV set changes
-        const double x1 = tl.x1[s + sh1], x2 = tl.x2[s + sh1];
-        const int orig = tl.orig[s + sh3];
-        {
-            const unsigned long long n2 = (unsigned long long)N * N;
-            cnt += (r == 1) ? (unsigned long long)run : (r == 5) ? (unsigned long long)run * N : (r == 6 || r == 7) ? run * n2 : 0ull;
-        }
-        run = 0;
-        __syncwarp(gm);
-        if (N + 1 > ldmax) {  // does not fit this bucket: hand the state to the next one
-            int pos = 0;
-            if (r == 0) pos = atomicAdd(a.queue_count, 1);
-            pos = __shfl_sync(gm, pos, 0, 16);
-            double* slot = a.handoff_out + (size_t)pos * slot_doubles(W_N, DOUT);
-            if (r == 0) {
-                a.queue[pos] = (int32_t)patch;
-                reinterpret_cast<int*>(slot)[0] = N;
-                reinterpret_cast<int*>(slot)[1] = tt;
+                for (int c = 0; c < DOUT; c++) v[c * W_N + r] = alpha[c];
+                v[DOUT * W_N + r] = b1; v[(DOUT + 1) * W_N + r] = b2;
+                reinterpret_cast<int*>(v + (DOUT + 2) * W_N + 2 * W_N * W_N)[r] = bidx;
+                for (int e = r; e < W_N * W_N; e += 16) {
+                    const int j = e / W_N, i = e - j * W_N;
+                    v[(DOUT + 2) * W_N + e] = C[i * W_LD + j];
+                    v[(DOUT + 2) * W_N + W_N * W_N + e] = Q[i * W_LD + j];
+                }
+                nl = 0;
+                fur = false;
             }
-            if (r < NCNT) reinterpret_cast<unsigned long long*>(slot + 2)[r] = cnt;
-            double* v = slot + 2 + NCNT;
+        }
+        double si = 0.0, ei = 0.0;
+        if (fur) {
+            cnt += (r == 2) ? 1ull : (r == 5) ? (unsigned long long)N : (r == 6) ? (unsigned long long)N * N
+                            : (r == 8) ? (unsigned long long)(N + 1) * (N + 1) : 0ull;
+            si = act ? rv : (r == N ? 1.0 : 0.0);    // s = [C k; 1], e_hat' = [Q k; -1]; zeros beyond N
+            ei = act ? el : (r == N ? -1.0 : 0.0);
+            sm.sv[r] = si;
+            sm.ev[r] = ei;
+            if (act) {
 #pragma unroll
-            for (int c = 0; c < DOUT; c++) v[c * W_N + r] = alpha[c];
-            v[DOUT * W_N + r] = b1; v[(DOUT + 1) * W_N + r] = b2;
-            reinterpret_cast<int*>(v + (DOUT + 2) * W_N + 2 * W_N * W_N)[r] = bidx;
-            for (int e = r; e < W_N * W_N; e += 16) {
-                const int j = e / W_N, i = e - j * W_N;
-                v[(DOUT + 2) * W_N + e] = C[i * W_LD + j];
-                v[(DOUT + 2) * W_N + W_N * W_N + e] = Q[i * W_LD + j];
+                for (int c = 0; c < DOUT; c++) alpha[c] = __dadd_rn(alpha[c], __dmul_rn(q[c], rv));
             }
-            done = true;
-            continue;
-        }
-        cnt += (r == 2) ? 1ull : (r == 5) ? (unsigned long long)N : (r == 6) ? (unsigned long long)N * N
-                        : (r == 8) ? (unsigned long long)(N + 1) * (N + 1) : 0ull;
-        if (act) {
-            sm.sv[r] = rv;
-            sm.ev[r] = el;
+            if (r == N) {
 #pragma unroll
-            for (int c = 0; c < DOUT; c++) alpha[c] = __dadd_rn(alpha[c], __dmul_rn(q[c], rv));
+                for (int c = 0; c < DOUT; c++) alpha[c] = __dadd_rn(0.0, __dmul_rn(q[c], 1.0));
+                b1 = tl.x1[s + sh1]; b2 = tl.x2[s + sh1]; bidx = tl.orig[s + sh3];
+            }
         }
-        if (r == N) {
-            sm.sv[N] = 1.0;
-            sm.ev[N] = -1.0;
-#pragma unroll
-            for (int c = 0; c < DOUT; c++) alpha[c] = __dadd_rn(0.0, __dmul_rn(q[c], 1.0));
-            b1 = x1; b2 = x2; bidx = orig;
-        }
-        __syncwarp(gm);
-        {
+        __syncwarp();
+        if (fur) {
             const double ig = __ddiv_rn(1.0, gamma);
             const int N1 = N + 1;
             if (r < N1) {
-                const double si = sm.sv[r], ei = sm.ev[r];
-                for (int j = 0; j < N1; j += 2) {  // column pairs; the pad column (j + 1 == N1) stays zero
-                    double2 c = *reinterpret_cast<double2*>(Crow + j), qq = *reinterpret_cast<double2*>(Qrow + j);
-                    const double2 s2v = *reinterpret_cast<const double2*>(sm.sv + j), e2v = *reinterpret_cast<const double2*>(sm.ev + j);
-                    c.x = fma(rr, __dmul_rn(si, s2v.x), c.x);
-                    qq.x = fma(ig, __dmul_rn(ei, e2v.x), qq.x);
-                    if (j + 1 < N1) {
-                        c.y = fma(rr, __dmul_rn(si, s2v.y), c.y);
-                        qq.y = fma(ig, __dmul_rn(ei, e2v.y), qq.y);
+                auto finite = [](double v) { return (__double2hiint(v) & 0x7ff00000) != 0x7ff00000; };
+                // finite factors: the columns beyond N1 get +0 (see the sparse update); otherwise guarded one by one
+                if (finite(rr) && finite(ig) && finite(si) && finite(ei)) {
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        if (4 * g < N1) {
+                            const double2 s01 = *reinterpret_cast<const double2*>(sm.sv + 4 * g), s23 = *reinterpret_cast<const double2*>(sm.sv + 4 * g + 2);
+                            const double2 e01 = *reinterpret_cast<const double2*>(sm.ev + 4 * g), e23 = *reinterpret_cast<const double2*>(sm.ev + 4 * g + 2);
+                            creg[4 * g] = fma(rr, __dmul_rn(si, s01.x), creg[4 * g]);
+                            creg[4 * g + 1] = fma(rr, __dmul_rn(si, s01.y), creg[4 * g + 1]);
+                            creg[4 * g + 2] = fma(rr, __dmul_rn(si, s23.x), creg[4 * g + 2]);
+                            creg[4 * g + 3] = fma(rr, __dmul_rn(si, s23.y), creg[4 * g + 3]);
+                            qreg[4 * g] = fma(ig, __dmul_rn(ei, e01.x), qreg[4 * g]);
+                            qreg[4 * g + 1] = fma(ig, __dmul_rn(ei, e01.y), qreg[4 * g + 1]);
+                            qreg[4 * g + 2] = fma(ig, __dmul_rn(ei, e23.x), qreg[4 * g + 2]);
+                            qreg[4 * g + 3] = fma(ig, __dmul_rn(ei, e23.y), qreg[4 * g + 3]);
+                        }
                     }
-                    *reinterpret_cast<double2*>(Crow + j) = c;
-                    *reinterpret_cast<double2*>(Qrow + j) = qq;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        if (j < N1) {
+                            creg[j] = fma(rr, __dmul_rn(si, sm.sv[j]), creg[j]);
+                            qreg[j] = fma(ig, __dmul_rn(ei, sm.ev[j]), qreg[j]);
+                        }
+                    }
                 }
+                qd = fma(ig, __dmul_rn(ei, ei), qd);  // the same operations as column r of the row above
             }
             N = N1;
-        }
-        __syncwarp(gm);
-        // capacity deletions (:206-223) then geometric deletions (:226-242)
-        double minscore = 0.0;
-        for (int phase = 0; phase < 2; phase++) {
-            for (;;) {
-                if (phase == 0 ? !(N > cap) : !(minscore < geo9() && N > 1)) break;
-                double sc = 0.0;
-                if (r < N) {
-                    const double qii = Q[r * W_LD + r];
-                    double num = __dmul_rn(alpha[0], alpha[0]);
-                    if (DOUT == 3) num = __dadd_rn(num, __dadd_rn(__dmul_rn(alpha[DOUT > 1 ? 1 : 0], alpha[DOUT > 1 ? 1 : 0]), __dmul_rn(alpha[DOUT > 2 ? 2 : 0], alpha[DOUT > 2 ? 2 : 0])));
-                    sc = (phase == 0) ? __ddiv_rn(num, __dadd_rn(qii, C[r * W_LD + r])) : __ddiv_rn(1.0, qii);
-                }
-                if (phase == 1) {
-                    // exact shortcut: the scan deletes iff score_0 is not NaN and some score is < 1e-9f
-                    const bool hit = __any_sync(gm, r < N && sc < geo9());
-                    const bool nan0 = __any_sync(gm, r == 0 && sc != sc);
-                    if (!hit || nan0) { minscore = geo9(); break; }
-                }
-                double best;
-                const int loc = half_first_min(gm, sc, r < N ? r : 0x7fffffff, &best);
-                if (phase == 1) minscore = best;
-                // ---- delete_bv(loc), :252-295 ----
-                const int L = N - 1, M = N - 1;
-                cnt += (r == 9) ? (unsigned long long)M * M : (r == (phase == 0 ? 3 : 4)) ? 1ull : 0ull;
-                double csi = 0, qsi = 0, repc = 0, repq = 0;
-                const int src = (r == loc) ? L : r;
-                if (r < N) {
-                    csi = C[loc * W_LD + src]; qsi = Q[loc * W_LD + src];
-                    repc = C[L * W_LD + src]; repq = Q[L * W_LD + src];
-                }
-                const double cstar = C[loc * W_LD + loc], qstar = Q[loc * W_LD + loc];
-                double astar[DOUT], aL[DOUT];
-#pragma unroll
-                for (int c = 0; c < DOUT; c++) { astar[c] = shfl16(gm, alpha[c], loc); aL[c] = shfl16(gm, alpha[c], L); }
-                const double b1L = shfl16(gm, b1, L), b2L = shfl16(gm, b2, L);
-                const int idL = __shfl_sync(gm, bidx, L, 16);
+            have_next = false;  // the BV set changed
+            // capacity deletions (:206-223) then geometric deletions (:226-242): decided here, done in shared memory
+            bool need_del = N > cap;
+            if (!need_del && N > 1) {
+                // exact shortcut: the geometric scan deletes iff score_0 is not NaN and some score 1 / Q_ii is < 1e-9f
+                const double sc = (r < N) ? __ddiv_rn(1.0, qd) : 0.0;
+                const bool hit = __any_sync(gm, r < N && sc < geo9());
+                const bool nan0 = __any_sync(gm, r == 0 && sc != sc);
+                need_del = hit && !nan0;
+            }
+            if (need_del) {
+                spill_rows();
                 __syncwarp(gm);
-                const double qcs = __dadd_rn(qstar, cstar);
-                const double coef = (DOUT == 1) ? __ddiv_rn(astar[0], qcs) : 0.0;
-                const double iq = __ddiv_rn(1.0, qstar), iqc = __ddiv_rn(1.0, qcs);
-                if (r < N) {
-                    if (r < M) {
-                        if (loc != L) {
-                            C[loc * W_LD + r] = repc; C[r * W_LD + loc] = repc;
-                            Q[loc * W_LD + r] = repq; Q[r * W_LD + loc] = repq;
-                            if (r == loc) { b1 = b1L; b2 = b2L; bidx = idL; }
+                double minscore = 0.0;
+                for (int phase = 0; phase < 2; phase++) {
+                    for (;;) {
+                        if (phase == 0 ? !(N > cap) : !(minscore < geo9() && N > 1)) break;
+                        double sc = 0.0;
+                        if (r < N) {
+                            const double qii = Q[r * W_LD + r];
+                            double num = __dmul_rn(alpha[0], alpha[0]);
+                            if (DOUT == 3) num = __dadd_rn(num, __dadd_rn(__dmul_rn(alpha[DOUT > 1 ? 1 : 0], alpha[DOUT > 1 ? 1 : 0]), __dmul_rn(alpha[DOUT > 2 ? 2 : 0], alpha[DOUT > 2 ? 2 : 0])));
+                            sc = (phase == 0) ? __ddiv_rn(num, __dadd_rn(qii, C[r * W_LD + r])) : __ddiv_rn(1.0, qii);
                         }
-                        const double qci = __dadd_rn(qsi, csi);
-#pragma unroll
-                        for (int c = 0; c < DOUT; c++) {
-                            const double ai = (r == loc) ? aL[c] : alpha[c];
-                            alpha[c] = (DOUT == 1) ? __dadd_rn(ai, -__dmul_rn(coef, qci))
-                                                   : __dadd_rn(ai, -__dmul_rn(astar[c], __dmul_rn(qcs, qci)));
+                        if (phase == 1) {
+                            const bool hit = __any_sync(gm, r < N && sc < geo9());
+                            const bool nan0 = __any_sync(gm, r == 0 && sc != sc);
+                            if (!hit || nan0) { minscore = geo9(); break; }
                         }
-                        sm.sv[r] = qsi;   // Qstar
-                        sm.ev[r] = qci;   // Qstar + Cstar
-                    }
-                    C[L * W_LD + r] = 0.0; C[r * W_LD + L] = 0.0;
-                    Q[L * W_LD + r] = 0.0; Q[r * W_LD + L] = 0.0;
-                    if (r == L) {
+                        double best;
+                        const int loc = half_first_min(gm, sc, r < N ? r : 0x7fffffff, &best);
+                        if (phase == 1) minscore = best;
+                        // ---- delete_bv(loc), :252-295 ----
+                        const int L = N - 1, M = N - 1;
+                        cnt += (r == 9) ? (unsigned long long)M * M : (r == (phase == 0 ? 3 : 4)) ? 1ull : 0ull;
+                        double csi = 0, qsi = 0, repc = 0, repq = 0;
+                        const int src = (r == loc) ? L : r;
+                        if (r < N) {
+                            csi = C[loc * W_LD + src]; qsi = Q[loc * W_LD + src];
+                            repc = C[L * W_LD + src]; repq = Q[L * W_LD + src];
+                        }
+                        const double cstar = C[loc * W_LD + loc], qstar = Q[loc * W_LD + loc];
+                        double astar[DOUT], aL[DOUT];
 #pragma unroll
-                        for (int c = 0; c < DOUT; c++) alpha[c] = 0.0;
-                        b1 = 0.0; b2 = 0.0; bidx = -1;
+                        for (int c = 0; c < DOUT; c++) { astar[c] = shfl16(gm, alpha[c], loc); aL[c] = shfl16(gm, alpha[c], L); }
+                        const double b1L = shfl16(gm, b1, L), b2L = shfl16(gm, b2, L);
+                        const int idL = __shfl_sync(gm, bidx, L, 16);
+                        __syncwarp(gm);
+                        const double qcs = __dadd_rn(qstar, cstar);
+                        const double coef = (DOUT == 1) ? __ddiv_rn(astar[0], qcs) : 0.0;
+                        const double iq = __ddiv_rn(1.0, qstar), iqc = __ddiv_rn(1.0, qcs);
+                        if (r < N) {
+                            if (r < M) {
+                                if (loc != L) {
+                                    C[loc * W_LD + r] = repc; C[r * W_LD + loc] = repc;
+                                    Q[loc * W_LD + r] = repq; Q[r * W_LD + loc] = repq;
+                                    if (r == loc) { b1 = b1L; b2 = b2L; bidx = idL; }
+                                }
+                                const double qci = __dadd_rn(qsi, csi);
+#pragma unroll
+                                for (int c = 0; c < DOUT; c++) {
+                                    const double ai = (r == loc) ? aL[c] : alpha[c];
+                                    alpha[c] = (DOUT == 1) ? __dadd_rn(ai, -__dmul_rn(coef, qci))
+                                                           : __dadd_rn(ai, -__dmul_rn(astar[c], __dmul_rn(qcs, qci)));
+                                }
+                                sm.sv[r] = qsi;   // Qstar
+                                sm.ev[r] = qci;   // Qstar + Cstar
+                            }
+                            C[L * W_LD + r] = 0.0; C[r * W_LD + L] = 0.0;
+                            Q[L * W_LD + r] = 0.0; Q[r * W_LD + L] = 0.0;
+                            if (r == L) {
+#pragma unroll
+                                for (int c = 0; c < DOUT; c++) alpha[c] = 0.0;
+                                b1 = 0.0; b2 = 0.0; bidx = -1;
+                            }
+                        }
+                        __syncwarp(gm);
+                        if (r < M) {
+                            const double qi = sm.sv[r], ci = sm.ev[r];
+                            for (int j = 0; j < M; j += 2) {  // column pairs; the pad column (j + 1 == M) stays zero
+                                double2 c = *reinterpret_cast<double2*>(Crow + j), qq = *reinterpret_cast<double2*>(Qrow + j);
+                                const double2 s2v = *reinterpret_cast<const double2*>(sm.sv + j), e2v = *reinterpret_cast<const double2*>(sm.ev + j);
+                                const double u0 = __dmul_rn(qi, s2v.x), v0 = __dmul_rn(ci, e2v.x);
+                                c.x = __dadd_rn(c.x, fma(u0, iq, -__dmul_rn(v0, iqc)));
+                                qq.x = fma(-u0, iq, qq.x);
+                                if (j + 1 < M) {
+                                    const double u1 = __dmul_rn(qi, s2v.y), v1 = __dmul_rn(ci, e2v.y);
+                                    c.y = __dadd_rn(c.y, fma(u1, iq, -__dmul_rn(v1, iqc)));
+                                    qq.y = fma(-u1, iq, qq.y);
+                                }
+                                *reinterpret_cast<double2*>(Crow + j) = c;
+                                *reinterpret_cast<double2*>(Qrow + j) = qq;
+                            }
+                        }
+                        N = M;
+                        __syncwarp(gm);
                     }
                 }
-                __syncwarp(gm);
-                if (r < M) {
-                    const double qi = sm.sv[r], ci = sm.ev[r];
-                    for (int j = 0; j < M; j += 2) {  // column pairs; the pad column (j + 1 == M) stays zero
-                        double2 c = *reinterpret_cast<double2*>(Crow + j), qq = *reinterpret_cast<double2*>(Qrow + j);
-                        const double2 s2v = *reinterpret_cast<const double2*>(sm.sv + j), e2v = *reinterpret_cast<const double2*>(sm.ev + j);
-                        const double u0 = __dmul_rn(qi, s2v.x), v0 = __dmul_rn(ci, e2v.x);
-                        c.x = __dadd_rn(c.x, fma(u0, iq, -__dmul_rn(v0, iqc)));
-                        qq.x = fma(-u0, iq, qq.x);
-                        if (j + 1 < M) {
-                            const double u1 = __dmul_rn(qi, s2v.y), v1 = __dmul_rn(ci, e2v.y);
-                            c.y = __dadd_rn(c.y, fma(u1, iq, -__dmul_rn(v1, iqc)));
-                            qq.y = fma(-u1, iq, qq.y);
-                        }
-                        *reinterpret_cast<double2*>(Crow + j) = c;
-                        *reinterpret_cast<double2*>(Qrow + j) = qq;
-                    }
+                // rows back into registers
+#pragma unroll
+                for (int p = 0; p < 8; p++) {
+                    const double2 c2 = *reinterpret_cast<const double2*>(Crow + 2 * p), q2 = *reinterpret_cast<const double2*>(Qrow + 2 * p);
+                    creg[2 * p] = c2.x; creg[2 * p + 1] = c2.y;
+                    qreg[2 * p] = q2.x; qreg[2 * p + 1] = q2.y;
                 }
-                N = M;
-                __syncwarp(gm);
+                qd = Q[r * W_LD + r];
             }
         }
-        __syncwarp(gm);
+        __syncwarp();
+        Nw = max(N, __shfl_xor_sync(FULL, N, 16));
     }
     __syncwarp();
     if (issued > waited) mbar_wait(&sm.mbar[waited & 1], (uint32_t)((waited >> 1) & 1));  // never leave with a copy in flight
-    if (w >= a.n_work || n == 0 || done) return;
-    if (inreg) {
-#pragma unroll
-        for (int p = 0; p < 8; p++) {
-            *reinterpret_cast<double2*>(Crow + 2 * p) = make_double2(creg[2 * p], creg[2 * p + 1]);
-            *reinterpret_cast<double2*>(Qrow + 2 * p) = make_double2(qreg[2 * p], qreg[2 * p + 1]);
-        }
-    }
-    {
-        const unsigned long long n2 = (unsigned long long)N * N;
-        cnt += (r == 1) ? (unsigned long long)run : (r == 5) ? (unsigned long long)run * N : (r == 6 || r == 7) ? run * n2 : 0ull;
-    }
+    if (w >= a.n_work || n == 0 || nl == 0) return;
+    spill_rows();
+    flush_run();
     __syncwarp(gm);
     if (r == 0) {
         a.nbv[op] = N;

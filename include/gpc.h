@@ -58,6 +58,12 @@ typedef struct gpc_config {
     int32_t rgb;        /* 1: also fit / decode the RGB field GP, sparse_gp_field (gp_compressor.cpp:163,334)  */
     double rgb_s0;      /* sparse_gp_field(capacity, s0), sparse_gp_field.h:43 (1e2f)                        */
     double rgb_eps_tol; /* sparse_gp_field ctor literal, sparse_gp_field.hpp:16 (1e-4f)                      */
+    int32_t decode_separable; /* 0 (default): the grid decode evaluates rbf_kernel::kernel_function p0*exp(cl*(dx^2+dy^2)) per
+                                 (grid point, BV) as the reference does (rbf_kernel.cpp:15-18 from sparse_gp.hpp:320-327 on the
+                                 lattice of gp_compressor.cpp:320-328).  1: flagged fast mode -- the kernel separated on the
+                                 lattice, (p0*exp(cl*dx^2))*exp(cl*dy^2) from per-patch tables: N(sz+rows) exps instead of
+                                 N*sz^2, heights within a few ulp of the kernel value of the direct form               */
+    int32_t pad0;
 } gpc_config;
 
 typedef struct gpc_sizes {

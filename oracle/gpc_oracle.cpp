@@ -169,6 +169,8 @@ inline double row4(const double* row, const double* k, int n) {
 struct SogpParams {
     int capacity;
     double s20, eps_tol, p0, p1, cl;  // cl = -0.5f / p1
+    int ref_order = 0;  // 1: the height GP evaluates every expression in the order of the reference source over
+                        // oracle/eigen_shim (sequential sums, libm exp, per-element divisions): bit-equal to oracle/_ref
 };
 
 struct SogpStats {
@@ -279,8 +281,178 @@ struct Sogp {
         N = M;
     }
 
+    // ================= reference-order arithmetic (P.ref_order, D == 1) =================
+    // The same recursion, but every expression is evaluated exactly as the reference source does when it is compiled over
+    // oracle/eigen_shim (the build behind oracle/_ref and tests/golden/ref_sogp.npz): Eigen products are plain sequential
+    // sums s += a*b without fma, exp is libm's, delete_bv divides element by element, r*s*s' is (r s_i) s_j.  C and Q
+    // are NOT symmetrised (k'C and C k are different sums).  The file:line of each statement is given.
+    inline double kern_ref(double x1, double x2, double y1, double y2) const {  // rbf_kernel.cpp:15-18
+        const double d1 = x1 - y1, d2 = x2 - y2;
+        double sq = 0.0;
+        sq += d1 * d1;
+        sq += d2 * d2;
+        return P.p0 * std::exp(P.cl * sq);
+    }
+    void delete_bv_ref(int loc) {  // sparse_gp.hpp:252-295
+        const int L = N - 1, M = N - 1;
+        st.sumN2_del += (double)M * M;
+        const double alphastar = al(0, loc);                     // :256-258
+        al(0, loc) = al(0, L);
+        const double cstar = c(loc, loc);                        // :261
+        for (int i = 0; i < N; i++) cs[i] = c(i, loc);           // :262 Cstar = C.col(loc)
+        cs[loc] = cs[L];                                         // :263
+        for (int i = 0; i < N; i++) sv[i] = c(i, L);             // :266 Crep = C.col(last)
+        sv[loc] = sv[L];                                         // :267
+        for (int j = 0; j < N; j++) c(loc, j) = sv[j];           // :268 C.row(loc) = Crep'
+        for (int i = 0; i < N; i++) c(i, loc) = sv[i];           // :269 C.col(loc) = Crep
+        const double qstar = q(loc, loc);                        // :273
+        for (int i = 0; i < N; i++) qs[i] = q(i, loc);           // :274
+        qs[loc] = qs[L];                                         // :275
+        for (int i = 0; i < N; i++) sv[i] = q(i, L);             // :277
+        sv[loc] = sv[L];                                         // :278
+        for (int j = 0; j < N; j++) q(loc, j) = sv[j];           // :279
+        for (int i = 0; i < N; i++) q(i, loc) = sv[i];           // :280
+        const double qcs = qstar + cstar;
+        const double coef = alphastar / qcs;                     // :285 alphastar/(qstar + cstar)*(Qstar + Cstar)
+        for (int i = 0; i < M; i++) qc[i] = qs[i] + cs[i];
+        for (int i = 0; i < M; i++) al(0, i) = al(0, i) - coef * qc[i];
+        for (int i = 0; i < M; i++)                              // :286-288
+            for (int j = 0; j < M; j++) {
+                const double A = (0.0 + qs[i] * qs[j]) / qstar;
+                const double B = (0.0 + qc[i] * qc[j]) / qcs;
+                c(i, j) = c(i, j) + (A - B);
+                q(i, j) = q(i, j) - A;
+            }
+        b1[loc] = b1[L]; b2[loc] = b2[L]; idx[loc] = idx[L];     // :291-292
+        for (int i = 0; i < N; i++) { c(L, i) = 0; c(i, L) = 0; q(L, i) = 0; q(i, L) = 0; }
+        al(0, L) = 0; b1[L] = 0; b2[L] = 0; idx[L] = -1;
+        N = M;
+    }
+    void add_ref(double x1, double x2, double y, int orig) {  // sparse_gp.hpp:89-249
+        st.n_add++;
+        const double kstar = P.p0 * std::exp(P.cl * 0.0);        // :98
+        if (N == 0) {                                            // :100-110
+            al(0, 0) = y / (kstar + P.s20);
+            c(0, 0) = -1.0 / (kstar + P.s20);
+            q(0, 0) = 1.0 / kstar;
+            b1[0] = x1; b2[0] = x2; idx[0] = orig;
+            N = 1;
+            st.n_first++;
+            if (std::isnan(c(0, 0))) flags |= 1;
+            return;
+        }
+        st.sumN += N;
+        st.sumN2_common += (double)N * N;
+        for (int i = 0; i < N; i++) k[i] = kern_ref(x1, x2, b1[i], b2[i]);   // :119
+        double m = 0.0;
+        for (int i = 0; i < N; i++) m += al(0, i) * k[i];                    // :121
+        double kCk = 0.0;                                                    // :122 (k'C) k
+        for (int j = 0; j < N; j++) {
+            double t = 0.0;
+            for (int i = 0; i < N; i++) t += k[i] * c(i, j);
+            sv[j] = t;
+        }
+        for (int j = 0; j < N; j++) kCk += sv[j] * k[j];
+        const double s2 = kstar + kCk;
+        const double r = -1.0 / (P.s20 + s2);                                // :134, gaussian_noise.cpp:15-18
+        const double qq = (y - m) / (P.s20 + s2);                            // :137, gaussian_noise.cpp:9-12
+        for (int i = 0; i < N; i++) {                                        // :140 e_hat = Q k
+            double t = 0.0;
+            for (int j = 0; j < N; j++) t += q(i, j) * k[j];
+            e[i] = t;
+        }
+        double ke = 0.0;
+        for (int i = 0; i < N; i++) ke += k[i] * e[i];
+        double gamma = kstar - ke;                                           // :144
+        if (gamma < TINY12) gamma = 0;                                       // :146-151
+        for (int i = 0; i < N; i++) {                                        // C k (:160 / :171)
+            double t = 0.0;
+            for (int j = 0; j < N; j++) t += c(i, j) * k[j];
+            ck[i] = t;
+        }
+        if (gamma < P.eps_tol && P.capacity != -1) {                         // :155-163
+            st.n_sparse++;
+            st.sumN2_sparse += (double)N * N;
+            const double eta = 1 / (1 + gamma * r);
+            for (int i = 0; i < N; i++) sv[i] = ck[i] + e[i];
+            const double qe = qq * eta;
+            for (int i = 0; i < N; i++) al(0, i) = al(0, i) + sv[i] * qe;
+            const double re = r * eta;
+            for (int i = 0; i < N; i++) {
+                const double t = re * sv[i];
+                for (int j = 0; j < N; j++) c(i, j) = c(i, j) + (0.0 + t * sv[j]);
+            }
+        } else {                                                             // :164-203
+            st.n_full++;
+            st.sumN2_full += (double)(N + 1) * (N + 1);
+            for (int i = 0; i < N; i++) sv[i] = ck[i];
+            sv[N] = 1.0;
+            al(0, N) = 0;
+            for (int i = 0; i <= N; i++) al(0, i) = al(0, i) + qq * sv[i];
+            for (int i = 0; i <= N; i++) {
+                const double t = r * sv[i];
+                for (int j = 0; j <= N; j++) c(i, j) = c(i, j) + (0.0 + t * sv[j]);
+            }
+            b1[N] = x1; b2[N] = x2; idx[N] = orig;
+            e[N] = -1.0;
+            const double ig = 1.0 / gamma;
+            for (int i = 0; i <= N; i++) {
+                const double t = ig * e[i];
+                for (int j = 0; j <= N; j++) q(i, j) = q(i, j) + (0.0 + t * e[j]);
+            }
+            N++;
+        }
+        while (N > P.capacity && P.capacity > 0) {                           // :206-223
+            double minscore = 0;
+            int minloc = -1;
+            for (int i = 0; i < N; i++) {
+                const double score = al(0, i) * al(0, i) / (q(i, i) + c(i, i));
+                if (i == 0 || score < minscore) { minscore = score; minloc = i; }
+            }
+            delete_bv_ref(minloc);
+            st.n_del_cap++;
+        }
+        double minscore = 0;                                                 // :226-242
+        int minloc = -1;
+        while (minscore < GEO9 && N > 1) {
+            for (int i = 0; i < N; i++) {
+                const double score = 1.0 / q(i, i);
+                if (i == 0 || score < minscore) { minscore = score; minloc = i; }
+            }
+            if (minscore < GEO9) {
+                delete_bv_ref(minloc);
+                st.n_del_geo++;
+            }
+        }
+        if (std::isnan(c(0, 0))) flags |= 1;
+    }
+    // sparse_gp.hpp:312-351: f* and sqrt(s20 + k** + k'Ck), reference order
+    double predict_ref(double x1, double x2, double* sigma) {
+        const double kstar = P.p0 * std::exp(P.cl * 0.0);
+        if (N == 0) {
+            if (sigma) *sigma = std::sqrt(kstar + P.s20);
+            return 0.0;
+        }
+        for (int i = 0; i < N; i++) k[i] = kern_ref(x1, x2, b1[i], b2[i]);
+        double f = 0.0;
+        for (int i = 0; i < N; i++) f += al(0, i) * k[i];
+        if (sigma) {
+            double kCk = 0.0;
+            for (int j = 0; j < N; j++) {
+                double t = 0.0;
+                for (int i = 0; i < N; i++) t += k[i] * c(i, j);
+                kCk += t * k[j];
+            }
+            double sg = P.s20 + kstar + kCk;
+            if (sg < 0) sg = 0;
+            *sigma = std::sqrt(sg);
+        }
+        return f;
+    }
+
     // sparse_gp.hpp:89-249 / sparse_gp_field.hpp:59-222 ; y has D entries
     void add(double x1, double x2, const double* y, int orig) {
+        if (P.ref_order && D == 1) { add_ref(x1, x2, y[0], orig); return; }
         st.n_add++;
         const double kstar = P.p0;  // kernel(X,X) = p0*exp(-0) exactly
         if (N == 0) {
@@ -370,6 +542,7 @@ struct Sogp {
 
     // sparse_gp.hpp:312-351 (mean only; the caller discards sigma, gp_compressor.cpp:333)
     double predict(double x1, double x2) {
+        if (P.ref_order && D == 1) return predict_ref(x1, x2, nullptr);
         if (N == 0) return 0.0;
         for (int i = 0; i < N; i++) k[i] = kern(x1, x2, b1[i], b2[i]);
         return row4(alpha.data(), k.data(), N);
@@ -765,6 +938,9 @@ struct Config {
     int rgb_rand = 1;    // account for the RGB field GP's shuffle in the rand stream
     int threads = 1;
     int rgb = 0;         // 1: also fit / decode the RGB field GP (sparse_gp_field, gp_compressor.cpp:163,334)
+    int ref_order = 0;   // 1: height GPs in the reference source's own evaluation order (SogpParams::ref_order)
+    int decode_separable = 0;  // 0: grid decode evaluates rbf_kernel::kernel_function per (grid point, BV) as the reference does
+                               // (sparse_gp.hpp:320-327); 1: the product's flagged fast mode, separable on the lattice
     double rgb_s0 = (double)1e2f;       // sparse_gp_field.h:43
     double rgb_eps_tol = (double)1e-4f; // sparse_gp_field.hpp:16
 };
@@ -814,6 +990,7 @@ struct Oracle {
         p.p0 = cfg.sigmaf_sq;
         p.p1 = cfg.l_sq;
         p.cl = (double)(-0.5f) / cfg.l_sq;
+        p.ref_order = cfg.ref_order;
         return p;
     }
     SogpParams rgb_params() const {  // sparse_gp_field(capacity, s0 = 1e2f), eps_tol 1e-4f, same default kernel
@@ -1246,14 +1423,18 @@ struct Oracle {
                 int64_t base = slot[p] * g2;
                 int64_t m = 0;
                 for (int a = 0; a < sz; a++) Xg[a] = cfg.res * (((double)a + 0.5f) / (double)sz - 0.5f);
-                gp.grid_tables(Xg.data(), sz, Xg.data(), sz, Ex, Ey);
-                if (have_rgb) gc.grid_tables(Xg.data(), sz, Xg.data(), sz, REx, REy);
+                const bool sep = cfg.decode_separable != 0;
+                if (sep) {
+                    gp.grid_tables(Xg.data(), sz, Xg.data(), sz, Ex, Ey);
+                    if (have_rgb) gc.grid_tables(Xg.data(), sz, Xg.data(), sz, REx, REy);
+                }
                 for (int yy = 0; yy < sz; yy++)
                     for (int xx = 0; xx < sz; xx++, m++) {
                         double X0 = Xg[xx];
                         double X1 = Xg[yy];
-                        gp.grid_k(Ex, sz, xx, Ey, sz, yy);
-                        double f = gp.predict_grid();
+                        double f;
+                        if (sep) { gp.grid_k(Ex, sz, xx, Ey, sz, yy); f = gp.predict_grid(); }
+                        else f = gp.predict(X0, X1);
                         if (with_sigma) acc += gp.predict_sigma(X0, X1);  // the work the reference discards
                         if (heights) heights[base + m] = f;
                         if (out32) {
@@ -1266,7 +1447,10 @@ struct Oracle {
                             uint8_t* cb = out32 + 32 * (base + m) + 16;
                             // c = C_star.row(m) + RGB_means[i] (gp_compressor.cpp:367); without the field GP: mean only
                             double cf[3] = {0, 0, 0};
-                            if (have_rgb) { gc.grid_k(REx, sz, xx, REy, sz, yy); gc.predict_field_grid(cf); }
+                            if (have_rgb) {
+                                if (sep) { gc.grid_k(REx, sz, xx, REy, sz, yy); gc.predict_field_grid(cf); }
+                                else gc.predict_field(X0, X1, cf);
+                            }
                             cb[2] = (uint8_t)flatten_color(cf[0] + cm[0]); cb[1] = (uint8_t)flatten_color(cf[1] + cm[1]);
                             cb[0] = (uint8_t)flatten_color(cf[2] + cm[2]); cb[3] = 255;
                             std::memset(out32 + 32 * (base + m) + 20, 0, 12);
@@ -1291,7 +1475,8 @@ extern "C" {
 struct orc_config {
     double res; int sz; int capacity; double s0; double eps_tol; double sigmaf_sq; double l_sq;
     int leaf_order; int shuffle; int rgb_rand; int threads;
-    int rgb; int pad; double rgb_s0; double rgb_eps_tol;
+    int rgb; int ref_order; double rgb_s0; double rgb_eps_tol;
+    int decode_separable; int pad2;
 };
 
 double orc_exp(double x) { return orc_exp_impl(x); }
@@ -1319,7 +1504,8 @@ void orc_config_default(orc_config* c) {
     c->res = d.res; c->sz = d.sz; c->capacity = d.capacity; c->s0 = d.s0; c->eps_tol = d.eps_tol;
     c->sigmaf_sq = d.sigmaf_sq; c->l_sq = d.l_sq; c->leaf_order = d.leaf_order; c->shuffle = d.shuffle;
     c->rgb_rand = d.rgb_rand; c->threads = d.threads;
-    c->rgb = d.rgb; c->pad = 0; c->rgb_s0 = d.rgb_s0; c->rgb_eps_tol = d.rgb_eps_tol;
+    c->rgb = d.rgb; c->ref_order = d.ref_order; c->rgb_s0 = d.rgb_s0; c->rgb_eps_tol = d.rgb_eps_tol;
+    c->decode_separable = d.decode_separable; c->pad2 = 0;
 }
 
 void* orc_create(const orc_config* c) {
@@ -1328,7 +1514,8 @@ void* orc_create(const orc_config* c) {
     o->cfg.eps_tol = c->eps_tol; o->cfg.sigmaf_sq = c->sigmaf_sq; o->cfg.l_sq = c->l_sq;
     o->cfg.leaf_order = c->leaf_order; o->cfg.shuffle = c->shuffle; o->cfg.rgb_rand = c->rgb_rand;
     o->cfg.threads = c->threads < 1 ? 1 : c->threads;
-    o->cfg.rgb = c->rgb; o->cfg.rgb_s0 = c->rgb_s0; o->cfg.rgb_eps_tol = c->rgb_eps_tol;
+    o->cfg.rgb = c->rgb; o->cfg.ref_order = c->ref_order; o->cfg.rgb_s0 = c->rgb_s0; o->cfg.rgb_eps_tol = c->rgb_eps_tol;
+    o->cfg.decode_separable = c->decode_separable;
     return o;
 }
 void orc_destroy(void* h) { delete (Oracle*)h; }
@@ -1459,6 +1646,10 @@ int orc_predict(void* h, int64_t patch, const double* X, int64_t m, double* f, d
         for (int i = 0; i < N; i++)
             for (int j = 0; j < N; j++) gp.c(i, j) = o->dumpC[o->dump_off[patch] + (size_t)i * N + j];
     for (int64_t t = 0; t < m; t++) {
+        if (gp.P.ref_order) {  // sparse_gp.hpp:312-351 as the reference evaluates it
+            f[t] = gp.predict_ref(X[2 * t], X[2 * t + 1], sigma ? sigma + t : nullptr);
+            continue;
+        }
         f[t] = gp.predict(X[2 * t], X[2 * t + 1]);
         if (sigma) sigma[t] = gp.predict_sigma(X[2 * t], X[2 * t + 1]);
     }

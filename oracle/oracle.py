@@ -17,7 +17,8 @@ class OrcConfig(C.Structure):
     _fields_ = [("res", C.c_double), ("sz", C.c_int), ("capacity", C.c_int), ("s0", C.c_double),
                 ("eps_tol", C.c_double), ("sigmaf_sq", C.c_double), ("l_sq", C.c_double),
                 ("leaf_order", C.c_int), ("shuffle", C.c_int), ("rgb_rand", C.c_int), ("threads", C.c_int),
-                ("rgb", C.c_int), ("pad", C.c_int), ("rgb_s0", C.c_double), ("rgb_eps_tol", C.c_double)]
+                ("rgb", C.c_int), ("ref_order", C.c_int), ("rgb_s0", C.c_double), ("rgb_eps_tol", C.c_double),
+                ("decode_separable", C.c_int), ("pad2", C.c_int)]
 
 
 class OrcSizes(C.Structure):
@@ -150,9 +151,12 @@ class Oracle:
 
     def __init__(self, res=float(np.float32(0.1)), sz=10, capacity=100, s0=float(np.float32(1e-1)),
                  eps_tol=float(np.float32(1e-6)), sigmaf_sq=100.0, l_sq=1.0, leaf_order=0, shuffle=1,
-                 rgb_rand=1, threads=1, rgb=0, rgb_s0=float(np.float32(1e2)), rgb_eps_tol=float(np.float32(1e-4))):
-        self.cfg = OrcConfig(res, sz, capacity, s0, eps_tol, sigmaf_sq, l_sq, leaf_order, shuffle, rgb_rand, threads, rgb, 0, rgb_s0,
-                             rgb_eps_tol)
+                 rgb_rand=1, threads=1, rgb=0, rgb_s0=float(np.float32(1e2)), rgb_eps_tol=float(np.float32(1e-4)),
+                 ref_order=0, decode_separable=0):
+        """ref_order=1: the height GPs run in the reference source's own evaluation order (bit-equal to oracle/_ref);
+        decode_separable=1: the grid decode follows the product's flagged separable mode instead of the direct kernel."""
+        self.cfg = OrcConfig(res, sz, capacity, s0, eps_tol, sigmaf_sq, l_sq, leaf_order, shuffle, rgb_rand, threads, rgb, ref_order,
+                             rgb_s0, rgb_eps_tol, decode_separable, 0)
         self.h = lib().orc_create(C.byref(self.cfg))
         self._np = 0
 

@@ -34,7 +34,8 @@ def test_defaults_are_the_reference_constructor_defaults(built):
     assert cfg.capacity == 100 and cfg.s0 == float(np.float32(1e-1))    # sparse_gp.h:48
     assert cfg.eps_tol == float(np.float32(1e-6))                       # sparse_gp.hpp:31
     assert cfg.sigmaf_sq == 100.0 and cfg.l_sq == 1.0                   # rbf_kernel.h:24
-    assert ctypes.sizeof(built.GpcConfig) == 96
+    assert ctypes.sizeof(built.GpcConfig) == 104
+    assert cfg.decode_separable == 0  # the reference's direct kernel evaluation is the default (rbf_kernel.cpp:15-18)
     assert cfg.rgb == 0 and cfg.rgb_s0 == float(np.float32(1e2)) and cfg.rgb_eps_tol == float(np.float32(1e-4))  # sparse_gp_field.h:43, .hpp:16
 
 

@@ -211,6 +211,50 @@ def test_wire_format_round_trip(G, oracle_mod, tmp_path):
         bad = tmp_path / "bad.gpc"
         bad.write_bytes(b"not a parameter file")
         G.Handle().load_file(bad)
+    # hostile / damaged files: every one is refused with an error (nothing thrown across the C ABI, nothing half-installed)
+    raw = bytearray(path.read_bytes())
+    hdr = 8 + 4 + 5 * 8          # magic, version, five doubles; then sz, capacity (int32), PL, T (int64)
+    def variant(name, edit):
+        b2 = bytearray(raw)
+        edit(b2)
+        q = tmp_path / name
+        q.write_bytes(bytes(b2))
+        return q
+    import struct
+    cases = {
+        "sz0.gpc": lambda d: d.__setitem__(slice(hdr, hdr + 4), struct.pack("<i", 0)),
+        "cap0.gpc": lambda d: d.__setitem__(slice(hdr + 4, hdr + 8), struct.pack("<i", 0)),
+        "cap_huge.gpc": lambda d: d.__setitem__(slice(hdr + 4, hdr + 8), struct.pack("<i", 1 << 30)),
+        "lsq_neg.gpc": lambda d: d.__setitem__(slice(8 + 4 + 32, 8 + 4 + 40), struct.pack("<d", -1.0)),
+        "pl_huge.gpc": lambda d: d.__setitem__(slice(hdr + 8, hdr + 16), struct.pack("<q", 1 << 60)),
+        "t_huge.gpc": lambda d: d.__setitem__(slice(hdr + 16, hdr + 24), struct.pack("<q", 1 << 59)),
+        "truncated.gpc": lambda d: d.__delitem__(slice(len(d) // 2, len(d))),
+    }
+    for name, edit in cases.items():
+        c = G.Handle(**cfg)
+        c.compress(cloud)
+        with pytest.raises(G.GpcError):
+            c.load_file(variant(name, edit))
+        assert c.cfg.sz == 12 and c.cfg.capacity == 40
+        assert eq(c.decompress(), want)   # a refused file leaves the handle's own fit and configuration untouched
+        c.load_file(path)
+        assert eq(c.decompress(), want)
+
+
+def test_heights_need_a_resident_decompress(G):
+    """gpc_get_heights returns the grid of the last gpc_decompress_resident; after gpc_decompress (which produces no
+    heights) it is a state error, not stale memory."""
+    cloud = synth.c2_indoor(20000, seed=4)
+    h = G.Handle(res=F32(0.1), sz=5, capacity=20)
+    h.compress(cloud)
+    n = h.decompress_resident()
+    hg = h.heights()
+    assert hg.size == n and np.isfinite(hg).all()
+    h.decompress()
+    with pytest.raises(G.GpcError):
+        h.heights()
+    h.decompress_resident()
+    assert eq(h.heights(), hg)
 
 
 def test_handle_reuse_across_different_clouds(G, oracle_mod):

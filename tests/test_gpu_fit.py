@@ -131,10 +131,13 @@ def test_duplicate_points_geometric_deletion(G, oracle_mod):
     check_fit(G, oracle_mod, off, x1, x2, y, capacity=12, sigmaf_sq=1.0, l_sq=1e-4, s0=1e-6, exact=False)
 
 
-@pytest.mark.parametrize("sz", [1, 10, 20])
-def test_decode_heights_and_cloud(G, oracle_mod, sz):
+@pytest.mark.parametrize("separable", [0, 1])
+@pytest.mark.parametrize("sz", [1, 10, 20, 40])
+def test_decode_heights_and_cloud(G, oracle_mod, sz, separable):
+    """separable = 0: rbf_kernel::kernel_function per (grid point, BV) as the reference (the default);
+    1: the flagged fast mode.  Both bit-equal to the oracle's restatement of the same mode."""
     off, x1, x2, y = make_patches(21, [0, 90, 200, 0, 31])
-    cfg = dict(capacity=20, sz=sz, **bind())
+    cfg = dict(capacity=20, sz=sz, decode_separable=separable, **bind())
     h = G.Handle(**cfg)
     h.fit_patches(off, x1, x2, y)
     o = oracle_mod.Oracle(**cfg)
@@ -151,10 +154,11 @@ def test_decode_heights_and_cloud(G, oracle_mod, sz):
     assert np.array_equal(h.predict(1, X), o.predict(1, X))
 
 
-def test_decode_only_with_frames(G, oracle_mod):
+@pytest.mark.parametrize("separable,sz", [(0, 16), (1, 16), (0, 64), (1, 64)])
+def test_decode_only_with_frames(G, oracle_mod, separable, sz):
     from gp_compressor_b200 import synth
-    prm = synth.c4_patch_params(n_patches=500, nbv=30, seed=4)
-    cfg = dict(capacity=30, sz=16, **REF)
+    prm = synth.c4_patch_params(n_patches=500 if sz == 16 else 40, nbv=30, seed=4)
+    cfg = dict(capacity=30, sz=sz, decode_separable=separable, **REF)
     h = G.Handle(**cfg)
     h.set_params(**prm)
     o = oracle_mod.Oracle(**cfg)

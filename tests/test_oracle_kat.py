@@ -164,7 +164,7 @@ def test_separable_grid_decode_matches_direct_kernel(oracle_mod):
     x1 = rng.uniform(-res / 2, res / 2, P * npts)
     x2 = rng.uniform(-res / 2, res / 2, P * npts)
     y = 0.02 * np.sin(40 * x1) * np.cos(30 * x2) + 1e-4 * rng.standard_normal(P * npts)
-    o = oracle_mod.Oracle(res=res, sz=sz, capacity=25, sigmaf_sq=p0, l_sq=l_sq, s0=s0)
+    o = oracle_mod.Oracle(res=res, sz=sz, capacity=25, sigmaf_sq=p0, l_sq=l_sq, s0=s0, decode_separable=1)  # the flagged fast mode
     o.fit_patches(off, x1, x2, y)
     r = o.fit_result()
     _, heights = o.decode(want_cloud=False)
@@ -196,6 +196,40 @@ def test_separable_grid_decode_matches_direct_kernel(oracle_mod):
     # and the point-wise predict (direct form) agrees with the grid decode to the same level
     f = o.predict(0, np.stack(np.meshgrid(grid, grid), -1).reshape(-1, 2))
     assert np.abs(f - heights[0].ravel()).max() <= 1e-12 * np.abs(r["alpha"][:r["nbv"][0]]).sum() * p0
+
+
+@pytest.mark.parametrize("separable", [0, 1])
+def test_grid_decode_modes_under_reference_hyperparameters(oracle_mod, separable):
+    """Both decode modes under the REFERENCE DEFAULTS (rbf 100 / 1, s0 1e-1f: sum|alpha| p0 >> |f|, the ill-conditioned
+    case the bench runs) against the reference expression evaluated in numpy with libm: f* = sum_i alpha_i p0
+    exp(cl ((X0-b1)^2 + (X1-b2)^2)) on the lattice of gp_compressor.cpp:320-328 (rbf_kernel.cpp:15-18, sparse_gp.hpp:320-327).
+    Contract of the path: 1e-9 relative to max|f| of the patch.  Direct mode (the default) meets it with orders of
+    magnitude to spare; the separable fast mode is measured with the same yardstick."""
+    rng = np.random.default_rng(23)
+    res, sz = float(np.float32(0.1)), 10
+    P, npts = 8, 400
+    off = np.arange(P + 1, dtype=np.int64) * npts
+    x1 = rng.uniform(-res / 2, res / 2, P * npts)
+    x2 = rng.uniform(-res / 2, res / 2, P * npts)
+    y = 0.02 * np.sin(40 * x1) * np.cos(30 * x2) + 0.3 * x1 + 0.003 * rng.standard_normal(P * npts)
+    o = oracle_mod.Oracle(res=res, sz=sz, capacity=30, decode_separable=separable)  # reference defaults
+    o.fit_patches(off, x1, x2, y)
+    r = o.fit_result()
+    _, heights = o.decode(want_cloud=False)
+    heights = heights.reshape(P, sz * sz)
+    grid = res * ((np.arange(sz, dtype=np.float64) + np.float32(0.5)) / sz - np.float32(0.5))
+    X0, X1 = (g.ravel() for g in np.meshgrid(grid, grid))
+    cl = float(np.float32(-0.5)) / 1.0
+    bo = np.concatenate([[0], np.cumsum(r["nbv"])])
+    worst = 0.0
+    for p in range(P):
+        sl = slice(bo[p], bo[p + 1])
+        b1, b2, al = r["bv1"][sl], r["bv2"][sl], r["alpha"][sl]
+        K = 100.0 * np.exp(cl * ((X0[:, None] - b1[None, :]) ** 2 + (X1[:, None] - b2[None, :]) ** 2))
+        want = np.array([math.fsum(K[m] * al) for m in range(sz * sz)])   # exactly rounded sum: the yardstick
+        worst = max(worst, float(np.abs(heights[p] - want).max() / np.abs(want).max()))
+        assert np.abs(al).sum() * 100.0 > 1e3 * np.abs(want).max()        # the cancellation this test is about
+    assert worst < 1e-9, worst
 
 
 @pytest.mark.parametrize("seed,res,order", [(1, 0.15, 0), (2, 0.1, 1), (3, 0.3, 0), (4, 0.07, 0)])
