@@ -138,3 +138,54 @@ def shuffle(n, rand_offset=0):
 
 def kernel(sigmaf_sq, l_sq, a, b):
     return lib().ref_kernel(sigmaf_sq, l_sq, a[0], a[1], b[0], b[1])
+
+
+# ---- gp_compressor::compute_rotation / project_points (gp_compressor.cpp:29-118) from the reference's own text ----
+SO_FRAMES = os.path.join(_HERE, "_ref", "libref_frames.so")
+_LIBF = None
+
+
+def frames_available():
+    if os.path.isdir("/root/reference/src"):
+        from . import ref_build
+        ref_build.build_frames()
+    return os.path.exists(SO_FRAMES)
+
+
+def _libf():
+    global _LIBF
+    if _LIBF is None:
+        L = C.CDLL(SO_FRAMES)
+        L.ref_compute_rotation.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_project_points.restype = C.c_int
+        L.ref_project_points.argtypes = [C.c_double, C.c_int, C.c_int] + [C.c_void_p] * 10
+        _LIBF = L
+    return _LIBF
+
+
+def compute_rotation(pts):
+    """pts: m x 3 doubles (the candidates of one leaf).  Returns R (3 x 3) as the reference computes it."""
+    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+    R = np.zeros(9)
+    _libf().ref_compute_rotation(pts.shape[0], _p(pts), _p(R))
+    return R.reshape(3, 3)
+
+
+def project_points(res, sz, pts, cols, index_search, occupied, R, center):
+    """One call of the reference's project_points.  occupied (int32 array over the cloud) is updated in place.
+    Returns dict(claimed = positions in the candidate list, local = n x 3 (height - mean, x1, x2), colour = n x 3 centred,
+    center = updated voxel centre, rgb_mean)."""
+    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+    cols = np.ascontiguousarray(cols, dtype=np.float64).reshape(-1, 3)
+    idx = np.ascontiguousarray(index_search, dtype=np.int32)
+    assert occupied.dtype == np.int32 and occupied.flags.c_contiguous
+    m = pts.shape[0]
+    Rr = np.ascontiguousarray(R, dtype=np.float64).reshape(9)
+    c3 = np.ascontiguousarray(center, dtype=np.float64).copy()
+    claimed = np.zeros(max(m, 1), dtype=np.int32)
+    local, colour, rgbm = np.zeros(3 * max(m, 1)), np.zeros(3 * max(m, 1)), np.zeros(3)
+    n = _libf().ref_project_points(float(res), int(sz), m, _p(pts), _p(cols), _p(idx), _p(occupied), _p(Rr), _p(c3), _p(claimed),
+                                   _p(local), _p(colour), _p(rgbm))
+    assert n >= 0
+    return dict(claimed=claimed[:n].copy(), local=local[:3 * n].reshape(n, 3).copy(), colour=colour[:3 * n].reshape(n, 3).copy(),
+                center=c3, rgb_mean=rgbm)

@@ -64,8 +64,11 @@ def rotation(pts4):
     return np.stack([n, c1, np.cross(n, c1)], axis=1)
 
 
-def project_cloud(xyz, res, leaf_order=0):
-    """xyz: n x 3 float32.  Returns lattice, leaves in visiting order and the greedy assignment."""
+def project_cloud(xyz, res, leaf_order=0, ref=None, rgb=None, sz=10):
+    """xyz: n x 3 float32.  Returns lattice, leaves in visiting order and the greedy assignment.
+    ref: oracle.ref_source -- when given, the frame of every leaf and its claim come from THE REFERENCE'S OWN
+    compute_rotation and project_points (gp_compressor.cpp:29-118 compiled by oracle/ref_build.py) instead of the numpy
+    restatement below; rgb: n x 3 colours (r, g, b) handed to project_points."""
     res = float(res)
     mn, depth = lattice(xyz, res)
     finite = np.isfinite(xyz).all(axis=1)
@@ -83,6 +86,9 @@ def project_cloud(xyz, res, leaf_order=0):
     radius = float(np.sqrt(F32(3.0)) / F32(2.0)) * res
     r2 = radius * radius
     occupied = np.zeros(xyz.shape[0], dtype=bool)
+    occ32 = np.zeros(xyz.shape[0], dtype=np.int32)
+    if rgb is None:
+        rgb = np.zeros((xyz.shape[0], 3))
     owner = np.full(xyz.shape[0], -1, dtype=np.int32)
     out = dict(lattice_min=mn, depth=depth, leaf_code=leaf_codes, ncand=[], R=[], stream=[], x1=[], x2=[], y=[], center=[])
     P = xyz[order]
@@ -96,8 +102,18 @@ def project_cloud(xyz, res, leaf_order=0):
         cand = order[d2.astype(np.float64) <= r2]
         out["ncand"].append(cand.size)
         pts = xyz[cand].astype(np.float64)
-        R = rotation(np.concatenate([pts, np.ones((cand.size, 1))], axis=1))
         mid = centre.astype(np.float64)
+        if ref is not None:
+            R = ref.compute_rotation(pts)                                            # gp_compressor.cpp:237
+            pr = ref.project_points(res, sz, pts, rgb[cand], cand.astype(np.int32), occ32, R, mid)   # :239
+            cl = cand[pr["claimed"]]
+            owner[cl] = i
+            out["R"].append(R); out["stream"].append(cl.astype(np.int64))
+            out["x1"].append(pr["local"][:, 1]); out["x2"].append(pr["local"][:, 2]); out["y"].append(pr["local"][:, 0])
+            out["center"].append(pr["center"] if cl.size else mid)
+            out.setdefault("colour", []).append(pr["colour"]); out.setdefault("rgb_mean", []).append(pr["rgb_mean"])
+            continue
+        R = rotation(np.concatenate([pts, np.ones((cand.size, 1))], axis=1))
         claimed, h, a1, a2 = [], [], [], []
         for m, j in enumerate(cand):                                                 # project_points, :78-100
             if occupied[j]:
