@@ -64,6 +64,74 @@ def _workload(name, points, seed_shift=0):
     raise SystemExit("unknown workload " + name)
 
 
+def config_dict(desc, n):
+    """The `config` object of the JSON line: identical in both arms (--impl ours / reference) for the same workload."""
+    return {"workload": desc, "per_gpu_points": int(n),
+            "l2": "inputs larger than L2 (%.0f MB cloud + sort buffers per step)" % (n * 32 / 1e6),
+            "parallelism": "one cloud per GPU, patches independent, no collective"}
+
+
+def strong_block(args, G, torch, dist, rank, world, local):
+    """Strong scaling of ONE cloud (north star: C5, 50 M points, capacity 100) over the N GPUs of the run, through
+    gpc_compress_shard_begin / _finish: every rank holds the whole cloud, bins its key range plus halo, ONE all-gather of two
+    integers per rank places its patches and its window of the rand() stream, then it fits / decodes the patches it owns
+    (gp_compressor.cpp:132-172, 204-243 are the loops being sharded).  Wall clock around begin + all-gather + finish
+    bracketed by barriers, max over ranks; the cloud is resident (uploaded before the timed region)."""
+    cloud, cfg, desc = _workload("c5", args.strong_points)      # same seed on every rank: the same cloud
+    n = cloud.shape[0]
+    h = G.Handle(device=local, shard_rank=rank, shard_count=world, **cfg)
+    h.upload_cloud(cloud)
+    counts = torch.zeros(2, dtype=torch.int64, device="cuda")
+    allc = torch.zeros(2 * world, dtype=torch.int64, device="cuda")
+    walls, gath, dev, dec, fit, decw = [], [], [], [], [], []
+    reps = 4
+    for it in range(reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        p, d = h.compress_shard_begin()
+        sb = h.stats()
+        g0 = time.perf_counter()
+        counts[0] = p; counts[1] = d
+        if world > 1:
+            dist.all_gather_into_tensor(allc, counts)
+            a = allc.cpu().numpy().reshape(world, 2)
+        else:
+            a = np.array([[p, d]], dtype=np.int64)
+        tg = time.perf_counter() - g0
+        h.compress_shard_finish(*G.binding.shard_prefix(a, rank))
+        st = h.stats()
+        torch.cuda.synchronize()
+        w1 = time.perf_counter()
+        nd = h.decompress_resident()
+        sd = h.stats()
+        torch.cuda.synchronize()
+        w2 = time.perf_counter()
+        if it >= 1:
+            walls.append(1e3 * (w1 - w0)); gath.append(1e3 * tg); dev.append(st["ms_total"]); dec.append(sd["ms_predict"])
+            fit.append(st["ms_fit"]); decw.append(1e3 * (w2 - w1))
+    sz = h.sizes()
+    own_pts = float(st["n_add"])   # points of the patches this rank owns (fed to its SOGP kernels)
+    mx = torch.tensor([float(np.mean(walls)), float(np.mean(gath)), float(np.mean(dev)), float(np.mean(dec)), float(np.mean(fit)),
+                       float(sz.n_claimed), own_pts, float(np.mean(decw))], dtype=torch.float64, device="cuda")
+    sm = torch.tensor([float(np.mean(fit)), float(sz.n_claimed), own_pts, float(nd), float(sz.patch_hi - sz.patch_lo)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    h.close()
+    wm, gm, dm, pm, fm, cl, op_, dw = mx.tolist()
+    fs, cs, os_, nds, ps = sm.tolist()
+    return {"workload": desc, "points": int(n), "n_gpus": world, "scaling": "strong",
+            "mode": "binning sharded by key range + halo, one all-gather of 2 integers, patches fitted where they are owned",
+            "compress_wall_ms": wm, "value": n / (wm * 1e-3), "unit": "pts/s", "allgather_wall_ms": gm,
+            "max_rank_device_ms": dm, "max_rank_fit_ms": fm, "mean_rank_fit_ms": fs / world,
+            "max_rank_binned_points": cl, "mean_rank_binned_points": cs / world,
+            "max_rank_owned_points": op_, "mean_rank_owned_points": os_ / world,
+            "decompress_wall_ms": dw, "max_rank_predict_ms": pm, "decompress_value": nds / (dw * 1e-3), "patches": int(ps),
+            "timed_reps": reps - 1}
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons during the timed region."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -166,7 +234,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "compress pts/s", "value": v, "unit": "pts/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * (sec + float(np.sum(td))) / len(tc), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "sample": "whole cloud per step", "l2": "n/a (CPU)"},
+            "config": config_dict(desc, n),
             "decompress": {"value": nd * len(td) / float(np.sum(td)), "unit": "grid pts/s"},
             "cpu_baseline": {"value": v, "unit": "pts/s", "cores": cores, "kind": "port", "sample": "%d pts (whole workload) per step" % n},
             "e2e": {"value": v, "unit": "pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -184,6 +252,8 @@ def main():
     ap.add_argument("--points", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rgb", action="store_true", help="also fit / decode the RGB field GP (next-row N1), in both arms")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling block (C5, one cloud sharded over the N GPUs)")
+    ap.add_argument("--strong-points", type=int, default=0, help="points of the strong-scaling cloud (default: C5's 50 M)")
     args = ap.parse_args()
     global RGB
     RGB = args.rgb
@@ -338,6 +408,16 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_cs, e2e_ds = te.tolist()
 
+    # ---- strong scaling of one cloud over the N GPUs (reported beside the weak headline, never instead of it) ----
+    strong = None
+    if not args.no_strong:
+        try:
+            h_keep = h  # the headline handle stays alive for the RMSE / roofline legs below
+            strong = strong_block(args, G, torch, dist, rank, world, local)
+        except Exception as e:  # reported, never fatal for the headline
+            strong = {"error": repr(e)}
+        barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -380,14 +460,14 @@ def main():
                 "traffic": None, "peak_source": "measured here: independent DFMA chains %.1f TFLOP/s, conflict-free LDS.128 %.1f TB/s (gpc_debug_peak)" % (fp64_peak / 1e12, smem_peak / 1e12), "stage_ms": stage_ms[dom],
                 "fp64_frac": f1, "smem_frac": f2, "mean_n": fit_stats["sum_n"] / max(1, fit_stats["n_add"] - fit_stats["n_first"])}
         if args.workload == "c2" and not args.points and not RGB:
-            # one `ncu --set full` capture of the same command (profiles/r1k_sogp_half_and_fused.md): bucket-0 kernel, per launch
-            roof["traffic"] = 156.9e6
-            roof["ncu"] = {"sm__pipe_fp64_cycles_active_pct": 36.6, "smsp__issue_active_pct": 61.1, "warps_per_sm": 18.2,
-                           "warp_instructions_per_point": 227, "source": "profiles/r1k_sogp_half_and_fused.md (captured once, not live)"}
-            roof["note"] = ("achieved / frac are ALGORITHMIC bytes and flops over the live stage time.  N ~ 10 under the reference "
-                            "hyper-parameters: the bucket-0 kernel (two patches per warp) is bound by dependent-instruction latency at "
-                            "18 warps/SM (ncu: FP64 pipe 37 % busy, issue slots 61 %), so neither roofline is the constraint; with "
-                            "capacity binding the SOGP kernels reach 0.16-0.26 of the LDS.128 roofline (profiles/r1_sweeps.md)")
+            # NOT live: one `ncu --set full` capture of this same command, kept under profiles/ with its grid and duration so
+            # that it can be told apart from the live numbers above (traffic = dram bytes read + written by the bucket-0 launches)
+            cap_path = os.path.join(ROOT, "profiles", "r2_k7_capture.json")
+            if os.path.exists(cap_path):
+                roof["captured_once"] = json.load(open(cap_path))
+                roof["traffic"] = roof["captured_once"].get("dram_bytes_per_step")
+            roof["note"] = ("achieved / frac are ALGORITHMIC bytes and flops (event counters of the run) over the live stage time; "
+                            "traffic and captured_once come from one ncu capture of the same command, not from this run")
     elif dom == "ms_predict":
         npatch = max(1, n_dec / (cfg["sz"] ** 2))
         fl = n_dec * (3.0 * (sizes.n_bv_total / npatch) + 36) + 2.0 * cfg["sz"] * sizes.n_bv_total * 37.0   # separable tables
@@ -415,8 +495,7 @@ def main():
         "metric": "compress pts/s", "value": value, "unit": "pts/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": desc, "per_gpu_points": n, "l2": "inputs larger than L2 (%.0f MB cloud + sort buffers per step)" % (n * 32 / 1e6),
-                   "parallelism": "one cloud per GPU, patches independent, no collective"},
+        "config": config_dict(desc, n),
         "decompress": {"value": dec_value, "unit": "grid pts/s", "points_per_step": ndec_all},
         "rmse_m": rmse,
         "compress_ms": 1e3 * comp_s / K, "decompress_ms": 1e3 * dec_s / K,
@@ -431,7 +510,7 @@ def main():
         "e2e_pipelined": {"value": None if lane_errors else n_all * 2 * per_lane / pipe_s, "errors": lane_errors, "unit": "pts/s", "in_flight": 2, "steps": 2 * per_lane,
                           "ms_per_step": 1e3 * pipe_s / (2 * per_lane),
                           "note": "same calls and bytes per step as e2e, two handles / host threads per GPU so that the H2D copy of one cloud overlaps the kernels of the other; wall clock"},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_launches": int(launches), "clocks": clocks, "strong": strong,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -95,3 +95,54 @@ def test_checksum_is_independent_of_sharding(run):
         apieces.append(hs.params()["alpha"])
     assert digest([np.concatenate(pieces)]) == digest([whole])
     assert np.array_equal(np.concatenate(apieces), alpha)
+
+
+# ---- full-size BIT-COMPARES against the oracle (every array of the path, not just properties) ----------------------
+def _oracle_threads():
+    import os
+    return max(1, os.cpu_count() or 1)
+
+
+def test_c1_full_size_bit_compare(oracle_mod):
+    """BASELINE configs[0] as stated: 100 000 points, gp_compressor(cloud, 0.15f, 20) (test_gp_compress.cpp:21), capacity 100,
+    reference hyper-parameters, with the RGB field GP as the reference runs it: lattice, patch assignment, frames, shuffles,
+    BV index sets, alpha, event counters, decoded cloud -- identical to the oracle."""
+    import gp_compressor_b200 as G
+    from test_gpu_compress import compare_all
+    cloud = synth.c1_planar_bumps(100_000, seed=1)
+    compare_all(G, oracle_mod, cloud, res=F32(0.15), sz=20, capacity=100)
+    h = G.Handle(res=F32(0.15), sz=20, capacity=100, rgb=1)
+    o = oracle_mod.Oracle(res=F32(0.15), sz=20, capacity=100, rgb=1, threads=_oracle_threads())
+    h.compress(cloud)
+    want = o.compress(cloud)
+    assert np.array_equal(h.params()["bv_idx"], want["bv_idx"]) and np.array_equal(h.params()["alpha"], want["alpha"])
+    rg, ro = h.params_rgb(), o.rgb_result()
+    assert np.array_equal(rg["nbv"], ro["nbv"]) and np.array_equal(rg["bv_idx"], ro["bv_idx"]) and np.array_equal(rg["alpha"], ro["alpha"])
+    co, _ = o.decode(want_heights=False)
+    assert np.array_equal(h.decompress(), co)
+
+
+def test_c2_full_size_bit_compare(run, oracle_mod):
+    """BASELINE configs[1] as stated (5 M points, res 0.1, capacity 30, reference hyper-parameters): the whole path against
+    the oracle run on all host cores -- identical patch assignment, per-patch order, BV index sets, alpha and decoded cloud."""
+    G, cloud, h = run
+    h.set_rand_offset(0)
+    h.compress(cloud)
+    o = oracle_mod.Oracle(res=F32(0.1), sz=10, capacity=30, threads=_oracle_threads())
+    want = o.compress(cloud)
+    bo, bg, ag = o.binning(), h.patches(), h.assignment()
+    assert bg["depth"] == bo["depth"] and np.array_equal(bg["lattice_min"], bo["lattice_min"])
+    for k in ("leaf_code", "leaf_center", "leaf_ncand", "patch_off", "leaf_R", "leaf_quat", "leaf_mean", "leaf_rgbmean"):
+        assert np.array_equal(bg[k], bo[k], equal_nan=True), k   # patches without claimed points hold NaN means (gp_compressor.cpp:101-102)
+    for k in ("owner", "st_idx", "st_x1", "st_x2", "st_y"):
+        assert np.array_equal(ag[k], bo[k]), k
+    assert np.array_equal(ag["perm"], want["perm"])
+    got = h.params()
+    assert np.array_equal(got["nbv"], want["nbv"]) and np.array_equal(got["bv_idx"], want["bv_idx"])
+    assert np.array_equal(got["alpha"], want["alpha"])
+    gs, os_ = h.stats(), o.stats()
+    for k in ("n_add", "n_first", "n_sparse", "n_full", "n_del_cap", "n_del_geo"):
+        assert gs[k] == os_[k], k
+    co, ho = o.decode()
+    assert h.decompress_resident() == ho.size and np.array_equal(h.heights(), ho)
+    assert np.array_equal(h.decompress(), co)
