@@ -24,6 +24,7 @@
 // writes its complete state (N, next point, counters, alpha, BV, C, Q) to a hand-off slot and
 // queues the patch; the next bucket's kernel resumes from that state — no work is redone
 // and the arithmetic is the same in every bucket.
+#include <cstdlib>
 #include <type_traits>
 
 #include "gpc_device.cuh"
