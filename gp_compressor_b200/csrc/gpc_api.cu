@@ -74,8 +74,9 @@ int fail(gpc_handle* h, int code, const std::string& msg) {
 // Layout of gpc_handle::small, the 256-byte device block for the few scalars that travel between kernels and the host.
 struct SmallScratch {
     unsigned long long pad0[4];
-    unsigned long long n_valid;      // count_valid_kernel
-    unsigned long long pad1[3];
+    unsigned long long n_valid;      // leaves_fused_kernel: finite points ...
+    unsigned long long n_leaves;     // ... and leaves (read back together)
+    unsigned long long pad1[2];
     int64_t plan[9];                 // fit_plan_kernel: n_claimed, lo, hi, off[lo], off[hi], roff[lo], roff[hi], roff[P], max patch
     int64_t pad2[3];
     int64_t owned_range[2];          // owned_range_kernel (sharded binning): first / one-past-last owned patch
@@ -611,29 +612,22 @@ int run_binning(gpc_handle* h, StageTimer& tm, bool sharded = false) {
     uint64_t* skeys = which ? h->keys2.as<uint64_t>() : h->keys.as<uint64_t>();
     uint32_t* svals = which ? h->vals2.as<uint32_t>() : h->vals.as<uint32_t>();
     uint64_t* fkeys = which ? h->keys.as<uint64_t>() : h->keys2.as<uint64_t>();  // free buffer for the owner keys
-    launch_count_valid(skeys, n, L.depth, d_nvalid, st);
     size_t t3 = tm.mark();
     tm.span(&h->stats.ms_sort, t2, t3);
-    unsigned long long nv = 0;
-    CK(cudaMemcpyAsync(&nv, d_nvalid, sizeof(nv), cudaMemcpyDeviceToHost, st));
+    // ---- leaves: valid count, leaf numbering, leaf tables and the sorted-point gather in one pass; ONE round trip ----
+    CK(h->leaf_of.reserve(n * sizeof(int32_t)));
+    CK(h->leaf_start.reserve((n + 1) * sizeof(int64_t)));
+    CK(h->leaf_code_a.reserve(n * sizeof(uint64_t)));
+    CK(h->spt.reserve(n * 16));
+    CK(h->scan_tmp.reserve(std::max(leaves_fused_tmp_bytes(n), scan_tmp_bytes(n))));
+    launch_leaves_fused(skeys, svals, n, L.depth, cloud, h->leaf_of.as<int32_t>(), h->leaf_start.as<int64_t>(),
+                        h->leaf_code_a.as<uint64_t>(), h->spt.p, d_nvalid, h->scan_tmp.p, st);
+    unsigned long long nvp[2] = {0, 0};
+    CK(cudaMemcpyAsync(nvp, d_nvalid, sizeof(nvp), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    const int64_t n_valid = (int64_t)nv;
-    // ---- leaves ----
-    CK(h->flags64.reserve(n_valid * sizeof(int64_t)));
-    CK(h->ex.reserve((n_valid + 1) * sizeof(int64_t)));
-    CK(h->scan_tmp.reserve(scan_tmp_bytes(n_valid)));
-    launch_mark_heads(skeys, n_valid, h->flags64.as<int64_t>(), st);
-    launch_exclusive_scan_i64(h->flags64.as<int64_t>(), h->ex.as<int64_t>(), n_valid, h->scan_tmp.p, st);
-    int64_t P = 0;
-    CK(cudaMemcpyAsync(&P, h->ex.as<int64_t>() + n_valid, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    const int64_t n_valid = (int64_t)nvp[0];
+    const int64_t P = (int64_t)nvp[1];
     h->n_patches = P;
-    CK(h->leaf_of.reserve(n_valid * sizeof(int32_t)));
-    CK(h->leaf_start.reserve((P + 1) * sizeof(int64_t)));
-    CK(h->leaf_code_a.reserve(P * sizeof(uint64_t)));
-    CK(h->spt.reserve(n_valid * 16));
-    launch_fill_leaves(skeys, svals, h->ex.as<int64_t>(), n_valid, cloud, h->leaf_of.as<int32_t>(), h->leaf_start.as<int64_t>(),
-                       h->leaf_code_a.as<uint64_t>(), h->spt.p, st);
     size_t t4 = tm.mark();
     tm.span(&h->stats.ms_leaves, t3, t4);
     // ---- neighbours + rotation ----

@@ -67,6 +67,9 @@ void launch_iota_u32(uint32_t* v, int64_t n, cudaStream_t s);
 void launch_mark_heads(const uint64_t* keys, int64_t n, int64_t* flags, cudaStream_t s);
 void launch_fill_leaves(const uint64_t* keys, const uint32_t* vals, const int64_t* ex, int64_t n, const uint8_t* cloud,
                         int32_t* leaf_of, int64_t* leaf_start, uint64_t* leaf_code, void* spt, cudaStream_t s);
+size_t leaves_fused_tmp_bytes(int64_t n);
+void launch_leaves_fused(const uint64_t* keys, const uint32_t* vals, int64_t n, uint32_t depth, const uint8_t* cloud, int32_t* leaf_of,
+                         int64_t* leaf_start, uint64_t* leaf_code, void* spt, unsigned long long* counts2, void* tmp, cudaStream_t s);
 void launch_leaf_neighbours(const uint64_t* leaf_code, int64_t P, const LatticeDev& lat, int32_t* nbr, int32_t* nnbr,
                             float* center, cudaStream_t s);
 void launch_leaf_rotation(const void* spt, const int64_t* leaf_start, const int32_t* nbr, const int32_t* nnbr,

@@ -187,6 +187,116 @@ __global__ void fill_leaves_kernel(const uint64_t* __restrict__ keys, const uint
     spt[s] = p;
 }
 
+// K3 fused: valid count, leaf heads, leaf numbering (chained scan with decoupled look-back over the blocks), leaf tables and
+// the gather of the sorted points, in ONE pass over the sorted keys.  Replaces count_valid + mark_heads + a three-kernel
+// int64 scan + fill_leaves (and one host round trip: n_valid and the leaf count come back together).
+//   counts[0] = n_valid (keys below `invalid`, i.e. finite points), counts[1] = number of leaves
+constexpr int LF_T = 256, LF_ITEMS = 8, LF_TILE = LF_T * LF_ITEMS;
+__global__ void __launch_bounds__(LF_T) leaves_fused_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n,
+                                                            uint64_t invalid, const uint8_t* __restrict__ cloud,
+                                                            int32_t* __restrict__ leaf_of, int64_t* __restrict__ leaf_start,
+                                                            uint64_t* __restrict__ leaf_code, float4* __restrict__ spt,
+                                                            unsigned long long* __restrict__ counts,
+                                                            unsigned long long* __restrict__ status, unsigned int* __restrict__ counter) {
+    __shared__ unsigned int tile_s;
+    __shared__ unsigned int wsum[LF_T / 32];
+    __shared__ unsigned long long prefix_s;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) tile_s = atomicAdd(counter, 1u);   // blocks start in the order of their tile numbers
+    __syncthreads();
+    const int64_t tile = tile_s;
+    const int64_t s0 = tile * LF_TILE + (int64_t)t * LF_ITEMS;
+    uint64_t k[LF_ITEMS];
+    uint64_t prev = 0;
+    bool have_prev = false;
+    if (s0 > 0 && s0 - 1 < n) { prev = keys[s0 - 1]; have_prev = true; }
+#pragma unroll
+    for (int i = 0; i < LF_ITEMS; i++) k[i] = s0 + i < n ? keys[s0 + i] : ~0ull;
+    // the point gathers do not depend on the scan: issue them now
+    float4 pt[LF_ITEMS];
+#pragma unroll
+    for (int i = 0; i < LF_ITEMS; i++) {
+        pt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s0 + i < n && k[i] < invalid) {
+            const uint8_t* src = cloud + (int64_t)vals[s0 + i] * GPC_POINT_BYTES;
+            pt[i] = *reinterpret_cast<const float4*>(src);
+            pt[i].w = __uint_as_float(*reinterpret_cast<const uint32_t*>(src + 16));  // b,g,r,a bytes
+        }
+    }
+    unsigned int head[LF_ITEMS], c = 0, nvalid = 0;
+#pragma unroll
+    for (int i = 0; i < LF_ITEMS; i++) {
+        const bool valid = s0 + i < n && k[i] < invalid;
+        const uint64_t before = i ? k[i - 1] : prev;
+        head[i] = (valid && (!(i || have_prev) || k[i] != before)) ? 1u : 0u;
+        c += head[i];
+        nvalid += valid ? 1u : 0u;
+    }
+    // block scan of the head counts (and the block's valid count)
+    unsigned int x = c, v = nvalid;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 31) wsum[w] = x;
+    if (lane == 0 && v) atomicAdd(counts + 0, (unsigned long long)v);
+    __syncthreads();
+    unsigned int wb = 0, total = 0;
+#pragma unroll
+    for (int ww = 0; ww < LF_T / 32; ww++) {
+        if (ww < w) wb += wsum[ww];
+        total += wsum[ww];
+    }
+    // chained scan over the tiles: status = flag (2 bits) | count.  Warp 0 looks back 32 tiles at a time.
+    constexpr unsigned long long AGG = 1ull << 62, INCL = 2ull << 62, MASK = (1ull << 62) - 1;
+    if (w == 0) {
+        unsigned long long excl = 0;
+        if (tile == 0) {
+            if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&status[0]) = INCL | total;
+        } else {
+            if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&status[tile]) = AGG | total;
+            for (int64_t j = tile - 1;; j -= 32) {
+                const int64_t idx = j - lane;
+                unsigned long long sw = INCL;   // before the first tile: an inclusive prefix of zero
+                if (idx >= 0) {
+                    do { sw = *reinterpret_cast<volatile const unsigned long long*>(&status[idx]); } while ((sw >> 62) == 0ull);
+                }
+                const unsigned incl = __ballot_sync(0xffffffffu, (sw & INCL) != 0ull);
+                const int stop = incl ? (__ffs(incl) - 1) : 31;            // nearest predecessor that holds an inclusive prefix
+                unsigned long long v = (lane <= stop) ? (sw & MASK) : 0ull;
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                excl += v;
+                if (incl) break;
+            }
+            if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&status[tile]) = INCL | (excl + total);
+        }
+        if (lane == 0) {
+            prefix_s = excl;
+            if ((tile + 1) * LF_TILE >= n) counts[1] = excl + total;   // the last tile: number of leaves
+        }
+    }
+    __syncthreads();
+    int64_t a = (int64_t)prefix_s + wb + (x - c) - 1;   // leaf of the element before this thread's first one
+#pragma unroll
+    for (int i = 0; i < LF_ITEMS; i++) {
+        const int64_t s = s0 + i;
+        const bool valid = s < n && k[i] < invalid;
+        if (valid) {
+            a += head[i];
+            leaf_of[s] = (int32_t)a;
+            if (head[i]) { leaf_start[a] = s; leaf_code[a] = k[i]; }
+            spt[s] = pt[i];
+            // end of the valid keys: leaf_start[P] = n_valid
+            const bool last = (s + 1 == n) || (i + 1 < LF_ITEMS ? !(k[i + 1] < invalid) : !(keys[s + 1] < invalid));
+            if (last) leaf_start[a + 1] = s + 1;
+        }
+    }
+}
+
 // ---- neighbour table + voxel centres, one warp per leaf ------------------------------------
 __global__ void __launch_bounds__(256) leaf_neighbours_kernel(const uint64_t* __restrict__ leaf_code, int64_t P, LatticeDev lat,
                                                               int32_t* __restrict__ nbr, int32_t* __restrict__ nnbr,
@@ -707,6 +817,23 @@ void launch_fill_leaves(const uint64_t* keys, const uint32_t* vals, const int64_
                         int32_t* leaf_of, int64_t* leaf_start, uint64_t* leaf_code, void* spt, cudaStream_t s) {
     fill_leaves_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, s>>>(keys, vals, ex, n, cloud, leaf_of, leaf_start, leaf_code,
                                                                      reinterpret_cast<float4*>(spt));
+    g_launches++;
+}
+
+size_t leaves_fused_tmp_bytes(int64_t n) { return (size_t)((n + LF_TILE - 1) / LF_TILE + 4) * sizeof(unsigned long long); }
+
+// counts2: two device counters (n_valid, leaves), zeroed here; tmp >= leaves_fused_tmp_bytes(n)
+void launch_leaves_fused(const uint64_t* keys, const uint32_t* vals, int64_t n, uint32_t depth, const uint8_t* cloud, int32_t* leaf_of,
+                         int64_t* leaf_start, uint64_t* leaf_code, void* spt, unsigned long long* counts2, void* tmp, cudaStream_t s) {
+    cudaMemsetAsync(counts2, 0, 2 * sizeof(unsigned long long), s);
+    cudaMemsetAsync(leaf_start, 0, sizeof(int64_t), s);   // no valid point: leaf_start[0] = 0
+    if (n <= 0) return;
+    const int64_t tiles = (n + LF_TILE - 1) / LF_TILE;
+    cudaMemsetAsync(tmp, 0, leaves_fused_tmp_bytes(n), s);
+    unsigned long long* status = reinterpret_cast<unsigned long long*>(tmp) + 2;
+    unsigned int* counter = reinterpret_cast<unsigned int*>(tmp);
+    leaves_fused_kernel<<<(unsigned)tiles, LF_T, 0, s>>>(keys, vals, n, 1ull << (3 * depth), cloud, leaf_of, leaf_start, leaf_code,
+                                                         reinterpret_cast<float4*>(spt), counts2, status, counter);
     g_launches++;
 }
 

@@ -34,6 +34,13 @@ __device__ __forceinline__ unsigned int flatten_color(double x) {
     return (unsigned int)s;
 }
 
+// x, y, z, 1.0f | rgba, 0, 0, 0 : 32 bytes, 32-byte aligned, written with st.global.v8.b32 (sm_100)
+__device__ __forceinline__ void store_record(uint8_t* dst, float x, float y, float z, unsigned int rgba) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(__float_as_uint(x)), "r"(__float_as_uint(y)),
+                 "r"(__float_as_uint(z)), "r"(0x3f800000u), "r"(rgba), "r"(0u), "r"(0u), "r"(0u)
+                 : "memory");
+}
+
 __device__ __forceinline__ void quat_to_rot(const double* q, double* R) {
     double tx = __dmul_rn(2.0, q[0]), ty = __dmul_rn(2.0, q[1]), tz = __dmul_rn(2.0, q[2]);
     double twx = __dmul_rn(tx, q[3]), twy = __dmul_rn(ty, q[3]), twz = __dmul_rn(tz, q[3]);
@@ -261,9 +268,8 @@ __global__ void __launch_bounds__(PRED_T, MINB) predict_grid_kernel(PredictArgs 
                                        bb = flatten_color(__dadd_rn(fb, cmean[2]));
                     col = bb | (gg << 8) | (rr << 16) | (255u << 24);
                 }
-                float4* dst = reinterpret_cast<float4*>(a.out32 + (size_t)(base + m) * GPC_POINT_BYTES);
-                dst[0] = make_float4(o[0], o[1], o[2], 1.0f);
-                dst[1] = make_float4(__uint_as_float(col), 0.0f, 0.0f, 0.0f);
+                // one 256-bit store per PointXYZRGB record (a whole 32-byte sector: no partial-sector write traffic)
+                store_record(a.out32 + (size_t)(base + m) * GPC_POINT_BYTES, o[0], o[1], o[2], col);
             }
         }
     }
