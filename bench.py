@@ -116,9 +116,17 @@ def strong_block(args, G, torch, dist, rank, world, local):
     mx = torch.tensor([float(np.mean(walls)), float(np.mean(gath)), float(np.mean(dev)), float(np.mean(dec)), float(np.mean(fit)),
                        float(sz.n_claimed), own_pts, float(np.mean(decw))], dtype=torch.float64, device="cuda")
     sm = torch.tensor([float(np.mean(fit)), float(sz.n_claimed), own_pts, float(nd), float(sz.patch_hi - sz.patch_lo)], dtype=torch.float64, device="cuda")
+    per_rank = None
+    mine = torch.tensor([float(np.mean(fit)), float(sz.n_claimed), own_pts, float(sb["ms_total"]), float(np.mean(dev)), float(sz.patch_hi - sz.patch_lo),
+                         float(st["ms_shuffle"]), float(np.mean(walls))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        allm = torch.zeros(world * mine.numel(), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allm, mine)
+        per_rank = allm.cpu().numpy().reshape(world, -1)
+    else:
+        per_rank = mine.cpu().numpy().reshape(1, -1)
     h.close()
     wm, gm, dm, pm, fm, cl, op_, dw = mx.tolist()
     fs, cs, os_, nds, ps = sm.tolist()
@@ -129,6 +137,8 @@ def strong_block(args, G, torch, dist, rank, world, local):
             "max_rank_binned_points": cl, "mean_rank_binned_points": cs / world,
             "max_rank_owned_points": op_, "mean_rank_owned_points": os_ / world,
             "decompress_wall_ms": dw, "max_rank_predict_ms": pm, "decompress_value": nds / (dw * 1e-3), "patches": int(ps),
+            "per_rank": {k: [round(float(v), 3) for v in per_rank[:, i]] for i, k in enumerate(
+                ["fit_ms", "binned_points", "owned_points", "begin_device_ms", "device_ms", "owned_patches", "shuffle_ms", "wall_ms"])},
             "timed_reps": reps - 1}
 
 

@@ -53,6 +53,7 @@ struct gpc_handle {
     uint64_t draws_before = 0, draws_total = 0, draws_owned = 0;
 
     // binning scratch
+    DevBuf cpt;  // 16-byte point records in input order (point_keys_kernel)
     DevBuf keys, keys2, vals, vals2, ovals, ovals2, sort_tmp, flags64, ex, leaf_of, leaf_start, leaf_code_a, spt, nbr, nnbr,
         center_a, Rm_a, ncand_a, pt0, pt1, pt2, hbuf, rgb, leaf_sums;
     std::vector<cudaEvent_t> ev;
@@ -563,7 +564,7 @@ int run_binning(gpc_handle* h, StageTimer& tm, bool sharded = false) {
         const int depth = (int)L.depth;
         CK(h->keys.reserve(n * sizeof(uint64_t)));
         CK(h->vals.reserve(n * sizeof(uint32_t)));
-        launch_point_keys(cloud, n, lat, h->keys.as<uint64_t>(), h->vals.as<uint32_t>(), st);
+        launch_point_keys(cloud, n, lat, h->keys.as<uint64_t>(), h->vals.as<uint32_t>(), nullptr, st);
         const int64_t stride = std::max<int64_t>(1, n >> 20);
         const int64_t m = (n + stride - 1) / stride;
         CK(h->coarse_hist.reserve((size_t)m * 2 * (sizeof(uint64_t) + sizeof(uint32_t)) + 64));
@@ -604,7 +605,8 @@ int run_binning(gpc_handle* h, StageTimer& tm, bool sharded = false) {
     CK(h->vals.reserve(n * sizeof(uint32_t)));
     CK(h->vals2.reserve(n * sizeof(uint32_t)));
     CK(h->sort_tmp.reserve(radix_sort_tmp_bytes(n)));
-    launch_point_keys(cloud, n, lat, h->keys.as<uint64_t>(), h->vals.as<uint32_t>(), st);
+    CK(h->cpt.reserve(n * 16));
+    launch_point_keys(cloud, n, lat, h->keys.as<uint64_t>(), h->vals.as<uint32_t>(), h->cpt.p, st);
     size_t t2 = tm.mark();
     tm.span(&h->stats.ms_keys, t1, t2);
     int which = launch_radix_sort(h->keys.as<uint64_t>(), h->vals.as<uint32_t>(), h->keys2.as<uint64_t>(), h->vals2.as<uint32_t>(), n,
@@ -620,7 +622,7 @@ int run_binning(gpc_handle* h, StageTimer& tm, bool sharded = false) {
     CK(h->leaf_code_a.reserve(n * sizeof(uint64_t)));
     CK(h->spt.reserve(n * 16));
     CK(h->scan_tmp.reserve(std::max(leaves_fused_tmp_bytes(n), scan_tmp_bytes(n))));
-    launch_leaves_fused(skeys, svals, n, L.depth, cloud, h->leaf_of.as<int32_t>(), h->leaf_start.as<int64_t>(),
+    launch_leaves_fused(skeys, svals, n, L.depth, h->cpt.p, h->leaf_of.as<int32_t>(), h->leaf_start.as<int64_t>(),
                         h->leaf_code_a.as<uint64_t>(), h->spt.p, d_nvalid, h->scan_tmp.p, st);
     unsigned long long nvp[2] = {0, 0};
     CK(cudaMemcpyAsync(nvp, d_nvalid, sizeof(nvp), cudaMemcpyDeviceToHost, st));
@@ -792,7 +794,7 @@ void gpc_destroy(gpc_handle* h) {
                       &h->r_alpha0, &h->r_alpha1, &h->r_alpha2, &h->r_b1, &h->r_b2, &h->r_bidx, &h->kstats_rgb, &h->nonempty, &h->slot, &h->out32,
                       &h->heights, &h->quat, &h->mean, &h->rgbmean, &h->Rm, &h->center, &h->code, &h->ncand, &h->owner,
                       &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->lat_state, &h->ev_in, &h->ev_out, &h->size_ids, &h->size_hist, &h->sel_cloud, &h->sel_idx, &h->coarse_hist, &h->fed, &h->forig, &h->cont_q, &h->cont_slots, &h->queueB, &h->handB, &h->r_dumpC, &h->r_dumpQ, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
-                      &h->ovals2, &h->sort_tmp, &h->flags64, &h->ex, &h->leaf_of, &h->leaf_start, &h->leaf_code_a, &h->spt,
+                      &h->cpt, &h->ovals2, &h->sort_tmp, &h->flags64, &h->ex, &h->leaf_of, &h->leaf_start, &h->leaf_code_a, &h->spt,
                       &h->nbr, &h->nnbr, &h->center_a, &h->Rm_a, &h->ncand_a, &h->pt0, &h->pt1, &h->pt2, &h->hbuf, &h->rgb, &h->leaf_sums};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);

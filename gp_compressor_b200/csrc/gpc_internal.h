@@ -58,17 +58,13 @@ void launch_shard_splitters(const uint64_t* sorted, int64_t m, int depth, int ra
 void launch_shard_select(const uint64_t* keys, int64_t n, int depth, const uint64_t* range2, int64_t* flags, cudaStream_t s);
 void launch_shard_compact(const uint8_t* cloud, const int64_t* ex, int64_t n, uint8_t* sel_cloud, int32_t* sel_idx, cudaStream_t s);
 void launch_owned_range(const uint64_t* code, int64_t P, int leaf_order, const uint64_t* range2, int64_t* out2, cudaStream_t s);
-void launch_point_keys(const uint8_t* cloud, int64_t n, const LatticeDev& lat, uint64_t* keys, uint32_t* vals, cudaStream_t s);
-void launch_count_valid(const uint64_t* sorted_keys, int64_t n, uint32_t depth, unsigned long long* n_valid, cudaStream_t s);
+void launch_point_keys(const uint8_t* cloud, int64_t n, const LatticeDev& lat, uint64_t* keys, uint32_t* vals, void* cpt16, cudaStream_t s);
 size_t radix_sort_tmp_bytes(int64_t n);
 int launch_radix_sort(uint64_t* keys, uint32_t* vals, uint64_t* keys2, uint32_t* vals2, int64_t n, int nbits, void* tmp,
                       cudaStream_t s);
 void launch_iota_u32(uint32_t* v, int64_t n, cudaStream_t s);
-void launch_mark_heads(const uint64_t* keys, int64_t n, int64_t* flags, cudaStream_t s);
-void launch_fill_leaves(const uint64_t* keys, const uint32_t* vals, const int64_t* ex, int64_t n, const uint8_t* cloud,
-                        int32_t* leaf_of, int64_t* leaf_start, uint64_t* leaf_code, void* spt, cudaStream_t s);
 size_t leaves_fused_tmp_bytes(int64_t n);
-void launch_leaves_fused(const uint64_t* keys, const uint32_t* vals, int64_t n, uint32_t depth, const uint8_t* cloud, int32_t* leaf_of,
+void launch_leaves_fused(const uint64_t* keys, const uint32_t* vals, int64_t n, uint32_t depth, const void* cpt16, int32_t* leaf_of,
                          int64_t* leaf_start, uint64_t* leaf_code, void* spt, unsigned long long* counts2, void* tmp, cudaStream_t s);
 void launch_leaf_neighbours(const uint64_t* leaf_code, int64_t P, const LatticeDev& lat, int32_t* nbr, int32_t* nnbr,
                             float* center, cudaStream_t s);

@@ -137,11 +137,19 @@ __global__ void lattice_adopt_kernel(const uint8_t* __restrict__ cloud, LatticeS
 }
 
 // ---- K1: voxel key -> Morton code (PCL genOctreeKeyforPoint) --------------------------------
+// Also writes the 16-byte record (x, y, z, rgba bits) of every point when cpt != nullptr: the PointXYZRGB sector is in
+// flight anyway, and the later gather into Morton order then reads a half-size array that stays in L2 for room-sized clouds.
 __global__ void __launch_bounds__(256) point_keys_kernel(const uint8_t* __restrict__ cloud, int64_t n, LatticeDev lat,
-                                                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                         float4* __restrict__ cpt) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
-        const float4 p = *reinterpret_cast<const float4*>(cloud + i * GPC_POINT_BYTES);
+        float4 p = *reinterpret_cast<const float4*>(cloud + i * GPC_POINT_BYTES);
+        if (cpt) {
+            float4 c = p;
+            c.w = __uint_as_float(*reinterpret_cast<const uint32_t*>(cloud + i * GPC_POINT_BYTES + 16));  // b,g,r,a bytes
+            cpt[i] = c;
+        }
         uint64_t code = 1ull << (3 * lat.depth);  // non-finite points sort behind every voxel
         if (finite3(p.x, p.y, p.z)) {
             uint32_t kx = __double2uint_rz(__ddiv_rn(__dadd_rn((double)p.x, -lat.mn[0]), lat.res));
@@ -154,46 +162,13 @@ __global__ void __launch_bounds__(256) point_keys_kernel(const uint8_t* __restri
     }
 }
 
-// number of finite points = first sorted position whose key carries the "non-finite" bit
-__global__ void count_valid_kernel(const uint64_t* __restrict__ skeys, int64_t n, uint64_t invalid, unsigned long long* __restrict__ n_valid) {
-    int64_t lo = 0, hi = n;
-    while (lo < hi) {
-        int64_t mid = (lo + hi) >> 1;
-        if (skeys[mid] < invalid) lo = mid + 1; else hi = mid;
-    }
-    *n_valid = (unsigned long long)lo;
-}
-
-// ---- K3: leaves = runs of equal codes --------------------------------------------------------
-__global__ void mark_heads_kernel(const uint64_t* __restrict__ keys, int64_t n, int64_t* __restrict__ flags) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < n) flags[s] = (s == 0 || keys[s] != keys[s - 1]) ? 1 : 0;
-}
-// ex = exclusive scan of flags (ex[n] = number of leaves)
-__global__ void fill_leaves_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                   const int64_t* __restrict__ ex, int64_t n, const uint8_t* __restrict__ cloud,
-                                   int32_t* __restrict__ leaf_of, int64_t* __restrict__ leaf_start,
-                                   uint64_t* __restrict__ leaf_code, float4* __restrict__ spt) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s > n) return;
-    if (s == n) { leaf_start[ex[n]] = n; return; }
-    const bool head = ex[s + 1] != ex[s];
-    const int64_t a = ex[s + 1] - 1;
-    leaf_of[s] = (int32_t)a;
-    if (head) { leaf_start[a] = s; leaf_code[a] = keys[s]; }
-    const uint8_t* src = cloud + (int64_t)vals[s] * GPC_POINT_BYTES;
-    float4 p = *reinterpret_cast<const float4*>(src);
-    p.w = __uint_as_float(*reinterpret_cast<const uint32_t*>(src + 16));  // b,g,r,a bytes
-    spt[s] = p;
-}
-
 // K3 fused: valid count, leaf heads, leaf numbering (chained scan with decoupled look-back over the blocks), leaf tables and
 // the gather of the sorted points, in ONE pass over the sorted keys.  Replaces count_valid + mark_heads + a three-kernel
 // int64 scan + fill_leaves (and one host round trip: n_valid and the leaf count come back together).
 //   counts[0] = n_valid (keys below `invalid`, i.e. finite points), counts[1] = number of leaves
 constexpr int LF_T = 256, LF_ITEMS = 8, LF_TILE = LF_T * LF_ITEMS;
 __global__ void __launch_bounds__(LF_T) leaves_fused_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n,
-                                                            uint64_t invalid, const uint8_t* __restrict__ cloud,
+                                                            uint64_t invalid, const float4* __restrict__ cpt,
                                                             int32_t* __restrict__ leaf_of, int64_t* __restrict__ leaf_start,
                                                             uint64_t* __restrict__ leaf_code, float4* __restrict__ spt,
                                                             unsigned long long* __restrict__ counts,
@@ -218,9 +193,7 @@ __global__ void __launch_bounds__(LF_T) leaves_fused_kernel(const uint64_t* __re
     for (int i = 0; i < LF_ITEMS; i++) {
         pt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (s0 + i < n && k[i] < invalid) {
-            const uint8_t* src = cloud + (int64_t)vals[s0 + i] * GPC_POINT_BYTES;
-            pt[i] = *reinterpret_cast<const float4*>(src);
-            pt[i].w = __uint_as_float(*reinterpret_cast<const uint32_t*>(src + 16));  // b,g,r,a bytes
+            pt[i] = cpt[vals[s0 + i]];
         }
     }
     unsigned int head[LF_ITEMS], c = 0, nvalid = 0;
@@ -796,34 +769,16 @@ void launch_owned_range(const uint64_t* code, int64_t P, int leaf_order, const u
     g_launches++;
 }
 
-void launch_point_keys(const uint8_t* cloud, int64_t n, const LatticeDev& lat, uint64_t* keys, uint32_t* vals, cudaStream_t s) {
+void launch_point_keys(const uint8_t* cloud, int64_t n, const LatticeDev& lat, uint64_t* keys, uint32_t* vals, void* cpt, cudaStream_t s) {
     if (n <= 0) return;
-    point_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cloud, n, lat, keys, vals);
-    g_launches++;
-}
-
-void launch_count_valid(const uint64_t* sorted_keys, int64_t n, uint32_t depth, unsigned long long* n_valid, cudaStream_t s) {
-    count_valid_kernel<<<1, 1, 0, s>>>(sorted_keys, n, 1ull << (3 * depth), n_valid);
-    g_launches++;
-}
-
-void launch_mark_heads(const uint64_t* keys, int64_t n, int64_t* flags, cudaStream_t s) {
-    if (n <= 0) return;
-    mark_heads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(keys, n, flags);
-    g_launches++;
-}
-
-void launch_fill_leaves(const uint64_t* keys, const uint32_t* vals, const int64_t* ex, int64_t n, const uint8_t* cloud,
-                        int32_t* leaf_of, int64_t* leaf_start, uint64_t* leaf_code, void* spt, cudaStream_t s) {
-    fill_leaves_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, s>>>(keys, vals, ex, n, cloud, leaf_of, leaf_start, leaf_code,
-                                                                     reinterpret_cast<float4*>(spt));
+    point_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cloud, n, lat, keys, vals, reinterpret_cast<float4*>(cpt));
     g_launches++;
 }
 
 size_t leaves_fused_tmp_bytes(int64_t n) { return (size_t)((n + LF_TILE - 1) / LF_TILE + 4) * sizeof(unsigned long long); }
 
 // counts2: two device counters (n_valid, leaves), zeroed here; tmp >= leaves_fused_tmp_bytes(n)
-void launch_leaves_fused(const uint64_t* keys, const uint32_t* vals, int64_t n, uint32_t depth, const uint8_t* cloud, int32_t* leaf_of,
+void launch_leaves_fused(const uint64_t* keys, const uint32_t* vals, int64_t n, uint32_t depth, const void* cpt, int32_t* leaf_of,
                          int64_t* leaf_start, uint64_t* leaf_code, void* spt, unsigned long long* counts2, void* tmp, cudaStream_t s) {
     cudaMemsetAsync(counts2, 0, 2 * sizeof(unsigned long long), s);
     cudaMemsetAsync(leaf_start, 0, sizeof(int64_t), s);   // no valid point: leaf_start[0] = 0
@@ -832,7 +787,7 @@ void launch_leaves_fused(const uint64_t* keys, const uint32_t* vals, int64_t n, 
     cudaMemsetAsync(tmp, 0, leaves_fused_tmp_bytes(n), s);
     unsigned long long* status = reinterpret_cast<unsigned long long*>(tmp) + 2;
     unsigned int* counter = reinterpret_cast<unsigned int*>(tmp);
-    leaves_fused_kernel<<<(unsigned)tiles, LF_T, 0, s>>>(keys, vals, n, 1ull << (3 * depth), cloud, leaf_of, leaf_start, leaf_code,
+    leaves_fused_kernel<<<(unsigned)tiles, LF_T, 0, s>>>(keys, vals, n, 1ull << (3 * depth), reinterpret_cast<const float4*>(cpt), leaf_of, leaf_start, leaf_code,
                                                          reinterpret_cast<float4*>(spt), counts2, status, counter);
     g_launches++;
 }
