@@ -511,7 +511,7 @@ def main():
         "compress_ms": 1e3 * comp_s / K, "decompress_ms": 1e3 * dec_s / K,
         "stages_ms": {k: round(v, 4) for k, v in sorted(stage_ms.items())},
         "patches": int(sizes.n_patches), "claimed": int(sizes.n_claimed), "mean_bv": sizes.n_bv_total / max(1, sizes.n_patches),
-        "escalated": fit_stats["escalated"],
+        "escalated": fit_stats["escalated"], "max_bv": fit_stats["max_bv"],
         "fit_events": {k: int(fit_stats[k]) for k in ("n_add", "n_first", "n_sparse", "n_full", "n_del_cap", "n_del_geo", "sum_n", "sum_n2_common",
                                                       "sum_n2_sparse", "sum_n2_full", "sum_n2_del")},
         "roofline": roof, "cpu_baseline": cpu,

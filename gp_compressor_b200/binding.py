@@ -47,7 +47,8 @@ _STAT_RGB = ["rgb_n_sparse", "rgb_n_full", "rgb_n_del_cap", "rgb_n_del_geo", "rg
 
 class GpcStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in _STAT_U64] + [("escalated", C.c_uint64 * 4), ("kernel_launches", C.c_uint64)] + \
-               [(n, C.c_uint64) for n in _STAT_RGB] + [(n, C.c_float) for n in _STAT_MS]
+               [(n, C.c_uint64) for n in _STAT_RGB] + [(n, C.c_float) for n in _STAT_MS] + \
+               [("max_bv", C.c_uint64), ("bv_hist", C.c_uint64 * 33)]
 
 
 def load():
@@ -273,6 +274,8 @@ class Handle:
         self._ck(load().gpc_get_stats(self.h, C.byref(s)))
         d = {n: getattr(s, n) for n in _STAT_U64 + _STAT_MS + _STAT_RGB + ["kernel_launches"]}
         d["escalated"] = list(s.escalated)
+        d["max_bv"] = int(s.max_bv)
+        d["bv_hist"] = list(s.bv_hist)   # [k] = patches with k basis vectors (k < 32), [32] = 32 or more
         return d
 
     def params(self):

@@ -16,6 +16,10 @@ FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-li
          "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr"]
 
 
+if os.environ.get("GPC_DEBUG"):
+    FLAGS.append("-DGPC_DEBUG_ASSERTS")   # device-side bounds traps (gpc_device.cuh)
+
+
 def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 

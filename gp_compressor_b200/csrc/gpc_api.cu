@@ -260,8 +260,8 @@ int run_fit(gpc_handle* h, StageTimer& tm, bool cont = false) {
     CK(h->queue0.reserve(PLa * sizeof(int32_t)));
     CK(h->queue1.reserve(PLa * sizeof(int32_t)));
     CK(h->qcount.reserve(8 * sizeof(int32_t)));
-    CK(h->kstats.reserve(16 * sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(h->kstats.p, 0, 16 * sizeof(unsigned long long), st));
+    CK(h->kstats.reserve(64 * sizeof(unsigned long long)));   // 16 event counters, then max BV count + histogram (34)
+    CK(cudaMemsetAsync(h->kstats.p, 0, 64 * sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(h->qcount.p, 0, 8 * sizeof(int32_t), st));
     SogpArgs a;
     a.off = h->off.as<int64_t>();
@@ -413,6 +413,7 @@ int run_fit(gpc_handle* h, StageTimer& tm, bool cont = false) {
     launch_compact_params(h->nbv.as<int32_t>(), PL, cap, h->alpha.as<double>(), h->b1.as<double>(), h->b2.as<double>(),
                           h->bidx.as<int32_t>(), h->nonempty.as<int64_t>(), h->bv_off.as<int64_t>(), h->scan_tmp.p,
                           h->palpha.as<double>(), h->pb1.as<double>(), h->pb2.as<double>(), h->pidx.as<int32_t>(), st);
+    launch_bv_hist(h->nbv.as<int32_t>(), PL, h->kstats.as<unsigned long long>() + 16, st);
     int64_t tot = 0;
     CK(cudaMemcpyAsync(&tot, h->bv_off.as<int64_t>() + PL, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -426,10 +427,12 @@ int run_fit(gpc_handle* h, StageTimer& tm, bool cont = false) {
 }
 
 int read_fit_stats(gpc_handle* h) {
-    unsigned long long k[16];
+    unsigned long long k[50];
     CK(cudaMemcpyAsync(k, h->kstats.p, sizeof(k), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     gpc_stats& s = h->stats;
+    s.max_bv = k[16];
+    for (int i = 0; i < 33; i++) s.bv_hist[i] = k[17 + i];
     s.n_add = k[0]; s.n_first = k[1]; s.n_sparse = k[2]; s.n_full = k[3]; s.n_del_cap = k[4]; s.n_del_geo = k[5];
     s.sum_n = k[6]; s.sum_n2_common = k[7]; s.sum_n2_sparse = k[8]; s.sum_n2_full = k[9]; s.sum_n2_del = k[10];
     if (h->have_rgb) {

@@ -9,6 +9,16 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Device-side bounds traps for the indices the kernels compute themselves (hand-off slots, overflow queues, tile slots):
+// compiled in with `GPC_DEBUG=1 python -m gp_compressor_b200.build --force` (-DGPC_DEBUG_ASSERTS); compute-sanitizer is closed on
+// the GPU pool, so this is the memory-safety check that can actually be run there.
+#ifdef GPC_DEBUG_ASSERTS
+#include <cassert>
+#define GPC_DASSERT(c) assert(c)
+#else
+#define GPC_DASSERT(c) ((void)0)
+#endif
+
 namespace gpc {
 
 // float literals of the reference widened to double (sparse_gp.hpp:124,146,229,236)

@@ -103,6 +103,7 @@ void launch_exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, void*
 // draws[p] = (n_p > 0 ? (n_p - 1) * mult : 0)
 // draws[p] + exclusive scan roff[0..P] + plan9 = { n_claimed, lo, hi, off[lo], off[hi], roff[lo], roff[hi], roff[P], max n_p }
 // ids[0..n): patches lo..lo+n-1 by decreasing point count; hist1024: 1024 ints of scratch
+void launch_bv_hist(const int32_t* nbv, int64_t n, unsigned long long* out34, cudaStream_t s);
 void launch_fed_update(const int64_t* off, int64_t n, int accumulate, int64_t* fed, cudaStream_t s);
 void launch_size_order(const int64_t* off, int64_t lo, int64_t n, int32_t* hist1024, int32_t* ids, cudaStream_t s);
 void launch_fit_plan(const int64_t* off, int64_t n_patches, int mult, int rank, int count, int64_t fixed_lo, int64_t fixed_hi,

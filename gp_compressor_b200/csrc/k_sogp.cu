@@ -312,6 +312,7 @@ __global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
             }
         }
         const HalfTile<DOUT>& tl = *tlp;
+        GPC_DASSERT(s + 1 + sh1 < 18 && s + sh3 < 20);   // staged slots stay inside the tile arrays
         if (tt == 0) {  // sparse_gp.hpp:100-110 (both halves: a half has n == 0 or starts here)
             if (live) {
                 if (r == 0) {
@@ -433,6 +434,7 @@ __global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
                 int pos = 0;
                 if (r == 0) pos = atomicAdd(a.queue_count, 1);
                 pos = __shfl_sync(gm, pos, 0, 16);
+                GPC_DASSERT(a.queue != nullptr && a.handoff_out != nullptr && pos >= 0 && pos < a.n_work);  // one slot per patch of this launch at most
                 double* slot = a.handoff_out + (size_t)pos * slot_doubles(W_N, DOUT);
                 if (r == 0) {
                     a.queue[pos] = (int32_t)patch;
@@ -818,7 +820,8 @@ __global__ void __launch_bounds__(64, 10) sogp_fit_pair_kernel(SogpArgs a) {
             if (t == 0) sm.spos = atomicAdd(a.queue_count, 1);
             __syncthreads();
             const int pos = sm.spos;
-            double* slot = a.handoff_out + (size_t)pos * slot_doubles(P_N);
+            GPC_DASSERT(a.queue != nullptr && a.handoff_out != nullptr && pos >= 0 && pos < a.n_work);  // one slot per patch of this launch at most
+                double* slot = a.handoff_out + (size_t)pos * slot_doubles(P_N);
             if (t == 0) {
                 a.queue[pos] = (int32_t)patch;
                 reinterpret_cast<int*>(slot)[0] = N;
@@ -1409,7 +1412,8 @@ __global__ void __launch_bounds__(NT) sogp_fit_kernel(SogpArgs a) {
             if (t == 0) spos = atomicAdd(a.queue_count, 1);
             __syncthreads();
             const int pos = spos;
-            double* slot = a.handoff_out + (size_t)pos * slot_doubles(LD, DOUT);
+            GPC_DASSERT(a.queue != nullptr && a.handoff_out != nullptr && pos >= 0 && pos < a.n_work);  // one slot per patch of this launch at most
+                double* slot = a.handoff_out + (size_t)pos * slot_doubles(LD, DOUT);
             if (t == 0) {
                 a.queue[pos] = (int32_t)patch;
                 reinterpret_cast<int*>(slot)[0] = N;
@@ -1787,7 +1791,8 @@ __global__ void __launch_bounds__(NT) sogp_fit_fused_kernel(SogpArgs a) {
             if (t == 0) spos = atomicAdd(a.queue_count, 1);
             __syncthreads();
             const int pos = spos;
-            double* slot = a.handoff_out + (size_t)pos * slot_doubles(LD_OUT, DOUT);
+            GPC_DASSERT(a.queue != nullptr && a.handoff_out != nullptr && pos >= 0 && pos < a.n_work);  // one slot per patch of this launch at most
+                double* slot = a.handoff_out + (size_t)pos * slot_doubles(LD_OUT, DOUT);
             if (t == 0) {
                 a.queue[pos] = (int32_t)patch;
                 reinterpret_cast<int*>(slot)[0] = N;

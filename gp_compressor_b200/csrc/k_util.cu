@@ -1,5 +1,7 @@
 // k_util.cu — scans, the per-patch shuffle (K6b) and the gather into the fit stream (K6c).
 #include "gpc_device.cuh"
+#include <algorithm>
+
 #include "gpc_internal.h"
 
 namespace gpc {
@@ -307,6 +309,27 @@ void launch_flag_nonempty(const int32_t* nbv, const int32_t* rgb_nbv, int64_t n,
     cudaMemsetAsync(maxes, 0, 2 * sizeof(int32_t), s);
     if (n <= 0) return;
     flag_nonempty_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(nbv, rgb_nbv, n, flags, maxes);
+    g_launches++;
+}
+
+// out34[0] = max nbv, out34[1 + k] = patches with k basis vectors (k < 32), out34[33] = patches with >= 32 (gpc_stats.bv_hist)
+__global__ void __launch_bounds__(256) bv_hist_kernel(const int32_t* __restrict__ nbv, int64_t n, unsigned long long* __restrict__ out34) {
+    __shared__ unsigned int h[34];
+    if (threadIdx.x < 34) h[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int v = nbv[i];
+        atomicAdd(&h[1 + (v < 32 ? v : 32)], 1u);
+        atomicMax(&h[0], (unsigned)v);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) atomicMax(out34, (unsigned long long)h[0]);
+    else if (threadIdx.x < 34 && h[threadIdx.x]) atomicAdd(out34 + threadIdx.x, (unsigned long long)h[threadIdx.x]);
+}
+void launch_bv_hist(const int32_t* nbv, int64_t n, unsigned long long* out34, cudaStream_t s) {
+    cudaMemsetAsync(out34, 0, 34 * sizeof(unsigned long long), s);
+    if (n <= 0) return;
+    bv_hist_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 592), 256, 0, s>>>(nbv, n, out34);
     g_launches++;
 }
 

@@ -46,7 +46,11 @@ public:
         std::cout << "Number of patches: " << s.n_patches << std::endl;
         gpc_stats st;
         check(gpc_get_stats(gpu_, &st));
-        std::cout << "Mean added: " << (s.n_patches ? (double)s.n_bv_total / (double)s.n_patches : 0.0) << std::endl;
+        // gp_compressor.cpp:164-174: running mean and max of gps[i].size() over the patches that received points
+        uint64_t trained = 0;
+        for (int k = 1; k < 33; k++) trained += st.bv_hist[k];
+        std::cout << "Mean added: " << (trained ? (double)s.n_bv_total / (double)trained : 0.0) << std::endl;
+        std::cout << "Max added: " << st.max_bv << std::endl;
     }
     // pointcloud::Ptr load_compressed(), gp_compressor.cpp:267-386
     pointcloud::Ptr load_compressed() {

@@ -92,6 +92,10 @@ typedef struct gpc_stats {
     uint64_t rgb_n_sparse, rgb_n_full, rgb_n_del_cap, rgb_n_del_geo, rgb_sum_n2_common;  /* RGB field GP events */
     float ms_h2d, ms_lattice, ms_keys, ms_sort, ms_leaves, ms_rotation, ms_claim, ms_group,
           ms_shuffle, ms_fit, ms_d2h, ms_predict, ms_total, ms_fit_rgb, ms_evaluate, pad_;
+    /* basis vectors per patch after the last fit of this shard: the largest count ("Max added", gp_compressor.cpp:165-174)
+     * and a histogram -- bv_hist[k] = patches with k basis vectors for k < 32, bv_hist[32] = patches with 32 or more */
+    uint64_t max_bv;
+    uint64_t bv_hist[33];
 } gpc_stats;
 
 /* ---- lifetime ---------------------------------------------------------------------- */

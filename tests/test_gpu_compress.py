@@ -52,6 +52,9 @@ def compare_all(G, O, cloud, decode=True, **cfg):
     for k in ("n_add", "n_first", "n_sparse", "n_full", "n_del_cap", "n_del_geo"):
         assert gs[k] == os_[k], k
     assert h.sizes().rand_offset == o.rand_offset()
+    # "Max added" (gp_compressor.cpp:165-174) and the BV histogram of gpc_stats
+    assert gs["max_bv"] == int(want["nbv"].max(initial=0))
+    assert gs["bv_hist"] == np.bincount(np.minimum(want["nbv"], 32), minlength=33).tolist()
     if decode:
         cloud_o, heights_o = o.decode()
         assert h.decompress_resident() == heights_o.size
