@@ -46,6 +46,7 @@ struct gpc_handle {
     DevBuf tmpA, tmpB, tmpC, lat_state, ev_in, ev_out, size_ids, size_hist, sel_cloud, sel_idx, coarse_hist, fed, forig, cont_q, cont_slots, queueB, handB, r_dumpC, r_dumpQ;
     cudaStream_t stream2 = nullptr;   // side stream: the bucket-1 chain of the largest patches runs beside bucket 0 of the rest
     cudaEvent_t ev_a = nullptr, ev_a2 = nullptr;
+    int32_t* pinned_counts = nullptr;  // 16 pinned host words for asynchronous read-backs of device counters
     // sharded binning (gpc_compress_shard_begin / _finish): this shard's patches are local indices [own_lo, own_hi) of a
     // binning that holds the shard's key range plus its halo; global patch index = local + gshift
     bool shard_mode = false;
@@ -54,6 +55,7 @@ struct gpc_handle {
 
     // binning scratch
     DevBuf cpt;  // 16-byte point records in input order (point_keys_kernel)
+    DevBuf chunk_queue, chunk_hand, chunk_queue1, chunk_hand1;  // second ping-pong pair of the main-stream bucket chain (chain B)
     DevBuf keys, keys2, vals, vals2, ovals, ovals2, sort_tmp, flags64, ex, leaf_of, leaf_start, leaf_code_a, spt, nbr, nnbr,
         center_a, Rm_a, ncand_a, pt0, pt1, pt2, hbuf, rgb, leaf_sums;
     std::vector<cudaEvent_t> ev;
@@ -179,6 +181,67 @@ int run_buckets(gpc_handle* h, SogpArgs& a, int need_ld, int64_t lo, uint64_t* e
     return GPC_OK;
 }
 
+// One chain of buckets advanced ONE LEVEL per call, so that several chains (on different streams) can be walked breadth
+// first: a patch is a strictly sequential recursion, the largest patches climb through several buckets, and the host must not
+// sit in one chain's synchronisation while another chain's next kernel could already be launched.
+struct BucketChain {
+    cudaStream_t st = nullptr;
+    int b = 0;                     // next bucket to launch
+    int64_t work = 0;              // patches of that launch
+    const int32_t* ids = nullptr;  // their ids
+    const double* hand_in = nullptr;
+    DevBuf *q[2] = {nullptr, nullptr}, *hand[2] = {nullptr, nullptr};  // ping-pong overflow queues / hand-off slots of this chain
+    int32_t* qcount = nullptr;     // 8 device counters of this chain
+    int step = 0;
+    bool pending = false;          // a launched bucket whose overflow count has not been read yet
+    int32_t* qn = nullptr;         // pinned host word the count is copied to (a pageable target would make the copy block)
+};
+// launches the chain's next bucket (if any); returns 0 / error.  After it, chain.pending tells whether a count is outstanding.
+int chain_launch(gpc_handle* h, SogpArgs a, int need_ld, int64_t lo, BucketChain& ch) {
+    ch.pending = false;
+    if (ch.b >= 5 || ch.work <= 0) { ch.work = 0; return GPC_OK; }
+    const int bl = sogp_bucket_ld(ch.b);
+    const bool final_bucket = need_ld <= bl;
+    a.spill = nullptr;
+    a.ld = final_bucket ? need_ld : bl;
+    a.patch_ids = ch.ids;
+    a.first_patch = lo;
+    a.n_work = (int)ch.work;
+    DevBuf& q = *ch.q[ch.step & 1];
+    DevBuf& ho = *ch.hand[ch.step & 1];
+    a.queue = nullptr; a.handoff_out = nullptr;
+    a.queue_count = ch.qcount + ch.b;
+    a.handoff_in = ch.hand_in;
+    if (!final_bucket) {
+        CK(q.reserve((size_t)ch.work * sizeof(int32_t)));
+        CK(ho.reserve((size_t)ch.work * sogp_handoff_slot_bytes(ch.b, a.dout)));
+        a.queue = q.as<int32_t>();
+        a.handoff_out = ho.as<double>();
+    }
+    if (ch.b == 4) {
+        CK(h->spill.reserve((size_t)ch.work * sogp_spill_bytes_per_patch()));
+        a.spill = h->spill.as<double>();
+    }
+    CK(launch_sogp_fit(ch.b, a, ch.st));
+    if (final_bucket) { ch.work = 0; return GPC_OK; }
+    CK(cudaMemcpyAsync(ch.qn, ch.qcount + ch.b, sizeof(int32_t), cudaMemcpyDeviceToHost, ch.st));
+    ch.pending = true;
+    return GPC_OK;
+}
+// waits for the outstanding count and moves the chain to its next bucket
+int chain_collect(gpc_handle* h, int dout, uint64_t* escalated, BucketChain& ch) {
+    if (!ch.pending) return GPC_OK;
+    CK(cudaStreamSynchronize(ch.st));
+    ch.pending = false;
+    if (escalated && ch.b < 4) escalated[ch.b] += (uint64_t)*ch.qn;
+    ch.ids = ch.q[ch.step & 1]->as<int32_t>();
+    ch.hand_in = ch.hand[ch.step & 1]->as<double>();
+    ch.work = *ch.qn;
+    ch.b = sogp_next_bucket(ch.b, dout);
+    ch.step++;
+    return GPC_OK;
+}
+
 // Shuffle + SOGP fit of patches [patch_lo, patch_hi) over the stream held in h->off/x1/x2/y.
 // cont: continue the kept state of every patch with the new stream (gpc_add_measurements)
 int run_fit(gpc_handle* h, StageTimer& tm, bool cont = false) {
@@ -259,7 +322,7 @@ int run_fit(gpc_handle* h, StageTimer& tm, bool cont = false) {
     }
     CK(h->queue0.reserve(PLa * sizeof(int32_t)));
     CK(h->queue1.reserve(PLa * sizeof(int32_t)));
-    CK(h->qcount.reserve(8 * sizeof(int32_t)));
+    CK(h->qcount.reserve(64 * sizeof(int32_t)));
     CK(h->kstats.reserve(64 * sizeof(unsigned long long)));   // 16 event counters, then max BV count + histogram (34)
     CK(cudaMemsetAsync(h->kstats.p, 0, 64 * sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(h->qcount.p, 0, 8 * sizeof(int32_t), st));
@@ -284,38 +347,37 @@ int run_fit(gpc_handle* h, StageTimer& tm, bool cont = false) {
         CK(h->size_hist.reserve(1024 * sizeof(int32_t)));
         launch_size_order(h->off.as<int64_t>(), lo, PL, h->size_hist.as<int32_t>(), h->size_ids.as<int32_t>(), st);
         if (need_ld > sogp_bucket_ld(0) && PL >= 4096) {
-            // Patches that outgrow bucket 0 are mostly the large ones, and their bucket-1 kernel runs at low occupancy.
-            // Bucket 0 is therefore launched in two parts that run concurrently (the largest quarter of the patches on a
-            // high-priority side stream); the bucket-1 chain of part A then runs beside the rest of part B, and part B's
-            // (short) chain follows.
-            const int64_t nA = ((PL / 4) + 1) & ~(int64_t)1, nB = PL - nA;
-            CK(h->hand0.reserve((size_t)nA * sogp_handoff_slot_bytes(0, 1)));
-            CK(h->handB.reserve((size_t)nB * sogp_handoff_slot_bytes(0, 1)));
-            CK(h->queueB.reserve((size_t)nB * sizeof(int32_t)));
-            SogpArgs a0 = a;
-            a0.spill = nullptr; a0.ld = sogp_bucket_ld(0); a0.first_patch = lo; a0.handoff_in = nullptr;
-            a0.patch_ids = h->size_ids.as<int32_t>(); a0.n_work = (int)nA;
-            a0.queue = h->queue0.as<int32_t>(); a0.queue_count = h->qcount.as<int32_t>() + 0; a0.handoff_out = h->hand0.as<double>();
-            // part A on the high-priority side stream, part B on the main stream: both start now, A's CTAs are placed first
+            // Patches that outgrow bucket 0 are mostly the large ones, a patch is a strictly sequential recursion, and the
+            // largest ones climb through several buckets: the stage cannot be shorter than the longest such chain.  So the
+            // size-ordered list is cut in two: chain A = the largest 1/32 of the patches on the high-priority side stream (their
+            // bucket-0 part is over quickly, and their continuation in the larger buckets starts while the rest is still in
+            // bucket 0), chain B = the rest on the main stream.  The two chains are advanced breadth first.
+            const int64_t nA = std::max<int64_t>(2368, (PL / 32)) & ~(int64_t)1, nB = PL - nA;
+            CK(h->qcount.reserve(64 * sizeof(int32_t)));
+            CK(cudaMemsetAsync(h->qcount.p, 0, 64 * sizeof(int32_t), st));
+            BucketChain A, B;
+            A.qn = h->pinned_counts; B.qn = h->pinned_counts + 1;
+            A.st = h->stream2; A.b = 0; A.work = nA; A.ids = h->size_ids.as<int32_t>();
+            A.q[0] = &h->queue0; A.q[1] = &h->queue1; A.hand[0] = &h->hand0; A.hand[1] = &h->hand1; A.qcount = h->qcount.as<int32_t>();
+            B.st = st; B.b = 0; B.work = nB; B.ids = h->size_ids.as<int32_t>() + nA;
+            B.q[0] = &h->queueB; B.q[1] = &h->chunk_queue1; B.hand[0] = &h->handB; B.hand[1] = &h->chunk_hand1; B.qcount = h->qcount.as<int32_t>() + 8;
             CK(cudaEventRecord(h->ev_a, st));
             CK(cudaStreamWaitEvent(h->stream2, h->ev_a, 0));
-            CK(launch_sogp_fit(0, a0, h->stream2));
-            a0.patch_ids = h->size_ids.as<int32_t>() + nA; a0.n_work = (int)nB;
-            a0.queue = h->queueB.as<int32_t>(); a0.queue_count = h->qcount.as<int32_t>() + 5; a0.handoff_out = h->handB.as<double>();
-            CK(launch_sogp_fit(0, a0, st));
-            int32_t qnA = 0, qnB = 0;
-            CK(cudaMemcpyAsync(&qnA, h->qcount.as<int32_t>() + 0, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream2));
-            CK(cudaStreamSynchronize(h->stream2));
-            int rc = run_buckets(h, a, need_ld, lo, h->stats.escalated, 1, qnA, h->queue0.as<int32_t>(), h->hand0.as<double>(), 1, h->stream2);
-            if (rc) return rc;
+            int rc;
+            if ((rc = chain_launch(h, a, need_ld, lo, A))) return rc;
+            if ((rc = chain_launch(h, a, need_ld, lo, B))) return rc;
+            while (A.pending || B.pending) {
+                if (A.pending) {
+                    if ((rc = chain_collect(h, 1, h->stats.escalated, A))) return rc;
+                    if ((rc = chain_launch(h, a, need_ld, lo, A))) return rc;
+                }
+                if (B.pending) {
+                    if ((rc = chain_collect(h, 1, h->stats.escalated, B))) return rc;
+                    if ((rc = chain_launch(h, a, need_ld, lo, B))) return rc;
+                }
+            }
             CK(cudaEventRecord(h->ev_a2, h->stream2));
-            CK(cudaMemcpyAsync(&qnB, h->qcount.as<int32_t>() + 5, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            h->stats.escalated[0] += (uint64_t)qnA + (uint64_t)qnB;
             CK(cudaStreamWaitEvent(st, h->ev_a2, 0));
-            CK(cudaMemsetAsync(h->qcount.as<int32_t>() + 1, 0, 4 * sizeof(int32_t), st));
-            rc = run_buckets(h, a, need_ld, lo, h->stats.escalated, 1, qnB, h->queueB.as<int32_t>(), h->handB.as<double>(), 1, st);
-            if (rc) return rc;
         } else {
             int rc = run_buckets(h, a, need_ld, lo, h->stats.escalated, 0, PL, h->size_ids.as<int32_t>(), nullptr);
             if (rc) return rc;
@@ -580,18 +642,21 @@ int run_binning(gpc_handle* h, StageTimer& tm, bool sharded = false) {
         const int which_s = launch_radix_sort(smp, dv, smp2, dv2, m, 3 * depth + 1, h->sort_tmp.p, st);
         CK(h->small.reserve(sizeof(SmallScratch)));
         uint64_t* d_range = h->small.as<SmallScratch>()->key_range;
-        launch_shard_splitters(which_s ? smp2 : smp, m, depth, c.shard_rank, c.shard_count, c.leaf_order, d_range, st);
-        CK(h->flags64.reserve((n + 1) * sizeof(int64_t)));
-        CK(h->ex.reserve((n + 1) * sizeof(int64_t)));
-        CK(h->scan_tmp.reserve(scan_tmp_bytes(n)));
-        launch_shard_select(h->keys.as<uint64_t>(), n, depth, d_range, h->flags64.as<int64_t>(), st);
-        launch_exclusive_scan_i64(h->flags64.as<int64_t>(), h->ex.as<int64_t>(), n, h->scan_tmp.p, st);
-        int64_t n_sel = 0;
-        CK(cudaMemcpyAsync(&n_sel, h->ex.as<int64_t>() + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CK(h->flags64.reserve((m + 1) * sizeof(int64_t)));
+        CK(h->ex.reserve((m + 1) * sizeof(int64_t)));
+        CK(h->scan_tmp.reserve(scan_tmp_bytes(m)));
+        launch_shard_splitters(which_s ? smp2 : smp, m, stride, depth, c.shard_rank, c.shard_count, c.leaf_order, h->flags64.as<int64_t>(),
+                               h->ex.as<int64_t>(), h->scan_tmp.p, d_range, st);
+        // halo test + scan + compaction of the selected records in one pass (sel_cloud / sel_idx sized for the whole cloud)
+        CK(h->sel_cloud.reserve(std::max<int64_t>(n, 1) * GPC_POINT_BYTES));
+        CK(h->sel_idx.reserve(std::max<int64_t>(n, 1) * sizeof(int32_t)));
+        CK(h->scan_tmp.reserve(std::max(shard_select_tmp_bytes(n), scan_tmp_bytes(n))));
+        launch_shard_select_compact(h->keys.as<uint64_t>(), n, depth, d_range, cloud, h->sel_cloud.as<uint8_t>(), h->sel_idx.as<int32_t>(),
+                                    d_nvalid, h->scan_tmp.p, st);
+        unsigned long long nsel_u = 0;
+        CK(cudaMemcpyAsync(&nsel_u, d_nvalid, sizeof(nsel_u), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        CK(h->sel_cloud.reserve(std::max<int64_t>(n_sel, 1) * GPC_POINT_BYTES));
-        CK(h->sel_idx.reserve(std::max<int64_t>(n_sel, 1) * sizeof(int32_t)));
-        launch_shard_compact(cloud, h->ex.as<int64_t>(), n, h->sel_cloud.as<uint8_t>(), h->sel_idx.as<int32_t>(), st);
+        const int64_t n_sel = (int64_t)nsel_u;
         h->n_sel = n_sel;
         h->shard_mode = true;
         cloud = h->sel_cloud.as<uint8_t>();
@@ -770,13 +835,15 @@ int gpc_create(const gpc_config* cfg, gpc_handle** out) {
         if (h->ev_a) cudaEventDestroy(h->ev_a);
         if (h->ev_a2) cudaEventDestroy(h->ev_a2);
         if (h->stream2) cudaStreamDestroy(h->stream2);
+        if (h->pinned_counts) cudaFreeHost(h->pinned_counts);
         cudaStreamDestroy(h->stream);
         delete h;
         return GPC_ERR_CUDA;
     };
     if (cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_a2, cudaEventDisableTiming) != cudaSuccess)
+        cudaEventCreateWithFlags(&h->ev_a2, cudaEventDisableTiming) != cudaSuccess ||
+        cudaHostAlloc(reinterpret_cast<void**>(&h->pinned_counts), 16 * sizeof(int32_t), cudaHostAllocDefault) != cudaSuccess)
         return bail();
     // process-wide jump-ahead tables of the glibc rand() generator: built once, whichever thread creates a handle first
     static RandTables tables;
@@ -797,13 +864,14 @@ void gpc_destroy(gpc_handle* h) {
                       &h->r_alpha0, &h->r_alpha1, &h->r_alpha2, &h->r_b1, &h->r_b2, &h->r_bidx, &h->kstats_rgb, &h->nonempty, &h->slot, &h->out32,
                       &h->heights, &h->quat, &h->mean, &h->rgbmean, &h->Rm, &h->center, &h->code, &h->ncand, &h->owner,
                       &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->lat_state, &h->ev_in, &h->ev_out, &h->size_ids, &h->size_hist, &h->sel_cloud, &h->sel_idx, &h->coarse_hist, &h->fed, &h->forig, &h->cont_q, &h->cont_slots, &h->queueB, &h->handB, &h->r_dumpC, &h->r_dumpQ, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
-                      &h->cpt, &h->ovals2, &h->sort_tmp, &h->flags64, &h->ex, &h->leaf_of, &h->leaf_start, &h->leaf_code_a, &h->spt,
+                      &h->cpt, &h->chunk_queue, &h->chunk_hand, &h->chunk_queue1, &h->chunk_hand1, &h->ovals2, &h->sort_tmp, &h->flags64, &h->ex, &h->leaf_of, &h->leaf_start, &h->leaf_code_a, &h->spt,
                       &h->nbr, &h->nnbr, &h->center_a, &h->Rm_a, &h->ncand_a, &h->pt0, &h->pt1, &h->pt2, &h->hbuf, &h->rgb, &h->leaf_sums};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     if (h->ev_a) cudaEventDestroy(h->ev_a);
     if (h->ev_a2) cudaEventDestroy(h->ev_a2);
     if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+    if (h->pinned_counts) cudaFreeHost(h->pinned_counts);
     cudaStreamDestroy(h->stream);
     delete h;
 }

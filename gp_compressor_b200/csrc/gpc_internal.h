@@ -53,10 +53,13 @@ struct LatticeState {        // device-resident state of the lattice replay
 void launch_lattice_step(const uint8_t* cloud, int64_t n, int64_t tiles_hint, LatticeState* st, cudaStream_t s);
 // sharded binning (k_binning.cu): key sample -> splitters -> halo selection -> compaction -> owned patch range
 void launch_shard_sample(const uint64_t* keys, int64_t n, int64_t stride, int64_t m, uint64_t* sample, uint32_t* dummy, cudaStream_t s);
-void launch_shard_splitters(const uint64_t* sorted, int64_t m, int depth, int rank, int count, int leaf_order, uint64_t* range2,
-                            cudaStream_t s);
+void launch_shard_splitters(const uint64_t* sorted, int64_t m, int64_t stride, int depth, int rank, int count, int leaf_order, int64_t* weight,
+                            int64_t* prefix, void* scan_tmp, uint64_t* range2, cudaStream_t s);
 void launch_shard_select(const uint64_t* keys, int64_t n, int depth, const uint64_t* range2, int64_t* flags, cudaStream_t s);
 void launch_shard_compact(const uint8_t* cloud, const int64_t* ex, int64_t n, uint8_t* sel_cloud, int32_t* sel_idx, cudaStream_t s);
+size_t shard_select_tmp_bytes(int64_t n);
+void launch_shard_select_compact(const uint64_t* keys, int64_t n, int depth, const uint64_t* range2, const uint8_t* cloud, uint8_t* sel_cloud,
+                                 int32_t* sel_idx, unsigned long long* n_sel_out, void* tmp, cudaStream_t s);
 void launch_owned_range(const uint64_t* code, int64_t P, int leaf_order, const uint64_t* range2, int64_t* out2, cudaStream_t s);
 void launch_point_keys(const uint8_t* cloud, int64_t n, const LatticeDev& lat, uint64_t* keys, uint32_t* vals, void* cpt16, cudaStream_t s);
 size_t radix_sort_tmp_bytes(int64_t n);

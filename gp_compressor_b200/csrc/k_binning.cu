@@ -667,24 +667,42 @@ __global__ void __launch_bounds__(256) shard_sample_kernel(const uint64_t* __res
     dummy[i] = 0u;
 }
 
-// range[0..1] = [klo, khi): the key range of `rank` in the visiting order (leaf_order 0 visits keys in descending order)
-__global__ void shard_splitters_kernel(const uint64_t* __restrict__ sorted, int64_t m, int depth3, int rank, int count, int leaf_order,
-                                       uint64_t* __restrict__ range) {
+// Cost weight of every sorted sample: equal keys are adjacent, and the length of the run times the sampling stride estimates
+// the points of that voxel.  A patch is a sequential recursion whose cost per point grows with the points it holds (more
+// points -> more basis vectors -> N^2 work, and a longer chain), so ranges are cut at equal COST, not equal point counts:
+// weight = 256 + estimated points of the voxel (a point in a 2 000-point patch counts 9x a point in a 30-point one).
+__global__ void __launch_bounds__(256) shard_weights_kernel(const uint64_t* __restrict__ sorted, int64_t m, int64_t stride, uint64_t invalid,
+                                                            int64_t* __restrict__ weight) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint64_t k = sorted[i];
+    if (k >= invalid) { weight[i] = 0; return; }
+    int64_t lo = 0, hi = i;        // first index with the same key
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (sorted[mid] < k) lo = mid + 1; else hi = mid; }
+    const int64_t first = lo;
+    lo = i; hi = m;                // first index with a larger key
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (sorted[mid] <= k) lo = mid + 1; else hi = mid; }
+    weight[i] = 256 + (lo - first) * stride;
+}
+// range[0..1] = [klo, khi): the key range of `rank` in the visiting order (leaf_order 0 visits keys in descending order).
+// prefix = exclusive scan of the weights (m + 1 entries): splitter j sits where the cumulative cost reaches j / count of the total.
+__global__ void shard_splitters_kernel(const uint64_t* __restrict__ sorted, const int64_t* __restrict__ prefix, int64_t m, int depth3, int rank,
+                                       int count, int leaf_order, uint64_t* __restrict__ range) {
     const uint64_t invalid = 1ull << depth3;
-    int64_t lo = 0, hi = m;  // number of finite samples
-    while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (sorted[mid] < invalid) lo = mid + 1; else hi = mid;
-    }
-    const int64_t mv = lo;
+    const int64_t total = prefix[m];
     const int ja = leaf_order == 0 ? count - 1 - rank : rank;   // ascending index of the rank's range
     uint64_t k[2];
     for (int e = 0; e < 2; e++) {
         const int j = ja + e;
         if (j <= 0) k[e] = 0;
-        else if (j >= count) k[e] = invalid;
-        else if (mv == 0) k[e] = invalid;
-        else k[e] = (sorted[(mv / count) * j + ((mv % count) * j) / count] >> SHARD_BLOCK_BITS) << SHARD_BLOCK_BITS;
+        else if (j >= count || total == 0) k[e] = invalid;
+        else {
+            const int64_t target = (int64_t)(((__int128)total * j) / count);
+            int64_t lo = 0, hi = m;   // first sample whose prefix reaches the target
+            while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (prefix[mid] < target) lo = mid + 1; else hi = mid; }
+            const int64_t at = lo < m ? lo : m - 1;
+            k[e] = sorted[at] >= invalid ? invalid : (sorted[at] >> SHARD_BLOCK_BITS) << SHARD_BLOCK_BITS;
+        }
     }
     range[0] = k[0];
     range[1] = k[1] < k[0] ? k[0] : k[1];
@@ -727,6 +745,116 @@ __global__ void __launch_bounds__(256) shard_compact_kernel(const uint8_t* __res
     sel_idx[d] = (int32_t)i;
 }
 
+// Sharded binning, one pass over the keys of the whole cloud: halo test, chained scan (decoupled look-back over the tiles)
+// and compaction of the selected PointXYZRGB records.  Replaces shard_select + a three-kernel int64 scan + shard_compact.
+// n_sel_out[0] = number of selected points.
+constexpr int SS_T = 256, SS_ITEMS = 8, SS_TILE = SS_T * SS_ITEMS;
+__global__ void __launch_bounds__(SS_T) shard_select_compact_kernel(const uint64_t* __restrict__ keys, int64_t n, int depth,
+                                                                    const uint64_t* __restrict__ range, const uint8_t* __restrict__ cloud,
+                                                                    uint8_t* __restrict__ sel_cloud, int32_t* __restrict__ sel_idx,
+                                                                    unsigned long long* __restrict__ n_sel_out,
+                                                                    unsigned long long* __restrict__ status, unsigned int* __restrict__ counter) {
+    __shared__ unsigned int tile_s;
+    __shared__ unsigned int wsum[SS_T / 32];
+    __shared__ unsigned long long prefix_s;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) tile_s = atomicAdd(counter, 1u);
+    __syncthreads();
+    const int64_t tile = tile_s;
+    const uint64_t klo = range[0], khi = range[1];
+    const int64_t kmax = (1ll << depth) - 1;
+    // thread t owns the points tile * SS_TILE + r * SS_T + t (coalesced key loads); its rank inside the tile follows the
+    // same order: round-major, so the compacted order is the input order
+    unsigned int sel = 0;   // bit r: point of round r is selected
+#pragma unroll
+    for (int r = 0; r < SS_ITEMS; r++) {
+        const int64_t i = tile * SS_TILE + (int64_t)r * SS_T + t;
+        if (i < n) {
+            const uint64_t k = keys[i];
+            if (!(k >> (3 * depth))) {
+                const int64_t vx = compact3(k >> 2), vy = compact3(k >> 1), vz = compact3(k);
+                int hit = 0;
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    int64_t x = vx + ((c & 4) ? SHARD_HALO : -SHARD_HALO), y = vy + ((c & 2) ? SHARD_HALO : -SHARD_HALO),
+                            z = vz + ((c & 1) ? SHARD_HALO : -SHARD_HALO);
+                    x = x < 0 ? 0 : (x > kmax ? kmax : x);
+                    y = y < 0 ? 0 : (y > kmax ? kmax : y);
+                    z = z < 0 ? 0 : (z > kmax ? kmax : z);
+                    const uint64_t kc = morton((uint32_t)x, (uint32_t)y, (uint32_t)z);
+                    hit |= (kc >= klo && kc < khi) ? 1 : 0;
+                }
+                sel |= (unsigned)hit << r;
+            }
+        }
+    }
+    // per round: ballot gives the warp's selected lanes; round-major exclusive offsets inside the tile
+    unsigned int wcount[SS_ITEMS], below[SS_ITEMS];
+    __shared__ unsigned int rcnt[SS_ITEMS][SS_T / 32];
+#pragma unroll
+    for (int r = 0; r < SS_ITEMS; r++) {
+        const unsigned b = __ballot_sync(0xffffffffu, (sel >> r) & 1u);
+        wcount[r] = __popc(b);
+        below[r] = __popc(b & ((1u << lane) - 1u));
+        if (lane == 0) rcnt[r][w] = wcount[r];
+    }
+    __syncthreads();
+    // offsets of (round r, warp w) in round-major order; the tile total
+    unsigned int base[SS_ITEMS], total = 0;
+#pragma unroll
+    for (int r = 0; r < SS_ITEMS; r++) {
+        unsigned int acc = total;
+#pragma unroll
+        for (int ww = 0; ww < SS_T / 32; ww++) {
+            if (ww == w) base[r] = acc;
+            acc += rcnt[r][ww];
+        }
+        total = acc;
+    }
+    constexpr unsigned long long AGG = 1ull << 62, INCL = 2ull << 62, MASK = (1ull << 62) - 1;
+    if (w == 0) {
+        unsigned long long excl = 0;
+        if (tile == 0) {
+            if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&status[0]) = INCL | total;
+        } else {
+            if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&status[tile]) = AGG | total;
+            for (int64_t j = tile - 1;; j -= 32) {
+                const int64_t idx = j - lane;
+                unsigned long long sw = INCL;
+                if (idx >= 0) {
+                    do { sw = *reinterpret_cast<volatile const unsigned long long*>(&status[idx]); } while ((sw >> 62) == 0ull);
+                }
+                const unsigned incl = __ballot_sync(0xffffffffu, (sw & INCL) != 0ull);
+                const int stop = incl ? (__ffs(incl) - 1) : 31;
+                unsigned long long v = (lane <= stop) ? (sw & MASK) : 0ull;
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                excl += v;
+                if (incl) break;
+            }
+            if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&status[tile]) = INCL | (excl + total);
+        }
+        if (lane == 0) {
+            prefix_s = excl;
+            if ((tile + 1) * SS_TILE >= n) n_sel_out[0] = excl + total;
+        }
+    }
+    __syncthreads();
+    const int64_t pre = (int64_t)prefix_s;
+#pragma unroll
+    for (int r = 0; r < SS_ITEMS; r++) {
+        if ((sel >> r) & 1u) {
+            const int64_t i = tile * SS_TILE + (int64_t)r * SS_T + t;
+            const int64_t d = pre + base[r] + below[r];
+            const float4* src = reinterpret_cast<const float4*>(cloud + i * GPC_POINT_BYTES);
+            float4* dst = reinterpret_cast<float4*>(sel_cloud + d * GPC_POINT_BYTES);
+            dst[0] = src[0];
+            dst[1] = src[1];
+            sel_idx[d] = (int32_t)i;
+        }
+    }
+}
+
 // patches are in visiting order: out[0] = first patch inside the key range, out[1] = first patch behind it
 __global__ void owned_range_kernel(const uint64_t* __restrict__ code, int64_t P, int leaf_order, const uint64_t* __restrict__ range,
                                    int64_t* __restrict__ out) {
@@ -749,10 +877,13 @@ void launch_shard_sample(const uint64_t* keys, int64_t n, int64_t stride, int64_
     shard_sample_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(keys, n, stride, m, sample, dummy);
     g_launches++;
 }
-void launch_shard_splitters(const uint64_t* sorted, int64_t m, int depth, int rank, int count, int leaf_order, uint64_t* range2,
-                            cudaStream_t s) {
-    shard_splitters_kernel<<<1, 1, 0, s>>>(sorted, m, 3 * depth, rank, count, leaf_order, range2);
-    g_launches++;
+// weight / prefix: m + 1 int64 each; scan_tmp >= scan_tmp_bytes(m)
+void launch_shard_splitters(const uint64_t* sorted, int64_t m, int64_t stride, int depth, int rank, int count, int leaf_order, int64_t* weight,
+                            int64_t* prefix, void* scan_tmp, uint64_t* range2, cudaStream_t s) {
+    shard_weights_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(sorted, m, stride, 1ull << (3 * depth), weight);
+    launch_exclusive_scan_i64(weight, prefix, m, scan_tmp, s);
+    shard_splitters_kernel<<<1, 1, 0, s>>>(sorted, prefix, m, 3 * depth, rank, count, leaf_order, range2);
+    g_launches += 2;
 }
 void launch_shard_select(const uint64_t* keys, int64_t n, int depth, const uint64_t* range2, int64_t* flags, cudaStream_t s) {
     if (n <= 0) return;
@@ -762,6 +893,19 @@ void launch_shard_select(const uint64_t* keys, int64_t n, int depth, const uint6
 void launch_shard_compact(const uint8_t* cloud, const int64_t* ex, int64_t n, uint8_t* sel_cloud, int32_t* sel_idx, cudaStream_t s) {
     if (n <= 0) return;
     shard_compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cloud, ex, n, sel_cloud, sel_idx);
+    g_launches++;
+}
+size_t shard_select_tmp_bytes(int64_t n) { return (size_t)((n + SS_TILE - 1) / SS_TILE + 4) * sizeof(unsigned long long); }
+// n_sel_out: one device counter; tmp >= shard_select_tmp_bytes(n); sel_cloud / sel_idx sized for n points
+void launch_shard_select_compact(const uint64_t* keys, int64_t n, int depth, const uint64_t* range2, const uint8_t* cloud, uint8_t* sel_cloud,
+                                 int32_t* sel_idx, unsigned long long* n_sel_out, void* tmp, cudaStream_t s) {
+    cudaMemsetAsync(n_sel_out, 0, sizeof(unsigned long long), s);
+    if (n <= 0) return;
+    cudaMemsetAsync(tmp, 0, shard_select_tmp_bytes(n), s);
+    unsigned long long* status = reinterpret_cast<unsigned long long*>(tmp) + 2;
+    unsigned int* counter = reinterpret_cast<unsigned int*>(tmp);
+    shard_select_compact_kernel<<<(unsigned)((n + SS_TILE - 1) / SS_TILE), SS_T, 0, s>>>(keys, n, depth, range2, cloud, sel_cloud, sel_idx, n_sel_out,
+                                                                                        status, counter);
     g_launches++;
 }
 void launch_owned_range(const uint64_t* code, int64_t P, int leaf_order, const uint64_t* range2, int64_t* out2, cudaStream_t s) {

@@ -24,6 +24,7 @@
 // writes its complete state (N, next point, counters, alpha, BV, C, Q) to a hand-off slot and
 // queues the patch; the next bucket's kernel resumes from that state — no work is redone
 // and the arithmetic is the same in every bucket.
+#include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 
@@ -688,12 +689,13 @@ __device__ __forceinline__ double row4_padded(const double* row, const double* k
     return __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
 }
 
-__global__ void __launch_bounds__(64, 10) sogp_fit_pair_kernel(SogpArgs a) {
-    __shared__ __align__(16) PairSmem sm;
+// one patch of the bucket-1 work list (work = position in the list / the hand-off slot array)
+__device__ __forceinline__ void pair_patch(const SogpArgs& a, PairSmem& sm, const int work) {
+
     const int t = threadIdx.x, lane = t & 31, mat = t >> 5;
     double* const Mown = mat ? sm.Q : sm.C;
     double* const Mrow = Mown + lane * P_LD;
-    const int64_t patch = a.patch_ids ? (int64_t)a.patch_ids[blockIdx.x] : a.first_patch + blockIdx.x;
+    const int64_t patch = a.patch_ids ? (int64_t)a.patch_ids[work] : a.first_patch + work;
     const int64_t o = a.off[patch];
     const int n = (int)(a.off[patch + 1] - o);
     const int64_t op = patch - a.out_first;
@@ -712,7 +714,7 @@ __global__ void __launch_bounds__(64, 10) sogp_fit_pair_kernel(SogpArgs a) {
     int N = 0, tt0 = 0;
     unsigned int run = 0;
     if (a.handoff_in) {  // resume a patch that outgrew bucket 0 (slots hold W_N x W_N column-major matrices)
-        const double* slot = a.handoff_in + (size_t)blockIdx.x * slot_doubles(W_N);
+        const double* slot = a.handoff_in + (size_t)work * slot_doubles(W_N);
         N = reinterpret_cast<const int*>(slot)[0];
         tt0 = reinterpret_cast<const int*>(slot)[1];
         if (t < NCNT) sm.cnt[t] = reinterpret_cast<const unsigned long long*>(slot + 2)[t];
@@ -981,6 +983,10 @@ __global__ void __launch_bounds__(64, 10) sogp_fit_pair_kernel(SogpArgs a) {
             a.dumpQ[od + e] = sm.Q[i * P_LD + j];
         }
     }
+}
+__global__ void __launch_bounds__(64, 10) sogp_fit_pair_kernel(SogpArgs a) {
+    __shared__ __align__(16) PairSmem sm;
+    pair_patch(a, sm, (int)blockIdx.x);
 }
 
 // =====================================================================================

@@ -182,7 +182,8 @@ __global__ void patch_of_kernel(const int64_t* __restrict__ off, int64_t n_patch
 //  * n <= SHUF_SMEM_MAX: one warp per patch, index array and r_i = draw_i % i in shared memory; every lane
 //    computes its share of the modulos, lane 0 walks the (inherently serial) swap chain at shared-memory latency;
 //  * larger patches: one thread per patch, swaps in global memory.
-constexpr int SHUF_SMEM_MAX = 1024;
+constexpr int SHUF_SMEM_MAX = 1024;    // per-patch limit of the separate shuffle_warp_kernel (32-bit indices)
+constexpr int SHUF_FUSED_MAX = 8192;   // per-patch limit of the fused shuffle + gather kernel (16-bit indices, <= 32 KB)
 
 __global__ void __launch_bounds__(32) shuffle_warp_kernel(const int64_t* __restrict__ off, int64_t n_patches,
                                                           const int64_t* __restrict__ roff, const uint32_t* __restrict__ rnd,
@@ -354,33 +355,36 @@ __global__ void forig_kernel(const int32_t* __restrict__ patch_of, const int32_t
 // Fused shuffle + gather for patches of up to SHUF_SMEM_MAX points (the common case): the permutation never leaves
 // shared memory before the fit streams are written in add order.  RGB: the field GP's own shuffle (the draws after the
 // patch's first n - 1) and its colour stream centred on the patch mean (p.second -= c_mn, gp_compressor.cpp:105).
+// cap: capacity of the index arrays (16-bit entries in dynamic shared memory: ind[cap], rr[cap]); patches of more than cap
+// points are left to the global-memory kernels.
 template <bool RGB>
-__global__ void __launch_bounds__(32) shuffle_gather_warp_kernel(ShuffleGatherArgs a) {
-    __shared__ int ind[SHUF_SMEM_MAX];
-    __shared__ int rr[SHUF_SMEM_MAX];
+__global__ void __launch_bounds__(32) shuffle_gather_warp_kernel(ShuffleGatherArgs a, int cap) {
+    extern __shared__ unsigned short shuf_smem[];
+    unsigned short* const ind = shuf_smem;
+    unsigned short* const rr = shuf_smem + cap;
     const int64_t p = blockIdx.x;
     const int lane = threadIdx.x;
     const int64_t o = a.off[p];
     const int n = (int)(a.off[p + 1] - o);
-    if (n == 0) return;
+    if (n == 0 || n > cap) return;
     if (a.do_shuffle && n >= 2) {
         const uint32_t* r = a.rnd + (a.roff[p] - a.roff[0]) + (RGB ? (n - 1) : 0);
         for (int i = lane; i < n; i += 32) {
-            ind[i] = i;
-            if (i > 0) rr[i] = (int)(r[n - 1 - i] % (uint32_t)i);
+            ind[i] = (unsigned short)i;
+            if (i > 0) rr[i] = (unsigned short)(r[n - 1 - i] % (uint32_t)i);
         }
         __syncwarp();
         if (lane == 0) {
             for (int i = n - 1; i > 0; --i) {
                 const int j = rr[i];
-                const int x = ind[i], y = ind[j];
+                const unsigned short x = ind[i], y = ind[j];
                 ind[i] = y;
                 ind[j] = x;
             }
         }
         __syncwarp();
     } else {
-        for (int i = lane; i < n; i += 32) ind[i] = i;
+        for (int i = lane; i < n; i += 32) ind[i] = (unsigned short)i;
         __syncwarp();
     }
     double m0 = 0.0, m1 = 0.0, m2 = 0.0;
@@ -407,9 +411,13 @@ __global__ void __launch_bounds__(32) shuffle_gather_warp_kernel(ShuffleGatherAr
 // SHUF_SMEM_MAX points (rare) take the separate global-memory kernels.
 void launch_shuffle_gather(const ShuffleGatherArgs& a, int64_t max_patch_points, int32_t* patch_of, cudaStream_t s) {
     if (a.s_count <= 0 || a.n_patches <= 0) return;
-    if (max_patch_points <= SHUF_SMEM_MAX) {
-        if (a.is_rgb) shuffle_gather_warp_kernel<true><<<(unsigned)a.n_patches, 32, 0, s>>>(a);
-        else shuffle_gather_warp_kernel<false><<<(unsigned)a.n_patches, 32, 0, s>>>(a);
+    if (max_patch_points <= SHUF_FUSED_MAX) {
+        // index arrays sized for the largest patch of the call: 4 KB for the common case (32 CTAs / SM), up to 32 KB
+        int cap = 1024;
+        while (cap < max_patch_points) cap *= 2;
+        const size_t smem = (size_t)cap * 2 * sizeof(unsigned short);
+        if (a.is_rgb) shuffle_gather_warp_kernel<true><<<(unsigned)a.n_patches, 32, smem, s>>>(a, cap);
+        else shuffle_gather_warp_kernel<false><<<(unsigned)a.n_patches, 32, smem, s>>>(a, cap);
         g_launches++;
         return;
     }
