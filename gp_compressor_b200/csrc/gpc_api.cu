@@ -352,7 +352,7 @@ int run_fit(gpc_handle* h, StageTimer& tm, bool cont = false) {
             // size-ordered list is cut in two: chain A = the largest 1/32 of the patches on the high-priority side stream (their
             // bucket-0 part is over quickly, and their continuation in the larger buckets starts while the rest is still in
             // bucket 0), chain B = the rest on the main stream.  The two chains are advanced breadth first.
-            const int64_t nA = std::max<int64_t>(2368, (PL / 32)) & ~(int64_t)1, nB = PL - nA;
+            const int64_t nA = std::min<int64_t>(PL, std::max<int64_t>(2368, (PL / 32))) & ~(int64_t)1, nB = PL - nA;   // 1/4 .. 1/32: within noise on C2 / C5
             CK(h->qcount.reserve(64 * sizeof(int32_t)));
             CK(cudaMemsetAsync(h->qcount.p, 0, 64 * sizeof(int32_t), st));
             BucketChain A, B;

@@ -667,22 +667,16 @@ __global__ void __launch_bounds__(256) shard_sample_kernel(const uint64_t* __res
     dummy[i] = 0u;
 }
 
-// Cost weight of every sorted sample: equal keys are adjacent, and the length of the run times the sampling stride estimates
-// the points of that voxel.  A patch is a sequential recursion whose cost per point grows with the points it holds (more
-// points -> more basis vectors -> N^2 work, and a longer chain), so ranges are cut at equal COST, not equal point counts:
-// weight = 256 + estimated points of the voxel (a point in a 2 000-point patch counts 9x a point in a 30-point one).
+// Weight of every sorted sample for the range cut.  Measured on C5 (profiles/r2_strong_scaling.md): cutting at equal COST
+// (weight growing with the points of the sample's voxel, estimated from the run of equal keys) moved a third of the points
+// off the ranks that own the dense core and did not shorten their fit -- they are bound by the sequential recursion of
+// their ~20 largest patches (2 000+ points, 40+ basis vectors), not by throughput -- while the halo of their neighbours
+// grew.  So the ranges are cut at equal point counts: weight 1 per finite sample.
 __global__ void __launch_bounds__(256) shard_weights_kernel(const uint64_t* __restrict__ sorted, int64_t m, int64_t stride, uint64_t invalid,
                                                             int64_t* __restrict__ weight) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
-    const uint64_t k = sorted[i];
-    if (k >= invalid) { weight[i] = 0; return; }
-    int64_t lo = 0, hi = i;        // first index with the same key
-    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (sorted[mid] < k) lo = mid + 1; else hi = mid; }
-    const int64_t first = lo;
-    lo = i; hi = m;                // first index with a larger key
-    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (sorted[mid] <= k) lo = mid + 1; else hi = mid; }
-    weight[i] = 256 + (lo - first) * stride;
+    weight[i] = sorted[i] < invalid ? 1 : 0;
 }
 // range[0..1] = [klo, khi): the key range of `rank` in the visiting order (leaf_order 0 visits keys in descending order).
 // prefix = exclusive scan of the weights (m + 1 entries): splitter j sits where the cumulative cost reaches j / count of the total.
