@@ -594,16 +594,10 @@ int run_binning(gpc_handle* h, StageTimer& tm, bool sharded = false) {
     L0.best = ~0ull;
     CK(cudaMemcpyAsync(h->lat_state.p, &L0, sizeof(L0), cudaMemcpyHostToDevice, st));
     LatticeState Lh = L0;
-    int64_t start = 0;
-    for (;;) {
-        // six growth events per round trip; once nothing violates the box the remaining steps are no-ops
-        for (int k = 0; k < 6; k++) launch_lattice_step(cloud, n, n - start, h->lat_state.as<LatticeState>(), st);
-        CK(cudaMemcpyAsync(&Lh, h->lat_state.p, sizeof(Lh), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if (Lh.lat.depth > 21) return fail(h, GPC_ERR_OVERFLOW, "octree deeper than 21 levels: res too small for the cloud extent");
-        if (!Lh.found) break;
-        start = Lh.start;
-    }
+    if (n > 0) CK(launch_lattice_replay(cloud, n, h->lat_state.as<LatticeState>(), st));
+    CK(cudaMemcpyAsync(&Lh, h->lat_state.p, sizeof(Lh), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (Lh.defined && Lh.lat.depth > 21) return fail(h, GPC_ERR_OVERFLOW, "octree deeper than 21 levels: res too small for the cloud extent");
     struct { unsigned depth; bool defined; double mn[3]; } L;
     L.depth = Lh.lat.depth;
     L.defined = Lh.defined != 0;

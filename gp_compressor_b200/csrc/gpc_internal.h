@@ -49,8 +49,7 @@ struct LatticeState {        // device-resident state of the lattice replay
     int32_t defined;         // PCL bounding_box_defined_
     int32_t found;           // 1 if the last step adopted a point
 };
-// searches points [st->start, n) (tiles_hint = how many points can still matter) and grows the box for the first violator
-void launch_lattice_step(const uint8_t* cloud, int64_t n, int64_t tiles_hint, LatticeState* st, cudaStream_t s);
+cudaError_t launch_lattice_replay(const uint8_t* cloud, int64_t n, LatticeState* st, cudaStream_t s);  // whole replay, one cooperative launch
 // sharded binning (k_binning.cu): key sample -> splitters -> halo selection -> compaction -> owned patch range
 void launch_shard_sample(const uint64_t* keys, int64_t n, int64_t stride, int64_t m, uint64_t* sample, uint32_t* dummy, cudaStream_t s);
 void launch_shard_splitters(const uint64_t* sorted, int64_t m, int64_t stride, int depth, int rank, int count, int leaf_order, int64_t* weight,

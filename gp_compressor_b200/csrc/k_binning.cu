@@ -14,8 +14,12 @@
 //   claim     : owner(p) = first leaf in visiting order that has p in its candidate list
 //               and accepts it in the box test (the occupied_indices greedy loop, :80-89)
 //   group     : stable sort by owner; per-patch mean height / colour and frame outputs
+#include <cooperative_groups.h>
+
 #include "gpc_device.cuh"
 #include "gpc_internal.h"
+
+namespace cg = cooperative_groups;
 
 namespace gpc {
 
@@ -52,41 +56,10 @@ __device__ __forceinline__ uint64_t morton(uint32_t kx, uint32_t ky, uint32_t kz
 // the cloud for the first finite point at index >= state.start that violates [mn, mx) (or any finite point while
 // the box is undefined); (2) one thread grows the box for that point exactly as PCL does [RECALLED PCL 1.7:
 // adoptBoundingBoxToPoint / getKeyBitSize] and advances state.start.  The host only polls state.best.
-__global__ void __launch_bounds__(256) first_violation_kernel(const uint8_t* __restrict__ cloud, int64_t n, LatticeState* __restrict__ st) {
-    __shared__ unsigned long long sbest;
-    __shared__ int skip;
-    const int64_t start = st->start;
-    const int64_t tile = (int64_t)blockIdx.x * 4096;
-    if (threadIdx.x == 0) {
-        sbest = ~0ull;
-        skip = (start >= n - tile) || (unsigned long long)(start + tile) >= *(volatile unsigned long long*)&st->best;  // an earlier hit exists
-    }
-    __syncthreads();
-    if (skip) return;
-    const int defined = st->defined;
-    const double mn0 = st->lat.mn[0], mn1 = st->lat.mn[1], mn2 = st->lat.mn[2];
-    const double mx0 = st->lat.mx[0], mx1 = st->lat.mx[1], mx2 = st->lat.mx[2];
-    unsigned long long mine = ~0ull;
-    for (int r = 0; r < 16; r++) {
-        int64_t i = start + tile + r * 256 + threadIdx.x;
-        if (i >= n) break;
-        const float4 p = *reinterpret_cast<const float4*>(cloud + i * GPC_POINT_BYTES);
-        if (!finite3(p.x, p.y, p.z)) continue;
-        bool hit = !defined;
-        if (defined) {
-            const double x = p.x, y = p.y, z = p.z;
-            hit = x < mn0 || y < mn1 || z < mn2 || x >= mx0 || y >= mx1 || z >= mx2;
-        }
-        if (hit) { mine = (unsigned long long)i; break; }
-    }
-    if (mine != ~0ull) atomicMin(&sbest, mine);
-    __syncthreads();
-    if (threadIdx.x == 0 && sbest != ~0ull) atomicMin(&st->best, sbest);
-}
-
-__global__ void lattice_adopt_kernel(const uint8_t* __restrict__ cloud, LatticeState* __restrict__ st) {
+__device__ void lattice_adopt(const uint8_t* __restrict__ cloud, LatticeState* __restrict__ st) {
     if (st->defined && st->lat.depth > 21) {  // the host rejects this cloud; do not grow further
         st->start = 0x7fffffffffffffffLL;
+        st->found = 0;
         return;
     }
     const unsigned long long b = st->best;
@@ -642,13 +615,112 @@ __global__ void __launch_bounds__(128) patch_frames_kernel(const int64_t* __rest
 
 }  // namespace
 
-// one growth event of the lattice replay (search + adopt); st->found tells the host whether anything happened
-void launch_lattice_step(const uint8_t* cloud, int64_t n, int64_t tiles_hint, LatticeState* st, cudaStream_t s) {
-    int64_t tiles = (tiles_hint + 4095) / 4096;
-    if (tiles < 1) tiles = 1;
-    first_violation_kernel<<<(unsigned)tiles, 256, 0, s>>>(cloud, n, st);
-    lattice_adopt_kernel<<<1, 1, 0, s>>>(cloud, st);
-    g_launches += 2;
+// The whole replay in ONE cooperative launch: search for the first violator behind state.start (every CTA walks tiles of
+// 4096 points in index order and stops behind the best hit so far), grid barrier, one thread grows the box, grid barrier,
+// until no point violates the box.  A cloud costs about one pass over its points plus two grid barriers per growth event
+// (~depth + 2 events); the host reads the final state once.
+__global__ void __launch_bounds__(256) lattice_replay_kernel(const uint8_t* __restrict__ cloud, int64_t n, LatticeState* st) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ unsigned long long sbest;
+    __shared__ int sskip;
+    // Growth events cluster at the head of the cloud (the k-th event needs ~2^k points to show up): CTA 0 replays the first
+    // LOCAL_W points on its own, event by event, without grid barriers; the grid-wide search handles the few events behind.
+    constexpr int64_t LOCAL_W = 8192;
+    if (blockIdx.x == 0) {
+        const int64_t end = n < LOCAL_W ? n : LOCAL_W;
+        for (;;) {
+            const int64_t pos = *reinterpret_cast<volatile int64_t*>(&st->start);
+            if (pos >= end) break;
+            const int defined = *reinterpret_cast<volatile int32_t*>(&st->defined);
+            const volatile double* vmn = st->lat.mn;
+            const volatile double* vmx = st->lat.mx;
+            const double mn0 = vmn[0], mn1 = vmn[1], mn2 = vmn[2], mx0 = vmx[0], mx1 = vmx[1], mx2 = vmx[2];
+            if (threadIdx.x == 0) sbest = ~0ull;
+            __syncthreads();
+            for (int64_t i = pos + threadIdx.x; i < end; i += 256) {
+                const float4 p = *reinterpret_cast<const float4*>(cloud + i * GPC_POINT_BYTES);
+                if (!finite3(p.x, p.y, p.z)) continue;
+                bool hit = !defined;
+                if (defined) {
+                    const double x = p.x, y = p.y, z = p.z;
+                    hit = x < mn0 || y < mn1 || z < mn2 || x >= mx0 || y >= mx1 || z >= mx2;
+                }
+                if (hit) { atomicMin(&sbest, (unsigned long long)i); break; }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                if (sbest == ~0ull) {
+                    st->start = end;            // the window is clean
+                } else {
+                    st->best = sbest;
+                    lattice_adopt(cloud, st);   // grows the box, start = best + 1, best = none
+                }
+                __threadfence();
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) { st->best = ~0ull; __threadfence(); }
+    }
+    grid.sync();
+    for (;;) {
+        const int64_t start = *reinterpret_cast<volatile int64_t*>(&st->start);
+        if (start >= n) break;   // nothing left (or the octree is too deep: the host rejects the cloud)
+        const int defined = *reinterpret_cast<volatile int32_t*>(&st->defined);
+        const volatile double* vmn = st->lat.mn;   // written by the adopting thread between two grid barriers
+        const volatile double* vmx = st->lat.mx;
+        const double mn0 = vmn[0], mn1 = vmn[1], mn2 = vmn[2];
+        const double mx0 = vmx[0], mx1 = vmx[1], mx2 = vmx[2];
+        for (int64_t tile = (int64_t)blockIdx.x * 4096; start + tile < n; tile += (int64_t)gridDim.x * 4096) {
+            // one thread decides for the CTA (best changes under our feet: every thread must take the same branch)
+            if (threadIdx.x == 0) {
+                sskip = (unsigned long long)(start + tile) >= *reinterpret_cast<volatile unsigned long long*>(&st->best);  // an earlier hit exists
+                sbest = ~0ull;
+            }
+            __syncthreads();
+            if (sskip) break;
+            unsigned long long mine = ~0ull;
+            for (int r = 0; r < 16; r++) {
+                const int64_t i = start + tile + r * 256 + threadIdx.x;
+                if (i >= n) break;
+                const float4 p = *reinterpret_cast<const float4*>(cloud + i * GPC_POINT_BYTES);
+                if (!finite3(p.x, p.y, p.z)) continue;
+                bool hit = !defined;
+                if (defined) {
+                    const double x = p.x, y = p.y, z = p.z;
+                    hit = x < mn0 || y < mn1 || z < mn2 || x >= mx0 || y >= mx1 || z >= mx2;
+                }
+                if (hit) { mine = (unsigned long long)i; break; }
+            }
+            if (mine != ~0ull) atomicMin(&sbest, mine);
+            __syncthreads();
+            const bool found = sbest != ~0ull;
+            if (threadIdx.x == 0 && found) atomicMin(&st->best, sbest);
+            __syncthreads();
+            if (found) break;   // later tiles of this CTA lie behind the hit
+        }
+        __threadfence();
+        grid.sync();
+        if (blockIdx.x == 0 && threadIdx.x == 0) { lattice_adopt(cloud, st); __threadfence(); }
+        grid.sync();
+        if (!*reinterpret_cast<volatile int32_t*>(&st->found)) break;
+    }
+}
+
+// the lattice replay of one cloud; the final LatticeState is read by the caller
+cudaError_t launch_lattice_replay(const uint8_t* cloud, int64_t n, LatticeState* st, cudaStream_t s) {
+    static int max_blocks = 0;
+    if (!max_blocks) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lattice_replay_kernel, 256, 0);
+        max_blocks = sms * std::max(1, std::min(per_sm, 4));
+    }
+    const int64_t tiles = std::max<int64_t>(1, (n + 4095) / 4096);
+    const unsigned grid = (unsigned)std::min<int64_t>(tiles, max_blocks);
+    void* args[] = {(void*)&cloud, (void*)&n, (void*)&st};
+    g_launches++;
+    return cudaLaunchCooperativeKernel((const void*)lattice_replay_kernel, dim3(grid), dim3(256), args, 0, s);
 }
 
 // ---- sharded binning (strong scaling of one cloud) -------------------------------------------------
