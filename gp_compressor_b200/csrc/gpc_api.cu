@@ -43,9 +43,10 @@ struct gpc_handle {
     DevBuf perm_rgb, fcr, fcg, fcb, r_nbv, r_flags, r_alpha0, r_alpha1, r_alpha2, r_b1, r_b2, r_bidx, kstats_rgb;
     bool have_rgb = false;
     DevBuf quat, mean, rgbmean, Rm, center, code, ncand, owner, st_idx;
-    DevBuf tmpA, tmpB, tmpC, lat_state, ev_in, ev_out, size_ids, size_hist, sel_cloud, sel_idx, coarse_hist, fed, forig, cont_q, cont_slots, queueB, handB, r_dumpC, r_dumpQ;
-    cudaStream_t stream2 = nullptr;   // side stream: the bucket-1 chain of the largest patches runs beside bucket 0 of the rest
-    cudaEvent_t ev_a = nullptr, ev_a2 = nullptr;
+    DevBuf tmpA, tmpB, tmpC, lat_state, ev_in, ev_out, size_ids, size_hist, sel_cloud, sel_idx, coarse_hist, fed, forig, cont_q, cont_slots, queueB, handB, queueC0, queueC1, handC0, handC1, r_dumpC, r_dumpQ;
+    cudaStream_t stream2 = nullptr;   // side streams: the bucket chains of the larger patches run beside bucket 0 of the rest
+    cudaStream_t stream3 = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_a2 = nullptr, ev_a3 = nullptr;
     int32_t* pinned_counts = nullptr;  // 16 pinned host words for asynchronous read-backs of device counters
     // sharded binning (gpc_compress_shard_begin / _finish): this shard's patches are local indices [own_lo, own_hi) of a
     // binning that holds the shard's key range plus its halo; global patch index = local + gshift
@@ -347,37 +348,49 @@ int run_fit(gpc_handle* h, StageTimer& tm, bool cont = false) {
         CK(h->size_hist.reserve(1024 * sizeof(int32_t)));
         launch_size_order(h->off.as<int64_t>(), lo, PL, h->size_hist.as<int32_t>(), h->size_ids.as<int32_t>(), st);
         if (need_ld > sogp_bucket_ld(0) && PL >= 4096) {
-            // Patches that outgrow bucket 0 are mostly the large ones, a patch is a strictly sequential recursion, and the
-            // largest ones climb through several buckets: the stage cannot be shorter than the longest such chain.  So the
-            // size-ordered list is cut in two: chain A = the largest 1/32 of the patches on the high-priority side stream (their
-            // bucket-0 part is over quickly, and their continuation in the larger buckets starts while the rest is still in
-            // bucket 0), chain B = the rest on the main stream.  The two chains are advanced breadth first.
-            const int64_t nA = std::min<int64_t>(PL, std::max<int64_t>(2368, (PL / 32))) & ~(int64_t)1, nB = PL - nA;   // 1/4 .. 1/32: within noise on C2 / C5
+            // A patch is a strictly sequential recursion, the patches that outgrow bucket 0 continue in the two-warp kernel (and
+            // the largest climb further), and a continuation can only be launched when the kernel that handed it off has ended:
+            // run as one chain, the stage would end with the continuations of the whole cloud after the last bucket-0 block.
+            // So the size-ordered list (largest first) is cut in three chains on three streams, advanced breadth first:
+            //   A  = the largest patches (1/32, at least one wave of 8 warps per SM): longest continuations, started first;
+            //   B1 = the next ones up to 3/5 of the list (about three quarters of the points): their continuations run beside
+            //        bucket 0 of B2 instead of after it;
+            //   B2 = the small patches on the main stream: what it hands off has few points left, so the tail is short.
+            const int64_t nA = std::min<int64_t>(PL, std::max<int64_t>(2368, (PL / 32))) & ~(int64_t)1;
+            const int64_t nB1 = std::max<int64_t>(0, (PL * 3 / 5 - nA)) & ~(int64_t)1;   // cut at 0.5 .. 0.7 of the list: within noise on C2
+            const int64_t nB2 = PL - nA - nB1;
             CK(h->qcount.reserve(64 * sizeof(int32_t)));
             CK(cudaMemsetAsync(h->qcount.p, 0, 64 * sizeof(int32_t), st));
-            BucketChain A, B;
-            A.qn = h->pinned_counts; B.qn = h->pinned_counts + 1;
-            A.st = h->stream2; A.b = 0; A.work = nA; A.ids = h->size_ids.as<int32_t>();
-            A.q[0] = &h->queue0; A.q[1] = &h->queue1; A.hand[0] = &h->hand0; A.hand[1] = &h->hand1; A.qcount = h->qcount.as<int32_t>();
-            B.st = st; B.b = 0; B.work = nB; B.ids = h->size_ids.as<int32_t>() + nA;
-            B.q[0] = &h->queueB; B.q[1] = &h->chunk_queue1; B.hand[0] = &h->handB; B.hand[1] = &h->chunk_hand1; B.qcount = h->qcount.as<int32_t>() + 8;
+            BucketChain ch[3];
+            const int32_t* ids = h->size_ids.as<int32_t>();
+            ch[0].st = h->stream2; ch[0].work = nA; ch[0].ids = ids;
+            ch[0].q[0] = &h->queue0; ch[0].q[1] = &h->queue1; ch[0].hand[0] = &h->hand0; ch[0].hand[1] = &h->hand1;
+            ch[1].st = h->stream3; ch[1].work = nB1; ch[1].ids = ids + nA;
+            ch[1].q[0] = &h->queueC0; ch[1].q[1] = &h->queueC1; ch[1].hand[0] = &h->handC0; ch[1].hand[1] = &h->handC1;
+            ch[2].st = st; ch[2].work = nB2; ch[2].ids = ids + nA + nB1;
+            ch[2].q[0] = &h->queueB; ch[2].q[1] = &h->chunk_queue1; ch[2].hand[0] = &h->handB; ch[2].hand[1] = &h->chunk_hand1;
+            for (int i = 0; i < 3; i++) { ch[i].b = 0; ch[i].qn = h->pinned_counts + i; ch[i].qcount = h->qcount.as<int32_t>() + 8 * i; }
             CK(cudaEventRecord(h->ev_a, st));
             CK(cudaStreamWaitEvent(h->stream2, h->ev_a, 0));
+            CK(cudaStreamWaitEvent(h->stream3, h->ev_a, 0));
             int rc;
-            if ((rc = chain_launch(h, a, need_ld, lo, A))) return rc;
-            if ((rc = chain_launch(h, a, need_ld, lo, B))) return rc;
-            while (A.pending || B.pending) {
-                if (A.pending) {
-                    if ((rc = chain_collect(h, 1, h->stats.escalated, A))) return rc;
-                    if ((rc = chain_launch(h, a, need_ld, lo, A))) return rc;
-                }
-                if (B.pending) {
-                    if ((rc = chain_collect(h, 1, h->stats.escalated, B))) return rc;
-                    if ((rc = chain_launch(h, a, need_ld, lo, B))) return rc;
+            for (int i = 0; i < 3; i++)
+                if ((rc = chain_launch(h, a, need_ld, lo, ch[i]))) return rc;
+            while (ch[0].pending || ch[1].pending || ch[2].pending) {
+                // whichever chain's count has arrived moves on first (the host thread has nothing else to do: it polls)
+                for (int i = 0; i < 3; i++) {
+                    if (!ch[i].pending) continue;
+                    const cudaError_t qe = cudaStreamQuery(ch[i].st);
+                    if (qe == cudaErrorNotReady) continue;
+                    if (qe != cudaSuccess) CK(qe);
+                    if ((rc = chain_collect(h, 1, h->stats.escalated, ch[i]))) return rc;
+                    if ((rc = chain_launch(h, a, need_ld, lo, ch[i]))) return rc;
                 }
             }
             CK(cudaEventRecord(h->ev_a2, h->stream2));
             CK(cudaStreamWaitEvent(st, h->ev_a2, 0));
+            CK(cudaEventRecord(h->ev_a3, h->stream3));
+            CK(cudaStreamWaitEvent(st, h->ev_a3, 0));
         } else {
             int rc = run_buckets(h, a, need_ld, lo, h->stats.escalated, 0, PL, h->size_ids.as<int32_t>(), nullptr);
             if (rc) return rc;
@@ -828,13 +841,17 @@ int gpc_create(const gpc_config* cfg, gpc_handle** out) {
     auto bail = [&]() {
         if (h->ev_a) cudaEventDestroy(h->ev_a);
         if (h->ev_a2) cudaEventDestroy(h->ev_a2);
+        if (h->ev_a3) cudaEventDestroy(h->ev_a3);
         if (h->stream2) cudaStreamDestroy(h->stream2);
+        if (h->stream3) cudaStreamDestroy(h->stream3);
         if (h->pinned_counts) cudaFreeHost(h->pinned_counts);
         cudaStreamDestroy(h->stream);
         delete h;
         return GPC_ERR_CUDA;
     };
     if (cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_a3, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_a2, cudaEventDisableTiming) != cudaSuccess ||
         cudaHostAlloc(reinterpret_cast<void**>(&h->pinned_counts), 16 * sizeof(int32_t), cudaHostAllocDefault) != cudaSuccess)
@@ -857,14 +874,16 @@ void gpc_destroy(gpc_handle* h) {
                       &h->dumpC, &h->dumpQ, &h->queue0, &h->queue1, &h->hand0, &h->hand1, &h->spill, &h->qcount, &h->kstats, &h->bv_off, &h->palpha, &h->pb1, &h->pb2, &h->pidx, &h->perm_rgb, &h->fcr, &h->fcg, &h->fcb, &h->r_nbv, &h->r_flags,
                       &h->r_alpha0, &h->r_alpha1, &h->r_alpha2, &h->r_b1, &h->r_b2, &h->r_bidx, &h->kstats_rgb, &h->nonempty, &h->slot, &h->out32,
                       &h->heights, &h->quat, &h->mean, &h->rgbmean, &h->Rm, &h->center, &h->code, &h->ncand, &h->owner,
-                      &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->lat_state, &h->ev_in, &h->ev_out, &h->size_ids, &h->size_hist, &h->sel_cloud, &h->sel_idx, &h->coarse_hist, &h->fed, &h->forig, &h->cont_q, &h->cont_slots, &h->queueB, &h->handB, &h->r_dumpC, &h->r_dumpQ, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
+                      &h->st_idx, &h->tmpA, &h->tmpB, &h->tmpC, &h->lat_state, &h->ev_in, &h->ev_out, &h->size_ids, &h->size_hist, &h->sel_cloud, &h->sel_idx, &h->coarse_hist, &h->fed, &h->forig, &h->cont_q, &h->cont_slots, &h->queueB, &h->handB, &h->queueC0, &h->queueC1, &h->handC0, &h->handC1, &h->r_dumpC, &h->r_dumpQ, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->ovals,
                       &h->cpt, &h->chunk_queue, &h->chunk_hand, &h->chunk_queue1, &h->chunk_hand1, &h->ovals2, &h->sort_tmp, &h->flags64, &h->ex, &h->leaf_of, &h->leaf_start, &h->leaf_code_a, &h->spt,
                       &h->nbr, &h->nnbr, &h->center_a, &h->Rm_a, &h->ncand_a, &h->pt0, &h->pt1, &h->pt2, &h->hbuf, &h->rgb, &h->leaf_sums};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     if (h->ev_a) cudaEventDestroy(h->ev_a);
     if (h->ev_a2) cudaEventDestroy(h->ev_a2);
+    if (h->ev_a3) cudaEventDestroy(h->ev_a3);
     if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+    if (h->stream3) { cudaStreamSynchronize(h->stream3); cudaStreamDestroy(h->stream3); }
     if (h->pinned_counts) cudaFreeHost(h->pinned_counts);
     cudaStreamDestroy(h->stream);
     delete h;

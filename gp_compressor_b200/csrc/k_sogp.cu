@@ -194,11 +194,18 @@ constexpr int TILE_PAD_BYTES = 256;  // the stream buffers end with at least thi
 
 template <int DOUT>
 struct __align__(16) HalfSmem {
-    double Q[W_N * W_LD];  // homes of Q and C: authoritative while the rows are NOT in registers (full updates, deletions,
-    double C[W_N * W_LD];  // hand-off, final dump); during runs of sparse points lane r keeps row r of both in registers
+    double Q[W_N * W_LD];  // lane r reads and updates row r in place
     double kv[W_N], sv[W_N], ev[W_N];
     HalfTile<DOUT> tile[2];
     unsigned long long mbar[2];
+};
+
+// One warp = two patches.  C lives in registers; its home in shared memory is needed only by the rare paths (deletions,
+// hand-off, final dump), so the two halves share ONE and take turns there: 2.3 KB less per warp, 20 warps per SM instead of 17.
+template <int DOUT>
+struct __align__(16) HalfWarpSmem {
+    HalfSmem<DOUT> h[2];
+    double Chome[W_N * W_LD];
 };
 
 template <int DOUT>
@@ -212,6 +219,8 @@ __device__ __forceinline__ void issue_tile(HalfTile<DOUT>& t, unsigned long long
     bulk_g2s(t.orig, a.forig + pi, 80, bar);
 }
 
+constexpr int HALF_BLOCKS = 20;   // 96 registers; 20 x (shared memory of one warp + 1 KB) <= 227 KB
+
 template <int V>
 struct IntC { static constexpr int value = V; };
 
@@ -219,25 +228,28 @@ struct IntC { static constexpr int value = V; };
 // |alpha_i|^2 / (Q_ii + C_ii) (sparse_gp_field.hpp:187) and delete_bv updates alpha with alphastar * ((q*+c*)(Qs+Cs)) (:250-253).
 //
 // Structure (sparse_gp.hpp:119-203 is the loop; the arithmetic and its order are those of every other bucket):
-//  * Lane r keeps row r of C AND of Q in registers.  A sparse update (:155-163, 93 % of the points under the reference
-//    hyper-parameters) and a full update (:164-203) touch no shared memory beyond the broadcast of k, s and e_hat (16 doubles
-//    each): the rank-1 updates run over the zero-padded width, so the new row / column of a full update needs no indexing.
+//  * Lane r keeps row r of C in registers and reads / updates row r of Q in place in shared memory (Q changes only at full
+//    updates, 7 % of the points under the reference hyper-parameters; C changes at every point).  A sparse update (:155-163)
+//    and a full update (:164-203) touch no other shared memory than the broadcasts of k, s and e_hat (16 doubles each): the
+//    rank-1 updates run over the zero-padded width, so the new row / column of a full update needs no indexing.
+//    96 registers and 4.9 KB of shared memory per patch: 20 warps (40 patches) per SM.
 //    The step is compiled once per number of occupied 4-column groups (N <= 8, 12, 16) so that it has no per-group
 //    predicates, and runs converged for both halves of the warp (full-mask shuffles).
-//  * Deletions and the hand-off to the next bucket (rare under the reference hyper-parameters) spill the rows to their
-//    homes in shared memory, work there, and reload.
+//  * Deletions (rare under the reference hyper-parameters) need full matrices: the rows of C are spilled to a home in shared
+//    memory that the two halves of the warp SHARE and use in turns; the hand-off to the next bucket and the final dump are
+//    written straight from the registers.
 //  * k of the next point is computed while this point's chain runs (it depends only on the BV set).
 //  * The point stream is staged 16 points at a time by bulk-async copies (TMA unit) into a double buffer, one tile ahead.
 template <int DOUT>
-__global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
-    __shared__ __align__(16) HalfSmem<DOUT> sm2[2];
+__global__ void __launch_bounds__(32, HALF_BLOCKS) sogp_fit_half_kernel(SogpArgs a) {
+    __shared__ __align__(16) HalfWarpSmem<DOUT> smw;
     const int lane = threadIdx.x;
     const int half = lane >> 4, r = lane & 15;
     const unsigned gm = 0xffffu << (16 * half);
     const unsigned FULL = 0xffffffffu;
     const int64_t w = 2 * (int64_t)blockIdx.x + half;
-    HalfSmem<DOUT>& sm = sm2[half];
-    double* const C = sm.C;
+    HalfSmem<DOUT>& sm = smw.h[half];
+    double* const C = smw.Chome;   // valid only inside take_turns()
     double* const Q = sm.Q;
     int64_t patch = 0, o = 0, op = 0;
     int n = 0;
@@ -250,7 +262,11 @@ __global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
     }
     // a half without work stays in the loop with n = 0: every warp-level operation of the step names all 32 lanes
 #pragma unroll
-    for (int i = 0; i < W_N * W_LD / 16; i++) { C[r + 16 * i] = 0.0; Q[r + 16 * i] = 0.0; }
+    for (int i = 0; i < W_N * W_LD / 16; i++) Q[r + 16 * i] = 0.0;
+    if (half == 0) {
+#pragma unroll
+        for (int i = 0; i < W_N * W_LD / 16; i++) C[r + 16 * i] = 0.0;
+    }
     sm.kv[r] = 0.0; sm.sv[r] = 0.0; sm.ev[r] = 0.0;
     if (r == 0) { mbar_init(&sm.mbar[0], 1); mbar_init(&sm.mbar[1], 1); }
     __syncwarp();
@@ -270,10 +286,10 @@ __global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
     int N = 0, Nw = 1;
     unsigned int run = 0;          // sparse points at the current N, folded into the counters when N changes
     unsigned long long cnt = 0;    // lane r < NCNT owns event counter r
-    double creg[16], qreg[16];     // rows r of C and Q
+    double creg[16];               // row r of C
     double qd = 0.0;               // Q(r, r)
 #pragma unroll
-    for (int j = 0; j < 16; j++) { creg[j] = 0.0; qreg[j] = 0.0; }
+    for (int j = 0; j < 16; j++) creg[j] = 0.0;
     int nl = n;                    // points of this half still to be processed here: 0 after a hand-off
     bool have_next = false;
     double kl_next = 0.0;
@@ -285,7 +301,6 @@ __global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
 #pragma unroll
         for (int p = 0; p < 8; p++) {
             *reinterpret_cast<double2*>(Crow + 2 * p) = make_double2(creg[2 * p], creg[2 * p + 1]);
-            *reinterpret_cast<double2*>(Qrow + 2 * p) = make_double2(qreg[2 * p], qreg[2 * p + 1]);
         }
     };
     auto flush_run = [&]() {
@@ -321,8 +336,8 @@ __global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
 #pragma unroll
                     for (int c = 0; c < DOUT; c++) alpha[c] = __ddiv_rn(tl.y[c][sh1], d);
                     creg[0] = __ddiv_rn(-1.0, d);
-                    qreg[0] = __ddiv_rn(1.0, kstar);
-                    qd = qreg[0];
+                    qd = __ddiv_rn(1.0, kstar);
+                    Qrow[0] = qd;
                     b1 = tl.x1[sh1]; b2 = tl.x2[sh1]; bidx = tl.orig[sh3];
                     cnt++;
                 }
@@ -350,8 +365,9 @@ __global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
                     const double2 k01 = *reinterpret_cast<const double2*>(sm.kv + 4 * g), k23 = *reinterpret_cast<const double2*>(sm.kv + 4 * g + 2);
                     a0 = fma(creg[4 * g], k01.x, a0); a1 = fma(creg[4 * g + 1], k01.y, a1);
                     a2 = fma(creg[4 * g + 2], k23.x, a2); a3 = fma(creg[4 * g + 3], k23.y, a3);
-                    e0 = fma(qreg[4 * g], k01.x, e0); e1 = fma(qreg[4 * g + 1], k01.y, e1);
-                    e2 = fma(qreg[4 * g + 2], k23.x, e2); e3 = fma(qreg[4 * g + 3], k23.y, e3);
+                    const double2 q01 = *reinterpret_cast<const double2*>(Qrow + 4 * g), q23 = *reinterpret_cast<const double2*>(Qrow + 4 * g + 2);
+                    e0 = fma(q01.x, k01.x, e0); e1 = fma(q01.y, k01.y, e1);
+                    e2 = fma(q23.x, k23.x, e2); e3 = fma(q23.y, k23.y, e3);
                 }
                 rv = __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));   // (C k)_r  (:122); rows >= N are zero
                 el = __dadd_rn(__dadd_rn(e0, e1), __dadd_rn(e2, e3));   // (Q k)_r = e_hat_r  (:140)
@@ -430,8 +446,6 @@ __global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
         if (fu) {
             flush_run();
             if (N + 1 > ldmax) {  // does not fit this bucket: hand the state to the next one
-                spill_rows();
-                __syncwarp(gm);
                 int pos = 0;
                 if (r == 0) pos = atomicAdd(a.queue_count, 1);
                 pos = __shfl_sync(gm, pos, 0, 16);
@@ -448,10 +462,10 @@ __global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
                 for (int c = 0; c < DOUT; c++) v[c * W_N + r] = alpha[c];
                 v[DOUT * W_N + r] = b1; v[(DOUT + 1) * W_N + r] = b2;
                 reinterpret_cast<int*>(v + (DOUT + 2) * W_N + 2 * W_N * W_N)[r] = bidx;
-                for (int e = r; e < W_N * W_N; e += 16) {
-                    const int j = e / W_N, i = e - j * W_N;
-                    v[(DOUT + 2) * W_N + e] = C[i * W_LD + j];
-                    v[(DOUT + 2) * W_N + W_N * W_N + e] = Q[i * W_LD + j];
+#pragma unroll
+                for (int j = 0; j < W_N; j++) {   // column-major slots: lane r owns row r
+                    v[(DOUT + 2) * W_N + j * W_N + r] = creg[j];
+                    v[(DOUT + 2) * W_N + W_N * W_N + j * W_N + r] = Qrow[j];
                 }
                 nl = 0;
                 fur = false;
@@ -476,6 +490,7 @@ __global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
             }
         }
         __syncwarp();
+        bool need_del = false;
         if (fur) {
             const double ig = __ddiv_rn(1.0, gamma);
             const int N1 = N + 1;
@@ -492,10 +507,10 @@ __global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
                             creg[4 * g + 1] = fma(rr, __dmul_rn(si, s01.y), creg[4 * g + 1]);
                             creg[4 * g + 2] = fma(rr, __dmul_rn(si, s23.x), creg[4 * g + 2]);
                             creg[4 * g + 3] = fma(rr, __dmul_rn(si, s23.y), creg[4 * g + 3]);
-                            qreg[4 * g] = fma(ig, __dmul_rn(ei, e01.x), qreg[4 * g]);
-                            qreg[4 * g + 1] = fma(ig, __dmul_rn(ei, e01.y), qreg[4 * g + 1]);
-                            qreg[4 * g + 2] = fma(ig, __dmul_rn(ei, e23.x), qreg[4 * g + 2]);
-                            qreg[4 * g + 3] = fma(ig, __dmul_rn(ei, e23.y), qreg[4 * g + 3]);
+                            double2 q01 = *reinterpret_cast<double2*>(Qrow + 4 * g), q23 = *reinterpret_cast<double2*>(Qrow + 4 * g + 2);
+                            q01.x = fma(ig, __dmul_rn(ei, e01.x), q01.x); q01.y = fma(ig, __dmul_rn(ei, e01.y), q01.y);
+                            q23.x = fma(ig, __dmul_rn(ei, e23.x), q23.x); q23.y = fma(ig, __dmul_rn(ei, e23.y), q23.y);
+                            *reinterpret_cast<double2*>(Qrow + 4 * g) = q01; *reinterpret_cast<double2*>(Qrow + 4 * g + 2) = q23;
                         }
                     }
                 } else {
@@ -503,7 +518,7 @@ __global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
                     for (int j = 0; j < 16; j++) {
                         if (j < N1) {
                             creg[j] = fma(rr, __dmul_rn(si, sm.sv[j]), creg[j]);
-                            qreg[j] = fma(ig, __dmul_rn(ei, sm.ev[j]), qreg[j]);
+                            Qrow[j] = fma(ig, __dmul_rn(ei, sm.ev[j]), Qrow[j]);
                         }
                     }
                 }
@@ -512,7 +527,7 @@ __global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
             N = N1;
             have_next = false;  // the BV set changed
             // capacity deletions (:206-223) then geometric deletions (:226-242): decided here, done in shared memory
-            bool need_del = N > cap;
+            need_del = N > cap;
             if (!need_del && N > 1) {
                 // exact shortcut: the geometric scan deletes iff score_0 is not NaN and some score 1 / Q_ii is < 1e-9f
                 const double sc = (r < N) ? __ddiv_rn(1.0, qd) : 0.0;
@@ -520,7 +535,11 @@ __global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
                 const bool nan0 = __any_sync(gm, r == 0 && sc != sc);
                 need_del = hit && !nan0;
             }
-            if (need_del) {
+        }
+        // deletions work on full matrices in shared memory; the two halves share one home for C and take turns
+        if (!__any_sync(FULL, need_del)) { Nw = max(N, __shfl_xor_sync(FULL, N, 16)); continue; }
+        for (int hh = 0; hh < 2; hh++) {
+            if (half == hh && need_del) {
                 spill_rows();
                 __syncwarp(gm);
                 double minscore = 0.0;
@@ -611,25 +630,22 @@ __global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
                 // rows back into registers
 #pragma unroll
                 for (int p = 0; p < 8; p++) {
-                    const double2 c2 = *reinterpret_cast<const double2*>(Crow + 2 * p), q2 = *reinterpret_cast<const double2*>(Qrow + 2 * p);
+                    const double2 c2 = *reinterpret_cast<const double2*>(Crow + 2 * p);
                     creg[2 * p] = c2.x; creg[2 * p + 1] = c2.y;
-                    qreg[2 * p] = q2.x; qreg[2 * p + 1] = q2.y;
                 }
                 qd = Q[r * W_LD + r];
             }
+            __syncwarp();
         }
-        __syncwarp();
         Nw = max(N, __shfl_xor_sync(FULL, N, 16));
     }
     __syncwarp();
     if (issued > waited) mbar_wait(&sm.mbar[waited & 1], (uint32_t)((waited >> 1) & 1));  // never leave with a copy in flight
     if (w >= a.n_work || n == 0 || nl == 0) return;
-    spill_rows();
     flush_run();
-    __syncwarp(gm);
     if (r == 0) {
         a.nbv[op] = N;
-        const double c00 = C[0];
+        const double c00 = creg[0];
         a.flags[op] = (c00 != c00) ? 1 : 0;
         atomicAdd(a.stats + 0, (unsigned long long)n);
     }
@@ -644,10 +660,14 @@ __global__ void __launch_bounds__(32, 16) sogp_fit_half_kernel(SogpArgs a) {
     }
     if (a.dumpC) {
         const int64_t od = op * (int64_t)cap * cap;
-        for (int e = r; e < N * N; e += 16) {
-            const int i = e / N, j = e - i * N;
-            a.dumpC[od + e] = C[i * W_LD + j];
-            a.dumpQ[od + e] = Q[i * W_LD + j];
+        if (r < N) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                if (j < N) {
+                    a.dumpC[od + r * N + j] = creg[j];
+                    a.dumpQ[od + r * N + j] = Qrow[j];
+                }
+            }
         }
     }
 }
@@ -2081,6 +2101,11 @@ int sogp_next_bucket(int bucket, int dout) {
 cudaError_t launch_sogp_fit(int bucket, const SogpArgs& a, cudaStream_t st) {
     if (a.n_work <= 0) return cudaSuccess;
     g_launches++;
+    if (bucket == 0) {  // 20 one-warp blocks per SM need the largest shared-memory carve-out (idempotent, cheap)
+        cudaError_t e = a.dout == 3 ? cudaFuncSetAttribute(sogp_fit_half_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
+                                    : cudaFuncSetAttribute(sogp_fit_half_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+    }
     if (a.dout == 3) {
         switch (bucket) {
             case 0:

@@ -340,7 +340,6 @@ int launch_radix_sort(uint64_t* keys, uint32_t* vals, uint64_t* keys2, uint32_t*
     const bool lookback = n < ((int64_t)1 << 30);   // status words carry 30-bit counts
     // digit width: up to 9 bits, fewer for huge inputs so that the (digit, tile) count table scans in one top-level block
     int maxbits = RS_MAXBITS;
-    if (const char* e = getenv("GPC_SORT_BITS")) maxbits = std::max(4, std::min(RS_MAXBITS, atoi(e)));
     while (!lookback && maxbits > 4 && (((int64_t)1 << maxbits) * tiles + SC_TILE - 1) / SC_TILE > SC_TILE) maxbits--;
     const int passes = (nbits + maxbits - 1) / maxbits;
     const bool narrow = nbits <= 32 && passes > 1;   // 32-bit keys between the first and the last pass
