@@ -2,6 +2,7 @@
 // Host-side orchestration only: buffer management, stage sequencing, sharding, timing.
 // All arithmetic of the path runs in the kernels of k_*.cu; there is no CPU fallback.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -185,6 +186,14 @@ int run_buckets(gpc_handle* h, SogpArgs& a, int need_ld, int64_t lo, uint64_t* e
 // One chain of buckets advanced ONE LEVEL per call, so that several chains (on different streams) can be walked breadth
 // first: a patch is a strictly sequential recursion, the largest patches climb through several buckets, and the host must not
 // sit in one chain's synchronisation while another chain's next kernel could already be launched.
+static inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#elif defined(__aarch64__)
+    asm volatile("yield");
+#endif
+}
+
 struct BucketChain {
     cudaStream_t st = nullptr;
     int b = 0;                     // next bucket to launch
@@ -377,7 +386,9 @@ int run_fit(gpc_handle* h, StageTimer& tm, bool cont = false) {
             for (int i = 0; i < 3; i++)
                 if ((rc = chain_launch(h, a, need_ld, lo, ch[i]))) return rc;
             while (ch[0].pending || ch[1].pending || ch[2].pending) {
-                // whichever chain's count has arrived moves on first (the host thread has nothing else to do: it polls)
+                // whichever chain's count has arrived moves on first.  The host thread has nothing else to do, so it polls --
+                // but not back to back: every query takes the driver's lock, which another handle's thread needs to launch.
+                bool moved = false;
                 for (int i = 0; i < 3; i++) {
                     if (!ch[i].pending) continue;
                     const cudaError_t qe = cudaStreamQuery(ch[i].st);
@@ -385,6 +396,11 @@ int run_fit(gpc_handle* h, StageTimer& tm, bool cont = false) {
                     if (qe != cudaSuccess) CK(qe);
                     if ((rc = chain_collect(h, 1, h->stats.escalated, ch[i]))) return rc;
                     if ((rc = chain_launch(h, a, need_ld, lo, ch[i]))) return rc;
+                    moved = true;
+                }
+                if (!moved) {
+                    const auto until = std::chrono::steady_clock::now() + std::chrono::microseconds(4);
+                    while (std::chrono::steady_clock::now() < until) cpu_relax();
                 }
             }
             CK(cudaEventRecord(h->ev_a2, h->stream2));

@@ -26,6 +26,7 @@
 // and the arithmetic is the same in every bucket.
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 #include <type_traits>
 
 #include "gpc_device.cuh"
@@ -2101,10 +2102,18 @@ int sogp_next_bucket(int bucket, int dout) {
 cudaError_t launch_sogp_fit(int bucket, const SogpArgs& a, cudaStream_t st) {
     if (a.n_work <= 0) return cudaSuccess;
     g_launches++;
-    if (bucket == 0) {  // 20 one-warp blocks per SM need the largest shared-memory carve-out (idempotent, cheap)
-        cudaError_t e = a.dout == 3 ? cudaFuncSetAttribute(sogp_fit_half_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
-                                    : cudaFuncSetAttribute(sogp_fit_half_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
+    if (bucket == 0) {  // 20 one-warp blocks per SM need the largest shared-memory carve-out: set once per process and device
+        static std::once_flag once[64];
+        static cudaError_t once_err[64];
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev = dev < 0 || dev >= 64 ? 0 : dev;
+        std::call_once(once[dev], [dev]() {
+            cudaError_t e1 = cudaFuncSetAttribute(sogp_fit_half_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaError_t e3 = cudaFuncSetAttribute(sogp_fit_half_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            once_err[dev] = e1 != cudaSuccess ? e1 : e3;
+        });
+        if (once_err[dev] != cudaSuccess) return once_err[dev];
     }
     if (a.dout == 3) {
         switch (bucket) {
