@@ -3,10 +3,28 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include <string>
 #include <vector>
 
 #include "../../include/gpc.h"
+
+// cudaFuncSetAttribute is not a cheap call: it serialises against the work other host threads have in flight on the device
+// (measured: with two handles in flight a per-launch call cost 30 % of the pipelined throughput).  This sets an integer
+// attribute of a kernel once per device (again only if a larger value is asked for) and is safe to call from several threads.
+#define GPC_FUNC_ATTR_ONCE(fn, attr, value)                                                                  \
+    ([&]() -> cudaError_t {                                                                                  \
+        static std::atomic<int> have__[64];                                                                  \
+        int dev__ = 0;                                                                                       \
+        cudaGetDevice(&dev__);                                                                               \
+        dev__ = (dev__ < 0 || dev__ >= 64) ? 0 : dev__;                                                      \
+        const int want__ = (int)(value);                                                                     \
+        if (have__[dev__].load(std::memory_order_acquire) >= want__) return cudaSuccess;                     \
+        const cudaError_t e__ = cudaFuncSetAttribute(fn, attr, want__);                                      \
+        if (e__ == cudaSuccess) have__[dev__].store(want__, std::memory_order_release);                      \
+        return e__;                                                                                          \
+    }())
 
 namespace gpc {
 

@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(EV_NT) evaluate_kernel(EvalArgs a) {
 
 template <int RPT, bool CSMEM, int DOUT>
 cudaError_t launch_variant(const EvalArgs& a, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(evaluate_kernel<RPT, CSMEM, DOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = GPC_FUNC_ATTR_ONCE((evaluate_kernel<RPT, CSMEM, DOUT>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     evaluate_kernel<RPT, CSMEM, DOUT><<<(unsigned)a.n_patches, EV_NT, smem, s>>>(a);
     return cudaGetLastError();

@@ -295,11 +295,11 @@ static cudaError_t launch_grid_variant(const PredictArgs& a, size_t smem, cudaSt
     const int64_t grid = (a.n_groups + per_cta - 1) / per_cta;
     if (grid > 0x7fffffff) return cudaErrorInvalidConfiguration;
     if (a.separable) {
-        cudaError_t e = cudaFuncSetAttribute(predict_grid_kernel<R, G, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = GPC_FUNC_ATTR_ONCE((predict_grid_kernel<R, G, MINB, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         predict_grid_kernel<R, G, MINB, false><<<(unsigned)grid, PRED_T, smem, s>>>(a);
     } else {
-        cudaError_t e = cudaFuncSetAttribute(predict_grid_kernel<R, G, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = GPC_FUNC_ATTR_ONCE((predict_grid_kernel<R, G, MINB, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         predict_grid_kernel<R, G, MINB, true><<<(unsigned)grid, PRED_T, smem, s>>>(a);
     }

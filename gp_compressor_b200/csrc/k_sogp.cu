@@ -26,7 +26,6 @@
 // and the arithmetic is the same in every bucket.
 #include <algorithm>
 #include <cstdlib>
-#include <mutex>
 #include <type_traits>
 
 #include "gpc_device.cuh"
@@ -1993,7 +1992,7 @@ template <int LD, int NT, int LD_IN, int LD_OUT, bool SPILL = false>
 cudaError_t launch_fused_bucket(const SogpArgs& a, cudaStream_t st) {
     constexpr size_t smem = fused_smem_bytes<LD, SPILL>();
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(sogp_fit_fused_kernel<LD, NT, LD_IN, LD_OUT, SPILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = GPC_FUNC_ATTR_ONCE((sogp_fit_fused_kernel<LD, NT, LD_IN, LD_OUT, SPILL>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
     }
     sogp_fit_fused_kernel<LD, NT, LD_IN, LD_OUT, SPILL><<<a.n_work, NT, smem, st>>>(a);
@@ -2006,8 +2005,8 @@ constexpr size_t cta_smem_bytes() { return (size_t)Smem<LD, DOUT>::kDoubles * si
 template <int LD, int RB, int NT, int LD_IN, bool SPILL, int DOUT>
 cudaError_t launch_cta_bucket(const SogpArgs& a, cudaStream_t st) {
     constexpr size_t smem = SPILL ? 0 : cta_smem_bytes<LD, DOUT>();
-    if (smem > 48 * 1024) {  // per device and cheap: set on every launch (handles may live on different GPUs)
-        cudaError_t e = cudaFuncSetAttribute(sogp_fit_kernel<LD, RB, NT, LD_IN, SPILL, DOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024) {
+        cudaError_t e = GPC_FUNC_ATTR_ONCE((sogp_fit_kernel<LD, RB, NT, LD_IN, SPILL, DOUT>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
     }
     sogp_fit_kernel<LD, RB, NT, LD_IN, SPILL, DOUT><<<a.n_work, NT, smem, st>>>(a);
@@ -2102,18 +2101,10 @@ int sogp_next_bucket(int bucket, int dout) {
 cudaError_t launch_sogp_fit(int bucket, const SogpArgs& a, cudaStream_t st) {
     if (a.n_work <= 0) return cudaSuccess;
     g_launches++;
-    if (bucket == 0) {  // 20 one-warp blocks per SM need the largest shared-memory carve-out: set once per process and device
-        static std::once_flag once[64];
-        static cudaError_t once_err[64];
-        int dev = 0;
-        cudaGetDevice(&dev);
-        dev = dev < 0 || dev >= 64 ? 0 : dev;
-        std::call_once(once[dev], [dev]() {
-            cudaError_t e1 = cudaFuncSetAttribute(sogp_fit_half_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            cudaError_t e3 = cudaFuncSetAttribute(sogp_fit_half_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            once_err[dev] = e1 != cudaSuccess ? e1 : e3;
-        });
-        if (once_err[dev] != cudaSuccess) return once_err[dev];
+    if (bucket == 0) {  // 20 one-warp blocks per SM need the largest shared-memory carve-out
+        cudaError_t e = a.dout == 3 ? GPC_FUNC_ATTR_ONCE((sogp_fit_half_kernel<3>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
+                                    : GPC_FUNC_ATTR_ONCE((sogp_fit_half_kernel<1>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
     }
     if (a.dout == 3) {
         switch (bucket) {

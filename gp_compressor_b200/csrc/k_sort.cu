@@ -302,11 +302,9 @@ __global__ void iota_u32_kernel(uint32_t* v, int64_t n) {
 template <class KIN, class KOUT, bool LOOKBACK>
 cudaError_t launch_scatter(const void* ki, const uint32_t* vi, int64_t n, int shift, int bits, int64_t tiles, const uint32_t* offs, void* ko,
                            uint32_t* vo, uint32_t* status, unsigned int* counter, cudaStream_t s) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(radix_scatter_kernel<KIN, KOUT, LOOKBACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<KOUT>));
+    {
+        cudaError_t e = GPC_FUNC_ATTR_ONCE((radix_scatter_kernel<KIN, KOUT, LOOKBACK>), cudaFuncAttributeMaxDynamicSharedMemorySize, sizeof(ScatterSmem<KOUT>));
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     radix_scatter_kernel<KIN, KOUT, LOOKBACK><<<(unsigned)tiles, RS_T, sizeof(ScatterSmem<KOUT>), s>>>(reinterpret_cast<const KIN*>(ki), vi, n, shift, bits, tiles,
                                                                                                  offs, reinterpret_cast<KOUT*>(ko), vo, status, counter);
