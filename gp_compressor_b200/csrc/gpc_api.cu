@@ -47,6 +47,10 @@ struct gpc_handle {
     DevBuf tmpA, tmpB, tmpC, lat_state, ev_in, ev_out, size_ids, size_hist, sel_cloud, sel_idx, coarse_hist, fed, forig, cont_q, cont_slots, queueB, handB, queueC0, queueC1, handC0, handC1, r_dumpC, r_dumpQ;
     cudaStream_t stream2 = nullptr;   // side streams: the bucket chains of the larger patches run beside bucket 0 of the rest
     cudaStream_t stream3 = nullptr;
+    // two or three bucket chains: measured per handle on its first calls (run_fit, chain_tune_after)
+    int chain_pick = 0, chain_trials = 0, chain_last = 0;
+    int64_t chain_PL = 0;
+    float chain_ms[2] = {0.f, 0.f};
     cudaEvent_t ev_a = nullptr, ev_a2 = nullptr, ev_a3 = nullptr;
     int32_t* pinned_counts = nullptr;  // 16 pinned host words for asynchronous read-backs of device counters
     // sharded binning (gpc_compress_shard_begin / _finish): this shard's patches are local indices [own_lo, own_hi) of a
@@ -91,6 +95,18 @@ struct SmallScratch {
 };
 static_assert(sizeof(SmallScratch) == 256, "scratch layout");
 
+// Two or three bucket chains for the fit (run_fit)?  Three win on a GPU used by one process (C2: 1.85 against 1.91 ms); in a
+// process that also holds an NCCL communicator (one rank per GPU) three were measured SLOWER (2.13 against 1.92 ms, at 2 and at 8
+// ranks alike; not explained: the chains' own timeline is unchanged).  So the handle measures: the call after the first uses two
+// chains, the next three, and the faster stays until the patch count changes by more than 2x.  The results do not depend on it.
+void chain_tune_after(gpc_handle* h) {
+    if (h->chain_last == 0 || h->chain_pick != 0) { h->chain_last = 0; return; }
+    if (h->chain_trials >= 1) h->chain_ms[h->chain_last == 3] = h->stats.ms_fit;
+    h->chain_trials++;
+    if (h->chain_trials == 3) h->chain_pick = h->chain_ms[1] <= h->chain_ms[0] ? 3 : 2;
+    h->chain_last = 0;
+}
+
 struct StageTimer {
     gpc_handle* h;
     size_t used = 0;
@@ -112,6 +128,7 @@ struct StageTimer {
             cudaEventElapsedTime(&ms, h->ev[s.second.first], h->ev[s.second.second]);
             *s.first += ms;
         }
+        chain_tune_after(h);
     }
 };
 
@@ -365,8 +382,11 @@ int run_fit(gpc_handle* h, StageTimer& tm, bool cont = false) {
             //   B1 = the next ones up to 3/5 of the list (about three quarters of the points): their continuations run beside
             //        bucket 0 of B2 instead of after it;
             //   B2 = the small patches on the main stream: what it hands off has few points left, so the tail is short.
+            if (h->chain_PL == 0 || PL > 2 * h->chain_PL || 2 * PL < h->chain_PL) { h->chain_pick = 0; h->chain_trials = 0; h->chain_PL = PL; }
+            const int chains = h->chain_pick ? h->chain_pick : (h->chain_trials == 1 ? 2 : 3);   // first call (cold) and third: three, second: two
+            h->chain_last = chains;
             const int64_t nA = std::min<int64_t>(PL, std::max<int64_t>(2368, (PL / 32))) & ~(int64_t)1;
-            const int64_t nB1 = std::max<int64_t>(0, (PL * 3 / 5 - nA)) & ~(int64_t)1;   // cut at 0.5 .. 0.7 of the list: within noise on C2
+            const int64_t nB1 = chains == 3 ? std::max<int64_t>(0, (PL * 3 / 5 - nA)) & ~(int64_t)1 : 0;   // cut at 0.5 .. 0.7 of the list: within noise on C2   // cut at 0.5 .. 0.7 of the list: within noise on C2
             const int64_t nB2 = PL - nA - nB1;
             CK(h->qcount.reserve(64 * sizeof(int32_t)));
             CK(cudaMemsetAsync(h->qcount.p, 0, 64 * sizeof(int32_t), st));
