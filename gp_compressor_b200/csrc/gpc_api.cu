@@ -48,9 +48,9 @@ struct gpc_handle {
     cudaStream_t stream2 = nullptr;   // side streams: the bucket chains of the larger patches run beside bucket 0 of the rest
     cudaStream_t stream3 = nullptr;
     // two or three bucket chains: measured per handle on its first calls (run_fit, chain_tune_after)
-    int chain_pick = 0, chain_trials = 0, chain_last = 0;
+    int chain_pick = 3, chain_calls = 0, chain_last = 0;   // mode in use, calls at this size, mode of the call in flight
     int64_t chain_PL = 0;
-    float chain_ms[2] = {0.f, 0.f};
+    float chain_ms[2] = {0.f, 0.f};                        // last fit-stage time with two / three chains
     cudaEvent_t ev_a = nullptr, ev_a2 = nullptr, ev_a3 = nullptr;
     int32_t* pinned_counts = nullptr;  // 16 pinned host words for asynchronous read-backs of device counters
     // sharded binning (gpc_compress_shard_begin / _finish): this shard's patches are local indices [own_lo, own_hi) of a
@@ -95,16 +95,21 @@ struct SmallScratch {
 };
 static_assert(sizeof(SmallScratch) == 256, "scratch layout");
 
-// Two or three bucket chains for the fit (run_fit)?  Three win on a GPU used by one process (C2: 1.85 against 1.91 ms); in a
-// process that also holds an NCCL communicator (one rank per GPU) three were measured SLOWER (2.13 against 1.92 ms, at 2 and at 8
-// ranks alike; not explained: the chains' own timeline is unchanged).  So the handle measures: the call after the first uses two
-// chains, the next three, and the faster stays until the patch count changes by more than 2x.  The results do not depend on it.
+// Two or three bucket chains for the fit (run_fit)?  Three win on a GPU whose process runs alone (C2: 1.85 against 1.91 ms); with
+// one process per GPU on several GPUs at once (the bench under torchrun, 2 and 8 ranks alike) three were measured SLOWER while the
+// other ranks are running (2.13 against 1.92 ms; not explained: the chains' own event timeline is unchanged).  So the handle keeps
+// measuring: it remembers the last fit time of either mode, uses the faster, and tries the other one every 8th call.  Results do
+// not depend on the mode.
 void chain_tune_after(gpc_handle* h) {
-    if (h->chain_last == 0 || h->chain_pick != 0) { h->chain_last = 0; return; }
-    if (h->chain_trials >= 1) h->chain_ms[h->chain_last == 3] = h->stats.ms_fit;
-    h->chain_trials++;
-    if (h->chain_trials == 3) h->chain_pick = h->chain_ms[1] <= h->chain_ms[0] ? 3 : 2;
+    const int mode = h->chain_last;
     h->chain_last = 0;
+    if (mode == 0) return;
+    if (h->chain_calls > 1) h->chain_ms[mode == 3] = h->stats.ms_fit;   // the first call of a size is cold (allocations): not used
+    const float t2 = h->chain_ms[0], t3 = h->chain_ms[1];
+    if (t2 > 0.f && t3 > 0.f) {
+        if (h->chain_pick == 3 && t2 < 0.98f * t3) h->chain_pick = 2;
+        else if (h->chain_pick == 2 && t3 < 0.98f * t2) h->chain_pick = 3;
+    }
 }
 
 struct StageTimer {
@@ -382,8 +387,12 @@ int run_fit(gpc_handle* h, StageTimer& tm, bool cont = false) {
             //   B1 = the next ones up to 3/5 of the list (about three quarters of the points): their continuations run beside
             //        bucket 0 of B2 instead of after it;
             //   B2 = the small patches on the main stream: what it hands off has few points left, so the tail is short.
-            if (h->chain_PL == 0 || PL > 2 * h->chain_PL || 2 * PL < h->chain_PL) { h->chain_pick = 0; h->chain_trials = 0; h->chain_PL = PL; }
-            const int chains = h->chain_pick ? h->chain_pick : (h->chain_trials == 1 ? 2 : 3);   // first call (cold) and third: three, second: two
+            if (h->chain_PL == 0 || PL > 2 * h->chain_PL || 2 * PL < h->chain_PL) {   // another workload: measure again
+                h->chain_pick = 3; h->chain_calls = 0; h->chain_PL = PL; h->chain_ms[0] = h->chain_ms[1] = 0.f;
+            }
+            h->chain_calls++;
+            const bool explore = (h->chain_calls & 7) == 2;   // calls 2, 10, 18, ...: the mode not in use
+            const int chains = explore ? (h->chain_pick == 3 ? 2 : 3) : h->chain_pick;
             h->chain_last = chains;
             const int64_t nA = std::min<int64_t>(PL, std::max<int64_t>(2368, (PL / 32))) & ~(int64_t)1;
             const int64_t nB1 = chains == 3 ? std::max<int64_t>(0, (PL * 3 / 5 - nA)) & ~(int64_t)1 : 0;   // cut at 0.5 .. 0.7 of the list: within noise on C2   // cut at 0.5 .. 0.7 of the list: within noise on C2
