@@ -97,7 +97,8 @@ static_assert(sizeof(SmallScratch) == 256, "scratch layout");
 
 // Two or three bucket chains for the fit (run_fit)?  Three win on a GPU whose process runs alone (C2: 1.85 against 1.91 ms); with
 // one process per GPU on several GPUs at once (the bench under torchrun, 2 and 8 ranks alike) three were measured SLOWER while the
-// other ranks are running (2.13 against 1.92 ms; not explained: the chains' own event timeline is unchanged).  So the handle keeps
+// other ranks are running (2.13 against 1.92 ms; not explained: the chains' own event timeline is unchanged, and neither two
+// independent processes without NCCL nor a communicator of world size 1 show it).  So the handle keeps
 // measuring: it remembers the last fit time of either mode, uses the faster, and tries the other one every 8th call.  Results do
 // not depend on the mode.
 void chain_tune_after(gpc_handle* h) {
