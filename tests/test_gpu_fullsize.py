@@ -97,6 +97,24 @@ def test_checksum_is_independent_of_sharding(run):
     assert np.array_equal(np.concatenate(apieces), alpha)
 
 
+def test_results_do_not_depend_on_the_bucket_chain_mode(run):
+    """The fit stage cuts the size-ordered patch list into two or three bucket chains and switches between the two modes on
+    measured time (call 1 of a handle: three chains, call 2: two, call 3: three; gpc_api.cu chain_tune_after).  Scheduling only:
+    parameters, BV index sets and event counters of the three calls are identical."""
+    G, cloud, _ = run
+    h = G.Handle(res=F32(0.1), sz=10, capacity=30)
+    h.upload_cloud(cloud)
+    got = []
+    for _ in range(3):
+        h.set_rand_offset(0)
+        h.compress_resident()
+        p, st = h.params(), h.stats()
+        got.append((p["nbv"].copy(), p["bv_idx"].copy(), p["alpha"].copy(), [st[k] for k in ("n_add", "n_sparse", "n_full", "n_del_cap", "n_del_geo")], list(st["escalated"])))
+    for g in got[1:]:
+        assert np.array_equal(g[0], got[0][0]) and np.array_equal(g[1], got[0][1]) and np.array_equal(g[2], got[0][2])
+        assert g[3] == got[0][3] and g[4] == got[0][4]
+
+
 # ---- full-size BIT-COMPARES against the oracle (every array of the path, not just properties) ----------------------
 def _oracle_threads():
     import os
