@@ -39,7 +39,9 @@ extern "C" {
 typedef struct gpc_handle gpc_handle;
 
 /* Constructor arguments of the reference classes on this path, plus the knobs the
- * reference hard-codes.  gpc_config_default() fills the reference's values. */
+ * reference hard-codes.  gpc_config_default() fills the reference's values, with ONE deviation: rgb = 0 (the reference always
+ * fits the colour field GP next to the height GP, gp_compressor.cpp:163, and decodes C* + RGB mean, :367); set rgb = 1 for the
+ * reference's behaviour -- with rgb = 0 the decoder paints every grid point with its patch's mean colour. */
 typedef struct gpc_config {
     double res;         /* gp_compressor(cloud, res, sz): voxel size, gp_compressor.h:65 (default 0.1f) */
     int32_t sz;         /* gp_compressor(cloud, res, sz): grid side at decode, gp_compressor.h:65 (10)  */
