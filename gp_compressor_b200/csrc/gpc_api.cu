@@ -95,12 +95,11 @@ struct SmallScratch {
 };
 static_assert(sizeof(SmallScratch) == 256, "scratch layout");
 
-// Two or three bucket chains for the fit (run_fit)?  Three win on a GPU whose process runs alone (C2: 1.85 against 1.91 ms); with
-// one process per GPU on several GPUs at once (the bench under torchrun, 2 and 8 ranks alike) three were measured SLOWER while the
-// other ranks are running (2.13 against 1.92 ms; not explained: the chains' own event timeline is unchanged, and neither two
-// independent processes without NCCL nor a communicator of world size 1 show it).  So the handle keeps
-// measuring: it remembers the last fit time of either mode, uses the faster, and tries the other one every 8th call.  Results do
-// not depend on the mode.
+// Two or three bucket chains for the fit (run_fit)?  Three win on a GPU whose process runs alone (C2: 1.85 against 1.91 ms).  In a
+// process that holds an NCCL communicator set up with NVLink SHARP (NVLS, NCCL's default on NVSwitch nodes) three were measured
+// SLOWER (2.13 against 1.92 ms at 2 and 8 ranks; NCCL_NVLS_ENABLE=0 removes it; the chains' own event timeline is unchanged).  The
+// library cannot know what else its process has set up, so the handle keeps measuring: it remembers the last fit time of either
+// mode, uses the faster, and tries the other one every 8th call.  Results do not depend on the mode.
 void chain_tune_after(gpc_handle* h) {
     const int mode = h->chain_last;
     h->chain_last = 0;

@@ -63,6 +63,7 @@ def c4(total_patches=1_000_000, chunk=125_000, sz=64):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     mine = total_patches // world
     for nbv in (30, 100):
