@@ -10,9 +10,9 @@
 // "row i" is read as the contiguous column i: conflict-free), plus work vectors.
 //
 // Bucket 0 (N + 1 <= 16): TWO PATCHES per warp, one per half-warp.  Lane r of a half-warp owns index r of
-// alpha / BV / k in registers and row r of C and of Q in shared memory; the three dot products are one product
+// alpha / BV / k and row r of C in registers, and row r of Q in shared memory; the three dot products are one product
 // per lane and a 4-step butterfly; patches are visited by decreasing size so that the two halves of a warp have
-// (almost) equal streams.  No block barrier, only __syncwarp on the half-warp's own mask.
+// (almost) equal streams.  No block barrier, only __syncwarp; the point stream arrives by bulk-async (TMA) tile copies.
 // Bucket 1 (N + 1 <= 32): two warps per patch, warp 0 owns C and warp 1 owns Q (sogp_fit_pair_kernel).
 // Buckets 2-4 (N + 1 <= 64 / 104 / 202), height GP: sogp_fit_fused_kernel -- the update of a point and the two matvecs
 // of the next one share ONE pass over C and Q (in shared memory; in a global-memory slice for bucket 4), and a capacity
