@@ -66,8 +66,10 @@ def _workload(name, points, seed_shift=0):
 
 def config_dict(desc, n):
     """The `config` object of the JSON line: identical in both arms (--impl ours / reference) for the same workload."""
-    return {"workload": desc, "per_gpu_points": int(n),
-            "l2": "inputs larger than L2 (%.0f MB cloud + sort buffers per step)" % (n * 32 / 1e6),
+    mb = n * 32 / 1e6
+    l2 = ("inputs larger than L2 (%.0f MB cloud + sort buffers per step)" % mb if mb > 126.0 else
+          "inputs SMALLER than the 126 MB L2 (%.0f MB cloud) and no flush between steps: a secondary workload, L2-warm numbers" % mb)
+    return {"workload": desc, "per_gpu_points": int(n), "l2": l2,
             "parallelism": "one cloud per GPU, patches independent, no collective"}
 
 
